@@ -1,0 +1,225 @@
+/* nunerf.h -- C-ABI of libnunerf_b200.so, the sm_100a engine behind the NU-NeRF renderer boundary.
+ *
+ * The reference (jjjkkyz/NU-NeRF) has no FFI of its own: its hot path is PyTorch eager code plus two
+ * third-party native tracers.  Each entry point below names the reference code it replaces
+ * (paths relative to the reference root; "ZT" = network/renderer_zerothick.py).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all buffers;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: 0 = ok, negative = error; nunerf_last_error() gives the message (thread local);
+ *   - row-major, fp32 unless stated.  "bf16 planes": a [rows, ld] bf16 matrix whose columns
+ *     [c, c+K) hold hi = bf16(x) and, in the split (fp32-accurate) mode, columns [lo_off + c, ...)
+ *     hold lo = bf16(x - hi); lo_off = 0 means single plane.
+ */
+#ifndef NUNERF_H
+#define NUNERF_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* nunerf_last_error(void);
+int nunerf_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long nunerf_launch_count(void);
+
+/* ------------------------------------------------------------------ dense layers (tcgen05)
+ * Replace every nn.Linear / F.linear on the path (cuBLAS in the reference): field.py:145 (SDFNetwork),
+ * :273-287 (NeRFNetwork), :386-394 (make_predictor), and their autograd backward / double backward.
+ */
+typedef struct {
+  /* C[M,N] = epi( A[M,K] * B[N,K]^T ), A and B bf16 planes, K-major */
+  const void* A; int lda; int a_lo_off;
+  const void* B; int ldb; int b_lo_off;
+  int M, N, K;                               /* N <= 256, N % 16 == 0, K % 64 == 0 */
+  const float* bias;                         /* [N] or NULL */
+  int act;                                   /* 0 none, 1 relu, 2 softplus(beta=100) */
+  const void* aux; int ldaux; int aux_lo_off;/* bf16 planes [M, >=N] or NULL */
+  int aux_mode;                              /* 0 none, 1 *= (aux>0), 2 *= 1-exp(-100*aux) */
+  const void* add; int ldadd; int add_lo_off;/* bf16 planes added after the mask, or NULL */
+  float out_scale;                           /* applied to the accumulator product (0 or 1.0 = none) */
+  void* out; int ldo; int out_lo_off;        /* bf16 planes or NULL */
+  float* out_f32; int ldo32;                 /* optional fp32 copy or NULL */
+  int n_store;                               /* store columns [0, n_store) only (0 = all) */
+  int impl;                                  /* 0 tcgen05, 1 SIMT debug kernel */
+} nunerf_linear_t;
+int nunerf_linear(const nunerf_linear_t* p, void* stream);
+
+typedef struct {
+  /* dW[N,K] += dZ[M,N]^T * X[M,K]  (fp32 atomics; caller zeroes dW), both operands MN-major bf16 planes */
+  const void* dZ; int ldz; int z_lo_off;
+  const void* X; int ldx; int x_lo_off;
+  int M, N, K;                               /* N <= 256, K % 64 == 0 */
+  float* dW; int lddw;
+  int impl;
+} nunerf_dw_t;
+int nunerf_linear_dw(const nunerf_dw_t* p, void* stream);
+
+/* out[n] += sum_m Z[m,n] (hi + lo) -- the bias gradient */
+int nunerf_colsum(const void* Z, int ldz, int z_lo_off, int M, int N, float* out, void* stream);
+/* fp32 [rows, cols] (ld_src) -> the block dst[row_off:+dst_rows, col_off:+dst_cols] of a bf16 plane matrix, zero
+ * filled outside the source; optional transpose and scale (weights: W -> W_kmajor and W^T_kmajor). */
+int nunerf_to_planes(const float* src, int rows, int cols, int ld_src, int transpose, float scale,
+                     void* dst, int dst_rows, int dst_cols, int ld, int lo_off, int col_off, int row_off, void* stream);
+int nunerf_from_planes(const void* src, int rows, int cols, int ld, int lo_off, float* dst, int ld_dst, void* stream);
+/* dst[:, col:col+width] = a (+ b), fp32 [M,C] -> planes, zero padded to `width` columns */
+int nunerf_f32_to_planes(const float* a, int lda, const float* b, int ldb, int M, int C, int width, void* dst, int ld,
+                         int lo, int col, void* stream);
+
+/* ------------------------------------------------------------------ sampling (ZT:572-612, field.py:468-498)
+ * tables (host-computed with torch.linspace, 160 floats): [0,64) linspace(0,1,64) | [64,96) bg lower |
+ *   [96,128) bg upper-lower | [128,160) bg unperturbed.  u_tab: linspace(.5/n_new, 1-.5/n_new, n_new).
+ * nunerf_ray_setup : near/far (ZT:320-327, when sphere != 0), 64 coarse z + 32 inverse-depth bg z (ZT:580-594).
+ * nunerf_upsample  : one importance round (ZT:525-554 + sample_pdf(det) + sorted merge ZT:556-561):
+ *                    z[R,n], sdf[R,n] -> z_new[R,n_new], inds[R,n_new], z_merged[R,n+n_new], perm[R,n+n_new];
+ *                    inv_s = min(*inv_s_dev, inv_s_cap) (ZT:604-605).
+ * nunerf_merge_sdf : sdf_merged = cat(sdf, sdf_new)[perm]  (ZT:564-568).
+ * nunerf_points    : p = o + d * z (ZT:598, :559).
+ */
+int nunerf_ray_setup(const float* o, const float* d, float* near, float* far, const float* U0, const float* U1,
+                     const float* tables, int R, int sphere, int perturb, float* z, float* z_bg, void* stream);
+int nunerf_points(const float* o, const float* d, const float* z, int R, int n, float* pts, void* stream);
+int nunerf_upsample(const float* o, const float* d, const float* z, const float* sdf, int R, int n, int n_new,
+                    const float* inv_s_dev, float inv_s_cap, const float* u_tab, float* z_new, int32_t* inds,
+                    float* z_merged, int32_t* perm, void* stream);
+int nunerf_merge_sdf(const float* sdf, const float* sdf_new, const int32_t* perm, int R, int n, int n_new,
+                     float* sdf_merged, void* stream);
+
+/* ------------------------------------------------------------------ render_core geometry + compositing
+ * nunerf_render_geometry (ZT:730-741): dists, mid points, inner mask and the row-major compaction of the
+ *   inner / outer sample sets (the order of the reference's boolean-mask indexing): slot[R*S] >= 0 -> index in
+ *   the inner list, < 0 -> -1 - index in the outer list; counts[2] = {N_in, N_out}; ray_scratch: 2R ints.
+ *   The compact arrays (capacity R*S each) receive points, dists, normalised ray dirs and the flat sample id.
+ * nunerf_composite_fwd/bwd (ZT:773-788): w = a * excl_cumprod(1-a+1e-7); rgb = clamp(sum w c (+1-acc)); acc;
+ *   background-only composite.  Backward recomputes the transmittance instead of storing it.
+ */
+int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists, float* pts,
+                           int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in, float* dists_in,
+                           float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out, float* dirs_out,
+                           int32_t* id_out, void* stream);
+int nunerf_composite_fwd(const float* alpha_in, const float* color_in, const float* alpha_out,
+                         const float* color_out, const int32_t* slot, int R, int S, int is_nerf, float* rgb,
+                         float* rgb_raw, float* acc, float* rgb_bkgr, float* weights, void* stream);
+int nunerf_composite_bwd(const float* alpha_in, const float* color_in, const float* alpha_out,
+                         const float* color_out, const int32_t* slot, int R, int S, int is_nerf, const float* rgb_raw,
+                         const float* d_rgb, const float* d_acc, const float* d_rgb_bkgr, float* d_alpha_in,
+                         float* d_color_in, float* d_alpha_out, float* d_color_out, void* stream);
+int nunerf_scatter_rows(const float* src, int M, int C, const int32_t* sample_id, float* dst, void* stream);
+
+/* ------------------------------------------------------------------ encodings + pointwise field math */
+/* positional encoding (field.py:14-61) of x[M,d] into planes; columns >= d(1+2F) up to `width` are zeroed */
+int nunerf_encode_pe(const float* x, int M, int d, int nfreq, void* dst, int ld, int lo_off, int col_off,
+                     int row_off, int width, void* stream);
+/* grad_x = J_pe(x)^T (ga + gb): last step of SDFNetwork.gradient (field.py:158-170); _bwd: J_pe(x) d_grad */
+int nunerf_sdf_grad_pe(const float* x, const float* ga, int lda, const float* gb, int ldb, int M, float* grad,
+                       void* stream);
+int nunerf_sdf_grad_pe_bwd(const float* x, const float* dgrad, int M, void* d1, int ld1, int lo1, int col1, int width1,
+                           void* d2, int ld2, int lo2, int col2, int width2, void* stream);
+
+/* compute_sdf_alpha ZT:657-685 + eikonal term ZT:769 */
+typedef struct {
+  int M; float cos_anneal; const float* inv_s_dev;       /* exp(10*variance), clipped to [1e-6,1e6] in-kernel */
+  const float* sdf; int ld_sdf; const float* grad; const float* dists; const float* dirs;
+  float* alpha; float* grad_err;
+  const float* d_alpha; const float* d_grad_err; float* d_sdf; float* d_grad; float* d_inv_s; /* d_inv_s NULL: frozen */
+} nunerf_sdf_alpha_t;
+int nunerf_sdf_alpha_fwd(const nunerf_sdf_alpha_t* p, void* stream);
+int nunerf_sdf_alpha_bwd(const nunerf_sdf_alpha_t* p, void* stream);
+
+/* NeRF++ glue: ZT:687-693 */
+int nunerf_nerf_prep(const float* pts, const float* dirs, int M, float* pts4, float* views, void* stream);
+int nunerf_nerf_out_fwd(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
+                        float* alpha, float* color, void* stream);
+int nunerf_nerf_out_bwd(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
+                        const float* d_alpha, const float* d_color, void* d_sig, int ld_ds, int lo_ds, int col_ds,
+                        void* d_rgb, int ld_dr, int lo_dr, int col_dr, void* stream);
+
+/* AppShadingNetwork.forward field.py:684-741: directions + encodings (IDE utils/ref_utils.py:85-114) */
+typedef struct {
+  int M;
+  const float* pts; const float* grad; const float* dirs;   /* [M,3]; dirs = normalised ray direction (view = -dirs) */
+  const float* rough_raw; int ld_rough;                      /* pre-sigmoid roughness head */
+  void* x_outer; int ld_outer; int lo_outer;                 /* [3M, ld]: IDE(n,1) | IDE(r,rough) | IDE(r,0) */
+  void* x_inner; int ld_inner; int lo_inner;                 /* [2M, ld]: PE6(p)++IDE(r,rough) | PE6(p)++IDE(r,0) */
+  void* x_weight; int ld_weight; int lo_weight;              /* [M, ld]: PE6(p) ++ PE6(r) */
+  void* x_refrac; int ld_refrac; int lo_refrac;              /* [M, ld]: PE6(p) ++ PE6(v) */
+  float* nov;                                                /* [M] */
+  /* backward */
+  const float* d_x_outer; int ld_dxo;                        /* fp32 [3M, ld] (72 cols used) */
+  const float* d_x_inner; int ld_dxi;                        /* fp32 [2M, ld] (cols 39..110 used) */
+  const float* d_nov;
+  float* d_grad;                                             /* [M,3] accumulated */
+  float* d_rough_raw; int ld_drough;                         /* accumulated */
+} nunerf_shade_encode_t;
+int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* stream);
+/* IDE(x, kinv) of M unit directions at one constant roughness -> planes (per-ray specular probe, ZT:780) */
+int nunerf_ide_encode(const float* x, int M, float kinv, void* dst, int ld, int lo, int col, void* stream);
+int nunerf_shade_encode_bwd(const nunerf_shade_encode_t* p, void* stream);
+
+/* material / light mixing, FG-LUT taps (dr.texture), sRGB (utils/raw_utils.py:5-12) */
+typedef struct {
+  int M; float exp_max;
+  const float* metallic; const float* rough; const float* albedo; const float* trans; int ld_mat; /* raw heads */
+  const float* outer; int ld_outer;       /* [3M, ld]: diffuse | direct | direct0 (3 cols) */
+  const float* inner; int ld_inner;       /* [2M, ld]: indirect | indirect0 */
+  const float* weight; int ld_weight;     /* [M, ld] */
+  const float* refrac; int ld_refrac;     /* [M, ld] */
+  const float* nov; const float* lut;     /* [M]; FG LUT [256,256,2] */
+  float* color; float* trans_out; float* metallic_out; float* occ_prob;
+  /* backward: dZ operands of the head layers as bf16 planes [*, ld_dz] (zero padded by the caller) */
+  const float* d_color; const float* d_trans_out; const float* d_metallic_out;
+  void* dz_metallic; void* dz_albedo; void* dz_trans; void* dz_outer; void* dz_inner; void* dz_weight; void* dz_refrac;
+  int ld_dz; int lo_dz;
+  float* d_rough_raw; float* d_nov;       /* fp32 [M] */
+} nunerf_shade_mix_t;
+int nunerf_shade_mix_fwd(const nunerf_shade_mix_t* p, void* stream);
+int nunerf_shade_mix_bwd(const nunerf_shade_mix_t* p, void* stream);
+
+/* SDF-network glue for the gradient pass and its reverse-over-reverse (field.py:158-170 with create_graph) */
+int nunerf_rowvec_mask(const float* w, const void* a, int lda, int a_lo, int M, int N, void* out, int ldo, int o_lo,
+                       void* stream);
+int nunerf_sdf_skip_split(const float* u4, const void* a3, int lda, int a_lo, int M, void* gs3, int ldg, int g_lo,
+                          float* g_skip, void* stream);
+int nunerf_sdf_bwd2_ew(const void* gts, int ldt, int t_lo, const void* a, int lda, int a_lo, const void* gs, int ldg,
+                       int g_lo, int M, int N, int n_real, void* u_next, int ldu, int u_lo, void* e, int lde, int e_lo,
+                       void* stream);
+/* torch.optim.Adam update (train/lr_common_manager.py:11-15) over a flat parameter vector */
+int nunerf_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
+                int step, void* stream);
+
+/* ------------------------------------------------------------------ tracing (DiffRender.py:410-416, :61-125;
+ * cuda/triangle.cu:48-99; raytracing/src/bvh.cu:259-301,526-602,694-713)
+ * nunerf_bvh_build_host: host build of a 4-wide BVH (recursive median split on the axis of largest centroid
+ *   variance, <= 4 triangles per leaf) into caller-provided host arrays; returns the node count (or negative).
+ * nunerf_bvh_trace    : closest hit with t in (0, tmax), double sided; hit[N] in {0,1}, tri[N] = ORIGINAL face
+ *   index (miss: 10000000), t[N] (miss: tmax).  Tie rule: min t, then min face index.
+ * nunerf_trace_brute  : same contract, exhaustive (on-device cross-check).
+ * nunerf_hit_interp   : DiffRender.py:61-125 re-intersection with the hit face: (u,v,t), x = o + t d, interpolated
+ *   unit vertex normal (tri_normals [F,9] = per-corner angle-weighted vertex normals, DiffRender.py:342-359).
+ * nunerf_refract_bounce: zero-thickness bounce ZT:1633-1684: eta = 1/(IoR(x)+1) (inverted when inside), TIR test
+ *   eta^2 sin^2 > 0.999, Snell direction, next origin x + 1e-5 d', d' / (|d'| + 1e-4).
+ */
+typedef struct { float lo[4][3]; float hi[4][3]; int32_t child[4]; int32_t count[4]; } nunerf_bvh_node_t;
+int nunerf_bvh_build_host(const float* verts_host, int V, const int32_t* faces_host, int F,
+                          nunerf_bvh_node_t* nodes_host, int max_nodes, int32_t* tri_order_host);
+int nunerf_bvh_trace(const nunerf_bvh_node_t* nodes, const float* tri_verts, const int32_t* tri_order,
+                     const float* rays_o, const float* rays_d, int N, float tmax, float* hit, int32_t* tri, float* t,
+                     void* stream);
+int nunerf_trace_brute(const float* tri_verts, int F, const float* rays_o, const float* rays_d, int N, float tmax,
+                       float* hit, int32_t* tri, float* t, void* stream);
+int nunerf_hit_interp(const float* tri_verts, const float* tri_normals, const int32_t* tri, const float* rays_o,
+                      const float* rays_d, int N, float* uvt, float* x_hit, float* n_hit, void* stream);
+int nunerf_refract_bounce(const float* x_hit, const float* n_hit, const float* rays_d, const float* eta,
+                          const int32_t* tri, int N, int inside, float* d_out, float* o_out, uint8_t* pass,
+                          void* stream);
+
+/* ------------------------------------------------------------------ grid sweep (field.py:1286-1307) */
+int nunerf_grid_points(int res, long long start, int count, const float* lin, float* pts, void* stream);
+int nunerf_grid_mask(const float* pts, const float* sdf, int ld_sdf, int count, float outside_val, float* u,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,130 @@
+// common.cuh -- shared helpers for libnunerf_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/nunerf.h"
+
+namespace nunerf {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(const char* fmt, const char* a = "", int code = -1) {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+
+#define NUNERF_CHECK_LAUNCH(name)                                                   \
+  do {                                                                              \
+    ::nunerf::g_launches.fetch_add(1, std::memory_order_relaxed);                   \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      snprintf(::nunerf::g_err, sizeof(::nunerf::g_err), "%s: %s", name, cudaGetErrorString(e__)); \
+      return -2;                                                                    \
+    }                                                                               \
+  } while (0)
+
+#define NUNERF_REQUIRE(cond, msg)                                                   \
+  do {                                                                              \
+    if (!(cond)) return ::nunerf::fail("%s", msg, -1);                              \
+  } while (0)
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- bf16 plane helpers
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16lo_to_f(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi_to_f(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// store one value into bf16 planes
+__device__ __forceinline__ void store_planes(__nv_bfloat16* base, long long idx, int lo_off, float v) {
+  __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  base[idx] = hi;
+  if (lo_off) base[idx + lo_off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+__device__ __forceinline__ float load_planes(const __nv_bfloat16* base, long long idx, int lo_off) {
+  float v = __bfloat162float(base[idx]);
+  if (lo_off) v += __bfloat162float(base[idx + lo_off]);
+  return v;
+}
+
+// ---------------------------------------------------------------- deterministic fp32 math (sampling path)
+// The sampling kernels and the C oracle (oracle/sampling_oracle.c) must agree bit for bit, so every
+// operation is an explicitly rounded fp32 op (no FMA contraction) and exp() is our own polynomial.
+__host__ __device__ __forceinline__ float det_mul(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b; return r;
+#endif
+}
+__host__ __device__ __forceinline__ float det_add(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(a, b);
+#else
+  volatile float r = a + b; return r;
+#endif
+}
+__host__ __device__ __forceinline__ float det_sub(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fsub_rn(a, b);
+#else
+  volatile float r = a - b; return r;
+#endif
+}
+__host__ __device__ __forceinline__ float det_div(float a, float b) {
+#ifdef __CUDA_ARCH__
+  return __fdiv_rn(a, b);
+#else
+  volatile float r = a / b; return r;
+#endif
+}
+__host__ __device__ __forceinline__ float det_sqrt(float a) {
+#ifdef __CUDA_ARCH__
+  return __fsqrt_rn(a);
+#else
+  volatile float r = sqrtf(a); return r;
+#endif
+}
+// exp(x) for x <= 0 (and moderately positive): Cody-Waite reduction + degree-7 Taylor/Horner, all rounded fp32 ops.
+__host__ __device__ __forceinline__ float det_exp(float x) {
+  if (x < -87.0f) return 0.0f;
+  if (x > 88.0f) x = 88.0f;
+  float t = det_mul(x, 1.44269504088896341f);
+  float n = (t >= 0.0f) ? (float)(int)(det_add(t, 0.5f)) : (float)(int)(det_sub(t, 0.5f));
+  float r = det_sub(x, det_mul(n, 0.693359375f));
+  r = det_sub(r, det_mul(n, -2.12194440e-4f));
+  float p = 1.0f / 5040.0f;
+  p = det_add(det_mul(p, r), 1.0f / 720.0f);
+  p = det_add(det_mul(p, r), 1.0f / 120.0f);
+  p = det_add(det_mul(p, r), 1.0f / 24.0f);
+  p = det_add(det_mul(p, r), 1.0f / 6.0f);
+  p = det_add(det_mul(p, r), 0.5f);
+  p = det_add(det_mul(p, r), 1.0f);
+  p = det_add(det_mul(p, r), 1.0f);
+  int e = (int)n + 127;
+  if (e <= 0) return 0.0f;
+  union { uint32_t u; float f; } s;
+  s.u = (uint32_t)e << 23;
+  return det_mul(p, s.f);
+}
+__host__ __device__ __forceinline__ float det_sigmoid(float x) {
+  // 1/(1+exp(-x)) evaluated on the non-overflowing branch
+  if (x >= 0.0f) return det_div(1.0f, det_add(1.0f, det_exp(-x)));
+  float e = det_exp(x);
+  return det_div(e, det_add(1.0f, e));
+}
+
+}  // namespace nunerf

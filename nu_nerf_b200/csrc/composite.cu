@@ -1,0 +1,324 @@
+// composite.cu -- render_core geometry, inner/outer compaction and the fused compositing kernels
+// (ZT:725-785).  One warp per ray; sample s lives in lane (s & 31), block (s >> 5): all [R,S] accesses are
+// coalesced.  Backward recomputes the transmittance with the same scan instead of reading a stored copy.
+#include "common.cuh"
+
+namespace nunerf {
+
+constexpr int WPB = 4;
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_BLK = 8;  // S <= 256
+
+__device__ __forceinline__ float scan_mul32(float x, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    float t = __shfl_up_sync(FULL, x, off);
+    if (lane >= off) x *= t;
+  }
+  return x;
+}
+__device__ __forceinline__ float scan_add32_rev(float x, int lane) {
+  // inclusive suffix sum within the warp
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    float t = __shfl_down_sync(FULL, x, off);
+    if (lane + off < 32) x += t;
+  }
+  return x;
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(FULL, x, off);
+  return x;
+}
+
+// ---- geometry pass 1: dists, mid points, per-ray inner count (ZT:730-736)
+__global__ void geometry_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
+                                int R, int S, float* dists, float* pts, int32_t* ray_inner) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
+  const float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
+  const float* zr = z + (long long)r * S;
+  int cnt = 0;
+  for (int s = lane; s < S + (32 - (S & 31)) % 32; s += 32) {
+    bool ok = s < S;
+    float z0 = ok ? zr[s] : 0.f;
+    float dist;
+    if (ok) {
+      if (s + 1 < S) dist = __fsub_rn(zr[s + 1], z0);
+      else dist = __fsub_rn(z0, zr[s - 1]);
+      float zm = __fadd_rn(z0, __fmul_rn(dist, 0.5f));
+      float px = __fadd_rn(ox, __fmul_rn(dx, zm)), py = __fadd_rn(oy, __fmul_rn(dy, zm)),
+            pz = __fadd_rn(oz, __fmul_rn(dz, zm));
+      long long i = (long long)r * S + s;
+      dists[i] = dist;
+      pts[3 * i] = px; pts[3 * i + 1] = py; pts[3 * i + 2] = pz;
+      float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+      ok = nrm <= 1.0f;
+    }
+    cnt += __popc(__ballot_sync(FULL, ok));
+  }
+  if (lane == 0) ray_inner[r] = cnt;
+}
+
+// ---- geometry pass 2: exclusive scan of the per-ray counts (single block) -> ray_off[R], counts[2]
+__global__ void ray_scan_kernel(const int32_t* __restrict__ ray_inner, int R, int S, int32_t* ray_off, int32_t* counts) {
+  __shared__ int s_part[1024];
+  const int t = threadIdx.x, nt = blockDim.x;
+  const int per = (R + nt - 1) / nt;
+  const int b = t * per, e = min(R, b + per);
+  int sum = 0;
+  for (int i = b; i < e; ++i) sum += ray_inner[i];
+  s_part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < nt; off <<= 1) {
+    int v = t >= off ? s_part[t - off] : 0;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  int run = s_part[t] - sum;
+  for (int i = b; i < e; ++i) { ray_off[i] = run; run += ray_inner[i]; }
+  if (t == nt - 1) { counts[0] = s_part[t]; counts[1] = R * S - s_part[t]; }
+}
+
+// ---- geometry pass 3: slots + compact gather of both sets (row-major mask order, as points[inner_mask])
+__global__ void compact_kernel(const float* __restrict__ d, const float* __restrict__ pts, const float* __restrict__ dists,
+                               const int32_t* __restrict__ ray_off, int R, int S, int32_t* slot, float* pts_in,
+                               float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out,
+                               float* dirs_out, int32_t* id_out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (r >= R) return;
+  // F.normalize(dirs) (ZT:740): d / max(||d||, 1e-12)
+  float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
+  float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
+  dx /= nrm; dy /= nrm; dz /= nrm;
+  int in_run = ray_off[r];
+  int out_run = r * S - in_run;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    int s = s0 + lane;
+    bool ok = s < S;
+    long long i = (long long)r * S + (ok ? s : 0);
+    float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    float pn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+    bool inner = ok && pn <= 1.0f;
+    bool outer = ok && !inner;
+    unsigned bi = __ballot_sync(FULL, inner), bo = __ballot_sync(FULL, outer);
+    unsigned lt = (1u << lane) - 1u;
+    if (inner) {
+      int k = in_run + __popc(bi & lt);
+      slot[i] = k;
+      pts_in[3 * k] = px; pts_in[3 * k + 1] = py; pts_in[3 * k + 2] = pz;
+      dists_in[k] = dists[i];
+      dirs_in[3 * k] = dx; dirs_in[3 * k + 1] = dy; dirs_in[3 * k + 2] = dz;
+      id_in[k] = (int32_t)i;
+    } else if (outer) {
+      int k = out_run + __popc(bo & lt);
+      slot[i] = -1 - k;
+      pts_out[3 * k] = px; pts_out[3 * k + 1] = py; pts_out[3 * k + 2] = pz;
+      dists_out[k] = dists[i];
+      dirs_out[3 * k] = dx; dirs_out[3 * k + 1] = dy; dirs_out[3 * k + 2] = dz;
+      id_out[k] = (int32_t)i;
+    }
+    in_run += __popc(bi);
+    out_run += __popc(bo);
+  }
+}
+
+// ---- compositing
+struct Sample { float a, ab, c0, c1, c2; };
+
+__device__ __forceinline__ Sample fetch(const float* __restrict__ a_in, const float* __restrict__ c_in,
+                                        const float* __restrict__ a_out, const float* __restrict__ c_out, int sl) {
+  Sample s;
+  if (sl >= 0) {
+    s.a = a_in[sl]; s.ab = 0.f;
+    s.c0 = c_in[3 * sl]; s.c1 = c_in[3 * sl + 1]; s.c2 = c_in[3 * sl + 2];
+  } else {
+    int k = -1 - sl;
+    s.a = a_out[k]; s.ab = s.a;
+    s.c0 = c_out[3 * k]; s.c1 = c_out[3 * k + 1]; s.c2 = c_out[3 * k + 2];
+  }
+  return s;
+}
+
+__global__ void composite_fwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
+                                     const float* __restrict__ a_out, const float* __restrict__ c_out,
+                                     const int32_t* __restrict__ slot, int R, int S, int is_nerf, float* rgb,
+                                     float* rgb_raw, float* acc, float* rgb_b, float* weights) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float carry = 1.f, carry_b = 1.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    int s = base + lane;
+    bool ok = s < S;
+    Sample sm = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ok) sm = fetch(a_in, c_in, a_out, c_out, slot[(long long)r * S + s]);
+    float v = ok ? (1.0f - sm.a + 1e-7f) : 1.0f;
+    float vb = ok ? (1.0f - sm.ab + 1e-7f) : 1.0f;
+    float incl = scan_mul32(v, lane), incl_b = scan_mul32(vb, lane);
+    float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, incl_b, 1);
+    if (lane == 0) { ex = 1.f; exb = 1.f; }
+    float w = sm.a * (carry * ex), wb = sm.ab * (carry_b * exb);
+    carry *= __shfl_sync(FULL, incl, 31);
+    carry_b *= __shfl_sync(FULL, incl_b, 31);
+    if (ok && weights) weights[(long long)r * S + s] = w;
+    s0 += w * sm.c0; s1 += w * sm.c1; s2 += w * sm.c2; sa += w;
+    b0 += wb * sm.c0; b1 += wb * sm.c1; b2 += wb * sm.c2;
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sa = warp_sum(sa);
+  b0 = warp_sum(b0); b1 = warp_sum(b1); b2 = warp_sum(b2);
+  if (lane == 0) {
+    if (is_nerf) { float bg = 1.0f - sa; s0 += bg; s1 += bg; s2 += bg; }
+    rgb_raw[3 * r] = s0; rgb_raw[3 * r + 1] = s1; rgb_raw[3 * r + 2] = s2;
+    rgb[3 * r] = fminf(fmaxf(s0, 0.f), 1.f); rgb[3 * r + 1] = fminf(fmaxf(s1, 0.f), 1.f);
+    rgb[3 * r + 2] = fminf(fmaxf(s2, 0.f), 1.f);
+    acc[r] = sa;
+    rgb_b[3 * r] = b0; rgb_b[3 * r + 1] = b1; rgb_b[3 * r + 2] = b2;
+  }
+}
+
+// d_alpha_i = g_i T_i - (sum_{k>i} g_k w_k) / (1 - a_i + eps),  g_k = d_rgb . c_k + d_acc - [is_nerf] sum(d_rgb)
+__global__ void composite_bwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
+                                     const float* __restrict__ a_out, const float* __restrict__ c_out,
+                                     const int32_t* __restrict__ slot, int R, int S, int is_nerf,
+                                     const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb,
+                                     const float* __restrict__ d_acc, const float* __restrict__ d_rgb_b,
+                                     float* d_a_in, float* d_c_in, float* d_a_out, float* d_c_out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float g0 = d_rgb ? d_rgb[3 * r] : 0.f, g1 = d_rgb ? d_rgb[3 * r + 1] : 0.f, g2 = d_rgb ? d_rgb[3 * r + 2] : 0.f;
+  // clamp(color, 0, 1) passes the gradient on the closed interval
+  float q0 = rgb_raw[3 * r], q1 = rgb_raw[3 * r + 1], q2 = rgb_raw[3 * r + 2];
+  if (!(q0 >= 0.f && q0 <= 1.f)) g0 = 0.f;
+  if (!(q1 >= 0.f && q1 <= 1.f)) g1 = 0.f;
+  if (!(q2 >= 0.f && q2 <= 1.f)) g2 = 0.f;
+  float ga = (d_acc ? d_acc[r] : 0.f) - (is_nerf ? (g0 + g1 + g2) : 0.f);
+  float h0 = d_rgb_b ? d_rgb_b[3 * r] : 0.f, h1 = d_rgb_b ? d_rgb_b[3 * r + 1] : 0.f,
+        h2 = d_rgb_b ? d_rgb_b[3 * r + 2] : 0.f;
+  const int nblk = (S + 31) >> 5;
+  // pass 1 (forward): T per sample, kept in registers (S <= 256)
+  float T[MAX_BLK], Tb[MAX_BLK], gw[MAX_BLK], gwb[MAX_BLK], va[MAX_BLK], vab[MAX_BLK], gk[MAX_BLK], gkb[MAX_BLK];
+  int sl[MAX_BLK];
+  float carry = 1.f, carry_b = 1.f;
+#pragma unroll
+  for (int k = 0; k < MAX_BLK; ++k) {
+    if (k < nblk) {
+      int s = k * 32 + lane;
+      bool ok = s < S;
+      sl[k] = ok ? slot[(long long)r * S + s] : 0;
+      Sample sm = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) sm = fetch(a_in, c_in, a_out, c_out, sl[k]);
+      float v = ok ? (1.0f - sm.a + 1e-7f) : 1.0f, vb = ok ? (1.0f - sm.ab + 1e-7f) : 1.0f;
+      float incl = scan_mul32(v, lane), incl_b = scan_mul32(vb, lane);
+      float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, incl_b, 1);
+      if (lane == 0) { ex = 1.f; exb = 1.f; }
+      T[k] = carry * ex; Tb[k] = carry_b * exb;
+      carry *= __shfl_sync(FULL, incl, 31);
+      carry_b *= __shfl_sync(FULL, incl_b, 31);
+      va[k] = v; vab[k] = vb;
+      float w = sm.a * T[k], wb = sm.ab * Tb[k];
+      gk[k] = ok ? (g0 * sm.c0 + g1 * sm.c1 + g2 * sm.c2 + ga) : 0.f;
+      gkb[k] = ok ? (h0 * sm.c0 + h1 * sm.c1 + h2 * sm.c2) : 0.f;
+      gw[k] = gk[k] * w; gwb[k] = gkb[k] * wb;
+      if (ok) {
+        // colour gradient: both composites share the colour of outer samples
+        float dc0 = w * g0 + wb * h0, dc1 = w * g1 + wb * h1, dc2 = w * g2 + wb * h2;
+        if (sl[k] >= 0) { float* p = d_c_in + 3 * (long long)sl[k]; p[0] = dc0; p[1] = dc1; p[2] = dc2; }
+        else { float* p = d_c_out + 3 * (long long)(-1 - sl[k]); p[0] = dc0; p[1] = dc1; p[2] = dc2; }
+      }
+    }
+  }
+  // pass 2 (reverse): exclusive suffix sums of g*w
+  float suf = 0.f, suf_b = 0.f;
+#pragma unroll
+  for (int k = MAX_BLK - 1; k >= 0; --k) {
+    if (k < nblk) {
+      int s = k * 32 + lane;
+      bool ok = s < S;
+      float incl = scan_add32_rev(gw[k], lane), incl_b = scan_add32_rev(gwb[k], lane);
+      float ex = __shfl_down_sync(FULL, incl, 1), exb = __shfl_down_sync(FULL, incl_b, 1);
+      if (lane == 31) { ex = 0.f; exb = 0.f; }
+      float after = suf + ex, after_b = suf_b + exb;
+      suf += __shfl_sync(FULL, incl, 0);
+      suf_b += __shfl_sync(FULL, incl_b, 0);
+      if (ok) {
+        float da = gk[k] * T[k] - after / va[k];
+        if (sl[k] >= 0) d_a_in[sl[k]] = da;
+        else d_a_out[-1 - sl[k]] = da + (gkb[k] * Tb[k] - after_b / vab[k]);
+      }
+    }
+  }
+}
+
+__global__ void scatter_rows_kernel(const float* __restrict__ src, long long M, int C, const int32_t* __restrict__ id,
+                                    float* dst) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * C) return;
+  long long m = i / C;
+  int c = (int)(i % C);
+  dst[(long long)id[m] * C + c] = src[i];
+}
+
+}  // namespace nunerf
+
+using namespace nunerf;
+
+extern "C" int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists,
+                                      float* pts, int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in,
+                                      float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out,
+                                      float* dirs_out, int32_t* id_out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NUNERF_REQUIRE(o && d && z && dists && pts && slot && counts && ray_scratch, "render_geometry: null argument");
+  NUNERF_REQUIRE(pts_in && dists_in && dirs_in && id_in && pts_out && dists_out && dirs_out && id_out,
+                 "render_geometry: null compact buffer");
+  NUNERF_REQUIRE(R > 0 && S >= 2 && S <= 256, "render_geometry: need 2 <= S <= 256");
+  geometry_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, R, S, dists, pts, ray_scratch);
+  NUNERF_CHECK_LAUNCH("geometry_kernel");
+  ray_scan_kernel<<<1, 1024, 0, stream>>>(ray_scratch, R, S, ray_scratch + R, counts);
+  NUNERF_CHECK_LAUNCH("ray_scan_kernel");
+  compact_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(d, pts, dists, ray_scratch + R, R, S, slot, pts_in, dists_in,
+                                                       dirs_in, id_in, pts_out, dists_out, dirs_out, id_out);
+  NUNERF_CHECK_LAUNCH("compact_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in, const float* alpha_out,
+                                    const float* color_out, const int32_t* slot, int R, int S, int is_nerf, float* rgb,
+                                    float* rgb_raw, float* acc, float* rgb_bkgr, float* weights, void* stream) {
+  NUNERF_REQUIRE(slot && rgb && rgb_raw && acc && rgb_bkgr && R > 0 && S > 0 && S <= 256, "composite_fwd: bad arguments");
+  composite_fwd_kernel<<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(alpha_in, color_in, alpha_out, color_out,
+                                                                          slot, R, S, is_nerf, rgb, rgb_raw, acc,
+                                                                          rgb_bkgr, weights);
+  NUNERF_CHECK_LAUNCH("composite_fwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_composite_bwd(const float* alpha_in, const float* color_in, const float* alpha_out,
+                                    const float* color_out, const int32_t* slot, int R, int S, int is_nerf,
+                                    const float* rgb_raw, const float* d_rgb, const float* d_acc,
+                                    const float* d_rgb_bkgr, float* d_alpha_in, float* d_color_in, float* d_alpha_out,
+                                    float* d_color_out, void* stream) {
+  NUNERF_REQUIRE(slot && rgb_raw && d_alpha_in && d_color_in && d_alpha_out && d_color_out && R > 0 && S > 0 && S <= 256,
+                 "composite_bwd: bad arguments");
+  composite_bwd_kernel<<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(alpha_in, color_in, alpha_out, color_out,
+                                                                          slot, R, S, is_nerf, rgb_raw, d_rgb, d_acc,
+                                                                          d_rgb_bkgr, d_alpha_in, d_color_in,
+                                                                          d_alpha_out, d_color_out);
+  NUNERF_CHECK_LAUNCH("composite_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_scatter_rows(const float* src, int M, int C, const int32_t* sample_id, float* dst, void* stream) {
+  NUNERF_REQUIRE(src && sample_id && dst && M > 0 && C > 0, "scatter_rows: bad arguments");
+  long long total = (long long)M * C;
+  scatter_rows_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, M, C, sample_id, dst);
+  NUNERF_CHECK_LAUNCH("scatter_rows_kernel");
+  return 0;
+}

@@ -1,0 +1,569 @@
+// field.cu -- encodings and pointwise field kernels (everything on the path that is not a dense layer,
+// a scan or a traversal).  Per-point math lives in pointwise.cuh; the kernels here only move data:
+// fp32 compact per-sample arrays in, bf16 "planes" (tensor-core operands) or fp32 out.
+#include "common.cuh"
+#include "pointwise.cuh"
+
+namespace nunerf {
+
+__constant__ pw::IdeTable c_ide;
+static pw::IdeTable h_ide;
+static bool g_ide_ready = false;
+
+static int ensure_ide() {
+  if (g_ide_ready) return 0;
+  pw::build_ide_table(&h_ide);
+  cudaError_t e = cudaMemcpyToSymbol(c_ide, &h_ide, sizeof(h_ide));
+  if (e != cudaSuccess) return fail("ide table upload: %s", cudaGetErrorString(e), -2);
+  g_ide_ready = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- positional encoding
+// dst[row_off + m, col_off + j] for j < width; j >= d*(1+2F) is zero fill.
+__global__ void encode_pe_kernel(const float* __restrict__ x, long long M, int d, int F, __nv_bfloat16* dst, int ld,
+                                 int lo_off, int col_off, long long row_off, int width) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * width) return;
+  long long m = idx / width;
+  int j = (int)(idx % width);
+  float v = 0.f;
+  if (j < d) v = x[m * d + j];
+  else if (j < d * (1 + 2 * F)) {
+    int t = (j - d) / d, c = (j - d) % d;
+    int k = t >> 1;
+    float a = x[m * d + c] * (float)(1 << k);
+    v = (t & 1) ? cosf(a) : sinf(a);
+  }
+  store_planes(dst, (row_off + m) * ld + col_off + j, lo_off, v);
+}
+
+// grad_x = J_pe^T (ga + gb), PE-6 of a 3-vector (39 columns)
+__global__ void sdf_grad_pe_kernel(const float* __restrict__ x, const float* __restrict__ ga, int lda,
+                                   const float* __restrict__ gb, int ldb, long long M, float* grad) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float* a = ga + m * lda;
+  const float* b = gb ? gb + m * ldb : nullptr;
+  for (int c = 0; c < 3; ++c) {
+    float xc = x[3 * m + c];
+    float g = a[c] + (b ? b[c] : 0.f);
+    for (int k = 0; k < 6; ++k) {
+      float f = (float)(1 << k);
+      float s, co;
+      sincosf(xc * f, &s, &co);
+      int is = 3 + 6 * k + c, ic = 6 + 6 * k + c;
+      g += (a[is] + (b ? b[is] : 0.f)) * f * co - (a[ic] + (b ? b[ic] : 0.f)) * f * s;
+    }
+    grad[3 * m + c] = g;
+  }
+}
+
+// u~ = J_pe d_grad written to up to two plane destinations (39 real columns, `width` written, zero padded)
+__global__ void sdf_grad_pe_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dgrad, long long M,
+                                       __nv_bfloat16* d1, int ld1, int lo1, int col1, int width1, __nv_bfloat16* d2,
+                                       int ld2, int lo2, int col2, int width2) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int wmax = width1 > width2 ? width1 : width2;
+  if (idx >= M * wmax) return;
+  long long m = idx / wmax;
+  int j = (int)(idx % wmax);
+  float v = 0.f;
+  if (j < 3) v = dgrad[3 * m + j];
+  else if (j < 39) {
+    int t = (j - 3) / 3, c = (j - 3) % 3, k = t >> 1;
+    float f = (float)(1 << k);
+    float s, co;
+    sincosf(x[3 * m + c] * f, &s, &co);
+    v = dgrad[3 * m + c] * ((t & 1) ? -f * s : f * co);
+  }
+  if (d1 && j < width1) store_planes(d1, m * ld1 + col1 + j, lo1, v);
+  if (d2 && j < width2) store_planes(d2, m * ld2 + col2 + j, lo2, v);
+}
+
+// ------------------------------------------------------------------------------------------- sdf -> alpha
+__global__ void sdf_alpha_fwd_kernel(nunerf_sdf_alpha_t p) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.M) return;
+  float inv_s = fminf(fmaxf(p.inv_s_dev[0], 1e-6f), 1e6f);
+  float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
+  float dr[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  pw::SdfAlphaOut o = pw::sdf_alpha_fwd(p.sdf[m * p.ld_sdf], g, p.dists[m], dr, inv_s, p.cos_anneal);
+  p.alpha[m] = o.alpha;
+  p.grad_err[m] = o.gerr;
+}
+
+__global__ void sdf_alpha_bwd_kernel(nunerf_sdf_alpha_t p) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float dinv = 0.f;
+  if (m < p.M) {
+    float raw = p.inv_s_dev[0];
+    float inv_s = fminf(fmaxf(raw, 1e-6f), 1e6f);
+    float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
+    float dr[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+    float dsdf, dg[3];
+    pw::sdf_alpha_bwd(p.sdf[m * p.ld_sdf], g, p.dists[m], dr, inv_s, p.cos_anneal, p.d_alpha[m],
+                      p.d_grad_err ? p.d_grad_err[m] : 0.f, &dsdf, dg, &dinv);
+    if (!(raw >= 1e-6f && raw <= 1e6f)) dinv = 0.f;
+    p.d_sdf[m] = dsdf;
+    p.d_grad[3 * m] = dg[0]; p.d_grad[3 * m + 1] = dg[1]; p.d_grad[3 * m + 2] = dg[2];
+  }
+  if (p.d_inv_s) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dinv += __shfl_xor_sync(0xffffffffu, dinv, off);
+    if ((threadIdx.x & 31) == 0 && dinv != 0.f) atomicAdd(p.d_inv_s, dinv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- NeRF++ glue
+__global__ void nerf_prep_kernel(const float* __restrict__ pts, const float* __restrict__ dirs, long long M,
+                                 float* pts4, float* views) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float x = pts[3 * m], y = pts[3 * m + 1], z = pts[3 * m + 2];
+  float n = sqrtf(x * x + y * y + z * z);  // ZT:688-689
+  pts4[4 * m] = x / n; pts4[4 * m + 1] = y / n; pts4[4 * m + 2] = z / n; pts4[4 * m + 3] = 1.0f / n;
+  views[3 * m] = -dirs[3 * m]; views[3 * m + 1] = -dirs[3 * m + 1]; views[3 * m + 2] = -dirs[3 * m + 2];
+}
+
+__global__ void nerf_out_fwd_kernel(const float* __restrict__ sigma, int ld_s, const float* __restrict__ rgb, int ld_c,
+                                    const float* __restrict__ dists, long long M, float* alpha, float* color) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float c[3] = {rgb[m * ld_c], rgb[m * ld_c + 1], rgb[m * ld_c + 2]};
+  float a, col[3];
+  pw::nerf_out_fwd(sigma[m * ld_s], c, dists[m], &a, col);
+  alpha[m] = a;
+  color[3 * m] = col[0]; color[3 * m + 1] = col[1]; color[3 * m + 2] = col[2];
+}
+
+__global__ void nerf_out_bwd_kernel(const float* __restrict__ sigma, int ld_s, const float* __restrict__ rgb, int ld_c,
+                                    const float* __restrict__ dists, long long M, const float* __restrict__ d_alpha,
+                                    const float* __restrict__ d_color, __nv_bfloat16* d_sig, int ld_ds, int lo_ds,
+                                    int col_ds, __nv_bfloat16* d_rgb, int ld_dr, int lo_dr, int col_dr) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float c[3] = {rgb[m * ld_c], rgb[m * ld_c + 1], rgb[m * ld_c + 2]};
+  float dc[3] = {d_color[3 * m], d_color[3 * m + 1], d_color[3 * m + 2]};
+  float ds, drgb[3];
+  pw::nerf_out_bwd(sigma[m * ld_s], c, dists[m], d_alpha[m], dc, &ds, drgb);
+  store_planes(d_sig, m * ld_ds + col_ds, lo_ds, ds);
+  for (int k = 0; k < 3; ++k) store_planes(d_rgb, m * ld_dr + col_dr + k, lo_dr, drgb[k]);
+}
+
+// ------------------------------------------------------------------------------------------- shading encode
+__device__ __forceinline__ void write_pe6(__nv_bfloat16* dst, long long base, int lo, const float* v3) {
+  for (int c = 0; c < 3; ++c) store_planes(dst, base + c, lo, v3[c]);
+  for (int k = 0; k < 6; ++k) {
+    float f = (float)(1 << k);
+    for (int c = 0; c < 3; ++c) {
+      float s, co;
+      sincosf(v3[c] * f, &s, &co);
+      store_planes(dst, base + 3 + 6 * k + c, lo, s);
+      store_planes(dst, base + 6 + 6 * k + c, lo, co);
+    }
+  }
+}
+
+// One thread per (point, job): job 0: IDE(n,1); 1: IDE(r,rough); 2: IDE(r,0); 3: PE blocks + nov
+__global__ void shade_encode_fwd_kernel(nunerf_shade_encode_t p) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = p.M;
+  if (idx >= 4 * M) return;
+  int job = (int)(idx / M);
+  long long m = idx % M;
+  float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
+  float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  pw::ShadeDirs s = pw::shade_dirs(g, rd);
+  __nv_bfloat16* xo = (__nv_bfloat16*)p.x_outer;
+  __nv_bfloat16* xi = (__nv_bfloat16*)p.x_inner;
+  if (job < 3) {
+    float rough = pw::sigmoidf_(p.rough_raw[m * p.ld_rough]);
+    float out[72];
+    if (job == 0) pw::ide_fwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, out);
+    else pw::ide_fwd(c_ide, s.r[0], s.r[1], s.r[2], job == 1 ? rough : 0.0f, out);
+    long long ro = ((long long)job * M + m) * p.ld_outer;
+    for (int j = 0; j < 72; ++j) store_planes(xo, ro + j, p.lo_outer, out[j]);
+    if (job >= 1) {
+      long long ri = ((long long)(job - 1) * M + m) * p.ld_inner + 39;
+      for (int j = 0; j < 72; ++j) store_planes(xi, ri + j, p.lo_inner, out[j]);
+    }
+  } else {
+    float pt[3] = {p.pts[3 * m], p.pts[3 * m + 1], p.pts[3 * m + 2]};
+    write_pe6(xi, m * p.ld_inner, p.lo_inner, pt);
+    write_pe6(xi, (M + m) * p.ld_inner, p.lo_inner, pt);
+    __nv_bfloat16* xw = (__nv_bfloat16*)p.x_weight;
+    __nv_bfloat16* xr = (__nv_bfloat16*)p.x_refrac;
+    write_pe6(xw, m * p.ld_weight, p.lo_weight, pt);
+    write_pe6(xw, m * p.ld_weight + 39, p.lo_weight, s.r);
+    write_pe6(xr, m * p.ld_refrac, p.lo_refrac, pt);
+    write_pe6(xr, m * p.ld_refrac + 39, p.lo_refrac, s.v);
+    p.nov[m] = s.nov;
+  }
+}
+
+__global__ void shade_encode_bwd_kernel(nunerf_shade_encode_t p) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = p.M;
+  if (m >= M) return;
+  float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
+  float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  pw::ShadeDirs s = pw::shade_dirs(g, rd);
+  float rough = pw::sigmoidf_(p.rough_raw[m * p.ld_rough]);
+  float dn[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f}, drough = 0.f;
+  float dout[72], gx, gy, gz, gk;
+  // IDE(n, 1)
+  const float* src = p.d_x_outer + m * p.ld_dxo;
+  for (int j = 0; j < 72; ++j) dout[j] = src[j];
+  pw::ide_bwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, dout, &gx, &gy, &gz, &gk);
+  dn[0] += gx; dn[1] += gy; dn[2] += gz;
+  // IDE(r, rough): outer block 1 + inner block 0
+  src = p.d_x_outer + (M + m) * p.ld_dxo;
+  const float* src2 = p.d_x_inner + m * p.ld_dxi + 39;
+  for (int j = 0; j < 72; ++j) dout[j] = src[j] + src2[j];
+  pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], rough, dout, &gx, &gy, &gz, &gk);
+  dr[0] += gx; dr[1] += gy; dr[2] += gz; drough += gk;
+  // IDE(r, 0): outer block 2 + inner block 1
+  src = p.d_x_outer + (2 * M + m) * p.ld_dxo;
+  src2 = p.d_x_inner + (M + m) * p.ld_dxi + 39;
+  for (int j = 0; j < 72; ++j) dout[j] = src[j] + src2[j];
+  pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], 0.0f, dout, &gx, &gy, &gz, &gk);
+  dr[0] += gx; dr[1] += gy; dr[2] += gz;
+  float dg[3];
+  pw::shade_dirs_bwd(s, dr, dn, p.d_nov[m], dg);
+  p.d_grad[3 * m] += dg[0]; p.d_grad[3 * m + 1] += dg[1]; p.d_grad[3 * m + 2] += dg[2];
+  p.d_rough_raw[m * p.ld_drough] += drough * rough * (1.0f - rough);
+}
+
+// IDE of M unit directions at a constant roughness (the per-ray specular probe, ZT:780)
+__global__ void ide_encode_kernel(const float* __restrict__ x, long long M, float kinv, __nv_bfloat16* dst, int ld,
+                                  int lo, int col) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float out[72];
+  pw::ide_fwd(c_ide, x[3 * m], x[3 * m + 1], x[3 * m + 2], kinv, out);
+  for (int j = 0; j < 72; ++j) store_planes(dst, m * ld + col + j, lo, out[j]);
+}
+
+// ------------------------------------------------------------------------------------------- shading mix
+__device__ __forceinline__ void load_mix(const nunerf_shade_mix_t& p, long long m, pw::ShadeMixIn* in) {
+  long long M = p.M;
+  in->metallic = p.metallic[m * p.ld_mat];
+  in->rough = p.rough[m * p.ld_mat];
+  in->trans = p.trans[m * p.ld_mat];
+  in->occ = p.weight[m * p.ld_weight];
+  in->nov = p.nov[m];
+  for (int c = 0; c < 3; ++c) {
+    in->albedo[c] = p.albedo[m * p.ld_mat + c];
+    in->diffuse_l[c] = p.outer[m * p.ld_outer + c];
+    in->direct[c] = p.outer[(M + m) * p.ld_outer + c];
+    in->direct0[c] = p.outer[(2 * M + m) * p.ld_outer + c];
+    in->indirect[c] = p.inner[m * p.ld_inner + c];
+    in->indirect0[c] = p.inner[(M + m) * p.ld_inner + c];
+    in->refrac[c] = p.refrac[m * p.ld_refrac + c];
+  }
+}
+
+__global__ void shade_mix_fwd_kernel(nunerf_shade_mix_t p) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= p.M) return;
+  pw::ShadeMixIn in;
+  load_mix(p, m, &in);
+  pw::ShadeMixOut o = pw::shade_mix_fwd(in, p.lut, p.exp_max);
+  p.color[3 * m] = o.color[0]; p.color[3 * m + 1] = o.color[1]; p.color[3 * m + 2] = o.color[2];
+  p.trans_out[m] = o.trans; p.metallic_out[m] = o.metallic; p.occ_prob[m] = o.occ_prob;
+}
+
+// gradients w.r.t. the raw heads are written as bf16 planes (the dZ operands of the head layers, 64-wide,
+// zero padded) plus fp32 d_nov / d_rough_raw for the encode backward.
+__global__ void shade_mix_bwd_kernel(nunerf_shade_mix_t p) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = p.M;
+  if (m >= M) return;
+  pw::ShadeMixIn in, d;
+  load_mix(p, m, &in);
+  float dc[3] = {p.d_color[3 * m], p.d_color[3 * m + 1], p.d_color[3 * m + 2]};
+  pw::shade_mix_bwd(in, p.lut, p.exp_max, dc, p.d_trans_out ? p.d_trans_out[m] : 0.f,
+                    p.d_metallic_out ? p.d_metallic_out[m] : 0.f, &d);
+  const int ld = p.ld_dz, lo = p.lo_dz;
+  store_planes((__nv_bfloat16*)p.dz_metallic, m * ld, lo, d.metallic);
+  store_planes((__nv_bfloat16*)p.dz_trans, m * ld, lo, d.trans);
+  store_planes((__nv_bfloat16*)p.dz_weight, m * ld, lo, d.occ);
+  for (int c = 0; c < 3; ++c) {
+    store_planes((__nv_bfloat16*)p.dz_albedo, m * ld + c, lo, d.albedo[c]);
+    store_planes((__nv_bfloat16*)p.dz_outer, m * ld + c, lo, d.diffuse_l[c]);
+    store_planes((__nv_bfloat16*)p.dz_outer, (M + m) * ld + c, lo, d.direct[c]);
+    store_planes((__nv_bfloat16*)p.dz_outer, (2 * M + m) * ld + c, lo, d.direct0[c]);
+    store_planes((__nv_bfloat16*)p.dz_inner, m * ld + c, lo, d.indirect[c]);
+    store_planes((__nv_bfloat16*)p.dz_inner, (M + m) * ld + c, lo, d.indirect0[c]);
+    store_planes((__nv_bfloat16*)p.dz_refrac, m * ld + c, lo, d.refrac[c]);
+  }
+  p.d_rough_raw[m] = d.rough;  // completed (and turned into planes) after shade_encode_bwd adds its share
+  p.d_nov[m] = d.nov;
+}
+
+// ------------------------------------------------------------------------------------------- SDF-net glue
+// out[m,n] = w[n] * (1 - exp(-100 a[m,n]))          (gs_7 = w_sdf . s_7)
+__global__ void rowvec_mask_kernel(const float* __restrict__ w, const __nv_bfloat16* __restrict__ a, int lda, int a_lo,
+                                   long long M, int N, __nv_bfloat16* out, int ldo, int o_lo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  long long m = idx / N;
+  int n = (int)(idx % N);
+  float av = load_planes(a, m * lda + n, a_lo);
+  store_planes(out, m * ldo + n, o_lo, w[n] * (1.0f - __expf(-100.0f * av)));
+}
+
+// u4 fp32 [M,256] -> gs3 planes (cols < 217 masked by s_3, rest 0) and g_skip fp32 [M,39]
+__global__ void sdf_skip_split_kernel(const float* __restrict__ u4, const __nv_bfloat16* __restrict__ a3, int lda,
+                                      int a_lo, long long M, __nv_bfloat16* gs3, int ldg, int g_lo, float* g_skip) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * 256) return;
+  long long m = idx >> 8;
+  int n = (int)(idx & 255);
+  float u = u4[idx];
+  if (n < 217) {
+    float av = load_planes(a3, m * lda + n, a_lo);
+    store_planes(gs3, m * ldg + n, g_lo, u * (1.0f - __expf(-100.0f * av)));
+  } else {
+    store_planes(gs3, m * ldg + n, g_lo, 0.f);
+    g_skip[m * 39 + (n - 217)] = u;
+  }
+}
+
+// reverse-over-reverse glue of one softplus layer:
+//   u_next = gts . s ;  e = gts . gs . 100 (1 - s)      with s = 1 - exp(-100 a)
+__global__ void sdf_bwd2_ew_kernel(const __nv_bfloat16* __restrict__ gts, int ldt, int t_lo,
+                                   const __nv_bfloat16* __restrict__ a, int lda, int a_lo,
+                                   const __nv_bfloat16* __restrict__ gs, int ldg, int g_lo, long long M, int N,
+                                   int n_real, __nv_bfloat16* u_next, int ldu, int u_lo, __nv_bfloat16* e, int lde,
+                                   int e_lo) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * N) return;
+  long long m = idx / N;
+  int n = (int)(idx % N);
+  float un = 0.f, ev = 0.f;
+  if (n < n_real) {
+    float t = load_planes(gts, m * ldt + n, t_lo);
+    float s = 1.0f - __expf(-100.0f * load_planes(a, m * lda + n, a_lo));
+    float g = load_planes(gs, m * ldg + n, g_lo);
+    un = t * s;
+    ev = t * g * 100.0f * (1.0f - s);
+  }
+  if (u_next && n < n_real) store_planes(u_next, m * ldu + n, u_lo, un);
+  store_planes(e, m * lde + n, e_lo, ev);
+}
+
+// fp32 [M, C] (+ optional second addend) -> planes at a column offset
+__global__ void f32_to_planes_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                                     long long M, int C, int width, __nv_bfloat16* dst, int ld, int lo, int col) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * width) return;
+  long long m = idx / width;
+  int c = (int)(idx % width);
+  float v = 0.f;
+  if (c < C) v = a[m * lda + c] + (b ? b[m * ldb + c] : 0.f);
+  store_planes(dst, m * ld + col + c, lo, v);
+}
+
+__global__ void adam_kernel(float* p, const float* __restrict__ g, float* m, float* v, long long n, float lr, float b1,
+                            float b2, float eps, float bc1, float bc2) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i];
+  float mi = b1 * m[i] + (1.0f - b1) * gi;
+  float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+  m[i] = mi; v[i] = vi;
+  // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+  p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+}
+
+// ------------------------------------------------------------------------------------------- grid sweep
+__global__ void grid_points_kernel(int res, long long start, long long count, const float* __restrict__ lin, float* pts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  long long g = start + i;
+  int zi = (int)(g % res), yi = (int)((g / res) % res), xi = (int)(g / ((long long)res * res));
+  pts[3 * i] = lin[xi]; pts[3 * i + 1] = lin[yi]; pts[3 * i + 2] = lin[zi];
+}
+__global__ void grid_mask_kernel(const float* __restrict__ pts, const float* __restrict__ sdf, int ld, long long count,
+                                 float outside, float* u) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float x = pts[3 * i], y = pts[3 * i + 1], z = pts[3 * i + 2];
+  float n = sqrtf(x * x + y * y + z * z);
+  u[i] = n >= 1.0f ? outside : sdf[i * ld];
+}
+
+}  // namespace nunerf
+
+using namespace nunerf;
+#define ST(s) ((cudaStream_t)(s))
+#define G1(n) cdiv((n), 256), 256
+
+extern "C" int nunerf_encode_pe(const float* x, int M, int d, int nfreq, void* dst, int ld, int lo_off, int col_off,
+                                int row_off, int width, void* stream) {
+  NUNERF_REQUIRE(x && dst && M > 0 && d > 0 && nfreq >= 0 && width >= d * (1 + 2 * nfreq), "encode_pe: bad arguments");
+  long long total = (long long)M * width;
+  encode_pe_kernel<<<G1(total), 0, ST(stream)>>>(x, M, d, nfreq, (__nv_bfloat16*)dst, ld, lo_off, col_off, row_off, width);
+  NUNERF_CHECK_LAUNCH("encode_pe_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_sdf_grad_pe(const float* x, const float* ga, int lda, const float* gb, int ldb, int M,
+                                  float* grad, void* stream) {
+  NUNERF_REQUIRE(x && ga && grad && M > 0, "sdf_grad_pe: bad arguments");
+  sdf_grad_pe_kernel<<<G1(M), 0, ST(stream)>>>(x, ga, lda, gb, ldb, M, grad);
+  NUNERF_CHECK_LAUNCH("sdf_grad_pe_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_sdf_grad_pe_bwd(const float* x, const float* dgrad, int M, void* d1, int ld1, int lo1, int col1,
+                                      int width1, void* d2, int ld2, int lo2, int col2, int width2, void* stream) {
+  NUNERF_REQUIRE(x && dgrad && M > 0 && (d1 || d2), "sdf_grad_pe_bwd: bad arguments");
+  int wmax = width1 > width2 ? width1 : width2;
+  long long total = (long long)M * wmax;
+  sdf_grad_pe_bwd_kernel<<<G1(total), 0, ST(stream)>>>(x, dgrad, M, (__nv_bfloat16*)d1, ld1, lo1, col1, width1,
+                                                      (__nv_bfloat16*)d2, ld2, lo2, col2, width2);
+  NUNERF_CHECK_LAUNCH("sdf_grad_pe_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_sdf_alpha_fwd(const nunerf_sdf_alpha_t* p, void* stream) {
+  NUNERF_REQUIRE(p && p->M > 0 && p->sdf && p->grad && p->dists && p->dirs && p->alpha && p->grad_err && p->inv_s_dev,
+                 "sdf_alpha_fwd: bad arguments");
+  sdf_alpha_fwd_kernel<<<G1(p->M), 0, ST(stream)>>>(*p);
+  NUNERF_CHECK_LAUNCH("sdf_alpha_fwd_kernel");
+  return 0;
+}
+extern "C" int nunerf_sdf_alpha_bwd(const nunerf_sdf_alpha_t* p, void* stream) {
+  NUNERF_REQUIRE(p && p->M > 0 && p->sdf && p->grad && p->dists && p->dirs && p->d_alpha && p->d_sdf && p->d_grad &&
+                     p->inv_s_dev,
+                 "sdf_alpha_bwd: bad arguments");
+  sdf_alpha_bwd_kernel<<<G1(p->M), 0, ST(stream)>>>(*p);
+  NUNERF_CHECK_LAUNCH("sdf_alpha_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_nerf_prep(const float* pts, const float* dirs, int M, float* pts4, float* views, void* stream) {
+  NUNERF_REQUIRE(pts && dirs && pts4 && views && M > 0, "nerf_prep: bad arguments");
+  nerf_prep_kernel<<<G1(M), 0, ST(stream)>>>(pts, dirs, M, pts4, views);
+  NUNERF_CHECK_LAUNCH("nerf_prep_kernel");
+  return 0;
+}
+extern "C" int nunerf_nerf_out_fwd(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
+                                   float* alpha, float* color, void* stream) {
+  NUNERF_REQUIRE(sigma && rgb && dists && alpha && color && M > 0, "nerf_out_fwd: bad arguments");
+  nerf_out_fwd_kernel<<<G1(M), 0, ST(stream)>>>(sigma, ld_s, rgb, ld_c, dists, M, alpha, color);
+  NUNERF_CHECK_LAUNCH("nerf_out_fwd_kernel");
+  return 0;
+}
+extern "C" int nunerf_nerf_out_bwd(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
+                                   const float* d_alpha, const float* d_color, void* d_sig, int ld_ds, int lo_ds,
+                                   int col_ds, void* d_rgb, int ld_dr, int lo_dr, int col_dr, void* stream) {
+  NUNERF_REQUIRE(sigma && rgb && dists && d_alpha && d_color && d_sig && d_rgb && M > 0, "nerf_out_bwd: bad arguments");
+  nerf_out_bwd_kernel<<<G1(M), 0, ST(stream)>>>(sigma, ld_s, rgb, ld_c, dists, M, d_alpha, d_color,
+                                               (__nv_bfloat16*)d_sig, ld_ds, lo_ds, col_ds, (__nv_bfloat16*)d_rgb, ld_dr,
+                                               lo_dr, col_dr);
+  NUNERF_CHECK_LAUNCH("nerf_out_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* stream) {
+  NUNERF_REQUIRE(p && p->M > 0 && p->pts && p->grad && p->dirs && p->rough_raw && p->x_outer && p->x_inner &&
+                     p->x_weight && p->x_refrac && p->nov,
+                 "shade_encode_fwd: bad arguments");
+  if (int r = ensure_ide()) return r;
+  shade_encode_fwd_kernel<<<G1(4LL * p->M), 0, ST(stream)>>>(*p);
+  NUNERF_CHECK_LAUNCH("shade_encode_fwd_kernel");
+  return 0;
+}
+extern "C" int nunerf_shade_encode_bwd(const nunerf_shade_encode_t* p, void* stream) {
+  NUNERF_REQUIRE(p && p->M > 0 && p->grad && p->dirs && p->rough_raw && p->d_x_outer && p->d_x_inner && p->d_nov &&
+                     p->d_grad && p->d_rough_raw,
+                 "shade_encode_bwd: bad arguments");
+  if (int r = ensure_ide()) return r;
+  shade_encode_bwd_kernel<<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
+  NUNERF_CHECK_LAUNCH("shade_encode_bwd_kernel");
+  return 0;
+}
+extern "C" int nunerf_ide_encode(const float* x, int M, float kinv, void* dst, int ld, int lo, int col, void* stream) {
+  NUNERF_REQUIRE(x && dst && M > 0, "ide_encode: bad arguments");
+  if (int r = ensure_ide()) return r;
+  ide_encode_kernel<<<cdiv(M, 128), 128, 0, ST(stream)>>>(x, M, kinv, (__nv_bfloat16*)dst, ld, lo, col);
+  NUNERF_CHECK_LAUNCH("ide_encode_kernel");
+  return 0;
+}
+extern "C" int nunerf_shade_mix_fwd(const nunerf_shade_mix_t* p, void* stream) {
+  NUNERF_REQUIRE(p && p->M > 0 && p->metallic && p->rough && p->albedo && p->trans && p->outer && p->inner &&
+                     p->weight && p->refrac && p->nov && p->lut && p->color && p->trans_out && p->metallic_out &&
+                     p->occ_prob,
+                 "shade_mix_fwd: bad arguments");
+  shade_mix_fwd_kernel<<<G1(p->M), 0, ST(stream)>>>(*p);
+  NUNERF_CHECK_LAUNCH("shade_mix_fwd_kernel");
+  return 0;
+}
+extern "C" int nunerf_shade_mix_bwd(const nunerf_shade_mix_t* p, void* stream) {
+  NUNERF_REQUIRE(p && p->M > 0 && p->d_color && p->dz_metallic && p->dz_albedo && p->dz_trans && p->dz_outer &&
+                     p->dz_inner && p->dz_weight && p->dz_refrac && p->d_rough_raw && p->d_nov,
+                 "shade_mix_bwd: bad arguments");
+  shade_mix_bwd_kernel<<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
+  NUNERF_CHECK_LAUNCH("shade_mix_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_rowvec_mask(const float* w, const void* a, int lda, int a_lo, int M, int N, void* out, int ldo,
+                                  int o_lo, void* stream) {
+  NUNERF_REQUIRE(w && a && out && M > 0 && N > 0, "rowvec_mask: bad arguments");
+  rowvec_mask_kernel<<<G1((long long)M * N), 0, ST(stream)>>>(w, (const __nv_bfloat16*)a, lda, a_lo, M, N,
+                                                             (__nv_bfloat16*)out, ldo, o_lo);
+  NUNERF_CHECK_LAUNCH("rowvec_mask_kernel");
+  return 0;
+}
+extern "C" int nunerf_sdf_skip_split(const float* u4, const void* a3, int lda, int a_lo, int M, void* gs3, int ldg,
+                                     int g_lo, float* g_skip, void* stream) {
+  NUNERF_REQUIRE(u4 && a3 && gs3 && g_skip && M > 0, "sdf_skip_split: bad arguments");
+  sdf_skip_split_kernel<<<G1((long long)M * 256), 0, ST(stream)>>>(u4, (const __nv_bfloat16*)a3, lda, a_lo, M,
+                                                                  (__nv_bfloat16*)gs3, ldg, g_lo, g_skip);
+  NUNERF_CHECK_LAUNCH("sdf_skip_split_kernel");
+  return 0;
+}
+extern "C" int nunerf_sdf_bwd2_ew(const void* gts, int ldt, int t_lo, const void* a, int lda, int a_lo, const void* gs,
+                                  int ldg, int g_lo, int M, int N, int n_real, void* u_next, int ldu, int u_lo, void* e,
+                                  int lde, int e_lo, void* stream) {
+  NUNERF_REQUIRE(gts && a && gs && e && M > 0 && N > 0, "sdf_bwd2_ew: bad arguments");
+  sdf_bwd2_ew_kernel<<<G1((long long)M * N), 0, ST(stream)>>>(
+      (const __nv_bfloat16*)gts, ldt, t_lo, (const __nv_bfloat16*)a, lda, a_lo, (const __nv_bfloat16*)gs, ldg, g_lo, M, N,
+      n_real, (__nv_bfloat16*)u_next, ldu, u_lo, (__nv_bfloat16*)e, lde, e_lo);
+  NUNERF_CHECK_LAUNCH("sdf_bwd2_ew_kernel");
+  return 0;
+}
+extern "C" int nunerf_f32_to_planes(const float* a, int lda, const float* b, int ldb, int M, int C, int width, void* dst,
+                                    int ld, int lo, int col, void* stream) {
+  NUNERF_REQUIRE(a && dst && M > 0 && C > 0 && width >= C, "f32_to_planes: bad arguments");
+  f32_to_planes_kernel<<<G1((long long)M * width), 0, ST(stream)>>>(a, lda, b, ldb, M, C, width, (__nv_bfloat16*)dst,
+                                                                   ld, lo, col);
+  NUNERF_CHECK_LAUNCH("f32_to_planes_kernel");
+  return 0;
+}
+extern "C" int nunerf_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
+                           float eps, int step, void* stream) {
+  NUNERF_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adam: bad arguments");
+  float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  adam_kernel<<<G1(n), 0, ST(stream)>>>(p, g, m, v, n, lr, b1, b2, eps, bc1, bc2);
+  NUNERF_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+extern "C" int nunerf_grid_points(int res, long long start, int count, const float* lin, float* pts, void* stream) {
+  NUNERF_REQUIRE(res > 1 && count > 0 && lin && pts, "grid_points: bad arguments");
+  grid_points_kernel<<<G1(count), 0, ST(stream)>>>(res, start, count, lin, pts);
+  NUNERF_CHECK_LAUNCH("grid_points_kernel");
+  return 0;
+}
+extern "C" int nunerf_grid_mask(const float* pts, const float* sdf, int ld_sdf, int count, float outside_val, float* u,
+                                void* stream) {
+  NUNERF_REQUIRE(pts && sdf && u && count > 0, "grid_mask: bad arguments");
+  grid_mask_kernel<<<G1(count), 0, ST(stream)>>>(pts, sdf, ld_sdf, count, outside_val, u);
+  NUNERF_CHECK_LAUNCH("grid_mask_kernel");
+  return 0;
+}

@@ -1,0 +1,311 @@
+// pointwise.cuh -- per-point math of the fields (forward and hand-derived backward), written as
+// __host__ __device__ functions so the same code is exercised by the CPU derivative checks
+// (tests/hostsim, test infrastructure only) and by the CUDA kernels in field.cu.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define PW_HD __host__ __device__ __forceinline__
+#else
+#define PW_HD inline
+#endif
+
+namespace nunerf {
+namespace pw {
+
+// ----------------------------------------------------------------------------- IDE tables
+// (m, l) pairs with l = 2^i, m = 0..l (utils/ref_utils.py:39-50) and the z-polynomial coefficients
+// mat[k][i] = sph_harm_coeff(l, m, k) (utils/ref_utils.py:71-81).
+constexpr int IDE_TERMS = 36;
+constexpr int IDE_DEG = 17;  // z^0 .. z^16
+struct IdeTable {
+  float mat[IDE_DEG][IDE_TERMS];
+  int m[IDE_TERMS];
+  int l[IDE_TERMS];
+  float sigma[IDE_TERMS];  // 0.5 * l * (l + 1)
+};
+
+inline void build_ide_table(IdeTable* t) {
+  auto fact = [](int n) { double r = 1; for (int i = 2; i <= n; ++i) r *= i; return r; };
+  int i = 0;
+  for (int e = 0; e < 5; ++e) {
+    int l = 1 << e;
+    for (int m = 0; m <= l; ++m, ++i) {
+      t->m[i] = m; t->l[i] = l; t->sigma[i] = 0.5f * l * (l + 1);
+      for (int k = 0; k < IDE_DEG; ++k) t->mat[k][i] = 0.f;
+      for (int k = 0; k <= l - m; ++k) {
+        // generalized binomial coefficient C(0.5*(l+k+m-1), l)
+        double a = 0.5 * (l + k + m - 1.0), gb = 1.0;
+        for (int j = 0; j < l; ++j) gb *= (a - j);
+        gb /= fact(l);
+        double leg = ((m & 1) ? -1.0 : 1.0) * pow(2.0, l) * fact(l) / fact(k) / fact(l - k - m) * gb;
+        double sh = sqrt((2.0 * l + 1.0) * fact(l - m) / (4.0 * M_PI * fact(l + m))) * leg;
+        t->mat[k][i] = (float)sh;
+      }
+    }
+  }
+}
+
+// out[0..35] = Re, out[36..71] = Im of (x+iy)^m P_i(z) exp(-sigma_i kinv)
+PW_HD void ide_fwd(const IdeTable& tb, float x, float y, float z, float kinv, float* out) {
+  float re[17], im[17];
+  re[0] = 1.f; im[0] = 0.f;
+  for (int m = 1; m <= 16; ++m) { re[m] = re[m - 1] * x - im[m - 1] * y; im[m] = re[m - 1] * y + im[m - 1] * x; }
+  for (int i = 0; i < IDE_TERMS; ++i) {
+    int deg = tb.l[i] - tb.m[i];
+    float p = tb.mat[deg][i];
+    for (int k = deg - 1; k >= 0; --k) p = p * z + tb.mat[k][i];
+    float a = expf(-tb.sigma[i] * kinv);
+    out[i] = re[tb.m[i]] * p * a;
+    out[IDE_TERMS + i] = im[tb.m[i]] * p * a;
+  }
+}
+
+PW_HD void ide_bwd(const IdeTable& tb, float x, float y, float z, float kinv, const float* dout, float* dx, float* dy,
+                   float* dz, float* dkinv) {
+  float re[17], im[17];
+  re[0] = 1.f; im[0] = 0.f;
+  for (int m = 1; m <= 16; ++m) { re[m] = re[m - 1] * x - im[m - 1] * y; im[m] = re[m - 1] * y + im[m - 1] * x; }
+  float gx = 0.f, gy = 0.f, gz = 0.f, gk = 0.f;
+  for (int i = 0; i < IDE_TERMS; ++i) {
+    int m = tb.m[i], deg = tb.l[i] - m;
+    float p = tb.mat[deg][i], dp = 0.f;
+    for (int k = deg - 1; k >= 0; --k) { dp = dp * z + p; p = p * z + tb.mat[k][i]; }
+    float a = expf(-tb.sigma[i] * kinv);
+    float dr = dout[i], di = dout[IDE_TERMS + i];
+    float s = dr * re[m] + di * im[m];
+    gz += s * a * dp;
+    gk += s * p * a * (-tb.sigma[i]);
+    if (m > 0) {
+      float dre = dr * p * a, dim = di * p * a, fm = (float)m;
+      gx += fm * (dre * re[m - 1] + dim * im[m - 1]);
+      gy += fm * (-dre * im[m - 1] + dim * re[m - 1]);
+    }
+  }
+  *dx = gx; *dy = gy; *dz = gz; *dkinv = gk;
+}
+
+// ----------------------------------------------------------------------------- small helpers
+PW_HD float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+PW_HD float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+PW_HD float srgb_fwd(float x) {  // utils/raw_utils.py:5-12
+  const float eps = 1.1920928955078125e-07f;
+  return x <= 0.0031308f ? (323.0f / 25.0f) * x : (211.0f * powf(fmaxf(x, eps), 5.0f / 12.0f) - 11.0f) / 200.0f;
+}
+PW_HD float srgb_bwd(float x) {
+  const float eps = 1.1920928955078125e-07f;
+  if (x <= 0.0031308f) return 323.0f / 25.0f;
+  if (x < eps) return 0.f;
+  return (211.0f / 200.0f) * (5.0f / 12.0f) * powf(x, -7.0f / 12.0f);
+}
+
+// positional encoding of one scalar coordinate layout: out index for (freq k, fn, dim c) with d dims:
+//   [x (d)] [sin(2^0 x) (d)] [cos(2^0 x) (d)] [sin(2^1 x) (d)] ...
+PW_HD int pe_index(int d, int k, int is_cos, int c) { return d + (2 * k + is_cos) * d + c; }
+
+// ----------------------------------------------------------------------------- sdf -> alpha (ZT:657-685, :769)
+struct SdfAlphaOut { float alpha, gerr; };
+PW_HD SdfAlphaOut sdf_alpha_fwd(float sdf, const float* g, float dist, const float* dir, float inv_s, float anneal) {
+  float tc = dir[0] * g[0] + dir[1] * g[1] + dir[2] * g[2];
+  float r1 = fmaxf(-tc * 0.5f + 0.5f, 0.f), r2 = fmaxf(-tc, 0.f);
+  float ic = -(r1 * (1.0f - anneal) + r2 * anneal);
+  float en = sdf + ic * dist * 0.5f, ep = sdf - ic * dist * 0.5f;
+  float pc = sigmoidf_(ep * inv_s), nc = sigmoidf_(en * inv_s);
+  float a = (pc - nc + 1e-5f) / (pc + 1e-5f);
+  float gn = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  SdfAlphaOut o;
+  o.alpha = clamp01(a);
+  o.gerr = (gn - 1.0f) * (gn - 1.0f);
+  return o;
+}
+PW_HD void sdf_alpha_bwd(float sdf, const float* g, float dist, const float* dir, float inv_s, float anneal,
+                         float d_alpha, float d_gerr, float* d_sdf, float* d_g, float* d_inv_s) {
+  float tc = dir[0] * g[0] + dir[1] * g[1] + dir[2] * g[2];
+  float q1 = -tc * 0.5f + 0.5f, q2 = -tc;
+  float r1 = fmaxf(q1, 0.f), r2 = fmaxf(q2, 0.f);
+  float ic = -(r1 * (1.0f - anneal) + r2 * anneal);
+  float en = sdf + ic * dist * 0.5f, ep = sdf - ic * dist * 0.5f;
+  float pc = sigmoidf_(ep * inv_s), nc = sigmoidf_(en * inv_s);
+  float num = pc - nc + 1e-5f, den = pc + 1e-5f;
+  float a = num / den;
+  float da = (a >= 0.f && a <= 1.f) ? d_alpha : 0.f;
+  float dnum = da / den, dden = -da * num / (den * den);
+  float dpc = dnum + dden, dnc = -dnum;
+  float dpa = dpc * pc * (1.0f - pc), dna = dnc * nc * (1.0f - nc);
+  float dep = dpa * inv_s, den_ = dna * inv_s;
+  *d_inv_s = dpa * ep + dna * en;
+  *d_sdf = dep + den_;
+  float dic = (den_ - dep) * dist * 0.5f;
+  float dr1 = -dic * (1.0f - anneal), dr2 = -dic * anneal;
+  float dtc = (q1 > 0.f ? dr1 * -0.5f : 0.f) + (q2 > 0.f ? -dr2 : 0.f);
+  float gn = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  float ge = gn > 0.f ? d_gerr * 2.0f * (gn - 1.0f) / gn : 0.f;
+  for (int c = 0; c < 3; ++c) d_g[c] = dtc * dir[c] + ge * g[c];
+}
+
+// ----------------------------------------------------------------------------- NeRF++ output (ZT:515-516, :691-692)
+PW_HD float softplus1(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+PW_HD void nerf_out_fwd(float sigma, const float* rgb, float dist, float* alpha, float* color) {
+  *alpha = 1.0f - expf(-softplus1(sigma) * dist);
+  for (int c = 0; c < 3; ++c) color[c] = srgb_fwd(expf(fminf(rgb[c], 5.0f)));
+}
+PW_HD void nerf_out_bwd(float sigma, const float* rgb, float dist, float d_alpha, const float* d_color, float* d_sigma,
+                        float* d_rgb) {
+  float sp = softplus1(sigma);
+  float dsp = d_alpha * expf(-sp * dist) * dist;
+  *d_sigma = dsp * (sigma > 20.f ? 1.0f : sigmoidf_(sigma));
+  for (int c = 0; c < 3; ++c) {
+    float e = expf(fminf(rgb[c], 5.0f));
+    d_rgb[c] = rgb[c] <= 5.0f ? d_color[c] * srgb_bwd(e) * e : 0.f;
+  }
+}
+
+// ----------------------------------------------------------------------------- shading directions (field.py:686-689)
+struct ShadeDirs { float n[3], v[3], r[3], nov, gn; };
+PW_HD ShadeDirs shade_dirs(const float* g, const float* raydir) {
+  ShadeDirs s;
+  s.gn = fmaxf(sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]), 1e-12f);
+  float vn = fmaxf(sqrtf(raydir[0] * raydir[0] + raydir[1] * raydir[1] + raydir[2] * raydir[2]), 1e-12f);
+  for (int c = 0; c < 3; ++c) { s.n[c] = g[c] / s.gn; s.v[c] = -raydir[c] / vn; }
+  s.nov = s.n[0] * s.v[0] + s.n[1] * s.v[1] + s.n[2] * s.v[2];
+  for (int c = 0; c < 3; ++c) s.r[c] = s.nov * s.n[c] * 2.0f - s.v[c];
+  return s;
+}
+// given d_r, d_n (direct), d_nov -> d_g
+PW_HD void shade_dirs_bwd(const ShadeDirs& s, const float* d_r, const float* d_n_direct, float d_nov, float* d_g) {
+  float ndr = s.n[0] * d_r[0] + s.n[1] * d_r[1] + s.n[2] * d_r[2];
+  float dn[3];
+  for (int c = 0; c < 3; ++c) dn[c] = d_n_direct[c] + 2.0f * s.v[c] * ndr + 2.0f * s.nov * d_r[c] + d_nov * s.v[c];
+  float ndn = s.n[0] * dn[0] + s.n[1] * dn[1] + s.n[2] * dn[2];
+  for (int c = 0; c < 3; ++c) d_g[c] = (dn[c] - s.n[c] * ndn) / s.gn;
+}
+
+// ----------------------------------------------------------------------------- FG LUT (dr.texture linear/clamp)
+PW_HD void fg_lookup(const float* lut, float u, float v, float* fg, float* dfg_du, float* dfg_dv) {
+  const int W = 256, H = 256;
+  float fx = u * W - 0.5f, fy = v * H - 0.5f;
+  bool cx = fx > 0.f && fx < (float)(W - 1), cy = fy > 0.f && fy < (float)(H - 1);
+  fx = fminf(fmaxf(fx, 0.f), (float)(W - 1));
+  fy = fminf(fmaxf(fy, 0.f), (float)(H - 1));
+  int x0 = (int)floorf(fx), y0 = (int)floorf(fy);
+  float tx = fx - x0, ty = fy - y0;
+  int x1 = x0 + 1 > W - 1 ? W - 1 : x0 + 1, y1 = y0 + 1 > H - 1 ? H - 1 : y0 + 1;
+  for (int c = 0; c < 2; ++c) {
+    float c00 = lut[(y0 * W + x0) * 2 + c], c01 = lut[(y0 * W + x1) * 2 + c];
+    float c10 = lut[(y1 * W + x0) * 2 + c], c11 = lut[(y1 * W + x1) * 2 + c];
+    fg[c] = (c00 * (1 - tx) + c01 * tx) * (1 - ty) + (c10 * (1 - tx) + c11 * tx) * ty;
+    if (dfg_du) {
+      dfg_du[c] = cx ? W * ((c01 - c00) * (1 - ty) + (c11 - c10) * ty) : 0.f;
+      dfg_dv[c] = cy ? H * ((c10 * (1 - tx) + c11 * tx) - (c00 * (1 - tx) + c01 * tx)) : 0.f;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- shading mix (field.py:691-741)
+struct ShadeMixIn {
+  float metallic, rough, albedo[3], trans;               // raw heads (pre-sigmoid)
+  float diffuse_l[3], direct[3], direct0[3];             // raw heads (pre-exp)
+  float indirect[3], indirect0[3], occ, refrac[3];
+  float nov;
+};
+struct ShadeMixOut { float color[3], trans, metallic, occ_prob; };
+
+PW_HD float exp_act(float x, float mx) { return expf(fminf(x, mx)); }
+
+PW_HD ShadeMixOut shade_mix_fwd(const ShadeMixIn& in, const float* lut, float exp_max) {
+  ShadeMixOut o;
+  float met = sigmoidf_(in.metallic), rough = sigmoidf_(in.rough), T = sigmoidf_(in.trans);
+  float occ = in.occ * 0.5f + 0.5f, oc = clamp01(occ);
+  float t = clamp01(1.0f - in.nov);
+  float rw = clamp01(0.04f + 0.96f * t * t * t * t * t);
+  float fg[2];
+  fg_lookup(lut, clamp01(in.nov), clamp01(rough), fg, nullptr, nullptr);
+  for (int c = 0; c < 3; ++c) {
+    float alb = sigmoidf_(in.albedo[c]);
+    float dl = exp_act(in.diffuse_l[c], exp_max), dr = exp_act(in.direct[c], exp_max),
+          d0 = exp_act(in.direct0[c], exp_max), il = exp_act(in.indirect[c], exp_max),
+          i0 = exp_act(in.indirect0[c], exp_max), rf = exp_act(in.refrac[c], exp_max);
+    float diffuse = (1.0f - met) * alb * dl;
+    float sa = 0.04f * (1.0f - met) + met * alb;
+    float light = il * oc + dr * (1.0f - oc), light0 = i0 * oc + d0 * (1.0f - oc);
+    float spec = (sa * fg[0] + fg[1]) * light;
+    float lin = (diffuse + spec) * (1.0f - T) + (rw * light0 + (1.0f - rw) * rf) * T;
+    o.color[c] = srgb_fwd(lin);
+  }
+  o.trans = T; o.metallic = met; o.occ_prob = occ;
+  return o;
+}
+
+// d_in receives gradients w.r.t. every raw head and nov
+PW_HD void shade_mix_bwd(const ShadeMixIn& in, const float* lut, float exp_max, const float* d_color, float d_trans_out,
+                         float d_met_out, ShadeMixIn* d_in) {
+  float met = sigmoidf_(in.metallic), rough = sigmoidf_(in.rough), T = sigmoidf_(in.trans);
+  float occ = in.occ * 0.5f + 0.5f, oc = clamp01(occ);
+  float t1 = 1.0f - in.nov, t = clamp01(t1);
+  float sch = 0.04f + 0.96f * t * t * t * t * t, rw = clamp01(sch);
+  float fg[2], dfu[2], dfv[2];
+  float un = clamp01(in.nov), vr = clamp01(rough);
+  fg_lookup(lut, un, vr, fg, dfu, dfv);
+  float d_met = 0.f, d_T = 0.f, d_oc = 0.f, d_rw = 0.f, d_fg0 = 0.f, d_fg1 = 0.f;
+  for (int c = 0; c < 3; ++c) {
+    float alb = sigmoidf_(in.albedo[c]);
+    float dl = exp_act(in.diffuse_l[c], exp_max), dr = exp_act(in.direct[c], exp_max),
+          d0 = exp_act(in.direct0[c], exp_max), il = exp_act(in.indirect[c], exp_max),
+          i0 = exp_act(in.indirect0[c], exp_max), rf = exp_act(in.refrac[c], exp_max);
+    float diffuse = (1.0f - met) * alb * dl;
+    float sa = 0.04f * (1.0f - met) + met * alb;
+    float light = il * oc + dr * (1.0f - oc), light0 = i0 * oc + d0 * (1.0f - oc);
+    float sref = sa * fg[0] + fg[1];
+    float spec = sref * light;
+    float mixB = rw * light0 + (1.0f - rw) * rf;
+    float lin = (diffuse + spec) * (1.0f - T) + mixB * T;
+    float dlin = d_color[c] * srgb_bwd(lin);
+    d_T += dlin * (mixB - (diffuse + spec));
+    float d_diffuse = dlin * (1.0f - T), d_spec = d_diffuse, d_mixB = dlin * T;
+    // diffuse = (1-met) alb dl
+    d_met += d_diffuse * (-alb * dl);
+    float d_alb = d_diffuse * (1.0f - met) * dl;
+    float d_dl = d_diffuse * (1.0f - met) * alb;
+    // spec = sref * light
+    float d_sref = d_spec * light, d_light = d_spec * sref;
+    float d_sa = d_sref * fg[0];
+    d_fg0 += d_sref * sa; d_fg1 += d_sref;
+    d_met += d_sa * (-0.04f + alb);
+    d_alb += d_sa * met;
+    // mixB
+    d_rw += d_mixB * (light0 - rf);
+    float d_light0 = d_mixB * rw, d_rf = d_mixB * (1.0f - rw);
+    // lights
+    float d_il = d_light * oc, d_dr = d_light * (1.0f - oc);
+    float d_i0 = d_light0 * oc, d_d0 = d_light0 * (1.0f - oc);
+    d_oc += d_light * (il - dr) + d_light0 * (i0 - d0);
+    // raw heads
+    d_in->albedo[c] = d_alb * alb * (1.0f - alb);
+    d_in->diffuse_l[c] = in.diffuse_l[c] <= exp_max ? d_dl * dl : 0.f;
+    d_in->direct[c] = in.direct[c] <= exp_max ? d_dr * dr : 0.f;
+    d_in->direct0[c] = in.direct0[c] <= exp_max ? d_d0 * d0 : 0.f;
+    d_in->indirect[c] = in.indirect[c] <= exp_max ? d_il * il : 0.f;
+    d_in->indirect0[c] = in.indirect0[c] <= exp_max ? d_i0 * i0 : 0.f;
+    d_in->refrac[c] = in.refrac[c] <= exp_max ? d_rf * rf : 0.f;
+  }
+  d_met += d_met_out;
+  d_T += d_trans_out;
+  d_in->metallic = d_met * met * (1.0f - met);
+  d_in->trans = d_T * T * (1.0f - T);
+  d_in->occ = (occ >= 0.f && occ <= 1.f) ? d_oc * 0.5f : 0.f;
+  // FG lookup: u = clamp(nov), v = clamp(rough)
+  float d_u = d_fg0 * dfu[0] + d_fg1 * dfu[1], d_v = d_fg0 * dfv[0] + d_fg1 * dfv[1];
+  float d_rough = (rough >= 0.f && rough <= 1.f) ? d_v : 0.f;
+  d_in->rough = d_rough * rough * (1.0f - rough);
+  float d_nov = (in.nov >= 0.f && in.nov <= 1.f) ? d_u : 0.f;
+  // schlick
+  float d_sch = (sch >= 0.f && sch <= 1.f) ? d_rw : 0.f;
+  float d_t = d_sch * 0.96f * 5.0f * t * t * t * t;
+  if (t1 >= 0.f && t1 <= 1.f) d_nov -= d_t;
+  d_in->nov = d_nov;
+}
+
+}  // namespace pw
+}  // namespace nunerf

@@ -1,0 +1,271 @@
+// sampling.cu -- per-ray warp-cooperative sampling kernels (stage-1 sample_ray, ZT:572-612).
+//
+// One warp owns one ray.  Sample j of a ray lives in lane (j & 31), block (j >> 5), so every global access of
+// a [R, n] row is a coalesced 128-byte request and no shared-memory staging is needed for the scans: each
+// block of 32 samples is scanned with 5 shuffle steps (Hillis-Steele) and chained through a scalar carry.
+//
+// Arithmetic contract (bit-exact against oracle/sampling_oracle.c): every fp32 operation is an explicitly
+// rounded __f{add,sub,mul,div}_rn (no FMA contraction), exp() is nunerf::det_exp, and the scan order is
+//   incl = HS32(v);  out_i = carry (op) shfl_up(incl, 1);  carry <- carry (op) incl_31      (exclusive product)
+//   cdf_i = carry + incl_i;  carry <- cdf_31                                                  (inclusive sum)
+//   total = butterfly xor-reduce over lanes of the per-lane sequential block sums.
+#include "common.cuh"
+
+namespace nunerf {
+
+constexpr int WARPS_PER_BLOCK = 4;
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float hs_scan_mul(float x, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    float t = __shfl_up_sync(FULL, x, off);
+    if (lane >= off) x = det_mul(t, x);
+  }
+  return x;
+}
+__device__ __forceinline__ float hs_scan_add(float x, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    float t = __shfl_up_sync(FULL, x, off);
+    if (lane >= off) x = det_add(t, x);
+  }
+  return x;
+}
+__device__ __forceinline__ float xor_reduce_add(float x) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) x = det_add(x, __shfl_xor_sync(FULL, x, off));
+  return x;
+}
+
+// tables: [0,64) linspace(0,1,64) | [64,96) bg lower | [96,128) bg (upper-lower) | [128,160) bg unperturbed
+__global__ void ray_setup_kernel(const float* __restrict__ o, const float* __restrict__ d, float* near, float* far,
+                                 const float* __restrict__ U0, const float* __restrict__ U1,
+                                 const float* __restrict__ tables, int R, int sphere, int perturb, float* z,
+                                 float* z_bg) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float nr, fr;
+  if (sphere) {
+    // ZT:320-327
+    float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
+    float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
+    float a = det_add(det_add(det_mul(dx, dx), det_mul(dy, dy)), det_mul(dz, dz));
+    float b = det_mul(2.0f, det_add(det_add(det_mul(ox, dx), det_mul(oy, dy)), det_mul(oz, dz)));
+    float mid = det_div(det_mul(0.5f, -b), a);
+    nr = fmaxf(det_sub(mid, 1.0f), 1e-3f);
+    fr = det_add(mid, 1.0f);
+    if (lane == 0) { near[r] = nr; far[r] = fr; }
+  } else {
+    nr = near[r];
+    fr = far[r];
+  }
+  const float span = det_sub(fr, nr);
+  float shift = 0.f;
+  if (perturb) shift = det_div(det_mul(det_sub(U0[r], 0.5f), 2.0f), 64.0f);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    int j = lane + 32 * k;
+    float v = det_add(nr, det_mul(span, tables[j]));
+    if (perturb) v = det_add(v, shift);
+    z[(long long)r * 64 + j] = v;
+  }
+  // background: far / flip(b) + 1/32  (ZT:582-594)
+  int jj = 31 - lane;
+  float b = perturb ? det_add(tables[64 + jj], det_mul(tables[96 + jj], U1[(long long)r * 32 + jj])) : tables[128 + jj];
+  z_bg[(long long)r * 32 + lane] = det_add(det_div(fr, b), 0.03125f);
+}
+
+__global__ void points_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
+                              long long total, int n, float* pts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long r = i / n;
+  float zz = z[i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) pts[3 * i + c] = det_add(o[3 * r + c], det_mul(d[3 * r + c], zz));
+}
+
+// One importance round.  n <= 128 samples in, n_new <= 32 out.
+__global__ void upsample_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
+                                const float* __restrict__ sdf, int R, int n, int n_new,
+                                const float* __restrict__ inv_s_dev, float inv_s_cap, const float* __restrict__ u_tab,
+                                float* z_new, int32_t* inds, float* z_merged, int32_t* perm) {
+  __shared__ float s_z[WARPS_PER_BLOCK][128];
+  __shared__ float s_cdf[WARPS_PER_BLOCK][132];
+  __shared__ float s_new[WARPS_PER_BLOCK][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + w;
+  if (r >= R) return;
+  const float inv_s = fminf(inv_s_dev[0], inv_s_cap);
+  const float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
+  const float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
+  const int nblk = (n + 31) >> 5;
+
+  // ---- load + radius
+  float zv[4], sv[4], rad[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int j = lane + 32 * k;
+    bool ok = k < nblk && j < n;
+    zv[k] = ok ? z[(long long)r * n + j] : 0.f;
+    sv[k] = ok ? sdf[(long long)r * n + j] : 0.f;
+    float px = det_add(ox, det_mul(dx, zv[k])), py = det_add(oy, det_mul(dy, zv[k])), pz = det_add(oz, det_mul(dz, zv[k]));
+    rad[k] = det_sqrt(det_add(det_add(det_mul(px, px), det_mul(py, py)), det_mul(pz, pz)));
+    if (ok) s_z[w][j] = zv[k];
+  }
+  __syncwarp();
+  // ---- per-section quantities; section j uses samples j, j+1 and the raw cosine of section j-1
+  float alpha[4], wgt[4];
+  float carry_prev_cos = 0.f;  // raw cosine of the last section of the previous block
+  float carryT = 1.0f;
+  float lane_sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int j = lane + 32 * k;
+    // neighbour j+1: lane+1 of this block, or lane 0 of the next block
+    float zn = __shfl_down_sync(FULL, zv[k], 1), sn = __shfl_down_sync(FULL, sv[k], 1),
+          rn = __shfl_down_sync(FULL, rad[k], 1);
+    float zn2 = __shfl_sync(FULL, k < 3 ? zv[k + 1 > 3 ? 3 : k + 1] : 0.f, 0);
+    float sn2 = __shfl_sync(FULL, k < 3 ? sv[k + 1 > 3 ? 3 : k + 1] : 0.f, 0);
+    float rn2 = __shfl_sync(FULL, k < 3 ? rad[k + 1 > 3 ? 3 : k + 1] : 0.f, 0);
+    if (lane == 31) { zn = zn2; sn = sn2; rn = rn2; }
+    const bool sec_ok = (j < n - 1);
+    float dist = det_sub(zn, zv[k]);
+    float cosv = det_div(det_sub(sn, sv[k]), det_add(dist, 1e-5f));
+    float prev = __shfl_up_sync(FULL, cosv, 1);
+    if (lane == 0) prev = carry_prev_cos;
+    carry_prev_cos = __shfl_sync(FULL, cosv, 31);
+    float c = fminf(prev, cosv);
+    c = fminf(fmaxf(c, -1e3f), 0.0f);
+    const bool inside = (rad[k] < 1.0f) || (rn < 1.0f);
+    c = inside ? c : det_mul(c, 0.0f);
+    float mid = det_mul(det_add(sv[k], sn), 0.5f);
+    float half = det_mul(det_mul(c, dist), 0.5f);
+    float pe = det_sub(mid, half), ne = det_add(mid, half);
+    float pc = det_sigmoid(det_mul(pe, inv_s)), nc = det_sigmoid(det_mul(ne, inv_s));
+    float a = det_div(det_add(det_sub(pc, nc), 1e-5f), det_add(pc, 1e-5f));
+    alpha[k] = sec_ok ? a : 0.f;
+    float v = sec_ok ? det_add(det_sub(1.0f, a), 1e-7f) : 1.0f;
+    float incl = hs_scan_mul(v, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float T = det_mul(carryT, excl);
+    carryT = det_mul(carryT, __shfl_sync(FULL, incl, 31));
+    wgt[k] = sec_ok ? det_add(det_mul(alpha[k], T), 1e-5f) : 0.f;  // sample_pdf's +1e-5 (field.py:471)
+    lane_sum = det_add(lane_sum, wgt[k]);
+  }
+  const float total = xor_reduce_add(lane_sum);
+  // ---- cdf = [0, cumsum(pdf)]
+  float carryC = 0.f;
+  if (lane == 0) s_cdf[w][0] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int j = lane + 32 * k;
+    float pdf = (j < n - 1) ? det_div(wgt[k], total) : 0.f;
+    float incl = hs_scan_add(pdf, lane);
+    float c = det_add(carryC, incl);
+    carryC = __shfl_sync(FULL, c, 31);
+    if (j < n - 1) s_cdf[w][j + 1] = c;
+  }
+  __syncwarp();
+  // ---- invert the cdf at n_new deterministic u's (field.py:476-496)
+  float zs = 0.f;
+  int ind = 0;
+  if (lane < n_new) {
+    const float u = u_tab[lane];
+    int lo = 0, hi = n;  // first index with cdf > u  (searchsorted right=True)
+    while (lo < hi) {
+      int m = (lo + hi) >> 1;
+      if (s_cdf[w][m] <= u) lo = m + 1; else hi = m;
+    }
+    ind = lo;
+    int below = ind - 1 < 0 ? 0 : ind - 1;
+    int above = ind > n - 1 ? n - 1 : ind;
+    float c0 = s_cdf[w][below], c1 = s_cdf[w][above];
+    float b0 = s_z[w][below], b1 = s_z[w][above];
+    float den = det_sub(c1, c0);
+    if (den < 1e-5f) den = 1.0f;
+    float t = det_div(det_sub(u, c0), den);
+    zs = det_add(b0, det_mul(t, det_sub(b1, b0)));
+    s_new[w][lane] = zs;
+    z_new[(long long)r * n_new + lane] = zs;
+    inds[(long long)r * n_new + lane] = ind;
+  }
+  __syncwarp();
+  // ---- stable merge (old samples first on ties): equals a stable sort of cat(z, z_new) (ZT:560-561)
+  const int nm = n + n_new;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    int j = lane + 32 * k;
+    if (j < n) {
+      int cnt = 0;
+      for (int t = 0; t < n_new; ++t) cnt += (s_new[w][t] < zv[k]) ? 1 : 0;
+      z_merged[(long long)r * nm + j + cnt] = zv[k];
+      perm[(long long)r * nm + j + cnt] = j;
+    }
+  }
+  if (lane < n_new) {
+    int lo = 0, hi = n;  // number of old samples <= zs
+    while (lo < hi) {
+      int m = (lo + hi) >> 1;
+      if (s_z[w][m] <= zs) lo = m + 1; else hi = m;
+    }
+    z_merged[(long long)r * nm + lane + lo] = zs;
+    perm[(long long)r * nm + lane + lo] = n + lane;
+  }
+}
+
+__global__ void merge_sdf_kernel(const float* __restrict__ sdf, const float* __restrict__ sdf_new,
+                                 const int32_t* __restrict__ perm, long long total, int n, int n_new, float* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int nm = n + n_new;
+  long long r = i / nm;
+  int src = perm[i];
+  out[i] = src < n ? sdf[r * n + src] : sdf_new[r * n_new + (src - n)];
+}
+
+}  // namespace nunerf
+
+using namespace nunerf;
+
+extern "C" int nunerf_ray_setup(const float* o, const float* d, float* near, float* far, const float* U0,
+                                const float* U1, const float* tables, int R, int sphere, int perturb, float* z,
+                                float* z_bg, void* stream) {
+  NUNERF_REQUIRE(o && d && near && far && tables && z && z_bg && R > 0, "ray_setup: bad arguments");
+  NUNERF_REQUIRE(!perturb || (U0 && U1), "ray_setup: perturb needs uniforms");
+  ray_setup_kernel<<<cdiv(R, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+      o, d, near, far, U0, U1, tables, R, sphere, perturb, z, z_bg);
+  NUNERF_CHECK_LAUNCH("ray_setup_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_points(const float* o, const float* d, const float* z, int R, int n, float* pts, void* stream) {
+  NUNERF_REQUIRE(o && d && z && pts && R > 0 && n > 0, "points: bad arguments");
+  long long total = (long long)R * n;
+  points_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(o, d, z, total, n, pts);
+  NUNERF_CHECK_LAUNCH("points_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_upsample(const float* o, const float* d, const float* z, const float* sdf, int R, int n,
+                               int n_new, const float* inv_s_dev, float inv_s_cap, const float* u_tab, float* z_new,
+                               int32_t* inds, float* z_merged, int32_t* perm, void* stream) {
+  NUNERF_REQUIRE(o && d && z && sdf && inv_s_dev && u_tab && z_new && inds && z_merged && perm, "upsample: null argument");
+  NUNERF_REQUIRE(R > 0 && n >= 2 && n <= 128 && n_new >= 1 && n_new <= 32, "upsample: need 2<=n<=128, 1<=n_new<=32");
+  upsample_kernel<<<cdiv(R, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+      o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
+  NUNERF_CHECK_LAUNCH("upsample_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_merge_sdf(const float* sdf, const float* sdf_new, const int32_t* perm, int R, int n, int n_new,
+                                float* sdf_merged, void* stream) {
+  NUNERF_REQUIRE(sdf && sdf_new && perm && sdf_merged && R > 0, "merge_sdf: bad arguments");
+  long long total = (long long)R * (n + n_new);
+  merge_sdf_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(sdf, sdf_new, perm, total, n, n_new, sdf_merged);
+  NUNERF_CHECK_LAUNCH("merge_sdf_kernel");
+  return 0;
+}

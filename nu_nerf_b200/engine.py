@@ -1,0 +1,617 @@
+"""Stage-1 render engine: orchestration of the sm_100a kernels for NeROShapeRenderer.render
+(reference network/renderer_zerothick.py:572-820, "ZT"; fields network/field.py).
+
+`sample_ray`      -- ZT:572-612, no-grad: ray set-up kernel, SDF-only MLP passes, 4 fused up-sample/merge rounds.
+`RenderCoreFn`    -- ZT:725-820 as ONE autograd node: the forward is an explicit launch sequence, the backward a
+                     hand-derived reverse sequence (incl. the reverse-over-reverse of SDFNetwork.gradient); torch
+                     only owns the parameters (weight-norm re-parametrisation happens outside, on tiny tensors).
+
+precision: "split" = bf16 hi/lo planes, 3 tcgen05 MMAs per product, fp32 accumulate (meets the 1e-4 / 1e-3 parity
+gates); "bf16" = single plane (the fast mode the benchmark reports; gradients within 2e-2).
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+from .ops import P, Dense, linear, linear_dw, colsum, to_planes, f32_to_planes, pad
+
+SQRT2 = math.sqrt(2.0)
+F32 = torch.float32
+
+
+def _f(*shape, dev):
+    return torch.empty(*shape, dtype=F32, device=dev)
+
+
+def _z(*shape, dev):
+    return torch.zeros(*shape, dtype=F32, device=dev)
+
+
+def sampling_tables(device):
+    """linspace tables of ZT:580-590 / field.py:477, computed with torch exactly as the reference does."""
+    t = torch.linspace(0.0, 1.0, 64)
+    b = torch.linspace(1e-3, 1.0 - 1.0 / 33.0, 32)
+    mids = 0.5 * (b[1:] + b[:-1])
+    upper = torch.cat([mids, b[-1:]])
+    lower = torch.cat([b[:1], mids])
+    return torch.cat([t, lower, upper - lower, b]).contiguous().to(device)
+
+
+# =============================================================================================== weights
+class SdfWeights:
+    """Operands of the 9 SDF layers (field.py:64-131).  lin4 is pre-scaled by 1/sqrt(2) (the skip concat
+    divides its input, field.py:143); lin8 is split into the feature rows (1..256) and the sdf row (0)."""
+
+    def __init__(self, Ws, bs, planes, head_only=False):
+        self.L = []
+        for l in range(8):
+            self.L.append(Dense(Ws[l], bs[l], planes, scale=(1.0 / SQRT2 if l == 4 else 1.0), need_t=not head_only))
+        W8, b8 = Ws[8], bs[8]
+        self.sdf_head = Dense(W8[0:1], b8[0:1], planes, need_t=False)
+        self.w_sdf = W8[0].detach().contiguous().float()
+        if not head_only:
+            # backward sees lin8 as one layer with rows ordered [features (256), sdf (1)]
+            self.feat = Dense(W8[1:], b8[1:], planes, need_t=False)
+            self.cat8 = Dense(torch.cat([W8[1:], W8[0:1]], 0), None, planes, need_t=True)
+
+
+class PredW:
+    """make_predictor (field.py:371-408): 4 dense layers."""
+
+    def __init__(self, Ws, bs, planes, need_dx0=True):
+        self.L = [Dense(Ws[i], bs[i], planes, need_t=(i > 0 or need_dx0)) for i in range(4)]
+        self.n_out = Ws[3].shape[0]
+
+
+class NerfW:
+    """NeRFNetwork (field.py:212-263).  Layer 5 input is stored [h (256) | PE (84)] so the previous layer can write
+    straight into it: its weight columns are permuted accordingly (reference order is [PE | h], field.py:276)."""
+
+    def __init__(self, sd, planes):
+        self.pts = []
+        for i in range(8):
+            W, b = sd[f"pts_linears.{i}.weight"], sd[f"pts_linears.{i}.bias"]
+            if i == 5:
+                W = torch.cat([W[:, 84:], W[:, :84]], 1)
+            self.pts.append(Dense(W, b, planes, need_t=(i > 0)))
+        Wf, bf = sd["feature_linear.weight"], sd["feature_linear.bias"]
+        Wa, ba = sd["alpha_linear.weight"], sd["alpha_linear.bias"]
+        self.feat = Dense(Wf, bf, planes, need_t=False)
+        self.alpha = Dense(Wa, ba, planes, need_t=False)
+        self.cat8 = Dense(torch.cat([Wf, Wa], 0), None, planes, need_t=True)
+        self.views = Dense(sd["views_linears.0.weight"], sd["views_linears.0.bias"], planes)
+        self.rgb = Dense(sd["rgb_linear.weight"], sd["rgb_linear.bias"], planes)
+
+
+# =============================================================================================== SDF network
+def sdf_infer(w: SdfWeights, pts, planes):
+    """sdf(x) only (SDFNetwork.sdf, field.py:152) for the sampling passes: 8 hidden layers + the 1-row head."""
+    M, dev = pts.shape[0], pts.device
+    x0 = P(M, 64, planes, dev)
+    call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, x0.ptr, x0.ld, x0.lo, 0, 0, 64)
+    a = P(M, 256, planes, dev)
+    b = P(M, 256, planes, dev)
+    cat = P(M, 256, planes, dev)
+    linear(x0, w.L[0].Wk, M, 256, 64, bias=w.L[0].b, act=2, out=a)
+    linear(a, w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=2, out=b)
+    linear(b, w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=2, out=a)
+    linear(a, w.L[3].Wk, M, 224, 256, bias=w.L[3].b, act=2, out=cat, n_store=217)
+    call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, cat.ptr, cat.ld, cat.lo, 217, 0, 39)
+    linear(cat, w.L[4].Wk, M, 256, 256, bias=w.L[4].b, act=2, out=a)
+    linear(a, w.L[5].Wk, M, 256, 256, bias=w.L[5].b, act=2, out=b)
+    linear(b, w.L[6].Wk, M, 256, 256, bias=w.L[6].b, act=2, out=a)
+    linear(a, w.L[7].Wk, M, 256, 256, bias=w.L[7].b, act=2, out=b)
+    out = _f(M, 16, dev=dev)
+    linear(b, w.sdf_head.Wk, M, 16, 256, bias=w.sdf_head.b, out_f32=out, n_store=1)
+    return out[:, 0]
+
+
+class SdfTape:
+    pass
+
+
+def sdf_forward(w: SdfWeights, pts, planes, xm: P):
+    """Full forward + the adjoint ("gradient") pass.  Writes the 256 features into xm[:, 0:256]; returns the tape
+    with sdf [M,16] (col 0), grad [M,3] and every activation needed by the backward."""
+    M, dev = pts.shape[0], pts.device
+    t = SdfTape()
+    t.M, t.pts = M, pts
+    t.x0 = P(M, 64, planes, dev)
+    call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, t.x0.ptr, t.x0.ld, t.x0.lo, 0, 0, 64)
+    A = [P(M, 256, planes, dev) for _ in range(8)]
+    t.A = A
+    linear(t.x0, w.L[0].Wk, M, 256, 64, bias=w.L[0].b, act=2, out=A[0])
+    linear(A[0], w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=2, out=A[1])
+    linear(A[1], w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=2, out=A[2])
+    linear(A[2], w.L[3].Wk, M, 224, 256, bias=w.L[3].b, act=2, out=A[3], n_store=217)   # A[3] = [a3 | PE]
+    call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, A[3].ptr, A[3].ld, A[3].lo, 217, 0, 39)
+    for l in range(4, 8):
+        linear(A[l - 1], w.L[l].Wk, M, 256, 256, bias=w.L[l].b, act=2, out=A[l])
+    linear(A[7], w.feat.Wk, M, 256, 256, bias=w.feat.b, out=xm, out_col=0)
+    t.sdf = _f(M, 16, dev=dev)
+    linear(A[7], w.sdf_head.Wk, M, 16, 256, bias=w.sdf_head.b, out_f32=t.sdf, n_store=1)
+    # ---- adjoint pass: gs_l = d sdf / d z_l
+    Gs = [P(M, 256, planes, dev) for _ in range(8)]
+    t.Gs = Gs
+    call("nunerf_rowvec_mask", w.w_sdf.data_ptr(), A[7].ptr, A[7].ld, A[7].lo, M, 256, Gs[7].ptr, Gs[7].ld, Gs[7].lo)
+    for l in (7, 6, 5):
+        linear(Gs[l], w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, out=Gs[l - 1])
+    u4 = _f(M, 256, dev=dev)
+    linear(Gs[4], w.L[4].WTk, M, 256, 256, out_f32=u4)
+    t.g_skip = _f(M, 39, dev=dev)
+    call("nunerf_sdf_skip_split", u4.data_ptr(), A[3].ptr, A[3].ld, A[3].lo, M, Gs[3].ptr, Gs[3].ld, Gs[3].lo,
+         t.g_skip.data_ptr())
+    for l in (3, 2, 1):
+        linear(Gs[l], w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, out=Gs[l - 1])
+    u0 = _f(M, 64, dev=dev)
+    linear(Gs[0], w.L[0].WTk, M, 64, 256, out_f32=u0)
+    t.grad = _f(M, 3, dev=dev)
+    call("nunerf_sdf_grad_pe", pts.data_ptr(), u0.data_ptr(), 64, t.g_skip.data_ptr(), 39, M, t.grad.data_ptr())
+    return t
+
+
+def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
+    """Backward of sdf_forward.  dxm[:, 0:256] holds d feat (planes); d_sdf [M], d_grad [M,3] fp32.
+    Returns (dW list for lin0..7, db list, dW8 [257,256], db8 [257])."""
+    M, dev = t.M, t.pts.device
+    A, Gs = t.A, t.Gs
+    dW = [w.L[l].new_grad() for l in range(8)]
+    db = [_z(256, dev=dev) for _ in range(8)]
+    # ---- (a) reverse of the adjoint pass (forward-like chain on u~), produces E_l and the gs (x) u~ weight terms
+    E = [P(M, 256, planes, dev) for _ in range(8)]
+    ut = P(M, 64, planes, dev)
+    ucat = P(M, 256, planes, dev)            # u~_4 = [u~ from layer 3 (217) | J d_grad (39)]
+    call("nunerf_sdf_grad_pe_bwd", t.pts.data_ptr(), d_grad.data_ptr(), M, ut.ptr, ut.ld, ut.lo, 0, 64,
+         ucat.ptr, ucat.ld, ucat.lo, 217, 39)
+    gts = P(M, 256, planes, dev)
+    u_a, u_b = P(M, 256, planes, dev), P(M, 256, planes, dev)
+    u_in, K_in = ut, 64
+    dw_sdf = _z(256, dev=dev)
+    for l in range(8):
+        N_l = 224 if l == 3 else 256
+        linear(u_in, w.L[l].Wk, M, N_l, K_in, out=gts)
+        linear_dw(Gs[l], u_in, M, 217 if l == 3 else 256, K_in, dW[l])
+        if l == 3:
+            u_next = ucat
+        elif l == 7:
+            u_next = u_a if u_in is not u_a else u_b
+        else:
+            u_next = u_a if u_in is not u_a else u_b
+        n_real = 217 if l == 3 else 256
+        call("nunerf_sdf_bwd2_ew", gts.ptr, gts.ld, gts.lo, A[l].ptr, A[l].ld, A[l].lo, Gs[l].ptr, Gs[l].ld, Gs[l].lo,
+             M, 256, n_real, u_next.ptr, u_next.ld, u_next.lo, E[l].ptr, E[l].ld, E[l].lo)
+        if l == 7:
+            colsum(u_next, M, 256, dw_sdf)       # d w_sdf = sum_m gts_7 . s_7
+        u_in, K_in = u_next, 256
+    # ---- (b) backward of the value network; dZ8 = [d feat (256) | d sdf | 0...]
+    f32_to_planes(d_sdf, dxm, M, 1, 64, col=256)
+    dW8 = torch.zeros(272, 256, dtype=F32, device=dev)
+    linear_dw(dxm, A[7], M, 256, 256, dW8)
+    dsdf_row = _z(16, 256, dev=dev)
+    linear_dw(dxm, A[7], M, 1, 256, dsdf_row, z_col=256)
+    db8c = _z(320, dev=dev)
+    colsum(dxm, M, 257, db8c)
+    dz = P(M, 256, planes, dev)
+    dz2 = P(M, 256, planes, dev, zero=True)
+    linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=dz)
+    cur, other = dz, dz2
+    for l in range(7, 0, -1):
+        n_l = 217 if l == 3 else 256
+        linear_dw(cur, A[l - 1], M, n_l, 256, dW[l])
+        colsum(cur, M, n_l, db[l])
+        if l == 4:
+            # input of lin4 is [a3 | PE]: only the first 217 columns carry on (PE has no parameters upstream)
+            nxt = P(M, 256, planes, dev, zero=True)
+            linear(cur, w.L[l].WTk, M, 224, 256, aux=A[3], aux_mode=2, add=E[3], out=nxt, n_store=217)
+            cur = nxt
+        else:
+            linear(cur, w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, add=E[l - 1], out=other)
+            cur, other = other, cur
+    linear_dw(cur, t.x0, M, 256, 64, dW[0])
+    colsum(cur, M, 256, db[0])
+    # assemble (undo the lin4 pre-scale and the lin8 row order)
+    gW = []
+    for l in range(8):
+        n, k = w.L[l].N, w.L[l].K
+        g = dW[l][:n, :k]
+        gW.append(g * w.L[l].scale if w.L[l].scale != 1.0 else g)
+    gb = [db[l][:w.L[l].N] for l in range(8)]
+    gW8 = torch.cat([(dsdf_row[0:1] + dw_sdf[None, :]), dW8[:256]], 0)
+    gb8 = torch.cat([db8c[256:257], db8c[:256]])
+    return gW, gb, gW8, gb8
+
+
+# =============================================================================================== predictors
+class PredTape:
+    pass
+
+
+def pred_forward(w: PredW, x: P, M, K0, planes):
+    dev = x.t.device
+    t = PredTape()
+    t.M, t.x, t.K0 = M, x, K0
+    t.H = [P(M, 256, planes, dev) for _ in range(3)]
+    linear(x, w.L[0].Wk, M, 256, K0, bias=w.L[0].b, act=1, out=t.H[0])
+    linear(t.H[0], w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=1, out=t.H[1])
+    linear(t.H[1], w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=1, out=t.H[2])
+    t.head = _f(M, 16, dev=dev)
+    linear(t.H[2], w.L[3].Wk, M, 16, 256, bias=w.L[3].b, out_f32=t.head, n_store=w.n_out)
+    return t
+
+
+def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None, dx_add=False, dx_f32=None, dx_n=0):
+    """dz_head: planes [M,64] (n_out real columns).  Optionally produces dX of the first layer either as planes
+    (accumulating when dx_add) or as fp32."""
+    M, dev = t.M, t.x.t.device
+    gW = [w.L[i].new_grad() for i in range(4)]
+    gb = [_z(w.L[i].Np, dev=dev) for i in range(4)]
+    linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3])
+    colsum(dz_head, M, w.n_out, gb[3])
+    d2, d1 = P(M, 256, planes, dev), P(M, 256, planes, dev)
+    linear(dz_head, w.L[3].WTk, M, 256, 64, aux=t.H[2], aux_mode=1, out=d2)
+    linear_dw(d2, t.H[1], M, 256, 256, gW[2]); colsum(d2, M, 256, gb[2])
+    linear(d2, w.L[2].WTk, M, 256, 256, aux=t.H[1], aux_mode=1, out=d1)
+    linear_dw(d1, t.H[0], M, 256, 256, gW[1]); colsum(d1, M, 256, gb[1])
+    linear(d1, w.L[1].WTk, M, 256, 256, aux=t.H[0], aux_mode=1, out=d2)
+    linear_dw(d2, t.x, M, 256, t.K0, gW[0]); colsum(d2, M, 256, gb[0])
+    if dx_planes is not None:
+        linear(d2, w.L[0].WTk, M, dx_n, 256, out=dx_planes, add=dx_planes if dx_add else None)
+    if dx_f32 is not None:
+        linear(d2, w.L[0].WTk, M, dx_n, 256, out_f32=dx_f32)
+    return [gW[i][:w.L[i].N, :w.L[i].K] for i in range(4)], [gb[i][:w.L[i].N] for i in range(4)]
+
+
+# =============================================================================================== NeRF++
+class NerfTape:
+    pass
+
+
+def nerf_forward(w: NerfW, pts, dirs, dists, planes):
+    """compute_density_alpha (ZT:687-693) on the compact outer samples -> alpha [M], colour [M,3]."""
+    M, dev = pts.shape[0], pts.device
+    t = NerfTape()
+    t.M, t.dists = M, dists
+    pts4, views = _f(M, 4, dev=dev), _f(M, 3, dev=dev)
+    call("nunerf_nerf_prep", pts.data_ptr(), dirs.data_ptr(), M, pts4.data_ptr(), views.data_ptr())
+    t.x0 = P(M, 128, planes, dev)
+    call("nunerf_encode_pe", pts4.data_ptr(), M, 4, 10, t.x0.ptr, t.x0.ld, t.x0.lo, 0, 0, 128)
+    H = [P(M, 256, planes, dev) for _ in range(8)]
+    H[4] = P(M, 384, planes, dev)                 # [h4 | PE(84) | 0]
+    t.H = H
+    call("nunerf_encode_pe", pts4.data_ptr(), M, 4, 10, H[4].ptr, H[4].ld, H[4].lo, 256, 0, 128)
+    linear(t.x0, w.pts[0].Wk, M, 256, 128, bias=w.pts[0].b, act=1, out=H[0])
+    for i in range(1, 8):
+        K = 384 if i == 5 else 256
+        linear(H[i - 1], w.pts[i].Wk, M, 256, K, bias=w.pts[i].b, act=1, out=H[i])
+    t.xv = P(M, 320, planes, dev)                 # [feature | PE4(view) (27) | 0]
+    linear(H[7], w.feat.Wk, M, 256, 256, bias=w.feat.b, out=t.xv)
+    call("nunerf_encode_pe", views.data_ptr(), M, 3, 4, t.xv.ptr, t.xv.ld, t.xv.lo, 256, 0, 64)
+    t.sigma = _f(M, 16, dev=dev)
+    linear(H[7], w.alpha.Wk, M, 16, 256, bias=w.alpha.b, out_f32=t.sigma, n_store=1)
+    t.hv = P(M, 128, planes, dev)
+    linear(t.xv, w.views.Wk, M, 128, 320, bias=w.views.b, act=1, out=t.hv)
+    t.rgb = _f(M, 16, dev=dev)
+    linear(t.hv, w.rgb.Wk, M, 16, 128, bias=w.rgb.b, out_f32=t.rgb, n_store=3)
+    alpha, color = _f(M, dev=dev), _f(M, 3, dev=dev)
+    call("nunerf_nerf_out_fwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, dists.data_ptr(), M, alpha.data_ptr(),
+         color.data_ptr())
+    return t, alpha, color
+
+
+def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
+    M, dev = t.M, t.dists.device
+    H = t.H
+    dz_rgb = P(M, 64, planes, dev, zero=True)
+    dz8 = P(M, 320, planes, dev, zero=True)
+    call("nunerf_nerf_out_bwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M, d_alpha.data_ptr(),
+         d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0)
+    g = {}
+    gw = w.rgb.new_grad(); gbv = _z(16, dev=dev)
+    linear_dw(dz_rgb, t.hv, M, 3, 128, gw); colsum(dz_rgb, M, 3, gbv)
+    g["rgb_linear.weight"], g["rgb_linear.bias"] = gw[:3, :128], gbv[:3]
+    dzv = P(M, 128, planes, dev)
+    linear(dz_rgb, w.rgb.WTk, M, 128, 64, aux=t.hv, aux_mode=1, out=dzv)
+    gw = w.views.new_grad(); gbv = _z(128, dev=dev)
+    linear_dw(dzv, t.xv, M, 128, 320, gw); colsum(dzv, M, 128, gbv)
+    g["views_linears.0.weight"], g["views_linears.0.bias"] = gw[:128, :283], gbv
+    linear(dzv, w.views.WTk, M, 256, 128, out=dz8)                       # d feature -> dz8[:, :256]
+    gw = torch.zeros(272, 256, dtype=F32, device=dev)
+    linear_dw(dz8, H[7], M, 256, 256, gw)
+    ga = _z(16, 256, dev=dev)
+    linear_dw(dz8, H[7], M, 1, 256, ga, z_col=256)
+    gbc = _z(320, dev=dev)
+    colsum(dz8, M, 257, gbc)
+    g["feature_linear.weight"], g["feature_linear.bias"] = gw[:256], gbc[:256]
+    g["alpha_linear.weight"], g["alpha_linear.bias"] = ga[0:1], gbc[256:257]
+    cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
+    linear(dz8, w.cat8.WTk, M, 256, 320, aux=H[7], aux_mode=1, out=cur)
+    for i in range(7, 0, -1):
+        K = 384 if i == 5 else 256
+        gw = w.pts[i].new_grad(); gbv = _z(256, dev=dev)
+        linear_dw(cur, H[i - 1], M, 256, K, gw); colsum(cur, M, 256, gbv)
+        if i == 5:
+            gwr = gw[:256, :340]
+            gw_ref = torch.cat([gwr[:, 256:], gwr[:, :256]], 1)     # back to the reference's [PE | h] column order
+        else:
+            gw_ref = gw[:256, :256]
+        g[f"pts_linears.{i}.weight"], g[f"pts_linears.{i}.bias"] = gw_ref, gbv
+        linear(cur, w.pts[i].WTk, M, 256, 256, aux=H[i - 1], aux_mode=1, out=other)
+        cur, other = other, cur
+    gw = w.pts[0].new_grad(); gbv = _z(256, dev=dev)
+    linear_dw(cur, t.x0, M, 256, 128, gw); colsum(cur, M, 256, gbv)
+    g["pts_linears.0.weight"], g["pts_linears.0.bias"] = gw[:256, :84], gbv
+    return g
+
+
+# =============================================================================================== sampling
+class Stage1Weights:
+    """All operands of one step, built from the (effective, fp32) weights in `W` -- a dict keyed like the
+    reference state_dict but with weight-norm already applied (`<layer>.weight`)."""
+
+    def __init__(self, Wd, planes, device):
+        self.planes = planes
+        sdfW = [Wd[f"sdf_network.lin{l}.weight"] for l in range(9)]
+        sdfb = [Wd[f"sdf_network.lin{l}.bias"] for l in range(9)]
+        self.sdf = SdfWeights(sdfW, sdfb, planes)
+        self.nerf = NerfW({k[len("outer_nerf."):]: v for k, v in Wd.items() if k.startswith("outer_nerf.")}, planes)
+        self.pred = {}
+        for name, need_dx0 in (("metallic_predictor", True), ("roughness_predictor", True), ("albedo_predictor", True),
+                               ("transmisstion_weight", True), ("outer_light", True), ("inner_light", True),
+                               ("inner_weight", False), ("refrac_light", False)):
+            pre = f"color_network.{name}"
+            self.pred[name] = PredW([Wd[f"{pre}.{i}.weight"] for i in (0, 2, 4, 6)],
+                                    [Wd[f"{pre}.{i}.bias"] for i in (0, 2, 4, 6)], planes, need_dx0=need_dx0)
+        self.inv_s = torch.exp(Wd["deviation_network.variance"].detach().float() * 10.0).reshape(1).contiguous()
+        self.lut = Wd["color_network.FG_LUT"].detach().float().contiguous()
+
+
+class SdfHeadWeights:
+    def __init__(self, Wd, planes):
+        sdfW = [Wd[f"sdf_network.lin{l}.weight"] for l in range(9)]
+        sdfb = [Wd[f"sdf_network.lin{l}.bias"] for l in range(9)]
+        self.sdf = SdfWeights(sdfW, sdfb, planes, head_only=True)
+        self.inv_s = torch.exp(Wd["deviation_network.variance"].detach().float() * 10.0).reshape(1).contiguous()
+
+
+_TABLES = {}
+
+
+def _tables(device):
+    key = str(device)
+    if key not in _TABLES:
+        _TABLES[key] = (sampling_tables(device),
+                        {n: torch.linspace(0.5 / n, 1.0 - 0.5 / n, n).to(device) for n in (16, 32, 64)})
+    return _TABLES[key]
+
+
+@torch.no_grad()
+def sample_ray(sw: SdfWeights, inv_s_dev, planes, rays_o, rays_d, near, far, perturb, U0=None, U1=None, sphere=False,
+               n_importance=64, up_steps=4, trace=None):
+    """ZT:572-612 -> z_vals [R,160].  U0 [R,1], U1 [R,32] are the uniform draws (torch.rand order of ZT:585,591)."""
+    R, dev = rays_o.shape[0], rays_o.device
+    tab, utabs = _tables(dev)
+    o, d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    near, far = near.reshape(-1).contiguous().float().clone(), far.reshape(-1).contiguous().float().clone()
+    z, z_bg = _f(R, 64, dev=dev), _f(R, 32, dev=dev)
+    call("nunerf_ray_setup", o.data_ptr(), d.data_ptr(), near.data_ptr(), far.data_ptr(), ptr(U0), ptr(U1),
+         tab.data_ptr(), R, int(sphere), int(perturb), z.data_ptr(), z_bg.data_ptr())
+    n = 64
+    pts = _f(R * n, 3, dev=dev)
+    call("nunerf_points", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, n, pts.data_ptr())
+    sdf = sdf_infer(sw, pts, planes).reshape(R, n).contiguous()
+    n_new = n_importance // up_steps
+    u_tab = utabs[n_new]
+    for i in range(up_steps):
+        z_new, inds = _f(R, n_new, dev=dev), torch.empty(R, n_new, dtype=torch.int32, device=dev)
+        z_m, perm = _f(R, n + n_new, dev=dev), torch.empty(R, n + n_new, dtype=torch.int32, device=dev)
+        call("nunerf_upsample", o.data_ptr(), d.data_ptr(), z.data_ptr(), sdf.data_ptr(), R, n, n_new,
+             inv_s_dev.data_ptr(), float(64 * 2 ** i), u_tab.data_ptr(), z_new.data_ptr(), inds.data_ptr(),
+             z_m.data_ptr(), perm.data_ptr())
+        if trace is not None:
+            trace[f"z_in_{i}"], trace[f"sdf_in_{i}"] = z, sdf
+            trace[f"z_new_{i}"], trace[f"inds_{i}"], trace[f"perm_{i}"], trace[f"z_merged_{i}"] = z_new, inds, perm, z_m
+        if i + 1 < up_steps:
+            npts = _f(R * n_new, 3, dev=dev)
+            call("nunerf_points", o.data_ptr(), d.data_ptr(), z_new.data_ptr(), R, n_new, npts.data_ptr())
+            sdf_new = sdf_infer(sw, npts, planes).reshape(R, n_new).contiguous()
+            sdf_m = _f(R, n + n_new, dev=dev)
+            call("nunerf_merge_sdf", sdf.data_ptr(), sdf_new.data_ptr(), perm.data_ptr(), R, n, n_new, sdf_m.data_ptr())
+            sdf = sdf_m
+        z, n = z_m, n + n_new
+    return torch.cat([z, z_bg], -1).contiguous()
+
+
+# =============================================================================================== render core
+class CoreTape:
+    pass
+
+
+_MAT = ("metallic_predictor", "roughness_predictor", "albedo_predictor", "transmisstion_weight")
+
+
+def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max):
+    """ZT:725-793 forward.  Returns the tape and the output tensors."""
+    planes = w.planes
+    R, S = z_vals.shape
+    dev = z_vals.device
+    t = CoreTape()
+    t.R, t.S, t.is_nerf, t.cos_anneal, t.exp_max = R, S, int(is_nerf), float(cos_anneal), float(exp_max)
+    o, d = rays_o.contiguous().float(), rays_d.contiguous().float()
+    z = z_vals.contiguous().float()
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    dists, pts = _f(R, S, dev=dev), _f(R, S, 3, dev=dev)
+    t.slot, counts, scratch = i32(R, S), i32(2), i32(2 * R)
+    cap = R * S
+    pts_in, dists_in, dirs_in, id_in = _f(cap, 3, dev=dev), _f(cap, dev=dev), _f(cap, 3, dev=dev), i32(cap)
+    pts_out, dists_out, dirs_out, id_out = _f(cap, 3, dev=dev), _f(cap, dev=dev), _f(cap, 3, dev=dev), i32(cap)
+    call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, dists.data_ptr(), pts.data_ptr(),
+         t.slot.data_ptr(), counts.data_ptr(), scratch.data_ptr(), pts_in.data_ptr(), dists_in.data_ptr(),
+         dirs_in.data_ptr(), id_in.data_ptr(), pts_out.data_ptr(), dists_out.data_ptr(), dirs_out.data_ptr(),
+         id_out.data_ptr())
+    n_in, n_out = (int(v) for v in counts.tolist())     # the one host sync of the step (output shapes need it)
+    t.n_in, t.n_out = n_in, n_out
+    t.pts_in, t.dists_in, t.dirs_in = pts_in[:n_in], dists_in[:n_in], dirs_in[:n_in]
+    t.pts, t.dists = pts, dists
+
+    # ---- outer samples: NeRF++ (ZT:743-751)
+    if n_out > 0:
+        t.nerf, t.a_out, t.c_out = nerf_forward(w.nerf, pts_out[:n_out], dirs_out[:n_out], dists_out[:n_out], planes)
+    else:
+        t.nerf, t.a_out, t.c_out = None, _z(1, dev=dev), _z(1, 3, dev=dev)
+
+    # ---- inner samples: SDF + shading (ZT:759-769)
+    M = n_in
+    if M > 0:
+        t.xm = P(M, 320, planes, dev)                                    # [feature (256) | p (3) | 0]
+        f32_to_planes(t.pts_in, t.xm, M, 3, 64, col=256)
+        t.sdf = sdf_forward(w.sdf, t.pts_in, planes, t.xm)
+        t.a_in, t.gerr = _f(M, dev=dev), _f(M, dev=dev)
+        sa = _lib.SdfAlphaT()
+        sa.M, sa.cos_anneal, sa.inv_s_dev = M, t.cos_anneal, w.inv_s.data_ptr()
+        sa.sdf, sa.ld_sdf, sa.grad, sa.dists, sa.dirs = t.sdf.sdf.data_ptr(), 16, t.sdf.grad.data_ptr(), \
+            t.dists_in.data_ptr(), t.dirs_in.data_ptr()
+        sa.alpha, sa.grad_err = t.a_in.data_ptr(), t.gerr.data_ptr()
+        call("nunerf_sdf_alpha_fwd", C.byref(sa))
+        # material predictors on [feature | p]
+        t.mat = {k: pred_forward(w.pred[k], t.xm, M, 320, planes) for k in _MAT}
+        # directions + encodings
+        t.xo, t.xi = P(3 * M, 128, planes, dev, zero=True), P(2 * M, 128, planes, dev, zero=True)
+        t.xw, t.xr = P(M, 128, planes, dev, zero=True), P(M, 128, planes, dev, zero=True)
+        t.nov = _f(M, dev=dev)
+        se = _lib.ShadeEncodeT()
+        se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.sdf.grad.data_ptr(), t.dirs_in.data_ptr()
+        se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
+        se.x_outer, se.ld_outer, se.lo_outer = t.xo.ptr, t.xo.ld, t.xo.lo
+        se.x_inner, se.ld_inner, se.lo_inner = t.xi.ptr, t.xi.ld, t.xi.lo
+        se.x_weight, se.ld_weight, se.lo_weight = t.xw.ptr, t.xw.ld, t.xw.lo
+        se.x_refrac, se.ld_refrac, se.lo_refrac = t.xr.ptr, t.xr.ld, t.xr.lo
+        se.nov = t.nov.data_ptr()
+        call("nunerf_shade_encode_fwd", C.byref(se))
+        t.lo_ = pred_forward(w.pred["outer_light"], t.xo, 3 * M, 128, planes)
+        t.li_ = pred_forward(w.pred["inner_light"], t.xi, 2 * M, 128, planes)
+        t.lw_ = pred_forward(w.pred["inner_weight"], t.xw, M, 128, planes)
+        t.lr_ = pred_forward(w.pred["refrac_light"], t.xr, M, 128, planes)
+        t.c_in, t.trans, t.metallic, t.occ = _f(M, 3, dev=dev), _f(M, dev=dev), _f(M, dev=dev), _f(M, dev=dev)
+        call("nunerf_shade_mix_fwd", C.byref(_mix_params(w, t)))
+    else:
+        t.a_in, t.c_in, t.gerr = _z(1, dev=dev), _z(1, 3, dev=dev), None
+
+    # ---- compositing (ZT:773-788)
+    rgb, t.rgb_raw, acc, bkgr = _f(R, 3, dev=dev), _f(R, 3, dev=dev), _f(R, dev=dev), _f(R, 3, dev=dev)
+    weights = _f(R, S, dev=dev)
+    call("nunerf_composite_fwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
+         t.slot.data_ptr(), R, S, t.is_nerf, rgb.data_ptr(), t.rgb_raw.data_ptr(), acc.data_ptr(), bkgr.data_ptr(),
+         weights.data_ptr())
+    # ---- per-ray specular probe: outer_light(IDE(d, 0)) (ZT:780-781), activation applied by the caller
+    t.xs = P(R, 128, planes, dev, zero=True)
+    t.dn = _norm_dirs(d)
+    call("nunerf_ide_encode", t.dn.data_ptr(), R, 0.0, t.xs.ptr, t.xs.ld, t.xs.lo, 0)
+    t.ls_ = pred_forward(w.pred["outer_light"], t.xs, R, 128, planes)
+    return t, rgb, acc, bkgr, weights
+
+
+def _norm_dirs(d):
+    # F.normalize(dirs) of ZT:740 for the [R,3] ray directions (tiny, once per step)
+    return (d / d.norm(dim=-1, keepdim=True).clamp_min(1e-12)).contiguous()
+
+
+def _mix_params(w, t, d_color=None, d_trans=None, d_met=None, dz=None, d_rough=None, d_nov=None):
+    M = t.n_in
+    mp = _lib.ShadeMixT()
+    mp.M, mp.exp_max = M, t.exp_max
+    mp.metallic, mp.rough = t.mat["metallic_predictor"].head.data_ptr(), t.mat["roughness_predictor"].head.data_ptr()
+    mp.albedo, mp.trans, mp.ld_mat = t.mat["albedo_predictor"].head.data_ptr(), \
+        t.mat["transmisstion_weight"].head.data_ptr(), 16
+    mp.outer, mp.ld_outer = t.lo_.head.data_ptr(), 16
+    mp.inner, mp.ld_inner = t.li_.head.data_ptr(), 16
+    mp.weight, mp.ld_weight = t.lw_.head.data_ptr(), 16
+    mp.refrac, mp.ld_refrac = t.lr_.head.data_ptr(), 16
+    mp.nov, mp.lut = t.nov.data_ptr(), w.lut.data_ptr()
+    mp.color, mp.trans_out, mp.metallic_out, mp.occ_prob = t.c_in.data_ptr(), t.trans.data_ptr(), \
+        t.metallic.data_ptr(), t.occ.data_ptr()
+    if d_color is not None:
+        mp.d_color, mp.d_trans_out, mp.d_metallic_out = d_color.data_ptr(), ptr(d_trans), ptr(d_met)
+        mp.dz_metallic, mp.dz_albedo, mp.dz_trans = dz["metallic"].ptr, dz["albedo"].ptr, dz["trans"].ptr
+        mp.dz_outer, mp.dz_inner, mp.dz_weight, mp.dz_refrac = dz["outer"].ptr, dz["inner"].ptr, dz["weight"].ptr, \
+            dz["refrac"].ptr
+        mp.ld_dz, mp.lo_dz = dz["metallic"].ld, dz["metallic"].lo
+        mp.d_rough_raw, mp.d_nov = d_rough.data_ptr(), d_nov.data_ptr()
+    return mp
+
+
+def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, want_inv_s):
+    """Reverse launch sequence of core_forward.  Returns {reference parameter name -> gradient of the EFFECTIVE
+    weight / bias} (+ 'inv_s')."""
+    planes, dev = w.planes, t.slot.device
+    R, S, M = t.R, t.S, t.n_in
+    g = {}
+    da_in, dc_in = _f(max(M, 1), dev=dev), _f(max(M, 1), 3, dev=dev)
+    da_out, dc_out = _f(max(t.n_out, 1), dev=dev), _f(max(t.n_out, 1), 3, dev=dev)
+    call("nunerf_composite_bwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
+         t.slot.data_ptr(), R, S, t.is_nerf, t.rgb_raw.data_ptr(), ptr(d_rgb), ptr(d_acc), ptr(d_bkgr),
+         da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
+    if t.n_out > 0:
+        for k, v in nerf_backward(w.nerf, t.nerf, da_out, dc_out, planes).items():
+            g["outer_nerf." + k] = v
+
+    def add_pred(name, gw, gb):
+        for j, i in enumerate((0, 2, 4, 6)):
+            kw, kb = f"color_network.{name}.{i}.weight", f"color_network.{name}.{i}.bias"
+            g[kw] = g[kw] + gw[j] if kw in g else gw[j]
+            g[kb] = g[kb] + gb[j] if kb in g else gb[j]
+
+    # ---- specular probe (outer_light on the ray directions)
+    if d_spec is not None:
+        dzs = P(R, 64, planes, dev, zero=True)
+        f32_to_planes(d_spec.contiguous(), dzs, R, 3, 64)
+        add_pred("outer_light", *pred_backward(w.pred["outer_light"], t.ls_, dzs, planes))
+    if M == 0:
+        return g
+    # ---- shading mix
+    dz = {k: P(M, 64, planes, dev, zero=True) for k in ("metallic", "albedo", "trans", "weight", "refrac")}
+    dz["outer"], dz["inner"] = P(3 * M, 64, planes, dev, zero=True), P(2 * M, 64, planes, dev, zero=True)
+    d_rough, d_nov = _f(M, dev=dev), _f(M, dev=dev)
+    call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov)))
+    dxo, dxi = _f(3 * M, 128, dev=dev), _f(2 * M, 128, dev=dev)
+    add_pred("outer_light", *pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128))
+    add_pred("inner_light", *pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128))
+    add_pred("inner_weight", *pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes))
+    add_pred("refrac_light", *pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes))
+    # ---- sdf -> alpha
+    d_sdf, d_grad = _f(M, dev=dev), _f(M, 3, dev=dev)
+    d_inv = _z(1, dev=dev) if want_inv_s else None
+    sa = _lib.SdfAlphaT()
+    sa.M, sa.cos_anneal, sa.inv_s_dev = M, t.cos_anneal, w.inv_s.data_ptr()
+    sa.sdf, sa.ld_sdf, sa.grad, sa.dists, sa.dirs = t.sdf.sdf.data_ptr(), 16, t.sdf.grad.data_ptr(), \
+        t.dists_in.data_ptr(), t.dirs_in.data_ptr()
+    sa.d_alpha, sa.d_grad_err = da_in.data_ptr(), ptr(d_gerr)
+    sa.d_sdf, sa.d_grad, sa.d_inv_s = d_sdf.data_ptr(), d_grad.data_ptr(), ptr(d_inv)
+    call("nunerf_sdf_alpha_bwd", C.byref(sa))
+    if want_inv_s:
+        g["inv_s"] = d_inv
+    # ---- directions / encodings (adds into d_grad and d_rough)
+    se = _lib.ShadeEncodeT()
+    se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.sdf.grad.data_ptr(), t.dirs_in.data_ptr()
+    se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
+    se.d_x_outer, se.ld_dxo, se.d_x_inner, se.ld_dxi = dxo.data_ptr(), 128, dxi.data_ptr(), 128
+    se.d_nov, se.d_grad, se.d_rough_raw, se.ld_drough = d_nov.data_ptr(), d_grad.data_ptr(), d_rough.data_ptr(), 1
+    call("nunerf_shade_encode_bwd", C.byref(se))
+    dz["rough"] = P(M, 64, planes, dev)
+    f32_to_planes(d_rough, dz["rough"], M, 1, 64)
+    # ---- material predictors, d feature accumulated in dxm[:, :256]
+    dxm = P(M, 320, planes, dev)
+    first = True
+    for name, key in (("metallic_predictor", "metallic"), ("roughness_predictor", "rough"),
+                      ("albedo_predictor", "albedo"), ("transmisstion_weight", "trans")):
+        add_pred(name, *pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first,
+                                      dx_n=256))
+        first = False
+    # ---- SDF network
+    gW, gb, gW8, gb8 = sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad)
+    for l in range(8):
+        g[f"sdf_network.lin{l}.weight"], g[f"sdf_network.lin{l}.bias"] = gW[l], gb[l]
+    g["sdf_network.lin8.weight"], g["sdf_network.lin8.bias"] = gW8, gb8
+    return g

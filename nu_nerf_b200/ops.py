@@ -1,0 +1,142 @@
+"""Thin Python wrappers over the C-ABI (nu_nerf_b200/_lib.py): plane buffers, dense layers, weight preparation.
+
+Nothing here computes on the CPU or with torch kernels beyond allocating / zero-filling device memory.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr
+
+BF16 = torch.bfloat16
+# NUNERF_GEMM_IMPL=simt selects the SIMT debug kernels (debugging aid only, never a fallback)
+GEMM_IMPL = 1 if os.environ.get("NUNERF_GEMM_IMPL", "tc") == "simt" else 0
+SMEM_B_BUDGET = 176 * 1024  # bytes of shared memory the resident weight tile may take (>= 3 activation stages left)
+
+
+def pad(n, m):
+    return (n + m - 1) // m * m
+
+
+class P:
+    """A bf16 plane matrix [rows, planes*w]: hi plane in columns [0,w), lo plane in [w,2w) when planes == 2."""
+    __slots__ = ("t", "rows", "w", "planes", "ld", "lo", "ptr")
+
+    def __init__(self, rows, w, planes, device, zero=False):
+        assert w % 8 == 0
+        self.rows, self.w, self.planes = rows, w, planes
+        self.ld = planes * w
+        self.lo = w if planes == 2 else 0
+        self.t = (torch.zeros if zero else torch.empty)(max(rows, 1), self.ld, dtype=BF16, device=device)
+        self.ptr = self.t.data_ptr()
+
+    def at(self, row=0, col=0):
+        return self.ptr + 2 * (row * self.ld + col)
+
+    def float(self, rows=None, cols=None):
+        """fp32 copy (hi + lo) -- for tests."""
+        rows = self.rows if rows is None else rows
+        cols = self.w if cols is None else cols
+        out = torch.empty(rows, cols, dtype=torch.float32, device=self.t.device)
+        call("nunerf_from_planes", self.ptr, rows, cols, self.ld, self.lo, out.data_ptr(), cols)
+        return out
+
+
+def to_planes(src, dst: P, rows, cols, transpose=False, scale=1.0, dst_rows=None, dst_cols=None, col_off=0, row_off=0):
+    """src fp32 [rows, cols] (contiguous) -> block of dst, zero padded."""
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    lr = cols if transpose else rows
+    lc = rows if transpose else cols
+    dst_rows = lr if dst_rows is None else dst_rows
+    dst_cols = lc if dst_cols is None else dst_cols
+    call("nunerf_to_planes", src.data_ptr(), rows, cols, src.stride(0) if src.dim() == 2 else cols, int(transpose),
+         float(scale), dst.ptr, dst_rows, dst_cols, dst.ld, dst.lo, col_off, row_off)
+
+
+def f32_to_planes(a, dst: P, M, C_, width, col=0, b=None):
+    call("nunerf_f32_to_planes", a.data_ptr(), a.stride(0) if a.dim() == 2 else 1, ptr(b),
+         (b.stride(0) if b.dim() == 2 else 1) if b is not None else 0, M, C_, width, dst.ptr, dst.ld, dst.lo, col)
+
+
+def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = None, aux_mode=0, aux_col=0,
+           add: P = None, add_col=0, out: P = None, out_col=0, out_f32=None, n_store=0, out_scale=1.0):
+    """out[:, out_col:out_col+N] = epi(A[:, a_col:a_col+K] @ B[b_row:b_row+N, :K]^T); splits N so the weight tile
+    stays resident in shared memory (see csrc/gemm.cu)."""
+    assert K % 64 == 0 and N % 16 == 0
+    planes_b = 2 if B.lo else 1
+    n_tile = min(256, (SMEM_B_BUDGET // (K * 2 * planes_b)) // 16 * 16)
+    assert n_tile >= 16
+    n_store = n_store if n_store else N
+    p = _lib.LinearT()
+    for n0 in range(0, N, n_tile):
+        nt = min(n_tile, N - n0)
+        if n0 >= n_store:
+            break
+        p.A, p.lda, p.a_lo_off = A.at(0, a_col), A.ld, A.lo
+        p.B, p.ldb, p.b_lo_off = B.at(b_row + n0, 0), B.ld, B.lo
+        p.M, p.N, p.K = M, nt, K
+        p.bias = (bias.data_ptr() + 4 * n0) if bias is not None else None
+        p.act = act
+        if aux is not None and aux_mode:
+            p.aux, p.ldaux, p.aux_lo_off, p.aux_mode = aux.at(0, aux_col + n0), aux.ld, aux.lo, aux_mode
+        else:
+            p.aux, p.ldaux, p.aux_lo_off, p.aux_mode = None, 0, 0, 0
+        if add is not None:
+            p.add, p.ldadd, p.add_lo_off = add.at(0, add_col + n0), add.ld, add.lo
+        else:
+            p.add, p.ldadd, p.add_lo_off = None, 0, 0
+        p.out_scale = out_scale
+        if out is not None:
+            p.out, p.ldo, p.out_lo_off = out.at(0, out_col + n0), out.ld, out.lo
+        else:
+            p.out, p.ldo, p.out_lo_off = None, 0, 0
+        if out_f32 is not None:
+            p.out_f32, p.ldo32 = out_f32.data_ptr() + 4 * n0, out_f32.stride(0)
+        else:
+            p.out_f32, p.ldo32 = None, 0
+        p.n_store = min(nt, n_store - n0)
+        p.impl = GEMM_IMPL
+        call("nunerf_linear", C.byref(p))
+
+
+def linear_dw(dZ: P, X: P, M, N, K, dW, *, z_col=0, x_col=0):
+    """dW[:N, :K] += dZ[:, z_col:z_col+N]^T @ X[:, x_col:x_col+K]   (dW fp32, pre-zeroed / accumulating)."""
+    assert K % 64 == 0
+    p = _lib.DwT()
+    p.dZ, p.ldz, p.z_lo_off = dZ.at(0, z_col), dZ.ld, dZ.lo
+    p.X, p.ldx, p.x_lo_off = X.at(0, x_col), X.ld, X.lo
+    p.M, p.N, p.K = M, N, K
+    p.dW, p.lddw = dW.data_ptr(), dW.stride(0)
+    p.impl = GEMM_IMPL
+    call("nunerf_linear_dw", C.byref(p))
+
+
+def colsum(Z: P, M, N, out, z_col=0):
+    call("nunerf_colsum", Z.at(0, z_col), Z.ld, Z.lo, M, N, out.data_ptr())
+
+
+class Dense:
+    """One dense layer's operands, re-materialised from the fp32 master weight every step:
+    Wk  [pad16(N), planes*pad64(K)]  K-major (forward:  Y = X W^T)
+    WTk [pad64(K), planes*pad64(N)]  K-major (backward: dX = dZ W)."""
+
+    def __init__(self, W, b, planes, scale=1.0, need_t=True):
+        W = W.detach().contiguous().float()
+        self.N, self.K = W.shape
+        self.Np, self.Kp, self.Np64 = pad(self.N, 16), pad(self.K, 64), pad(self.N, 64)
+        dev = W.device
+        self.Wk = P(self.Np, self.Kp, planes, dev)
+        to_planes(W, self.Wk, self.N, self.K, False, scale, self.Np, self.Kp)
+        self.WTk = None
+        if need_t:
+            self.WTk = P(self.Kp, self.Np64, planes, dev)
+            to_planes(W, self.WTk, self.N, self.K, True, scale, self.Kp, self.Np64)
+        self.b = b.detach().contiguous().float() if b is not None else None
+        self.scale = scale
+        if self.b is not None and self.Np != self.N:
+            self.b = torch.cat([self.b, torch.zeros(self.Np - self.N, device=dev)])
+
+    def new_grad(self):
+        return torch.zeros(self.Np, self.Kp, dtype=torch.float32, device=self.Wk.t.device)

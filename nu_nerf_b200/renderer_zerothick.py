@@ -1,0 +1,296 @@
+"""Drop-in boundary: the renderer classes of the reference's network/renderer_zerothick.py ("ZT"), backed by the
+sm_100a engine (nu_nerf_b200/engine.py).  Same class names, constructor `(cfg, training=True)`, parameter /
+state_dict names, `forward(data)`, `render(...)`, `sample_ray(...)`, `render_core(...)` signatures and outputs dict.
+
+What stays in torch: parameter storage, the weight-norm re-parametrisation of the (tiny) weight matrices, the
+charbonnier loss on [R,3] and scalar bookkeeping.  Everything per-sample runs in libnunerf_b200.so; there is no
+CPU or eager fallback (constructing a renderer without CUDA works -- parameters only -- but rendering raises).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .field import (SDFNetwork, SingleVarianceNetwork, NeRFNetwork, AppShadingNetwork, InfOutNetwork, WNLinear,
+                    PlainLinear)
+
+SPHEREPOT_STAGE1_CFG = {
+    # configs/shape/nerf/spherepot.yaml of the reference
+    "name": "spherepot", "network": "shape", "database_name": "nerf/spherepot", "apply_occ_loss": True,
+    "occ_loss_step": 15000, "is_nerf": True, "zero_thickness": True, "get_mask": False,
+    "loss": ["nerf_render", "eikonal", "std", "init_sdf_reg", "occ", "mask", "outer_reg"],
+    "val_metric": ["shape_render"], "key_metric_name": "psnr", "eikonal_weight": 0.1, "freeze_inv_s_step": 15000,
+    "train_dataset_type": "dummy", "dataset_dir": "./datasets", "optimizer_type": "adam", "lr_type": "warm_up_cos",
+    "lr_cfg": {}, "total_step": 200000, "val_interval": 5000, "save_interval": 1000, "train_log_step": 20,
+}
+
+
+def load_default_cfg():
+    return dict(SPHEREPOT_STAGE1_CFG)
+
+
+def load_cfg(path):
+    """utils/base_utils.py:319-321."""
+    import yaml
+    with open(path, "r") as f:
+        return yaml.load(f, Loader=yaml.FullLoader)
+
+
+def linear_to_srgb(x):
+    """utils/raw_utils.py:5-12 (used on tiny per-ray tensors only)."""
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.0031308, 323.0 / 25.0 * x, (211.0 * torch.clamp(x, min=eps) ** (5.0 / 12.0) - 11.0) / 200.0)
+
+
+def _engine():
+    from . import engine
+    return engine
+
+
+class _RenderCoreFn(torch.autograd.Function):
+    """ZT:725-793 as one autograd node (see engine.core_forward / core_backward)."""
+
+    @staticmethod
+    def forward(ctx, pack, inv_s, *weights):
+        eng = _engine()
+        w, names, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_inv_s = pack
+        t, rgb, acc, bkgr, wts = eng.core_forward(w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max)
+        ctx.tape, ctx.w, ctx.names, ctx.want_inv_s = t, w, names, want_inv_s
+        dev = rgb.device
+        if t.n_in > 0:
+            gerr, trans, met, occ = t.gerr, t.trans[:, None], t.metallic[:, None], t.occ[:, None]
+        else:
+            gerr, trans, met, occ = (torch.zeros(1, device=dev), torch.zeros(0, 1, device=dev),
+                                     torch.zeros(0, 1, device=dev), torch.zeros(0, 1, device=dev))
+        spec = t.ls_.head[:, :3].clone()
+        ctx.mark_non_differentiable(wts, occ)
+        return rgb, acc, bkgr, gerr, trans, met, spec, wts, occ
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, _dw, _docc):
+        eng = _engine()
+        t = ctx.tape
+        c = lambda x: None if x is None else x.contiguous().float()
+        has = t.n_in > 0
+        g = eng.core_backward(ctx.w, t, c(d_rgb), c(d_acc), c(d_bkgr), c(d_gerr) if has else None,
+                              c(d_trans).reshape(-1) if (has and d_trans is not None) else None,
+                              c(d_met).reshape(-1) if (has and d_met is not None) else None, c(d_spec), ctx.want_inv_s)
+        grads = [g.get(name) for name in ctx.names]
+        ctx.tape = None
+        return (None, g.get("inv_s").reshape(()) if ctx.want_inv_s and "inv_s" in g else None, *grads)
+
+
+class NeROShapeRenderer(nn.Module):
+    default_cfg = {
+        # standard deviation for opacity density
+        "std_net": "default", "std_act": "exp", "inv_s_init": 0.3, "freeze_inv_s_step": None,
+        # geometry network
+        "sdf_net": "default", "sdf_activation": "none", "sdf_bias": 0.5, "sdf_n_layers": 8, "sdf_freq": 6,
+        "sdf_d_out": 257, "geometry_init": True,
+        # shader network
+        "shader_config": {},
+        # sampling strategy
+        "n_samples": 64, "n_bg_samples": 32, "inf_far": 1000.0, "n_importance": 64, "up_sample_steps": 4,
+        "perturb": 1.0, "anneal_end": 50000, "train_ray_num": 512, "test_ray_num": 1024,
+        "clip_sample_variance": True, "is_nerf": False,
+        # dataset
+        "database_name": "nerf_synthetic/lego/black_800",
+        # validation
+        "test_downsample_ratio": True, "downsample_ratio": 0.5, "val_geometry": False,
+        # losses
+        "rgb_loss": "charbonier", "apply_occ_loss": True, "occ_loss_step": 20000, "occ_loss_max_pn": 2048,
+        "occ_sdf_thresh": 0.01,
+        "fixed_camera": False,
+        # B200 engine: "split" (fp32-accurate, 3 MMAs per product) or "bf16" (fast)
+        "precision": "split",
+    }
+
+    def __init__(self, cfg, training=True):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        self.is_nerf = self.cfg["is_nerf"]
+        if (self.cfg["sdf_n_layers"], self.cfg["sdf_freq"], self.cfg["sdf_d_out"]) != (8, 6, 257):
+            raise NotImplementedError("the B200 engine is built for the 8x256 / PE-6 / 257-output SDF network")
+        if (self.cfg["n_samples"], self.cfg["n_bg_samples"], self.cfg["n_importance"], self.cfg["up_sample_steps"]) \
+                != (64, 32, 64, 4) or not self.cfg["clip_sample_variance"]:
+            raise NotImplementedError("sampling kernels are built for 64 + 4x16 + 32 samples with clipped variance")
+        self.sdf_network = SDFNetwork(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=(4,), multires=6,
+                                      bias=self.cfg["sdf_bias"], scale=1.0, geometric_init=self.cfg["geometry_init"])
+        self.deviation_network = SingleVarianceNetwork(init_val=self.cfg["inv_s_init"], activation=self.cfg["std_act"])
+        self.outer_nerf = NeRFNetwork(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, skips=(4,))
+        nn.init.constant_(self.outer_nerf.rgb_linear.bias, np.log(0.5))
+        self.color_network = AppShadingNetwork(self.cfg["shader_config"])
+        self.infinity_far_bkgr = InfOutNetwork()
+        self.ray_source = None       # callable(step, n) -> dict(rays_o, rays_d, rgbs) ; replaces the image database
+        if training:
+            self._init_dataset()
+
+    # ------------------------------------------------------------------ data
+    def _init_dataset(self):
+        """The reference builds the ray table from an image database here (ZT:167-197).  Dataset ingest is outside
+        the hot path: attach a ray source with `set_ray_source` (bench.py / the trainer adapter do)."""
+        self.ray_source = None
+
+    def set_ray_source(self, fn):
+        self.ray_source = fn
+
+    # ------------------------------------------------------------------ helpers identical to the reference
+    def get_anneal_val(self, step):
+        if self.cfg["anneal_end"] < 0:
+            return 1.0
+        return np.min([1.0, step / self.cfg["anneal_end"]])
+
+    @staticmethod
+    def near_far_from_sphere(rays_o, rays_d):
+        a = torch.sum(rays_d ** 2, dim=-1, keepdim=True)
+        b = 2.0 * torch.sum(rays_o * rays_d, dim=-1, keepdim=True)
+        mid = 0.5 * (-b) / a
+        return torch.clamp(mid - 1.0, min=1e-3), mid + 1.0
+
+    def compute_rgb_loss(self, rgb_pr, rgb_gt):
+        kind = self.cfg["rgb_loss"]
+        if kind == "l2":
+            return torch.sum((rgb_pr - rgb_gt) ** 2, -1)
+        if kind == "l1":
+            return torch.sum(F.l1_loss(rgb_pr, rgb_gt, reduction="none"), -1)
+        if kind == "smooth_l1":
+            return torch.sum(F.smooth_l1_loss(rgb_pr, rgb_gt, reduction="none", beta=0.25), -1)
+        if kind == "charbonier":
+            return torch.sqrt(torch.sum((rgb_gt - rgb_pr) ** 2, dim=-1) + 0.001)
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ weights
+    def effective_weights(self):
+        """{reference state_dict-style name -> effective fp32 tensor}: weight-norm applied (`W = g v / |v|`)."""
+        Wd = {}
+        for name, mod in self.named_modules():
+            if isinstance(mod, WNLinear):
+                Wd[name + ".weight"] = mod.effective_weight()
+                Wd[name + ".bias"] = mod.bias
+            elif isinstance(mod, PlainLinear):
+                Wd[name + ".weight"] = mod.weight
+                Wd[name + ".bias"] = mod.bias
+        Wd["deviation_network.variance"] = self.deviation_network.variance
+        Wd["color_network.FG_LUT"] = self.color_network.FG_LUT
+        return Wd
+
+    def _planes(self):
+        p = self.cfg["precision"]
+        if p not in ("split", "bf16"):
+            raise NotImplementedError(f"precision {p}")
+        return 2 if p == "split" else 1
+
+    def _prepare(self):
+        if not torch.cuda.is_available() or self.deviation_network.variance.device.type != "cuda":
+            raise RuntimeError("nu_nerf_b200 renders on a CUDA device only (no CPU fallback): move the module with .cuda()")
+        eng = _engine()
+        Wd = self.effective_weights()
+        w = eng.Stage1Weights(Wd, self._planes(), self.deviation_network.variance.device)
+        return Wd, w
+
+    # ------------------------------------------------------------------ ZT:572-612
+    def sample_ray(self, rays_o, rays_d, near, far, perturb, uniforms=None, prepared=None, trace=None, sphere=False):
+        eng = _engine()
+        _, w = prepared if prepared is not None else self._prepare()
+        R, dev = rays_o.shape[0], rays_o.device
+        U0 = U1 = None
+        if perturb > 0:
+            if uniforms is not None:
+                U0, U1 = (u.contiguous().float() for u in uniforms)
+            else:
+                U0 = torch.rand([R, 1], device=dev)       # same draw order as ZT:585, :591
+                U1 = torch.rand([R, 32], device=dev)
+        return eng.sample_ray(w.sdf, w.inv_s, w.planes, rays_o, rays_d, near, far, perturb > 0, U0, U1, sphere=sphere,
+                              trace=trace)
+
+    # ------------------------------------------------------------------ ZT:725-820
+    def render_core(self, rays_o, rays_d, z_vals, human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True,
+                    is_nerf=False, prepared=None):
+        Wd, w = prepared if prepared is not None else self._prepare()
+        names = [k for k in Wd if k not in ("deviation_network.variance", "color_network.FG_LUT")
+                 and not k.startswith("infinity_far_bkgr") and not k.startswith("color_network.iors")]
+        freeze = self.cfg["freeze_inv_s_step"]
+        frozen = freeze is not None and step is not None and step < freeze
+        inv_s = torch.exp(self.deviation_network.variance * 10.0)
+        exp_max = self.color_network.cfg["light_exp_max"]
+        pack = (w, names, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen)
+        rgb, acc, bkgr, gerr, trans, met, spec, weights, occ = _RenderCoreFn.apply(pack, inv_s, *[Wd[k] for k in names])
+        inv_s_c = inv_s.clip(1e-6, 1e6)
+        if frozen:
+            inv_s_c = inv_s_c.detach()
+        has_inner = trans.shape[0] > 0
+        outputs = {
+            "ray_rgb": rgb, "gradient_error": gerr, "acc": acc, "color_bkgr": bkgr,
+            "color_spec": linear_to_srgb(torch.exp(torch.clamp(spec, max=exp_max))),
+            "std": torch.mean(1.0 / inv_s_c) if has_inner else torch.zeros(1, device=rgb.device),
+        }
+        if has_inner:
+            outputs["transmission"] = trans
+            outputs["metallic"] = met
+        if self.cfg["apply_occ_loss"]:
+            if step is not None and step >= self.cfg["occ_loss_step"] and has_inner:
+                raise NotImplementedError("occlusion-probe loss (ZT:695-723) is a 'next' row (SURVEY 8f rank 4); "
+                                          "run with step < occ_loss_step or apply_occ_loss False")
+            outputs["loss_occ"] = torch.zeros(1, device=rgb.device)
+        if step is not None and step < 1000:
+            raise NotImplementedError("sdf_pts / sdf_vals warm-up outputs (ZT:804-807, step < 1000)")
+        if not is_train:
+            outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=(Wd, w)))
+        outputs["_weights"] = weights
+        return outputs
+
+    def compute_validation_info(self, z_vals, rays_o, rays_d, weights, human_poses, step, prepared=None):
+        """ZT:636-655: depth = sum w z ; normal = (normalize(grad sdf(o + depth d)) + 1) / 2 inside the unit sphere."""
+        eng = _engine()
+        _, w = prepared if prepared is not None else self._prepare()
+        with torch.no_grad():
+            depth = torch.sum(weights * z_vals, -1, keepdim=True)
+            points = (depth * rays_d + rays_o).contiguous()
+            xm = eng.P(points.shape[0], 320, w.planes, points.device)
+            tape = eng.sdf_forward(w.sdf, points, w.planes, xm)
+            inner = torch.norm(points, dim=-1, keepdim=True) <= 1.0
+            normal = ((F.normalize(tape.grad, dim=-1) + 1.0) * 0.5) * inner
+        return {"depth": depth, "normal": normal}
+
+    # ------------------------------------------------------------------ ZT:614-634
+    def render(self, rays_o, rays_d, near, far, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,
+               is_train=True, step=None, is_nerf=False, uniforms=None):
+        perturb = self.cfg["perturb"]
+        if perturb_overwrite >= 0:
+            perturb = perturb_overwrite
+        prepared = self._prepare()
+        z_vals = self.sample_ray(rays_o, rays_d, near, far, perturb, uniforms=uniforms, prepared=prepared)
+        return self.render_core(rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step,
+                                is_train=is_train, is_nerf=is_nerf, prepared=prepared)
+
+    # ------------------------------------------------------------------ ZT:447-466
+    def train_step(self, step):
+        if self.ray_source is None:
+            raise RuntimeError("no ray source attached: call set_ray_source(fn) (dataset ingest is outside the hot path)")
+        rn = self.cfg["train_ray_num"]
+        batch = self.ray_source(step, rn)
+        rays_o = batch["rays_o"]
+        rays_d = F.normalize(batch["rays_d"], dim=-1)
+        if self.is_nerf:
+            near = torch.full((rays_o.shape[0], 1), 0.8, device=rays_o.device)
+            far = torch.full((rays_o.shape[0], 1), 4.5, device=rays_o.device)
+        else:
+            near, far = self.near_far_from_sphere(rays_o, rays_d)
+        outputs = self.render(rays_o, rays_d, near, far, None, -1, self.get_anneal_val(step), is_train=True, step=step,
+                              is_nerf=self.is_nerf, uniforms=batch.get("uniforms"))
+        outputs["loss_rgb"] = self.compute_rgb_loss(outputs["ray_rgb"], batch["rgbs"])
+        return outputs
+
+    def forward(self, data):
+        step = data["step"]
+        if "eval" in data:
+            raise NotImplementedError("test_step needs the image database (dataset ingest is outside the hot path); "
+                                      "use render(..., is_train=False) on rays")
+        out = self.train_step(step)
+        out.pop("_weights", None)
+        return out
+
+
+name2renderer = {
+    "shape": NeROShapeRenderer,
+}

@@ -1,0 +1,178 @@
+"""Ray / mesh tracing objects with the reference's tracer interfaces.
+
+  TriangleBVH   -- host-built 4-wide BVH + the sm_100a traversal kernel (csrc/bvh.cu)
+  optix_mesh    -- drop-in for network/tracing_optix.py:119-158 (`update_mesh`, `update_vert`, `intersect`)
+  RayTracer     -- drop-in for raytracing/raytracing/raytracer.py:8-54 (`trace` -> positions, normals, depth)
+  Scene         -- the parts of network/DiffRender.py:318-360, 410-416, 539-549 the renderers use
+                   (angle-weighted vertex normals, `optix_intersect`, `Dintersect`)
+
+Everything runs on the current CUDA stream with no host round trip (the reference copies rays through numpy
+on every query, tracing_optix.py:155-158).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+
+MISS_ID = 10000000  # cuda/triangle.cu:85-89
+
+
+class TriangleBVH:
+    def __init__(self, vertices, faces):
+        self.update(vertices, faces)
+
+    def update(self, vertices, faces):
+        dev = vertices.device
+        V = vertices.detach().to(torch.float32).cpu().contiguous()
+        F = faces.detach().to(torch.int32).cpu().contiguous()
+        nF = F.shape[0]
+        max_nodes = max(16, nF)  # every node owns >= 2 leaves / >= 5 triangles
+        nodes = (_lib.BvhNode * max_nodes)()
+        order = torch.zeros(nF, dtype=torch.int32)
+        n = _lib.lib.nunerf_bvh_build_host(V.data_ptr(), V.shape[0], F.data_ptr(), nF, C.cast(nodes, C.c_void_p),
+                                           max_nodes, order.data_ptr())
+        if n < 0:
+            raise RuntimeError("nunerf_bvh_build_host: " + _lib.lib.nunerf_last_error().decode())
+        raw = np.frombuffer(nodes, dtype=np.uint8, count=n * C.sizeof(_lib.BvhNode)).copy()
+        self.n_nodes = n
+        self.nodes = torch.from_numpy(raw).to(dev)
+        self.tri_order = order.to(dev)
+        tv = V[F.long()].reshape(nF, 9)
+        self.tri_verts = tv.to(dev).contiguous()                     # original face order (brute force / interp)
+        self.tri_verts_sorted = tv[order.long()].to(dev).contiguous()  # leaf order (traversal)
+        self.n_faces = nF
+        self.device = dev
+
+    def trace(self, rays_o, rays_d, tmax=1e16, return_t=False):
+        N = rays_o.shape[0]
+        o = rays_o.detach().float().contiguous()
+        d = rays_d.detach().float().contiguous()
+        hit = torch.empty(N, device=o.device)
+        tri = torch.empty(N, dtype=torch.int32, device=o.device)
+        t = torch.empty(N, device=o.device)
+        if N > 0:
+            call("nunerf_bvh_trace", self.nodes.data_ptr(), self.tri_verts_sorted.data_ptr(), self.tri_order.data_ptr(),
+                 o.data_ptr(), d.data_ptr(), N, float(tmax), hit.data_ptr(), tri.data_ptr(), t.data_ptr())
+        return (hit, tri, t) if return_t else (hit, tri)
+
+    def trace_brute(self, rays_o, rays_d, tmax=1e16):
+        N = rays_o.shape[0]
+        o = rays_o.detach().float().contiguous()
+        d = rays_d.detach().float().contiguous()
+        hit = torch.empty(N, device=o.device)
+        tri = torch.empty(N, dtype=torch.int32, device=o.device)
+        t = torch.empty(N, device=o.device)
+        call("nunerf_trace_brute", self.tri_verts.data_ptr(), self.n_faces, o.data_ptr(), d.data_ptr(), N, float(tmax),
+             hit.data_ptr(), tri.data_ptr(), t.data_ptr())
+        return hit, tri, t
+
+
+class optix_mesh:
+    """Same surface as the reference's OptiX wrapper (tracing_optix.py:119-158); hit is 1.0/0.0, idx int32 with
+    10000000 on a miss."""
+
+    def __init__(self):
+        self.bvh = None
+        self.faces = None
+
+    def update_mesh(self, F, V):
+        self.faces = F
+        self.bvh = TriangleBVH(V, F)
+
+    def update_vert(self, V):
+        self.bvh.update(V, self.faces)
+
+    def intersect(self, ray):
+        if self.bvh is None:
+            raise RuntimeError("optix_mesh.intersect called before update_mesh")
+        ray = ray.reshape(-1, 6)
+        return self.bvh.trace(ray[:, :3], ray[:, 3:])
+
+
+class RayTracer:
+    """raytracing.RayTracer(vertices ndarray[V,3], triangles ndarray[F,3]); trace -> (positions, face normals, depth).
+    Depth is clamped at MAX_DIST = 10 as in raytracing/src/bvh.cu:36; misses return depth 10."""
+    MAX_DIST = 10.0
+
+    def __init__(self, vertices, triangles, device="cuda"):
+        assert triangles.shape[0] > 8, "BVH needs at least 8 triangles!"
+        V = torch.as_tensor(np.asarray(vertices), dtype=torch.float32, device=device)
+        F = torch.as_tensor(np.asarray(triangles), dtype=torch.int32, device=device)
+        self.bvh = TriangleBVH(V, F)
+        tv = self.bvh.tri_verts.reshape(-1, 3, 3)
+        n = torch.cross(tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0], dim=-1)
+        self.face_normals = torch.nn.functional.normalize(n, dim=-1)
+
+    def trace(self, rays_o, rays_d, inplace=False):
+        prefix = rays_o.shape[:-1]
+        o = rays_o.float().contiguous().view(-1, 3)
+        d = rays_d.float().contiguous().view(-1, 3)
+        hit, tri, t = self.bvh.trace(o, d, tmax=self.MAX_DIST, return_t=True)
+        depth = torch.where(hit > 0, t, torch.full_like(t, self.MAX_DIST))
+        positions = o + depth[:, None] * d
+        normals = torch.where((hit > 0)[:, None], self.face_normals[tri.clamp(max=self.bvh.n_faces - 1).long()],
+                              torch.zeros_like(o))
+        if inplace:
+            rays_o.copy_(positions.view(*prefix, 3))
+            rays_d.copy_(normals.view(*prefix, 3))
+            return rays_o, rays_d, depth.view(*prefix)
+        return positions.view(*prefix, 3), normals.view(*prefix, 3), depth.view(*prefix)
+
+
+def angle_weighted_vertex_normals(V, F):
+    """DiffRender.py:342-359 (init_VN): per-vertex normals = normalised sum of face normals weighted by the corner
+    angle.  V float64/float32 [V,3], F long [F,3] -> float32 [V,3]."""
+    V = V.double()
+    tri = V[F.long()]
+    e = [tri[:, (i + 1) % 3] - tri[:, i] for i in range(3)]
+    fn = torch.cross(e[0], -e[2], dim=-1)
+    fn = fn / fn.norm(dim=1, keepdim=True)
+    ang = []
+    for i in range(3):
+        a, b = e[i], -e[(i + 2) % 3]
+        cosv = (a * b).sum(-1) / (a.norm(dim=1) * b.norm(dim=1))
+        ang.append(torch.acos(cosv.clamp(-1, 1)))
+    ang = torch.stack(ang, 1)
+    vn = torch.zeros_like(V)
+    for i in range(3):
+        vn.index_add_(0, F[:, i].long(), fn * ang[:, i:i + 1])
+    return (vn / vn.norm(dim=1, keepdim=True)).float()
+
+
+class Scene:
+    """The subset of DiffRender.Scene used by Stage2Renderer.ray_trace: mesh upload, vertex normals and the
+    hit query + re-intersection (`Dintersect`)."""
+
+    def __init__(self, vertices, faces, device="cuda"):
+        self.device = device
+        self.optix_mesh = optix_mesh()
+        self.update_mesh(vertices, faces)
+
+    def update_mesh(self, vertices, faces):
+        self.vertices = torch.as_tensor(vertices, dtype=torch.float64, device=self.device)
+        self.faces = torch.as_tensor(faces, dtype=torch.long, device=self.device)
+        self.optix_mesh.update_mesh(self.faces.to(torch.int32), self.vertices.to(torch.float32))
+        self.normals = angle_weighted_vertex_normals(self.vertices, self.faces)
+        self.tri_normals = self.normals[self.faces].reshape(-1, 9).contiguous()
+
+    def optix_intersect(self, origin, direction):
+        ray = torch.cat([origin.float(), direction.float()], dim=1)
+        T, idx = self.optix_mesh.intersect(ray)
+        return idx.to(torch.long), T > 0
+
+    def Dintersect(self, origin, direction):
+        """-> dict(u, v, t, n, x) for every ray (zeros where missed) and the hit mask."""
+        N = origin.shape[0]
+        o = origin.detach().float().contiguous()
+        d = direction.detach().float().contiguous()
+        hit, tri = self.optix_mesh.intersect(torch.cat([o, d], 1))
+        uvt = torch.empty(N, 3, device=o.device)
+        x = torch.empty(N, 3, device=o.device)
+        n = torch.empty(N, 3, device=o.device)
+        bvh = self.optix_mesh.bvh
+        call("nunerf_hit_interp", bvh.tri_verts.data_ptr(), self.tri_normals.data_ptr(), tri.data_ptr(), o.data_ptr(),
+             d.data_ptr(), N, uvt.data_ptr(), x.data_ptr(), n.data_ptr())
+        return {"u": uvt[:, 0], "v": uvt[:, 1], "t": uvt[:, 2], "n": n, "x": x, "faces_ind": tri}, hit > 0

@@ -1,0 +1,62 @@
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def _make(target):
+    subprocess.run(["make", "-s", target], cwd=ROOT, check=True)
+
+
+@pytest.fixture(scope="session")
+def oracle_c():
+    """The plain-C oracle (oracle/sampling_oracle.c), built on demand with gcc."""
+    path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(os.path.join(ROOT, "oracle", "sampling_oracle.c")):
+        _make("oracle/_build/liboracle.so")
+    return ctypes.CDLL(path)
+
+
+@pytest.fixture(scope="session")
+def stage1_sd():
+    """state_dict of a freshly initialised stage-1 renderer (bit-identical to the reference's, see test_init)."""
+    from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
+    torch.manual_seed(0)
+    net = NeROShapeRenderer(load_default_cfg(), training=False)
+    return {k: v.detach().clone() for k, v in net.state_dict().items()}
+
+
+def np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def sampling_tables():
+    """The linspace tables the sampling kernels take (computed with torch exactly as ZT:580-590 does)."""
+    t = torch.linspace(0.0, 1.0, 64)
+    b = torch.linspace(1e-3, 1.0 - 1.0 / 33.0, 32)
+    mids = 0.5 * (b[1:] + b[:-1])
+    upper = torch.cat([mids, b[-1:]])
+    lower = torch.cat([b[:1], mids])
+    return torch.cat([t, lower, upper - lower, b]).contiguous()

@@ -1,0 +1,41 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol include/nunerf.h declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "nunerf.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(nunerf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    path = os.path.join(ROOT, "nu_nerf_b200", "libnunerf_b200.so")
+    assert os.path.exists(path), "build the engine first (make / __graft_entry__.build())"
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nunerf.h but not exported"
+    lib.nunerf_version.restype = ctypes.c_int
+    assert lib.nunerf_version() >= 100
+    lib.nunerf_last_error.restype = ctypes.c_char_p
+    assert lib.nunerf_last_error() is not None
+
+
+def test_python_binding_covers_the_header():
+    from nu_nerf_b200 import _lib
+    assert sorted(_lib.ALL_SYMBOLS) == declared_symbols()
+
+
+def test_argument_validation_without_gpu():
+    """Error convention: negative return code + message, no CUDA call needed for bad arguments."""
+    from nu_nerf_b200 import _lib
+    p = _lib.LinearT()
+    rc = _lib.lib.nunerf_linear(ctypes.byref(p), None)
+    assert rc < 0 and b"linear" in _lib.lib.nunerf_last_error()
+    rc = _lib.lib.nunerf_upsample(None, None, None, None, 4, 300, 16, None, 1.0, None, None, None, None, None, None)
+    assert rc < 0

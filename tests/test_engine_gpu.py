@@ -1,0 +1,163 @@
+"""GPU parity of the stage-1 renderer (the drop-in boundary) against the CPU oracle and the committed goldens.
+
+Tolerances (north_star): rgb / depth / normal <= 1e-4 abs in the fp32-accurate ("split") mode, parameter gradients
+<= 1e-3 relative (max |g - g_ref| / max |g_ref| per tensor); the fast bf16 mode is held to 2e-2 on gradients and
+5e-3 on rgb (stated).  z_vals are produced by the oracle and fed to both sides for the render_core checks, so the
+comparison is not polluted by the (documented) ulp-level sampling ties.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _renderer(precision):
+    from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
+    torch.manual_seed(0)
+    cfg = load_default_cfg()
+    cfg["precision"] = precision
+    return NeROShapeRenderer(cfg, training=False).cuda()
+
+
+def _oracle_params(net):
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
+              if v.dtype.is_floating_point and k != "color_network.FG_LUT"}
+    sdp = dict(sd)
+    sdp.update(params)
+    return sdp, params
+
+
+@pytest.mark.parametrize("precision,tol", [("split", 3e-5), ("bf16", 2e-2)])
+def test_sdf_network_value_feature_gradient(precision, tol):
+    from nu_nerf_b200 import engine as eng
+    from oracle import nunerf_oracle as orc
+    net = _renderer(precision)
+    _, w = net._prepare()
+    g = torch.Generator().manual_seed(3)
+    pts = (torch.rand(3001, 3, generator=g) * 1.6 - 0.8)
+    sdp, _ = _oracle_params(net)
+    with torch.no_grad():
+        y, grad = orc.sdf_forward(sdp, pts, with_grad=True)
+    xm = eng.P(pts.shape[0], 320, w.planes, DEV)
+    tape = eng.sdf_forward(w.sdf, pts.to(DEV).contiguous(), w.planes, xm)
+    assert (tape.sdf[:, 0].cpu() - y[:, 0]).abs().max().item() < tol
+    assert (xm.float(cols=256).cpu() - y[:, 1:]).abs().max().item() < tol * 4
+    assert (tape.grad.cpu() - grad).abs().max().item() < tol * 10
+    sdf_only = eng.sdf_infer(w.sdf, pts.to(DEV).contiguous(), w.planes)
+    assert (sdf_only.cpu() - y[:, 0]).abs().max().item() < tol
+
+
+def _run_core(net, o, d, z, gt, cos_anneal, step):
+    net.zero_grad()
+    out = net.render_core(o.to(DEV), d.to(DEV), z.to(DEV), None, cos_anneal_ratio=cos_anneal, step=step, is_train=True,
+                          is_nerf=True)
+    loss = net.compute_rgb_loss(out["ray_rgb"], gt.to(DEV)).mean() + (0.1 * out["gradient_error"]).mean()
+    loss.backward()
+    return out, loss
+
+
+@pytest.mark.parametrize("precision,rgb_tol,grad_tol", [("split", 1e-4, 1e-3), ("bf16", 5e-3, 2e-2)])
+def test_render_core_outputs_and_parameter_gradients(precision, rgb_tol, grad_tol):
+    from oracle import nunerf_oracle as orc
+    R = 192
+    net = _renderer(precision)
+    sdp, params = _oracle_params(net)
+    o, d = orc.synthetic_rays(R)
+    U0, U1 = orc.synthetic_uniforms(R)
+    gt = orc.synthetic_targets(R)
+    near, far = torch.full((R, 1), 0.8), torch.full((R, 1), 4.5)
+    with torch.no_grad():
+        z = orc.sample_ray(sdp, o, d, near, far, U0, U1)
+    ref = orc.render_core(sdp, o, d, z, 0.2, 10000)
+    ref_loss = orc.train_loss(ref, gt)
+    ref_loss.backward()
+    out, loss = _run_core(net, o, d, z, gt, 0.2, 10000)
+    assert out["gradient_error"].shape == ref["gradient_error"].shape, "inner sample set differs"
+    for k in ("ray_rgb", "acc", "color_bkgr", "color_spec"):
+        err = (out[k].detach().cpu() - ref[k].detach()).abs().max().item()
+        assert err < rgb_tol, (k, err)
+    for k, t in (("gradient_error", 20 * rgb_tol), ("transmission", rgb_tol), ("metallic", rgb_tol)):
+        err = (out[k].detach().cpu() - ref[k].detach()).abs().max().item()
+        assert err < t, (k, err)
+    assert abs(loss.item() - ref_loss.item()) < rgb_tol
+    worst = {}
+    for name, p in net.named_parameters():
+        gr = params[name].grad
+        if gr is None or gr.abs().max() == 0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-9, name
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        rel = (p.grad.cpu() - gr).abs().max().item() / gr.abs().max().item()
+        worst[name] = rel
+    bad = {k: v for k, v in worst.items() if v > grad_tol}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:8]
+
+
+def test_render_core_matches_reference_golden():
+    """CUDA path against outputs of the UNMODIFIED reference (tests/golden/stage1_train_R64.npz)."""
+    G = np.load(os.path.join(GOLDEN, "stage1_train_R64.npz"))
+    T = lambda k: torch.from_numpy(G[k])
+    net = _renderer("split")
+    out, loss = _run_core(net, T("o"), T("d"), T("z_vals"), T("gt"), float(G["cos_anneal"]), int(G["step"]))
+    for k in ("ray_rgb", "acc", "color_bkgr", "color_spec", "transmission", "metallic"):
+        err = (out[k].detach().cpu() - T("out_" + k)).abs().max().item()
+        assert err < 1e-4, (k, err)
+    assert (out["gradient_error"].detach().cpu() - T("out_gradient_error")).abs().max().item() < 2e-3
+    assert abs(loss.item() - float(G["loss"])) < 1e-4
+    for name, p in net.named_parameters():
+        key = "gradnorm/" + name
+        if key not in G.files:
+            continue
+        ref_norm = float(G[key])
+        assert abs(p.grad.double().norm().item() - ref_norm) <= 2e-3 * ref_norm + 1e-12, name
+
+
+def test_sample_ray_end_to_end():
+    """sample_ray on the GPU vs the oracle: the per-round kernels are bit exact given identical inputs
+    (test_kernels_gpu), end to end the MLP rounding moves sdf by ~1e-6 which the CDF inversion amplifies."""
+    from oracle import nunerf_oracle as orc
+    R = 512
+    net = _renderer("split")
+    sdp, _ = _oracle_params(net)
+    o, d = orc.synthetic_rays(R)
+    U0, U1 = orc.synthetic_uniforms(R)
+    near, far = torch.full((R, 1), 0.8), torch.full((R, 1), 4.5)
+    tr_ref, tr = {}, {}
+    with torch.no_grad():
+        z_ref = orc.sample_ray(sdp, o, d, near, far, U0, U1, trace=tr_ref)
+    z = net.sample_ray(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), 1.0, uniforms=(U0.to(DEV), U1.to(DEV)), trace=tr)
+    assert z.shape == (R, 160)
+    assert torch.equal(tr["z_in_0"].cpu(), tr_ref["z_in_0"]) or (tr["z_in_0"].cpu() - tr_ref["z_in_0"]).abs().max() < 5e-7
+    assert (tr["sdf_in_0"].cpu() - tr_ref["sdf_in_0"]).abs().max().item() < 2e-5
+    flips = (tr["inds_0"].cpu() != tr_ref["inds_0"].int()).sum().item()
+    assert flips <= 8, flips
+    assert (z.cpu() - z_ref).abs().max().item() < 5e-3
+    assert (z.cpu()[:, :128][:, 1:] >= z.cpu()[:, :128][:, :-1]).all()
+
+
+def test_eval_outputs_depth_normal():
+    from oracle import nunerf_oracle as orc
+    R = 64
+    net = _renderer("split")
+    sdp, _ = _oracle_params(net)
+    o, d = orc.synthetic_rays(R)
+    near, far = orc.near_far_from_sphere(o, d)
+    with torch.no_grad():
+        z = orc.sample_ray(sdp, o, d, near, far, None, None, perturb=False)
+        ref = orc.render_core(sdp, o, d, z, 0.0, 10000)
+        depth = (ref["weights"] * z).sum(-1, keepdim=True)
+        pts = depth * d + o
+        _, grad = orc.sdf_forward(sdp, pts, with_grad=True)
+        normal = ((torch.nn.functional.normalize(grad, dim=-1) + 1) * 0.5) * (pts.norm(dim=-1, keepdim=True) <= 1.0)
+    with torch.no_grad():
+        out = net.render_core(o.to(DEV), d.to(DEV), z.to(DEV), None, 0.0, step=10000, is_train=False, is_nerf=True)
+    assert (out["depth"].cpu() - depth).abs().max().item() < 1e-4
+    assert (out["normal"].cpu() - normal).abs().max().item() < 1e-4
+    assert (out["ray_rgb"].cpu() - ref["ray_rgb"]).abs().max().item() < 1e-4

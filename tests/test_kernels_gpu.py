@@ -1,0 +1,331 @@
+"""GPU parity tests of the individual kernels, all called through the C-ABI (nu_nerf_b200/_lib.py).
+
+Bars: integer / index outputs bit-exact against oracle/sampling_oracle.c; floating point against a plain
+torch fp32 reference with the tolerance written in each test.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import np_ptr, sampling_tables
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _ops():
+    from nu_nerf_b200 import ops
+    return ops
+
+
+def _mk_planes(x, width, planes, rows=None):
+    """fp32 [M,K] -> P with zero padding."""
+    ops = _ops()
+    M, K = x.shape
+    rows = M if rows is None else rows
+    p = ops.P(rows, width, planes, x.device, zero=True)
+    ops.to_planes(x.contiguous(), p, M, K, False, 1.0, M, width)
+    return p
+
+
+# ----------------------------------------------------------------------------------------- dense layers
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("M,N,K,act", [(1000, 256, 256, 1), (4096 + 77, 256, 64, 2), (300, 16, 256, 0),
+                                       (2048, 224, 256, 2), (5000, 128, 320, 1), (129, 256, 384, 0)])
+def test_linear_matches_torch(planes, M, N, K, act):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(M + N + K)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    b = torch.randn(N, device=DEV, generator=g) * 0.1
+    A = _mk_planes(x, K, planes)
+    B = _mk_planes(w, K, planes)
+    out = ops.P(M, N, planes, DEV, zero=True)
+    out32 = torch.zeros(M, N, device=DEV)
+    ops.linear(A, B, M, N, K, bias=b, act=act, out=out, out_f32=out32)
+    xr, wr = A.float(), B.float()          # the values the kernel actually saw
+    ref = xr.double() @ wr.double().t() + b.double()
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.softplus(ref, beta=100)
+    ref = ref.float()
+    tol = 2e-5 if planes == 2 else 2e-5  # inputs are pre-rounded, so both modes see exact operands
+    if planes == 2:
+        # split mode drops the lo*lo term: relative 2^-16 per product
+        tol = 1e-4
+    err = (out32 - ref).abs().max().item()
+    assert err < tol * max(1.0, ref.abs().max().item()), err
+    back = out.float()
+    rel = 2 ** -8 if planes == 1 else 2 ** -15
+    assert (back - out32).abs().max().item() <= rel * out32.abs().max().item() + 1e-6
+
+
+def test_linear_tc_equals_simt_and_epilogue_modes():
+    ops = _ops()
+    M, N, K = 777, 256, 256
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / 16
+    auxv = torch.randn(M, N, device=DEV, generator=g) * 0.02
+    addv = torch.randn(M, N, device=DEV, generator=g)
+    for planes in (1, 2):
+        A, B = _mk_planes(x, K, planes), _mk_planes(w, K, planes)
+        aux, add = _mk_planes(auxv, N, planes), _mk_planes(addv, N, planes)
+        for mode in (1, 2):
+            o1 = torch.zeros(M, N, device=DEV)
+            ops.linear(A, B, M, N, K, aux=aux, aux_mode=mode, add=add, out_f32=o1, n_store=217, out_scale=0.5)
+            ref = 0.5 * (A.float().double() @ B.float().double().t())
+            av = aux.float().double()
+            ref = ref * ((av > 0).double() if mode == 1 else (1 - torch.exp(-100 * av))) + add.float().double()
+            ref[:, 217:] = 0
+            assert (o1 - ref.float()).abs().max().item() < 2e-4
+            old = ops.GEMM_IMPL
+            try:
+                ops.GEMM_IMPL = 1
+                o2 = torch.zeros(M, N, device=DEV)
+                ops.linear(A, B, M, N, K, aux=aux, aux_mode=mode, add=add, out_f32=o2, n_store=217, out_scale=0.5)
+            finally:
+                ops.GEMM_IMPL = old
+            assert (o1 - o2).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(4096, 256, 256), (1000, 217, 256), (70000, 256, 64), (333, 3, 128), (2500, 256, 384)])
+def test_linear_dw_matches_torch(planes, M, N, K):
+    ops = _ops()
+    g = torch.Generator(device=DEV).manual_seed(M + N)
+    z = torch.randn(M, N, device=DEV, generator=g)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    Z = _mk_planes(z, ops.pad(N, 64), planes)
+    X = _mk_planes(x, K, planes)
+    dW = torch.zeros(ops.pad(N, 16), K, device=DEV)
+    ops.linear_dw(Z, X, M, N, K, dW)
+    ref = (Z.float()[:, :N].double().t() @ X.float().double()).float()
+    scale = ref.abs().max().item()
+    err = (dW[:N] - ref).abs().max().item()
+    assert err < 2e-4 * scale, (err, scale)
+    bsum = torch.zeros(N, device=DEV)
+    ops.colsum(Z, M, N, bsum)
+    assert (bsum - Z.float()[:, :N].sum(0)).abs().max().item() < 1e-3 * M ** 0.5
+
+
+# ----------------------------------------------------------------------------------------- sampling
+def _c_upsample(lib, o, d, z, sdf, n_new, inv_s, cap, u):
+    R, n = z.shape
+    z_new = np.zeros((R, n_new), np.float32)
+    inds = np.zeros((R, n_new), np.int32)
+    zm = np.zeros((R, n + n_new), np.float32)
+    perm = np.zeros((R, n + n_new), np.int32)
+    lib.oracle_upsample(np_ptr(o), np_ptr(d), np_ptr(z), np_ptr(sdf), R, n, n_new, ctypes.c_float(inv_s),
+                        ctypes.c_float(cap), np_ptr(u), np_ptr(z_new), np_ptr(inds), np_ptr(zm), np_ptr(perm))
+    return z_new, inds, zm, perm
+
+
+@pytest.mark.parametrize("sphere,perturb", [(0, 1), (1, 0), (1, 1)])
+def test_ray_setup_bit_exact(oracle_c, sphere, perturb):
+    from nu_nerf_b200 import _lib
+    from oracle import nunerf_oracle as orc
+    R = 1031
+    o, d = orc.synthetic_rays(R)
+    U0, U1 = orc.synthetic_uniforms(R)
+    tab = sampling_tables()
+    near = np.full((R,), 0.8, np.float32)
+    far = np.full((R,), 4.5, np.float32)
+    z, zb = np.zeros((R, 64), np.float32), np.zeros((R, 32), np.float32)
+    oracle_c.oracle_ray_setup(np_ptr(o.numpy()), np_ptr(d.numpy()), np_ptr(near), np_ptr(far), np_ptr(U0.numpy()),
+                              np_ptr(U1.numpy()), np_ptr(tab.numpy()), R, sphere, perturb, np_ptr(z), np_ptr(zb))
+    dn, df = torch.full((R,), 0.8, device=DEV), torch.full((R,), 4.5, device=DEV)
+    dz, dzb = torch.zeros(R, 64, device=DEV), torch.zeros(R, 32, device=DEV)
+    _lib.call("nunerf_ray_setup", o.to(DEV).data_ptr(), d.to(DEV).data_ptr(), dn.data_ptr(), df.data_ptr(),
+              U0.to(DEV).data_ptr(), U1.to(DEV).data_ptr(), tab.to(DEV).data_ptr(), R, sphere, perturb, dz.data_ptr(),
+              dzb.data_ptr())
+    assert np.array_equal(dz.cpu().numpy(), z) and np.array_equal(dzb.cpu().numpy(), zb)
+    assert np.array_equal(dn.cpu().numpy(), near) and np.array_equal(df.cpu().numpy(), far)
+    # and against the torch restatement of the reference arithmetic (ZT:580-594)
+    nr, fr = torch.from_numpy(near)[:, None], torch.from_numpy(far)[:, None]
+    zr, zbr = orc.coarse_samples(nr, fr, U0, U1, perturb=bool(perturb))
+    assert (zr - torch.from_numpy(z)).abs().max().item() <= 5e-7
+    assert ((zbr - torch.from_numpy(zb)).abs() / zbr.abs()).max().item() <= 3e-7
+
+
+@pytest.mark.parametrize("n,n_new,cap", [(64, 16, 64.0), (80, 16, 128.0), (96, 16, 256.0), (112, 16, 512.0), (64, 32, 64.0), (97, 7, 1e9)])
+def test_upsample_bit_exact_vs_c_oracle(oracle_c, n, n_new, cap):
+    from nu_nerf_b200 import _lib
+    from oracle import nunerf_oracle as orc
+    R = 2053
+    o, d = orc.synthetic_rays(R)
+    g = torch.Generator().manual_seed(n)
+    z = torch.sort(0.8 + 3.7 * torch.rand(R, n, generator=g), dim=-1)[0].contiguous()
+    # a plausible sdf: distance to a sphere of radius 0.5 plus noise, sometimes with exact ties in z
+    pts = o[:, None, :] + d[:, None, :] * z[..., None]
+    sdf = (pts.norm(dim=-1) - 0.5 + 0.01 * torch.randn(R, n, generator=g)).contiguous()
+    z[::7, 5] = z[::7, 4]
+    u = torch.linspace(0.5 / n_new, 1 - 0.5 / n_new, n_new)
+    inv_s = 20.0855
+    ref = _c_upsample(oracle_c, o.numpy(), d.numpy(), z.numpy(), sdf.numpy(), n_new, inv_s, cap, u.numpy())
+    dz_new = torch.zeros(R, n_new, device=DEV)
+    dinds = torch.zeros(R, n_new, dtype=torch.int32, device=DEV)
+    dzm = torch.zeros(R, n + n_new, device=DEV)
+    dperm = torch.zeros(R, n + n_new, dtype=torch.int32, device=DEV)
+    inv_dev = torch.tensor([inv_s], device=DEV)
+    _lib.call("nunerf_upsample", o.to(DEV).data_ptr(), d.to(DEV).data_ptr(), z.to(DEV).data_ptr(),
+              sdf.to(DEV).data_ptr(), R, n, n_new, inv_dev.data_ptr(), cap, u.to(DEV).data_ptr(), dz_new.data_ptr(),
+              dinds.data_ptr(), dzm.data_ptr(), dperm.data_ptr())
+    assert np.array_equal(dinds.cpu().numpy(), ref[1]), "sample indices must be bit exact"
+    assert np.array_equal(dz_new.cpu().numpy(), ref[0])
+    assert np.array_equal(dzm.cpu().numpy(), ref[2])
+    assert np.array_equal(dperm.cpu().numpy(), ref[3]), "merge permutation must be bit exact"
+    # merged depths are sorted and the permutation is a permutation
+    assert (dzm[:, 1:] >= dzm[:, :-1]).all()
+    assert (torch.sort(dperm, dim=-1)[0].cpu() == torch.arange(n + n_new)[None]).all()
+    # merge_sdf gathers by the permutation
+    sdf_new = torch.randn(R, n_new, device=DEV)
+    merged = torch.zeros(R, n + n_new, device=DEV)
+    _lib.call("nunerf_merge_sdf", sdf.to(DEV).data_ptr(), sdf_new.data_ptr(), dperm.data_ptr(), R, n, n_new,
+              merged.data_ptr())
+    assert torch.equal(merged, torch.gather(torch.cat([sdf.to(DEV), sdf_new], -1), 1, dperm.long()))
+
+
+# ----------------------------------------------------------------------------------------- geometry + compositing
+def _geometry(o, d, z):
+    from nu_nerf_b200 import _lib
+    R, S = z.shape
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=DEV)
+    out = dict(dists=f(R, S), pts=f(R, S, 3), slot=i32(R, S), counts=i32(2), scratch=i32(2 * R),
+               pts_in=f(R * S, 3), dists_in=f(R * S), dirs_in=f(R * S, 3), id_in=i32(R * S),
+               pts_out=f(R * S, 3), dists_out=f(R * S), dirs_out=f(R * S, 3), id_out=i32(R * S))
+    _lib.call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, *[out[k].data_ptr() for k in
+              ("dists", "pts", "slot", "counts", "scratch", "pts_in", "dists_in", "dirs_in", "id_in", "pts_out",
+               "dists_out", "dirs_out", "id_out")])
+    return out
+
+
+def test_render_geometry_and_compaction_order():
+    from oracle import nunerf_oracle as orc
+    R, S = 777, 160
+    o, d = orc.synthetic_rays(R)
+    g = torch.Generator().manual_seed(0)
+    z = torch.sort(0.8 + 3.7 * torch.rand(R, S, generator=g), dim=-1)[0]
+    out = _geometry(o.to(DEV), d.to(DEV), z.to(DEV).contiguous())
+    dists = z[:, 1:] - z[:, :-1]
+    dists = torch.cat([dists, dists[:, -1:]], -1)
+    pts = o[:, None, :] + d[:, None, :] * (z + dists * 0.5)[..., None]
+    inner = pts.norm(dim=-1) <= 1.0
+    assert torch.equal(out["dists"].cpu(), dists)
+    assert (out["pts"].cpu() - pts).abs().max().item() <= 5e-7
+    gi = (out["slot"] >= 0).cpu()
+    # the mask may differ only where ||p|| is within rounding of 1
+    assert ((gi != inner) & ((pts.norm(dim=-1) - 1).abs() > 1e-6)).sum().item() == 0
+    n_in = int(out["counts"][0])
+    assert n_in == int(gi.sum()) and int(out["counts"][1]) == R * S - n_in
+    # row-major mask order == boolean-mask indexing order of the reference (points[inner_mask])
+    assert torch.equal(out["pts_in"][:n_in].cpu(), out["pts"].cpu()[gi])
+    assert torch.equal(out["dists_in"][:n_in].cpu(), out["dists"].cpu()[gi])
+    assert torch.equal(out["pts_out"][:R * S - n_in].cpu(), out["pts"].cpu()[~gi])
+    assert torch.equal(out["id_in"][:n_in].cpu().long(), torch.nonzero(gi.reshape(-1))[:, 0])
+    dn = torch.nn.functional.normalize(d, dim=-1)[:, None, :].expand(R, S, 3)
+    assert (out["dirs_in"][:n_in].cpu() - dn[gi]).abs().max().item() <= 2e-7
+
+
+def test_composite_forward_and_backward():
+    from nu_nerf_b200 import _lib
+    from oracle import nunerf_oracle as orc
+    R, S = 515, 160
+    o, d = orc.synthetic_rays(R)
+    g = torch.Generator().manual_seed(1)
+    z = torch.sort(0.8 + 3.7 * torch.rand(R, S, generator=g), dim=-1)[0]
+    geo = _geometry(o.to(DEV), d.to(DEV), z.to(DEV).contiguous())
+    n_in, n_out = int(geo["counts"][0]), int(geo["counts"][1])
+    inner = (geo["slot"] >= 0)
+    a_in = (torch.rand(n_in, generator=g) ** 3).to(DEV).requires_grad_(True)
+    c_in = torch.rand(n_in, 3, generator=g).to(DEV).requires_grad_(True)
+    a_out = (torch.rand(n_out, generator=g) ** 3).to(DEV).requires_grad_(True)
+    c_out = torch.rand(n_out, 3, generator=g).to(DEV).requires_grad_(True)
+    a_in.data[::50] = 1.0  # opaque samples exercise the 1e-7 floor
+    rgb, raw, acc, bk, w = (torch.zeros(R, 3, device=DEV), torch.zeros(R, 3, device=DEV), torch.zeros(R, device=DEV),
+                            torch.zeros(R, 3, device=DEV), torch.zeros(R, S, device=DEV))
+    _lib.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+              geo["slot"].data_ptr(), R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), w.data_ptr())
+    # torch fp32 reference (ZT:773-788)
+    alpha = torch.zeros(R, S, device=DEV).masked_scatter(inner, a_in).masked_scatter(~inner, a_out)
+    color = torch.zeros(R, S, 3, device=DEV).masked_scatter(inner[..., None].expand(-1, -1, 3), c_in) \
+        .masked_scatter((~inner)[..., None].expand(-1, -1, 3), c_out)
+    w_ref, rgb_ref = orc.composite(alpha.cpu(), color.cpu())
+    # (run the reference on the GPU tensors for autograd)
+    T = torch.cumprod(torch.cat([torch.ones(R, 1, device=DEV), 1. - alpha + 1e-7], -1), -1)[:, :-1]
+    wt = alpha * T
+    acc_t = wt.sum(-1)
+    rgb_t = torch.clamp((color * wt[..., None]).sum(1) + (1 - acc_t[..., None]), 0, 1)
+    ab = alpha * (~inner)
+    Tb = torch.cumprod(torch.cat([torch.ones(R, 1, device=DEV), 1. - ab + 1e-7], -1), -1)[:, :-1]
+    bk_t = (color * (ab * Tb)[..., None]).sum(1)
+    assert (rgb - rgb_t).abs().max().item() < 2e-6 and (acc - acc_t).abs().max().item() < 2e-6
+    assert (bk - bk_t).abs().max().item() < 2e-6 and (w - wt).abs().max().item() < 1e-6
+    assert (w.cpu() - w_ref.detach()).abs().max().item() < 1e-6
+    g_rgb = torch.randn(R, 3, generator=g).to(DEV)
+    g_acc = torch.randn(R, generator=g).to(DEV)
+    g_bk = torch.randn(R, 3, generator=g).to(DEV)
+    ((rgb_t * g_rgb).sum() + (acc_t * g_acc).sum() + (bk_t * g_bk).sum()).backward()
+    da_in, dc_in, da_out, dc_out = (torch.zeros_like(a_in), torch.zeros_like(c_in), torch.zeros_like(a_out),
+                                    torch.zeros_like(c_out))
+    _lib.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+              geo["slot"].data_ptr(), R, S, 1, raw.data_ptr(), g_rgb.data_ptr(), g_acc.data_ptr(), g_bk.data_ptr(),
+              da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
+    for mine, ref in ((da_in, a_in.grad), (dc_in, c_in.grad), (da_out, a_out.grad), (dc_out, c_out.grad)):
+        scale = ref.abs().max().item()
+        assert (mine - ref).abs().max().item() < 1e-4 * scale, ((mine - ref).abs().max().item(), scale)
+
+
+# ----------------------------------------------------------------------------------------- tracing
+def _uv_sphere(nu, nv, radius=0.6):
+    th = torch.linspace(0, np.pi, nv + 1)
+    ph = torch.linspace(0, 2 * np.pi, nu + 1)[:-1]
+    v = [torch.tensor([[0.0, 0.0, radius]])]
+    for i in range(1, nv):
+        v.append(torch.stack([radius * torch.sin(th[i]) * torch.cos(ph), radius * torch.sin(th[i]) * torch.sin(ph),
+                              radius * torch.cos(th[i]).expand(nu)], -1))
+    v.append(torch.tensor([[0.0, 0.0, -radius]]))
+    V = torch.cat(v, 0).float()
+    F = []
+    for j in range(nu):
+        F.append([0, 1 + j, 1 + (j + 1) % nu])
+    for i in range(1, nv - 1):
+        a, b = 1 + (i - 1) * nu, 1 + i * nu
+        for j in range(nu):
+            j2 = (j + 1) % nu
+            F.append([a + j, b + j, b + j2])
+            F.append([a + j, b + j2, a + j2])
+    last = V.shape[0] - 1
+    a = 1 + (nv - 2) * nu
+    for j in range(nu):
+        F.append([a + j, last, a + (j + 1) % nu])
+    return V, torch.tensor(F, dtype=torch.int32)
+
+
+@pytest.mark.parametrize("nu,nv", [(24, 12), (224, 224)])
+def test_bvh_trace_hit_ids_bit_exact(oracle_c, nu, nv):
+    from nu_nerf_b200.tracer import TriangleBVH
+    from oracle import nunerf_oracle as orc
+    V, F = _uv_sphere(nu, nv)
+    N = 4096 if nu > 100 else 2000
+    o, d = orc.synthetic_rays(N)
+    # half of the rays start inside the mesh (the second bounce of stage 2)
+    o[::2] = 0.3 * o[::2] / 3.0
+    bvh = TriangleBVH(V.to(DEV), F.to(DEV))
+    hit, tri, t = bvh.trace(o.to(DEV), d.to(DEV), return_t=True)
+    hb, tb, ttb = bvh.trace_brute(o.to(DEV), d.to(DEV))
+    assert torch.equal(tri, tb) and torch.equal(hit, hb) and torch.equal(t, ttb)
+    sub = slice(0, 512 if nu > 100 else N)
+    tv = V[F.long()].reshape(-1, 9).contiguous().numpy()
+    n = o[sub].shape[0]
+    h = np.zeros(n, np.float32); ti = np.zeros(n, np.int32); tt = np.zeros(n, np.float32); uv = np.zeros((n, 2), np.float32)
+    oracle_c.oracle_closest_hit(np_ptr(tv), tv.shape[0], np_ptr(o[sub].contiguous().numpy()),
+                                np_ptr(d[sub].contiguous().numpy()), n, ctypes.c_float(1e16), np_ptr(h), np_ptr(ti),
+                                np_ptr(tt), np_ptr(uv))
+    assert np.array_equal(tri[sub].cpu().numpy(), ti), "triangle hit ids must be bit exact"
+    assert np.array_equal(hit[sub].cpu().numpy(), h) and np.array_equal(t[sub].cpu().numpy(), tt)
+    assert hit.sum().item() > 0.5 * N

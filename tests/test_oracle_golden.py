@@ -1,0 +1,123 @@
+"""CPU checks that pin the oracle (oracle/nunerf_oracle.py, oracle/sampling_oracle.c) against fixtures produced
+by the UNMODIFIED reference (tests/golden/make_golden.py), and the product's initialisation against the reference's."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, np_ptr
+
+
+def _fp(t):
+    t = t.detach().double().reshape(-1)
+    idx = torch.linspace(0, t.numel() - 1, min(t.numel(), 8)).long()
+    return np.concatenate([[t.sum().item(), t.abs().sum().item(), (t * t).sum().item()], t[idx].numpy()])
+
+
+def test_initialisation_is_bit_identical_to_the_reference(stage1_sd):
+    G = np.load(os.path.join(GOLDEN, "stage1_init.npz"))
+    assert len(G.files) == 175
+    for k in G.files:
+        assert k in stage1_sd, f"missing parameter {k}"
+        assert np.array_equal(_fp(stage1_sd[k]), G[k]), k
+    assert sorted(set(stage1_sd) - set(G.files)) == ["color_network.FG_LUT"]
+
+
+@pytest.mark.parametrize("name,perturb", [("stage1_train_R64", True), ("stage1_sphere_R64", False)])
+def test_torch_oracle_matches_reference_render_core(stage1_sd, name, perturb):
+    from oracle import nunerf_oracle as orc
+    G = np.load(os.path.join(GOLDEN, name + ".npz"))
+    T = lambda k: torch.from_numpy(G[k])
+    params = {k: v.clone().requires_grad_(True) for k, v in stage1_sd.items()
+              if v.dtype.is_floating_point and k != "color_network.FG_LUT"}
+    sd = dict(stage1_sd)
+    sd.update(params)
+    out = orc.render_core(sd, T("o"), T("d"), T("z_vals"), float(G["cos_anneal"]), int(G["step"]))
+    for k in ("ray_rgb", "gradient_error", "acc", "color_bkgr", "color_spec", "std", "transmission", "metallic"):
+        assert (out[k] - T("out_" + k)).abs().max().item() < 2e-6, k
+    loss = orc.train_loss(out, T("gt"))
+    assert abs(loss.item() - float(G["loss"])) < 1e-6
+    loss.backward()
+    for k, p in params.items():
+        if "gradnorm/" + k not in G.files:
+            continue
+        nrm = float(G["gradnorm/" + k])
+        assert abs(p.grad.double().norm().item() - nrm) <= 2e-4 * nrm + 1e-12, k
+        g = p.grad.reshape(-1)
+        idx = torch.linspace(0, g.numel() - 1, min(g.numel(), 64)).long()
+        # sampled entries, relative to the tensor's rms magnitude
+        rms = nrm / max(g.numel(), 1) ** 0.5
+        assert (g[idx] - T("grad/" + k)).abs().max().item() <= 5e-2 * rms + 1e-9, k
+
+
+@pytest.mark.parametrize("name,perturb", [("stage1_train_R64", True), ("stage1_sphere_R64", False)])
+def test_torch_oracle_sampling_vs_reference(stage1_sd, name, perturb):
+    """End-to-end sample_ray: indices may flip only at ulp-level cdf ties; z stays within 1e-3."""
+    from oracle import nunerf_oracle as orc
+    G = np.load(os.path.join(GOLDEN, name + ".npz"))
+    T = lambda k: torch.from_numpy(G[k])
+    tr = {}
+    z = orc.sample_ray(stage1_sd, T("o"), T("d"), T("near"), T("far"), T("U0"), T("U1"), perturb=perturb, trace=tr)
+    assert torch.equal(tr["z_in_0"], T("z_in_0"))
+    assert (tr["inds_0"].int() != T("inds_0")).sum().item() == 0
+    total_flips = sum((tr[f"inds_{i}"].int() != T(f"inds_{i}")).sum().item() for i in range(4))
+    assert total_flips <= 16
+    assert (z - T("z_vals")).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("name", ["stage1_train_R64", "stage1_sphere_R64"])
+def test_c_oracle_upsample_vs_reference(oracle_c, name):
+    """The plain-C oracle on the reference's own per-round inputs: sample indices equal the reference's except at
+    cdf ties within a few ulp; new depths within 2e-5; merged depths / permutation equal modulo exact z ties."""
+    G = np.load(os.path.join(GOLDEN, name + ".npz"))
+    o, d = G["o"], G["d"]
+    R = o.shape[0]
+    u = torch.linspace(0.5 / 16, 1 - 0.5 / 16, 16).numpy()
+    flips = 0
+    for i in range(4):
+        z, sdf = np.ascontiguousarray(G[f"z_in_{i}"]), np.ascontiguousarray(G[f"sdf_in_{i}"])
+        n = z.shape[1]
+        z_new = np.zeros((R, 16), np.float32); inds = np.zeros((R, 16), np.int32)
+        zm = np.zeros((R, n + 16), np.float32); perm = np.zeros((R, n + 16), np.int32)
+        oracle_c.oracle_upsample(np_ptr(o), np_ptr(d), np_ptr(z), np_ptr(sdf), R, n, 16, ctypes.c_float(float(G[f"inv_s_{i}"])),
+                                 ctypes.c_float(1e30), np_ptr(u), np_ptr(z_new), np_ptr(inds), np_ptr(zm), np_ptr(perm))
+        ref_inds = G[f"inds_{i}"]
+        diff = inds != ref_inds
+        flips += int(diff.sum())
+        assert np.abs(inds - ref_inds).max() <= 1
+        # the reference's merged depths: a flip moves a sample by ulps only (sample_pdf is continuous across bins)
+        ref_zm = G[f"z_merged_{i}"]
+        assert np.abs(zm - ref_zm).max() < 2e-5
+        same = np.isclose(zm, ref_zm, rtol=0, atol=0)
+        ref_perm = G[f"perm_{i}"]
+        mism = perm != ref_perm
+        # a permutation mismatch is only allowed where neighbouring depths tie (or a flipped sample moved by ulps)
+        if mism.any():
+            cat = np.concatenate([z, z_new], 1)
+            assert np.abs(np.take_along_axis(cat, perm, 1) - np.take_along_axis(cat, ref_perm, 1)).max() < 2e-5
+    assert flips <= 6, flips
+
+
+def test_c_oracle_composite_and_hit(oracle_c):
+    from oracle import nunerf_oracle as orc
+    g = torch.Generator().manual_seed(0)
+    R, S = 33, 160
+    alpha = torch.rand(R, S, generator=g) ** 3
+    color = torch.rand(R, S, 3, generator=g)
+    inner = (torch.rand(R, S, generator=g) > 0.4)
+    w_ref, rgb_ref = orc.composite(alpha, color)
+    rgb = np.zeros((R, 3), np.float32); acc = np.zeros(R, np.float32); rb = np.zeros((R, 3), np.float32)
+    w = np.zeros((R, S), np.float32)
+    oracle_c.oracle_composite(np_ptr(alpha.numpy()), np_ptr(color.numpy()), np_ptr(inner.numpy().astype(np.uint8)), R, S, 0,
+                              np_ptr(rgb), np_ptr(acc), np_ptr(rb), np_ptr(w))
+    assert np.abs(w - w_ref.numpy()).max() < 1e-6
+    assert np.abs(rgb - np.clip(rgb_ref.numpy(), 0, 1)).max() < 2e-6
+    # one triangle, three rays: centre hit, edge-parallel miss, behind-origin miss
+    tri = np.array([[0, 0, 1, 1, 0, 1, 0, 1, 1]], np.float32)
+    o = np.array([[0.2, 0.2, 0], [2, 2, 0], [0.2, 0.2, 2]], np.float32)
+    d = np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1]], np.float32)
+    hit = np.zeros(3, np.float32); ti = np.zeros(3, np.int32); t = np.zeros(3, np.float32); uv = np.zeros((3, 2), np.float32)
+    oracle_c.oracle_closest_hit(np_ptr(tri), 1, np_ptr(o), np_ptr(d), 3, ctypes.c_float(1e16), np_ptr(hit), np_ptr(ti), np_ptr(t), np_ptr(uv))
+    assert hit.tolist() == [1.0, 0.0, 0.0] and ti.tolist() == [0, 10000000, 10000000] and abs(t[0] - 1.0) < 1e-7
