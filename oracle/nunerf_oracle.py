@@ -74,8 +74,8 @@ def ide(xyz, kappa_inv):
         im.append(r * y + i * x)
     vre = torch.cat([re[m] for m in _MS], -1)
     vim = torch.cat([im[m] for m in _MS], -1)
-    pz = vmz @ _MAT_T
-    att = torch.exp(-_SIGMA * kappa_inv)
+    pz = vmz @ _MAT_T.to(xyz.dtype)
+    att = torch.exp(-_SIGMA.to(xyz.dtype) * kappa_inv)
     return torch.cat([vre * pz * att, vim * pz * att], -1)
 
 

@@ -69,7 +69,7 @@ def test_linear_tc_equals_simt_and_epilogue_modes():
     g = torch.Generator(device=DEV).manual_seed(5)
     x = torch.randn(M, K, device=DEV, generator=g)
     w = torch.randn(N, K, device=DEV, generator=g) / 16
-    auxv = torch.randn(M, N, device=DEV, generator=g) * 0.02
+    auxv = (torch.randn(M, N, device=DEV, generator=g) * 0.02).abs() * (torch.rand(M, N, device=DEV, generator=g) > 0.3)
     addv = torch.randn(M, N, device=DEV, generator=g)
     for planes in (1, 2):
         A, B = _mk_planes(x, K, planes), _mk_planes(w, K, planes)
@@ -81,7 +81,7 @@ def test_linear_tc_equals_simt_and_epilogue_modes():
             av = aux.float().double()
             ref = ref * ((av > 0).double() if mode == 1 else (1 - torch.exp(-100 * av))) + add.float().double()
             ref[:, 217:] = 0
-            assert (o1 - ref.float()).abs().max().item() < 2e-4
+            assert (o1 - ref.float()).abs().max().item() < 2e-4 * ref.abs().max().item()
             old = ops.GEMM_IMPL
             try:
                 ops.GEMM_IMPL = 1
@@ -89,7 +89,7 @@ def test_linear_tc_equals_simt_and_epilogue_modes():
                 ops.linear(A, B, M, N, K, aux=aux, aux_mode=mode, add=add, out_f32=o2, n_store=217, out_scale=0.5)
             finally:
                 ops.GEMM_IMPL = old
-            assert (o1 - o2).abs().max().item() < 2e-4
+            assert (o1 - o2).abs().max().item() < 2e-4 * ref.abs().max().item()
 
 
 @pytest.mark.parametrize("planes", [1, 2])
@@ -139,9 +139,11 @@ def test_ray_setup_bit_exact(oracle_c, sphere, perturb):
                               np_ptr(U1.numpy()), np_ptr(tab.numpy()), R, sphere, perturb, np_ptr(z), np_ptr(zb))
     dn, df = torch.full((R,), 0.8, device=DEV), torch.full((R,), 4.5, device=DEV)
     dz, dzb = torch.zeros(R, 64, device=DEV), torch.zeros(R, 32, device=DEV)
-    _lib.call("nunerf_ray_setup", o.to(DEV).data_ptr(), d.to(DEV).data_ptr(), dn.data_ptr(), df.data_ptr(),
-              U0.to(DEV).data_ptr(), U1.to(DEV).data_ptr(), tab.to(DEV).data_ptr(), R, sphere, perturb, dz.data_ptr(),
+    do, dd, dU0, dU1, dtab = o.to(DEV), d.to(DEV), U0.to(DEV), U1.to(DEV), tab.to(DEV)   # keep alive across the launch
+    _lib.call("nunerf_ray_setup", do.data_ptr(), dd.data_ptr(), dn.data_ptr(), df.data_ptr(),
+              dU0.data_ptr(), dU1.data_ptr(), dtab.data_ptr(), R, sphere, perturb, dz.data_ptr(),
               dzb.data_ptr())
+    torch.cuda.synchronize()
     assert np.array_equal(dz.cpu().numpy(), z) and np.array_equal(dzb.cpu().numpy(), zb)
     assert np.array_equal(dn.cpu().numpy(), near) and np.array_equal(df.cpu().numpy(), far)
     # and against the torch restatement of the reference arithmetic (ZT:580-594)
@@ -171,9 +173,11 @@ def test_upsample_bit_exact_vs_c_oracle(oracle_c, n, n_new, cap):
     dzm = torch.zeros(R, n + n_new, device=DEV)
     dperm = torch.zeros(R, n + n_new, dtype=torch.int32, device=DEV)
     inv_dev = torch.tensor([inv_s], device=DEV)
-    _lib.call("nunerf_upsample", o.to(DEV).data_ptr(), d.to(DEV).data_ptr(), z.to(DEV).data_ptr(),
-              sdf.to(DEV).data_ptr(), R, n, n_new, inv_dev.data_ptr(), cap, u.to(DEV).data_ptr(), dz_new.data_ptr(),
+    do, dd, dzz, dsdf, du = o.to(DEV), d.to(DEV), z.to(DEV), sdf.to(DEV), u.to(DEV)      # keep alive across the launch
+    _lib.call("nunerf_upsample", do.data_ptr(), dd.data_ptr(), dzz.data_ptr(),
+              dsdf.data_ptr(), R, n, n_new, inv_dev.data_ptr(), cap, du.data_ptr(), dz_new.data_ptr(),
               dinds.data_ptr(), dzm.data_ptr(), dperm.data_ptr())
+    torch.cuda.synchronize()
     assert np.array_equal(dinds.cpu().numpy(), ref[1]), "sample indices must be bit exact"
     assert np.array_equal(dz_new.cpu().numpy(), ref[0])
     assert np.array_equal(dzm.cpu().numpy(), ref[2])
@@ -184,9 +188,9 @@ def test_upsample_bit_exact_vs_c_oracle(oracle_c, n, n_new, cap):
     # merge_sdf gathers by the permutation
     sdf_new = torch.randn(R, n_new, device=DEV)
     merged = torch.zeros(R, n + n_new, device=DEV)
-    _lib.call("nunerf_merge_sdf", sdf.to(DEV).data_ptr(), sdf_new.data_ptr(), dperm.data_ptr(), R, n, n_new,
+    _lib.call("nunerf_merge_sdf", dsdf.data_ptr(), sdf_new.data_ptr(), dperm.data_ptr(), R, n, n_new,
               merged.data_ptr())
-    assert torch.equal(merged, torch.gather(torch.cat([sdf.to(DEV), sdf_new], -1), 1, dperm.long()))
+    assert torch.equal(merged, torch.gather(torch.cat([dsdf, sdf_new], -1), 1, dperm.long()))
 
 
 # ----------------------------------------------------------------------------------------- geometry + compositing
@@ -210,7 +214,9 @@ def test_render_geometry_and_compaction_order():
     o, d = orc.synthetic_rays(R)
     g = torch.Generator().manual_seed(0)
     z = torch.sort(0.8 + 3.7 * torch.rand(R, S, generator=g), dim=-1)[0]
-    out = _geometry(o.to(DEV), d.to(DEV), z.to(DEV).contiguous())
+    do, dd, dzz = o.to(DEV), d.to(DEV), z.to(DEV).contiguous()
+    out = _geometry(do, dd, dzz)
+    torch.cuda.synchronize()
     dists = z[:, 1:] - z[:, :-1]
     dists = torch.cat([dists, dists[:, -1:]], -1)
     pts = o[:, None, :] + d[:, None, :] * (z + dists * 0.5)[..., None]
@@ -238,7 +244,8 @@ def test_composite_forward_and_backward():
     o, d = orc.synthetic_rays(R)
     g = torch.Generator().manual_seed(1)
     z = torch.sort(0.8 + 3.7 * torch.rand(R, S, generator=g), dim=-1)[0]
-    geo = _geometry(o.to(DEV), d.to(DEV), z.to(DEV).contiguous())
+    do, dd, dzz = o.to(DEV), d.to(DEV), z.to(DEV).contiguous()
+    geo = _geometry(do, dd, dzz)
     n_in, n_out = int(geo["counts"][0]), int(geo["counts"][1])
     inner = (geo["slot"] >= 0)
     a_in = (torch.rand(n_in, generator=g) ** 3).to(DEV).requires_grad_(True)
