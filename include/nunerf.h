@@ -36,8 +36,10 @@ typedef struct {
   const float* bias;                         /* [N] or NULL */
   int act;                                   /* 0 none, 1 relu, 2 softplus(beta=100) */
   const void* aux; int ldaux; int aux_lo_off;/* bf16 planes [M, >=N] or NULL */
-  int aux_mode;                              /* 0 none, 1 *= (aux>0), 2 *= 1-exp(-100*aux) */
+  int aux_mode;                              /* 0 none, 1 *= (aux>0), 2 *= 1-exp(-100*aux), 3 *= bit of mask_in */
   const void* add; int ldadd; int add_lo_off;/* bf16 planes added after the mask, or NULL */
+  const void* mask_in; int ldmask_in;        /* aux_mode 3: 1 bit / element, row pitch in bytes (multiple of 8) */
+  void* mask_out; int ldmask_out;            /* optional: bit = (output > 0), same layout (ReLU layers) */
   float out_scale;                           /* applied to the accumulator product (0 or 1.0 = none) */
   void* out; int ldo; int out_lo_off;        /* bf16 planes or NULL */
   float* out_f32; int ldo32;                 /* optional fp32 copy or NULL */

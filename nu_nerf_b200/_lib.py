@@ -23,7 +23,8 @@ class LinearT(C.Structure):
     _fields_ = [("A", vp), ("lda", ci), ("a_lo_off", ci), ("B", vp), ("ldb", ci), ("b_lo_off", ci),
                 ("M", ci), ("N", ci), ("K", ci), ("bias", vp), ("act", ci),
                 ("aux", vp), ("ldaux", ci), ("aux_lo_off", ci), ("aux_mode", ci),
-                ("add", vp), ("ldadd", ci), ("add_lo_off", ci), ("out_scale", cf),
+                ("add", vp), ("ldadd", ci), ("add_lo_off", ci),
+                ("mask_in", vp), ("ldmask_in", ci), ("mask_out", vp), ("ldmask_out", ci), ("out_scale", cf),
                 ("out", vp), ("ldo", ci), ("out_lo_off", ci), ("out_f32", vp), ("ldo32", ci),
                 ("n_store", ci), ("impl", ci)]
 

@@ -338,20 +338,54 @@ __global__ void sdf_bwd2_ew_kernel(const __nv_bfloat16* __restrict__ gts, int ld
                                    const __nv_bfloat16* __restrict__ gs, int ldg, int g_lo, long long M, int N,
                                    int n_real, __nv_bfloat16* u_next, int ldu, int u_lo, __nv_bfloat16* e, int lde,
                                    int e_lo) {
+  // 8 consecutive columns per thread, 16-byte loads / stores
+  const int n8 = N >> 3;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * N) return;
-  long long m = idx / N;
-  int n = (int)(idx % N);
-  float un = 0.f, ev = 0.f;
-  if (n < n_real) {
-    float t = load_planes(gts, m * ldt + n, t_lo);
-    float s = 1.0f - __expf(-100.0f * load_planes(a, m * lda + n, a_lo));
-    float g = load_planes(gs, m * ldg + n, g_lo);
-    un = t * s;
-    ev = t * g * 100.0f * (1.0f - s);
+  if (idx >= M * n8) return;
+  long long m = idx / n8;
+  int n0 = (int)(idx % n8) << 3;
+  auto ld8 = [](const __nv_bfloat16* base, long long off, int lo, float* f) {
+    uint4 h = *reinterpret_cast<const uint4*>(base + off);
+    const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = bf16lo_to_f(w[j]); f[2 * j + 1] = bf16hi_to_f(w[j]); }
+    if (lo) {
+      uint4 l = *reinterpret_cast<const uint4*>(base + off + lo);
+      const uint32_t v[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { f[2 * j] += bf16lo_to_f(v[j]); f[2 * j + 1] += bf16hi_to_f(v[j]); }
+    }
+  };
+  auto st8 = [](__nv_bfloat16* base, long long off, int lo, const float* f) {
+    uint32_t hw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hw[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    if (lo) {
+      uint32_t lw[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        lw[j] = pack_bf16x2(f[2 * j] - bf16lo_to_f(hw[j]), f[2 * j + 1] - bf16hi_to_f(hw[j]));
+      *reinterpret_cast<uint4*>(base + off + lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+  };
+  float t[8], av[8], g[8], un[8], ev[8];
+  ld8(gts, m * ldt + n0, t_lo, t);
+  ld8(a, m * lda + n0, a_lo, av);
+  ld8(gs, m * ldg + n0, g_lo, g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float s = 1.0f - __expf(-100.0f * av[j]);
+    bool real = (n0 + j) < n_real;
+    un[j] = real ? t[j] * s : 0.f;
+    ev[j] = real ? t[j] * g[j] * 100.0f * (1.0f - s) : 0.f;
   }
-  if (u_next && n < n_real) store_planes(u_next, m * ldu + n, u_lo, un);
-  store_planes(e, m * lde + n, e_lo, ev);
+  if (u_next) {
+    if (n0 + 8 <= n_real) st8(u_next, m * ldu + n0, u_lo, un);
+    else
+      for (int j = 0; j < 8 && n0 + j < n_real; ++j) store_planes(u_next, m * ldu + n0 + j, u_lo, un[j]);
+  }
+  st8(e, m * lde + n0, e_lo, ev);
 }
 
 // fp32 [M, C] (+ optional second addend) -> planes at a column offset
@@ -531,8 +565,10 @@ extern "C" int nunerf_sdf_skip_split(const float* u4, const void* a3, int lda, i
 extern "C" int nunerf_sdf_bwd2_ew(const void* gts, int ldt, int t_lo, const void* a, int lda, int a_lo, const void* gs,
                                   int ldg, int g_lo, int M, int N, int n_real, void* u_next, int ldu, int u_lo, void* e,
                                   int lde, int e_lo, void* stream) {
-  NUNERF_REQUIRE(gts && a && gs && e && M > 0 && N > 0, "sdf_bwd2_ew: bad arguments");
-  sdf_bwd2_ew_kernel<<<G1((long long)M * N), 0, ST(stream)>>>(
+  NUNERF_REQUIRE(gts && a && gs && e && M > 0 && N > 0 && N % 8 == 0, "sdf_bwd2_ew: bad arguments");
+  NUNERF_REQUIRE(ldt % 8 == 0 && lda % 8 == 0 && ldg % 8 == 0 && lde % 8 == 0 && (!u_next || ldu % 8 == 0),
+                 "sdf_bwd2_ew: leading dimensions must be multiples of 8");
+  sdf_bwd2_ew_kernel<<<G1((long long)M * (N / 8)), 0, ST(stream)>>>(
       (const __nv_bfloat16*)gts, ldt, t_lo, (const __nv_bfloat16*)a, lda, a_lo, (const __nv_bfloat16*)gs, ldg, g_lo, M, N,
       n_real, (__nv_bfloat16*)u_next, ldu, u_lo, (__nv_bfloat16*)e, lde, e_lo);
   NUNERF_CHECK_LAUNCH("sdf_bwd2_ew_kernel");

@@ -13,6 +13,7 @@
 // TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tma_host.cuh"
 
 #include <cuda.h>
 #include <mutex>
@@ -40,10 +41,10 @@ static EncodeTiledFn get_encode() {
 }
 
 // bf16 row-major [rows, ld]; box = box_cols x box_rows, 128B swizzle (box_cols must be 64)
-static int make_map(CUtensorMap* m, const void* base, long long rows, long long ld, int box_cols, int box_rows) {
+int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return fail("%s", "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
@@ -59,7 +60,7 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, long long 
 }
 
 static int g_num_sms = 0;
-static int num_sms() {
+int num_sms() {
   if (!g_num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -67,266 +68,6 @@ static int num_sms() {
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   return g_num_sms;
-}
-
-// ------------------------------------------------------------------------------------------- linear kernel
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int LIN_THREADS = 192;
-
-struct LinearK {
-  int M, N, nkb, nseg;
-  int a_seg_col[3];   // column offset of the A plane used by segment s
-  int b_seg_plane[3]; // which resident B plane segment s multiplies with
-  int b_planes, b_lo_off;
-  int stages, num_tiles, acc_stride, tmem_cols;
-  const float* bias;
-  int act, aux_mode;
-  const __nv_bfloat16* aux; int ldaux, aux_lo;
-  const __nv_bfloat16* add; int ldadd, add_lo;
-  float out_scale;
-  __nv_bfloat16* out; int ldo, out_lo;
-  float* out32; int ldo32;
-  int n_store;
-};
-
-__device__ __forceinline__ float softplus100(float x) {
-  float t = 100.0f * x;
-  float e = __expf(-fabsf(t));
-  return fmaxf(x, 0.0f) + 0.01f * __logf(1.0f + e);
-}
-
-__global__ void __launch_bounds__(LIN_THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const LinearK p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int b_block_bytes = p.N * 128;
-  uint8_t* sB = smem;
-  uint8_t* sA = sB + (size_t)p.b_planes * p.nkb * b_block_bytes;
-  uint64_t* bars = (uint64_t*)(sA + (size_t)p.stages * A_STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + p.stages;
-  uint64_t* b_full = bars + 2 * p.stages;
-  uint64_t* t_full = b_full + 1;   // [2]
-  uint64_t* t_empty = t_full + 2;  // [2]
-  uint32_t* tmem_ptr = (uint32_t*)(t_empty + 2);
-  float* s_bias = (float*)(tmem_ptr + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&mapA);
-    ptx::prefetch_tmap(&mapB);
-    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
-    ptx::mbar_init(b_full, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 128); }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
-    ptx::tmem_relinquish();
-  }
-  for (int i = threadIdx.x; i < p.N; i += blockDim.x) s_bias[i] = p.bias ? p.bias[i] : 0.0f;
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      ptx::mbar_expect_tx(b_full, (uint32_t)(p.b_planes * p.nkb * b_block_bytes));
-      for (int pl = 0; pl < p.b_planes; ++pl)
-        for (int kb = 0; kb < p.nkb; ++kb)
-          ptx::tma_load_2d(sB + (size_t)(pl * p.nkb + kb) * b_block_bytes, &mapB, b_full, pl * p.b_lo_off + kb * BK, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int s = 0; s < p.nseg; ++s)
-          for (int kb = 0; kb < p.nkb; ++kb) {
-            ptx::mbar_wait(&empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&full[stage], A_STAGE_BYTES);
-            ptx::tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &mapA, &full[stage], p.a_seg_col[s] + kb * BK,
-                             tile * BM);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_bf16(BM, p.N, 0, 0);
-      ptx::mbar_wait(b_full, 0);
-      ptx::tc_fence_after();
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-        ptx::mbar_wait(&t_empty[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.acc_stride);
-        uint32_t accum = 0;
-        for (int s = 0; s < p.nseg; ++s)
-          for (int kb = 0; kb < p.nkb; ++kb) {
-            ptx::mbar_wait(&full[stage], phase);
-            ptx::tc_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
-            const uint32_t b_addr = ptx::smem_u32(sB + (size_t)(p.b_seg_plane[s] * p.nkb + kb) * b_block_bytes);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              uint64_t ad = ptx::smem_desc(a_addr + k * 32, 16, 1024);
-              uint64_t bd = ptx::smem_desc(b_addr + k * 32, 16, 1024);
-              ptx::umma_bf16(d_tmem, ad, bd, idesc, accum);
-              accum = 1;
-            }
-            ptx::tc_commit(&empty[stage]);
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-        ptx::tc_commit(&t_full[acc]);
-      }
-    }
-  } else {
-    // ================= epilogue warps (2..5) =================
-    const int q = warp & 3;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-      ptx::mbar_wait(&t_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      const long long row = (long long)tile * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride);
-      for (int c0 = 0; c0 < p.N; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld16(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        if (!row_ok || c0 >= p.n_store) continue;
-        float x[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c0 + j];
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = fmaxf(x[j], 0.0f);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = softplus100(x[j]);
-        }
-        if (p.aux_mode) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + c0);
-          uint4 h0 = __ldg(ap), h1 = __ldg(ap + 1);
-          uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-          float a[16];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { a[2 * j] = bf16lo_to_f(hw[j]); a[2 * j + 1] = bf16hi_to_f(hw[j]); }
-          if (p.aux_lo) {
-            const uint4* lp = reinterpret_cast<const uint4*>(p.aux + row * p.ldaux + p.aux_lo + c0);
-            uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
-            uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { a[2 * j] += bf16lo_to_f(lw[j]); a[2 * j + 1] += bf16hi_to_f(lw[j]); }
-          }
-          if (p.aux_mode == 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] = a[j] > 0.0f ? x[j] : 0.0f;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x[j] *= (1.0f - __expf(-100.0f * a[j]));
-          }
-        }
-        if (p.out_scale != 1.0f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] *= p.out_scale;
-        }
-        if (p.add) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.add + row * p.ldadd + c0);
-          uint4 h0 = __ldg(ap), h1 = __ldg(ap + 1);
-          uint32_t hw[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { x[2 * j] += bf16lo_to_f(hw[j]); x[2 * j + 1] += bf16hi_to_f(hw[j]); }
-          if (p.add_lo) {
-            const uint4* lp = reinterpret_cast<const uint4*>(p.add + row * p.ldadd + p.add_lo + c0);
-            uint4 l0 = __ldg(lp), l1 = __ldg(lp + 1);
-            uint32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { x[2 * j] += bf16lo_to_f(lw[j]); x[2 * j + 1] += bf16hi_to_f(lw[j]); }
-          }
-        }
-        const bool full16 = (c0 + 16 <= p.n_store);
-        if (p.out) {
-          __nv_bfloat16* op = p.out + row * p.ldo + c0;
-          if (full16) {
-            uint32_t hw[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) hw[j] = pack_bf16x2(x[2 * j], x[2 * j + 1]);
-            uint4* o4 = reinterpret_cast<uint4*>(op);
-            o4[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            o4[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-            if (p.out_lo) {
-              uint32_t lw[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                lw[j] = pack_bf16x2(x[2 * j] - bf16lo_to_f(hw[j]), x[2 * j + 1] - bf16hi_to_f(hw[j]));
-              uint4* l4 = reinterpret_cast<uint4*>(op + p.out_lo);
-              l4[0] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-              l4[1] = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-            }
-          } else {
-            for (int j = 0; j < 16 && c0 + j < p.n_store; ++j) store_planes(op, j, p.out_lo, x[j]);
-          }
-        }
-        if (p.out32) {
-          float* o32 = p.out32 + row * p.ldo32 + c0;
-          if (full16 && (p.ldo32 & 3) == 0) {
-            float4* o4 = reinterpret_cast<float4*>(o32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          } else {
-            for (int j = 0; j < 16 && c0 + j < p.n_store; ++j) o32[j] = x[j];
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&t_empty[acc]);
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-}
-
-// SIMT debug kernel (same contract, reconstructs hi+lo in fp32).  Selected with impl=1; not a fallback:
-// the Python layer only uses it when NUNERF_GEMM_IMPL=simt is set for debugging.
-__global__ void linear_simt_kernel(const __nv_bfloat16* A, int lda, int a_lo, const __nv_bfloat16* B, int ldb, int b_lo,
-                                   int K, const LinearK p) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)p.M * p.n_store;
-  if (idx >= total) return;
-  long long row = idx / p.n_store;
-  int col = (int)(idx % p.n_store);
-  const __nv_bfloat16* a = A + row * lda;
-  const __nv_bfloat16* b = B + (long long)col * ldb;
-  float acc = 0.f;
-  for (int k = 0; k < K; ++k) {
-    float av = __bfloat162float(a[k]) + (a_lo ? __bfloat162float(a[k + a_lo]) : 0.f);
-    float bv = __bfloat162float(b[k]) + (b_lo ? __bfloat162float(b[k + b_lo]) : 0.f);
-    acc = fmaf(av, bv, acc);
-  }
-  float x = acc + (p.bias ? p.bias[col] : 0.f);
-  if (p.act == 1) x = fmaxf(x, 0.f);
-  else if (p.act == 2) x = softplus100(x);
-  if (p.aux_mode) {
-    float av = load_planes(p.aux, row * p.ldaux + col, p.aux_lo);
-    if (p.aux_mode == 1) x = av > 0.f ? x : 0.f;
-    else x *= (1.0f - __expf(-100.0f * av));
-  }
-  x *= p.out_scale;
-  if (p.add) x += load_planes(p.add, row * p.ldadd + col, p.add_lo);
-  if (p.out) store_planes(p.out, row * p.ldo + col, p.out_lo, x);
-  if (p.out32) p.out32[row * p.ldo32 + col] = x;
 }
 
 // ------------------------------------------------------------------------------------------- dW kernel
@@ -494,7 +235,7 @@ __global__ void from_planes_kernel(const __nv_bfloat16* src, int rows, int cols,
   dst[(long long)r * ld_dst + c] = load_planes(src, (long long)r * ld + c, lo_off);
 }
 
-static int env_int(const char* name, int dflt) {
+int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
 }
@@ -506,71 +247,6 @@ using namespace nunerf;
 extern "C" const char* nunerf_last_error(void) { return g_err; }
 extern "C" int nunerf_version(void) { return 100; }
 extern "C" long long nunerf_launch_count(void) { return g_launches.load(); }
-
-extern "C" int nunerf_linear(const nunerf_linear_t* a, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  NUNERF_REQUIRE(a && a->A && a->B, "linear: null operand");
-  NUNERF_REQUIRE(a->M > 0, "linear: M must be positive");
-  NUNERF_REQUIRE(a->N >= 16 && a->N <= 256 && a->N % 16 == 0, "linear: N must be a multiple of 16 in [16,256]");
-  NUNERF_REQUIRE(a->K >= 64 && a->K % 64 == 0, "linear: K must be a positive multiple of 64");
-  NUNERF_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "linear: lda/ldb must be multiples of 8");
-  NUNERF_REQUIRE(a->out || a->out_f32, "linear: no output");
-  NUNERF_REQUIRE(!a->out || (a->ldo % 8 == 0 && a->out_lo_off % 8 == 0), "linear: ldo/out_lo_off must be multiples of 8");
-  NUNERF_REQUIRE(!a->aux_mode || (a->aux && a->ldaux % 8 == 0 && a->aux_lo_off % 8 == 0), "linear: bad aux");
-  NUNERF_REQUIRE(!a->add || (a->ldadd % 8 == 0 && a->add_lo_off % 8 == 0), "linear: bad addend");
-  NUNERF_REQUIRE(((uintptr_t)a->A & 15) == 0 && ((uintptr_t)a->B & 15) == 0, "linear: operands must be 16B aligned");
-  LinearK k;
-  memset(&k, 0, sizeof(k));
-  k.M = a->M; k.N = a->N; k.nkb = a->K / BK;
-  const bool a2 = a->a_lo_off != 0, b2 = a->b_lo_off != 0;
-  // split mode: hi*hi + hi*lo + lo*hi ; mixed cases degrade gracefully
-  k.nseg = 0;
-  k.a_seg_col[k.nseg] = 0; k.b_seg_plane[k.nseg] = 0; k.nseg++;
-  if (b2) { k.a_seg_col[k.nseg] = 0; k.b_seg_plane[k.nseg] = 1; k.nseg++; }
-  if (a2) { k.a_seg_col[k.nseg] = a->a_lo_off; k.b_seg_plane[k.nseg] = 0; k.nseg++; }
-  k.b_planes = b2 ? 2 : 1; k.b_lo_off = a->b_lo_off;
-  k.num_tiles = cdiv(a->M, BM);
-  k.acc_stride = ((a->N + 31) / 32) * 32;
-  int tc = 32;
-  while (tc < 2 * k.acc_stride) tc <<= 1;
-  k.tmem_cols = tc;
-  k.bias = a->bias; k.act = a->act; k.aux_mode = a->aux_mode;
-  k.aux = (const __nv_bfloat16*)a->aux; k.ldaux = a->ldaux; k.aux_lo = a->aux_lo_off;
-  k.add = (const __nv_bfloat16*)a->add; k.ldadd = a->ldadd; k.add_lo = a->add_lo_off;
-  k.out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
-  k.out = (__nv_bfloat16*)a->out; k.ldo = a->ldo; k.out_lo = a->out_lo_off;
-  k.out32 = a->out_f32; k.ldo32 = a->ldo32;
-  k.n_store = (a->n_store > 0 && a->n_store < a->N) ? a->n_store : a->N;
-
-  int impl = a->impl;
-  if (impl == 1) {
-    long long total = (long long)k.M * k.n_store;
-    linear_simt_kernel<<<cdiv(total, 256), 256, 0, stream>>>((const __nv_bfloat16*)a->A, a->lda, a->a_lo_off,
-                                                            (const __nv_bfloat16*)a->B, a->ldb, a->b_lo_off, a->K, k);
-    NUNERF_CHECK_LAUNCH("linear_simt_kernel");
-    return 0;
-  }
-  const size_t b_bytes = (size_t)k.b_planes * k.nkb * a->N * 128;
-  const size_t budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - 1024 /*bias*/;
-  NUNERF_REQUIRE(b_bytes + 2 * A_STAGE_BYTES <= budget, "linear: weight tile does not fit in shared memory (split N)");
-  int stages = (int)((budget - b_bytes) / A_STAGE_BYTES);
-  if (stages > 8) stages = 8;
-  k.stages = stages;
-  const size_t smem = 1024 + b_bytes + (size_t)stages * A_STAGE_BYTES + 256 + 1024;
-  CUtensorMap mapA, mapB;
-  if (int r = make_map(&mapA, a->A, a->M, a->lda, BK, BM)) return r;
-  if (int r = make_map(&mapB, a->B, a->N, a->ldb, BK, a->N)) return r;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return fail("linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e), -2);
-    configured = 227 * 1024;
-  }
-  int grid = k.num_tiles < num_sms() ? k.num_tiles : num_sms();
-  linear_tc_kernel<<<grid, LIN_THREADS, smem, stream>>>(mapA, mapB, k);
-  NUNERF_CHECK_LAUNCH("linear_tc_kernel");
-  return 0;
-}
 
 extern "C" int nunerf_linear_dw(const nunerf_dw_t* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -596,8 +272,8 @@ extern "C" int nunerf_linear_dw(const nunerf_dw_t* a, void* stream_) {
   }
   const bool split = a->z_lo_off != 0 && a->x_lo_off != 0;
   CUtensorMap mapZ, mapX;
-  if (int r = make_map(&mapZ, a->dZ, a->M, a->ldz, 64, 64)) return r;
-  if (int r = make_map(&mapX, a->X, a->M, a->ldx, 64, 64)) return r;
+  if (int r = make_map(&mapZ, a->dZ, a->M, a->ldz, a->ldz, 64, 64)) return r;
+  if (int r = make_map(&mapX, a->X, a->M, a->ldx, a->ldx, 64, 64)) return r;
   const int n_tiles = cdiv(a->N, 128);
   for (int k0 = 0; k0 < a->K; k0 += 256) {
     DwK k;

@@ -234,9 +234,10 @@ def pred_forward(w: PredW, x: P, M, K0, planes):
     t = PredTape()
     t.M, t.x, t.K0 = M, x, K0
     t.H = [P(M, 256, planes, dev) for _ in range(3)]
-    linear(x, w.L[0].Wk, M, 256, K0, bias=w.L[0].b, act=1, out=t.H[0])
-    linear(t.H[0], w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=1, out=t.H[1])
-    linear(t.H[1], w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=1, out=t.H[2])
+    t.Mk = [torch.empty(M, 32, dtype=torch.uint8, device=dev) for _ in range(3)]     # 1-bit ReLU masks
+    linear(x, w.L[0].Wk, M, 256, K0, bias=w.L[0].b, act=1, out=t.H[0], mask_out=t.Mk[0])
+    linear(t.H[0], w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=1, out=t.H[1], mask_out=t.Mk[1])
+    linear(t.H[1], w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=1, out=t.H[2], mask_out=t.Mk[2])
     t.head = _f(M, 16, dev=dev)
     linear(t.H[2], w.L[3].Wk, M, 16, 256, bias=w.L[3].b, out_f32=t.head, n_store=w.n_out)
     return t
@@ -251,11 +252,11 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
     linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3])
     colsum(dz_head, M, w.n_out, gb[3])
     d2, d1 = P(M, 256, planes, dev), P(M, 256, planes, dev)
-    linear(dz_head, w.L[3].WTk, M, 256, 64, aux=t.H[2], aux_mode=1, out=d2)
+    linear(dz_head, w.L[3].WTk, M, 256, 64, mask_in=t.Mk[2], out=d2)
     linear_dw(d2, t.H[1], M, 256, 256, gW[2]); colsum(d2, M, 256, gb[2])
-    linear(d2, w.L[2].WTk, M, 256, 256, aux=t.H[1], aux_mode=1, out=d1)
+    linear(d2, w.L[2].WTk, M, 256, 256, mask_in=t.Mk[1], out=d1)
     linear_dw(d1, t.H[0], M, 256, 256, gW[1]); colsum(d1, M, 256, gb[1])
-    linear(d1, w.L[1].WTk, M, 256, 256, aux=t.H[0], aux_mode=1, out=d2)
+    linear(d1, w.L[1].WTk, M, 256, 256, mask_in=t.Mk[0], out=d2)
     linear_dw(d2, t.x, M, 256, t.K0, gW[0]); colsum(d2, M, 256, gb[0])
     if dx_planes is not None:
         linear(d2, w.L[0].WTk, M, dx_n, 256, out=dx_planes, add=dx_planes if dx_add else None)
@@ -282,17 +283,19 @@ def nerf_forward(w: NerfW, pts, dirs, dists, planes):
     H[4] = P(M, 384, planes, dev)                 # [h4 | PE(84) | 0]
     t.H = H
     call("nunerf_encode_pe", pts4.data_ptr(), M, 4, 10, H[4].ptr, H[4].ld, H[4].lo, 256, 0, 128)
-    linear(t.x0, w.pts[0].Wk, M, 256, 128, bias=w.pts[0].b, act=1, out=H[0])
+    t.Mk = [torch.empty(M, 32, dtype=torch.uint8, device=dev) for _ in range(8)]
+    t.Mv = torch.empty(M, 16, dtype=torch.uint8, device=dev)
+    linear(t.x0, w.pts[0].Wk, M, 256, 128, bias=w.pts[0].b, act=1, out=H[0], mask_out=t.Mk[0])
     for i in range(1, 8):
         K = 384 if i == 5 else 256
-        linear(H[i - 1], w.pts[i].Wk, M, 256, K, bias=w.pts[i].b, act=1, out=H[i])
+        linear(H[i - 1], w.pts[i].Wk, M, 256, K, bias=w.pts[i].b, act=1, out=H[i], mask_out=t.Mk[i])
     t.xv = P(M, 320, planes, dev)                 # [feature | PE4(view) (27) | 0]
     linear(H[7], w.feat.Wk, M, 256, 256, bias=w.feat.b, out=t.xv)
     call("nunerf_encode_pe", views.data_ptr(), M, 3, 4, t.xv.ptr, t.xv.ld, t.xv.lo, 256, 0, 64)
     t.sigma = _f(M, 16, dev=dev)
     linear(H[7], w.alpha.Wk, M, 16, 256, bias=w.alpha.b, out_f32=t.sigma, n_store=1)
     t.hv = P(M, 128, planes, dev)
-    linear(t.xv, w.views.Wk, M, 128, 320, bias=w.views.b, act=1, out=t.hv)
+    linear(t.xv, w.views.Wk, M, 128, 320, bias=w.views.b, act=1, out=t.hv, mask_out=t.Mv)
     t.rgb = _f(M, 16, dev=dev)
     linear(t.hv, w.rgb.Wk, M, 16, 128, bias=w.rgb.b, out_f32=t.rgb, n_store=3)
     alpha, color = _f(M, dev=dev), _f(M, 3, dev=dev)
@@ -313,7 +316,7 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
     linear_dw(dz_rgb, t.hv, M, 3, 128, gw); colsum(dz_rgb, M, 3, gbv)
     g["rgb_linear.weight"], g["rgb_linear.bias"] = gw[:3, :128], gbv[:3]
     dzv = P(M, 128, planes, dev)
-    linear(dz_rgb, w.rgb.WTk, M, 128, 64, aux=t.hv, aux_mode=1, out=dzv)
+    linear(dz_rgb, w.rgb.WTk, M, 128, 64, mask_in=t.Mv, out=dzv)
     gw = w.views.new_grad(); gbv = _z(128, dev=dev)
     linear_dw(dzv, t.xv, M, 128, 320, gw); colsum(dzv, M, 128, gbv)
     g["views_linears.0.weight"], g["views_linears.0.bias"] = gw[:128, :283], gbv
@@ -327,7 +330,7 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
     g["feature_linear.weight"], g["feature_linear.bias"] = gw[:256], gbc[:256]
     g["alpha_linear.weight"], g["alpha_linear.bias"] = ga[0:1], gbc[256:257]
     cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
-    linear(dz8, w.cat8.WTk, M, 256, 320, aux=H[7], aux_mode=1, out=cur)
+    linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
     for i in range(7, 0, -1):
         K = 384 if i == 5 else 256
         gw = w.pts[i].new_grad(); gbv = _z(256, dev=dev)
@@ -338,7 +341,7 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
         else:
             gw_ref = gw[:256, :256]
         g[f"pts_linears.{i}.weight"], g[f"pts_linears.{i}.bias"] = gw_ref, gbv
-        linear(cur, w.pts[i].WTk, M, 256, 256, aux=H[i - 1], aux_mode=1, out=other)
+        linear(cur, w.pts[i].WTk, M, 256, 256, mask_in=t.Mk[i - 1], out=other)
         cur, other = other, cur
     gw = w.pts[0].new_grad(); gbv = _z(256, dev=dev)
     linear_dw(cur, t.x0, M, 256, 128, gw); colsum(cur, M, 256, gbv)

@@ -13,7 +13,7 @@ from ._lib import call, ptr
 BF16 = torch.bfloat16
 # NUNERF_GEMM_IMPL=simt selects the SIMT debug kernels (debugging aid only, never a fallback)
 GEMM_IMPL = 1 if os.environ.get("NUNERF_GEMM_IMPL", "tc") == "simt" else 0
-SMEM_B_BUDGET = 176 * 1024  # bytes of shared memory the resident weight tile may take (>= 3 activation stages left)
+SMEM_B_BUDGET = 148224  # bytes of shared memory the resident weight tile may take (>= 3 activation stages left)
 
 
 def pad(n, m):
@@ -61,13 +61,16 @@ def f32_to_planes(a, dst: P, M, C_, width, col=0, b=None):
 
 
 def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = None, aux_mode=0, aux_col=0,
-           add: P = None, add_col=0, out: P = None, out_col=0, out_f32=None, n_store=0, out_scale=1.0):
+           add: P = None, add_col=0, out: P = None, out_col=0, out_f32=None, n_store=0, out_scale=1.0,
+           mask_in=None, mask_out=None, mask_col=0):
     """out[:, out_col:out_col+N] = epi(A[:, a_col:a_col+K] @ B[b_row:b_row+N, :K]^T); splits N so the weight tile
     stays resident in shared memory (see csrc/gemm.cu)."""
     assert K % 64 == 0 and N % 16 == 0
     planes_b = 2 if B.lo else 1
     n_tile = min(256, (SMEM_B_BUDGET // (K * 2 * planes_b)) // 16 * 16)
     assert n_tile >= 16
+    if n_tile >= 64:
+        n_tile = n_tile // 64 * 64      # 64-column chunks (mask words, TMA-store boxes) never straddle a split
     n_store = n_store if n_store else N
     p = _lib.LinearT()
     for n0 in range(0, N, n_tile):
@@ -79,10 +82,21 @@ def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = 
         p.M, p.N, p.K = M, nt, K
         p.bias = (bias.data_ptr() + 4 * n0) if bias is not None else None
         p.act = act
-        if aux is not None and aux_mode:
+        if aux is not None and aux_mode in (1, 2):
             p.aux, p.ldaux, p.aux_lo_off, p.aux_mode = aux.at(0, aux_col + n0), aux.ld, aux.lo, aux_mode
         else:
             p.aux, p.ldaux, p.aux_lo_off, p.aux_mode = None, 0, 0, 0
+        if mask_in is not None:
+            # uint8 [M, pitch] bit masks; chunks of 64 columns = 8 bytes
+            assert (mask_col + n0) % 64 == 0
+            p.mask_in, p.ldmask_in, p.aux_mode = mask_in.data_ptr() + (mask_col + n0) // 8, mask_in.stride(0), 3
+        else:
+            p.mask_in, p.ldmask_in = None, 0
+        if mask_out is not None:
+            assert n0 % 64 == 0
+            p.mask_out, p.ldmask_out = mask_out.data_ptr() + n0 // 8, mask_out.stride(0)
+        else:
+            p.mask_out, p.ldmask_out = None, 0
         if add is not None:
             p.add, p.ldadd, p.add_lo_off = add.at(0, add_col + n0), add.ld, add.lo
         else:

@@ -336,3 +336,29 @@ def test_bvh_trace_hit_ids_bit_exact(oracle_c, nu, nv):
     assert np.array_equal(tri[sub].cpu().numpy(), ti), "triangle hit ids must be bit exact"
     assert np.array_equal(hit[sub].cpu().numpy(), h) and np.array_equal(t[sub].cpu().numpy(), tt)
     assert hit.sum().item() > 0.5 * N
+
+
+@pytest.mark.parametrize("planes", [1, 2])
+def test_linear_relu_bitmask_roundtrip(planes):
+    """ReLU layers emit 1 bit per element; the backward GEMM masks with those bits instead of re-reading activations."""
+    ops = _ops()
+    M, N, K = 1000, 256, 128
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(M, K, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / K ** 0.5
+    A, B = _mk_planes(x, K, planes), _mk_planes(w, K, planes)
+    out = ops.P(M, N, planes, DEV, zero=True)
+    o32 = torch.zeros(M, N, device=DEV)
+    mask = torch.zeros(M, 32, dtype=torch.uint8, device=DEV)
+    ops.linear(A, B, M, N, K, act=1, out=out, out_f32=o32, mask_out=mask)
+    bits = ((mask[:, :, None] >> torch.arange(8, device=DEV, dtype=torch.uint8)) & 1).reshape(M, 256).bool()
+    assert torch.equal(bits, o32 > 0)
+    assert (out.float() - o32).abs().max().item() <= (2 ** -8 if planes == 1 else 2 ** -15) * o32.abs().max().item() + 1e-6
+    # backward-style GEMM: dX = (dZ W) masked by the bits
+    dz = torch.randn(M, K, device=DEV, generator=g)
+    Z = _mk_planes(dz, K, planes)
+    WT = _mk_planes(w, K, planes)          # any [256, K] operand
+    r1 = torch.zeros(M, N, device=DEV)
+    ops.linear(Z, WT, M, N, K, mask_in=mask, out_f32=r1)
+    ref = (Z.float().double() @ WT.float().double().t()).float() * bits
+    assert (r1 - ref).abs().max().item() < 2e-4 * ref.abs().max().item()
