@@ -159,6 +159,52 @@ def flatten_parameters(net):
     return flat, gflat
 
 
+def profile_step(train_step, inputs, ops, torch):
+    """Per-entry-point device time of one step (CUDA events around every C-ABI call; printed to stderr)."""
+    import collections
+    rec = []
+    orig_call = ops.call
+    from nu_nerf_b200 import engine as eng
+
+    def timed_call(name, *a):
+        key = name
+        if name == "nunerf_linear":
+            p = a[0]._obj
+            key = f"linear K={p.K} N={p.N} act={p.act} aux={p.aux_mode} add={int(bool(p.add))} mask_out={int(bool(p.mask_out))} f32={int(bool(p.out_f32))} bf16={int(bool(p.out))} lo={int(bool(p.a_lo_off))}"
+            nbytes = 2.0 * p.M * (p.K + (p.N if p.out else 0)) * (2 if p.a_lo_off else 1)
+        elif name == "nunerf_linear_dw":
+            p = a[0]._obj
+            key = f"dw K={p.K} N={p.N}"
+            nbytes = 2.0 * p.M * (p.K + p.N) * (2 if p.z_lo_off else 1)
+        else:
+            nbytes = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_call(name, *a)
+        e1.record()
+        rec.append((key, e0, e1, nbytes))
+    ops.call = timed_call
+    eng.call = timed_call
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    try:
+        t0.record()
+        train_step(*inputs)
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.call = orig_call
+        eng.call = orig_call
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for key, e0, e1, nb in rec:
+        a = agg[key]
+        a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += nb
+    tot = sum(v[1] for v in agg.values())
+    print(f"[profile] step {t0.elapsed_time(t1):.2f} ms, inside C-ABI calls {tot:.2f} ms", file=sys.stderr)
+    for key, (n, ms, nb) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+        gbs = f"{nb / ms / 1e6:8.0f} GB/s" if nb else ""
+        print(f"[profile] {ms:8.3f} ms {n:4d}x  {key} {gbs}", file=sys.stderr)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -272,6 +318,8 @@ def run_ours(args):
         torch.cuda.synchronize()
     finally:
         ops.call = orig_call
+    if args.profile:
+        profile_step(train_step, (o_d, d_d, gt_d), ops, torch)
     t_lin = sum(e0.elapsed_time(e1) for e0, e1, *_ in rec) * 1e-3
     fl_lin = sum(2.0 * M * (ns if ns else N) * K for _, _, M, N, K, ns in rec)
     by_lin = sum(2.0 * M * (K + (ns if ns else N)) for _, _, M, N, K, ns in rec)
@@ -333,6 +381,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "split"])
     ap.add_argument("--cpu-rays", type=int, default=128, help="bounded CPU sample (rays per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print a per-entry-point device-time table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
