@@ -292,6 +292,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(1.5)          # nvidia-smi start-up takes driver locks; keep it out of the timed region
+    for _ in range(2):
+        train_step(o_d, d_d, gt_d)
     l0 = _lib.launch_count()
     ms = timed(lambda: train_step(o_d, d_d, gt_d), args.steps)
     launches = (_lib.launch_count() - l0) // args.steps

@@ -186,6 +186,27 @@ int nunerf_sdf_skip_split(const float* u4, const void* a3, int lda, int a_lo, in
 int nunerf_sdf_bwd2_ew(const void* gts, int ldt, int t_lo, const void* a, int lda, int a_lo, const void* gs, int ldg,
                        int g_lo, int M, int N, int n_real, void* u_next, int ldu, int u_lo, void* e, int lde, int e_lo,
                        void* stream);
+/* Per-step weight pipeline (one launch each way instead of hundreds of framework kernels): weight-norm
+ * W = g v / |v| (nn.utils.weight_norm, field.py:121-122, :386-394), optional row/column rotation + scale, conversion to
+ * the bf16 plane operands (K-major W and W^T), padded bias copy; and the adjoint that turns effective-weight gradients
+ * (prepared layout) into gradients of weight_v / weight_g / bias (or the plain weight), accumulated into .grad storage.
+ * One thread block per emitted row: blk_desc[b] / blk_row[b] give the descriptor and the row of block b. */
+typedef struct {
+  const float* v; const float* g;            /* source [N,K] pitch ld; g NULL = plain weight */
+  int N, K, ld; float scale;
+  int row_rot, col_rot, src_row0, n_rows;    /* dst row r <- src row (src_row0 + r + row_rot) % N ; dst col c <- (c + col_rot) % K */
+  void* wk; int wk_ld, wk_lo, wk_row_off;    /* K-major destination or NULL */
+  void* wtk; int wtk_ld, wtk_lo, wtk_col_off;/* transposed destination or NULL */
+  float* inv_norm; float* row_f32;           /* [N] 1/|v| (by source row) ; optional fp32 copy [n_rows,K] */
+  const float* bias_src; float* bias_dst;    /* bias_dst[wk_row_off + r] = bias_src[src row] */
+  const float* dW; int lddw, dw_row_off;     /* backward: gradient of the prepared matrix (NULL = none) */
+  float* dv; float* dg;                      /* accumulated: d weight_v (or d weight) pitch ld ; d weight_g [N] */
+  const float* db; float* dbias;             /* accumulated: dbias[src row] += db[dw_row_off + r] */
+} nunerf_wdesc_t;
+int nunerf_weights_prepare(const nunerf_wdesc_t* descs, const int32_t* blk_desc, const int32_t* blk_row, int n_blocks,
+                           void* stream);
+int nunerf_weights_backward(const nunerf_wdesc_t* descs, const int32_t* blk_desc, const int32_t* blk_row, int n_blocks,
+                            void* stream);
 /* torch.optim.Adam update (train/lr_common_manager.py:11-15) over a flat parameter vector */
 int nunerf_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 int step, void* stream);

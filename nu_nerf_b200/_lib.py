@@ -58,6 +58,15 @@ class ShadeMixT(C.Structure):
                 ("d_rough_raw", vp), ("d_nov", vp)]
 
 
+class WDesc(C.Structure):
+    _fields_ = [("v", vp), ("g", vp), ("N", ci), ("K", ci), ("ld", ci), ("scale", cf),
+                ("row_rot", ci), ("col_rot", ci), ("src_row0", ci), ("n_rows", ci),
+                ("wk", vp), ("wk_ld", ci), ("wk_lo", ci), ("wk_row_off", ci),
+                ("wtk", vp), ("wtk_ld", ci), ("wtk_lo", ci), ("wtk_col_off", ci),
+                ("inv_norm", vp), ("row_f32", vp), ("bias_src", vp), ("bias_dst", vp),
+                ("dW", vp), ("lddw", ci), ("dw_row_off", ci), ("dv", vp), ("dg", vp), ("db", vp), ("dbias", vp)]
+
+
 class BvhNode(C.Structure):
     _fields_ = [("lo", cf * 12), ("hi", cf * 12), ("child", ci * 4), ("count", ci * 4)]
 
@@ -96,6 +105,8 @@ _SIGS = {
     "nunerf_rowvec_mask": [vp, vp, ci, ci, ci, ci, vp, ci, ci, vp],
     "nunerf_sdf_skip_split": [vp, vp, ci, ci, ci, vp, ci, ci, vp, vp],
     "nunerf_sdf_bwd2_ew": [vp, ci, ci, vp, ci, ci, vp, ci, ci, ci, ci, ci, vp, ci, ci, vp, ci, ci, vp],
+    "nunerf_weights_prepare": [vp, vp, vp, ci, vp],
+    "nunerf_weights_backward": [vp, vp, vp, ci, vp],
     "nunerf_adam": [vp, vp, vp, vp, cll, cf, cf, cf, cf, ci, vp],
     "nunerf_bvh_build_host": [vp, ci, vp, ci, vp, ci, vp],
     "nunerf_bvh_trace": [vp, vp, vp, vp, vp, ci, cf, vp, vp, vp, vp],

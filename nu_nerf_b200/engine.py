@@ -16,7 +16,8 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr
-from .ops import P, Dense, linear, linear_dw, colsum, to_planes, f32_to_planes, pad
+from .ops import P, linear, linear_dw, colsum, to_planes, f32_to_planes, pad
+from .weights import Dense, WeightBank
 
 SQRT2 = math.sqrt(2.0)
 F32 = torch.float32
@@ -41,49 +42,63 @@ def sampling_tables(device):
 
 
 # =============================================================================================== weights
+def _wn(mod):
+    """(v, g, bias) of a WNLinear / (weight, None, bias) of a PlainLinear."""
+    if hasattr(mod, "weight_v"):
+        return mod.weight_v, mod.weight_g, mod.bias
+    return mod.weight, None, mod.bias
+
+
 class SdfWeights:
     """Operands of the 9 SDF layers (field.py:64-131).  lin4 is pre-scaled by 1/sqrt(2) (the skip concat
     divides its input, field.py:143); lin8 is split into the feature rows (1..256) and the sdf row (0)."""
 
-    def __init__(self, Ws, bs, planes, head_only=False):
+    def __init__(self, bank, net):
+        lins = net.layers()
         self.L = []
         for l in range(8):
-            self.L.append(Dense(Ws[l], bs[l], planes, scale=(1.0 / SQRT2 if l == 4 else 1.0), need_t=not head_only))
-        W8, b8 = Ws[8], bs[8]
-        self.sdf_head = Dense(W8[0:1], b8[0:1], planes, need_t=False)
-        self.w_sdf = W8[0].detach().contiguous().float()
-        if not head_only:
-            # backward sees lin8 as one layer with rows ordered [features (256), sdf (1)]
-            self.feat = Dense(W8[1:], b8[1:], planes, need_t=False)
-            self.cat8 = Dense(torch.cat([W8[1:], W8[0:1]], 0), None, planes, need_t=True)
+            v, g, b = _wn(lins[l])
+            self.L.append(Dense(bank, v, g, b, scale=(1.0 / SQRT2 if l == 4 else 1.0)))
+        v8, g8, b8 = _wn(lins[8])
+        self.sdf_head = Dense(bank, v8, g8, b8, rows=(0, 1), need_t=False, row_f32=True)
+        self.feat = Dense(bank, v8, g8, b8, rows=(1, 257), need_t=False)
+        # backward sees lin8 as one layer with rows ordered [features (256), sdf (1)]
+        self.cat8 = Dense(bank, v8, g8, None, row_rot=1, need_k=False, need_t=True, grad=False)
+
+    @property
+    def w_sdf(self):
+        return self.sdf_head.row_f32
 
 
 class PredW:
-    """make_predictor (field.py:371-408): 4 dense layers."""
+    """make_predictor (field.py:371-408): 4 dense layers at Sequential indices 0, 2, 4, 6."""
 
-    def __init__(self, Ws, bs, planes, need_dx0=True):
-        self.L = [Dense(Ws[i], bs[i], planes, need_t=(i > 0 or need_dx0)) for i in range(4)]
-        self.n_out = Ws[3].shape[0]
+    def __init__(self, bank, seq, need_dx0=True):
+        self.L = []
+        for j, i in enumerate((0, 2, 4, 6)):
+            v, g, b = _wn(seq[i])
+            self.L.append(Dense(bank, v, g, b, need_t=(j > 0 or need_dx0)))
+        self.n_out = self.L[3].N
 
 
 class NerfW:
     """NeRFNetwork (field.py:212-263).  Layer 5 input is stored [h (256) | PE (84)] so the previous layer can write
-    straight into it: its weight columns are permuted accordingly (reference order is [PE | h], field.py:276)."""
+    straight into it: its weight columns are rotated accordingly (reference order is [PE | h], field.py:276)."""
 
-    def __init__(self, sd, planes):
+    def __init__(self, bank, net):
         self.pts = []
         for i in range(8):
-            W, b = sd[f"pts_linears.{i}.weight"], sd[f"pts_linears.{i}.bias"]
-            if i == 5:
-                W = torch.cat([W[:, 84:], W[:, :84]], 1)
-            self.pts.append(Dense(W, b, planes, need_t=(i > 0)))
-        Wf, bf = sd["feature_linear.weight"], sd["feature_linear.bias"]
-        Wa, ba = sd["alpha_linear.weight"], sd["alpha_linear.bias"]
-        self.feat = Dense(Wf, bf, planes, need_t=False)
-        self.alpha = Dense(Wa, ba, planes, need_t=False)
-        self.cat8 = Dense(torch.cat([Wf, Wa], 0), None, planes, need_t=True)
-        self.views = Dense(sd["views_linears.0.weight"], sd["views_linears.0.bias"], planes)
-        self.rgb = Dense(sd["rgb_linear.weight"], sd["rgb_linear.bias"], planes)
+            v, g, b = _wn(net.pts_linears[i])
+            self.pts.append(Dense(bank, v, g, b, col_rot=(84 if i == 5 else 0), need_t=(i > 0)))
+        vf, _, bf = _wn(net.feature_linear)
+        va, _, ba = _wn(net.alpha_linear)
+        self.feat = Dense(bank, vf, None, bf, need_t=False)
+        self.alpha = Dense(bank, va, None, ba, need_t=False)
+        # backward operand [feature rows (256) ; alpha row (1)]^T, shared buffer filled by two descriptors
+        self.cat8 = Dense(bank, vf, None, None, need_k=False, need_t=True, grad=False, t_cols=320)
+        Dense(bank, va, None, None, need_k=False, need_t=False, grad=False, wtk_share=(self.cat8.WTk, 256))
+        self.views = Dense(bank, *_wn(net.views_linears[0]))
+        self.rgb = Dense(bank, *_wn(net.rgb_linear))
 
 
 # =============================================================================================== SDF network
@@ -155,11 +170,11 @@ def sdf_forward(w: SdfWeights, pts, planes, xm: P):
 
 def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
     """Backward of sdf_forward.  dxm[:, 0:256] holds d feat (planes); d_sdf [M], d_grad [M,3] fp32.
-    Returns (dW list for lin0..7, db list, dW8 [257,256], db8 [257])."""
+    Weight / bias gradients accumulate in the Dense objects (w.L[l].dW / .db, w.feat, w.sdf_head)."""
     M, dev = t.M, t.pts.device
     A, Gs = t.A, t.Gs
-    dW = [w.L[l].new_grad() for l in range(8)]
-    db = [_z(256, dev=dev) for _ in range(8)]
+    dW = [w.L[l].dW for l in range(8)]
+    db = [w.L[l].db for l in range(8)]
     # ---- (a) reverse of the adjoint pass (forward-like chain on u~), produces E_l and the gs (x) u~ weight terms
     E = [P(M, 256, planes, dev) for _ in range(8)]
     ut = P(M, 64, planes, dev)
@@ -169,7 +184,6 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
     gts = P(M, 256, planes, dev)
     u_a, u_b = P(M, 256, planes, dev), P(M, 256, planes, dev)
     u_in, K_in = ut, 64
-    dw_sdf = _z(256, dev=dev)
     for l in range(8):
         N_l = 224 if l == 3 else 256
         linear(u_in, w.L[l].Wk, M, N_l, K_in, out=gts)
@@ -184,16 +198,14 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
         call("nunerf_sdf_bwd2_ew", gts.ptr, gts.ld, gts.lo, A[l].ptr, A[l].ld, A[l].lo, Gs[l].ptr, Gs[l].ld, Gs[l].lo,
              M, 256, n_real, u_next.ptr, u_next.ld, u_next.lo, E[l].ptr, E[l].ld, E[l].lo)
         if l == 7:
-            colsum(u_next, M, 256, dw_sdf)       # d w_sdf = sum_m gts_7 . s_7
+            colsum(u_next, M, 256, w.sdf_head.dW[0])       # d w_sdf += sum_m gts_7 . s_7
         u_in, K_in = u_next, 256
     # ---- (b) backward of the value network; dZ8 = [d feat (256) | d sdf | 0...]
     f32_to_planes(d_sdf, dxm, M, 1, 64, col=256)
-    dW8 = torch.zeros(272, 256, dtype=F32, device=dev)
-    linear_dw(dxm, A[7], M, 256, 256, dW8)
-    dsdf_row = _z(16, 256, dev=dev)
-    linear_dw(dxm, A[7], M, 1, 256, dsdf_row, z_col=256)
-    db8c = _z(320, dev=dev)
-    colsum(dxm, M, 257, db8c)
+    linear_dw(dxm, A[7], M, 256, 256, w.feat.dW)
+    linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256)
+    colsum(dxm, M, 256, w.feat.db)
+    colsum(dxm, M, 1, w.sdf_head.db, z_col=256)
     dz = P(M, 256, planes, dev)
     dz2 = P(M, 256, planes, dev, zero=True)
     linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=dz)
@@ -212,16 +224,6 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
             cur, other = other, cur
     linear_dw(cur, t.x0, M, 256, 64, dW[0])
     colsum(cur, M, 256, db[0])
-    # assemble (undo the lin4 pre-scale and the lin8 row order)
-    gW = []
-    for l in range(8):
-        n, k = w.L[l].N, w.L[l].K
-        g = dW[l][:n, :k]
-        gW.append(g * w.L[l].scale if w.L[l].scale != 1.0 else g)
-    gb = [db[l][:w.L[l].N] for l in range(8)]
-    gW8 = torch.cat([(dsdf_row[0:1] + dw_sdf[None, :]), dW8[:256]], 0)
-    gb8 = torch.cat([db8c[256:257], db8c[:256]])
-    return gW, gb, gW8, gb8
 
 
 # =============================================================================================== predictors
@@ -247,8 +249,8 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
     """dz_head: planes [M,64] (n_out real columns).  Optionally produces dX of the first layer either as planes
     (accumulating when dx_add) or as fp32."""
     M, dev = t.M, t.x.t.device
-    gW = [w.L[i].new_grad() for i in range(4)]
-    gb = [_z(w.L[i].Np, dev=dev) for i in range(4)]
+    gW = [w.L[i].dW for i in range(4)]
+    gb = [w.L[i].db for i in range(4)]
     linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3])
     colsum(dz_head, M, w.n_out, gb[3])
     d2, d1 = P(M, 256, planes, dev), P(M, 256, planes, dev)
@@ -262,7 +264,6 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
         linear(d2, w.L[0].WTk, M, dx_n, 256, out=dx_planes, add=dx_planes if dx_add else None)
     if dx_f32 is not None:
         linear(d2, w.L[0].WTk, M, dx_n, 256, out_f32=dx_f32)
-    return [gW[i][:w.L[i].N, :w.L[i].K] for i in range(4)], [gb[i][:w.L[i].N] for i in range(4)]
 
 
 # =============================================================================================== NeRF++
@@ -311,72 +312,48 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
     dz8 = P(M, 320, planes, dev, zero=True)
     call("nunerf_nerf_out_bwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M, d_alpha.data_ptr(),
          d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0)
-    g = {}
-    gw = w.rgb.new_grad(); gbv = _z(16, dev=dev)
-    linear_dw(dz_rgb, t.hv, M, 3, 128, gw); colsum(dz_rgb, M, 3, gbv)
-    g["rgb_linear.weight"], g["rgb_linear.bias"] = gw[:3, :128], gbv[:3]
+    linear_dw(dz_rgb, t.hv, M, 3, 128, w.rgb.dW); colsum(dz_rgb, M, 3, w.rgb.db)
     dzv = P(M, 128, planes, dev)
     linear(dz_rgb, w.rgb.WTk, M, 128, 64, mask_in=t.Mv, out=dzv)
-    gw = w.views.new_grad(); gbv = _z(128, dev=dev)
-    linear_dw(dzv, t.xv, M, 128, 320, gw); colsum(dzv, M, 128, gbv)
-    g["views_linears.0.weight"], g["views_linears.0.bias"] = gw[:128, :283], gbv
+    linear_dw(dzv, t.xv, M, 128, 320, w.views.dW); colsum(dzv, M, 128, w.views.db)
     linear(dzv, w.views.WTk, M, 256, 128, out=dz8)                       # d feature -> dz8[:, :256]
-    gw = torch.zeros(272, 256, dtype=F32, device=dev)
-    linear_dw(dz8, H[7], M, 256, 256, gw)
-    ga = _z(16, 256, dev=dev)
-    linear_dw(dz8, H[7], M, 1, 256, ga, z_col=256)
-    gbc = _z(320, dev=dev)
-    colsum(dz8, M, 257, gbc)
-    g["feature_linear.weight"], g["feature_linear.bias"] = gw[:256], gbc[:256]
-    g["alpha_linear.weight"], g["alpha_linear.bias"] = ga[0:1], gbc[256:257]
+    linear_dw(dz8, H[7], M, 256, 256, w.feat.dW)
+    linear_dw(dz8, H[7], M, 1, 256, w.alpha.dW, z_col=256)
+    colsum(dz8, M, 256, w.feat.db)
+    colsum(dz8, M, 1, w.alpha.db, z_col=256)
     cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
     linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
     for i in range(7, 0, -1):
         K = 384 if i == 5 else 256
-        gw = w.pts[i].new_grad(); gbv = _z(256, dev=dev)
-        linear_dw(cur, H[i - 1], M, 256, K, gw); colsum(cur, M, 256, gbv)
-        if i == 5:
-            gwr = gw[:256, :340]
-            gw_ref = torch.cat([gwr[:, 256:], gwr[:, :256]], 1)     # back to the reference's [PE | h] column order
-        else:
-            gw_ref = gw[:256, :256]
-        g[f"pts_linears.{i}.weight"], g[f"pts_linears.{i}.bias"] = gw_ref, gbv
+        linear_dw(cur, H[i - 1], M, 256, K, w.pts[i].dW); colsum(cur, M, 256, w.pts[i].db)
         linear(cur, w.pts[i].WTk, M, 256, 256, mask_in=t.Mk[i - 1], out=other)
         cur, other = other, cur
-    gw = w.pts[0].new_grad(); gbv = _z(256, dev=dev)
-    linear_dw(cur, t.x0, M, 256, 128, gw); colsum(cur, M, 256, gbv)
-    g["pts_linears.0.weight"], g["pts_linears.0.bias"] = gw[:256, :84], gbv
-    return g
+    linear_dw(cur, t.x0, M, 256, 128, w.pts[0].dW); colsum(cur, M, 256, w.pts[0].db)
 
 
 # =============================================================================================== sampling
 class Stage1Weights:
-    """All operands of one step, built from the (effective, fp32) weights in `W` -- a dict keyed like the
-    reference state_dict but with weight-norm already applied (`<layer>.weight`)."""
+    """Persistent operands of the whole stage-1 field, refreshed from the module's parameters by ONE launch per step
+    (WeightBank.prepare).  Built once per (module storage, precision)."""
 
-    def __init__(self, Wd, planes, device):
+    def __init__(self, net, planes, device):
         self.planes = planes
-        sdfW = [Wd[f"sdf_network.lin{l}.weight"] for l in range(9)]
-        sdfb = [Wd[f"sdf_network.lin{l}.bias"] for l in range(9)]
-        self.sdf = SdfWeights(sdfW, sdfb, planes)
-        self.nerf = NerfW({k[len("outer_nerf."):]: v for k, v in Wd.items() if k.startswith("outer_nerf.")}, planes)
+        self.bank = WeightBank(planes, device)
+        self.sdf = SdfWeights(self.bank, net.sdf_network)
+        self.nerf = NerfW(self.bank, net.outer_nerf)
         self.pred = {}
         for name, need_dx0 in (("metallic_predictor", True), ("roughness_predictor", True), ("albedo_predictor", True),
                                ("transmisstion_weight", True), ("outer_light", True), ("inner_light", True),
                                ("inner_weight", False), ("refrac_light", False)):
-            pre = f"color_network.{name}"
-            self.pred[name] = PredW([Wd[f"{pre}.{i}.weight"] for i in (0, 2, 4, 6)],
-                                    [Wd[f"{pre}.{i}.bias"] for i in (0, 2, 4, 6)], planes, need_dx0=need_dx0)
-        self.inv_s = torch.exp(Wd["deviation_network.variance"].detach().float() * 10.0).reshape(1).contiguous()
-        self.lut = Wd["color_network.FG_LUT"].detach().float().contiguous()
+            self.pred[name] = PredW(self.bank, getattr(net.color_network, name), need_dx0=need_dx0)
+        self.bank.finalize()
+        self._variance = net.deviation_network.variance
+        self.lut = net.color_network.FG_LUT.detach().float().contiguous()
+        self.inv_s = torch.zeros(1, device=device)
 
-
-class SdfHeadWeights:
-    def __init__(self, Wd, planes):
-        sdfW = [Wd[f"sdf_network.lin{l}.weight"] for l in range(9)]
-        sdfb = [Wd[f"sdf_network.lin{l}.bias"] for l in range(9)]
-        self.sdf = SdfWeights(sdfW, sdfb, planes, head_only=True)
-        self.inv_s = torch.exp(Wd["deviation_network.variance"].detach().float() * 10.0).reshape(1).contiguous()
+    def refresh(self):
+        self.bank.prepare()
+        self.inv_s = torch.exp(self._variance.detach().float() * 10.0).reshape(1).contiguous()
 
 
 _TABLES = {}
@@ -557,20 +534,16 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
          t.slot.data_ptr(), R, S, t.is_nerf, t.rgb_raw.data_ptr(), ptr(d_rgb), ptr(d_acc), ptr(d_bkgr),
          da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
     if t.n_out > 0:
-        for k, v in nerf_backward(w.nerf, t.nerf, da_out, dc_out, planes).items():
-            g["outer_nerf." + k] = v
+        nerf_backward(w.nerf, t.nerf, da_out, dc_out, planes)
 
-    def add_pred(name, gw, gb):
-        for j, i in enumerate((0, 2, 4, 6)):
-            kw, kb = f"color_network.{name}.{i}.weight", f"color_network.{name}.{i}.bias"
-            g[kw] = g[kw] + gw[j] if kw in g else gw[j]
-            g[kb] = g[kb] + gb[j] if kb in g else gb[j]
+    def add_pred(name, _):
+        pass
 
     # ---- specular probe (outer_light on the ray directions)
     if d_spec is not None:
         dzs = P(R, 64, planes, dev, zero=True)
         f32_to_planes(d_spec.contiguous(), dzs, R, 3, 64)
-        add_pred("outer_light", *pred_backward(w.pred["outer_light"], t.ls_, dzs, planes))
+        add_pred("outer_light", pred_backward(w.pred["outer_light"], t.ls_, dzs, planes))
     if M == 0:
         return g
     # ---- shading mix
@@ -579,10 +552,10 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     d_rough, d_nov = _f(M, dev=dev), _f(M, dev=dev)
     call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov)))
     dxo, dxi = _f(3 * M, 128, dev=dev), _f(2 * M, 128, dev=dev)
-    add_pred("outer_light", *pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128))
-    add_pred("inner_light", *pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128))
-    add_pred("inner_weight", *pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes))
-    add_pred("refrac_light", *pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes))
+    add_pred("outer_light", pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128))
+    add_pred("inner_light", pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128))
+    add_pred("inner_weight", pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes))
+    add_pred("refrac_light", pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes))
     # ---- sdf -> alpha
     d_sdf, d_grad = _f(M, dev=dev), _f(M, 3, dev=dev)
     d_inv = _z(1, dev=dev) if want_inv_s else None
@@ -609,12 +582,9 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     first = True
     for name, key in (("metallic_predictor", "metallic"), ("roughness_predictor", "rough"),
                       ("albedo_predictor", "albedo"), ("transmisstion_weight", "trans")):
-        add_pred(name, *pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first,
+        add_pred(name, pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first,
                                       dx_n=256))
         first = False
     # ---- SDF network
-    gW, gb, gW8, gb8 = sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad)
-    for l in range(8):
-        g[f"sdf_network.lin{l}.weight"], g[f"sdf_network.lin{l}.bias"] = gW[l], gb[l]
-    g["sdf_network.lin8.weight"], g["sdf_network.lin8.bias"] = gW8, gb8
+    sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad)
     return g

@@ -51,11 +51,11 @@ class _RenderCoreFn(torch.autograd.Function):
     """ZT:725-793 as one autograd node (see engine.core_forward / core_backward)."""
 
     @staticmethod
-    def forward(ctx, pack, inv_s, *weights):
+    def forward(ctx, pack, inv_s, *params):
         eng = _engine()
-        w, names, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_inv_s = pack
+        w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_inv_s = pack
         t, rgb, acc, bkgr, wts = eng.core_forward(w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max)
-        ctx.tape, ctx.w, ctx.names, ctx.want_inv_s = t, w, names, want_inv_s
+        ctx.tape, ctx.w, ctx.n_params, ctx.want_inv_s = t, w, len(params), want_inv_s
         dev = rgb.device
         if t.n_in > 0:
             gerr, trans, met, occ = t.gerr, t.trans[:, None], t.metallic[:, None], t.occ[:, None]
@@ -72,12 +72,16 @@ class _RenderCoreFn(torch.autograd.Function):
         t = ctx.tape
         c = lambda x: None if x is None else x.contiguous().float()
         has = t.n_in > 0
+        ctx.w.bank.zero_grads()
         g = eng.core_backward(ctx.w, t, c(d_rgb), c(d_acc), c(d_bkgr), c(d_gerr) if has else None,
                               c(d_trans).reshape(-1) if (has and d_trans is not None) else None,
                               c(d_met).reshape(-1) if (has and d_met is not None) else None, c(d_spec), ctx.want_inv_s)
-        grads = [g.get(name) for name in ctx.names]
+        # effective-weight gradients -> d weight_v / d weight_g / d bias, added in place to .grad (one launch);
+        # autograd therefore receives None for the parameter inputs
+        ctx.w.bank.backward()
         ctx.tape = None
-        return (None, g.get("inv_s").reshape(()) if ctx.want_inv_s and "inv_s" in g else None, *grads)
+        return (None, g.get("inv_s").reshape(()) if ctx.want_inv_s and "inv_s" in g else None,
+                *([None] * ctx.n_params))
 
 
 class NeROShapeRenderer(nn.Module):
@@ -181,17 +185,22 @@ class NeROShapeRenderer(nn.Module):
         return 2 if p == "split" else 1
 
     def _prepare(self):
-        if not torch.cuda.is_available() or self.deviation_network.variance.device.type != "cuda":
+        """Operands of this step: persistent WeightBank (rebuilt only if the parameter storage or the precision
+        changed) refreshed from the current parameter values by one kernel launch."""
+        dev = self.deviation_network.variance.device
+        if not torch.cuda.is_available() or dev.type != "cuda":
             raise RuntimeError("nu_nerf_b200 renders on a CUDA device only (no CPU fallback): move the module with .cuda()")
         eng = _engine()
-        Wd = self.effective_weights()
-        w = eng.Stage1Weights(Wd, self._planes(), self.deviation_network.variance.device)
-        return Wd, w
+        key = (self._planes(),) + tuple(p.data_ptr() for p in self.parameters())
+        if getattr(self, "_w", None) is None or self._w_key != key:
+            self._w, self._w_key = eng.Stage1Weights(self, self._planes(), dev), key
+        self._w.refresh()
+        return self._w
 
     # ------------------------------------------------------------------ ZT:572-612
     def sample_ray(self, rays_o, rays_d, near, far, perturb, uniforms=None, prepared=None, trace=None, sphere=False):
         eng = _engine()
-        _, w = prepared if prepared is not None else self._prepare()
+        w = prepared if prepared is not None else self._prepare()
         R, dev = rays_o.shape[0], rays_o.device
         U0 = U1 = None
         if perturb > 0:
@@ -206,15 +215,15 @@ class NeROShapeRenderer(nn.Module):
     # ------------------------------------------------------------------ ZT:725-820
     def render_core(self, rays_o, rays_d, z_vals, human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True,
                     is_nerf=False, prepared=None):
-        Wd, w = prepared if prepared is not None else self._prepare()
-        names = [k for k in Wd if k not in ("deviation_network.variance", "color_network.FG_LUT")
-                 and not k.startswith("infinity_far_bkgr") and not k.startswith("color_network.iors")]
+        w = prepared if prepared is not None else self._prepare()
+        params = [p for d in w.bank.denses if d.has_grad for p in (d.v, d.g, d.bias) if p is not None]
+        params = list({id(p): p for p in params}.values())
         freeze = self.cfg["freeze_inv_s_step"]
         frozen = freeze is not None and step is not None and step < freeze
         inv_s = torch.exp(self.deviation_network.variance * 10.0)
         exp_max = self.color_network.cfg["light_exp_max"]
-        pack = (w, names, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen)
-        rgb, acc, bkgr, gerr, trans, met, spec, weights, occ = _RenderCoreFn.apply(pack, inv_s, *[Wd[k] for k in names])
+        pack = (w, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen)
+        rgb, acc, bkgr, gerr, trans, met, spec, weights, occ = _RenderCoreFn.apply(pack, inv_s, *params)
         inv_s_c = inv_s.clip(1e-6, 1e6)
         if frozen:
             inv_s_c = inv_s_c.detach()
@@ -235,14 +244,14 @@ class NeROShapeRenderer(nn.Module):
         if step is not None and step < 1000:
             raise NotImplementedError("sdf_pts / sdf_vals warm-up outputs (ZT:804-807, step < 1000)")
         if not is_train:
-            outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=(Wd, w)))
+            outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=w))
         outputs["_weights"] = weights
         return outputs
 
     def compute_validation_info(self, z_vals, rays_o, rays_d, weights, human_poses, step, prepared=None):
         """ZT:636-655: depth = sum w z ; normal = (normalize(grad sdf(o + depth d)) + 1) / 2 inside the unit sphere."""
         eng = _engine()
-        _, w = prepared if prepared is not None else self._prepare()
+        w = prepared if prepared is not None else self._prepare()
         with torch.no_grad():
             depth = torch.sum(weights * z_vals, -1, keepdim=True)
             points = (depth * rays_d + rays_o).contiguous()
