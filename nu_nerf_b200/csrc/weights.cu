@@ -14,6 +14,19 @@ namespace nunerf {
 
 constexpr int WTHREADS = 128;
 
+__device__ __forceinline__ double block_sum_d(double x, double* red) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[warp] = x;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < WTHREADS / 32; ++w) t += red[w];
+  return t;
+}
+
 __device__ __forceinline__ float block_sum(float x, float* red) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
@@ -40,7 +53,7 @@ weights_prepare_kernel(const nunerf_wdesc_t* __restrict__ descs, const int32_t* 
     float ss = 0.f;
     for (int k = threadIdx.x; k < d.K; k += WTHREADS) { float x = vrow[k]; ss += x * x; }
     ss = block_sum(ss, red);
-    const float inv = rsqrtf(ss);
+    const float inv = 1.0f / sqrtf(ss);
     if (threadIdx.x == 0 && d.inv_norm) d.inv_norm[src_row] = inv;
     s *= d.g[src_row] * inv;
   }
@@ -60,7 +73,7 @@ weights_prepare_kernel(const nunerf_wdesc_t* __restrict__ descs, const int32_t* 
 __global__ void __launch_bounds__(WTHREADS)
 weights_backward_kernel(const nunerf_wdesc_t* __restrict__ descs, const int32_t* __restrict__ blk_desc,
                         const int32_t* __restrict__ blk_row) {
-  __shared__ float red[WTHREADS / 32];
+  __shared__ double red[WTHREADS / 32];
   const nunerf_wdesc_t d = descs[blk_desc[blockIdx.x]];
   if (!d.dW) return;
   const int r_dst = blk_row[blockIdx.x];
@@ -70,20 +83,24 @@ weights_backward_kernel(const nunerf_wdesc_t* __restrict__ descs, const int32_t*
   float* dvrow = d.dv + (long long)src_row * d.ld;
   if (d.g) {
     // W = (g / |v|) v  ->  dg = (dW . v) / |v| ;  dv = (g / |v|) (dW - v (dW . v) / |v|^2)
-    float dot = 0.f;
+    // (the two terms of dv nearly cancel for some layers: accumulate the row reductions in fp64)
+    double dot = 0.0, ss = 0.0;
     for (int c = threadIdx.x; c < d.K; c += WTHREADS) {
       int sc = c + d.col_rot;
       if (sc >= d.K) sc -= d.K;
-      dot += grow[c] * d.scale * vrow[sc];
+      dot += (double)grow[c] * (double)d.scale * (double)vrow[sc];
+      ss += (double)vrow[sc] * (double)vrow[sc];
     }
-    dot = block_sum(dot, red);
-    const float inv = d.inv_norm[src_row];
-    const float gi = d.g[src_row] * inv;
-    if (threadIdx.x == 0) d.dg[src_row] += dot * inv;
+    dot = block_sum_d(dot, red);
+    ss = block_sum_d(ss, red);
+    const double inv = 1.0 / sqrt(ss);
+    const double gi = (double)d.g[src_row] * inv;
+    if (threadIdx.x == 0) d.dg[src_row] += (float)(dot * inv);
+    const double proj = dot / ss;
     for (int c = threadIdx.x; c < d.K; c += WTHREADS) {
       int sc = c + d.col_rot;
       if (sc >= d.K) sc -= d.K;
-      dvrow[sc] += gi * (grow[c] * d.scale - vrow[sc] * dot * inv * inv);
+      dvrow[sc] += (float)(gi * ((double)grow[c] * (double)d.scale - (double)vrow[sc] * proj));
     }
   } else {
     for (int c = threadIdx.x; c < d.K; c += WTHREADS) {
