@@ -55,6 +55,7 @@ typedef struct {
   int M, N, K;                               /* N <= 256, K % 64 == 0 */
   float* dW; int lddw;
   int impl;
+  float* db;                                 /* optional: db[n] += sum_m dZ[m,n] (the bias gradient), fused */
 } nunerf_dw_t;
 int nunerf_linear_dw(const nunerf_dw_t* p, void* stream);
 

@@ -31,7 +31,7 @@ class LinearT(C.Structure):
 
 class DwT(C.Structure):
     _fields_ = [("dZ", vp), ("ldz", ci), ("z_lo_off", ci), ("X", vp), ("ldx", ci), ("x_lo_off", ci),
-                ("M", ci), ("N", ci), ("K", ci), ("dW", vp), ("lddw", ci), ("impl", ci)]
+                ("M", ci), ("N", ci), ("K", ci), ("dW", vp), ("lddw", ci), ("impl", ci), ("db", vp)]
 
 
 class SdfAlphaT(C.Structure):

@@ -20,22 +20,66 @@ static int ensure_ide() {
 }
 
 // ------------------------------------------------------------------------------------------- positional encoding
-// dst[row_off + m, col_off + j] for j < width; j >= d*(1+2F) is zero fill.
-__global__ void encode_pe_kernel(const float* __restrict__ x, long long M, int d, int F, __nv_bfloat16* dst, int ld,
-                                 int lo_off, int col_off, long long row_off, int width) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * width) return;
-  long long m = idx / width;
-  int j = (int)(idx % width);
-  float v = 0.f;
-  if (j < d) v = x[m * d + j];
-  else if (j < d * (1 + 2 * F)) {
-    int t = (j - d) / d, c = (j - d) % d;
-    int k = t >> 1;
-    float a = x[m * d + c] * (float)(1 << k);
-    v = (t & 1) ? cosf(a) : sinf(a);
+// Row helpers: a thread builds one whole operand row in registers (every index is a compile-time constant once the
+// loops are unrolled) and writes it as 16-byte packed bf16 chunks, hi plane and (split mode) lo plane.
+__device__ __forceinline__ void store8(__nv_bfloat16* dst, long long idx, int lo, const float* v) {
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  *reinterpret_cast<uint4*>(dst + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+  if (lo) {
+    uint32_t l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l[j] = pack_bf16x2(v[2 * j] - bf16lo_to_f(h[j]), v[2 * j + 1] - bf16hi_to_f(h[j]));
+    *reinterpret_cast<uint4*>(dst + idx + lo) = make_uint4(l[0], l[1], l[2], l[3]);
   }
-  store_planes(dst, (row_off + m) * ld + col_off + j, lo_off, v);
+}
+
+// [x (D), sin(2^0 x) (D), cos(2^0 x) (D), sin(2^1 x) (D), ...] (field.py:14-61) -> row[0 .. D(1+2F))
+template <int D, int F>
+__device__ __forceinline__ void fill_pe(float* row, const float* x) {
+#pragma unroll
+  for (int c = 0; c < D; ++c) row[c] = x[c];
+#pragma unroll
+  for (int k = 0; k < F; ++k)
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      float sn, co;
+      sincosf(x[c] * (float)(1 << k), &sn, &co);
+      row[D + (2 * k) * D + c] = sn;
+      row[D + (2 * k + 1) * D + c] = co;
+    }
+}
+
+// dst[row_off + m, col_off + j] for j < width; j >= D(1+2F) is zero fill.  One thread per row.
+template <int D, int F>
+__global__ void __launch_bounds__(128)
+encode_pe_kernel(const float* __restrict__ x, long long M, __nv_bfloat16* dst, int ld, int lo_off, int col_off,
+                 long long row_off, int width) {
+  constexpr int REAL = D * (1 + 2 * F);
+  constexpr int PADW = (REAL + 7) / 8 * 8;
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float xin[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) xin[c] = x[m * D + c];
+  float row[PADW];
+  fill_pe<D, F>(row, xin);
+#pragma unroll
+  for (int j = REAL; j < PADW; ++j) row[j] = 0.f;
+  const long long base = (row_off + m) * ld + col_off;
+  if (((col_off | ld | lo_off) & 7) == 0 && (width & 7) == 0) {
+#pragma unroll
+    for (int c = 0; c < PADW / 8; ++c)
+      if (c * 8 < width) store8(dst, base + c * 8, lo_off, row + c * 8);
+    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = PADW / 8; c * 8 < width; ++c) store8(dst, base + c * 8, lo_off, zero);
+  } else {
+#pragma unroll
+    for (int j = 0; j < PADW; ++j)
+      if (j < width) store_planes(dst, base + j, lo_off, row[j]);
+    for (int j = PADW; j < width; ++j) store_planes(dst, base + j, lo_off, 0.f);
+  }
 }
 
 // grad_x = J_pe^T (ga + gb), PE-6 of a 3-vector (39 columns)
@@ -152,21 +196,10 @@ __global__ void nerf_out_bwd_kernel(const float* __restrict__ sigma, int ld_s, c
 }
 
 // ------------------------------------------------------------------------------------------- shading encode
-__device__ __forceinline__ void write_pe6(__nv_bfloat16* dst, long long base, int lo, const float* v3) {
-  for (int c = 0; c < 3; ++c) store_planes(dst, base + c, lo, v3[c]);
-  for (int k = 0; k < 6; ++k) {
-    float f = (float)(1 << k);
-    for (int c = 0; c < 3; ++c) {
-      float s, co;
-      sincosf(v3[c] * f, &s, &co);
-      store_planes(dst, base + 3 + 6 * k + c, lo, s);
-      store_planes(dst, base + 6 + 6 * k + c, lo, co);
-    }
-  }
-}
-
-// One thread per (point, job): job 0: IDE(n,1); 1: IDE(r,rough); 2: IDE(r,0); 3: PE blocks + nov
-__global__ void shade_encode_fwd_kernel(nunerf_shade_encode_t p) {
+// One thread per (point, job): job 0: IDE(n,1) -> x_outer; 1: IDE(r,rough) -> x_outer + [PE6(p) | IDE] -> x_inner;
+// 2: same at roughness 0; 3: [PE6(p) | PE6(r)] -> x_weight, [PE6(p) | PE6(v)] -> x_refrac, NoV.
+// Every row is written whole (128 columns, zero padded), so the operand buffers need no prior zero fill.
+__global__ void __launch_bounds__(128) shade_encode_fwd_kernel(nunerf_shade_encode_t p) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long M = p.M;
   if (idx >= 4 * M) return;
@@ -174,30 +207,44 @@ __global__ void shade_encode_fwd_kernel(nunerf_shade_encode_t p) {
   long long m = idx % M;
   float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
   float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  float pt[3] = {p.pts[3 * m], p.pts[3 * m + 1], p.pts[3 * m + 2]};
   pw::ShadeDirs s = pw::shade_dirs(g, rd);
-  __nv_bfloat16* xo = (__nv_bfloat16*)p.x_outer;
-  __nv_bfloat16* xi = (__nv_bfloat16*)p.x_inner;
+  float row[128];
   if (job < 3) {
-    float rough = pw::sigmoidf_(p.rough_raw[m * p.ld_rough]);
-    float out[72];
+    __nv_bfloat16* xo = (__nv_bfloat16*)p.x_outer;
+    __nv_bfloat16* xi = (__nv_bfloat16*)p.x_inner;
+    float* out = row + 40;     // IDE block, 16-byte aligned inside the row buffer
     if (job == 0) pw::ide_fwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, out);
-    else pw::ide_fwd(c_ide, s.r[0], s.r[1], s.r[2], job == 1 ? rough : 0.0f, out);
-    long long ro = ((long long)job * M + m) * p.ld_outer;
-    for (int j = 0; j < 72; ++j) store_planes(xo, ro + j, p.lo_outer, out[j]);
+    else pw::ide_fwd(c_ide, s.r[0], s.r[1], s.r[2], job == 1 ? pw::sigmoidf_(p.rough_raw[m * p.ld_rough]) : 0.0f, out);
+#pragma unroll
+    for (int j = 112; j < 128; ++j) row[j] = 0.f;
+    const long long ro = ((long long)job * M + m) * p.ld_outer;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) store8(xo, ro + c * 8, p.lo_outer, out + c * 8);
+#pragma unroll
+    for (int c = 9; c < 16; ++c) store8(xo, ro + c * 8, p.lo_outer, row + 112);
     if (job >= 1) {
-      long long ri = ((long long)(job - 1) * M + m) * p.ld_inner + 39;
-      for (int j = 0; j < 72; ++j) store_planes(xi, ri + j, p.lo_inner, out[j]);
+      // inner input row = [PE6(p) (39) | IDE (72) | 0]: shift the IDE block down by one column
+#pragma unroll
+      for (int j = 39; j < 111; ++j) row[j] = row[j + 1];
+      row[111] = 0.f;
+      fill_pe<3, 6>(row, pt);
+      const long long ri = ((long long)(job - 1) * M + m) * p.ld_inner;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) store8(xi, ri + c * 8, p.lo_inner, row + c * 8);
     }
   } else {
-    float pt[3] = {p.pts[3 * m], p.pts[3 * m + 1], p.pts[3 * m + 2]};
-    write_pe6(xi, m * p.ld_inner, p.lo_inner, pt);
-    write_pe6(xi, (M + m) * p.ld_inner, p.lo_inner, pt);
     __nv_bfloat16* xw = (__nv_bfloat16*)p.x_weight;
     __nv_bfloat16* xr = (__nv_bfloat16*)p.x_refrac;
-    write_pe6(xw, m * p.ld_weight, p.lo_weight, pt);
-    write_pe6(xw, m * p.ld_weight + 39, p.lo_weight, s.r);
-    write_pe6(xr, m * p.ld_refrac, p.lo_refrac, pt);
-    write_pe6(xr, m * p.ld_refrac + 39, p.lo_refrac, s.v);
+    fill_pe<3, 6>(row, pt);
+    fill_pe<3, 6>(row + 39, s.r);
+#pragma unroll
+    for (int j = 78; j < 128; ++j) row[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) store8(xw, m * p.ld_weight + c * 8, p.lo_weight, row + c * 8);
+    fill_pe<3, 6>(row + 39, s.v);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) store8(xr, m * p.ld_refrac + c * 8, p.lo_refrac, row + c * 8);
     p.nov[m] = s.nov;
   }
 }
@@ -235,14 +282,19 @@ __global__ void shade_encode_bwd_kernel(nunerf_shade_encode_t p) {
   p.d_rough_raw[m * p.ld_drough] += drough * rough * (1.0f - rough);
 }
 
-// IDE of M unit directions at a constant roughness (the per-ray specular probe, ZT:780)
-__global__ void ide_encode_kernel(const float* __restrict__ x, long long M, float kinv, __nv_bfloat16* dst, int ld,
-                                  int lo, int col) {
+// IDE of M unit directions at a constant roughness (the per-ray specular probe, ZT:780); writes 128 columns
+// (72 real + zero padding) starting at the 8-aligned column `col`.
+__global__ void __launch_bounds__(128)
+ide_encode_kernel(const float* __restrict__ x, long long M, float kinv, __nv_bfloat16* dst, int ld, int lo, int col) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float out[72];
   pw::ide_fwd(c_ide, x[3 * m], x[3 * m + 1], x[3 * m + 2], kinv, out);
-  for (int j = 0; j < 72; ++j) store_planes(dst, m * ld + col + j, lo, out[j]);
+  const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 9; ++c) store8(dst, m * ld + col + c * 8, lo, out + c * 8);
+#pragma unroll
+  for (int c = 9; c < 16; ++c) store8(dst, m * ld + col + c * 8, lo, zero);
 }
 
 // ------------------------------------------------------------------------------------------- shading mix
@@ -438,8 +490,12 @@ using namespace nunerf;
 extern "C" int nunerf_encode_pe(const float* x, int M, int d, int nfreq, void* dst, int ld, int lo_off, int col_off,
                                 int row_off, int width, void* stream) {
   NUNERF_REQUIRE(x && dst && M > 0 && d > 0 && nfreq >= 0 && width >= d * (1 + 2 * nfreq), "encode_pe: bad arguments");
-  long long total = (long long)M * width;
-  encode_pe_kernel<<<G1(total), 0, ST(stream)>>>(x, M, d, nfreq, (__nv_bfloat16*)dst, ld, lo_off, col_off, row_off, width);
+  const int grid = cdiv(M, 128);
+  __nv_bfloat16* o = (__nv_bfloat16*)dst;
+  if (d == 3 && nfreq == 6) encode_pe_kernel<3, 6><<<grid, 128, 0, ST(stream)>>>(x, M, o, ld, lo_off, col_off, row_off, width);
+  else if (d == 4 && nfreq == 10) encode_pe_kernel<4, 10><<<grid, 128, 0, ST(stream)>>>(x, M, o, ld, lo_off, col_off, row_off, width);
+  else if (d == 3 && nfreq == 4) encode_pe_kernel<3, 4><<<grid, 128, 0, ST(stream)>>>(x, M, o, ld, lo_off, col_off, row_off, width);
+  else return fail("%s", "encode_pe: supported (d, nfreq) are (3,6), (4,10), (3,4)");
   NUNERF_CHECK_LAUNCH("encode_pe_kernel");
   return 0;
 }
@@ -508,7 +564,11 @@ extern "C" int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* str
                      p->x_weight && p->x_refrac && p->nov,
                  "shade_encode_fwd: bad arguments");
   if (int r = ensure_ide()) return r;
-  shade_encode_fwd_kernel<<<G1(4LL * p->M), 0, ST(stream)>>>(*p);
+  NUNERF_REQUIRE(((p->ld_outer | p->lo_outer | p->ld_inner | p->lo_inner | p->ld_weight | p->lo_weight | p->ld_refrac |
+                   p->lo_refrac) & 7) == 0 && p->ld_outer >= 128 && p->ld_inner >= 128 && p->ld_weight >= 128 &&
+                     p->ld_refrac >= 128,
+                 "shade_encode_fwd: operand rows must be >= 128 columns with 8-column aligned pitches");
+  shade_encode_fwd_kernel<<<cdiv(4LL * p->M, 128), 128, 0, ST(stream)>>>(*p);
   NUNERF_CHECK_LAUNCH("shade_encode_fwd_kernel");
   return 0;
 }
@@ -522,7 +582,7 @@ extern "C" int nunerf_shade_encode_bwd(const nunerf_shade_encode_t* p, void* str
   return 0;
 }
 extern "C" int nunerf_ide_encode(const float* x, int M, float kinv, void* dst, int ld, int lo, int col, void* stream) {
-  NUNERF_REQUIRE(x && dst && M > 0, "ide_encode: bad arguments");
+  NUNERF_REQUIRE(x && dst && M > 0 && ((ld | lo | col) & 7) == 0 && ld >= col + 128, "ide_encode: bad arguments");
   if (int r = ensure_ide()) return r;
   ide_encode_kernel<<<cdiv(M, 128), 128, 0, ST(stream)>>>(x, M, kinv, (__nv_bfloat16*)dst, ld, lo, col);
   NUNERF_CHECK_LAUNCH("ide_encode_kernel");

@@ -82,6 +82,8 @@ struct DwK {
   int chunk_pts;           // points per CTA (multiple of 64)
   int stages, stage_bytes, z_bytes_plane, x_bytes_plane, tmem_cols;
   float* dW; int lddw; int dw_col0;
+  float* db;               // optional bias gradient: db[n] += sum_m dZ[m,n] (fused column sum, k0 == 0 launch only)
+  int n_halves;            // 128-row halves of dZ^T handled by one CTA (2 = whole 256-wide layer per CTA)
   uint32_t lbo, sbo;
 };
 
@@ -94,8 +96,9 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
   uint64_t* empty = bars + p.stages;
   uint64_t* t_full = bars + 2 * p.stages;
   uint32_t* tmem_ptr = (uint32_t*)(t_full + 1);
+  float* s_colsum = (float*)(bars + 32);   // 256 floats, 256 bytes past the barrier block
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * 128;
+  const int n0 = blockIdx.x * 128 * p.n_halves;
   const long long m_begin = (long long)blockIdx.y * p.chunk_pts;
   long long m_end = m_begin + p.chunk_pts;
   if (m_end > p.M) m_end = p.M;
@@ -104,7 +107,8 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&mapZ);
     ptx::prefetch_tmap(&mapX);
-    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    // a stage is released by the MMA commit and, when the bias gradient is fused, by the 4 column-sum warps
+    for (int i = 0; i < p.stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], p.db ? 5 : 1); }
     ptx::mbar_init(t_full, 1);
     ptx::fence_barrier_init();
   }
@@ -112,11 +116,13 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
     ptx::tmem_alloc(tmem_ptr, (uint32_t)p.tmem_cols);
     ptx::tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) s_colsum[i] = 0.f;
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int xboxes = p.Kc / 64;
+  const int zboxes = 2 * p.n_halves;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -128,7 +134,7 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
         ptx::mbar_expect_tx(&full[stage], (uint32_t)p.stage_bytes);
         uint8_t* base = smem + (size_t)stage * p.stage_bytes;
         for (int pl = 0; pl < p.z_planes; ++pl)
-          for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < zboxes; ++j)
             ptx::tma_load_2d(base + pl * p.z_bytes_plane + j * DW_BOX_BYTES, &mapZ, &full[stage],
                              pl * p.z_lo + n0 + j * 64, m);
         uint8_t* xb = base + p.z_planes * p.z_bytes_plane;
@@ -150,18 +156,19 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
         ptx::tc_fence_after();
         const uint32_t zb = ptx::smem_u32(smem + (size_t)stage * p.stage_bytes);
         const uint32_t xb = zb + p.z_planes * p.z_bytes_plane;
-        for (int s = 0; s < p.nseg; ++s) {
-          // segments: (z_hi,x_hi), (z_hi,x_lo), (z_lo,x_hi)
-          const uint32_t za = zb + (s == 2 ? p.z_bytes_plane : 0);
-          const uint32_t xa = xb + (s == 1 ? p.x_bytes_plane : 0);
+        for (int h = 0; h < p.n_halves; ++h)
+          for (int s = 0; s < p.nseg; ++s) {
+            // segments: (z_hi,x_hi), (z_hi,x_lo), (z_lo,x_hi)
+            const uint32_t za = zb + (s == 2 ? p.z_bytes_plane : 0) + h * 2 * DW_BOX_BYTES;
+            const uint32_t xa = xb + (s == 1 ? p.x_bytes_plane : 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint64_t ad = ptx::smem_desc(za + k * 2048, p.lbo, p.sbo);
-            uint64_t bd = ptx::smem_desc(xa + k * 2048, p.lbo, p.sbo);
-            ptx::umma_bf16(tmem_base, ad, bd, idesc, accum);
-            accum = 1;
+            for (int k = 0; k < 4; ++k) {
+              uint64_t ad = ptx::smem_desc(za + k * 2048, p.lbo, p.sbo);
+              uint64_t bd = ptx::smem_desc(xa + k * 2048, p.lbo, p.sbo);
+              ptx::umma_bf16(tmem_base + (uint32_t)(h * p.Kc), ad, bd, idesc, (accum || s || k) ? 1u : 0u);
+            }
           }
-        }
+        accum = 1;
         ptx::tc_commit(&empty[stage]);
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -169,18 +176,65 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
     }
   } else if (nsteps > 0) {
     const int q = warp & 3;
+    if (p.db) {
+      // ---- fused bias gradient: column sums of the dZ tiles as they pass through shared memory.
+      // thread t owns the 8 columns of group g = t & 15 (per 128-column half) for the points p = psub + 8 i;
+      // (p & 7) == psub, so the 128B-swizzled 16-byte chunk of those columns sits at ((g & 7) ^ psub).
+      const int t = threadIdx.x - 64;
+      const int g = t & 15, psub = t >> 4;
+      const uint32_t off = (uint32_t)((g >> 3) * DW_BOX_BYTES + psub * 128 + (((g & 7) ^ psub) << 4));
+      float acc[2][8];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[h][j] = 0.f;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int st = 0; st < nsteps; ++st) {
+        ptx::mbar_wait(&full[stage], phase);
+        const uint8_t* zb = smem + (size_t)stage * p.stage_bytes;
+        for (int pl = 0; pl < p.z_planes; ++pl)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h < p.n_halves) {
+              const uint8_t* src = zb + pl * p.z_bytes_plane + h * 2 * DW_BOX_BYTES + off;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(src + i * 1024);
+                acc[h][0] += bf16lo_to_f(v.x); acc[h][1] += bf16hi_to_f(v.x);
+                acc[h][2] += bf16lo_to_f(v.y); acc[h][3] += bf16hi_to_f(v.y);
+                acc[h][4] += bf16lo_to_f(v.z); acc[h][5] += bf16hi_to_f(v.z);
+                acc[h][6] += bf16lo_to_f(v.w); acc[h][7] += bf16hi_to_f(v.w);
+              }
+            }
+          }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (h < p.n_halves)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(&s_colsum[h * 128 + g * 8 + j], acc[h][j]);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = t; c < 128 * p.n_halves; c += 128)
+        if (n0 + c < p.N) atomicAdd(p.db + n0 + c, s_colsum[c]);
+    }
     ptx::mbar_wait(t_full, 0);
     ptx::tc_fence_after();
-    const int n = n0 + q * 32 + lane;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.Kc; c0 += 16) {
-      uint32_t v[16];
-      ptx::tmem_ld16(taddr + c0, v);
-      ptx::tmem_ld_wait();
-      if (n < p.N) {
-        float* dst = p.dW + (long long)n * p.lddw + p.dw_col0 + c0;
+    for (int h = 0; h < p.n_halves; ++h) {
+      const int n = n0 + h * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * p.Kc);
+      for (int c0 = 0; c0 < p.Kc; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld16(taddr + c0, v);
+        ptx::tmem_ld_wait();
+        if (n < p.N) {
+          float* dst = p.dW + (long long)n * p.lddw + p.dw_col0 + c0;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+        }
       }
     }
   }
@@ -274,7 +328,11 @@ extern "C" int nunerf_linear_dw(const nunerf_dw_t* a, void* stream_) {
   CUtensorMap mapZ, mapX;
   if (int r = make_map(&mapZ, a->dZ, a->M, a->ldz, a->ldz, 64, 64)) return r;
   if (int r = make_map(&mapX, a->X, a->M, a->ldx, a->ldx, 64, 64)) return r;
-  const int n_tiles = cdiv(a->N, 128);
+  // one 128-row half of dW per CTA by default (grid = halves x point chunks; the second half re-reads X from L2).
+  // NUNERF_DW_HALVES=2 lets one CTA own the whole <= 256-wide layer (both halves in TMEM): measured SLOWER on B200
+  // (166 us vs 108 us for 384k x 256 x 256, profiles/r1b_micro_dw.txt), kept for experiments only.
+  const int n_halves = (a->N > 128 && !split && env_int("NUNERF_DW_HALVES", 1) == 2) ? 2 : 1;
+  const int n_tiles = cdiv(a->N, 128 * n_halves);
   for (int k0 = 0; k0 < a->K; k0 += 256) {
     DwK k;
     memset(&k, 0, sizeof(k));
@@ -282,15 +340,17 @@ extern "C" int nunerf_linear_dw(const nunerf_dw_t* a, void* stream_) {
     k.z_planes = split ? 2 : 1; k.x_planes = split ? 2 : 1;
     k.z_lo = a->z_lo_off; k.x_lo = a->x_lo_off; k.x_col0 = k0;
     k.nseg = split ? 3 : 1;
-    k.z_bytes_plane = 2 * DW_BOX_BYTES;
+    k.n_halves = n_halves;
+    k.db = (k0 == 0) ? a->db : nullptr;
+    k.z_bytes_plane = n_halves * 2 * DW_BOX_BYTES;
     k.x_bytes_plane = (k.Kc / 64) * DW_BOX_BYTES;
     k.stage_bytes = k.z_planes * k.z_bytes_plane + k.x_planes * k.x_bytes_plane;
-    int stages = (int)((size_t)(224 * 1024) / k.stage_bytes);
+    int stages = (int)((size_t)(223 * 1024) / k.stage_bytes);
     if (stages > 6) stages = 6;
     NUNERF_REQUIRE(stages >= 2, "dw: stage does not fit");
     k.stages = stages;
     int tc = 32;
-    while (tc < k.Kc) tc <<= 1;
+    while (tc < n_halves * k.Kc) tc <<= 1;
     k.tmem_cols = tc;
     k.dW = a->dW; k.lddw = a->lddw; k.dw_col0 = k0;
     k.lbo = (uint32_t)env_int("NUNERF_DW_LBO", 8192);
@@ -301,7 +361,7 @@ extern "C" int nunerf_linear_dw(const nunerf_dw_t* a, void* stream_) {
     if (chunks > steps_total) chunks = steps_total;
     k.chunk_pts = cdiv(steps_total, chunks) * 64;
     chunks = cdiv(a->M, k.chunk_pts);
-    const size_t smem = 1024 + (size_t)k.stages * k.stage_bytes + 256;
+    const size_t smem = 1024 + (size_t)k.stages * k.stage_bytes + 256 + 1024;
     dw_tc_kernel<<<dim3(n_tiles, chunks), DW_THREADS, smem, stream>>>(mapZ, mapX, k);
     NUNERF_CHECK_LAUNCH("dw_tc_kernel");
   }

@@ -7,8 +7,10 @@
 
 #ifdef __CUDACC__
 #define PW_HD __host__ __device__ __forceinline__
+#define PW_UNROLL _Pragma("unroll")
 #else
 #define PW_HD inline
+#define PW_UNROLL
 #endif
 
 namespace nunerf {
@@ -47,18 +49,30 @@ inline void build_ide_table(IdeTable* t) {
   }
 }
 
+// (m, l) of term i as compile-time functions: once the term loop is fully unrolled every table index below is a
+// constant, so re/im/out live in registers and the coefficients are constant-bank operands (no local memory).
+PW_HD constexpr int ide_l(int i) { return i < 2 ? 1 : i < 5 ? 2 : i < 10 ? 4 : i < 19 ? 8 : 16; }
+PW_HD constexpr int ide_m(int i) { return i < 2 ? i : i < 5 ? i - 2 : i < 10 ? i - 5 : i < 19 ? i - 10 : i - 19; }
+
 // out[0..35] = Re, out[36..71] = Im of (x+iy)^m P_i(z) exp(-sigma_i kinv)
 PW_HD void ide_fwd(const IdeTable& tb, float x, float y, float z, float kinv, float* out) {
   float re[17], im[17];
   re[0] = 1.f; im[0] = 0.f;
+PW_UNROLL
   for (int m = 1; m <= 16; ++m) { re[m] = re[m - 1] * x - im[m - 1] * y; im[m] = re[m - 1] * y + im[m - 1] * x; }
+  // attenuation per degree l (5 distinct values): exp(-0.5 l (l+1) kinv)
+  float att[5];
+PW_UNROLL
+  for (int e = 0; e < 5; ++e) { const int l = 1 << e; att[e] = expf(-0.5f * (float)(l * (l + 1)) * kinv); }
+PW_UNROLL
   for (int i = 0; i < IDE_TERMS; ++i) {
-    int deg = tb.l[i] - tb.m[i];
+    const int l = ide_l(i), m = ide_m(i), deg = l - m;
+    const int e = l == 1 ? 0 : l == 2 ? 1 : l == 4 ? 2 : l == 8 ? 3 : 4;
     float p = tb.mat[deg][i];
+PW_UNROLL
     for (int k = deg - 1; k >= 0; --k) p = p * z + tb.mat[k][i];
-    float a = expf(-tb.sigma[i] * kinv);
-    out[i] = re[tb.m[i]] * p * a;
-    out[IDE_TERMS + i] = im[tb.m[i]] * p * a;
+    out[i] = re[m] * p * att[e];
+    out[IDE_TERMS + i] = im[m] * p * att[e];
   }
 }
 
@@ -66,17 +80,24 @@ PW_HD void ide_bwd(const IdeTable& tb, float x, float y, float z, float kinv, co
                    float* dz, float* dkinv) {
   float re[17], im[17];
   re[0] = 1.f; im[0] = 0.f;
+PW_UNROLL
   for (int m = 1; m <= 16; ++m) { re[m] = re[m - 1] * x - im[m - 1] * y; im[m] = re[m - 1] * y + im[m - 1] * x; }
+  float att[5];
+PW_UNROLL
+  for (int e = 0; e < 5; ++e) { const int l = 1 << e; att[e] = expf(-0.5f * (float)(l * (l + 1)) * kinv); }
   float gx = 0.f, gy = 0.f, gz = 0.f, gk = 0.f;
+PW_UNROLL
   for (int i = 0; i < IDE_TERMS; ++i) {
-    int m = tb.m[i], deg = tb.l[i] - m;
+    const int l = ide_l(i), m = ide_m(i), deg = l - m;
+    const int e = l == 1 ? 0 : l == 2 ? 1 : l == 4 ? 2 : l == 8 ? 3 : 4;
     float p = tb.mat[deg][i], dp = 0.f;
+PW_UNROLL
     for (int k = deg - 1; k >= 0; --k) { dp = dp * z + p; p = p * z + tb.mat[k][i]; }
-    float a = expf(-tb.sigma[i] * kinv);
+    const float a = att[e];
     float dr = dout[i], di = dout[IDE_TERMS + i];
     float s = dr * re[m] + di * im[m];
     gz += s * a * dp;
-    gk += s * p * a * (-tb.sigma[i]);
+    gk += s * p * a * (-0.5f * (float)(l * (l + 1)));
     if (m > 0) {
       float dre = dr * p * a, dim = di * p * a, fm = (float)m;
       gx += fm * (dre * re[m - 1] + dim * im[m - 1]);

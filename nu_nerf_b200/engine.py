@@ -202,18 +202,15 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
         u_in, K_in = u_next, 256
     # ---- (b) backward of the value network; dZ8 = [d feat (256) | d sdf | 0...]
     f32_to_planes(d_sdf, dxm, M, 1, 64, col=256)
-    linear_dw(dxm, A[7], M, 256, 256, w.feat.dW)
-    linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256)
-    colsum(dxm, M, 256, w.feat.db)
-    colsum(dxm, M, 1, w.sdf_head.db, z_col=256)
+    linear_dw(dxm, A[7], M, 256, 256, w.feat.dW, db=w.feat.db)
+    linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256, db=w.sdf_head.db)
     dz = P(M, 256, planes, dev)
     dz2 = P(M, 256, planes, dev, zero=True)
     linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=dz)
     cur, other = dz, dz2
     for l in range(7, 0, -1):
         n_l = 217 if l == 3 else 256
-        linear_dw(cur, A[l - 1], M, n_l, 256, dW[l])
-        colsum(cur, M, n_l, db[l])
+        linear_dw(cur, A[l - 1], M, n_l, 256, dW[l], db=db[l])
         if l == 4:
             # input of lin4 is [a3 | PE]: only the first 217 columns carry on (PE has no parameters upstream)
             nxt = P(M, 256, planes, dev, zero=True)
@@ -222,8 +219,7 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
         else:
             linear(cur, w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, add=E[l - 1], out=other)
             cur, other = other, cur
-    linear_dw(cur, t.x0, M, 256, 64, dW[0])
-    colsum(cur, M, 256, db[0])
+    linear_dw(cur, t.x0, M, 256, 64, dW[0], db=db[0])
 
 
 # =============================================================================================== predictors
@@ -251,15 +247,14 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
     M, dev = t.M, t.x.t.device
     gW = [w.L[i].dW for i in range(4)]
     gb = [w.L[i].db for i in range(4)]
-    linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3])
-    colsum(dz_head, M, w.n_out, gb[3])
+    linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3], db=gb[3])
     d2, d1 = P(M, 256, planes, dev), P(M, 256, planes, dev)
     linear(dz_head, w.L[3].WTk, M, 256, 64, mask_in=t.Mk[2], out=d2)
-    linear_dw(d2, t.H[1], M, 256, 256, gW[2]); colsum(d2, M, 256, gb[2])
+    linear_dw(d2, t.H[1], M, 256, 256, gW[2], db=gb[2])
     linear(d2, w.L[2].WTk, M, 256, 256, mask_in=t.Mk[1], out=d1)
-    linear_dw(d1, t.H[0], M, 256, 256, gW[1]); colsum(d1, M, 256, gb[1])
+    linear_dw(d1, t.H[0], M, 256, 256, gW[1], db=gb[1])
     linear(d1, w.L[1].WTk, M, 256, 256, mask_in=t.Mk[0], out=d2)
-    linear_dw(d2, t.x, M, 256, t.K0, gW[0]); colsum(d2, M, 256, gb[0])
+    linear_dw(d2, t.x, M, 256, t.K0, gW[0], db=gb[0])
     if dx_planes is not None:
         linear(d2, w.L[0].WTk, M, dx_n, 256, out=dx_planes, add=dx_planes if dx_add else None)
     if dx_f32 is not None:
@@ -312,23 +307,21 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
     dz8 = P(M, 320, planes, dev, zero=True)
     call("nunerf_nerf_out_bwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M, d_alpha.data_ptr(),
          d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0)
-    linear_dw(dz_rgb, t.hv, M, 3, 128, w.rgb.dW); colsum(dz_rgb, M, 3, w.rgb.db)
+    linear_dw(dz_rgb, t.hv, M, 3, 128, w.rgb.dW, db=w.rgb.db)
     dzv = P(M, 128, planes, dev)
     linear(dz_rgb, w.rgb.WTk, M, 128, 64, mask_in=t.Mv, out=dzv)
-    linear_dw(dzv, t.xv, M, 128, 320, w.views.dW); colsum(dzv, M, 128, w.views.db)
+    linear_dw(dzv, t.xv, M, 128, 320, w.views.dW, db=w.views.db)
     linear(dzv, w.views.WTk, M, 256, 128, out=dz8)                       # d feature -> dz8[:, :256]
-    linear_dw(dz8, H[7], M, 256, 256, w.feat.dW)
-    linear_dw(dz8, H[7], M, 1, 256, w.alpha.dW, z_col=256)
-    colsum(dz8, M, 256, w.feat.db)
-    colsum(dz8, M, 1, w.alpha.db, z_col=256)
+    linear_dw(dz8, H[7], M, 256, 256, w.feat.dW, db=w.feat.db)
+    linear_dw(dz8, H[7], M, 1, 256, w.alpha.dW, z_col=256, db=w.alpha.db)
     cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
     linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
     for i in range(7, 0, -1):
         K = 384 if i == 5 else 256
-        linear_dw(cur, H[i - 1], M, 256, K, w.pts[i].dW); colsum(cur, M, 256, w.pts[i].db)
+        linear_dw(cur, H[i - 1], M, 256, K, w.pts[i].dW, db=w.pts[i].db)
         linear(cur, w.pts[i].WTk, M, 256, 256, mask_in=t.Mk[i - 1], out=other)
         cur, other = other, cur
-    linear_dw(cur, t.x0, M, 256, 128, w.pts[0].dW); colsum(cur, M, 256, w.pts[0].db)
+    linear_dw(cur, t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
 
 
 # =============================================================================================== sampling
@@ -458,8 +451,9 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
         # material predictors on [feature | p]
         t.mat = {k: pred_forward(w.pred[k], t.xm, M, 320, planes) for k in _MAT}
         # directions + encodings
-        t.xo, t.xi = P(3 * M, 128, planes, dev, zero=True), P(2 * M, 128, planes, dev, zero=True)
-        t.xw, t.xr = P(M, 128, planes, dev, zero=True), P(M, 128, planes, dev, zero=True)
+        # (the encode kernel writes whole 128-column rows, zero padded: no prior fill needed)
+        t.xo, t.xi = P(3 * M, 128, planes, dev), P(2 * M, 128, planes, dev)
+        t.xw, t.xr = P(M, 128, planes, dev), P(M, 128, planes, dev)
         t.nov = _f(M, dev=dev)
         se = _lib.ShadeEncodeT()
         se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.sdf.grad.data_ptr(), t.dirs_in.data_ptr()
@@ -486,7 +480,7 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
          t.slot.data_ptr(), R, S, t.is_nerf, rgb.data_ptr(), t.rgb_raw.data_ptr(), acc.data_ptr(), bkgr.data_ptr(),
          weights.data_ptr())
     # ---- per-ray specular probe: outer_light(IDE(d, 0)) (ZT:780-781), activation applied by the caller
-    t.xs = P(R, 128, planes, dev, zero=True)
+    t.xs = P(R, 128, planes, dev)
     t.dn = _norm_dirs(d)
     call("nunerf_ide_encode", t.dn.data_ptr(), R, 0.0, t.xs.ptr, t.xs.ld, t.xs.lo, 0)
     t.ls_ = pred_forward(w.pred["outer_light"], t.xs, R, 128, planes)

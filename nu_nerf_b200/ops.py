@@ -115,8 +115,9 @@ def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = 
         call("nunerf_linear", C.byref(p))
 
 
-def linear_dw(dZ: P, X: P, M, N, K, dW, *, z_col=0, x_col=0):
-    """dW[:N, :K] += dZ[:, z_col:z_col+N]^T @ X[:, x_col:x_col+K]   (dW fp32, pre-zeroed / accumulating)."""
+def linear_dw(dZ: P, X: P, M, N, K, dW, *, z_col=0, x_col=0, db=None):
+    """dW[:N, :K] += dZ[:, z_col:z_col+N]^T @ X[:, x_col:x_col+K]   (dW fp32, pre-zeroed / accumulating);
+    db[:N] += column sums of dZ (the bias gradient) in the same launch when given."""
     assert K % 64 == 0
     p = _lib.DwT()
     p.dZ, p.ldz, p.z_lo_off = dZ.at(0, z_col), dZ.ld, dZ.lo
@@ -124,6 +125,12 @@ def linear_dw(dZ: P, X: P, M, N, K, dW, *, z_col=0, x_col=0):
     p.M, p.N, p.K = M, N, K
     p.dW, p.lddw = dW.data_ptr(), dW.stride(0)
     p.impl = GEMM_IMPL
+    p.db = None
+    if db is not None:
+        if GEMM_IMPL == 1:
+            colsum(dZ, M, N, db, z_col=z_col)
+        else:
+            p.db = db.data_ptr()
     call("nunerf_linear_dw", C.byref(p))
 
 

@@ -102,14 +102,22 @@ def test_linear_dw_matches_torch(planes, M, N, K):
     Z = _mk_planes(z, ops.pad(N, 64), planes)
     X = _mk_planes(x, K, planes)
     dW = torch.zeros(ops.pad(N, 16), K, device=DEV)
-    ops.linear_dw(Z, X, M, N, K, dW)
+    db = torch.zeros(ops.pad(N, 16), device=DEV)
+    ops.linear_dw(Z, X, M, N, K, dW, db=db)          # bias gradient fused into the same launch
     ref = (Z.float()[:, :N].double().t() @ X.float().double()).float()
     scale = ref.abs().max().item()
     err = (dW[:N] - ref).abs().max().item()
     assert err < 2e-4 * scale, (err, scale)
+    ref_b = Z.float()[:, :N].double().sum(0).float()
+    assert (db[:N] - ref_b).abs().max().item() < 1e-3 * M ** 0.5
+    assert db[N:].abs().max().item() == 0 if db.shape[0] > N else True
     bsum = torch.zeros(N, device=DEV)
     ops.colsum(Z, M, N, bsum)
-    assert (bsum - Z.float()[:, :N].sum(0)).abs().max().item() < 1e-3 * M ** 0.5
+    assert (bsum - ref_b).abs().max().item() < 1e-3 * M ** 0.5
+    # accumulation semantics: a second call adds
+    ops.linear_dw(Z, X, M, N, K, dW, db=db)
+    assert (dW[:N] - 2 * ref).abs().max().item() < 4e-4 * scale
+    assert (db[:N] - 2 * ref_b).abs().max().item() < 2e-3 * M ** 0.5
 
 
 # ----------------------------------------------------------------------------------------- sampling

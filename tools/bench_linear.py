@@ -64,10 +64,21 @@ def main():
         nbytes = 2.0 * M * (K + N) + (2.0 * M * N if "aux" in kw else 0) + (2.0 * M * N if "add" in kw else 0)
         print(f"linear {name:22s} {ms*1e3:8.1f} us  {nbytes/ms/1e6:7.0f} GB/s (algorithmic)  {2.0*M*N*K/ms/1e9:7.1f} TFLOP/s", flush=True)
     if not only:
-        Z, X = mk(M, 256, planes), mk(M, 256, planes)
+        zx = [(mk(M, 256, planes), mk(M, 256, planes)) for _ in range(3)]
+        Z, X = zx[0]
         dW = torch.zeros(256, 256, device=DEV)
-        ms = timeit(lambda: ops.linear_dw(Z, X, M, 256, 256, dW))
-        print(f"dw 256x256             {ms*1e3:8.1f} us  {2.0*M*512/ms/1e6:7.0f} GB/s", flush=True)
+        db = torch.zeros(256, device=DEV)
+
+        def dwrun(with_db):
+            def f():
+                Zi, Xi = zx[it[0] % 3]
+                it[0] += 1
+                ops.linear_dw(Zi, Xi, M, 256, 256, dW, db=db if with_db else None)
+            return f
+        for with_db in (False, True):
+            ms = timeit(dwrun(with_db))
+            print(f"dw 256x256 db={int(with_db)}        {ms*1e3:8.1f} us  {2.0*M*512/ms/1e6:7.0f} GB/s  "
+                  f"{2.0*M*65536/ms/1e9:7.1f} TFLOP/s", flush=True)
         s = torch.zeros(256, device=DEV)
         ms = timeit(lambda: ops.colsum(Z, M, 256, s))
         print(f"colsum                 {ms*1e3:8.1f} us  {2.0*M*256/ms/1e6:7.0f} GB/s", flush=True)
