@@ -59,6 +59,20 @@ typedef struct {
 } nunerf_dw_t;
 int nunerf_linear_dw(const nunerf_dw_t* p, void* stream);
 
+/* Fused SDF query (SDFNetwork.sdf, field.py:133-152): PE-6 computed in-kernel, 8 Softplus(beta=100) layers with the
+ * skip concat, 1-row sdf head; the activations stay in shared memory / TMEM between layers (csrc/chain.cu).  Used for
+ * the no-grad SDF passes of sample_ray (ZT:598, :563), extract_fields (field.py:1286-1307) and the occlusion probes
+ * (field.py:524-554).  w[l]: K-major bf16 weight of lin_l zero padded to [256,64], [256,256] x2, [224,256], [256,256] x4
+ * and (w[8]) the sdf row of lin8 padded to [16,256]; lin4 pre-scaled by 1/sqrt(2); bias[l] fp32 padded alike. */
+#define NUNERF_CHAIN_MAX_LAYERS 10
+typedef struct {
+  const float* pts; int M;                   /* [M,3] */
+  const void* w[9]; int ldw[9];
+  const float* bias[9];
+  float* sdf; int ld_sdf;                    /* sdf[m * ld_sdf] */
+} nunerf_sdf_infer_t;
+int nunerf_sdf_infer(const nunerf_sdf_infer_t* p, void* stream);
+
 /* out[n] += sum_m Z[m,n] (hi + lo) -- the bias gradient */
 int nunerf_colsum(const void* Z, int ldz, int z_lo_off, int M, int N, float* out, void* stream);
 /* fp32 [rows, cols] (ld_src) -> the block dst[row_off:+dst_rows, col_off:+dst_cols] of a bf16 plane matrix, zero
@@ -154,6 +168,8 @@ typedef struct {
   const float* d_nov;
   float* d_grad;                                             /* [M,3] accumulated */
   float* d_rough_raw; int ld_drough;                         /* accumulated */
+  float* refl;                                               /* optional forward output [M,3]: reflected direction
+                                                                (occ_info['reflective'], field.py:688, :744) */
 } nunerf_shade_encode_t;
 int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* stream);
 /* IDE(x, kinv) of M unit directions at one constant roughness -> planes (per-ray specular probe, ZT:780) */
@@ -175,6 +191,7 @@ typedef struct {
   void* dz_metallic; void* dz_albedo; void* dz_trans; void* dz_outer; void* dz_inner; void* dz_weight; void* dz_refrac;
   int ld_dz; int lo_dz;
   float* d_rough_raw; float* d_nov;       /* fp32 [M] */
+  const float* d_occ_prob;                /* optional [M]: gradient w.r.t. the occ_prob output (occlusion loss) */
 } nunerf_shade_mix_t;
 int nunerf_shade_mix_fwd(const nunerf_shade_mix_t* p, void* stream);
 int nunerf_shade_mix_bwd(const nunerf_shade_mix_t* p, void* stream);

@@ -34,6 +34,10 @@ class DwT(C.Structure):
                 ("M", ci), ("N", ci), ("K", ci), ("dW", vp), ("lddw", ci), ("impl", ci), ("db", vp)]
 
 
+class SdfInferT(C.Structure):
+    _fields_ = [("pts", vp), ("M", ci), ("w", vp * 9), ("ldw", ci * 9), ("bias", vp * 9), ("sdf", vp), ("ld_sdf", ci)]
+
+
 class SdfAlphaT(C.Structure):
     _fields_ = [("M", ci), ("cos_anneal", cf), ("inv_s_dev", vp), ("sdf", vp), ("ld_sdf", ci), ("grad", vp),
                 ("dists", vp), ("dirs", vp), ("alpha", vp), ("grad_err", vp), ("d_alpha", vp), ("d_grad_err", vp),
@@ -45,7 +49,7 @@ class ShadeEncodeT(C.Structure):
                 ("x_outer", vp), ("ld_outer", ci), ("lo_outer", ci), ("x_inner", vp), ("ld_inner", ci), ("lo_inner", ci),
                 ("x_weight", vp), ("ld_weight", ci), ("lo_weight", ci), ("x_refrac", vp), ("ld_refrac", ci),
                 ("lo_refrac", ci), ("nov", vp), ("d_x_outer", vp), ("ld_dxo", ci), ("d_x_inner", vp), ("ld_dxi", ci),
-                ("d_nov", vp), ("d_grad", vp), ("d_rough_raw", vp), ("ld_drough", ci)]
+                ("d_nov", vp), ("d_grad", vp), ("d_rough_raw", vp), ("ld_drough", ci), ("refl", vp)]
 
 
 class ShadeMixT(C.Structure):
@@ -55,7 +59,7 @@ class ShadeMixT(C.Structure):
                 ("trans_out", vp), ("metallic_out", vp), ("occ_prob", vp), ("d_color", vp), ("d_trans_out", vp),
                 ("d_metallic_out", vp), ("dz_metallic", vp), ("dz_albedo", vp), ("dz_trans", vp), ("dz_outer", vp),
                 ("dz_inner", vp), ("dz_weight", vp), ("dz_refrac", vp), ("ld_dz", ci), ("lo_dz", ci),
-                ("d_rough_raw", vp), ("d_nov", vp)]
+                ("d_rough_raw", vp), ("d_nov", vp), ("d_occ_prob", vp)]
 
 
 class WDesc(C.Structure):
@@ -77,6 +81,7 @@ lib.nunerf_launch_count.restype = cll
 _SIGS = {
     "nunerf_linear": [C.POINTER(LinearT), vp],
     "nunerf_linear_dw": [C.POINTER(DwT), vp],
+    "nunerf_sdf_infer": [C.POINTER(SdfInferT), vp],
     "nunerf_colsum": [vp, ci, ci, ci, ci, vp, vp],
     "nunerf_to_planes": [vp, ci, ci, ci, ci, cf, vp, ci, ci, ci, ci, ci, ci, vp],
     "nunerf_from_planes": [vp, ci, ci, ci, ci, vp, ci, vp],

@@ -1,0 +1,456 @@
+// chain.cu -- fused multi-layer perceptron chains on tcgen05 tensor cores (sm_100a).
+//
+// One 128-row tile of points runs through a whole chain of dense layers without its activations ever leaving the
+// SM: the bf16 activation of layer l sits in shared memory (four 128x64 K-blocks, 128B swizzle) as the A operand of
+// layer l+1, accumulators are double-buffered in TMEM (2 x 256 fp32 columns), and only the weights stream in
+// (from L2, by TMA, through a ring of 32 KB K-blocks).  Layers overlap at K-block granularity: the 16 epilogue warps
+// all work on the same 64-column chunk of the accumulator, publish it (mbarrier x_ready[c]) and the MMA warp starts
+// the next layer's k-block c while chunks c+1.. are still being activated.
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 0       TMA producer (weight K-blocks; the tile's input rows when they come from global memory)
+//   warp 1       tcgen05.mma issuer (one lane) + TMEM allocation + TMA stores of activations that must be kept
+//   warps 2..17  epilogue: warp (q, j) owns TMEM lane quarter q and the 16 columns j of every 64-column chunk
+//
+// Programs built on it (host side, below):
+//   nunerf_sdf_infer   SDFNetwork.sdf (field.py:133-152): PE-6 in-kernel, 8 Softplus(beta=100) layers with the skip
+//                      concat at layer 4, 1-row sdf head -- the no-grad SDF queries of sample_ray (ZT:598, :563),
+//                      extract_fields (field.py:1286-1307) and the occlusion probes (field.py:524-554)
+//   nunerf_mlp_chain   generic ReLU / Softplus chains with optional per-layer stores (predictors, NeRF++)
+#include "common.cuh"
+#include "ptx.cuh"
+#include "tma_host.cuh"
+
+namespace nunerf {
+
+constexpr int CH_BLOCK_BYTES = 128 * 64 * 2;     // one activation K-block: 128 rows x 64 bf16
+constexpr int CH_WSTAGE_BYTES = 256 * 64 * 2;    // one weight K-block: <= 256 rows x 64 bf16
+constexpr int CH_EPI_WARPS = 16;
+constexpr int CH_THREADS = 32 * (2 + CH_EPI_WARPS);
+constexpr int CH_MAXL = NUNERF_CHAIN_MAX_LAYERS;
+
+struct ChainLayer {
+  int N;            // MMA N (multiple of 16, 16..256)
+  int n_real;       // produced columns >= n_real are replaced (zeros, or the PE side block when cat_pe)
+  int kb0, nkb;     // input K-blocks [kb0, kb0 + nkb) (blocks 0..3 = activation, 4.. = tile input)
+  int act;          // 0 none, 1 relu, 2 softplus(beta = 100)
+  int cat_pe;       // columns [n_real, 256) <- columns [0, 256 - n_real) of input block 4 (SDF skip concat)
+  int to_x;         // write the activation back to X blocks 0..3 (a next layer or a TMA store consumes it)
+  int store_chunks; // > 0: TMA-store that many 64-column chunks of the activation through out_map
+  int hot;          // plain 256-wide hidden layer (bias + act -> X, optional mask_out): specialised epilogue
+  const float* bias;
+  uint8_t* mask_out; int ldmask_out;       // optional 1-bit (x > 0) mask, 32 bytes per row
+  const uint8_t* mask_in; int ldmask_in;   // optional 1-bit multiplicative mask
+  float* out32; int ldo32; int n32;        // optional fp32 copy of the first n32 columns
+};
+
+struct ChainParams {
+  CUtensorMap in_map;
+  CUtensorMap w_map[CH_MAXL];
+  CUtensorMap out_map[CH_MAXL];
+  ChainLayer layer[CH_MAXL];
+  int n_layers, M, num_tiles;
+  int in_mode;           // 0: X0 = rows of a bf16 matrix (TMA), 1: X0 = PE-6 of pts (computed in-kernel)
+  int in_blocks;         // K-blocks of the tile input
+  int in_release_layer;  // the input blocks may be refilled once this layer's MMAs have completed
+  int w_stages;
+  const float* pts;
+};
+
+// Hot epilogue of a plain hidden layer (N = 256, bias + activation -> bf16 -> shared memory): 16 columns of one row.
+template <int ACT>
+__device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict__ bias, uint8_t* dst, int j, uint32_t sw,
+                                         uint32_t* obits) {
+  uint32_t v[16];
+  ptx::tmem_ld16(taddr, v);
+  float4 b[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+  ptx::tmem_ld_wait();
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[4 * i] = __uint_as_float(v[4 * i]) + b[i].x;
+    x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b[i].y;
+    x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b[i].z;
+    x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b[i].w;
+  }
+  if (ACT == 2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
+  } else {
+    uint32_t ob = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      ob |= (x[i] > 0.0f ? 1u : 0u) << i;
+      x[i] = fmaxf(x[i], 0.0f);
+    }
+    *obits = ob;
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+__device__ __forceinline__ void ch_tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int n_xblocks = 4 + p.in_blocks;
+  uint8_t* sX = smem;                                         // activation + input K-blocks
+  uint8_t* sW = sX + (size_t)n_xblocks * CH_BLOCK_BYTES;      // weight ring
+  uint64_t* bars = (uint64_t*)(sW + (size_t)p.w_stages * CH_WSTAGE_BYTES);
+  uint64_t* w_full = bars;                  // [w_stages]
+  uint64_t* w_empty = bars + 8;             // [w_stages]
+  uint64_t* x_ready = bars + 16;            // [4]  chunk c of the activation is in shared memory
+  uint64_t* t_full = bars + 20;             // [2]  accumulator complete
+  uint64_t* in_full = bars + 22;            // tile input is in shared memory
+  uint64_t* in_empty = bars + 23;           // tile input consumed
+  uint32_t* tmem_ptr = (uint32_t*)(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < p.n_layers; ++l) {
+      ptx::prefetch_tmap(&p.w_map[l]);
+      if (p.layer[l].store_chunks > 0) ptx::prefetch_tmap(&p.out_map[l]);
+    }
+    if (p.in_mode == 0) ptx::prefetch_tmap(&p.in_map);
+    for (int i = 0; i < p.w_stages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) ptx::mbar_init(&x_ready[i], CH_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1);
+    ptx::mbar_init(in_full, p.in_mode == 0 ? 1 : CH_EPI_WARPS);
+    ptx::mbar_init(in_empty, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, 512u);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        if (p.in_mode == 0) {
+          ptx::mbar_wait_parked(in_empty, (uint32_t)(it & 1) ^ 1);
+          ptx::mbar_expect_tx(in_full, (uint32_t)(p.in_blocks * CH_BLOCK_BYTES));
+          for (int b = 0; b < p.in_blocks; ++b)
+            ptx::tma_load_2d(sX + (size_t)(4 + b) * CH_BLOCK_BYTES, &p.in_map, in_full, b * 64, tile * 128);
+        }
+        for (int l = 0; l < p.n_layers; ++l) {
+          const int N = p.layer[l].N, nkb = p.layer[l].nkb;
+          for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait_parked(&w_empty[stage], phase ^ 1);
+            ptx::mbar_expect_tx(&w_full[stage], (uint32_t)(N * 128));
+            ptx::tma_load_2d(sW + (size_t)stage * CH_WSTAGE_BYTES, &p.w_map[l], &w_full[stage], kb * 64, 0);
+            if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      long long g = 0;             // global layer counter: accumulator g & 1, x_ready phase g
+      bool stores_pending = false;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        for (int l = 0; l < p.n_layers; ++l, ++g) {
+          const ChainLayer& L = p.layer[l];
+          const uint32_t idesc = ptx::idesc_bf16(128, L.N, 0, 0);
+          const uint32_t d_tmem = tmem_base + (uint32_t)((g & 1) * 256);
+          const uint32_t xpar = (uint32_t)((g - 1) & 1);
+          const bool prev_store = l > 0 && p.layer[l - 1].store_chunks > 0;
+          bool waited[4] = {false, false, false, false};
+          if (l == 0) {
+            // in-order rule: every x_ready phase is observed, also the previous tile's last layer (see header)
+            if (g > 0)
+              for (int c = 0; c < 4; ++c) { ptx::mbar_wait_parked(&x_ready[c], xpar); waited[c] = true; }
+            ptx::mbar_wait_parked(in_full, (uint32_t)(it & 1));
+          }
+          ptx::tc_fence_after();
+          uint32_t accum = 0;
+          for (int kb = 0; kb < L.nkb; ++kb) {
+            const int blk = L.kb0 + kb;
+            if (blk < 4 && !waited[blk]) {
+              ptx::mbar_wait_parked(&x_ready[blk], xpar);
+              waited[blk] = true;
+              ptx::tc_fence_after();
+              if (prev_store && blk < p.layer[l - 1].store_chunks) {
+                ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)blk * CH_BLOCK_BYTES, blk * 64, tile * 128);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                stores_pending = true;
+              }
+            }
+            ptx::mbar_wait_parked(&w_full[stage], phase);
+            ptx::tc_fence_after();
+            const uint32_t a_addr = ptx::smem_u32(sX + (size_t)blk * CH_BLOCK_BYTES);
+            const uint32_t b_addr = ptx::smem_u32(sW + (size_t)stage * CH_WSTAGE_BYTES);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint64_t ad = ptx::smem_desc(a_addr + k * 32, 16, 1024);
+              uint64_t bd = ptx::smem_desc(b_addr + k * 32, 16, 1024);
+              ptx::umma_bf16(d_tmem, ad, bd, idesc, accum);
+              accum = 1;
+            }
+            ptx::tc_commit(&w_empty[stage]);
+            if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+          }
+          // chunks this layer did not read still have to be observed (in-order rule) and, if asked, stored
+          if (g > 0)
+            for (int c = 0; c < 4; ++c)
+              if (!waited[c]) {
+                ptx::mbar_wait_parked(&x_ready[c], xpar);
+                if (prev_store && c < p.layer[l - 1].store_chunks) {
+                  ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  stores_pending = true;
+                }
+              }
+          if (p.in_mode == 0 && l == p.in_release_layer) ptx::tc_commit(in_empty);
+          // the epilogue of this layer overwrites the X blocks: outstanding TMA stores must have read them
+          if (stores_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); stores_pending = false; }
+          ptx::tc_commit(&t_full[g & 1]);
+        }
+        // a stored last layer: wait for its chunks and store them before the next tile starts
+        const ChainLayer& LL = p.layer[p.n_layers - 1];
+        if (LL.store_chunks > 0) {
+          const uint32_t xpar = (uint32_t)((g - 1) & 1);
+          for (int c = 0; c < 4; ++c) {
+            ptx::mbar_wait_parked(&x_ready[c], xpar);
+            if (c < LL.store_chunks) {
+              ch_tma_store_2d(&p.out_map[p.n_layers - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+          }
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else {
+    // ================================================================ epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;      // TMEM lane quarter this warp may access
+    const int j = ew >> 2;       // its 16 columns inside every 64-column chunk
+    const int r = q * 32 + lane; // row inside the tile
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);
+    int it = 0;
+    long long g = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const long long row = (long long)tile * 128 + r;
+      const bool row_ok = row < p.M;
+      if (p.in_mode == 1) {
+        // ---- tile input: PE-6 of the point, 39 columns + zero padding to 64, into input block 4
+        if (j == 0) {
+          float x[3] = {0.f, 0.f, 0.f};
+          if (row_ok) { x[0] = p.pts[3 * row]; x[1] = p.pts[3 * row + 1]; x[2] = p.pts[3 * row + 2]; }
+          float pe[64];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) pe[c] = x[c];
+#pragma unroll
+          for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              float sn, co;
+              sincosf(x[c] * (float)(1 << k), &sn, &co);
+              pe[3 + 6 * k + c] = sn;
+              pe[6 + 6 * k + c] = co;
+            }
+#pragma unroll
+          for (int c = 39; c < 64; ++c) pe[c] = 0.f;
+          uint8_t* dst = sX + (size_t)4 * CH_BLOCK_BYTES + row_off;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            uint4 v = make_uint4(pack_bf16x2(pe[8 * ch], pe[8 * ch + 1]), pack_bf16x2(pe[8 * ch + 2], pe[8 * ch + 3]),
+                                 pack_bf16x2(pe[8 * ch + 4], pe[8 * ch + 5]), pack_bf16x2(pe[8 * ch + 6], pe[8 * ch + 7]));
+            *reinterpret_cast<uint4*>(dst + (((uint32_t)ch ^ sw) << 4)) = v;
+          }
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(in_full);
+      }
+      for (int l = 0; l < p.n_layers; ++l, ++g) {
+        const ChainLayer& L = p.layer[l];
+        const int acc = (int)(g & 1);
+        // one parked waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier (no spin loops competing
+        // for issue slots with the warps that still work)
+        if (ew == 0 && lane == 0) ptx::mbar_wait_parked(&t_full[acc], (uint32_t)(g >> 1) & 1);
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        ptx::tc_fence_after();
+        for (int c = 0; c < 4; ++c) {
+          const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
+          if (L.hot) {
+            uint32_t ob = 0;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0);
+            uint8_t* dst = sX + (size_t)c * CH_BLOCK_BYTES + row_off;
+            if (L.act == 2) ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob);
+            else {
+              ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob);
+              if (L.mask_out && row_ok)
+                *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
+            }
+            ptx::fence_proxy_async();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&x_ready[c]);
+            continue;
+          }
+          const bool in_acc = c0 < L.N;       // columns the MMA produced
+          // columns that must be (re)written in shared memory: the produced ones, the concatenated PE columns,
+          // and the zero tail of a partially produced K-block (the next layer reads whole 64-column blocks)
+          const bool in_x = L.to_x && c0 < (L.cat_pe ? 256 : ((L.N + 63) & ~63));
+          if (in_acc || in_x) {
+            float x[16];
+            if (in_acc) {
+              uint32_t v[16];
+              ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+              if (L.bias) {
+                const float4* b4 = reinterpret_cast<const float4*>(L.bias + c0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float4 b = __ldg(b4 + i);
+                  x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
+                }
+              }
+              if (L.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.0f);
+              } else if (L.act == 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
+              }
+              if (L.mask_in) {
+                const uint32_t mb =
+                    *reinterpret_cast<const uint16_t*>(L.mask_in + (row_ok ? row : 0) * L.ldmask_in + (c0 >> 3));
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = ((mb >> i) & 1u) ? x[i] : 0.0f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) x[i] = 0.0f;
+            }
+            if (c0 + 16 > L.n_real) {
+              if (L.cat_pe) {
+                const uint8_t* src = sX + (size_t)4 * CH_BLOCK_BYTES + row_off;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int col = c0 + i;
+                  if (col >= L.n_real) {
+                    const int pc = col - L.n_real;
+                    const __nv_bfloat16 b =
+                        *reinterpret_cast<const __nv_bfloat16*>(src + ((((uint32_t)pc >> 3) ^ sw) << 4) + (pc & 7) * 2);
+                    x[i] = __bfloat162float(b);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c0 + i >= L.n_real) x[i] = 0.0f;
+              }
+            }
+            if (in_acc && L.mask_out) {
+              uint32_t ob = 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) ob |= (x[i] > 0.0f ? 1u : 0u) << i;
+              if (row_ok) *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
+            }
+            if (in_x) {
+              uint8_t* dst = sX + (size_t)c * CH_BLOCK_BYTES + row_off;
+              uint32_t h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+              *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+              *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+            if (in_acc && L.out32 && row_ok) {
+              float* o = L.out32 + row * L.ldo32 + c0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < L.n32) o[i] = x[i];
+            }
+          }
+          ptx::fence_proxy_async();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&x_ready[c]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512u);
+}
+
+// ------------------------------------------------------------------------------------------- host side
+static int chain_launch(ChainParams& P, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return fail("chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e), -2);
+    configured = true;
+  }
+  const size_t xbytes = (size_t)(4 + P.in_blocks) * CH_BLOCK_BYTES;
+  const size_t fixed = 1024 + 512;
+  int stages = (int)((227 * 1024 - fixed - xbytes) / CH_WSTAGE_BYTES);
+  if (stages > 4) stages = 4;
+  NUNERF_REQUIRE(stages >= 2, "chain: input too wide for shared memory");
+  P.w_stages = stages;
+  P.num_tiles = cdiv(P.M, 128);
+  const size_t smem = fixed + xbytes + (size_t)stages * CH_WSTAGE_BYTES;
+  const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
+  mlp_chain_kernel<<<grid, CH_THREADS, smem, stream>>>(P);
+  NUNERF_CHECK_LAUNCH("mlp_chain_kernel");
+  return 0;
+}
+
+}  // namespace nunerf
+
+using namespace nunerf;
+
+extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NUNERF_REQUIRE(a && a->pts && a->sdf && a->M > 0, "sdf_infer: bad arguments");
+  static const int Ns[9] = {256, 256, 256, 224, 256, 256, 256, 256, 16};
+  static const int Ks[9] = {64, 256, 256, 256, 256, 256, 256, 256, 256};
+  ChainParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_layers = 9; P.M = a->M; P.in_mode = 1; P.in_blocks = 1; P.in_release_layer = 0; P.pts = a->pts;
+  for (int l = 0; l < 9; ++l) {
+    NUNERF_REQUIRE(a->w[l] && a->ldw[l] >= Ks[l] && a->ldw[l] % 8 == 0, "sdf_infer: bad weight operand");
+    if (int r = make_map(&P.w_map[l], a->w[l], Ns[l], Ks[l], a->ldw[l], 64, Ns[l])) return r;
+    ChainLayer& L = P.layer[l];
+    L.N = Ns[l]; L.n_real = Ns[l];
+    L.kb0 = l == 0 ? 4 : 0; L.nkb = Ks[l] / 64;
+    L.act = l < 8 ? 2 : 0; L.to_x = l < 8 ? 1 : 0;
+    L.bias = a->bias[l];
+    L.hot = (l < 8 && l != 3) ? 1 : 0;
+  }
+  P.layer[3].n_real = 217; P.layer[3].cat_pe = 1;      // x <- cat([x, PE]) / sqrt(2) (the scale lives in lin4's weights)
+  P.layer[8].n_real = 16; P.layer[8].out32 = a->sdf; P.layer[8].ldo32 = a->ld_sdf; P.layer[8].n32 = 1;
+  return chain_launch(P, stream);
+}

@@ -60,6 +60,19 @@ __device__ __forceinline__ float load_planes(const __nv_bfloat16* base, long lon
   return v;
 }
 
+// Softplus(beta = 100): max(x, 0) + 0.01 log1p(e), e = exp(-|100 x|).  One MUFU (ex2) per element; log1p(e) on (0, 1]
+// is e Q(e) with a degree-4 near-minimax Q (|error| < 1e-5, i.e. < 1e-7 after the 0.01 factor, folded into Q).
+__device__ __forceinline__ float softplus100(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fabsf(x) * -144.26950408889634f));
+  float q = 3.215121477842331e-4f;
+  q = fmaf(q, e, -1.3604211807250977e-3f);
+  q = fmaf(q, e, 2.8945398330688477e-3f);
+  q = fmaf(q, e, -4.9190032482147217e-3f);
+  q = fmaf(q, e, 9.994943737983704e-3f);
+  return fmaf(e, q, fmaxf(x, 0.0f));
+}
+
 // ---------------------------------------------------------------- deterministic fp32 math (sampling path)
 // The sampling kernels and the C oracle (oracle/sampling_oracle.c) must agree bit for bit, so every
 // operation is an explicitly rounded fp32 op (no FMA contraction) and exp() is our own polynomial.

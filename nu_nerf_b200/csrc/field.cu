@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(128) shade_encode_fwd_kernel(nunerf_shade_enco
 #pragma unroll
     for (int c = 0; c < 16; ++c) store8(xr, m * p.ld_refrac + c * 8, p.lo_refrac, row + c * 8);
     p.nov[m] = s.nov;
+    if (p.refl) { p.refl[3 * m] = s.r[0]; p.refl[3 * m + 1] = s.r[1]; p.refl[3 * m + 2] = s.r[2]; }
   }
 }
 
@@ -337,6 +338,7 @@ __global__ void shade_mix_bwd_kernel(nunerf_shade_mix_t p) {
   float dc[3] = {p.d_color[3 * m], p.d_color[3 * m + 1], p.d_color[3 * m + 2]};
   pw::shade_mix_bwd(in, p.lut, p.exp_max, dc, p.d_trans_out ? p.d_trans_out[m] : 0.f,
                     p.d_metallic_out ? p.d_metallic_out[m] : 0.f, &d);
+  if (p.d_occ_prob) d.occ += 0.5f * p.d_occ_prob[m];   // occ_prob = raw * 0.5 + 0.5 (field.py:659), unclipped output
   const int ld = p.ld_dz, lo = p.lo_dz;
   store_planes((__nv_bfloat16*)p.dz_metallic, m * ld, lo, d.metallic);
   store_planes((__nv_bfloat16*)p.dz_trans, m * ld, lo, d.trans);

@@ -23,6 +23,8 @@ namespace nunerf {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 
+int env_int(const char* name, int dflt);
+
 // ------------------------------------------------------------------------------------------- TMA maps
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -48,9 +50,13 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  static const int promo_env = env_int("NUNERF_L2_PROMO", 128);
+  const CUtensorMapL2promotion promo = promo_env == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                       : promo_env == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                       : promo_env == 0  ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                                         : CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (%d) rows=%lld ld=%lld box=%dx%d base=%p", (int)r,
              rows, ld, box_cols, box_rows, base);
@@ -59,6 +65,7 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, l
   return 0;
 }
 
+int env_int(const char* name, int dflt);
 static int g_num_sms = 0;
 int num_sms() {
   if (!g_num_sms) {

@@ -51,12 +51,6 @@ struct LinearK {
   int n_store;
 };
 
-__device__ __forceinline__ float softplus100(float x) {
-  float t = 100.0f * x;
-  float e = __expf(-fabsf(t));
-  return fmaxf(x, 0.0f) + 0.01f * __logf(1.0f + e);
-}
-
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),

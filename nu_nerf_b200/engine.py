@@ -102,8 +102,27 @@ class NerfW:
 
 
 # =============================================================================================== SDF network
-def sdf_infer(w: SdfWeights, pts, planes):
-    """sdf(x) only (SDFNetwork.sdf, field.py:152) for the sampling passes: 8 hidden layers + the 1-row head."""
+def sdf_infer_fused(w: SdfWeights, pts):
+    """sdf(x) in ONE launch (csrc/chain.cu): PE + 9 layers with the activations resident on the SM (bf16 mode)."""
+    M, dev = pts.shape[0], pts.device
+    out = _f(M, dev=dev)
+    a = _lib.SdfInferT()
+    a.pts, a.M, a.sdf, a.ld_sdf = pts.data_ptr(), M, out.data_ptr(), 1
+    lays = [w.L[l] for l in range(8)] + [w.sdf_head]
+    for l, d in enumerate(lays):
+        a.w[l], a.ldw[l], a.bias[l] = d.Wk.ptr, d.Wk.ld, d.b.data_ptr()
+    call("nunerf_sdf_infer", C.byref(a))
+    return out
+
+
+def sdf_infer(w: SdfWeights, pts, planes, fused=None):
+    """sdf(x) only (SDFNetwork.sdf, field.py:152) for the sampling passes: 8 hidden layers + the 1-row head.
+    bf16 mode runs the fused chain kernel; the fp32-accurate split mode runs layer by layer (hi/lo planes)."""
+    from .ops import GEMM_IMPL
+    if fused is None:
+        fused = planes == 1 and GEMM_IMPL == 0
+    if fused:
+        return sdf_infer_fused(w, pts.contiguous())
     M, dev = pts.shape[0], pts.device
     x0 = P(M, 64, planes, dev)
     call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, x0.ptr, x0.ld, x0.lo, 0, 0, 64)
@@ -463,6 +482,8 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
         se.x_weight, se.ld_weight, se.lo_weight = t.xw.ptr, t.xw.ld, t.xw.lo
         se.x_refrac, se.ld_refrac, se.lo_refrac = t.xr.ptr, t.xr.ld, t.xr.lo
         se.nov = t.nov.data_ptr()
+        t.refl = _f(M, 3, dev=dev)
+        se.refl = t.refl.data_ptr()
         call("nunerf_shade_encode_fwd", C.byref(se))
         t.lo_ = pred_forward(w.pred["outer_light"], t.xo, 3 * M, 128, planes)
         t.li_ = pred_forward(w.pred["inner_light"], t.xi, 2 * M, 128, planes)
@@ -492,7 +513,7 @@ def _norm_dirs(d):
     return (d / d.norm(dim=-1, keepdim=True).clamp_min(1e-12)).contiguous()
 
 
-def _mix_params(w, t, d_color=None, d_trans=None, d_met=None, dz=None, d_rough=None, d_nov=None):
+def _mix_params(w, t, d_color=None, d_trans=None, d_met=None, dz=None, d_rough=None, d_nov=None, d_occ=None):
     M = t.n_in
     mp = _lib.ShadeMixT()
     mp.M, mp.exp_max = M, t.exp_max
@@ -513,10 +534,12 @@ def _mix_params(w, t, d_color=None, d_trans=None, d_met=None, dz=None, d_rough=N
             dz["refrac"].ptr
         mp.ld_dz, mp.lo_dz = dz["metallic"].ld, dz["metallic"].lo
         mp.d_rough_raw, mp.d_nov = d_rough.data_ptr(), d_nov.data_ptr()
+        mp.d_occ_prob = ptr(d_occ)
     return mp
 
 
-def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, want_inv_s):
+def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, want_inv_s,
+                  d_occ=None):
     """Reverse launch sequence of core_forward.  Returns {reference parameter name -> gradient of the EFFECTIVE
     weight / bias} (+ 'inv_s')."""
     planes, dev = w.planes, t.slot.device
@@ -544,7 +567,7 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     dz = {k: P(M, 64, planes, dev, zero=True) for k in ("metallic", "albedo", "trans", "weight", "refrac")}
     dz["outer"], dz["inner"] = P(3 * M, 64, planes, dev, zero=True), P(2 * M, 64, planes, dev, zero=True)
     d_rough, d_nov = _f(M, dev=dev), _f(M, dev=dev)
-    call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov)))
+    call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov, d_occ)))
     dxo, dxi = _f(3 * M, 128, dev=dev), _f(2 * M, 128, dev=dev)
     add_pred("outer_light", pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128))
     add_pred("inner_light", pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128))

@@ -63,11 +63,15 @@ class _RenderCoreFn(torch.autograd.Function):
             gerr, trans, met, occ = (torch.zeros(1, device=dev), torch.zeros(0, 1, device=dev),
                                      torch.zeros(0, 1, device=dev), torch.zeros(0, 1, device=dev))
         spec = t.ls_.head[:, :3].clone()
-        ctx.mark_non_differentiable(wts, occ)
-        return rgb, acc, bkgr, gerr, trans, met, spec, wts, occ
+        if t.n_in > 0:
+            aux = (t.pts_in, t.sdf.sdf[:, 0], t.sdf.grad, t.dirs_in, t.refl)
+        else:
+            aux = tuple(torch.zeros(0, 3, device=dev) if i != 1 else torch.zeros(0, device=dev) for i in range(5))
+        ctx.mark_non_differentiable(wts, *aux)
+        return (rgb, acc, bkgr, gerr, trans, met, spec, occ, wts) + aux
 
     @staticmethod
-    def backward(ctx, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, _dw, _docc):
+    def backward(ctx, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, d_occ, *_unused):
         eng = _engine()
         t = ctx.tape
         c = lambda x: None if x is None else x.contiguous().float()
@@ -75,7 +79,8 @@ class _RenderCoreFn(torch.autograd.Function):
         ctx.w.bank.zero_grads()
         g = eng.core_backward(ctx.w, t, c(d_rgb), c(d_acc), c(d_bkgr), c(d_gerr) if has else None,
                               c(d_trans).reshape(-1) if (has and d_trans is not None) else None,
-                              c(d_met).reshape(-1) if (has and d_met is not None) else None, c(d_spec), ctx.want_inv_s)
+                              c(d_met).reshape(-1) if (has and d_met is not None) else None, c(d_spec), ctx.want_inv_s,
+                              d_occ=c(d_occ).reshape(-1) if (has and d_occ is not None) else None)
         # effective-weight gradients -> d weight_v / d weight_g / d bias, added in place to .grad (one launch);
         # autograd therefore receives None for the parameter inputs
         ctx.w.bank.backward()
@@ -214,7 +219,7 @@ class NeROShapeRenderer(nn.Module):
 
     # ------------------------------------------------------------------ ZT:725-820
     def render_core(self, rays_o, rays_d, z_vals, human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True,
-                    is_nerf=False, prepared=None):
+                    is_nerf=False, prepared=None, occ_perm=None):
         w = prepared if prepared is not None else self._prepare()
         params = [p for d in w.bank.denses if d.has_grad for p in (d.v, d.g, d.bias) if p is not None]
         params = list({id(p): p for p in params}.values())
@@ -223,7 +228,8 @@ class NeROShapeRenderer(nn.Module):
         inv_s = torch.exp(self.deviation_network.variance * 10.0)
         exp_max = self.color_network.cfg["light_exp_max"]
         pack = (w, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen)
-        rgb, acc, bkgr, gerr, trans, met, spec, weights, occ = _RenderCoreFn.apply(pack, inv_s, *params)
+        (rgb, acc, bkgr, gerr, trans, met, spec, occ, weights, pts_in, sdf_in, grad_in, dirs_in,
+         refl_in) = _RenderCoreFn.apply(pack, inv_s, *params)
         inv_s_c = inv_s.clip(1e-6, 1e6)
         if frozen:
             inv_s_c = inv_s_c.detach()
@@ -237,16 +243,81 @@ class NeROShapeRenderer(nn.Module):
             outputs["transmission"] = trans
             outputs["metallic"] = met
         if self.cfg["apply_occ_loss"]:
-            if step is not None and step >= self.cfg["occ_loss_step"] and has_inner:
-                raise NotImplementedError("occlusion-probe loss (ZT:695-723) is a 'next' row (SURVEY 8f rank 4); "
-                                          "run with step < occ_loss_step or apply_occ_loss False")
-            outputs["loss_occ"] = torch.zeros(1, device=rgb.device)
+            if has_inner and step is not None:
+                outputs["loss_occ"] = self.compute_occ_loss({"occ_prob": occ, "reflective": refl_in}, pts_in, sdf_in,
+                                                            grad_in, dirs_in, step, prepared=w, perm=occ_perm)
+            else:
+                outputs["loss_occ"] = torch.zeros(1, device=rgb.device)
         if step is not None and step < 1000:
             raise NotImplementedError("sdf_pts / sdf_vals warm-up outputs (ZT:804-807, step < 1000)")
         if not is_train:
             outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=w))
         outputs["_weights"] = weights
         return outputs
+
+    # ------------------------------------------------------------------ ZT:695-723, field.py:501-554
+    def compute_occ_loss(self, occ_info, points, sdf, gradients, dirs, step, prepared=None, perm=None):
+        """L1 between the predicted occlusion probability and the hit probability of a 64 + 16 sample SDF probe along
+        the reflected ray, on (at most occ_loss_max_pn) surface samples.  torch glue on <= 2048-row tensors around the
+        fused SDF-inference kernel; `perm` injects the torch.randperm draw of ZT:710 (parity tests)."""
+        dev = points.device
+        if step < self.cfg["occ_loss_step"]:
+            return torch.zeros(1, device=dev)
+        occ_prob, reflective = occ_info["occ_prob"], occ_info["reflective"]
+        mask = (torch.norm(points, dim=-1) < 0.999) & (torch.sum(gradients * dirs, -1) < 0) & \
+               (torch.abs(sdf) < self.cfg["occ_sdf_thresh"])
+        n = int(mask.sum())
+        max_pn = self.cfg["occ_loss_max_pn"]
+        if n > max_pn:
+            indices = torch.nonzero(mask)[:, 0]
+            idx = perm.to(dev) if perm is not None else torch.randperm(indices.shape[0], device=dev)
+            indices = indices[idx[:max_pn]]
+            mask = torch.zeros_like(mask)
+            mask[indices] = True
+        if n == 0:
+            return torch.zeros(1, device=dev)
+        w = prepared if prepared is not None else self._prepare()
+        occ_gt = self.occ_probability(points[mask], reflective[mask].detach(), w)
+        return F.l1_loss(occ_prob[mask], occ_gt)
+
+    @torch.no_grad()
+    def occ_probability(self, pts, dirs, w, sn0=64, sn1=16):
+        """get_intersection (field.py:524-554): probability that the ray pts + t dirs hits the surface before it
+        leaves the unit sphere.  pts must lie inside radius 0.999 (the caller's mask)."""
+        eng = _engine()
+        inv_s = torch.exp(self.deviation_network.variance.detach() * 10.0)
+        dtx = torch.sum(pts * dirs, dim=-1, keepdim=True)
+        xtx = torch.sum(pts ** 2, dim=-1, keepdim=True)
+        max_dist = -dtx + torch.sqrt(dtx ** 2 - xtx + 1 + 1e-6)                 # get_sphere_intersection :458-464
+
+        def weights(z):                                                        # get_weights :501-521
+            p = (z.unsqueeze(-1) * dirs.unsqueeze(-2) + pts.unsqueeze(-2)).reshape(-1, 3).contiguous()
+            sdf = eng.sdf_infer(w.sdf, p, w.planes).reshape(z.shape)
+            ps, ns, pz, nz = sdf[:, :-1], sdf[:, 1:], z[:, :-1], z[:, 1:]
+            mid = (ps + ns) * 0.5
+            cos = (ns - ps) / (nz - pz + 1e-5)
+            surf = cos < 0
+            cos = torch.clamp(cos, max=0)
+            dist = nz - pz
+            pc = torch.sigmoid((mid - cos * dist * 0.5) * inv_s)
+            nc = torch.sigmoid((mid + cos * dist * 0.5) * inv_s)
+            alpha = (pc - nc + 1e-5) / (pc + 1e-5) * surf.float()
+            T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+            return alpha * T
+
+        z = max_dist * torch.linspace(0, 1, sn0, device=pts.device).unsqueeze(0)
+        wts = weights(z) + 1e-5                                                # sample_pdf(det) field.py:468-498
+        pdf = wts / torch.sum(wts, -1, keepdim=True)
+        cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)
+        u = torch.linspace(0.5 / sn1, 1.0 - 0.5 / sn1, sn1, device=pts.device).expand(cdf.shape[0], sn1).contiguous()
+        inds = torch.searchsorted(cdf, u, right=True)
+        lo, hi = torch.clamp(inds - 1, min=0), torch.clamp(inds, max=cdf.shape[-1] - 1)
+        c0, c1 = torch.gather(cdf, 1, lo), torch.gather(cdf, 1, hi)
+        b0, b1 = torch.gather(z, 1, lo), torch.gather(z, 1, hi)
+        den = c1 - c0
+        den = torch.where(den < 1e-5, torch.ones_like(den), den)
+        z_new = b0 + (u - c0) / den * (b1 - b0)
+        return torch.sum(weights(z_new), -1, keepdim=True)
 
     def compute_validation_info(self, z_vals, rays_o, rays_d, weights, human_poses, step, prepared=None):
         """ZT:636-655: depth = sum w z ; normal = (normalize(grad sdf(o + depth d)) + 1) / 2 inside the unit sphere."""
@@ -263,14 +334,14 @@ class NeROShapeRenderer(nn.Module):
 
     # ------------------------------------------------------------------ ZT:614-634
     def render(self, rays_o, rays_d, near, far, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,
-               is_train=True, step=None, is_nerf=False, uniforms=None):
+               is_train=True, step=None, is_nerf=False, uniforms=None, occ_perm=None):
         perturb = self.cfg["perturb"]
         if perturb_overwrite >= 0:
             perturb = perturb_overwrite
         prepared = self._prepare()
         z_vals = self.sample_ray(rays_o, rays_d, near, far, perturb, uniforms=uniforms, prepared=prepared)
         return self.render_core(rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step,
-                                is_train=is_train, is_nerf=is_nerf, prepared=prepared)
+                                is_train=is_train, is_nerf=is_nerf, prepared=prepared, occ_perm=occ_perm)
 
     # ------------------------------------------------------------------ ZT:447-466
     def train_step(self, step):

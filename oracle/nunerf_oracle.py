@@ -326,8 +326,63 @@ def composite(alpha, color):
     return w, (color * w[..., None]).sum(1)
 
 
-def render_core(sd, o, d, z, cos_anneal, step, is_nerf=True, freeze_inv_s_step=15000, exp_max=3.0):
-    """ZT:725-820 (training outputs; occ loss excluded: step < occ_loss_step)."""
+# ----------------------------------------------------------------------------- occlusion-probe loss
+def get_sphere_intersection(pts, dirs):
+    """field.py:458-464."""
+    dtx = (pts * dirs).sum(-1, keepdim=True)
+    xtx = (pts ** 2).sum(-1, keepdim=True)
+    dist = dtx ** 2 - xtx + 1
+    return -dtx + torch.sqrt(dist + 1e-6)
+
+
+def probe_weights(sd, z, origins, dirs, inv_s):
+    """get_weights field.py:501-521 (sdf network + SingleVarianceNetwork of the stage-1 field)."""
+    pts = z[..., None] * dirs[:, None, :] + origins[:, None, :]
+    sdf = sdf_forward(sd, pts.reshape(-1, 3))[:, 0].reshape(z.shape)
+    ps, ns = sdf[:, :-1], sdf[:, 1:]
+    pz, nz = z[:, :-1], z[:, 1:]
+    mid = (ps + ns) * 0.5
+    cos = (ns - ps) / (nz - pz + 1e-5)
+    surf = cos < 0
+    cos = torch.clamp(cos, max=0)
+    dist = nz - pz
+    pe, ne = mid - cos * dist * 0.5, mid + cos * dist * 0.5
+    pc, nc = torch.sigmoid(pe * inv_s), torch.sigmoid(ne * inv_s)
+    alpha = (pc - nc + 1e-5) / (pc + 1e-5) * surf.float()
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    return alpha * T
+
+
+def occ_probability(sd, pts, dirs, sn0=64, sn1=16):
+    """get_intersection field.py:524-554 -> sum of the hit weights (occ_prob_gt of ZT:718-719).  pts must satisfy
+    |p| < 0.999 (the caller's mask, ZT:704)."""
+    with torch.no_grad():
+        inv_s = torch.exp(sd["deviation_network.variance"] * 10.0)
+        max_dist = get_sphere_intersection(pts, dirs)
+        z = max_dist * torch.linspace(0, 1, sn0)[None, :]
+        w = probe_weights(sd, z, pts, dirs, inv_s)
+        z_new, _ = sample_pdf_det(z, w, sn1)
+        w = probe_weights(sd, z_new, pts, dirs, inv_s)
+    return w.sum(-1, keepdim=True)
+
+
+def occ_loss(sd, info, points, sdf, grads, dirs, max_pn=2048, sdf_thresh=0.01, perm=None):
+    """compute_occ_loss ZT:695-723.  `perm` = the torch.randperm draw used when more than max_pn samples qualify."""
+    mask = (torch.norm(points, dim=-1) < 0.999) & ((grads * dirs).sum(-1) < 0) & (sdf.abs() < sdf_thresh)
+    if mask.sum() > max_pn:
+        idx = torch.nonzero(mask)[:, 0]
+        idx = idx[perm[:max_pn]]
+        mask = torch.zeros_like(mask)
+        mask[idx] = True
+    if mask.sum() == 0:
+        return torch.zeros(1), mask
+    gt = occ_probability(sd, points[mask], info["reflective"][mask].detach())
+    return F.l1_loss(info["occ_prob"][mask], gt), mask
+
+
+def render_core(sd, o, d, z, cos_anneal, step, is_nerf=True, freeze_inv_s_step=15000, exp_max=3.0,
+                occ_loss_step=15000, occ_perm=None, occ_max_pn=2048):
+    """ZT:725-820 (training outputs; the occlusion loss is active from occ_loss_step on)."""
     R, S = z.shape
     dists = z[:, 1:] - z[:, :-1]
     dists = torch.cat([dists, dists[:, -1:]], -1)
@@ -369,7 +424,12 @@ def render_core(sd, o, d, z, cos_anneal, step, is_nerf=True, freeze_inv_s_step=1
         out["std"] = torch.mean(1.0 / inv_s)
         out["transmission"] = info["transmission_weight"]
         out["metallic"] = info["metallic"]
+        if step >= occ_loss_step:
+            out["loss_occ"], out["occ_mask"] = occ_loss(sd, info, p, sdf, grad, dd, max_pn=occ_max_pn, perm=occ_perm)
+        else:
+            out["loss_occ"] = torch.zeros(1)
     else:
+        out["loss_occ"] = torch.zeros(1)
         out["gradient_error"] = torch.zeros(1)
         out["std"] = torch.zeros(1)
     w, rgb = composite(alpha, color)
@@ -397,9 +457,13 @@ def charbonnier(pr, gt):
     return torch.sqrt(((gt - pr) ** 2).sum(-1) + 0.001)
 
 
-def train_loss(out, gt, eikonal_weight=0.1):
-    """trainer_zero.py:157-161 with loss.py adapters active at step 10000: rgb + eikonal."""
-    return charbonnier(out["ray_rgb"], gt).mean() + (eikonal_weight * out["gradient_error"]).mean()
+def train_loss(out, gt, eikonal_weight=0.1, step=10000, occ_loss_step=15000):
+    """trainer_zero.py:157-161 with the loss.py adapters of spherepot.yaml: rgb + eikonal (+ occ + outer_reg from
+    occ_loss_step on: loss.py:97, :206-209 -- loss_occ * 1.0 and 0.5 * mse(color_bkgr, color_spec))."""
+    loss = charbonnier(out["ray_rgb"], gt).mean() + (eikonal_weight * out["gradient_error"]).mean()
+    if step >= occ_loss_step:
+        loss = loss + out["loss_occ"].mean() + 0.5 * F.mse_loss(out["color_bkgr"], out["color_spec"])
+    return loss
 
 
 # ----------------------------------------------------------------------------- synthetic inputs (SURVEY 8d)

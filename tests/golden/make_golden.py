@@ -8,6 +8,8 @@ Fixtures (all small):
                        synthetic rays: z_vals, every searchsorted index / sort permutation of sample_ray,
                        outputs dict, and strided samples of every parameter gradient of the trainer loss.
   stage1_sphere_R64.npz same with near/far from the unit sphere and perturb=0 (eval-style sampling).
+  stage1_occ_R64.npz   same rays at step 20000: occlusion-probe loss (ZT:695-723) with its recorded randperm draw,
+                       outer_reg, trainable inv_s.
 """
 import os
 import sys
@@ -62,6 +64,26 @@ class Recorder:
         torch.searchsorted, torch.sort = self._ss, self._sort
 
 
+class RandpermRecorder:
+    """torch.randperm (ZT:710) replaced by a seeded draw that is recorded for the fixture."""
+
+    def __init__(self, seed=4):
+        self.g, self.perms = torch.Generator().manual_seed(seed), []
+
+    def __enter__(self):
+        self._orig = torch.randperm
+
+        def rp(n, *a, **k):
+            p = self._orig(n, generator=self.g)
+            self.perms.append(p.clone())
+            return p
+        torch.randperm = rp
+        return self
+
+    def __exit__(self, *e):
+        torch.randperm = self._orig
+
+
 def run_case(net, R, sphere, perturb, step=10000):
     o, d = rh.synthetic_rays(R)
     U0, U1 = rh.synthetic_uniforms(R)
@@ -83,9 +105,14 @@ def run_case(net, R, sphere, perturb, step=10000):
     with Recorder() as rec, rh.injected_rand([U0, U1] if perturb else []):
         z = net.sample_ray(o, d, near, far, 1.0 if perturb else 0.0)
     net.upsample = orig_up
-    out = net.render_core(o, d, z, poses, cos_anneal_ratio=net.get_anneal_val(step), step=step, is_train=True,
-                          is_nerf=True)
+    with RandpermRecorder() as rp:
+        out = net.render_core(o, d, z, poses, cos_anneal_ratio=net.get_anneal_val(step), step=step, is_train=True,
+                              is_nerf=True)
     loss = net.compute_rgb_loss(out["ray_rgb"], gt).mean() + (0.1 * out["gradient_error"]).mean()
+    if step >= net.cfg["occ_loss_step"]:
+        # trainer rule with the spherepot loss list (loss.py:97-98, :206-209)
+        loss = loss + out["loss_occ"].mean() + 0.5 * torch.nn.functional.mse_loss(out["color_bkgr"].flatten(),
+                                                                                  out["color_spec"].flatten())
     loss.backward()
     res = {"o": o, "d": d, "near": near, "far": far, "U0": U0, "U1": U1, "gt": gt, "z_vals": z,
            "loss": loss.detach(), "step": torch.tensor(step),
@@ -95,8 +122,12 @@ def run_case(net, R, sphere, perturb, step=10000):
         res[f"perm_{i}"] = rec.perms[i].int()
         res[f"z_merged_{i}"] = rec.sorted[i]
         res[f"z_in_{i}"], res[f"sdf_in_{i}"], res[f"inv_s_{i}"] = ups_in[i]
-    for k in ["ray_rgb", "gradient_error", "acc", "color_bkgr", "color_spec", "std", "transmission", "metallic"]:
+    for k in ["ray_rgb", "gradient_error", "acc", "color_bkgr", "color_spec", "std", "transmission", "metallic",
+              "loss_occ"]:
         res["out_" + k] = out[k].detach()
+    if rp.perms:
+        res["occ_perm"] = rp.perms[0]
+    res["occ_loss_max_pn"] = torch.tensor(net.cfg["occ_loss_max_pn"])
     for name, p in net.named_parameters():
         if p.grad is None:
             continue
@@ -114,6 +145,12 @@ def main():
                         **{k: fingerprint(v) for k, v in sd.items() if k != "color_network.FG_LUT"})
     np.savez_compressed(os.path.join(OUT, "stage1_train_R64.npz"), **run_case(net, 64, sphere=False, perturb=True))
     np.savez_compressed(os.path.join(OUT, "stage1_sphere_R64.npz"), **run_case(net, 64, sphere=True, perturb=False))
+    # step 20000: occlusion-probe loss + outer_reg active, inv_s trainable; occ_loss_max_pn lowered so that the
+    # randperm sub-sampling branch (ZT:708-714) is exercised with 64 rays
+    net.cfg["occ_loss_max_pn"] = 48
+    np.savez_compressed(os.path.join(OUT, "stage1_occ_R64.npz"), **run_case(net, 64, sphere=False, perturb=True,
+                                                                            step=20000))
+    net.cfg["occ_loss_max_pn"] = 2048
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

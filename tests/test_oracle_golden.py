@@ -25,8 +25,11 @@ def test_initialisation_is_bit_identical_to_the_reference(stage1_sd):
     assert sorted(set(stage1_sd) - set(G.files)) == ["color_network.FG_LUT"]
 
 
-@pytest.mark.parametrize("name,perturb", [("stage1_train_R64", True), ("stage1_sphere_R64", False)])
+@pytest.mark.parametrize("name,perturb", [("stage1_train_R64", True), ("stage1_sphere_R64", False),
+                                          ("stage1_occ_R64", True)])
 def test_torch_oracle_matches_reference_render_core(stage1_sd, name, perturb):
+    """stage1_occ_R64 is the step-20000 case: occlusion-probe loss with the reference's recorded randperm draw,
+    outer_reg, trainable inv_s."""
     from oracle import nunerf_oracle as orc
     G = np.load(os.path.join(GOLDEN, name + ".npz"))
     T = lambda k: torch.from_numpy(G[k])
@@ -34,10 +37,16 @@ def test_torch_oracle_matches_reference_render_core(stage1_sd, name, perturb):
               if v.dtype.is_floating_point and k != "color_network.FG_LUT"}
     sd = dict(stage1_sd)
     sd.update(params)
-    out = orc.render_core(sd, T("o"), T("d"), T("z_vals"), float(G["cos_anneal"]), int(G["step"]))
+    step = int(G["step"])
+    perm = T("occ_perm") if "occ_perm" in G.files else None
+    out = orc.render_core(sd, T("o"), T("d"), T("z_vals"), float(G["cos_anneal"]), step, occ_perm=perm,
+                          occ_max_pn=int(G["occ_loss_max_pn"]))
     for k in ("ray_rgb", "gradient_error", "acc", "color_bkgr", "color_spec", "std", "transmission", "metallic"):
         assert (out[k] - T("out_" + k)).abs().max().item() < 2e-6, k
-    loss = orc.train_loss(out, T("gt"))
+    assert abs(out["loss_occ"].mean().item() - float(G["out_loss_occ"].mean())) < 2e-6
+    if step >= 15000:
+        assert float(G["out_loss_occ"].mean()) > 1e-3 and perm is not None      # the probe really ran
+    loss = orc.train_loss(out, T("gt"), step=step)
     assert abs(loss.item() - float(G["loss"])) < 1e-6
     loss.backward()
     for k, p in params.items():
