@@ -142,23 +142,6 @@ def run_reference(args):
 
 
 # =============================================================================================== our arm
-def flatten_parameters(net):
-    """All parameters (and their gradients) as views of two flat fp32 buffers: one NCCL all-reduce, one Adam launch."""
-    import torch
-    ps = [p for p in net.parameters()]
-    total = sum(p.numel() for p in ps)
-    dev = ps[0].device
-    flat, gflat = torch.zeros(total, device=dev), torch.zeros(total, device=dev)
-    off = 0
-    for p in ps:
-        n = p.numel()
-        flat[off:off + n].copy_(p.data.reshape(-1))
-        p.data = flat[off:off + n].view_as(p.data)
-        p.grad = gflat[off:off + n].view_as(p.data)
-        off += n
-    return flat, gflat
-
-
 def profile_step(train_step, inputs, ops, torch):
     """Per-entry-point device time of one step (CUDA events around every C-ABI call; printed to stderr)."""
     import collections
@@ -209,6 +192,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from nu_nerf_b200 import _lib, ops
+    from nu_nerf_b200 import dist as nd
     from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
     from oracle import nunerf_oracle as orc   # synthetic input generators only (seeded rays / targets)
 
@@ -226,41 +210,26 @@ def run_ours(args):
     cfg["train_ray_num"] = R
     torch.manual_seed(0)
     net = NeROShapeRenderer(cfg, training=False).to(dev)
-    flat, gflat = flatten_parameters(net)
-    m_buf, v_buf = torch.zeros_like(flat), torch.zeros_like(flat)
-    lr = lr_at(STEP)
+    anneal = float(net.get_anneal_val(STEP))
+
+    def render_fn(o, d, near_, far_, step):
+        return net.render(o, d, near_, far_, None, -1, anneal, is_train=True, step=step, is_nerf=True)
+    # the product's ray-sharded trainer: global-denominator losses, one all-reduce of the flat gradient, CUDA Adam
+    trainer = nd.DataParallelTrainer(net, render_fn, net.compute_rgb_loss, lr_fn=lambda s: lr_at(s), eikonal_weight=EIK_W)
+    flat = trainer.fp.flat
     # rays: the same generator on every rank, rank-strided slices of one global batch
     o_all, d_all = orc.synthetic_rays(R * world, seed=1)
     gt_all = orc.synthetic_targets(R * world, seed=3)
-    o_h, d_h, gt_h = (t[rank::world].contiguous().pin_memory() for t in (o_all, d_all, gt_all))
+    sel = nd.shard_batch(torch.arange(R * world), rank, world)
+    o_h, d_h, gt_h = (t[sel].contiguous().pin_memory() for t in (o_all, d_all, gt_all))
     o_d, d_d, gt_d = o_h.to(dev), d_h.to(dev), gt_h.to(dev)
     near = torch.full((R, 1), 0.8, device=dev)
     far = torch.full((R, 1), 4.5, device=dev)
-    anneal = float(net.get_anneal_val(STEP))
-    adam_t = [0]
     stats = {"n_in": 0, "n_out": 0}
 
     def train_step(o, d, gt):
-        gflat.zero_()
-        total = torch.zeros((), device=dev)
-        for c0 in range(0, R, chunk):
-            sl = slice(c0, min(R, c0 + chunk))
-            out = net.render(o[sl], d[sl], near[sl], far[sl], None, -1, anneal, is_train=True, step=STEP, is_nerf=True)
-            n_in = torch.tensor(float(out["gradient_error"].shape[0]), device=dev)
-            if world > 1:
-                # global denominators so that SUM-all-reduced gradients equal the large-batch gradient
-                dist.all_reduce(n_in)
-                n_in = n_in / world
-            stats["n_in"] = int(out["gradient_error"].shape[0])
-            loss = net.compute_rgb_loss(out["ray_rgb"], gt[sl]).sum() / R + EIK_W * out["gradient_error"].sum() / (n_in * (R / (sl.stop - sl.start)))
-            loss.backward()
-            total = total + loss.detach()
-        if world > 1:
-            dist.all_reduce(gflat)
-            gflat.div_(world)
-        adam_t[0] += 1
-        _lib.call("nunerf_adam", flat.data_ptr(), gflat.data_ptr(), m_buf.data_ptr(), v_buf.data_ptr(), flat.numel(),
-                  lr, 0.9, 0.999, 1e-8, adam_t[0])
+        total = trainer.step(o, d, gt, near, far, STEP, chunk=chunk)
+        stats["n_in"] = trainer.last["n_in"]
         return total
 
     def e2e_step():

@@ -255,7 +255,10 @@ int nunerf_refract_bounce(const float* x_hit, const float* n_hit, const float* r
                           const int32_t* tri, int N, int inside, float* d_out, float* o_out, uint8_t* pass,
                           void* stream);
 
-/* ------------------------------------------------------------------ grid sweep (field.py:1286-1307) */
+/* ------------------------------------------------------------------ grid sweep (field.py:1286-1307)
+ * grid_points: points start..start+count of the res^3 grid in x-major order (the order of torch.meshgrid 'ij' +
+ *   reshape, field.py:1297-1300); lin = the three per-axis torch.linspace tables, [3, res].
+ * grid_mask  : u = outside_val where |p| >= 1 else sdf (field.py:1303-1304). */
 int nunerf_grid_points(int res, long long start, int count, const float* lin, float* pts, void* stream);
 int nunerf_grid_mask(const float* pts, const float* sdf, int ld_sdf, int count, float outside_val, float* u,
                      void* stream);

@@ -472,7 +472,7 @@ __global__ void grid_points_kernel(int res, long long start, long long count, co
   if (i >= count) return;
   long long g = start + i;
   int zi = (int)(g % res), yi = (int)((g / res) % res), xi = (int)(g / ((long long)res * res));
-  pts[3 * i] = lin[xi]; pts[3 * i + 1] = lin[yi]; pts[3 * i + 2] = lin[zi];
+  pts[3 * i] = lin[xi]; pts[3 * i + 1] = lin[res + yi]; pts[3 * i + 2] = lin[2 * res + zi];   // per-axis tables
 }
 __global__ void grid_mask_kernel(const float* __restrict__ pts, const float* __restrict__ sdf, int ld, long long count,
                                  float outside, float* u) {

@@ -89,6 +89,15 @@ class SDFNetwork(nn.Module):
     def layers(self):
         return [getattr(self, "lin" + str(l)) for l in range(self.num_layers - 1)]
 
+    # the renderer that owns this network installs the engine query (prepared weights live there)
+    _query = None
+
+    def sdf(self, x):
+        """SDFNetwork.sdf (field.py:152): [N,3] -> [N,1], no-grad engine query (extract_mesh_stage1.py:36)."""
+        if self._query is None:
+            raise RuntimeError("SDFNetwork.sdf needs the owning renderer's engine (construct it through a renderer)")
+        return self._query(x)
+
 
 class SingleVarianceNetwork(nn.Module):
     """field.py:191-208 -- inv_s = exp(10 * variance)."""

@@ -130,6 +130,7 @@ class NeROShapeRenderer(nn.Module):
         nn.init.constant_(self.outer_nerf.rgb_linear.bias, np.log(0.5))
         self.color_network = AppShadingNetwork(self.cfg["shader_config"])
         self.infinity_far_bkgr = InfOutNetwork()
+        self.sdf_network._query = self._sdf_query
         self.ray_source = None       # callable(step, n) -> dict(rays_o, rays_d, rgbs) ; replaces the image database
         if training:
             self._init_dataset()
@@ -201,6 +202,14 @@ class NeROShapeRenderer(nn.Module):
             self._w, self._w_key = eng.Stage1Weights(self, self._planes(), dev), key
         self._w.refresh()
         return self._w
+
+    @torch.no_grad()
+    def _sdf_query(self, x):
+        eng = _engine()
+        w = self._prepare()
+        shape = x.shape[:-1]
+        pts = x.reshape(-1, 3).float().contiguous()
+        return eng.sdf_infer(w.sdf, pts, w.planes).reshape(*shape, 1)
 
     # ------------------------------------------------------------------ ZT:572-612
     def sample_ray(self, rays_o, rays_d, near, far, perturb, uniforms=None, prepared=None, trace=None, sphere=False):
