@@ -424,6 +424,59 @@ class CoreTape:
 _MAT = ("metallic_predictor", "roughness_predictor", "albedo_predictor", "transmisstion_weight")
 
 
+def inner_forward(w: Stage1Weights, t):
+    """SDF network + sdf->alpha + shading on the compact inner samples t.pts_in / t.dists_in / t.dirs_in (ZT:759-769;
+    stage 2: ZT:1887-1906 with the inner field).  Fills t.a_in, t.c_in, t.gerr and the tape entries."""
+    planes, dev, M = w.planes, t.pts_in.device, t.n_in
+    t.xm = P(M, 320, planes, dev)                                    # [feature (256) | p (3) | 0]
+    f32_to_planes(t.pts_in, t.xm, M, 3, 64, col=256)
+    t.sdf = sdf_forward(w.sdf, t.pts_in, planes, t.xm)
+    t.a_in, t.gerr = _f(M, dev=dev), _f(M, dev=dev)
+    sa = _lib.SdfAlphaT()
+    sa.M, sa.cos_anneal, sa.inv_s_dev = M, t.cos_anneal, w.inv_s.data_ptr()
+    sa.sdf, sa.ld_sdf, sa.grad, sa.dists, sa.dirs = t.sdf.sdf.data_ptr(), 16, t.sdf.grad.data_ptr(), \
+        t.dists_in.data_ptr(), t.dirs_in.data_ptr()
+    sa.alpha, sa.grad_err = t.a_in.data_ptr(), t.gerr.data_ptr()
+    call("nunerf_sdf_alpha_fwd", C.byref(sa))
+    shade_forward(w, t, t.sdf.grad)
+
+
+def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
+    """AppShadingNetwork.forward (field.py:684-741) on M = t.n_in points: t.xm = [feature | p] planes, t.pts_in,
+    t.dirs_in (ray directions; view = -dirs), `normals` [M,3] (un-normalised: the SDF gradient in stage 1, the mesh
+    normal for the stage-2 surface hits).  no_refraction: the stage-2 surface shader has no refraction-light term
+    (field.py:966-967): its head is fed -inf so that exp(.) = 0 in the shared mixing kernel."""
+    planes, dev, M = w.planes, t.pts_in.device, t.n_in
+    # material predictors on [feature | p]
+    t.mat = {k: pred_forward(w.pred[k], t.xm, M, 320, planes) for k in _MAT}
+    # directions + encodings (the encode kernel writes whole 128-column rows, zero padded: no prior fill needed)
+    t.xo, t.xi = P(3 * M, 128, planes, dev), P(2 * M, 128, planes, dev)
+    t.xw, t.xr = P(M, 128, planes, dev), P(M, 128, planes, dev)
+    t.nov = _f(M, dev=dev)
+    t.normals = normals
+    se = _lib.ShadeEncodeT()
+    se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), normals.data_ptr(), t.dirs_in.data_ptr()
+    se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
+    se.x_outer, se.ld_outer, se.lo_outer = t.xo.ptr, t.xo.ld, t.xo.lo
+    se.x_inner, se.ld_inner, se.lo_inner = t.xi.ptr, t.xi.ld, t.xi.lo
+    se.x_weight, se.ld_weight, se.lo_weight = t.xw.ptr, t.xw.ld, t.xw.lo
+    se.x_refrac, se.ld_refrac, se.lo_refrac = t.xr.ptr, t.xr.ld, t.xr.lo
+    se.nov = t.nov.data_ptr()
+    t.refl = _f(M, 3, dev=dev)
+    se.refl = t.refl.data_ptr()
+    call("nunerf_shade_encode_fwd", C.byref(se))
+    t.lo_ = pred_forward(w.pred["outer_light"], t.xo, 3 * M, 128, planes)
+    t.li_ = pred_forward(w.pred["inner_light"], t.xi, 2 * M, 128, planes)
+    t.lw_ = pred_forward(w.pred["inner_weight"], t.xw, M, 128, planes)
+    if no_refraction:
+        t.lr_ = PredTape()
+        t.lr_.head = torch.full((M, 16), float("-inf"), device=dev)
+    else:
+        t.lr_ = pred_forward(w.pred["refrac_light"], t.xr, M, 128, planes)
+    t.c_in, t.trans, t.metallic, t.occ = _f(M, 3, dev=dev), _f(M, dev=dev), _f(M, dev=dev), _f(M, dev=dev)
+    call("nunerf_shade_mix_fwd", C.byref(_mix_params(w, t)))
+
+
 def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max):
     """ZT:725-793 forward.  Returns the tape and the output tensors."""
     planes = w.planes
@@ -455,42 +508,8 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
         t.nerf, t.a_out, t.c_out = None, _z(1, dev=dev), _z(1, 3, dev=dev)
 
     # ---- inner samples: SDF + shading (ZT:759-769)
-    M = n_in
-    if M > 0:
-        t.xm = P(M, 320, planes, dev)                                    # [feature (256) | p (3) | 0]
-        f32_to_planes(t.pts_in, t.xm, M, 3, 64, col=256)
-        t.sdf = sdf_forward(w.sdf, t.pts_in, planes, t.xm)
-        t.a_in, t.gerr = _f(M, dev=dev), _f(M, dev=dev)
-        sa = _lib.SdfAlphaT()
-        sa.M, sa.cos_anneal, sa.inv_s_dev = M, t.cos_anneal, w.inv_s.data_ptr()
-        sa.sdf, sa.ld_sdf, sa.grad, sa.dists, sa.dirs = t.sdf.sdf.data_ptr(), 16, t.sdf.grad.data_ptr(), \
-            t.dists_in.data_ptr(), t.dirs_in.data_ptr()
-        sa.alpha, sa.grad_err = t.a_in.data_ptr(), t.gerr.data_ptr()
-        call("nunerf_sdf_alpha_fwd", C.byref(sa))
-        # material predictors on [feature | p]
-        t.mat = {k: pred_forward(w.pred[k], t.xm, M, 320, planes) for k in _MAT}
-        # directions + encodings
-        # (the encode kernel writes whole 128-column rows, zero padded: no prior fill needed)
-        t.xo, t.xi = P(3 * M, 128, planes, dev), P(2 * M, 128, planes, dev)
-        t.xw, t.xr = P(M, 128, planes, dev), P(M, 128, planes, dev)
-        t.nov = _f(M, dev=dev)
-        se = _lib.ShadeEncodeT()
-        se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.sdf.grad.data_ptr(), t.dirs_in.data_ptr()
-        se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
-        se.x_outer, se.ld_outer, se.lo_outer = t.xo.ptr, t.xo.ld, t.xo.lo
-        se.x_inner, se.ld_inner, se.lo_inner = t.xi.ptr, t.xi.ld, t.xi.lo
-        se.x_weight, se.ld_weight, se.lo_weight = t.xw.ptr, t.xw.ld, t.xw.lo
-        se.x_refrac, se.ld_refrac, se.lo_refrac = t.xr.ptr, t.xr.ld, t.xr.lo
-        se.nov = t.nov.data_ptr()
-        t.refl = _f(M, 3, dev=dev)
-        se.refl = t.refl.data_ptr()
-        call("nunerf_shade_encode_fwd", C.byref(se))
-        t.lo_ = pred_forward(w.pred["outer_light"], t.xo, 3 * M, 128, planes)
-        t.li_ = pred_forward(w.pred["inner_light"], t.xi, 2 * M, 128, planes)
-        t.lw_ = pred_forward(w.pred["inner_weight"], t.xw, M, 128, planes)
-        t.lr_ = pred_forward(w.pred["refrac_light"], t.xr, M, 128, planes)
-        t.c_in, t.trans, t.metallic, t.occ = _f(M, 3, dev=dev), _f(M, dev=dev), _f(M, dev=dev), _f(M, dev=dev)
-        call("nunerf_shade_mix_fwd", C.byref(_mix_params(w, t)))
+    if t.n_in > 0:
+        inner_forward(w, t)
     else:
         t.a_in, t.c_in, t.gerr = _z(1, dev=dev), _z(1, 3, dev=dev), None
 
@@ -605,3 +624,198 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     # ---- SDF network
     sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad)
     return g
+
+
+# =============================================================================================== stage 2 (forward)
+class IorWeights:
+    """IoRNetwork (field.py:1046-1065): PE-6 -> 256 relu -> 256 relu -> 256 -> 1, sigmoid (Sequential 0, 2, 4, 5)."""
+
+    def __init__(self, net, planes, device):
+        self.planes = planes
+        self.bank = WeightBank(planes, device)
+        self.L = [Dense(self.bank, *_wn(net.module0[i]), need_t=False, grad=False) for i in (0, 2, 4, 5)]
+        self.bank.finalize()
+
+    def refresh(self):
+        self.bank.prepare()
+
+
+@torch.no_grad()
+def ior_forward(w: IorWeights, pts):
+    """IoRNetwork.forward on [M,3] points -> [M] (after the sigmoid)."""
+    M, dev, planes = pts.shape[0], pts.device, w.planes
+    x0 = P(M, 64, planes, dev)
+    call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, x0.ptr, x0.ld, x0.lo, 0, 0, 64)
+    a, b = P(M, 256, planes, dev), P(M, 256, planes, dev)
+    linear(x0, w.L[0].Wk, M, 256, 64, bias=w.L[0].b, act=1, out=a)
+    linear(a, w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=1, out=b)
+    linear(b, w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=0, out=a)
+    out = _f(M, 16, dev=dev)
+    linear(a, w.L[3].Wk, M, 16, 256, bias=w.L[3].b, out_f32=out, n_store=1)
+    return torch.sigmoid(out[:, 0])
+
+
+def segment_points(start, delta, z):
+    """[R, n, 3] points start + delta * z (ZT:1727-1731, :1760, :1799)."""
+    R, n = z.shape
+    pts = _f(R, n, 3, dev=z.device)
+    if R > 0:
+        call("nunerf_points", start.contiguous().data_ptr(), delta.contiguous().data_ptr(), z.contiguous().data_ptr(),
+             R, n, pts.data_ptr())
+    return pts
+
+
+@torch.no_grad()
+def upsample_rounds(w: Stage1Weights, o, d, z, sdf, n_new, rounds):
+    """`rounds` SDF-guided importance rounds with `n_new` samples each on the field `w` (ZT:1748-1758: inv_s capped at
+    64 * 2^i, new SDF values queried at o + d * z_new, no query after the last round).  Returns the merged z."""
+    R, n = z.shape
+    dev = z.device
+    _, utabs = _tables(dev)
+    u_tab = utabs[n_new]
+    for i in range(rounds):
+        z_new, inds = _f(R, n_new, dev=dev), torch.empty(R, n_new, dtype=torch.int32, device=dev)
+        z_m, perm = _f(R, n + n_new, dev=dev), torch.empty(R, n + n_new, dtype=torch.int32, device=dev)
+        call("nunerf_upsample", o.data_ptr(), d.data_ptr(), z.data_ptr(), sdf.data_ptr(), R, n, n_new,
+             w.inv_s.data_ptr(), float(64 * 2 ** i), u_tab.data_ptr(), z_new.data_ptr(), inds.data_ptr(),
+             z_m.data_ptr(), perm.data_ptr())
+        if i + 1 < rounds:
+            npts = segment_points(o, d, z_new)
+            sdf_new = sdf_infer(w.sdf, npts.reshape(-1, 3), w.planes).reshape(R, n_new).contiguous()
+            sdf_m = _f(R, n + n_new, dev=dev)
+            call("nunerf_merge_sdf", sdf.data_ptr(), sdf_new.data_ptr(), perm.data_ptr(), R, n, n_new, sdf_m.data_ptr())
+            sdf = sdf_m
+        z, n = z_m, n + n_new
+    return z
+
+
+@torch.no_grad()
+def nerf_alpha(w: NerfW, pts, dirs, dists, planes):
+    """alpha of compute_density_alpha (ZT:1531-1539) on a flat list of samples."""
+    _, alpha, _ = nerf_forward(w, pts.contiguous(), dirs.contiguous(), dists.contiguous(), planes)
+    return alpha
+
+
+@torch.no_grad()
+def importance_merge(z, alpha, n_new):
+    """upsample_nerf + cat_z_vals_nerf (ZT:1367-1397): weights = alpha * T, sample_pdf(z, weights[:, :-1], n_new, det),
+    sorted merge.  Only the rays that miss the outer mesh take this path ([R_miss, 192] tensors): torch glue."""
+    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
+    w = (alpha * T)[:, :-1] + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)
+    u = torch.linspace(0.5 / n_new, 1.0 - 0.5 / n_new, n_new, device=z.device).expand(cdf.shape[0], n_new).contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    lo, hi = torch.clamp(inds - 1, min=0), torch.clamp(inds, max=cdf.shape[-1] - 1)
+    c0, c1 = torch.gather(cdf, 1, lo), torch.gather(cdf, 1, hi)
+    b0, b1 = torch.gather(z, 1, lo), torch.gather(z, 1, hi)
+    den = c1 - c0
+    den = torch.where(den < 1e-5, torch.ones_like(den), den)
+    z_new = b0 + (u - c0) / den * (b1 - b0)
+    return torch.sort(torch.cat([z, z_new], -1), dim=-1)[0].contiguous()
+
+
+def _srgb_to_linear(x):
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.04045, 25.0 / 323.0 * x, ((200.0 * x + 11.0) / 211.0).clamp(min=eps) ** (12.0 / 5.0))
+
+
+@torch.no_grad()
+def segment_forward(w1: Stage1Weights, w_inner, cand, dirs, cos_anneal, exp_max_inner):
+    """One path segment of Stage2Renderer.render_core (ZT:1853-1951): cand [N, S+1, 3] sampled points (the last one is
+    the surface hit and is shaded separately), dirs [N,3].  NeRF++ (stage-1 outer_nerf) on the samples outside the unit
+    sphere, the inner SDF field (+ shading) on the inside ones when `w_inner` is given (segment 1).
+    Returns color_lin [N,3] = sum_j w_j srgb_to_linear(c_j), t_end [N,1], the inner gradient error and counts."""
+    N, S1, _ = cand.shape
+    S = S1 - 1
+    dev = cand.device
+    pts = cand[:, :-1, :].contiguous()
+    d = pts[:, 1:] - pts[:, :-1]
+    dists = torch.linalg.norm(d, dim=-1)
+    dists = torch.cat([dists, dists[:, -1:]], -1)
+    inner = torch.norm(pts, dim=-1) <= 1.0
+    outer = ~inner
+    alpha = torch.zeros(N, S, device=dev)
+    color = torch.zeros(N, S, 3, device=dev)
+    dirs_e = dirs[:, None, :].expand(N, S, 3)
+    out = {"n_in": 0, "gerr": None}
+    if bool(outer.any()):
+        p_o, d_o, di_o = pts[outer].contiguous(), dirs_e[outer].contiguous(), dists[outer].contiguous()
+        _, a_o, c_o = nerf_forward(w1.nerf, p_o, d_o, di_o, w1.planes)
+        alpha[outer] = a_o
+        color[outer] = c_o
+    if w_inner is not None and bool(inner.any()):
+        t = CoreTape()
+        t.pts_in, t.dirs_in, t.dists_in = pts[inner].contiguous(), dirs_e[inner].contiguous(), dists[inner].contiguous()
+        t.n_in, t.cos_anneal, t.exp_max = t.pts_in.shape[0], float(cos_anneal), float(exp_max_inner)
+        inner_forward(w_inner, t)
+        alpha[inner] = t.a_in
+        color[inner] = t.c_in
+        out["n_in"], out["gerr"] = t.n_in, t.gerr
+    # linear-space compositing (ZT:1942-1951)
+    color = _srgb_to_linear(color)
+    Tc = torch.cumprod(torch.cat([torch.ones(N, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)
+    wts = alpha * Tc[:, :-1]
+    out["color_lin"] = (color * wts[..., None]).sum(dim=1)
+    out["t_end"] = Tc[:, -1:]
+    return out
+
+
+@torch.no_grad()
+def surface_shade(w1: Stage1Weights, pts, normals, dirs, exp_max, internal=False, extras=False):
+    """AppShadingNetwork_S2.forward (field.py:909-1010) at the mesh hits: stage-1 SDF feature vector (ZT:1519-1529),
+    stage-1 predictors, MESH normal, no refraction-light term; `internal` zeroes the colour (field.py:969)."""
+    M, dev, planes = pts.shape[0], pts.device, w1.planes
+    t = CoreTape()
+    t.pts_in, t.dirs_in, t.n_in, t.exp_max = pts, dirs, M, float(exp_max)
+    t.xm = P(M, 320, planes, dev)
+    f32_to_planes(pts, t.xm, M, 3, 64, col=256)
+    sdf_forward(w1.sdf, pts, planes, t.xm)                 # value pass fills the feature columns of xm
+    shade_forward(w1, t, normals.contiguous(), no_refraction=True)
+    nov = t.nov[:, None]
+    tn = torch.clamp(1.0 - nov, 0.0, 1.0)
+    rw = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)
+    trans = t.trans[:, None]
+    color = t.c_in
+    if internal:
+        color = torch.zeros_like(color)                    # linear_to_srgb(0) = 0
+    res = {"color": color, "refraction_coefficient": (1.0 - rw) * trans}
+    if extras:
+        # eval-mode buffers of field.py:981-1001, rebuilt from the predictor heads (per-ray tensors)
+        head = lambda tp, n: tp.head[:, :n]
+        met = torch.sigmoid(head(t.mat["metallic_predictor"], 1))
+        rough = torch.sigmoid(head(t.mat["roughness_predictor"], 1))
+        alb = torch.sigmoid(head(t.mat["albedo_predictor"], 3))
+        ex = lambda x: torch.exp(torch.clamp(x, max=exp_max))
+        lo = head(t.lo_, 3)
+        direct, direct0 = ex(lo[M:2 * M]), ex(lo[2 * M:3 * M])
+        li = head(t.li_, 3)
+        ind, ind0 = ex(li[:M]), ex(li[M:2 * M])
+        occ = torch.clamp(head(t.lw_, 1) * 0.5 + 0.5, 0.0, 1.0)
+        light = ind * occ + direct * (1 - occ)
+        light0 = ind0 * occ + direct0 * (1 - occ)
+        spec_albedo = 0.04 * (1 - met) + met * alb
+        fg = _fg_lookup_torch(w1.lut, torch.clamp(nov[:, 0], 0.0, 1.0), torch.clamp(rough[:, 0], 0.0, 1.0))
+        spec_ref = spec_albedo * fg[:, 0:1] + fg[:, 1:2]
+        spec_color = _lin2srgb(spec_ref * light)
+        res["specular_ref"] = torch.clamp(spec_ref, 0.0, 1.0)
+        res["specular_light"] = torch.clamp(_lin2srgb(light0), 0.0, 1.0)
+        res["specular_color"] = torch.clamp(spec_color * (1 - trans) + rw * light0 * trans, 0.0, 1.0)
+    return res
+
+
+def _lin2srgb(x):
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.0031308, 323.0 / 25.0 * x, (211.0 * torch.clamp(x, min=eps) ** (5.0 / 12.0) - 11.0) / 200.0)
+
+
+def _fg_lookup_torch(lut, u, v):
+    """dr.texture(FG_LUT, (u, v), linear, clamp) on per-ray tensors (eval buffers only)."""
+    tex = lut.reshape(256, 256, 2)
+    fx = torch.clamp(u * 256 - 0.5, 0.0, 255.0)
+    fy = torch.clamp(v * 256 - 0.5, 0.0, 255.0)
+    x0, y0 = fx.floor().long(), fy.floor().long()
+    x1, y1 = torch.clamp(x0 + 1, max=255), torch.clamp(y0 + 1, max=255)
+    tx, ty = (fx - x0)[:, None], (fy - y0)[:, None]
+    c00, c01, c10, c11 = tex[y0, x0], tex[y0, x1], tex[y1, x0], tex[y1, x1]
+    return (c00 * (1 - tx) + c01 * tx) * (1 - ty) + (c10 * (1 - tx) + c11 * tx) * ty

@@ -198,3 +198,29 @@ class IoRNetwork(nn.Module):
         self.module0 = nn.Sequential(
             WNLinear(nn.Linear(d, run_dim)), _Slot(), WNLinear(nn.Linear(run_dim, run_dim)), _Slot(),
             WNLinear(nn.Linear(run_dim, run_dim)), WNLinear(nn.Linear(run_dim, 1)), _Slot())
+
+
+class ThicknessNetwork(nn.Module):
+    """field.py:1068-1081 -- same layout as IoRNetwork; constructed by Stage2Renderer (ZT:951) and only evaluated by the
+    non-zero-thickness renderer (network/renderer.py), kept here so that seeds and checkpoints line up."""
+
+    def __init__(self):
+        super().__init__()
+        run_dim, d = 256, pe_dim(6)
+        self.module0 = nn.Sequential(
+            WNLinear(nn.Linear(d, run_dim)), _Slot(), WNLinear(nn.Linear(run_dim, run_dim)), _Slot(),
+            WNLinear(nn.Linear(run_dim, run_dim)), WNLinear(nn.Linear(run_dim, 1)), _Slot())
+
+
+class AppShadingNetwork_S2(nn.Module):
+    """field.py:786-803 -- the stage-2 surface shader owns no parameters: it evaluates the stage-1 colour network's
+    predictors (registered here again as `stage1_network`, as the reference does, so state_dict keys match)."""
+    default_cfg = {"human_light": False, "sphere_direction": True, "light_pos_freq": 6, "inner_init": -0.95,
+                   "roughness_init": 0.0, "metallic_init": 0.0, "light_exp_max": 5.0, "refrac_freq": 6}
+
+    def __init__(self, cfg, stage1):
+        super().__init__()
+        self.cfg = {**self.default_cfg, **cfg}
+        if self.cfg["human_light"] or self.cfg["sphere_direction"]:
+            raise NotImplementedError("stage-2 shader: human_light / sphere_direction variants are not built")
+        self.stage1_network = stage1

@@ -1,0 +1,315 @@
+"""Stage2Renderer -- the zero-thickness nested-refraction renderer of network/renderer_zerothick.py:868-2011 ("ZT")
+on the sm_100a engine.  FORWARD path (ray_trace + render_core, train- and eval-mode outputs); the backward through the
+bounce geometry is not built yet (rendering under autograd raises).
+
+  ray_trace   ZT:1571-1828   <= 3 bounces: BVH closest hit + re-intersection (csrc/bvh.cu), IoR MLP on tensor cores,
+                             Snell / TIR kernel, segment sampling (256 uniform | 64 + 2 x 32 SDF-guided with the warp
+                             per-ray up-sampling kernel | 192 + 64 NeRF-guided on [0.1, 64])
+  render_core ZT:1835-2011   per segment: NeRF++ on the outer samples, inner SDF + shading on segment 1, surface
+                             shading at the hit with the mesh normal and the stage-1 predictors, linear-space
+                             compositing with the throughput chain T *= T_end (1 - schlick) transmission
+
+Lists returned by ray_trace have the reference's exact structure (per-segment compacted rows in boolean-mask order),
+so render_core accepts the reference's ray_trace output and vice versa.  The per-ray bookkeeping between bounces
+(mask compaction, TIR chain) is torch indexing on [R]-sized tensors, as in the reference; everything per sample point
+runs in libnunerf_b200.so.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .field import (SDFNetwork, SingleVarianceNetwork, NeRFNetwork, AppShadingNetwork, AppShadingNetwork_S2, IoRNetwork,
+                    ThicknessNetwork)
+
+
+def _engine():
+    from . import engine
+    return engine
+
+
+def srgb_to_linear(x):
+    """utils/raw_utils.py:21-27."""
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.04045, 25.0 / 323.0 * x, ((200.0 * x + 11.0) / 211.0).clamp(min=eps) ** (12.0 / 5.0))
+
+
+def linear_to_srgb(x):
+    eps = torch.finfo(torch.float32).eps
+    return torch.where(x <= 0.0031308, 323.0 / 25.0 * x, (211.0 * torch.clamp(x, min=eps) ** (5.0 / 12.0) - 11.0) / 200.0)
+
+
+class _InnerField:
+    """The (sdf_network_inner, deviation_network_inner, color_network_inner) triple seen as a stage-1 field."""
+
+    def __init__(self, r):
+        self.sdf_network, self.deviation_network = r.sdf_network_inner, r.deviation_network_inner
+        self.color_network, self.outer_nerf = r.color_network_inner, r.outer_nerf
+
+
+class Stage2Renderer(nn.Module):
+    default_cfg = {
+        "std_net": "default", "std_act": "exp", "inv_s_init": 0.3, "freeze_inv_s_step": None,
+        "sdf_net": "default", "sdf_activation": "none", "sdf_bias": 0.5, "sdf_n_layers": 8, "sdf_freq": 6,
+        "sdf_d_out": 257, "geometry_init": True, "shader_config": {},
+        "n_samples": 64, "n_bg_samples": 32, "inf_far": 1000.0, "n_importance": 64, "up_sample_steps": 4,
+        "perturb": 1.0, "anneal_end": 50000, "train_ray_num": 1024, "test_ray_num": 1024,
+        "clip_sample_variance": True, "database_name": "nerf_synthetic/lego/black_800", "is_nerf": False,
+        "test_downsample_ratio": True, "downsample_ratio": 0.5, "val_geometry": False,
+        "rgb_loss": "charbonier", "apply_occ_loss": True, "occ_loss_step": 20000, "occ_loss_max_pn": 2048,
+        "occ_sdf_thresh": 0.01, "fixed_camera": False,
+        "precision": "split",
+    }
+
+    def __init__(self, cfg, training=True):
+        super().__init__()
+        from .renderer_zerothick import NeROShapeRenderer, load_cfg
+        from .tracer import Scene
+        self.cfg = {**self.default_cfg, **cfg}
+        self.is_nerf = self.cfg["is_nerf"]
+        if (self.cfg["sdf_n_layers"], self.cfg["sdf_freq"], self.cfg["sdf_d_out"]) != (8, 6, 257) or \
+                not self.cfg["clip_sample_variance"]:
+            raise NotImplementedError("the B200 engine is built for the 8x256 / PE-6 / 257-output SDF network")
+        # construction order = the reference's (ZT:919-975): same seed => bit-identical initial parameters
+        self.nerf_network = NeRFNetwork(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, skips=(4,))
+        self.IORs = nn.Parameter(torch.zeros(10))
+        cfg1 = cfg["stage1_cfg_dir"]
+        cfg1 = dict(cfg1) if isinstance(cfg1, dict) else load_cfg(cfg1)
+        cfg1.setdefault("precision", self.cfg["precision"])
+        self.stage1_network = NeROShapeRenderer(cfg1, training=False)
+        ckpt = cfg["stage1_ckpt_dir"]
+        ckpt = ckpt if isinstance(ckpt, dict) else torch.load(ckpt, map_location="cpu")
+        self.stage1_network.load_state_dict(ckpt["network_state_dict"], strict=False)
+        self._mesh = cfg["stage1_mesh_dir"]          # path (.ply / .npz) or (vertices, faces)
+        self.scene = None                            # built on first use, on the parameters' device
+        self._scene_cls = Scene
+        self.IORs_pred = IoRNetwork()
+        self.IoRint_pred = IoRNetwork()
+        self.thickness_pred = ThicknessNetwork()
+        self.outer_nerf = NeRFNetwork(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, skips=(4,))
+        self.color_network = AppShadingNetwork_S2(self.cfg["shader_config"], self.stage1_network)
+        self.sdf_network_inner = SDFNetwork(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=(4,), multires=6,
+                                            bias=self.cfg["sdf_bias"], scale=1.0,
+                                            geometric_init=self.cfg["geometry_init"])
+        self.deviation_network_inner = SingleVarianceNetwork(init_val=self.cfg["inv_s_init"],
+                                                             activation=self.cfg["std_act"])
+        self.color_network_inner = AppShadingNetwork(self.cfg["shader_config"])
+        self.sdf_network_inner._query = self._sdf_inner_query
+        self.ray_source = None
+
+    # ------------------------------------------------------------------ helpers identical to the reference
+    def set_ray_source(self, fn):
+        self.ray_source = fn
+
+    def get_anneal_val(self, step):
+        if self.cfg["anneal_end"] < 0:
+            return 1.0
+        return np.min([1.0, step / self.cfg["anneal_end"]])
+
+    def compute_rgb_loss(self, rgb_pr, rgb_gt):
+        if self.cfg["rgb_loss"] == "charbonier":
+            return torch.sqrt(torch.sum((rgb_gt - rgb_pr) ** 2, dim=-1) + 0.001)
+        raise NotImplementedError
+
+    # ------------------------------------------------------------------ engine operands
+    def _planes(self):
+        return 2 if self.cfg["precision"] == "split" else 1
+
+    def _prepare(self):
+        dev = self.deviation_network_inner.variance.device
+        if not torch.cuda.is_available() or dev.type != "cuda":
+            raise RuntimeError("nu_nerf_b200 renders on a CUDA device only (no CPU fallback): move the module with .cuda()")
+        eng = _engine()
+        self.stage1_network.cfg["precision"] = self.cfg["precision"]
+        w1 = self.stage1_network._prepare()
+        key = (self._planes(),) + tuple(p.data_ptr() for p in self.parameters())
+        if getattr(self, "_w", None) is None or self._w_key != key:
+            inner = eng.Stage1Weights(_InnerField(self), self._planes(), dev)
+            ior = eng.IorWeights(self.IORs_pred, self._planes(), dev)
+            self._w, self._w_key = (inner, ior), key
+        self._w[0].refresh()
+        self._w[1].refresh()
+        if self.scene is None:
+            m = self._mesh
+            self.scene = self._scene_cls(m, device=dev) if isinstance(m, str) else self._scene_cls(m[0], m[1], device=dev)
+        return w1, self._w[0], self._w[1]
+
+    @torch.no_grad()
+    def _sdf_inner_query(self, x):
+        eng = _engine()
+        _, wi, _ = self._prepare()
+        shape = x.shape[:-1]
+        return eng.sdf_infer(wi.sdf, x.reshape(-1, 3).float().contiguous(), wi.planes).reshape(*shape, 1)
+
+    # ------------------------------------------------------------------ ZT:1571-1828
+    @torch.no_grad()
+    def ray_trace(self, rays_o, rays_d, prepared=None, trace=None):
+        eng = _engine()
+        w1, wi, wior = prepared if prepared is not None else self._prepare()
+        dev = rays_o.device
+        o, d = rays_o.float().contiguous(), rays_d.float().contiguous()
+        next_start, next_dir = o, d
+        starts, directions = [o], [d]
+        intersections, converges, infinity_bkgr, ior_ratios, gradient_mesh, tirs = [], [], [], [], [], []
+        inside = False
+        for i in range(3):
+            N = next_start.shape[0]
+            info, hit = self.scene.Dintersect(next_start, next_dir)       # closest hit + re-intersection (a14, a15)
+            if trace is not None:
+                trace[f"trace_hit_{i}"], trace[f"trace_tri_{i}"] = hit.float(), info["faces_ind"]
+            converged = hit.reshape(-1, 1)
+            x_c = info["x"][hit].contiguous()
+            n_c = F.normalize(info["n"][hit], dim=-1)
+            if inside:
+                n_c = -n_c
+            d_c = next_dir[hit].contiguous()
+            infinity_bkgr.append(~converged)
+            M = x_c.shape[0]
+            if M > 0:
+                eta = 1.0 / (eng.ior_forward(wior, x_c) + 1.0)                 # ZT:1642-1643
+                d_out, o_out = torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev)
+                ok = torch.empty(M, dtype=torch.uint8, device=dev)
+                tri_c = info["faces_ind"][hit].contiguous()
+                eng.call("nunerf_refract_bounce", x_c.data_ptr(), info["n"][hit].contiguous().data_ptr(),
+                         d_c.data_ptr(), eta.contiguous().data_ptr(), tri_c.data_ptr(), M, int(inside),
+                         d_out.data_ptr(), o_out.data_ptr(), ok.data_ptr())
+                ok = ok.bool()
+                ratio = (1.0 / eta if inside else eta).reshape(-1, 1)
+            else:
+                d_out = o_out = torch.zeros(0, 3, device=dev)
+                ok = torch.zeros(0, dtype=torch.bool, device=dev)
+                ratio = torch.zeros(0, 1, device=dev)
+            converged_out = converged.clone()
+            converged_out[hit] = ok.reshape(-1, 1)
+            tir = torch.ones(N, 1, dtype=torch.bool, device=dev)
+            tir[hit] = ok.reshape(-1, 1)
+            tirs.append(tir)
+            next_dir, next_start = d_out[ok].contiguous(), o_out[ok].contiguous()
+            directions.append(next_dir)
+            starts.append(next_start)
+            converges.append(converged_out)
+            intersections.append(x_c)
+            if not bool(converged_out.any()):
+                break
+            gradient_mesh.append(n_c[ok])
+            ior_ratios.append(ratio[ok])
+            inside = not inside
+        for i in range(len(tirs) - 1, 0, -1):
+            m = converges[i - 1].flatten()
+            tirs[i - 1][m] = tirs[i - 1][m] & tirs[i]
+        # ---- per-segment sample generation (ZT:1719-1813)
+        pathes = []
+        for k in range(len(converges)):
+            start, dk = starts[k], directions[k]
+            bk = infinity_bkgr[k].flatten()
+            end = start + dk * 4.5
+            if bool((~bk).any()):
+                end[~bk] = intersections[k]
+            n_pts = 256 if k != 1 else 128
+            lin = torch.linspace(0, 1, n_pts, device=dev)
+            pts = eng.segment_points(start, end - start, lin.unsqueeze(0).expand(start.shape[0], n_pts).contiguous())
+            if k == 1 and bool((~bk).any()):
+                # inside the outer mesh: 64 uniform samples to the hit, 2 rounds of SDF-guided up-sampling with 32 new
+                # samples each on the inner field; z is the unit parameter of the segment while the SDF is queried at
+                # start + dir * z -- the reference's mixed parametrisation, reproduced as written (ZT:1742-1760)
+                s_h, e_h, d_h = start[~bk].contiguous(), end[~bk].contiguous(), dk[~bk].contiguous()
+                Rh = s_h.shape[0]
+                z = torch.linspace(0, 1, 64, device=dev).unsqueeze(0).expand(Rh, 64).contiguous()
+                p64 = eng.segment_points(s_h, e_h - s_h, z)
+                sdf = eng.sdf_infer(wi.sdf, p64.reshape(-1, 3), wi.planes).reshape(Rh, 64).contiguous()
+                z = eng.upsample_rounds(wi, s_h, d_h, z, sdf, n_new=32, rounds=2)
+                pts[~bk] = eng.segment_points(s_h, e_h - s_h, z)
+            if k != 1 and bool(bk.any()):
+                # rays that leave the scene: 192 samples on [0.1, 64] + 64 NeRF++-guided ones (ZT:1762-1799)
+                s_m, d_m = start[bk].contiguous(), dk[bk].contiguous()
+                Rm = s_m.shape[0]
+                z = torch.linspace(0.1, 64.0, 192, device=dev).unsqueeze(0).expand(Rm, 192).contiguous()
+                p = eng.segment_points(s_m, d_m, z)
+                dists = z[:, 1:] - z[:, :-1]
+                dists = torch.cat([dists, dists[:, -1:]], -1).contiguous()
+                alpha = eng.nerf_alpha(w1.nerf, p.reshape(-1, 3), d_m.repeat_interleave(192, 0), dists.reshape(-1),
+                                       w1.planes).reshape(Rm, 192)
+                z = eng.importance_merge(z, alpha, 64)
+                pts[bk] = eng.segment_points(s_m, d_m, z)
+            pathes.append(pts)
+        return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
+
+    # ------------------------------------------------------------------ ZT:1835-2011
+    @torch.no_grad()
+    def render_core(self, rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
+                    human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True, is_nerf=False, prepared=None):
+        eng = _engine()
+        w1, wi, _ = prepared if prepared is not None else self._prepare()
+        dev = rays_o.device
+        R = converges[0].shape[0]
+        T = torch.ones(R, 3, device=dev)
+        normals_out = torch.zeros(R, 3, device=dev)
+        spec_color_out, spec_light_out, spec_ref_out = (torch.zeros(R, 3, device=dev) for _ in range(3))
+        colors, tmp = [], {}
+        exp_max1 = self.stage1_network.color_network.cfg["light_exp_max"]
+        exp_maxi = self.color_network_inner.cfg["light_exp_max"]
+        for i in range(len(pathes)):
+            cand = pathes[i]
+            N = cand.shape[0]
+            conv = converges[i].flatten()
+            dirs_i = directions[i]
+            seg = eng.segment_forward(w1, wi if i == 1 else None, cand, dirs_i, float(cos_anneal_ratio), exp_maxi)
+            if i == 1 and seg["n_in"] > 0:
+                inv_s = torch.exp(self.deviation_network_inner.variance.detach() * 10.0).clip(1e-6, 1e6)
+                tmp["std"] = torch.mean(1.0 / inv_s)
+                tmp["gradient_error"] = seg["gerr"]
+            color_now = seg["color_lin"] * T                              # sum w * srgb_to_linear(c), ZT:1946-1951
+            T = T * seg["t_end"]
+            n_hit = int(conv.sum())
+            if n_hit > 0:
+                p_hit = cand[conv][:, -1, :].contiguous()
+                sh = eng.surface_shade(w1, p_hit, gradient_mesh[i].contiguous(), dirs_i[conv].contiguous(), exp_max1,
+                                       internal=(i % 2 != 0), extras=(i == 0 and not is_train))
+                color_now[conv] = color_now[conv] + srgb_to_linear(sh["color"]) * T[conv]
+                if i == 0 and not is_train:
+                    normals_out[conv] = (F.normalize(gradient_mesh[i].reshape(-1, 3), dim=-1) + 1.0) * 0.5
+                    spec_color_out[conv], spec_light_out[conv], spec_ref_out[conv] = \
+                        sh["specular_color"], sh["specular_light"], sh["specular_ref"]
+                T = T[conv] * sh["refraction_coefficient"]
+                colors.append(color_now)
+            else:
+                colors.append(color_now)
+                break
+        for i in range(len(colors) - 1, 0, -1):
+            m = converges[i - 1].flatten()
+            colors[i - 1][m] = colors[i - 1][m] + colors[i]
+        ray_rgb = torch.clamp(linear_to_srgb(colors[0]), min=0.0, max=1.0)
+        return {
+            "ray_rgb": ray_rgb,
+            "gradient_error": tmp.get("gradient_error", torch.zeros(1, device=dev)),
+            "acc": torch.ones(1, device=dev),
+            "normal": normals_out, "specular_color": spec_color_out, "specular_light": spec_light_out,
+            "specular_ref": spec_ref_out,
+            "std": tmp.get("std", torch.zeros(1, device=dev)),
+        }
+
+    # ------------------------------------------------------------------ ZT:1442-1466
+    def render(self, rays_o, rays_d, near=None, far=None, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,
+               is_train=True, step=None, is_nerf=False):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and is_train:
+            raise NotImplementedError("Stage2Renderer: the backward through the refraction bounce is not built yet; "
+                                      "render under torch.no_grad() (forward parity with the reference is tested)")
+        prepared = self._prepare()
+        pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = \
+            self.ray_trace(rays_o, rays_d, prepared=prepared)
+        ret = self.render_core(rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
+                               human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train,
+                               is_nerf=is_nerf, prepared=prepared)
+        ret["tir_mask"] = tir_mask
+        return ret
+
+    def forward(self, data):
+        step = data["step"]
+        if "eval" in data or self.ray_source is None:
+            raise NotImplementedError("dataset ingest is outside the hot path: attach a ray source and call render()")
+        batch = self.ray_source(step, self.cfg["train_ray_num"])
+        rays_d = F.normalize(batch["rays_d"], dim=-1)
+        out = self.render(batch["rays_o"], rays_d, None, None, None, -1, self.get_anneal_val(step), is_train=True,
+                          step=step, is_nerf=self.is_nerf)
+        out["loss_rgb"] = self.compute_rgb_loss(out["ray_rgb"], batch["rgbs"])
+        return out

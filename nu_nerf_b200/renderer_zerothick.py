@@ -380,6 +380,9 @@ class NeROShapeRenderer(nn.Module):
         return out
 
 
+from .renderer_stage2 import Stage2Renderer  # noqa: E402  (ZT:868-2011)
+
 name2renderer = {
     "shape": NeROShapeRenderer,
+    "stage2": Stage2Renderer,
 }

@@ -142,13 +142,76 @@ def angle_weighted_vertex_normals(V, F):
     return (vn / vn.norm(dim=1, keepdim=True)).float()
 
 
+def load_mesh(path):
+    """Vertices [V,3] float64 and faces [F,3] int64 of a triangle mesh file: .npz (arrays `vertices`, `faces`) or .ply
+    (ascii / binary_little_endian, as written by trimesh for data/meshes/*_simplified.ply, extract_mesh_stage1.py:43-52)."""
+    if path.endswith(".npz"):
+        z = np.load(path)
+        return np.asarray(z["vertices"], np.float64), np.asarray(z["faces"], np.int64)
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt, elems, cur = None, [], None
+        while True:
+            ln = f.readline().decode("ascii", "replace").strip()
+            if ln == "end_header":
+                break
+            tok = ln.split()
+            if not tok:
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                cur = {"name": tok[1], "count": int(tok[2]), "props": []}
+                elems.append(cur)
+            elif tok[0] == "property":
+                cur["props"].append(tok[1:])
+        np_t = {"char": "i1", "uchar": "u1", "short": "i2", "ushort": "u2", "int": "i4", "uint": "u4", "float": "f4",
+                "double": "f8", "int8": "i1", "uint8": "u1", "int16": "i2", "uint16": "u2", "int32": "i4",
+                "uint32": "u4", "float32": "f4", "float64": "f8"}
+        V = Fc = None
+        for e in elems:
+            if fmt == "ascii":
+                rows = [f.readline().split() for _ in range(e["count"])]
+                if e["name"] == "vertex":
+                    names = [p[-1] for p in e["props"]]
+                    ix = [names.index(c) for c in ("x", "y", "z")]
+                    V = np.asarray([[float(r[i]) for i in ix] for r in rows], np.float64)
+                elif e["name"] == "face":
+                    Fc = np.asarray([[int(v) for v in r[1:4]] for r in rows], np.int64)
+            elif fmt == "binary_little_endian":
+                if e["name"] == "vertex":
+                    dt = np.dtype([(p[-1], "<" + np_t[p[0]]) for p in e["props"]])
+                    a = np.frombuffer(f.read(dt.itemsize * e["count"]), dtype=dt)
+                    V = np.stack([a["x"], a["y"], a["z"]], 1).astype(np.float64)
+                elif e["name"] == "face":
+                    lp = [p for p in e["props"] if p[0] == "list"][0]
+                    ct, it = "<" + np_t[lp[1]], "<" + np_t[lp[2]]
+                    if len(e["props"]) != 1:
+                        raise ValueError("PLY faces with extra properties are not supported")
+                    dt = np.dtype([("n", ct), ("v", it, (3,))])
+                    a = np.frombuffer(f.read(dt.itemsize * e["count"]), dtype=dt)
+                    if not (a["n"] == 3).all():
+                        raise ValueError("PLY: only triangle meshes are supported")
+                    Fc = a["v"].astype(np.int64)
+                else:
+                    raise ValueError(f"PLY: cannot skip binary element {e['name']}")
+            else:
+                raise ValueError(f"PLY format {fmt} not supported")
+        if V is None or Fc is None:
+            raise ValueError(f"{path}: vertex / face elements missing")
+        return V, Fc
+
+
 class Scene:
     """The subset of DiffRender.Scene used by Stage2Renderer.ray_trace: mesh upload, vertex normals and the
     hit query + re-intersection (`Dintersect`)."""
 
-    def __init__(self, vertices, faces, device="cuda"):
+    def __init__(self, vertices, faces=None, device="cuda"):
         self.device = device
         self.optix_mesh = optix_mesh()
+        if isinstance(vertices, str):           # Scene(mesh_path) as in DiffRender.py:319
+            vertices, faces = load_mesh(vertices)
         self.update_mesh(vertices, faces)
 
     def update_mesh(self, vertices, faces):

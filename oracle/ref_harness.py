@@ -159,3 +159,115 @@ def synthetic_uniforms(R, seed=2):
 def synthetic_targets(R, seed=3):
     g = torch.Generator().manual_seed(seed)
     return torch.rand(R, 3, generator=g)
+
+
+# ------------------------------------------------------------------------------------------------ stage 2
+def uv_sphere(radius=0.6, nu=48, nv=24):
+    """Closed UV sphere (the synthetic outer mesh): nu longitudes, nv latitude bands.
+    Returns float64 vertices [V,3] and int64 faces [F,3], counter-clockwise seen from outside."""
+    verts = [[0.0, 0.0, radius]]
+    for i in range(1, nv):
+        th = math.pi * i / nv
+        for j in range(nu):
+            ph = 2.0 * math.pi * j / nu
+            verts.append([radius * math.sin(th) * math.cos(ph), radius * math.sin(th) * math.sin(ph),
+                          radius * math.cos(th)])
+    verts.append([0.0, 0.0, -radius])
+    faces = []
+    ring = lambda i, j: 1 + (i - 1) * nu + (j % nu)
+    for j in range(nu):
+        faces.append([0, ring(1, j), ring(1, j + 1)])
+    for i in range(1, nv - 1):
+        for j in range(nu):
+            a, b, c, d = ring(i, j), ring(i, j + 1), ring(i + 1, j), ring(i + 1, j + 1)
+            faces.append([a, c, d])
+            faces.append([a, d, b])
+    last = len(verts) - 1
+    for j in range(nu):
+        faces.append([last, ring(nv - 1, j + 1), ring(nv - 1, j)])
+    return np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int64)
+
+
+def brute_force_closest_hit(V, Fc, o, d, chunk=256):
+    """Oracle definition of optix_mesh.intersect (SURVEY 8c shim 6): double-sided Moeller-Trumbore in fp32 in the
+    operation order of JIT_Dintersect, 0 < t < 1e16, u,v >= 0, u+v <= 1; closest hit, ties: min t then min face id.
+    Returns (hit float32 {0,1}, idx int32 with 10000000 on a miss)."""
+    tri = V[Fc.long()].float()
+    v0, e1, e2 = tri[:, 0], tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    N = o.shape[0]
+    hit = torch.zeros(N)
+    idx = torch.full((N,), 10000000, dtype=torch.int32)
+    for s in range(0, N, chunk):
+        oo, dd = o[s:s + chunk].float()[:, None, :], d[s:s + chunk].float()[:, None, :]
+        pvec = torch.cross(dd.expand(-1, e2.shape[0], -1), e2[None].expand(oo.shape[0], -1, -1), dim=-1)
+        det = (e1[None] * pvec).sum(-1)
+        inv = 1.0 / det
+        tvec = oo - v0[None]
+        u = (tvec * pvec).sum(-1) * inv
+        qvec = torch.cross(tvec, e1[None].expand(oo.shape[0], -1, -1), dim=-1)
+        v = (dd * qvec).sum(-1) * inv
+        t = (e2[None] * qvec).sum(-1) * inv
+        ok = (det != 0) & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 0) & (t < 1e16)
+        tt = torch.where(ok, t, torch.full_like(t, float("inf")))
+        tmin, _ = tt.min(dim=1)
+        first = (tt == tmin[:, None]) & ok
+        fid = torch.where(first, torch.arange(tt.shape[1])[None], torch.full_like(tt, 1 << 30, dtype=torch.long)).min(1)[0]
+        h = torch.isfinite(tmin)
+        hit[s:s + chunk] = h.float()
+        idx[s:s + chunk] = torch.where(h, fid, torch.full_like(fid, 10000000)).int()
+    return hit, idx
+
+
+def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tmp"):
+    """Stage2Renderer(cfg, training=False) of renderer_zerothick with configs/stage2/nerf/spherepot.yaml, a stage-1
+    checkpoint made from a seeded random-init NeROShapeRenderer, and the in-memory mesh (shim 5: Scene built from V, F
+    with the reference's own corner-angle vertex normals; curvature zero -- unused by the zero-thickness path)."""
+    install()
+    net1, _ = load_stage1(seed=stage1_seed, fg_lut=fg_lut)
+    ckpt = os.path.join(tmp_dir, "nunerf_stage1_ckpt.pth")
+    torch.save({"network_state_dict": net1.state_dict(), "step": 0}, ckpt)
+    with in_ref_dir():
+        from utils.base_utils import load_cfg
+        import network.DiffRender as DR
+        import network.renderer_zerothick as ZT
+
+        class ShimOptix:
+            def update_mesh(self, F_, V_):
+                self.F, self.V = F_.long(), V_.float()
+
+            def update_vert(self, V_):
+                self.V = V_.float()
+
+            def intersect(self, ray):
+                return brute_force_closest_hit(self.V, self.F, ray[:, :3], ray[:, 3:])
+
+        class ShimScene(DR.Scene):
+            def __init__(self, mesh_path, cuda_device=0):
+                self.optix_mesh = ShimOptix()
+                self.vertices = torch.tensor(mesh_V, dtype=torch.float64)
+                self.faces = torch.tensor(mesh_F, dtype=torch.long)
+                self.triangles = self.vertices[self.faces]
+                self.optix_mesh.update_mesh(self.faces.to(torch.int32), self.vertices.to(torch.float32))
+                # init_VN (DiffRender.py:342-359) with the reference's JIT_corner_angles; curvature unused (ZT)
+                corner_angles, face_N = DR.JIT_corner_angles(self.triangles)
+                row = self.faces.view(-1)
+                col = torch.arange(len(self.faces)).unsqueeze(1).expand(-1, 3).reshape(-1)
+                M = torch.sparse_coo_tensor(torch.stack((row, col)), corner_angles.detach(),
+                                            (len(self.vertices), len(self.faces)))
+                vert_N = torch.sparse.mm(M, face_N)
+                self.normals = vert_N / vert_N.norm(dim=1, p=2, keepdim=True)
+                self.gaussian_curvatures = torch.zeros(len(self.vertices), 1, dtype=torch.float64)
+
+        DR.device = "cpu"            # module-level placement constant of DiffRender.py:16 (shim 3)
+        ZT.Scene = ShimScene
+        cfg = load_cfg("configs/stage2/nerf/spherepot.yaml")
+        cfg["stage1_ckpt_dir"] = ckpt
+        cfg["stage1_cfg_dir"] = "configs/shape/nerf/spherepot.yaml"
+        cfg["stage1_mesh_dir"] = "<in-memory>"
+        torch.manual_seed(seed)
+        net = ZT.Stage2Renderer(cfg, training=False)
+    if fg_lut is not None:
+        lut = torch.as_tensor(fg_lut).reshape(1, 256, 256, 2)
+        net.stage1_network.color_network.FG_LUT.copy_(lut)
+        net.color_network_inner.FG_LUT.copy_(lut)
+    return net, cfg

@@ -1,0 +1,77 @@
+"""Generates tests/golden/stage2_*.npz by running the UNMODIFIED reference Stage2Renderer (zero-thickness,
+/root/reference/network/renderer_zerothick.py:868-2011) on CPU through oracle/ref_harness.py.
+Run in the build container only:  python tests/golden/make_golden_stage2.py
+
+  stage2_init.npz   per-tensor fingerprints of the reference Stage2Renderer state_dict (seed 5, stage-1 checkpoint from
+                    seed 0): the product must reproduce the reference initialisation exactly.
+  stage2_R64.npz    SURVEY 8(d) config-4 style case on 64 rays: outer mesh = UV sphere r 0.6 (48 x 24, 2208
+                    triangles), random-init nested inner field; ray_trace intermediates per bounce (hit masks, hit
+                    triangle ids from the brute-force oracle, refracted directions, IoR ratios, mesh normals, TIR mask,
+                    every sampled path point) and the outputs dict in train and eval mode.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_harness as rh  # noqa: E402
+from nu_nerf_b200.fg_lut import make_fg_lut  # noqa: E402
+from make_golden import fingerprint  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+MESH = dict(radius=0.6, nu=48, nv=24)
+
+
+def main():
+    V, Fc = rh.uv_sphere(**MESH)
+    net, cfg = rh.load_stage2(V, Fc, fg_lut=make_fg_lut())
+    sd = net.state_dict()
+    np.savez_compressed(os.path.join(OUT, "stage2_init.npz"),
+                        **{k: fingerprint(v) for k, v in sd.items() if not k.endswith("FG_LUT")})
+    R = 64
+    o, d = rh.synthetic_rays(R)
+    res = {"o": o.numpy(), "d": d.numpy(), "mesh_radius": np.array(MESH["radius"]), "mesh_nu": np.array(MESH["nu"]),
+           "mesh_nv": np.array(MESH["nv"]), "step": np.array(10000), "cos_anneal": np.array(0.2)}
+    # hit triangle ids per bounce (the oracle's closest-hit rule), recorded from the shimmed optix_mesh.intersect
+    hits = []
+    orig = net.scene.optix_mesh.intersect
+
+    def rec(ray):
+        h, i = orig(ray)
+        hits.append((ray.clone(), h.clone(), i.clone()))
+        return h, i
+    net.scene.optix_mesh.intersect = rec
+    with torch.no_grad():
+        pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = net.ray_trace(o, d)
+    n_seg = len(pathes)
+    res["n_segments"] = np.array(n_seg)
+    for k in range(n_seg):
+        res[f"path_{k}"] = pathes[k].numpy()
+        res[f"converge_{k}"] = converges[k].numpy()
+        res[f"bkgr_{k}"] = infinity_bkgr[k].numpy()
+        res[f"dir_{k}"] = directions[k].numpy()
+        res[f"trace_ray_{k}"] = hits[k][0].numpy()
+        res[f"trace_hit_{k}"] = hits[k][1].numpy()
+        res[f"trace_tri_{k}"] = hits[k][2].numpy()
+    res[f"dir_{n_seg}"] = directions[n_seg].numpy() if len(directions) > n_seg else np.zeros((0, 3), np.float32)
+    for k in range(len(ior_ratios)):
+        res[f"ior_{k}"] = ior_ratios[k].numpy()
+        res[f"nmesh_{k}"] = gradient_mesh[k].numpy()
+    res["tir_mask"] = tir_mask.numpy()
+    with torch.no_grad():
+        for mode, is_train in (("train", True), ("eval", False)):
+            out = net.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
+                                  cos_anneal_ratio=0.2, step=10000, is_train=is_train, is_nerf=True)
+            for kk, v in out.items():
+                res[f"{mode}_{kk}"] = v.detach().float().numpy()
+    np.savez_compressed(os.path.join(OUT, "stage2_R64.npz"), **res)
+    for f in ("stage2_init.npz", "stage2_R64.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+    print({k: (v.shape, float(np.mean(v))) for k, v in res.items() if k.startswith(("train_", "eval_", "converge", "tir"))})
+
+
+if __name__ == "__main__":
+    main()

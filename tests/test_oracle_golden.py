@@ -130,3 +130,50 @@ def test_c_oracle_composite_and_hit(oracle_c):
     hit = np.zeros(3, np.float32); ti = np.zeros(3, np.int32); t = np.zeros(3, np.float32); uv = np.zeros((3, 2), np.float32)
     oracle_c.oracle_closest_hit(np_ptr(tri), 1, np_ptr(o), np_ptr(d), 3, ctypes.c_float(1e16), np_ptr(hit), np_ptr(ti), np_ptr(t), np_ptr(uv))
     assert hit.tolist() == [1.0, 0.0, 0.0] and ti.tolist() == [0, 10000000, 10000000] and abs(t[0] - 1.0) < 1e-7
+
+
+def test_stage2_initialisation_is_bit_identical_to_the_reference():
+    """Stage2Renderer (ZT:919-975): same construction order => same RNG consumption => identical parameters, and the
+    same state_dict key set (including the stage-1 network registered twice, as in the reference)."""
+    from conftest import make_stage2
+    net = make_stage2()
+    sd = net.state_dict()
+    G = np.load(os.path.join(GOLDEN, "stage2_init.npz"))
+    assert len(G.files) == 571
+    for k in G.files:
+        assert k in sd, f"missing parameter {k}"
+        assert np.array_equal(_fp(sd[k]), G[k]), k
+    extra = sorted(k for k in set(sd) - set(G.files) if not k.endswith("FG_LUT"))
+    assert extra == [], extra
+
+
+def test_uv_sphere_and_ply_loader(tmp_path):
+    from conftest import uv_sphere
+    from nu_nerf_b200.tracer import load_mesh
+    V, Fc = uv_sphere(0.6, 12, 6)
+    assert V.shape == (62, 3) and Fc.shape == (120, 3)
+    # outward orientation: face normal . centroid > 0
+    tri = V[Fc]
+    n = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    assert (np.einsum("ij,ij->i", n, tri.mean(1)) > 0).all()
+    # ascii and binary PLY round trips
+    p1 = tmp_path / "a.ply"
+    with open(p1, "w") as f:
+        f.write(f"ply\nformat ascii 1.0\nelement vertex {len(V)}\nproperty float x\nproperty float y\nproperty float z\n"
+                f"element face {len(Fc)}\nproperty list uchar int vertex_indices\nend_header\n")
+        for v in V:
+            f.write("%.9g %.9g %.9g\n" % tuple(v))
+        for t in Fc:
+            f.write("3 %d %d %d\n" % tuple(t))
+    V1, F1 = load_mesh(str(p1))
+    assert np.allclose(V1, V, atol=1e-7) and np.array_equal(F1, Fc)
+    p2 = tmp_path / "b.ply"
+    with open(p2, "wb") as f:
+        f.write((f"ply\nformat binary_little_endian 1.0\nelement vertex {len(V)}\nproperty float x\nproperty float y\n"
+                 f"property float z\nelement face {len(Fc)}\nproperty list uchar int vertex_indices\nend_header\n").encode())
+        f.write(V.astype("<f4").tobytes())
+        rec = np.zeros(len(Fc), dtype=np.dtype([("n", "u1"), ("v", "<i4", (3,))]))
+        rec["n"], rec["v"] = 3, Fc
+        f.write(rec.tobytes())
+    V2, F2 = load_mesh(str(p2))
+    assert np.allclose(V2, V.astype(np.float32)) and np.array_equal(F2, Fc)
