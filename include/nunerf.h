@@ -70,6 +70,8 @@ typedef struct {
   const void* w[9]; int ldw[9];
   const float* bias[9];
   float* sdf; int ld_sdf;                    /* sdf[m * ld_sdf] */
+  void* timeline;                            /* NULL, or 512 int64 (device): clock64 stamps of CTA 0's second tile
+                                                (development aid, tools/chain_timeline.py) */
 } nunerf_sdf_infer_t;
 int nunerf_sdf_infer(const nunerf_sdf_infer_t* p, void* stream);
 

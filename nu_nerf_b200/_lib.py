@@ -35,7 +35,7 @@ class DwT(C.Structure):
 
 
 class SdfInferT(C.Structure):
-    _fields_ = [("pts", vp), ("M", ci), ("w", vp * 9), ("ldw", ci * 9), ("bias", vp * 9), ("sdf", vp), ("ld_sdf", ci)]
+    _fields_ = [("pts", vp), ("M", ci), ("w", vp * 9), ("ldw", ci * 9), ("bias", vp * 9), ("sdf", vp), ("ld_sdf", ci), ("timeline", vp)]
 
 
 class SdfAlphaT(C.Structure):

@@ -55,13 +55,19 @@ struct ChainParams {
   int in_release_layer;  // the input blocks may be refilled once this layer's MMAs have completed
   int w_stages;
   const float* pts;
+  int dbg_flags;         // timing experiments only (NUNERF_CHAIN_DEBUG): 1 = skip the TMEM load, 2 = skip the smem store
+  long long* dbg;        // optional timeline buffer (NUNERF_CHAIN_TIMELINE): [2][256] clock64 stamps of CTA 0
 };
 
 // Hot epilogue of a plain hidden layer (N = 256, bias + activation -> bf16 -> shared memory): 16 columns of one row.
 template <int ACT>
 __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict__ bias, uint8_t* dst, int j, uint32_t sw,
-                                         uint32_t* obits) {
+                                         uint32_t* obits, int dbg_flags) {
   uint32_t v[16];
+  if (dbg_flags & 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = taddr + i;
+  } else
   ptx::tmem_ld16(taddr, v);
   float4 b[4];
 #pragma unroll
@@ -90,6 +96,10 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
   uint32_t h[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+  if (dbg_flags & 2) {
+    if (h[0] == 0x12345678u && h[5] == 0x9abcdef0u) *obits = h[3];   // keep the math alive without the store
+    return;
+  }
   *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
 }
@@ -166,85 +176,106 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
+    // The WHOLE warp runs this control flow (every value below is warp-uniform, so ptxas keeps descriptors and
+    // counters in uniform registers and the per-MMA instruction count stays small: this warp shares its scheduler
+    // with four busy epilogue warps); only the MMA / commit / TMA-store instructions are issued by lane 0.
+    {
+      const bool leader = lane == 0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       long long g = 0;             // global layer counter: accumulator g & 1, x_ready phase g
       bool stores_pending = false;
+      // descriptor templates: K-major, 128B swizzle, 8-row groups 1024 B apart (address field filled per k-step)
+      const uint64_t desc_hi = ptx::smem_desc(0, 16, 1024);
+      const uint32_t sx_base = ptx::smem_u32(sX), sw_base = ptx::smem_u32(sW);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         for (int l = 0; l < p.n_layers; ++l, ++g) {
           const ChainLayer& L = p.layer[l];
           const uint32_t idesc = ptx::idesc_bf16(128, L.N, 0, 0);
           const uint32_t d_tmem = tmem_base + (uint32_t)((g & 1) * 256);
           const uint32_t xpar = (uint32_t)((g - 1) & 1);
-          const bool prev_store = l > 0 && p.layer[l - 1].store_chunks > 0;
-          bool waited[4] = {false, false, false, false};
+          const int prev_store = l > 0 ? p.layer[l - 1].store_chunks : 0;
+          uint32_t waited = 0;     // bit c: x_ready[c] of the previous layer already observed
           if (l == 0) {
             // in-order rule: every x_ready phase is observed, also the previous tile's last layer (see header)
-            if (g > 0)
-              for (int c = 0; c < 4; ++c) { ptx::mbar_wait_parked(&x_ready[c], xpar); waited[c] = true; }
-            ptx::mbar_wait_parked(in_full, (uint32_t)(it & 1));
+            if (g > 0) {
+              for (int c = 0; c < 4; ++c) ptx::mbar_wait(&x_ready[c], xpar);
+              waited = 0xf;
+            }
+            ptx::mbar_wait(in_full, (uint32_t)(it & 1));
           }
           ptx::tc_fence_after();
           uint32_t accum = 0;
           for (int kb = 0; kb < L.nkb; ++kb) {
             const int blk = L.kb0 + kb;
-            if (blk < 4 && !waited[blk]) {
-              ptx::mbar_wait_parked(&x_ready[blk], xpar);
-              waited[blk] = true;
+            if (blk < 4 && !((waited >> blk) & 1u)) {
+              ptx::mbar_wait(&x_ready[blk], xpar);
+              if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 4 + blk) * 2] = clock64();
+              waited |= 1u << blk;
               ptx::tc_fence_after();
-              if (prev_store && blk < p.layer[l - 1].store_chunks) {
-                ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)blk * CH_BLOCK_BYTES, blk * 64, tile * 128);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              if (blk < prev_store) {
+                if (leader) {
+                  ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)blk * CH_BLOCK_BYTES, blk * 64, tile * 128);
+                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
                 stores_pending = true;
               }
             }
-            ptx::mbar_wait_parked(&w_full[stage], phase);
+            ptx::mbar_wait(&w_full[stage], phase);
             ptx::tc_fence_after();
-            const uint32_t a_addr = ptx::smem_u32(sX + (size_t)blk * CH_BLOCK_BYTES);
-            const uint32_t b_addr = ptx::smem_u32(sW + (size_t)stage * CH_WSTAGE_BYTES);
+            const uint64_t ad0 = desc_hi | (uint64_t)(((sx_base + (uint32_t)blk * CH_BLOCK_BYTES) >> 4) & 0x3fff);
+            const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * CH_WSTAGE_BYTES) >> 4) & 0x3fff);
+            if (leader) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              uint64_t ad = ptx::smem_desc(a_addr + k * 32, 16, 1024);
-              uint64_t bd = ptx::smem_desc(b_addr + k * 32, 16, 1024);
-              ptx::umma_bf16(d_tmem, ad, bd, idesc, accum);
-              accum = 1;
+              for (int k = 0; k < 4; ++k) {        // +32 bytes per K = 16 step: +2 in the (address >> 4) field
+                ptx::umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, accum | (uint32_t)k);
+              }
+              ptx::tc_commit(&w_empty[stage]);
             }
-            ptx::tc_commit(&w_empty[stage]);
+            accum = 1;
+            __syncwarp();
+            if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l < 12 && blk < 4) p.dbg[(l * 4 + blk) * 2 + 1] = clock64();
             if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
           }
           // chunks this layer did not read still have to be observed (in-order rule) and, if asked, stored
           if (g > 0)
             for (int c = 0; c < 4; ++c)
-              if (!waited[c]) {
-                ptx::mbar_wait_parked(&x_ready[c], xpar);
-                if (prev_store && c < p.layer[l - 1].store_chunks) {
-                  ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              if (!((waited >> c) & 1u)) {
+                ptx::mbar_wait(&x_ready[c], xpar);
+                if (c < prev_store) {
+                  if (leader) {
+                    ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                  }
                   stores_pending = true;
                 }
               }
-          if (p.in_mode == 0 && l == p.in_release_layer) ptx::tc_commit(in_empty);
-          // the epilogue of this layer overwrites the X blocks: outstanding TMA stores must have read them
-          if (stores_pending) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); stores_pending = false; }
-          ptx::tc_commit(&t_full[g & 1]);
+          if (leader) {
+            if (p.in_mode == 0 && l == p.in_release_layer) ptx::tc_commit(in_empty);
+            // the epilogue of this layer overwrites the X blocks: outstanding TMA stores must have read them
+            if (stores_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            ptx::tc_commit(&t_full[g & 1]);
+          }
+          stores_pending = false;
+          __syncwarp();
         }
         // a stored last layer: wait for its chunks and store them before the next tile starts
-        const ChainLayer& LL = p.layer[p.n_layers - 1];
-        if (LL.store_chunks > 0) {
+        const int last_store = p.layer[p.n_layers - 1].store_chunks;
+        if (last_store > 0) {
           const uint32_t xpar = (uint32_t)((g - 1) & 1);
           for (int c = 0; c < 4; ++c) {
-            ptx::mbar_wait_parked(&x_ready[c], xpar);
-            if (c < LL.store_chunks) {
+            ptx::mbar_wait(&x_ready[c], xpar);
+            if (c < last_store && leader) {
               ch_tma_store_2d(&p.out_map[p.n_layers - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
           }
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
         }
       }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else {
     // ================================================================ epilogue warps
@@ -295,25 +326,29 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
         const int acc = (int)(g & 1);
         // one parked waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier (no spin loops competing
         // for issue slots with the warps that still work)
-        if (ew == 0 && lane == 0) ptx::mbar_wait_parked(&t_full[acc], (uint32_t)(g >> 1) & 1);
+        if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[acc], (uint32_t)(g >> 1) & 1);
         asm volatile("bar.sync 1, 512;" ::: "memory");
         ptx::tc_fence_after();
+        if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && (ew == 0 || ew == 15))
+          p.dbg[256 + (ew ? 128 : 0) + l * 8] = clock64();
         for (int c = 0; c < 4; ++c) {
           const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
           if (L.hot) {
             uint32_t ob = 0;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0);
             uint8_t* dst = sX + (size_t)c * CH_BLOCK_BYTES + row_off;
-            if (L.act == 2) ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob);
+            if (L.act == 2) ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
             else {
-              ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob);
+              ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
               if (L.mask_out && row_ok)
                 *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
             }
-            ptx::fence_proxy_async();
+            if (!(p.dbg_flags & 4)) ptx::fence_proxy_async();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&x_ready[c]);
+            if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && (ew == 0 || ew == 15))
+              p.dbg[256 + (ew ? 128 : 0) + l * 8 + 1 + c] = clock64();
             continue;
           }
           const bool in_acc = c0 < L.N;       // columns the MMA produced
@@ -450,7 +485,11 @@ extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
     L.bias = a->bias[l];
     L.hot = (l < 8 && l != 3) ? 1 : 0;
   }
+  if (env_int("NUNERF_CHAIN_DEBUG_RELU", 0))           // timing experiment only: ReLU epilogue instead of Softplus
+    for (int l = 0; l < 8; ++l) P.layer[l].act = 1;
   P.layer[3].n_real = 217; P.layer[3].cat_pe = 1;      // x <- cat([x, PE]) / sqrt(2) (the scale lives in lin4's weights)
   P.layer[8].n_real = 16; P.layer[8].out32 = a->sdf; P.layer[8].ldo32 = a->ld_sdf; P.layer[8].n32 = 1;
+  P.dbg = (long long*)a->timeline;
+  P.dbg_flags = env_int("NUNERF_CHAIN_DEBUG", 0);
   return chain_launch(P, stream);
 }

@@ -102,12 +102,13 @@ class NerfW:
 
 
 # =============================================================================================== SDF network
-def sdf_infer_fused(w: SdfWeights, pts):
+def sdf_infer_fused(w: SdfWeights, pts, timeline=None):
     """sdf(x) in ONE launch (csrc/chain.cu): PE + 9 layers with the activations resident on the SM (bf16 mode)."""
     M, dev = pts.shape[0], pts.device
     out = _f(M, dev=dev)
     a = _lib.SdfInferT()
     a.pts, a.M, a.sdf, a.ld_sdf = pts.data_ptr(), M, out.data_ptr(), 1
+    a.timeline = ptr(timeline)
     lays = [w.L[l] for l in range(8)] + [w.sdf_head]
     for l, d in enumerate(lays):
         a.w[l], a.ldw[l], a.bias[l] = d.Wk.ptr, d.Wk.ld, d.b.data_ptr()

@@ -1,0 +1,61 @@
+"""Config 4 of BASELINE.json: stage-2 nested refraction on a ~100k-triangle synthetic outer mesh (UV sphere r 0.6,
+224 x 224 -> 99 904 triangles) + random-init nested inner field.  Reports trace-only Mrays/s (BVH closest hit +
+re-intersection, 32 B/ray/bounce algorithmic) and the full forward rays/s (ray_trace + render_core, bf16 mode)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from conftest import make_stage2, uv_sphere  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    R = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    V, Fc = uv_sphere(0.6, 224, 224)
+    net = make_stage2("bf16", mesh=(V, Fc)).cuda()
+    g = torch.Generator().manual_seed(1)
+    o = 3.0 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(R, 3, generator=g), dim=-1)
+    o, d = o.cuda(), d.cuda()
+    net._prepare()
+    bvh = net.scene.optix_mesh.bvh
+    # trace-only: many rays so that the kernel is not launch bound
+    Rt = 1 << 20
+    ot = 3.0 * torch.nn.functional.normalize(torch.randn(Rt, 3, device="cuda"), dim=-1)
+    dt = torch.nn.functional.normalize(-ot + 0.3 * torch.randn(Rt, 3, device="cuda"), dim=-1)
+    ms_trace = timeit(lambda: bvh.trace(ot, dt))
+    ms_di = timeit(lambda: net.scene.Dintersect(ot, dt))
+    hit, _ = bvh.trace(ot, dt)
+    with torch.no_grad():
+        ms_full = timeit(lambda: net.render(o, d, None, None, None, -1, 0.2, is_train=False, step=10000, is_nerf=True),
+                         iters=5, warm=2)
+        ms_rt = timeit(lambda: net.ray_trace(o, d), iters=5, warm=2)
+    print(json.dumps({
+        "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
+                    f"{R} rays, bf16 mode",
+        "trace_only": {"rays": Rt, "ms": ms_trace, "Mrays_per_s": Rt / ms_trace / 1e3,
+                       "algorithmic_GBs": 32.0 * Rt / ms_trace / 1e6, "hit_fraction": float(hit.mean())},
+        "trace_plus_reintersection": {"ms": ms_di, "Mrays_per_s": Rt / ms_di / 1e3},
+        "ray_trace_with_sampling": {"rays": R, "ms": ms_rt, "rays_per_s": R / ms_rt * 1e3},
+        "full_forward": {"rays": R, "ms": ms_full, "rays_per_s": R / ms_full * 1e3},
+    }))
+
+
+if __name__ == "__main__":
+    main()
