@@ -1,11 +1,12 @@
 // chain.cu -- fused multi-layer perceptron chains on tcgen05 tensor cores (sm_100a).
 //
-// One 128-row tile of points runs through a whole chain of dense layers without its activations ever leaving the
-// SM: the bf16 activation of layer l sits in shared memory (four 128x64 K-blocks, 128B swizzle) as the A operand of
-// layer l+1, accumulators are double-buffered in TMEM (2 x 256 fp32 columns), and only the weights stream in
-// (from L2, by TMA, through a ring of 32 KB K-blocks).  Layers overlap at K-block granularity: the 16 epilogue warps
-// all work on the same 64-column chunk of the accumulator, publish it (mbarrier x_ready[c]) and the MMA warp starts
-// the next layer's k-block c while chunks c+1.. are still being activated.
+// Two 128-row tiles of points per CTA run through a whole chain of dense layers without their activations ever
+// leaving the SM: the bf16 activation of layer l sits in shared memory (four 128x64 K-blocks per tile, 128B swizzle)
+// as the A operand of layer l+1, each tile owns one 256-column fp32 accumulator in TMEM, and only the weights stream
+// in (from L2, by TMA, through a ring of 32 KB K-blocks).  The two tiles run in PING-PONG: while the tensor core
+// computes layer l of one tile, the 16 epilogue warps activate layer l (or l-1) of the other one, so neither the
+// tensor pipe nor the epilogue warps wait for each other in steady state (measured timelines of the earlier
+// single-tile version, tools/chain_timeline.py: the MMA warp trails the epilogue by ~3000 cycles per layer).
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 0       TMA producer (weight K-blocks; the tile's input rows when they come from global memory)
@@ -21,10 +22,16 @@
 #include "ptx.cuh"
 #include "tma_host.cuh"
 
+// timeline stamps inside the MMA / producer loops cost issue slots on a starved warp: compile them in only on demand
+#ifndef NUNERF_CHAIN_TIMELINE_DETAIL
+#define NUNERF_CHAIN_TIMELINE_DETAIL 0
+#endif
+
 namespace nunerf {
 
 constexpr int CH_BLOCK_BYTES = 128 * 64 * 2;     // one activation K-block: 128 rows x 64 bf16
-constexpr int CH_WSTAGE_BYTES = 256 * 64 * 2;    // one weight K-block: <= 256 rows x 64 bf16
+constexpr int CH_WROWS = 256;                    // output rows per weight block (128 = half layers: measured slower)
+constexpr int CH_WSTAGE_BYTES = CH_WROWS * 64 * 2;   // one weight block: <= CH_WROWS output rows x 64 bf16 of K
 constexpr int CH_EPI_WARPS = 16;
 constexpr int CH_THREADS = 32 * (2 + CH_EPI_WARPS);
 constexpr int CH_MAXL = NUNERF_CHAIN_MAX_LAYERS;
@@ -32,11 +39,12 @@ constexpr int CH_MAXL = NUNERF_CHAIN_MAX_LAYERS;
 struct ChainLayer {
   int N;            // MMA N (multiple of 16, 16..256)
   int n_real;       // produced columns >= n_real are replaced (zeros, or the PE side block when cat_pe)
-  int kb0, nkb;     // input K-blocks [kb0, kb0 + nkb) (blocks 0..3 = activation, 4.. = tile input)
+  int kb0, nkb;     // input K-blocks [kb0, kb0 + nkb) of the tile's four activation blocks
   int act;          // 0 none, 1 relu, 2 softplus(beta = 100)
-  int cat_pe;       // columns [n_real, 256) <- columns [0, 256 - n_real) of input block 4 (SDF skip concat)
+  int cat_pe;       // columns [n_real, 256) <- PE-6 columns [0, 256 - n_real) of the point (SDF skip concat)
   int to_x;         // write the activation back to X blocks 0..3 (a next layer or a TMA store consumes it)
   int store_chunks; // > 0: TMA-store that many 64-column chunks of the activation through out_map
+  int w_box_bytes;  // bytes of one weight TMA box: 128 B x min(128, N) rows
   int hot;          // plain 256-wide hidden layer (bias + act -> X, optional mask_out): specialised epilogue
   const float* bias;
   uint8_t* mask_out; int ldmask_out;       // optional 1-bit (x > 0) mask, 32 bytes per row
@@ -50,9 +58,9 @@ struct ChainParams {
   CUtensorMap out_map[CH_MAXL];
   ChainLayer layer[CH_MAXL];
   int n_layers, M, num_tiles;
-  int in_mode;           // 0: X0 = rows of a bf16 matrix (TMA), 1: X0 = PE-6 of pts (computed in-kernel)
-  int in_blocks;         // K-blocks of the tile input
-  int in_release_layer;  // the input blocks may be refilled once this layer's MMAs have completed
+  int in_mode;           // 0: X0 = rows of a bf16 matrix (TMA, into the activation blocks), 1: X0 = PE-6 of pts
+  int in_blocks;         // K-blocks of the TMA input (1..4)
+  int in_release_layer;  // (unused)
   int w_stages;
   const float* pts;
   int dbg_flags;         // timing experiments only (NUNERF_CHAIN_DEBUG): 1 = skip the TMEM load, 2 = skip the smem store
@@ -111,22 +119,44 @@ __device__ __forceinline__ void ch_tma_store_2d(const CUtensorMap* m, const void
                : "memory");
 }
 
+// Block ids inside sX: tile t in {0,1} owns activation blocks t*4 + (0..3).  The tile input (TMA rows or the in-kernel
+// PE) is written into those same blocks: they are free between the last layer of one pair and the first of the next.
+__device__ __forceinline__ int ch_block(int t, int id) { return t * 4 + id; }
+
+// PE-6 value of column pc (0..38) of [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] (field.py:14-61), rounded to bf16
+// exactly as the tile-input writer does (the SDF skip concat re-creates these columns instead of keeping a copy in
+// shared memory: the 32 KB go to a third weight stage, which the L2 latency of the weight stream needs).
+__device__ __forceinline__ float ch_pe_col(const float* x, int pc) {
+  if (pc < 3) return __bfloat162float(__float2bfloat16_rn(x[pc]));
+  const int t = (pc - 3) / 3, c = (pc - 3) % 3;
+  float sn, co;
+  sincosf(x[c] * (float)(1 << (t >> 1)), &sn, &co);
+  return __bfloat162float(__float2bfloat16_rn((t & 1) ? co : sn));
+}
+
 __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int n_xblocks = 4 + p.in_blocks;
-  uint8_t* sX = smem;                                         // activation + input K-blocks
+  const int n_xblocks = 8;
+  uint8_t* sX = smem;                                         // activation K-blocks of both tiles
   uint8_t* sW = sX + (size_t)n_xblocks * CH_BLOCK_BYTES;      // weight ring
   uint64_t* bars = (uint64_t*)(sW + (size_t)p.w_stages * CH_WSTAGE_BYTES);
   uint64_t* w_full = bars;                  // [w_stages]
   uint64_t* w_empty = bars + 8;             // [w_stages]
-  uint64_t* x_ready = bars + 16;            // [4]  chunk c of the activation is in shared memory
-  uint64_t* t_full = bars + 20;             // [2]  accumulator complete
-  uint64_t* in_full = bars + 22;            // tile input is in shared memory
-  uint64_t* in_empty = bars + 23;           // tile input consumed
+  uint64_t* x_done = bars + 16;             // [2]  epilogue of tile t finished (X written, accumulator drained)
+  uint64_t* t_full = bars + 18;             // [2]  accumulator of tile t complete
+  uint64_t* in_full = bars + 20;            // [2]  tile input is in shared memory
+  uint64_t* in_empty = bars + 22;           // [2]  X blocks of tile t may be refilled (TMA input mode)
   uint32_t* tmem_ptr = (uint32_t*)(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_pairs = (p.num_tiles + 1) >> 1;
+  // Clusters: the CTAs of a cluster stream the SAME weight blocks, so each block is fetched from L2 once and multicast
+  // into every CTA's ring (weight traffic out of L2 is what bounds this kernel otherwise: 128 KB per tile-layer per
+  // SM).  Every CTA of a cluster therefore runs the same number of tile pairs (surplus pairs are all-masked).
+  const uint32_t cl_n = ptx::cluster_nctarank(), cl_rank = ptx::cluster_ctarank();
+  const uint16_t cl_mask = (uint16_t)((1u << cl_n) - 1u);
+  const int num_iters = (num_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int l = 0; l < p.n_layers; ++l) {
@@ -134,11 +164,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
       if (p.layer[l].store_chunks > 0) ptx::prefetch_tmap(&p.out_map[l]);
     }
     if (p.in_mode == 0) ptx::prefetch_tmap(&p.in_map);
-    for (int i = 0; i < p.w_stages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-    for (int i = 0; i < 4; ++i) ptx::mbar_init(&x_ready[i], CH_EPI_WARPS);
-    for (int i = 0; i < 2; ++i) ptx::mbar_init(&t_full[i], 1);
-    ptx::mbar_init(in_full, p.in_mode == 0 ? 1 : CH_EPI_WARPS);
-    ptx::mbar_init(in_empty, 1);
+    for (int i = 0; i < p.w_stages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], cl_n); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&x_done[i], CH_EPI_WARPS);
+      ptx::mbar_init(&t_full[i], 1);
+      ptx::mbar_init(&in_full[i], p.in_mode == 0 ? 1 : CH_EPI_WARPS);
+      ptx::mbar_init(&in_empty[i], 1);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -147,6 +179,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (cl_n > 1) ptx::cluster_sync();       // peers must not signal barriers that are not initialised yet
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -155,128 +188,130 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      uint32_t wblk = 0;         // running weight-block counter: block b is fetched by cluster rank b % cl_n
+      for (int it = 0; it < num_iters; ++it) {
+        const int pair = (int)blockIdx.x + it * (int)gridDim.x;
         if (p.in_mode == 0) {
-          ptx::mbar_wait_parked(in_empty, (uint32_t)(it & 1) ^ 1);
-          ptx::mbar_expect_tx(in_full, (uint32_t)(p.in_blocks * CH_BLOCK_BYTES));
-          for (int b = 0; b < p.in_blocks; ++b)
-            ptx::tma_load_2d(sX + (size_t)(4 + b) * CH_BLOCK_BYTES, &p.in_map, in_full, b * 64, tile * 128);
+          for (int t = 0; t < 2; ++t) {
+            ptx::mbar_wait_parked(&in_empty[t], (uint32_t)(it & 1) ^ 1);
+            ptx::mbar_expect_tx(&in_full[t], (uint32_t)(p.in_blocks * CH_BLOCK_BYTES));
+            for (int b = 0; b < p.in_blocks; ++b)      // rows beyond M (or a missing second tile) are zero filled
+              ptx::tma_load_2d(sX + (size_t)(t * 4 + b) * CH_BLOCK_BYTES, &p.in_map, &in_full[t], b * 64,
+                               (pair * 2 + t) * 128);
+          }
         }
         for (int l = 0; l < p.n_layers; ++l) {
-          const int N = p.layer[l].N, nkb = p.layer[l].nkb;
-          for (int kb = 0; kb < nkb; ++kb) {
-            ptx::mbar_wait_parked(&w_empty[stage], phase ^ 1);
-            ptx::mbar_expect_tx(&w_full[stage], (uint32_t)(N * 128));
-            ptx::tma_load_2d(sW + (size_t)stage * CH_WSTAGE_BYTES, &p.w_map[l], &w_full[stage], kb * 64, 0);
-            if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
-          }
+          const int nkb = p.layer[l].nkb, nh = (p.layer[l].N + CH_WROWS - 1) / CH_WROWS;
+          for (int t = 0; t < 2; ++t)
+           for (int h = 0; h < nh; ++h)
+            for (int kb = 0; kb < nkb; ++kb, ++wblk) {
+              // the stage is free once EVERY CTA of the cluster has consumed it (multicast commits, count cl_n)
+              ptx::mbar_wait_parked(&w_empty[stage], phase ^ 1);
+              if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[400 + (t * 4 + kb)] = clock64();
+              // box = 64 K-columns x min(128, N) rows; rows beyond N are zero filled but count as transferred bytes
+              ptx::mbar_expect_tx(&w_full[stage], (uint32_t)p.layer[l].w_box_bytes);
+              if (cl_n == 1)
+                ptx::tma_load_2d(sW + (size_t)stage * CH_WSTAGE_BYTES, &p.w_map[l], &w_full[stage], kb * 64, h * CH_WROWS);
+              else if (wblk % cl_n == cl_rank)
+                ptx::tma_load_2d_mc(sW + (size_t)stage * CH_WSTAGE_BYTES, &p.w_map[l], &w_full[stage], kb * 64,
+                                    h * CH_WROWS, cl_mask);
+              if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+            }
         }
       }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    // The WHOLE warp runs this control flow (every value below is warp-uniform, so ptxas keeps descriptors and
-    // counters in uniform registers and the per-MMA instruction count stays small: this warp shares its scheduler
-    // with four busy epilogue warps); only the MMA / commit / TMA-store instructions are issued by lane 0.
-    {
-      const bool leader = lane == 0;
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      long long g = 0;             // global layer counter: accumulator g & 1, x_ready phase g
-      bool stores_pending = false;
-      // descriptor templates: K-major, 128B swizzle, 8-row groups 1024 B apart (address field filled per k-step)
-      const uint64_t desc_hi = ptx::smem_desc(0, 16, 1024);
-      const uint32_t sx_base = ptx::smem_u32(sX), sw_base = ptx::smem_u32(sW);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        for (int l = 0; l < p.n_layers; ++l, ++g) {
-          const ChainLayer& L = p.layer[l];
-          const uint32_t idesc = ptx::idesc_bf16(128, L.N, 0, 0);
-          const uint32_t d_tmem = tmem_base + (uint32_t)((g & 1) * 256);
-          const uint32_t xpar = (uint32_t)((g - 1) & 1);
-          const int prev_store = l > 0 ? p.layer[l - 1].store_chunks : 0;
-          uint32_t waited = 0;     // bit c: x_ready[c] of the previous layer already observed
-          if (l == 0) {
-            // in-order rule: every x_ready phase is observed, also the previous tile's last layer (see header)
-            if (g > 0) {
-              for (int c = 0; c < 4; ++c) ptx::mbar_wait(&x_ready[c], xpar);
-              waited = 0xf;
-            }
-            ptx::mbar_wait(in_full, (uint32_t)(it & 1));
-          }
+    // The WHOLE warp runs this control flow (every value is warp-uniform: descriptors and counters live in uniform
+    // registers, a handful of instructions per MMA); only MMA / commit / TMA-store are issued by lane 0.
+    // Ping-pong: (layer l, tile 0), (layer l, tile 1), (layer l+1, tile 0), ... -- while the tensor core works on one
+    // tile the 16 epilogue warps activate the other one.
+    const bool leader = lane == 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    long long g = 0;             // layer counter per tile (both tiles advance together): x_done / t_full phase g
+    const uint64_t desc_hi = ptx::smem_desc(0, 16, 1024);
+    const uint32_t sx_base = ptx::smem_u32(sX), sw_base = ptx::smem_u32(sW);
+    for (it = 0; it < num_iters; ++it) {
+      const int pair = (int)blockIdx.x + it * (int)gridDim.x;
+      for (int l = 0; l < p.n_layers; ++l, ++g) {
+        const ChainLayer& L = p.layer[l];
+        const int prev_store = l > 0 ? p.layer[l - 1].store_chunks : 0;
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+          // the previous layer's epilogue of this tile has drained the accumulator and written the activation
+          if (g > 0) ptx::mbar_wait(&x_done[t], (uint32_t)((g - 1) & 1));
+          if (l == 0) ptx::mbar_wait(&in_full[t], (uint32_t)(it & 1));
           ptx::tc_fence_after();
-          uint32_t accum = 0;
-          for (int kb = 0; kb < L.nkb; ++kb) {
-            const int blk = L.kb0 + kb;
-            if (blk < 4 && !((waited >> blk) & 1u)) {
-              ptx::mbar_wait(&x_ready[blk], xpar);
-              if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 4 + blk) * 2] = clock64();
-              waited |= 1u << blk;
-              ptx::tc_fence_after();
-              if (blk < prev_store) {
-                if (leader) {
-                  ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)blk * CH_BLOCK_BYTES, blk * 64, tile * 128);
-                  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                stores_pending = true;
-              }
-            }
-            ptx::mbar_wait(&w_full[stage], phase);
-            ptx::tc_fence_after();
-            const uint64_t ad0 = desc_hi | (uint64_t)(((sx_base + (uint32_t)blk * CH_BLOCK_BYTES) >> 4) & 0x3fff);
-            const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * CH_WSTAGE_BYTES) >> 4) & 0x3fff);
+#if NUNERF_CHAIN_TIMELINE_DETAIL
+          if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[420 + t] = clock64();
+#endif
+          bool stores_pending = false;
+          if (prev_store > 0) {
             if (leader) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {        // +32 bytes per K = 16 step: +2 in the (address >> 4) field
-                ptx::umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, accum | (uint32_t)k);
-              }
-              ptx::tc_commit(&w_empty[stage]);
-            }
-            accum = 1;
-            __syncwarp();
-            if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l < 12 && blk < 4) p.dbg[(l * 4 + blk) * 2 + 1] = clock64();
-            if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
-          }
-          // chunks this layer did not read still have to be observed (in-order rule) and, if asked, stored
-          if (g > 0)
-            for (int c = 0; c < 4; ++c)
-              if (!((waited >> c) & 1u)) {
-                ptx::mbar_wait(&x_ready[c], xpar);
-                if (c < prev_store) {
-                  if (leader) {
-                    ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                  }
-                  stores_pending = true;
-                }
-              }
-          if (leader) {
-            if (p.in_mode == 0 && l == p.in_release_layer) ptx::tc_commit(in_empty);
-            // the epilogue of this layer overwrites the X blocks: outstanding TMA stores must have read them
-            if (stores_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            ptx::tc_commit(&t_full[g & 1]);
-          }
-          stores_pending = false;
-          __syncwarp();
-        }
-        // a stored last layer: wait for its chunks and store them before the next tile starts
-        const int last_store = p.layer[p.n_layers - 1].store_chunks;
-        if (last_store > 0) {
-          const uint32_t xpar = (uint32_t)((g - 1) & 1);
-          for (int c = 0; c < 4; ++c) {
-            ptx::mbar_wait(&x_ready[c], xpar);
-            if (c < last_store && leader) {
-              ch_tma_store_2d(&p.out_map[p.n_layers - 1], sX + (size_t)c * CH_BLOCK_BYTES, c * 64, tile * 128);
+              for (int c = 0; c < prev_store; ++c)
+                ch_tma_store_2d(&p.out_map[l - 1], sX + (size_t)(t * 4 + c) * CH_BLOCK_BYTES, c * 64, (pair * 2 + t) * 128);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            stores_pending = true;
           }
-          if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          const int nh = (L.N + CH_WROWS - 1) / CH_WROWS;
+          for (int h = 0; h < nh; ++h) {
+            const int n_h = L.N - h * CH_WROWS < CH_WROWS ? L.N - h * CH_WROWS : CH_WROWS;
+            const uint32_t idesc = ptx::idesc_bf16(128, n_h, 0, 0);
+            const uint32_t d_half = d_tmem + (uint32_t)(h * CH_WROWS);
+            for (int kb = 0; kb < L.nkb; ++kb) {
+              const int blk = ch_block(t, L.kb0 + kb);
+              ptx::mbar_wait(&w_full[stage], phase);
+              ptx::tc_fence_after();
+#if NUNERF_CHAIN_TIMELINE_DETAIL
+              if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5 && h == 0) p.dbg[430 + (t * 4 + kb) * 2] = clock64();
+#endif
+              const uint64_t ad0 = desc_hi | (uint64_t)(((sx_base + (uint32_t)blk * CH_BLOCK_BYTES) >> 4) & 0x3fff);
+              const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * CH_WSTAGE_BYTES) >> 4) & 0x3fff);
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)        // +32 bytes per K = 16 step: +2 in the (address >> 4) field
+                  ptx::umma_bf16(d_half, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                if (cl_n == 1) ptx::tc_commit(&w_empty[stage]);
+                else ptx::tc_commit_mc(&w_empty[stage], cl_mask);
+#if NUNERF_CHAIN_TIMELINE_DETAIL
+                if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5 && h == 0) p.dbg[430 + (t * 4 + kb) * 2 + 1] = clock64();
+#endif
+              }
+              if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          if (leader) {
+            // this layer's epilogue overwrites the X blocks: outstanding TMA stores must have read them
+            if (stores_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            ptx::tc_commit(&t_full[t]);
+            if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 2 + t) * 2] = clock64();
+          }
           __syncwarp();
         }
       }
-      if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // end of the pair: store a kept last layer, then hand the X blocks back to the producer (TMA input mode)
+      const int last_store = p.layer[p.n_layers - 1].store_chunks;
+      if (last_store > 0 || p.in_mode == 0) {
+        for (int t = 0; t < 2; ++t) {
+          ptx::mbar_wait(&x_done[t], (uint32_t)((g - 1) & 1));
+          if (leader) {
+            if (last_store > 0) {
+              for (int c = 0; c < last_store; ++c)
+                ch_tma_store_2d(&p.out_map[p.n_layers - 1], sX + (size_t)(t * 4 + c) * CH_BLOCK_BYTES, c * 64,
+                                (pair * 2 + t) * 128);
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            if (p.in_mode == 0) ptx::mbar_arrive(&in_empty[t]);
+          }
+          __syncwarp();
+        }
+      }
     }
+    if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ================================================================ epilogue warps
     const int ew = warp - 2;
@@ -285,159 +320,156 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     const int r = q * 32 + lane; // row inside the tile
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t sw = (uint32_t)(r & 7);
-    int it = 0;
     long long g = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-      const long long row = (long long)tile * 128 + r;
-      const bool row_ok = row < p.M;
+    for (int it = 0; it < num_iters; ++it) {
+      const int pair = (int)blockIdx.x + it * (int)gridDim.x;
       if (p.in_mode == 1) {
-        // ---- tile input: PE-6 of the point, 39 columns + zero padding to 64, into input block 4
-        if (j == 0) {
-          float x[3] = {0.f, 0.f, 0.f};
-          if (row_ok) { x[0] = p.pts[3 * row]; x[1] = p.pts[3 * row + 1]; x[2] = p.pts[3 * row + 2]; }
-          float pe[64];
+        // ---- tile inputs: PE-6 of the point, 39 columns + zero padding to 64, into the tile's input block
+        for (int t = 0; t < 2; ++t) {
+          if (j == 0) {
+            const long long row = ((long long)pair * 2 + t) * 128 + r;
+            float x[3] = {0.f, 0.f, 0.f};
+            if (row < p.M) { x[0] = p.pts[3 * row]; x[1] = p.pts[3 * row + 1]; x[2] = p.pts[3 * row + 2]; }
+            float pe[64];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) pe[c] = x[c];
+            for (int c = 0; c < 3; ++c) pe[c] = x[c];
 #pragma unroll
-          for (int k = 0; k < 6; ++k)
+            for (int k = 0; k < 6; ++k)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              float sn, co;
-              sincosf(x[c] * (float)(1 << k), &sn, &co);
-              pe[3 + 6 * k + c] = sn;
-              pe[6 + 6 * k + c] = co;
-            }
-#pragma unroll
-          for (int c = 39; c < 64; ++c) pe[c] = 0.f;
-          uint8_t* dst = sX + (size_t)4 * CH_BLOCK_BYTES + row_off;
-#pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            uint4 v = make_uint4(pack_bf16x2(pe[8 * ch], pe[8 * ch + 1]), pack_bf16x2(pe[8 * ch + 2], pe[8 * ch + 3]),
-                                 pack_bf16x2(pe[8 * ch + 4], pe[8 * ch + 5]), pack_bf16x2(pe[8 * ch + 6], pe[8 * ch + 7]));
-            *reinterpret_cast<uint4*>(dst + (((uint32_t)ch ^ sw) << 4)) = v;
-          }
-        }
-        ptx::fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(in_full);
-      }
-      for (int l = 0; l < p.n_layers; ++l, ++g) {
-        const ChainLayer& L = p.layer[l];
-        const int acc = (int)(g & 1);
-        // one parked waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier (no spin loops competing
-        // for issue slots with the warps that still work)
-        if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[acc], (uint32_t)(g >> 1) & 1);
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        ptx::tc_fence_after();
-        if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && (ew == 0 || ew == 15))
-          p.dbg[256 + (ew ? 128 : 0) + l * 8] = clock64();
-        for (int c = 0; c < 4; ++c) {
-          const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
-          if (L.hot) {
-            uint32_t ob = 0;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0);
-            uint8_t* dst = sX + (size_t)c * CH_BLOCK_BYTES + row_off;
-            if (L.act == 2) ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
-            else {
-              ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
-              if (L.mask_out && row_ok)
-                *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
-            }
-            if (!(p.dbg_flags & 4)) ptx::fence_proxy_async();
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&x_ready[c]);
-            if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && (ew == 0 || ew == 15))
-              p.dbg[256 + (ew ? 128 : 0) + l * 8 + 1 + c] = clock64();
-            continue;
-          }
-          const bool in_acc = c0 < L.N;       // columns the MMA produced
-          // columns that must be (re)written in shared memory: the produced ones, the concatenated PE columns,
-          // and the zero tail of a partially produced K-block (the next layer reads whole 64-column blocks)
-          const bool in_x = L.to_x && c0 < (L.cat_pe ? 256 : ((L.N + 63) & ~63));
-          if (in_acc || in_x) {
-            float x[16];
-            if (in_acc) {
-              uint32_t v[16];
-              ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
-              if (L.bias) {
-                const float4* b4 = reinterpret_cast<const float4*>(L.bias + c0);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  float4 b = __ldg(b4 + i);
-                  x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
-                }
+              for (int c = 0; c < 3; ++c) {
+                float sn, co;
+                sincosf(x[c] * (float)(1 << k), &sn, &co);
+                pe[3 + 6 * k + c] = sn;
+                pe[6 + 6 * k + c] = co;
               }
-              if (L.act == 1) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.0f);
-              } else if (L.act == 2) {
+            for (int c = 39; c < 64; ++c) pe[c] = 0.f;
+            uint8_t* dst = sX + (size_t)(t * 4) * CH_BLOCK_BYTES + row_off;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
-              }
-              if (L.mask_in) {
-                const uint32_t mb =
-                    *reinterpret_cast<const uint16_t*>(L.mask_in + (row_ok ? row : 0) * L.ldmask_in + (c0 >> 3));
-#pragma unroll
-                for (int i = 0; i < 16; ++i) x[i] = ((mb >> i) & 1u) ? x[i] : 0.0f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) x[i] = 0.0f;
-            }
-            if (c0 + 16 > L.n_real) {
-              if (L.cat_pe) {
-                const uint8_t* src = sX + (size_t)4 * CH_BLOCK_BYTES + row_off;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int col = c0 + i;
-                  if (col >= L.n_real) {
-                    const int pc = col - L.n_real;
-                    const __nv_bfloat16 b =
-                        *reinterpret_cast<const __nv_bfloat16*>(src + ((((uint32_t)pc >> 3) ^ sw) << 4) + (pc & 7) * 2);
-                    x[i] = __bfloat162float(b);
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (c0 + i >= L.n_real) x[i] = 0.0f;
-              }
-            }
-            if (in_acc && L.mask_out) {
-              uint32_t ob = 0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) ob |= (x[i] > 0.0f ? 1u : 0u) << i;
-              if (row_ok) *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
-            }
-            if (in_x) {
-              uint8_t* dst = sX + (size_t)c * CH_BLOCK_BYTES + row_off;
-              uint32_t h[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-              *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-              *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
-            }
-            if (in_acc && L.out32 && row_ok) {
-              float* o = L.out32 + row * L.ldo32 + c0;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (c0 + i < L.n32) o[i] = x[i];
+            for (int ch = 0; ch < 8; ++ch) {
+              uint4 v = make_uint4(pack_bf16x2(pe[8 * ch], pe[8 * ch + 1]), pack_bf16x2(pe[8 * ch + 2], pe[8 * ch + 3]),
+                                   pack_bf16x2(pe[8 * ch + 4], pe[8 * ch + 5]), pack_bf16x2(pe[8 * ch + 6], pe[8 * ch + 7]));
+              *reinterpret_cast<uint4*>(dst + (((uint32_t)ch ^ sw) << 4)) = v;
             }
           }
           ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&in_full[t]);
+        }
+      }
+      for (int l = 0; l < p.n_layers; ++l, ++g) {
+        const ChainLayer& L = p.layer[l];
+        for (int t = 0; t < 2; ++t) {
+          const long long row = ((long long)pair * 2 + t) * 128 + r;
+          const bool row_ok = row < p.M;
+          // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier
+          if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[t], (uint32_t)(g & 1));
+          asm volatile("bar.sync 1, 512;" ::: "memory");
+          ptx::tc_fence_after();
+          if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2] = clock64();
+          uint8_t* xt = sX + (size_t)(t * 4) * CH_BLOCK_BYTES;
+          for (int c = 0; c < 4; ++c) {
+            const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
+            if (L.hot) {
+              uint32_t ob = 0;
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c0);
+              uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
+              if (L.act == 2) ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
+              else {
+                ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
+                if (L.mask_out && row_ok)
+                  *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
+              }
+              if (p.dbg_flags & 8) __nanosleep(p.dbg_flags >> 4);   // experiment: yield issue slots to the MMA warp
+              continue;
+            }
+            const bool in_acc = c0 < L.N;       // columns the MMA produced
+            // columns that must be (re)written in shared memory: the produced ones, the concatenated PE columns,
+            // and the zero tail of a partially produced K-block (the next layer reads whole 64-column blocks)
+            const bool in_x = L.to_x && c0 < (L.cat_pe ? 256 : ((L.N + 63) & ~63));
+            if (in_acc || in_x) {
+              float x[16];
+              if (in_acc) {
+                uint32_t v[16];
+                ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c0), v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+                if (L.bias) {
+                  const float4* b4 = reinterpret_cast<const float4*>(L.bias + c0);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float4 b = __ldg(b4 + i);
+                    x[4 * i] += b.x; x[4 * i + 1] += b.y; x[4 * i + 2] += b.z; x[4 * i + 3] += b.w;
+                  }
+                }
+                if (L.act == 1) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) x[i] = fmaxf(x[i], 0.0f);
+                } else if (L.act == 2) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
+                }
+                if (L.mask_in) {
+                  const uint32_t mb =
+                      *reinterpret_cast<const uint16_t*>(L.mask_in + (row_ok ? row : 0) * L.ldmask_in + (c0 >> 3));
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) x[i] = ((mb >> i) & 1u) ? x[i] : 0.0f;
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = 0.0f;
+              }
+              if (c0 + 16 > L.n_real) {
+                if (L.cat_pe) {
+                  float px[3] = {0.f, 0.f, 0.f};
+                  if (row_ok) { px[0] = p.pts[3 * row]; px[1] = p.pts[3 * row + 1]; px[2] = p.pts[3 * row + 2]; }
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) {
+                    const int col = c0 + i;
+                    if (col >= L.n_real) x[i] = ch_pe_col(px, col - L.n_real);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (c0 + i >= L.n_real) x[i] = 0.0f;
+                }
+              }
+              if (in_acc && L.mask_out) {
+                uint32_t ob = 0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) ob |= (x[i] > 0.0f ? 1u : 0u) << i;
+                if (row_ok) *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
+              }
+              if (in_x) {
+                uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
+                uint32_t h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+                *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+              }
+              if (in_acc && L.out32 && row_ok) {
+                float* o = L.out32 + row * L.ldo32 + c0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c0 + i < L.n32) o[i] = x[i];
+              }
+            }
+          }
+          // publish: generic-proxy writes of this warp -> visible to the tensor core / TMA (async proxy)
+          ptx::fence_proxy_async();
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&x_ready[c]);
+          if (lane == 0) ptx::mbar_arrive(&x_done[t]);
+          if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2 + 1] = clock64();
         }
       }
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (cl_n > 1) ptx::cluster_sync();       // no CTA leaves while a peer may still multicast into its ring
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512u);
 }
 
@@ -449,16 +481,44 @@ static int chain_launch(ChainParams& P, cudaStream_t stream) {
     if (e != cudaSuccess) return fail("chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e), -2);
     configured = true;
   }
-  const size_t xbytes = (size_t)(4 + P.in_blocks) * CH_BLOCK_BYTES;
+  NUNERF_REQUIRE(P.in_mode == 1 || (P.in_blocks >= 1 && P.in_blocks <= 4), "chain: TMA input must be 1..4 K-blocks");
+  const size_t xbytes = (size_t)8 * CH_BLOCK_BYTES;
   const size_t fixed = 1024 + 512;
   int stages = (int)((227 * 1024 - fixed - xbytes) / CH_WSTAGE_BYTES);
-  if (stages > 4) stages = 4;
+  if (stages > 8) stages = 8;
   NUNERF_REQUIRE(stages >= 2, "chain: input too wide for shared memory");
+  for (int l = 0; l < P.n_layers; ++l) P.layer[l].w_box_bytes = 128 * (P.layer[l].N < CH_WROWS ? P.layer[l].N : CH_WROWS);
   P.w_stages = stages;
   P.num_tiles = cdiv(P.M, 128);
   const size_t smem = fixed + xbytes + (size_t)stages * CH_WSTAGE_BYTES;
-  const int grid = P.num_tiles < num_sms() ? P.num_tiles : num_sms();
-  mlp_chain_kernel<<<grid, CH_THREADS, smem, stream>>>(P);
+  const int num_pairs = (P.num_tiles + 1) / 2;
+  int cluster = env_int("NUNERF_CHAIN_CLUSTER", 1);
+  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
+  while (cluster > 1 && (num_sms() % cluster != 0 || num_pairs < cluster)) cluster >>= 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(CH_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  // persistent grid = the number of clusters that are co-resident (GPC sizes need not be multiples of the cluster)
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  if (max_clusters[cluster] == 0) {
+    cfg.gridDim = dim3(num_sms() / cluster * cluster);
+    int n = 0;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, mlp_chain_kernel, &cfg);
+    max_clusters[cluster] = (qe == cudaSuccess && n > 0) ? n : num_sms() / cluster;
+    (void)cudaGetLastError();
+  }
+  int grid = max_clusters[cluster] * cluster;
+  if (grid > num_sms()) grid = num_sms() / cluster * cluster;
+  const int need = (num_pairs + cluster - 1) / cluster * cluster;
+  if (grid > need) grid = need;
+  cfg.gridDim = dim3(grid);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_chain_kernel, P);
+  if (e != cudaSuccess) return fail("chain: cudaLaunchKernelEx: %s", cudaGetErrorString(e), -2);
   NUNERF_CHECK_LAUNCH("mlp_chain_kernel");
   return 0;
 }
@@ -477,10 +537,10 @@ extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
   P.n_layers = 9; P.M = a->M; P.in_mode = 1; P.in_blocks = 1; P.in_release_layer = 0; P.pts = a->pts;
   for (int l = 0; l < 9; ++l) {
     NUNERF_REQUIRE(a->w[l] && a->ldw[l] >= Ks[l] && a->ldw[l] % 8 == 0, "sdf_infer: bad weight operand");
-    if (int r = make_map(&P.w_map[l], a->w[l], Ns[l], Ks[l], a->ldw[l], 64, Ns[l])) return r;
+    if (int r = make_map(&P.w_map[l], a->w[l], Ns[l], Ks[l], a->ldw[l], 64, Ns[l] < CH_WROWS ? Ns[l] : CH_WROWS)) return r;
     ChainLayer& L = P.layer[l];
     L.N = Ns[l]; L.n_real = Ns[l];
-    L.kb0 = l == 0 ? 4 : 0; L.nkb = Ks[l] / 64;
+    L.kb0 = 0; L.nkb = Ks[l] / 64;
     L.act = l < 8 ? 2 : 0; L.to_x = l < 8 ? 1 : 0;
     L.bias = a->bias[l];
     L.hot = (l < 8 && l != 3) ? 1 : 0;

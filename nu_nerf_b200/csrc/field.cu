@@ -358,31 +358,53 @@ __global__ void shade_mix_bwd_kernel(nunerf_shade_mix_t p) {
 
 // ------------------------------------------------------------------------------------------- SDF-net glue
 // out[m,n] = w[n] * (1 - exp(-100 a[m,n]))          (gs_7 = w_sdf . s_7)
-__global__ void rowvec_mask_kernel(const float* __restrict__ w, const __nv_bfloat16* __restrict__ a, int lda, int a_lo,
-                                   long long M, int N, __nv_bfloat16* out, int ldo, int o_lo) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * N) return;
-  long long m = idx / N;
-  int n = (int)(idx % N);
-  float av = load_planes(a, m * lda + n, a_lo);
-  store_planes(out, m * ldo + n, o_lo, w[n] * (1.0f - __expf(-100.0f * av)));
+// 8 consecutive columns of bf16 planes <-> fp32 (16-byte accesses; callers guarantee 8-column alignment)
+__device__ __forceinline__ void load8_planes(const __nv_bfloat16* base, long long idx, int lo, float* v) {
+  const uint4 h = *reinterpret_cast<const uint4*>(base + idx);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[2 * j] = bf16lo_to_f(hw[j]); v[2 * j + 1] = bf16hi_to_f(hw[j]); }
+  if (lo) {
+    const uint4 l = *reinterpret_cast<const uint4*>(base + idx + lo);
+    const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { v[2 * j] += bf16lo_to_f(lw[j]); v[2 * j + 1] += bf16hi_to_f(lw[j]); }
+  }
 }
 
-// u4 fp32 [M,256] -> gs3 planes (cols < 217 masked by s_3, rest 0) and g_skip fp32 [M,39]
+// one thread per 8 columns
+__global__ void rowvec_mask_kernel(const float* __restrict__ w, const __nv_bfloat16* __restrict__ a, int lda, int a_lo,
+                                   long long M, int N, __nv_bfloat16* out, int ldo, int o_lo) {
+  const int groups = N >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * groups) return;
+  const long long m = idx / groups;
+  const int n = (int)(idx % groups) << 3;
+  float av[8], r[8];
+  load8_planes(a, m * lda + n, a_lo, av);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = w[n + j] * (1.0f - __expf(-100.0f * av[j]));
+  store8(out, m * ldo + n, o_lo, r);
+}
+// u4 [M,256] fp32 = d sdf / d (input of lin4): columns < 217 -> gs_3 = u . s_3 (planes), columns 217.. -> g_skip (the PE part)
 __global__ void sdf_skip_split_kernel(const float* __restrict__ u4, const __nv_bfloat16* __restrict__ a3, int lda,
                                       int a_lo, long long M, __nv_bfloat16* gs3, int ldg, int g_lo, float* g_skip) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * 256) return;
-  long long m = idx >> 8;
-  int n = (int)(idx & 255);
-  float u = u4[idx];
-  if (n < 217) {
-    float av = load_planes(a3, m * lda + n, a_lo);
-    store_planes(gs3, m * ldg + n, g_lo, u * (1.0f - __expf(-100.0f * av)));
-  } else {
-    store_planes(gs3, m * ldg + n, g_lo, 0.f);
-    g_skip[m * 39 + (n - 217)] = u;
+  if (idx >= M * 32) return;
+  const long long m = idx >> 5;
+  const int n = (int)(idx & 31) << 3;
+  const float4 u0 = *reinterpret_cast<const float4*>(u4 + m * 256 + n);
+  const float4 u1 = *reinterpret_cast<const float4*>(u4 + m * 256 + n + 4);
+  const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+  float av[8], r[8];
+  load8_planes(a3, m * lda + n, a_lo, av);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int col = n + j;
+    if (col < 217) r[j] = u[j] * (1.0f - __expf(-100.0f * av[j]));
+    else { r[j] = 0.f; g_skip[m * 39 + (col - 217)] = u[j]; }
   }
+  store8(gs3, m * ldg + n, g_lo, r);
 }
 
 // reverse-over-reverse glue of one softplus layer:
@@ -611,7 +633,8 @@ extern "C" int nunerf_shade_mix_bwd(const nunerf_shade_mix_t* p, void* stream) {
 extern "C" int nunerf_rowvec_mask(const float* w, const void* a, int lda, int a_lo, int M, int N, void* out, int ldo,
                                   int o_lo, void* stream) {
   NUNERF_REQUIRE(w && a && out && M > 0 && N > 0, "rowvec_mask: bad arguments");
-  rowvec_mask_kernel<<<G1((long long)M * N), 0, ST(stream)>>>(w, (const __nv_bfloat16*)a, lda, a_lo, M, N,
+  NUNERF_REQUIRE(((N | lda | a_lo | ldo | o_lo) & 7) == 0, "rowvec_mask: columns / pitches must be multiples of 8");
+  rowvec_mask_kernel<<<G1((long long)M * (N / 8)), 0, ST(stream)>>>(w, (const __nv_bfloat16*)a, lda, a_lo, M, N,
                                                              (__nv_bfloat16*)out, ldo, o_lo);
   NUNERF_CHECK_LAUNCH("rowvec_mask_kernel");
   return 0;
@@ -619,7 +642,8 @@ extern "C" int nunerf_rowvec_mask(const float* w, const void* a, int lda, int a_
 extern "C" int nunerf_sdf_skip_split(const float* u4, const void* a3, int lda, int a_lo, int M, void* gs3, int ldg,
                                      int g_lo, float* g_skip, void* stream) {
   NUNERF_REQUIRE(u4 && a3 && gs3 && g_skip && M > 0, "sdf_skip_split: bad arguments");
-  sdf_skip_split_kernel<<<G1((long long)M * 256), 0, ST(stream)>>>(u4, (const __nv_bfloat16*)a3, lda, a_lo, M,
+  NUNERF_REQUIRE(((lda | a_lo | ldg | g_lo) & 7) == 0, "sdf_skip_split: pitches must be multiples of 8");
+  sdf_skip_split_kernel<<<G1((long long)M * 32), 0, ST(stream)>>>(u4, (const __nv_bfloat16*)a3, lda, a_lo, M,
                                                                   (__nv_bfloat16*)gs3, ldg, g_lo, g_skip);
   NUNERF_CHECK_LAUNCH("sdf_skip_split_kernel");
   return 0;

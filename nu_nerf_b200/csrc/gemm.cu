@@ -238,9 +238,13 @@ dw_tc_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ C
         ptx::tmem_ld16(taddr + c0, v);
         ptx::tmem_ld_wait();
         if (n < p.N) {
+          // 16-byte vector reductions (REDG.ADD.F32x4): a quarter of the L2 atomic operations of scalar atomicAdd
           float* dst = p.dW + (long long)n * p.lddw + p.dw_col0 + c0;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          for (int j = 0; j < 16; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(v[j])),
+                         "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                         : "memory");
         }
       }
     }
@@ -315,6 +319,7 @@ extern "C" int nunerf_linear_dw(const nunerf_dw_t* a, void* stream_) {
   NUNERF_REQUIRE(a->M > 0 && a->N >= 1 && a->N <= 256, "dw: bad M/N");
   NUNERF_REQUIRE(a->K >= 64 && a->K % 64 == 0 && a->K <= 1024, "dw: K must be a multiple of 64");
   NUNERF_REQUIRE(a->ldz % 8 == 0 && a->ldx % 8 == 0, "dw: ld must be multiples of 8");
+  NUNERF_REQUIRE(a->lddw % 4 == 0 && ((uintptr_t)a->dW & 15) == 0, "dw: dW must be 16-byte aligned with a pitch % 4 == 0");
   if (a->impl == 1) {
     int chunks = 64;
     int rpb = cdiv(a->M, chunks);

@@ -22,10 +22,15 @@ for _ in range(3):
 torch.cuda.synchronize()
 t = tl.cpu().tolist()
 t0 = min(x for x in t if x > 0)
-print("layer: epilogue start (warp0 / warp15) | chunk publish times (warp 0) | MMA: saw chunk c / issued k-block c")
+rel = lambda v: v - t0 if v else -1
+print("layer/tile: MMA issued+committed at | epilogue start -> end   (cycles since the first stamp, second tile pair of CTA 0)")
 for l in range(9):
-    e0 = [t[256 + l * 8 + i] - t0 if t[256 + l * 8 + i] else -1 for i in range(5)]
-    e15 = [t[256 + 128 + l * 8 + i] - t0 if t[256 + 128 + l * 8 + i] else -1 for i in range(5)]
-    mm = [(t[(l * 4 + b) * 2] - t0 if t[(l * 4 + b) * 2] else -1, t[(l * 4 + b) * 2 + 1] - t0 if t[(l * 4 + b) * 2 + 1] else -1)
-          for b in range(4)]
-    print(f"L{l}: epi0 {e0}  epi15 {e15}  mma {mm}")
+    for tt in range(2):
+        i = (l * 2 + tt) * 2
+        print(f"L{l} tile{tt}: mma commit {rel(t[i]):7d} | epilogue {rel(t[256 + i]):7d} -> {rel(t[256 + i + 1]):7d}")
+
+print("layer 5 detail: producer saw w_empty (tile, kb) | MMA: x_done seen, per kb: w_full seen -> issued")
+for tt in range(2):
+    print(f" tile{tt}: x_done seen {rel(t[420 + tt])}")
+    for kb in range(4):
+        print(f"   kb{kb}: producer w_empty seen {rel(t[400 + tt * 4 + kb]):7d} | w_full seen {rel(t[430 + (tt * 4 + kb) * 2]):7d} -> issued {rel(t[430 + (tt * 4 + kb) * 2 + 1]):7d}")
