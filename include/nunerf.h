@@ -75,6 +75,32 @@ typedef struct {
 } nunerf_sdf_infer_t;
 int nunerf_sdf_infer(const nunerf_sdf_infer_t* p, void* stream);
 
+/* Generic fused chain of dense layers on ONE 128-row tile pair per SM (csrc/chain.cu): layer l computes
+ *   y = act(x_l W_l^T + bias) [. mask_in]   with x_0 = the bf16 input rows and x_{l+1} = y when `keep` (or `store`) is set;
+ * a layer with keep = store = 0 (a narrow head) leaves the activation in place, so the next layer still reads x_l.
+ * The activations never leave shared memory / TMEM unless `store` asks for a bf16 copy (needed by the weight-gradient
+ * GEMMs of the training step).  Replaces the per-layer evaluation of make_predictor MLPs (field.py:371-408: forward
+ * with ReLU masks kept, and the dX chain of their backward). bf16 single-plane operands only. */
+typedef struct {
+  const void* w; int ldw;                    /* K-major bf16 [N (padded to 16), K] */
+  int N, K;                                  /* N % 16 == 0, <= 256; K % 64 == 0, <= 256 */
+  int n_real;                                /* 0 = N; produced columns >= n_real are zeroed */
+  const float* bias;                         /* NULL or fp32 [N] */
+  int act;                                   /* 0 none, 1 relu, 2 softplus(beta = 100) */
+  unsigned char* mask_out; int ldmask_out;   /* optional 1-bit (y > 0) mask, N/8 bytes per row */
+  const unsigned char* mask_in; int ldmask_in; /* optional 1-bit multiplicative mask */
+  void* store; int ld_store;                 /* optional bf16 [M, pad64(N)] copy of y (TMA store) */
+  float* out32; int ldo32; int n32;          /* optional fp32 copy of the first n32 columns */
+  int keep;                                  /* y becomes the next layer's input */
+} nunerf_chain_layer_t;
+typedef struct {
+  const void* x; int ldx; int K0;            /* bf16 [M, K0], K0 in {64,128,192,256} */
+  int M, n_layers;
+  nunerf_chain_layer_t layer[NUNERF_CHAIN_MAX_LAYERS];
+  void* timeline;                            /* NULL, or 512 int64 (device) clock64 stamps (development aid) */
+} nunerf_mlp_chain_t;
+int nunerf_mlp_chain(const nunerf_mlp_chain_t* p, void* stream);
+
 /* out[n] += sum_m Z[m,n] (hi + lo) -- the bias gradient */
 int nunerf_colsum(const void* Z, int ldz, int z_lo_off, int M, int N, float* out, void* stream);
 /* fp32 [rows, cols] (ld_src) -> the block dst[row_off:+dst_rows, col_off:+dst_cols] of a bf16 plane matrix, zero

@@ -38,6 +38,16 @@ class SdfInferT(C.Structure):
     _fields_ = [("pts", vp), ("M", ci), ("w", vp * 9), ("ldw", ci * 9), ("bias", vp * 9), ("sdf", vp), ("ld_sdf", ci), ("timeline", vp)]
 
 
+class ChainLayerT(C.Structure):
+    _fields_ = [("w", vp), ("ldw", ci), ("N", ci), ("K", ci), ("n_real", ci), ("bias", vp), ("act", ci),
+                ("mask_out", vp), ("ldmask_out", ci), ("mask_in", vp), ("ldmask_in", ci), ("store", vp), ("ld_store", ci),
+                ("out32", vp), ("ldo32", ci), ("n32", ci), ("keep", ci)]
+
+
+class MlpChainT(C.Structure):
+    _fields_ = [("x", vp), ("ldx", ci), ("K0", ci), ("M", ci), ("n_layers", ci), ("layer", ChainLayerT * 10), ("timeline", vp)]
+
+
 class SdfAlphaT(C.Structure):
     _fields_ = [("M", ci), ("cos_anneal", cf), ("inv_s_dev", vp), ("sdf", vp), ("ld_sdf", ci), ("grad", vp),
                 ("dists", vp), ("dirs", vp), ("alpha", vp), ("grad_err", vp), ("d_alpha", vp), ("d_grad_err", vp),
@@ -82,6 +92,7 @@ _SIGS = {
     "nunerf_linear": [C.POINTER(LinearT), vp],
     "nunerf_linear_dw": [C.POINTER(DwT), vp],
     "nunerf_sdf_infer": [C.POINTER(SdfInferT), vp],
+    "nunerf_mlp_chain": [C.POINTER(MlpChainT), vp],
     "nunerf_colsum": [vp, ci, ci, ci, ci, vp, vp],
     "nunerf_to_planes": [vp, ci, ci, ci, ci, cf, vp, ci, ci, ci, ci, ci, ci, vp],
     "nunerf_from_planes": [vp, ci, ci, ci, ci, vp, ci, vp],

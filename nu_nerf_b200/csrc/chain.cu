@@ -45,7 +45,7 @@ struct ChainLayer {
   int to_x;         // write the activation back to X blocks 0..3 (a next layer or a TMA store consumes it)
   int store_chunks; // > 0: TMA-store that many 64-column chunks of the activation through out_map
   int w_box_bytes;  // bytes of one weight TMA box: 128 B x min(128, N) rows
-  int hot;          // plain 256-wide hidden layer (bias + act -> X, optional mask_out): specialised epilogue
+  int hot;          // plain 256-wide hidden layer with a specialised epilogue (ch_hot16 KIND 1..3), 0 = generic path
   const float* bias;
   uint8_t* mask_out; int ldmask_out;       // optional 1-bit (x > 0) mask, 32 bytes per row
   const uint8_t* mask_in; int ldmask_in;   // optional 1-bit multiplicative mask
@@ -67,39 +67,48 @@ struct ChainParams {
   long long* dbg;        // optional timeline buffer (NUNERF_CHAIN_TIMELINE): [2][256] clock64 stamps of CTA 0
 };
 
-// Hot epilogue of a plain hidden layer (N = 256, bias + activation -> bf16 -> shared memory): 16 columns of one row.
-template <int ACT>
+// Hot epilogue of a plain 256-wide hidden layer -> bf16 -> shared memory: 16 columns of one row.
+//   KIND 1: bias + Softplus(beta = 100)              (SDF network)
+//   KIND 2: bias + ReLU, emits the 16 (x > 0) bits    (predictor / NeRF++ forward)
+//   KIND 3: multiply by the 16 mask bits `mbits`      (ReLU backward: dZ_l = (dZ_{l+1} W_{l+1}) . [z_l > 0])
+template <int KIND>
 __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict__ bias, uint8_t* dst, int j, uint32_t sw,
-                                         uint32_t* obits, int dbg_flags) {
+                                         uint32_t* obits, uint32_t mbits, int dbg_flags) {
   uint32_t v[16];
   if (dbg_flags & 1) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = taddr + i;
   } else
   ptx::tmem_ld16(taddr, v);
-  float4 b[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
-  ptx::tmem_ld_wait();
   float x[16];
+  if (KIND == 3) {
+    ptx::tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    x[4 * i] = __uint_as_float(v[4 * i]) + b[i].x;
-    x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b[i].y;
-    x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b[i].z;
-    x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b[i].w;
-  }
-  if (ACT == 2) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
+    for (int i = 0; i < 16; ++i) x[i] = ((mbits >> i) & 1u) ? __uint_as_float(v[i]) : 0.0f;
   } else {
-    uint32_t ob = 0;
+    float4 b[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      ob |= (x[i] > 0.0f ? 1u : 0u) << i;
-      x[i] = fmaxf(x[i], 0.0f);
+    for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x[4 * i] = __uint_as_float(v[4 * i]) + b[i].x;
+      x[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + b[i].y;
+      x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b[i].z;
+      x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b[i].w;
     }
-    *obits = ob;
+    if (KIND == 1) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
+    } else {
+      uint32_t ob = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        ob |= (x[i] > 0.0f ? 1u : 0u) << i;
+        x[i] = fmaxf(x[i], 0.0f);
+      }
+      *obits = ob;
+    }
   }
   uint32_t h[8];
 #pragma unroll
@@ -362,6 +371,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
         for (int t = 0; t < 2; ++t) {
           const long long row = ((long long)pair * 2 + t) * 128 + r;
           const bool row_ok = row < p.M;
+          // ReLU-backward layers: this thread's 4 x 16 mask bits, fetched while the tensor core is still busy
+          unsigned long long hot_mask = 0ull;
+          if (L.hot == 3) {
+            const uint8_t* mrow = L.mask_in + (row_ok ? row : 0) * L.ldmask_in + 2 * j;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              hot_mask |= (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(mrow + 8 * c)) << (16 * c);
+            if (!row_ok) hot_mask = 0ull;
+          }
           // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier
           if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[t], (uint32_t)(g & 1));
           asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -374,11 +392,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               uint32_t ob = 0;
               const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c0);
               uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
-              if (L.act == 2) ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
-              else {
-                ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, p.dbg_flags);
+              if (L.hot == 1) ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
+              else if (L.hot == 2) {
+                ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
                 if (L.mask_out && row_ok)
                   *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
+              } else {
+                ch_hot16<3>(taddr, nullptr, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu,
+                            p.dbg_flags);
               }
               if (p.dbg_flags & 8) __nanosleep(p.dbg_flags >> 4);   // experiment: yield issue slots to the MMA warp
               continue;
@@ -451,9 +472,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               }
               if (in_acc && L.out32 && row_ok) {
                 float* o = L.out32 + row * L.ldo32 + c0;
+                if (c0 + 16 <= L.n32 && (L.ldo32 & 3) == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (c0 + i < L.n32) o[i] = x[i];
+                  for (int i = 0; i < 4; ++i)
+                    reinterpret_cast<float4*>(o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (c0 + i < L.n32) o[i] = x[i];
+                }
               }
             }
           }
@@ -543,13 +570,64 @@ extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
     L.kb0 = 0; L.nkb = Ks[l] / 64;
     L.act = l < 8 ? 2 : 0; L.to_x = l < 8 ? 1 : 0;
     L.bias = a->bias[l];
-    L.hot = (l < 8 && l != 3) ? 1 : 0;
+    L.hot = (l < 8 && l != 3) ? 1 : 0;             // KIND 1: bias + softplus
   }
   if (env_int("NUNERF_CHAIN_DEBUG_RELU", 0))           // timing experiment only: ReLU epilogue instead of Softplus
-    for (int l = 0; l < 8; ++l) P.layer[l].act = 1;
+    for (int l = 0; l < 8; ++l) { P.layer[l].act = 1; if (P.layer[l].hot) P.layer[l].hot = 2; }
   P.layer[3].n_real = 217; P.layer[3].cat_pe = 1;      // x <- cat([x, PE]) / sqrt(2) (the scale lives in lin4's weights)
   P.layer[8].n_real = 16; P.layer[8].out32 = a->sdf; P.layer[8].ldo32 = a->ld_sdf; P.layer[8].n32 = 1;
   P.dbg = (long long*)a->timeline;
   P.dbg_flags = env_int("NUNERF_CHAIN_DEBUG", 0);
+  return chain_launch(P, stream);
+}
+
+extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NUNERF_REQUIRE(a && a->x && a->M > 0, "mlp_chain: bad arguments");
+  NUNERF_REQUIRE(a->n_layers >= 1 && a->n_layers <= CH_MAXL, "mlp_chain: 1..NUNERF_CHAIN_MAX_LAYERS layers");
+  NUNERF_REQUIRE(a->K0 >= 64 && a->K0 % 64 == 0 && a->K0 <= 256 && a->ldx % 8 == 0 && a->ldx >= a->K0,
+                 "mlp_chain: input must be 64..256 columns (multiple of 64), pitch % 8 == 0");
+  ChainParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_layers = a->n_layers; P.M = a->M; P.in_mode = 0; P.in_blocks = a->K0 / 64;
+  if (int r = make_map(&P.in_map, a->x, a->M, a->K0, a->ldx, 64, 128)) return r;
+  int width = a->K0;                 // valid (written) columns of the activation blocks
+  for (int l = 0; l < a->n_layers; ++l) {
+    const nunerf_chain_layer_t& s = a->layer[l];
+    ChainLayer& L = P.layer[l];
+    NUNERF_REQUIRE(s.w && s.N >= 16 && s.N % 16 == 0 && s.N <= 256, "mlp_chain: N must be a multiple of 16, <= 256");
+    NUNERF_REQUIRE(s.K >= 64 && s.K % 64 == 0 && s.K <= width, "mlp_chain: K exceeds the activation produced so far");
+    NUNERF_REQUIRE(s.ldw % 8 == 0 && s.ldw >= s.K, "mlp_chain: bad weight pitch");
+    NUNERF_REQUIRE(s.act >= 0 && s.act <= 2, "mlp_chain: act must be 0 (none), 1 (relu) or 2 (softplus 100)");
+    if (int r = make_map(&P.w_map[l], s.w, s.N, s.K, s.ldw, 64, s.N < CH_WROWS ? s.N : CH_WROWS)) return r;
+    L.N = s.N; L.n_real = s.n_real > 0 ? s.n_real : s.N;
+    L.kb0 = 0; L.nkb = s.K / 64;
+    L.act = s.act; L.bias = s.bias;
+    L.mask_out = s.mask_out; L.ldmask_out = s.ldmask_out;
+    L.mask_in = s.mask_in; L.ldmask_in = s.ldmask_in;
+    L.out32 = s.out32; L.ldo32 = s.ldo32; L.n32 = s.n32;
+    const bool last = l + 1 == a->n_layers;
+    L.to_x = (s.keep || s.store) ? 1 : 0;
+    (void)last;
+    if (s.store) {
+      NUNERF_REQUIRE(s.ld_store % 8 == 0 && s.ld_store >= s.N, "mlp_chain: bad store pitch");
+      const int cols = (s.N + 63) / 64 * 64 <= s.ld_store ? (s.N + 63) / 64 * 64 : s.N;
+      L.store_chunks = (s.N + 63) / 64;
+      if (int r = make_map(&P.out_map[l], s.store, a->M, cols, s.ld_store, 64, 128)) return r;
+    }
+    if (L.to_x) width = (s.N + 63) / 64 * 64;        // a layer that keeps nothing leaves the previous activation in place
+    // specialised epilogues
+    const bool plain = s.N == 256 && L.n_real == 256 && L.to_x && !s.out32;
+    if (plain && s.bias && s.act == 2 && !s.mask_in && !s.mask_out) L.hot = 1;
+    else if (plain && s.bias && s.act == 1 && !s.mask_in) L.hot = 2;
+    else if (plain && !s.bias && s.act == 0 && s.mask_in && !s.mask_out) L.hot = 3;
+    if (s.mask_in) NUNERF_REQUIRE(s.ldmask_in >= s.N / 8, "mlp_chain: mask_in pitch");
+    if (s.mask_out) NUNERF_REQUIRE(s.ldmask_out >= s.N / 8, "mlp_chain: mask_out pitch");
+  }
+  // timing experiments only (results are wrong with these set): drop the activation stores / the mask writes
+  if (env_int("NUNERF_CHAIN_NOSTORE", 0)) for (int l = 0; l < a->n_layers; ++l) P.layer[l].store_chunks = 0;
+  if (env_int("NUNERF_CHAIN_NOMASK", 0)) for (int l = 0; l < a->n_layers; ++l) P.layer[l].mask_out = nullptr;
+  P.dbg = (long long*)a->timeline;
+  P.dbg_flags = 0;
   return chain_launch(P, stream);
 }

@@ -11,16 +11,24 @@ gates); "bf16" = single plane (the fast mode the benchmark reports; gradients wi
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
 from . import _lib
 from ._lib import call, ptr
-from .ops import P, linear, linear_dw, colsum, to_planes, f32_to_planes, pad
+from .ops import P, linear, linear_dw, colsum, to_planes, f32_to_planes, pad, chain, GEMM_IMPL
 from .weights import Dense, WeightBank
 
 SQRT2 = math.sqrt(2.0)
 F32 = torch.float32
+# bf16 mode: evaluate predictor MLPs (and their dX chains) as ONE fused launch each (csrc/chain.cu) instead of one launch
+# per layer.  NUNERF_FUSED_CHAINS=0 keeps the layer-by-layer path (A/B measurements; the split mode always uses it).
+FUSED_CHAINS = os.environ.get("NUNERF_FUSED_CHAINS", "1") != "0"
+
+
+def _fused(planes):
+    return FUSED_CHAINS and planes == 1 and GEMM_IMPL == 0
 
 
 def _f(*shape, dev):
@@ -253,10 +261,20 @@ def pred_forward(w: PredW, x: P, M, K0, planes):
     t.M, t.x, t.K0 = M, x, K0
     t.H = [P(M, 256, planes, dev) for _ in range(3)]
     t.Mk = [torch.empty(M, 32, dtype=torch.uint8, device=dev) for _ in range(3)]     # 1-bit ReLU masks
+    t.head = _f(M, 16, dev=dev)
+    if _fused(planes):
+        # one launch: hidden activations stay on the SM, each is written out once (dW needs it) with its ReLU mask
+        hidden = lambda i, K: dict(W=w.L[i].Wk, N=256, K=K, bias=w.L[i].b, act=1, mask_out=t.Mk[i], store=t.H[i], keep=1)
+        head = dict(W=w.L[3].Wk, N=16, K=256, bias=w.L[3].b, out32=t.head, n32=16)
+        if K0 <= 256:
+            chain(x, M, K0, [hidden(0, K0), hidden(1, 256), hidden(2, 256), head])
+        else:
+            linear(x, w.L[0].Wk, M, 256, K0, bias=w.L[0].b, act=1, out=t.H[0], mask_out=t.Mk[0])
+            chain(t.H[0], M, 256, [hidden(1, 256), hidden(2, 256), head])
+        return t
     linear(x, w.L[0].Wk, M, 256, K0, bias=w.L[0].b, act=1, out=t.H[0], mask_out=t.Mk[0])
     linear(t.H[0], w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=1, out=t.H[1], mask_out=t.Mk[1])
     linear(t.H[1], w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=1, out=t.H[2], mask_out=t.Mk[2])
-    t.head = _f(M, 16, dev=dev)
     linear(t.H[2], w.L[3].Wk, M, 16, 256, bias=w.L[3].b, out_f32=t.head, n_store=w.n_out)
     return t
 
@@ -267,14 +285,30 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
     M, dev = t.M, t.x.t.device
     gW = [w.L[i].dW for i in range(4)]
     gb = [w.L[i].db for i in range(4)]
-    linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3], db=gb[3])
-    d2, d1 = P(M, 256, planes, dev), P(M, 256, planes, dev)
-    linear(dz_head, w.L[3].WTk, M, 256, 64, mask_in=t.Mk[2], out=d2)
-    linear_dw(d2, t.H[1], M, 256, 256, gW[2], db=gb[2])
-    linear(d2, w.L[2].WTk, M, 256, 256, mask_in=t.Mk[1], out=d1)
-    linear_dw(d1, t.H[0], M, 256, 256, gW[1], db=gb[1])
-    linear(d1, w.L[1].WTk, M, 256, 256, mask_in=t.Mk[0], out=d2)
-    linear_dw(d2, t.x, M, 256, t.K0, gW[0], db=gb[0])
+    if _fused(planes):
+        # dX chain in one launch: dZ_l = (dZ_{l+1} W_{l+1}) . relu'(z_l), each dZ_l written once for its dW GEMM
+        d2, d1, d0 = P(M, 256, planes, dev), P(M, 256, planes, dev), P(M, 256, planes, dev)
+        lays = [dict(W=w.L[3].WTk, N=256, K=64, mask_in=t.Mk[2], store=d2, keep=1),
+                dict(W=w.L[2].WTk, N=256, K=256, mask_in=t.Mk[1], store=d1, keep=1),
+                dict(W=w.L[1].WTk, N=256, K=256, mask_in=t.Mk[0], store=d0, keep=1)]
+        if dx_f32 is not None and dx_n % 16 == 0 and dx_n <= 256:
+            lays.append(dict(W=w.L[0].WTk, N=dx_n, K=256, out32=dx_f32, n32=dx_n))
+            dx_f32 = None
+        chain(dz_head, M, 64, lays)
+        linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3], db=gb[3])
+        linear_dw(d2, t.H[1], M, 256, 256, gW[2], db=gb[2])
+        linear_dw(d1, t.H[0], M, 256, 256, gW[1], db=gb[1])
+        linear_dw(d0, t.x, M, 256, t.K0, gW[0], db=gb[0])
+        d2 = d0
+    else:
+        linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3], db=gb[3])
+        d2, d1 = P(M, 256, planes, dev), P(M, 256, planes, dev)
+        linear(dz_head, w.L[3].WTk, M, 256, 64, mask_in=t.Mk[2], out=d2)
+        linear_dw(d2, t.H[1], M, 256, 256, gW[2], db=gb[2])
+        linear(d2, w.L[2].WTk, M, 256, 256, mask_in=t.Mk[1], out=d1)
+        linear_dw(d1, t.H[0], M, 256, 256, gW[1], db=gb[1])
+        linear(d1, w.L[1].WTk, M, 256, 256, mask_in=t.Mk[0], out=d2)
+        linear_dw(d2, t.x, M, 256, t.K0, gW[0], db=gb[0])
     if dx_planes is not None:
         linear(d2, w.L[0].WTk, M, dx_n, 256, out=dx_planes, add=dx_planes if dx_add else None)
     if dx_f32 is not None:

@@ -115,6 +115,33 @@ def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = 
         call("nunerf_linear", C.byref(p))
 
 
+def chain(X: P, M, K0, layers, x_col=0, timeline=None):
+    """Fused chain of dense layers (csrc/chain.cu, bf16 single-plane operands): `layers` is a list of dicts with keys
+    W (P, K-major weight), N, K and optionally n_real, bias, act, mask_out, mask_in, store (P) / store_col, out32, n32,
+    keep.  See nunerf_mlp_chain_t in include/nunerf.h."""
+    assert X.planes == 1 and len(layers) <= 10
+    a = _lib.MlpChainT()
+    a.x, a.ldx, a.K0, a.M, a.n_layers = X.at(0, x_col), X.ld, K0, M, len(layers)
+    for l, d in enumerate(layers):
+        L = a.layer[l]
+        W = d["W"]
+        assert W.planes == 1
+        L.w, L.ldw, L.N, L.K = W.at(d.get("w_row", 0), 0), W.ld, d["N"], d["K"]
+        L.n_real = d.get("n_real", 0)
+        L.bias = ptr(d.get("bias"))
+        L.act = d.get("act", 0)
+        mo, mi = d.get("mask_out"), d.get("mask_in")
+        L.mask_out, L.ldmask_out = (mo.data_ptr(), mo.stride(0)) if mo is not None else (None, 0)
+        L.mask_in, L.ldmask_in = (mi.data_ptr(), mi.stride(0)) if mi is not None else (None, 0)
+        st = d.get("store")
+        L.store, L.ld_store = (st.at(0, d.get("store_col", 0)), st.ld) if st is not None else (None, 0)
+        o32 = d.get("out32")
+        L.out32, L.ldo32, L.n32 = (o32.data_ptr(), o32.stride(0), d.get("n32", d["N"])) if o32 is not None else (None, 0, 0)
+        L.keep = int(d.get("keep", 0))
+    a.timeline = ptr(timeline)
+    call("nunerf_mlp_chain", C.byref(a))
+
+
 def linear_dw(dZ: P, X: P, M, N, K, dW, *, z_col=0, x_col=0, db=None):
     """dW[:N, :K] += dZ[:, z_col:z_col+N]^T @ X[:, x_col:x_col+K]   (dW fp32, pre-zeroed / accumulating);
     db[:N] += column sums of dZ (the bias gradient) in the same launch when given."""

@@ -8,6 +8,9 @@ Run in the build container only:  python tests/golden/make_golden_stage2.py
                     triangles), random-init nested inner field; ray_trace intermediates per bounce (hit masks, hit
                     triangle ids from the brute-force oracle, refracted directions, IoR ratios, mesh normals, TIR mask,
                     every sampled path point) and the outputs dict in train and eval mode.
+  stage2_grads_R64.npz  same case with autograd on: trainer loss of configs/stage2/nerf/spherepot.yaml
+                    (mean(loss_rgb with the TIR mask, ZT:1272) + mean(0.02 * gradient_error)) and strided samples + norms of
+                    every parameter gradient (incl. IORs_pred, whose gradient flows through the path geometry).
 """
 import os
 import sys
@@ -19,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh  # noqa: E402
 from nu_nerf_b200.fg_lut import make_fg_lut  # noqa: E402
-from make_golden import fingerprint  # noqa: E402
+from make_golden import fingerprint, strided  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 MESH = dict(radius=0.6, nu=48, nv=24)
@@ -68,7 +71,26 @@ def main():
             for kk, v in out.items():
                 res[f"{mode}_{kk}"] = v.detach().float().numpy()
     np.savez_compressed(os.path.join(OUT, "stage2_R64.npz"), **res)
-    for f in ("stage2_init.npz", "stage2_R64.npz"):
+    # ---- gradients of the stage-2 trainer loss (autograd through ray_trace + render_core)
+    gt = rh.synthetic_targets(R)
+    net.zero_grad()
+    pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = net.ray_trace(o, d)
+    out = net.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
+                          cos_anneal_ratio=0.2, step=10000, is_train=True, is_nerf=True)
+    tm = tir_mask.detach()
+    loss_rgb = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm)
+    loss = loss_rgb.mean() + (0.02 * out["gradient_error"]).mean()
+    loss.backward()
+    gres = {"gt": gt.numpy(), "loss": loss.detach().numpy(), "ray_rgb": out["ray_rgb"].detach().numpy()}
+    for name, p_ in net.named_parameters():
+        if p_.grad is None:
+            continue
+        vals, idx = strided(p_.grad)
+        gres["grad/" + name] = vals
+        gres["gradnorm/" + name] = np.array(p_.grad.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, "stage2_grads_R64.npz"), **gres)
+    print("params with grad:", sum(1 for k in gres if k.startswith("grad/")), "loss", float(loss))
+    for f in ("stage2_init.npz", "stage2_R64.npz", "stage2_grads_R64.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)))
     print({k: (v.shape, float(np.mean(v))) for k, v in res.items() if k.startswith(("train_", "eval_", "converge", "tir"))})
 

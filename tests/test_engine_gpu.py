@@ -76,6 +76,53 @@ def test_fused_sdf_chain_matches_layerwise_and_oracle(M):
     assert (fused.cpu() - y).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("M", [1, 300, 148 * 256 + 77])
+@pytest.mark.parametrize("name,K0", [("outer_light", 128), ("metallic_predictor", 320)])
+def test_fused_predictor_chain_matches_layerwise(M, name, K0):
+    """make_predictor MLPs (field.py:371-408) as ONE fused launch per direction (csrc/chain.cu: activations resident on
+    the SM, each hidden activation / dZ written once) against the layer-by-layer bf16 path on the same operands: same
+    rounding points, so activations, ReLU masks, heads, dX and dW must agree to fp32 accumulation-order noise."""
+    from nu_nerf_b200 import engine as eng
+    net = _renderer("bf16")
+    w = net._prepare()
+    pw = w.pred[name]
+    g = torch.Generator().manual_seed(M + K0)
+    x = eng.P(M, K0, 1, DEV, zero=True)
+    x.t[:M, :K0 - 40] = (torch.randn(M, K0 - 40, generator=g) * 0.7).to(DEV).to(torch.bfloat16)
+    dz = eng.P(M, 64, 1, DEV, zero=True)
+    dz.t[:M, :pw.n_out] = torch.randn(M, pw.n_out, generator=g).to(DEV).to(torch.bfloat16)
+    res = {}
+    for fused in (False, True):
+        eng.FUSED_CHAINS = fused
+        try:
+            w.bank.zero_grads()
+            t = eng.pred_forward(pw, x, M, K0, 1)
+            dx = torch.zeros(M, 128, device=DEV)
+            if K0 == 128:
+                eng.pred_backward(pw, t, dz, 1, dx_f32=dx, dx_n=128)
+            else:
+                dxp = eng.P(M, 320, 1, DEV, zero=True)
+                eng.pred_backward(pw, t, dz, 1, dx_planes=dxp, dx_add=False, dx_n=256)
+                dx = dxp.t[:M, :256].float()
+            torch.cuda.synchronize()
+            res[fused] = dict(head=t.head[:, :pw.n_out].clone(), H=[h.t[:M].float().clone() for h in t.H],
+                              Mk=[m.clone() for m in t.Mk], dx=dx.clone(), g=w.bank.gflat.clone())
+        finally:
+            eng.FUSED_CHAINS = True
+    a, b = res[False], res[True]
+    assert torch.isfinite(b["head"]).all()
+    assert (a["head"] - b["head"]).abs().max().item() < 1e-3 * max(1.0, a["head"].abs().max().item())
+    for l in range(3):
+        tol = 2.0 ** -7 * max(1.0, a["H"][l].abs().max().item())        # one bf16 ulp at the largest magnitude
+        assert (a["H"][l] - b["H"][l]).abs().max().item() <= tol, l
+        flips = (a["Mk"][l] != b["Mk"][l]).float().mean().item()
+        assert flips < 1e-3, (l, flips)
+    scale = max(a["dx"].abs().max().item(), 1e-6)
+    assert (a["dx"] - b["dx"]).abs().max().item() < 2e-2 * scale
+    gs = max(a["g"].abs().max().item(), 1e-6)
+    assert (a["g"] - b["g"]).abs().max().item() < 5e-3 * gs
+
+
 def _run_core(net, o, d, z, gt, cos_anneal, step):
     net.zero_grad()
     out = net.render_core(o.to(DEV), d.to(DEV), z.to(DEV), None, cos_anneal_ratio=cos_anneal, step=step, is_train=True,
