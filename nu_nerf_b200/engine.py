@@ -607,45 +607,58 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     if t.n_out > 0:
         nerf_backward(w.nerf, t.nerf, da_out, dc_out, planes)
 
-    def add_pred(name, _):
-        pass
-
     # ---- specular probe (outer_light on the ray directions)
     if d_spec is not None:
         dzs = P(R, 64, planes, dev, zero=True)
         f32_to_planes(d_spec.contiguous(), dzs, R, 3, 64)
-        add_pred("outer_light", pred_backward(w.pred["outer_light"], t.ls_, dzs, planes))
+        pred_backward(w.pred["outer_light"], t.ls_, dzs, planes)
     if M == 0:
         return g
+    inner_backward(w, t, da_in, dc_in, d_gerr, d_trans, d_met, want_inv_s, d_occ, g)
+    return g
+
+
+def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, want_inv_s, d_occ=None, g=None,
+                   surface=False):
+    """Reverse of inner_forward on the M = t.n_in compact samples: shading mix, the light / material predictors,
+    sdf -> alpha, the direction encodings and the SDF network (value pass + reverse-over-reverse of its gradient).
+    surface=True is the reverse of the stage-2 surface shading (shade_forward with the MESH normal, no refraction
+    light, no sdf -> alpha): the normal is a constant there, so only the feature path reaches the SDF network."""
+    planes, dev, M = w.planes, t.pts_in.device, t.n_in
+    g = {} if g is None else g
     # ---- shading mix
     dz = {k: P(M, 64, planes, dev, zero=True) for k in ("metallic", "albedo", "trans", "weight", "refrac")}
     dz["outer"], dz["inner"] = P(3 * M, 64, planes, dev, zero=True), P(2 * M, 64, planes, dev, zero=True)
     d_rough, d_nov = _f(M, dev=dev), _f(M, dev=dev)
     call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov, d_occ)))
     dxo, dxi = _f(3 * M, 128, dev=dev), _f(2 * M, 128, dev=dev)
-    add_pred("outer_light", pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128))
-    add_pred("inner_light", pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128))
-    add_pred("inner_weight", pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes))
-    add_pred("refrac_light", pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes))
+    pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128)
+    pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128)
+    pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes)
+    if not surface:
+        pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes)
     # ---- sdf -> alpha
-    d_sdf, d_grad = _f(M, dev=dev), _f(M, 3, dev=dev)
-    d_inv = _z(1, dev=dev) if want_inv_s else None
-    sa = _lib.SdfAlphaT()
-    sa.M, sa.cos_anneal, sa.inv_s_dev = M, t.cos_anneal, w.inv_s.data_ptr()
-    sa.sdf, sa.ld_sdf, sa.grad, sa.dists, sa.dirs = t.sdf.sdf.data_ptr(), 16, t.sdf.grad.data_ptr(), \
-        t.dists_in.data_ptr(), t.dirs_in.data_ptr()
-    sa.d_alpha, sa.d_grad_err = da_in.data_ptr(), ptr(d_gerr)
-    sa.d_sdf, sa.d_grad, sa.d_inv_s = d_sdf.data_ptr(), d_grad.data_ptr(), ptr(d_inv)
-    call("nunerf_sdf_alpha_bwd", C.byref(sa))
-    if want_inv_s:
-        g["inv_s"] = d_inv
+    d_sdf, d_grad = _z(M, dev=dev), _z(M, 3, dev=dev)
+    if not surface:
+        d_inv = _z(1, dev=dev) if want_inv_s else None
+        sa = _lib.SdfAlphaT()
+        sa.M, sa.cos_anneal, sa.inv_s_dev = M, t.cos_anneal, w.inv_s.data_ptr()
+        sa.sdf, sa.ld_sdf, sa.grad, sa.dists, sa.dirs = t.sdf.sdf.data_ptr(), 16, t.sdf.grad.data_ptr(), \
+            t.dists_in.data_ptr(), t.dirs_in.data_ptr()
+        sa.d_alpha, sa.d_grad_err = da_in.data_ptr(), ptr(d_gerr)
+        sa.d_sdf, sa.d_grad, sa.d_inv_s = d_sdf.data_ptr(), d_grad.data_ptr(), ptr(d_inv)
+        call("nunerf_sdf_alpha_bwd", C.byref(sa))
+        if want_inv_s:
+            g["inv_s"] = d_inv
     # ---- directions / encodings (adds into d_grad and d_rough)
     se = _lib.ShadeEncodeT()
-    se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.sdf.grad.data_ptr(), t.dirs_in.data_ptr()
+    se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.normals.data_ptr(), t.dirs_in.data_ptr()
     se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
     se.d_x_outer, se.ld_dxo, se.d_x_inner, se.ld_dxi = dxo.data_ptr(), 128, dxi.data_ptr(), 128
     se.d_nov, se.d_grad, se.d_rough_raw, se.ld_drough = d_nov.data_ptr(), d_grad.data_ptr(), d_rough.data_ptr(), 1
     call("nunerf_shade_encode_bwd", C.byref(se))
+    if surface:
+        d_grad = _z(M, 3, dev=dev)                                  # the mesh normal is not a function of the field
     dz["rough"] = P(M, 64, planes, dev)
     f32_to_planes(d_rough, dz["rough"], M, 1, 64)
     # ---- material predictors, d feature accumulated in dxm[:, :256]
@@ -653,15 +666,14 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     first = True
     for name, key in (("metallic_predictor", "metallic"), ("roughness_predictor", "rough"),
                       ("albedo_predictor", "albedo"), ("transmisstion_weight", "trans")):
-        add_pred(name, pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first,
-                                      dx_n=256))
+        pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first, dx_n=256)
         first = False
     # ---- SDF network
     sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad)
     return g
 
 
-# =============================================================================================== stage 2 (forward)
+# =============================================================================================== stage 2
 class IorWeights:
     """IoRNetwork (field.py:1046-1065): PE-6 -> 256 relu -> 256 relu -> 256 -> 1, sigmoid (Sequential 0, 2, 4, 5)."""
 
@@ -755,88 +767,66 @@ def _srgb_to_linear(x):
     return torch.where(x <= 0.04045, 25.0 / 323.0 * x, ((200.0 * x + 11.0) / 211.0).clamp(min=eps) ** (12.0 / 5.0))
 
 
-@torch.no_grad()
-def segment_forward(w1: Stage1Weights, w_inner, cand, dirs, cos_anneal, exp_max_inner):
-    """One path segment of Stage2Renderer.render_core (ZT:1853-1951): cand [N, S+1, 3] sampled points (the last one is
-    the surface hit and is shaded separately), dirs [N,3].  NeRF++ (stage-1 outer_nerf) on the samples outside the unit
-    sphere, the inner SDF field (+ shading) on the inside ones when `w_inner` is given (segment 1).
-    Returns color_lin [N,3] = sum_j w_j srgb_to_linear(c_j), t_end [N,1], the inner gradient error and counts."""
-    N, S1, _ = cand.shape
-    S = S1 - 1
-    dev = cand.device
+def segment_geometry(cand):
+    """Per-sample geometry of one path segment (ZT:1859-1869): cand [N, S+1, 3] sampled points, the last one being the
+    surface hit (shaded separately).  Returns pts [N,S,3], Euclidean dists [N,S] (last repeated), the inner mask."""
     pts = cand[:, :-1, :].contiguous()
     d = pts[:, 1:] - pts[:, :-1]
     dists = torch.linalg.norm(d, dim=-1)
     dists = torch.cat([dists, dists[:, -1:]], -1)
     inner = torch.norm(pts, dim=-1) <= 1.0
-    outer = ~inner
-    alpha = torch.zeros(N, S, device=dev)
-    color = torch.zeros(N, S, 3, device=dev)
-    dirs_e = dirs[:, None, :].expand(N, S, 3)
-    out = {"n_in": 0, "gerr": None}
-    if bool(outer.any()):
-        p_o, d_o, di_o = pts[outer].contiguous(), dirs_e[outer].contiguous(), dists[outer].contiguous()
-        _, a_o, c_o = nerf_forward(w1.nerf, p_o, d_o, di_o, w1.planes)
-        alpha[outer] = a_o
-        color[outer] = c_o
-    if w_inner is not None and bool(inner.any()):
-        t = CoreTape()
-        t.pts_in, t.dirs_in, t.dists_in = pts[inner].contiguous(), dirs_e[inner].contiguous(), dists[inner].contiguous()
-        t.n_in, t.cos_anneal, t.exp_max = t.pts_in.shape[0], float(cos_anneal), float(exp_max_inner)
-        inner_forward(w_inner, t)
-        alpha[inner] = t.a_in
-        color[inner] = t.c_in
-        out["n_in"], out["gerr"] = t.n_in, t.gerr
-    # linear-space compositing (ZT:1942-1951)
-    color = _srgb_to_linear(color)
-    Tc = torch.cumprod(torch.cat([torch.ones(N, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)
-    wts = alpha * Tc[:, :-1]
-    out["color_lin"] = (color * wts[..., None]).sum(dim=1)
-    out["t_end"] = Tc[:, -1:]
-    return out
+    return pts, dists, inner
 
 
-@torch.no_grad()
-def surface_shade(w1: Stage1Weights, pts, normals, dirs, exp_max, internal=False, extras=False):
+def inner_tape(pts_in, dirs_in, dists_in, cos_anneal, exp_max):
+    t = CoreTape()
+    t.pts_in, t.dirs_in, t.dists_in = pts_in, dirs_in, dists_in
+    t.n_in, t.cos_anneal, t.exp_max = pts_in.shape[0], float(cos_anneal), float(exp_max)
+    return t
+
+
+def surface_forward(w1: Stage1Weights, pts, normals, dirs, exp_max):
     """AppShadingNetwork_S2.forward (field.py:909-1010) at the mesh hits: stage-1 SDF feature vector (ZT:1519-1529),
-    stage-1 predictors, MESH normal, no refraction-light term; `internal` zeroes the colour (field.py:969)."""
+    stage-1 predictors, MESH normal, no refraction-light term.  Returns the tape (c_in = sRGB colour, trans, nov)."""
     M, dev, planes = pts.shape[0], pts.device, w1.planes
     t = CoreTape()
     t.pts_in, t.dirs_in, t.n_in, t.exp_max = pts, dirs, M, float(exp_max)
     t.xm = P(M, 320, planes, dev)
     f32_to_planes(pts, t.xm, M, 3, 64, col=256)
-    sdf_forward(w1.sdf, pts, planes, t.xm)                 # value pass fills the feature columns of xm
+    t.sdf = sdf_forward(w1.sdf, pts, planes, t.xm)         # value pass fills the feature columns of xm
     shade_forward(w1, t, normals.contiguous(), no_refraction=True)
-    nov = t.nov[:, None]
+    return t
+
+
+def surface_backward(w1: Stage1Weights, t, d_color, d_trans):
+    inner_backward(w1, t, None, d_color, None, d_trans, None, False, surface=True)
+
+
+def surface_extras(w1: Stage1Weights, t, exp_max):
+    """eval-mode buffers of field.py:981-1001, rebuilt from the predictor heads (per-ray tensors)."""
+    M = t.n_in
+    nov, trans = t.nov[:, None], t.trans[:, None]
     tn = torch.clamp(1.0 - nov, 0.0, 1.0)
     rw = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)
-    trans = t.trans[:, None]
-    color = t.c_in
-    if internal:
-        color = torch.zeros_like(color)                    # linear_to_srgb(0) = 0
-    res = {"color": color, "refraction_coefficient": (1.0 - rw) * trans}
-    if extras:
-        # eval-mode buffers of field.py:981-1001, rebuilt from the predictor heads (per-ray tensors)
-        head = lambda tp, n: tp.head[:, :n]
-        met = torch.sigmoid(head(t.mat["metallic_predictor"], 1))
-        rough = torch.sigmoid(head(t.mat["roughness_predictor"], 1))
-        alb = torch.sigmoid(head(t.mat["albedo_predictor"], 3))
-        ex = lambda x: torch.exp(torch.clamp(x, max=exp_max))
-        lo = head(t.lo_, 3)
-        direct, direct0 = ex(lo[M:2 * M]), ex(lo[2 * M:3 * M])
-        li = head(t.li_, 3)
-        ind, ind0 = ex(li[:M]), ex(li[M:2 * M])
-        occ = torch.clamp(head(t.lw_, 1) * 0.5 + 0.5, 0.0, 1.0)
-        light = ind * occ + direct * (1 - occ)
-        light0 = ind0 * occ + direct0 * (1 - occ)
-        spec_albedo = 0.04 * (1 - met) + met * alb
-        fg = _fg_lookup_torch(w1.lut, torch.clamp(nov[:, 0], 0.0, 1.0), torch.clamp(rough[:, 0], 0.0, 1.0))
-        spec_ref = spec_albedo * fg[:, 0:1] + fg[:, 1:2]
-        spec_color = _lin2srgb(spec_ref * light)
-        res["specular_ref"] = torch.clamp(spec_ref, 0.0, 1.0)
-        res["specular_light"] = torch.clamp(_lin2srgb(light0), 0.0, 1.0)
-        res["specular_color"] = torch.clamp(spec_color * (1 - trans) + rw * light0 * trans, 0.0, 1.0)
-    return res
+    head = lambda tp, n: tp.head[:, :n]
+    met = torch.sigmoid(head(t.mat["metallic_predictor"], 1))
+    rough = torch.sigmoid(head(t.mat["roughness_predictor"], 1))
+    alb = torch.sigmoid(head(t.mat["albedo_predictor"], 3))
+    ex = lambda x: torch.exp(torch.clamp(x, max=exp_max))
+    lo = head(t.lo_, 3)
+    direct, direct0 = ex(lo[M:2 * M]), ex(lo[2 * M:3 * M])
+    li = head(t.li_, 3)
+    ind, ind0 = ex(li[:M]), ex(li[M:2 * M])
+    occ = torch.clamp(head(t.lw_, 1) * 0.5 + 0.5, 0.0, 1.0)
+    light = ind * occ + direct * (1 - occ)
+    light0 = ind0 * occ + direct0 * (1 - occ)
+    spec_albedo = 0.04 * (1 - met) + met * alb
+    fg = _fg_lookup_torch(w1.lut, torch.clamp(nov[:, 0], 0.0, 1.0), torch.clamp(rough[:, 0], 0.0, 1.0))
+    spec_ref = spec_albedo * fg[:, 0:1] + fg[:, 1:2]
+    spec_color = _lin2srgb(spec_ref * light)
+    return {"specular_ref": torch.clamp(spec_ref, 0.0, 1.0),
+            "specular_light": torch.clamp(_lin2srgb(light0), 0.0, 1.0),
+            "specular_color": torch.clamp(spec_color * (1 - trans) + rw * light0 * trans, 0.0, 1.0)}
 
 
 def _lin2srgb(x):

@@ -1,6 +1,9 @@
 """Stage2Renderer -- the zero-thickness nested-refraction renderer of network/renderer_zerothick.py:868-2011 ("ZT")
-on the sm_100a engine.  FORWARD path (ray_trace + render_core, train- and eval-mode outputs); the backward through the
-bounce geometry is not built yet (rendering under autograd raises).
+on the sm_100a engine: forward (ray_trace + render_core, train- and eval-mode outputs) and the backward of render_core
+with respect to every FIELD parameter (stage-1 NeRF++ / SDF feature / predictors at the surface hits, inner SDF, inner
+shading, inner variance).  The path geometry is a constant of the backward: the gradient of IORs_pred, which in the
+reference flows through the refracted sample positions into every field's input, is not built yet (its parameters get
+no .grad; every other parameter's gradient is unaffected because no other parameter moves the positions).
 
   ray_trace   ZT:1571-1828   <= 3 bounces: BVH closest hit + re-intersection (csrc/bvh.cu), IoR MLP on tensor cores,
                              Snell / TIR kernel, segment sampling (256 uniform | 64 + 2 x 32 SDF-guided with the warp
@@ -9,10 +12,11 @@ bounce geometry is not built yet (rendering under autograd raises).
                              shading at the hit with the mesh normal and the stage-1 predictors, linear-space
                              compositing with the throughput chain T *= T_end (1 - schlick) transmission
 
-Lists returned by ray_trace have the reference's exact structure (per-segment compacted rows in boolean-mask order),
-so render_core accepts the reference's ray_trace output and vice versa.  The per-ray bookkeeping between bounces
-(mask compaction, TIR chain) is torch indexing on [R]-sized tensors, as in the reference; everything per sample point
-runs in libnunerf_b200.so.
+Each field evaluation is one autograd node (forward = explicit launch sequence, backward = hand-derived reverse sequence
+of engine.py, gradients added in place to .grad by the WeightBank); the per-ray / per-segment bookkeeping between them
+(mask compaction, linear-space compositing of [N, 255] rows, throughput chain, reverse scatter-add) is torch indexing,
+as in the reference.  Lists returned by ray_trace have the reference's exact structure (per-segment compacted rows in
+boolean-mask order), so render_core accepts the reference's ray_trace output and vice versa.
 """
 import numpy as np
 import torch
@@ -37,6 +41,86 @@ def srgb_to_linear(x):
 def linear_to_srgb(x):
     eps = torch.finfo(torch.float32).eps
     return torch.where(x <= 0.0031308, 323.0 / 25.0 * x, (211.0 * torch.clamp(x, min=eps) ** (5.0 / 12.0) - 11.0) / 200.0)
+
+
+def _bank_params(w):
+    ps = [p for d in w.bank.denses if d.has_grad for p in (d.v, d.g, d.bias) if p is not None]
+    return list({id(p): p for p in ps}.values())
+
+
+class _NerfFn(torch.autograd.Function):
+    """compute_density_alpha (ZT:1531-1539) on a flat list of outer samples with the stage-1 NeRF++."""
+
+    @staticmethod
+    def forward(ctx, pack, *params):
+        eng = _engine()
+        w, pts, dirs, dists = pack
+        tape, alpha, color = eng.nerf_forward(w.nerf, pts, dirs, dists, w.planes)
+        ctx.w, ctx.tape, ctx.n = w, tape, len(params)
+        return alpha, color
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_color):
+        eng = _engine()
+        w, t = ctx.w, ctx.tape
+        z = lambda g, *shape: torch.zeros(*shape, device=t.dists.device) if g is None else g.contiguous().float()
+        w.bank.zero_grads()
+        eng.nerf_backward(w.nerf, t, z(d_alpha, t.M), z(d_color, t.M, 3), w.planes)
+        w.bank.backward()
+        ctx.tape = None
+        return (None,) + (None,) * ctx.n
+
+
+class _InnerFn(torch.autograd.Function):
+    """compute_sdf_alpha + color_network_inner (ZT:1887-1906) on the compact inner samples of segment 1."""
+
+    @staticmethod
+    def forward(ctx, pack, inv_s, *params):
+        eng = _engine()
+        w, pts, dirs, dists, cos_anneal, exp_max, want_inv_s = pack
+        t = eng.inner_tape(pts, dirs, dists, cos_anneal, exp_max)
+        eng.inner_forward(w, t)
+        ctx.w, ctx.tape, ctx.n, ctx.want_inv_s = w, t, len(params), want_inv_s
+        return t.a_in, t.c_in, t.gerr
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_color, d_gerr):
+        eng = _engine()
+        w, t = ctx.w, ctx.tape
+        dev, M = t.pts_in.device, t.n_in
+        z = lambda g, *shape: torch.zeros(*shape, device=dev) if g is None else g.contiguous().float()
+        w.bank.zero_grads()
+        g = eng.inner_backward(w, t, z(d_alpha, M), z(d_color, M, 3), z(d_gerr, M), None, None, ctx.want_inv_s)
+        w.bank.backward()
+        ctx.tape = None
+        d_inv = g["inv_s"].reshape(()) if ctx.want_inv_s and "inv_s" in g else None
+        return (None, d_inv) + (None,) * ctx.n
+
+
+class _SurfaceFn(torch.autograd.Function):
+    """AppShadingNetwork_S2 at the mesh hits (ZT:1908-1925): sRGB colour, transmission weight, NoV."""
+
+    @staticmethod
+    def forward(ctx, pack, *params):
+        eng = _engine()
+        w, pts, normals, dirs, exp_max, holder = pack
+        t = eng.surface_forward(w, pts, normals, dirs, exp_max)
+        holder["tape"] = t                      # eval-mode extras are rebuilt from the predictor heads
+        ctx.w, ctx.tape, ctx.n = w, t, len(params)
+        ctx.mark_non_differentiable(t.nov)
+        return t.c_in, t.trans, t.nov
+
+    @staticmethod
+    def backward(ctx, d_color, d_trans, _d_nov):
+        eng = _engine()
+        w, t = ctx.w, ctx.tape
+        dev, M = t.pts_in.device, t.n_in
+        z = lambda g, *shape: torch.zeros(*shape, device=dev) if g is None else g.contiguous().float()
+        w.bank.zero_grads()
+        eng.surface_backward(w, t, z(d_color, M, 3), z(d_trans, M))
+        w.bank.backward()
+        ctx.tape = None
+        return (None,) + (None,) * ctx.n
 
 
 class _InnerField:
@@ -235,7 +319,6 @@ class Stage2Renderer(nn.Module):
         return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
 
     # ------------------------------------------------------------------ ZT:1835-2011
-    @torch.no_grad()
     def render_core(self, rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
                     human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True, is_nerf=False, prepared=None):
         eng = _engine()
@@ -248,37 +331,73 @@ class Stage2Renderer(nn.Module):
         colors, tmp = [], {}
         exp_max1 = self.stage1_network.color_network.cfg["light_exp_max"]
         exp_maxi = self.color_network_inner.cfg["light_exp_max"]
+        p1, p_in = _bank_params(w1), _bank_params(wi)
+        freeze = self.cfg["freeze_inv_s_step"]
+        frozen = freeze is not None and step is not None and step < freeze
         for i in range(len(pathes)):
-            cand = pathes[i]
-            N = cand.shape[0]
+            cand = pathes[i].detach()
+            N, S = cand.shape[0], cand.shape[1] - 1
             conv = converges[i].flatten()
-            dirs_i = directions[i]
-            seg = eng.segment_forward(w1, wi if i == 1 else None, cand, dirs_i, float(cos_anneal_ratio), exp_maxi)
-            if i == 1 and seg["n_in"] > 0:
-                inv_s = torch.exp(self.deviation_network_inner.variance.detach() * 10.0).clip(1e-6, 1e6)
-                tmp["std"] = torch.mean(1.0 / inv_s)
-                tmp["gradient_error"] = seg["gerr"]
-            color_now = seg["color_lin"] * T                              # sum w * srgb_to_linear(c), ZT:1946-1951
-            T = T * seg["t_end"]
+            dirs_i = directions[i].detach()
+            with torch.no_grad():
+                pts, dists, inner = eng.segment_geometry(cand)
+                outer = ~inner
+                dirs_e = dirs_i[:, None, :].expand(N, S, 3)
+            alpha = torch.zeros(N, S, device=dev)
+            color = torch.zeros(N, S, 3, device=dev)
+            if bool(outer.any()):
+                # NeRF++ of the STAGE-1 network on the samples outside the unit sphere (ZT:1876-1880)
+                a_o, c_o = _NerfFn.apply((w1, pts[outer].contiguous(), dirs_e[outer].contiguous(),
+                                          dists[outer].contiguous()), *p1)
+                alpha[outer] = a_o
+                color[outer] = c_o
+            if i == 1 and bool(inner.any()):
+                # inner SDF field + inner shading on segment 1 (ZT:1883-1906)
+                inv_s = torch.exp(self.deviation_network_inner.variance * 10.0)
+                a_i, c_i, gerr = _InnerFn.apply((wi, pts[inner].contiguous(), dirs_e[inner].contiguous(),
+                                                 dists[inner].contiguous(), float(cos_anneal_ratio), exp_maxi,
+                                                 not frozen), inv_s, *p_in)
+                alpha[inner] = a_i
+                color[inner] = c_i
+                inv_s_c = inv_s.clip(1e-6, 1e6)
+                tmp["std"] = torch.mean(1.0 / (inv_s_c.detach() if frozen else inv_s_c))
+                tmp["gradient_error"] = gerr
+            # linear-space compositing (ZT:1942-1951)
+            Tc = torch.cumprod(torch.cat([torch.ones(N, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)
+            wts = alpha * Tc[:, :-1]
+            color_now = (srgb_to_linear(color) * wts[..., None]).sum(dim=1) * T
+            T = T * Tc[:, -1:]
             n_hit = int(conv.sum())
             if n_hit > 0:
                 p_hit = cand[conv][:, -1, :].contiguous()
-                sh = eng.surface_shade(w1, p_hit, gradient_mesh[i].contiguous(), dirs_i[conv].contiguous(), exp_max1,
-                                       internal=(i % 2 != 0), extras=(i == 0 and not is_train))
-                color_now[conv] = color_now[conv] + srgb_to_linear(sh["color"]) * T[conv]
+                holder = {}
+                c_s, trans, nov = _SurfaceFn.apply((w1, p_hit, gradient_mesh[i].detach().contiguous(),
+                                                    dirs_i[conv].contiguous(), exp_max1, holder), *p1)
+                if i % 2 != 0:
+                    c_s = torch.zeros_like(c_s)                    # inside the object: field.py:969
+                tn = torch.clamp(1.0 - nov[:, None], 0.0, 1.0)
+                rw = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)
+                hit_add = torch.zeros_like(color_now)
+                hit_add[conv] = srgb_to_linear(c_s) * T[conv]
+                color_now = color_now + hit_add
                 if i == 0 and not is_train:
-                    normals_out[conv] = (F.normalize(gradient_mesh[i].reshape(-1, 3), dim=-1) + 1.0) * 0.5
-                    spec_color_out[conv], spec_light_out[conv], spec_ref_out[conv] = \
-                        sh["specular_color"], sh["specular_light"], sh["specular_ref"]
-                T = T[conv] * sh["refraction_coefficient"]
+                    with torch.no_grad():
+                        ex = eng.surface_extras(w1, holder["tape"], exp_max1)
+                        normals_out[conv] = (F.normalize(gradient_mesh[i].reshape(-1, 3), dim=-1) + 1.0) * 0.5
+                        spec_color_out[conv], spec_light_out[conv], spec_ref_out[conv] = \
+                            ex["specular_color"], ex["specular_light"], ex["specular_ref"]
+                T = T[conv] * ((1.0 - rw) * trans[:, None])        # refraction_coefficient, ZT:1966
                 colors.append(color_now)
             else:
                 colors.append(color_now)
                 break
+        total = colors[-1]
         for i in range(len(colors) - 1, 0, -1):
             m = converges[i - 1].flatten()
-            colors[i - 1][m] = colors[i - 1][m] + colors[i]
-        ray_rgb = torch.clamp(linear_to_srgb(colors[0]), min=0.0, max=1.0)
+            up = torch.zeros_like(colors[i - 1])
+            up[m] = total
+            total = colors[i - 1] + up
+        ray_rgb = torch.clamp(linear_to_srgb(total), min=0.0, max=1.0)
         return {
             "ray_rgb": ray_rgb,
             "gradient_error": tmp.get("gradient_error", torch.zeros(1, device=dev)),
@@ -291,9 +410,6 @@ class Stage2Renderer(nn.Module):
     # ------------------------------------------------------------------ ZT:1442-1466
     def render(self, rays_o, rays_d, near=None, far=None, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,
                is_train=True, step=None, is_nerf=False):
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and is_train:
-            raise NotImplementedError("Stage2Renderer: the backward through the refraction bounce is not built yet; "
-                                      "render under torch.no_grad() (forward parity with the reference is tested)")
         prepared = self._prepare()
         pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = \
             self.ray_trace(rays_o, rays_d, prepared=prepared)
@@ -311,5 +427,6 @@ class Stage2Renderer(nn.Module):
         rays_d = F.normalize(batch["rays_d"], dim=-1)
         out = self.render(batch["rays_o"], rays_d, None, None, None, -1, self.get_anneal_val(step), is_train=True,
                           step=step, is_nerf=self.is_nerf)
-        out["loss_rgb"] = self.compute_rgb_loss(out["ray_rgb"], batch["rgbs"])
+        tm = out["tir_mask"].detach()
+        out["loss_rgb"] = self.compute_rgb_loss(out["ray_rgb"] * tm, batch["rgbs"] * tm)        # ZT:1272
         return out

@@ -3,7 +3,13 @@ reference run through oracle/ref_harness.py (tests/golden/stage2_R64.npz, made b
 
 Bars: hit masks, hit triangle ids and TIR mask bit-exact; refracted directions / IoR ratios / mesh normals 1e-5;
 sampled path points 1e-4 (uniform segments) and the quantile gate of the importance samplers; rendered colour 1e-4 in
-the fp32-accurate mode when render_core is fed the reference's own ray_trace lists, 2e-3 end to end.
+the fp32-accurate mode when render_core is fed the reference's own ray_trace lists, 2e-3 end to end; parameter gradients
+of the stage-2 trainer loss against the reference's autograd (tests/golden/stage2_grads_R64.npz): gradient norms within
+2e-3 relative and strided samples within 1e-3 of the tensor's largest sampled magnitude for >= 80 % of the tensors (all
+within 1e-2), in the fp32-accurate mode -- measured: 220 / 259 tensors within 1e-3, worst 8.7e-3; the tail sits in the
+stage-1 SDF / material layers whose gradient comes from only ~110 surface-hit points, where a single ReLU mask flipped
+by the 1e-5 forward error of the bf16x3 products moves the sum by ~1e-3 (same effect as in the stage-1 gate).  IORs_pred is excluded: its gradient flows through the path geometry, which the
+backward treats as a constant (documented in renderer_stage2.py / DESIGN.md).
 """
 import os
 
@@ -103,8 +109,6 @@ def test_render_end_to_end(net, golden):
     err = (out["ray_rgb"].cpu() - ref).abs()
     assert err.max().item() < 2e-3, err.max().item()
     assert torch.equal(out["tir_mask"].cpu(), torch.from_numpy(G["tir_mask"]))
-    with pytest.raises(NotImplementedError):
-        net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)   # autograd on: no backward yet
 
 
 def test_bf16_mode_is_close(golden):
@@ -115,3 +119,75 @@ def test_bf16_mode_is_close(golden):
     out = net16.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2,
                             step=10000, is_train=True, is_nerf=True)
     assert (out["ray_rgb"].cpu() - torch.from_numpy(G["train_ray_rgb"])).abs().max().item() < 2e-2
+
+
+def _stage2_loss_backward(net, G, GG):
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    pathes, converges, directions, iors, bkgr, nmesh = _lists(G)
+    gt = torch.from_numpy(GG["gt"]).to(DEV)
+    tm = torch.from_numpy(G["tir_mask"]).to(DEV)
+    net.zero_grad()
+    out = net.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2,
+                          step=10000, is_train=True, is_nerf=True)
+    loss = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
+    loss.backward()
+    return out, loss
+
+
+def test_parameter_gradients_match_reference(net, golden):
+    """Backward of Stage2Renderer.render_core on the reference's own path lists against the reference's autograd."""
+    GG = np.load(os.path.join(GOLDEN, "stage2_grads_R64.npz"))
+    out, loss = _stage2_loss_backward(net, golden, GG)
+    assert abs(loss.item() - float(GG["loss"])) < 1e-4
+    named = dict(net.named_parameters())
+    checked, bad, report = 0, [], []
+    for key in GG.files:
+        if not key.startswith("grad/"):
+            continue
+        name = key[5:]
+        if name.startswith("IORs_pred"):
+            continue
+        ref = torch.from_numpy(GG[key])
+        ref_norm = float(GG["gradnorm/" + name])
+        p = named[name]
+        if ref_norm == 0.0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-9, name
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        g = p.grad.detach().reshape(-1).cpu()
+        idx = torch.linspace(0, g.numel() - 1, min(g.numel(), 64)).long()
+        scale = max(ref.abs().max().item(), ref_norm / max(g.numel(), 1) ** 0.5)
+        rel = (g[idx] - ref).abs().max().item() / scale
+        nrel = abs(p.grad.double().norm().item() - ref_norm) / ref_norm
+        report.append((name, rel, nrel))
+        checked += 1
+        assert rel < 1e-2 and nrel < 1e-2, (name, rel, nrel)
+        if rel > 1e-3 or nrel > 2e-3:
+            bad.append((name, rel, nrel))
+    report.sort(key=lambda r: -r[1])
+    print("worst stage-2 parameter gradients (name, sampled rel. error, norm rel. error):")
+    for r in report[:8]:
+        print("   %-60s %.2e %.2e" % r)
+    assert checked >= 250, checked
+    assert len(bad) <= 0.20 * checked, bad[:8]
+
+
+def test_bf16_mode_gradients_are_close(golden):
+    """Fast mode: gradient norms within 2e-2 + the fp32 tolerance for >= 85 % of the tensors."""
+    GG = np.load(os.path.join(GOLDEN, "stage2_grads_R64.npz"))
+    net16 = make_stage2("bf16").cuda()
+    out, loss = _stage2_loss_backward(net16, golden, GG)
+    assert abs(loss.item() - float(GG["loss"])) < 5e-3
+    named = dict(net16.named_parameters())
+    n, bad = 0, []
+    for key in GG.files:
+        if not key.startswith("gradnorm/") or key[9:].startswith("IORs_pred"):
+            continue
+        name, ref_norm = key[9:], float(GG[key])
+        if ref_norm == 0.0:
+            continue
+        n += 1
+        nrel = abs(named[name].grad.double().norm().item() - ref_norm) / ref_norm
+        if nrel > 2e-2:
+            bad.append((name, nrel))
+    assert len(bad) <= 0.15 * n, sorted(bad, key=lambda b: -b[1])[:8]
