@@ -142,6 +142,71 @@ def run_reference(args):
 
 
 # =============================================================================================== our arm
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json: written by hand from tools/ncu_metrics.py output, names the capture)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f).get(kernel)
+    return t if t else None
+
+
+def tc_work(name, a):
+    """(kernel family, key, algorithmic FLOPs, algorithmic HBM bytes) of one tensor-core entry-point call."""
+    if name == "nunerf_linear":
+        p = a[0]._obj
+        n = p.n_store if p.n_store else p.N
+        key = (f"linear K={p.K} N={p.N} act={p.act} aux={p.aux_mode} add={int(bool(p.add))} "
+               f"mask_out={int(bool(p.mask_out))} f32={int(bool(p.out_f32))} bf16={int(bool(p.out))} lo={int(bool(p.a_lo_off))}")
+        return "linear_tc_kernel", key, 2.0 * p.M * n * p.K, 2.0 * p.M * (p.K + (n if p.out else 0)) * (2 if p.a_lo_off else 1)
+    if name == "nunerf_linear_dw":
+        p = a[0]._obj
+        return "dw_tc_kernel", f"dw K={p.K} N={p.N}", 2.0 * p.M * p.N * p.K, 2.0 * p.M * (p.K + p.N) * (2 if p.z_lo_off else 1)
+    if name == "nunerf_mlp_chain":
+        p = a[0]._obj
+        fl, by, desc = 0.0, 2.0 * p.M * p.K0, []
+        for l in range(p.n_layers):
+            L = p.layer[l]
+            fl += 2.0 * p.M * L.N * L.K
+            by += p.M * ((2.0 * L.N if L.store else 0.0) + (L.N / 8.0 if L.mask_out else 0.0)
+                         + (L.N / 8.0 if L.mask_in else 0.0) + (4.0 * L.n32 if L.out32 else 0.0))
+            desc.append(f"{L.K}>{L.N}")
+        return "mlp_chain_kernel", "chain " + " ".join(desc), fl, by
+    if name == "nunerf_sdf_infer":
+        p = a[0]._obj
+        return "mlp_chain_kernel", "chain sdf_infer (PE + 9 layers)", 2.0 * p.M * M_SDF_HEAD, 16.0 * p.M
+    return None
+
+
+def hbm_work(name, a):
+    """Algorithmic HBM bytes of one launch of the sampling / compositing kernels (fp32 I/O that the kernel must do:
+    its inputs once, its outputs once; SURVEY 8d conventions)."""
+    if name == "nunerf_composite_fwd":
+        R, S = a[5], a[6]
+        return 16.0 * R * S + 28.0 * R
+    if name == "nunerf_composite_bwd":
+        R, S = a[5], a[6]
+        return 32.0 * R * S + 12.0 * R
+    if name == "nunerf_upsample":
+        R, n, nn = a[4], a[5], a[6]
+        return R * (24.0 + 8.0 * n + 8.0 * nn + 8.0 * (n + nn))
+    if name == "nunerf_points":
+        R, n = a[3], a[4]
+        return R * (24.0 + 16.0 * n)
+    if name == "nunerf_merge_sdf":
+        R, n, nn = a[3], a[4], a[5]
+        return R * 4.0 * (n + nn + 2 * (n + nn))
+    if name == "nunerf_ray_setup":
+        R = a[7]
+        return R * (24.0 + 8.0 + 132.0 + 4.0 * 96)
+    if name == "nunerf_render_geometry":
+        R, S = a[3], a[4]
+        return R * (24.0 + 56.0 * S)
+    return 0.0
+
+
 def profile_step(train_step, inputs, ops, torch):
     """Per-entry-point device time of one step (CUDA events around every C-ABI call; printed to stderr)."""
     import collections
@@ -150,17 +215,11 @@ def profile_step(train_step, inputs, ops, torch):
     from nu_nerf_b200 import engine as eng
 
     def timed_call(name, *a):
-        key = name
-        if name == "nunerf_linear":
-            p = a[0]._obj
-            key = f"linear K={p.K} N={p.N} act={p.act} aux={p.aux_mode} add={int(bool(p.add))} mask_out={int(bool(p.mask_out))} f32={int(bool(p.out_f32))} bf16={int(bool(p.out))} lo={int(bool(p.a_lo_off))}"
-            nbytes = 2.0 * p.M * (p.K + (p.N if p.out else 0)) * (2 if p.a_lo_off else 1)
-        elif name == "nunerf_linear_dw":
-            p = a[0]._obj
-            key = f"dw K={p.K} N={p.N}"
-            nbytes = 2.0 * p.M * (p.K + p.N) * (2 if p.z_lo_off else 1)
+        w = tc_work(name, a)
+        if w is not None:
+            key, nbytes = w[1], w[3]
         else:
-            nbytes = 0.0
+            key, nbytes = name, hbm_work(name, a)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig_call(name, *a)
@@ -183,7 +242,7 @@ def profile_step(train_step, inputs, ops, torch):
         a[0] += 1; a[1] += e0.elapsed_time(e1); a[2] += nb
     tot = sum(v[1] for v in agg.values())
     print(f"[profile] step {t0.elapsed_time(t1):.2f} ms, inside C-ABI calls {tot:.2f} ms", file=sys.stderr)
-    for key, (n, ms, nb) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    for key, (n, ms, nb) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         gbs = f"{nb / ms / 1e6:8.0f} GB/s" if nb else ""
         print(f"[profile] {ms:8.3f} ms {n:4d}x  {key} {gbs}", file=sys.stderr)
 
@@ -270,31 +329,37 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel (linear_tc_kernel), measured with CUDA events around every launch of
-    #      one extra step on the launching stream
+    # ---- roofline of the tensor-core kernels (linear_tc_kernel, dw_tc_kernel, mlp_chain_kernel), measured with CUDA
+    #      events around every launch of one extra step on the launching stream; the dominant one is reported
     rec = []
     orig_call = ops.call
+    from nu_nerf_b200 import engine as eng
 
     def timed_call(name, *a):
-        if name != "nunerf_linear":
+        w = tc_work(name, a)
+        if w is None:
             return orig_call(name, *a)
-        p = a[0]._obj
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         orig_call(name, *a)
         e1.record()
-        rec.append((e0, e1, p.M, p.N, p.K, p.n_store))
+        rec.append((w[0], e0, e1, w[2], w[3]))
     ops.call = timed_call
+    eng.call = timed_call
     try:
         train_step(o_d, d_d, gt_d)
         torch.cuda.synchronize()
     finally:
         ops.call = orig_call
+        eng.call = orig_call
     if args.profile:
         profile_step(train_step, (o_d, d_d, gt_d), ops, torch)
-    t_lin = sum(e0.elapsed_time(e1) for e0, e1, *_ in rec) * 1e-3
-    fl_lin = sum(2.0 * M * (ns if ns else N) * K for _, _, M, N, K, ns in rec)
-    by_lin = sum(2.0 * M * (K + (ns if ns else N)) for _, _, M, N, K, ns in rec)
+    fam = {}
+    for k, e0, e1, fl, by in rec:
+        f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+        f["ms"] += e0.elapsed_time(e1); f["flops"] += fl; f["bytes"] += by; f["launches"] += 1
+    top = max(fam, key=lambda k: fam[k]["ms"])
+    t_lin, fl_lin, by_lin, n_lin = fam[top]["ms"] * 1e-3, fam[top]["flops"], fam[top]["bytes"], fam[top]["launches"]
     hbm, tf_burst, tf_sus, which = peaks()
     n_in, n_out = stats["n_in"], chunk * 160 - stats["n_in"]
     flops_step = (R / chunk) * (2.0 * chunk * 112 * M_SDF_HEAD + n_in * 2.0 * (3 * M_SDF + 3 * M_SDF_HEAD + 3 * M_COL)
@@ -316,11 +381,15 @@ def run_ours(args):
         "e2e": {"value": R * world / (ms_e2e * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "linear_tc_kernel (tcgen05 dense layer)",
+        "roofline": {"bound": "tensor", "kernel": top + " (tcgen05)",
                      "achieved": fl_lin / t_lin / 1e12 if t_lin > 0 else None, "peak": tf_sus, "unit": "TFLOP/s",
-                     "frac": fl_lin / t_lin / 1e12 / tf_sus if t_lin > 0 else None, "traffic": None,
+                     "frac": fl_lin / t_lin / 1e12 / tf_sus if t_lin > 0 else None, "traffic": (ncu_traffic(top) or {}).get("dram_bytes_per_launch"),
+                     "traffic_note": (ncu_traffic(top) or {}).get("note"),
                      "peak_source": f"bf16_tflops_sustained of {which} (kernel timed inside a long step)",
-                     "launches_timed": len(rec), "kernel_share_of_step": t_lin * 1e3 / ms,
+                     "launches_timed": n_lin, "kernel_share_of_step": t_lin * 1e3 / ms,
+                     "kernels": {k: {"ms_per_step": v["ms"], "launches": v["launches"], "share_of_step": v["ms"] / ms,
+                                     "tflops": v["flops"] / v["ms"] / 1e9, "frac_of_tensor_peak": v["flops"] / v["ms"] / 1e9 / tf_sus,
+                                     "algorithmic_hbm_gbs": v["bytes"] / v["ms"] / 1e6} for k, v in fam.items()},
                      "hbm_achieved_gbs": by_lin / t_lin / 1e9 if t_lin > 0 else None,
                      "hbm_frac": by_lin / t_lin / 1e9 / hbm if t_lin > 0 else None,
                      "step_algorithmic_tflops": flops_step / (ms * 1e-3) / 1e12,

@@ -1,6 +1,7 @@
 """Config 4 of BASELINE.json: stage-2 nested refraction on a ~100k-triangle synthetic outer mesh (UV sphere r 0.6,
 224 x 224 -> 99 904 triangles) + random-init nested inner field.  Reports trace-only Mrays/s (BVH closest hit +
-re-intersection, 32 B/ray/bounce algorithmic) and the full forward rays/s (ray_trace + render_core, bf16 mode)."""
+re-intersection, 32 B/ray/bounce algorithmic), the full forward rays/s (ray_trace + render_core, bf16 mode) and the
+stage-2 TRAINING step rays/s (ray_trace + render_core forward + backward w.r.t. the field parameters + Adam)."""
 import json
 import os
 import sys
@@ -46,6 +47,19 @@ def main():
         ms_full = timeit(lambda: net.render(o, d, None, None, None, -1, 0.2, is_train=False, step=10000, is_nerf=True),
                          iters=5, warm=2)
         ms_rt = timeit(lambda: net.ray_trace(o, d), iters=5, warm=2)
+    # training step: trainer loss of configs/stage2/nerf/spherepot.yaml (TIR-masked charbonnier + 0.02 eikonal), Adam
+    gt = torch.rand(R, 3, generator=g).cuda()
+    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=5e-4, fused=True)
+
+    def train_step():
+        opt.zero_grad(set_to_none=True)
+        out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+        tm = out["tir_mask"].detach()
+        loss = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
+        loss.backward()
+        opt.step()
+        return loss
+    ms_train = timeit(train_step, iters=5, warm=3)
     print(json.dumps({
         "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
                     f"{R} rays, bf16 mode",
@@ -54,6 +68,9 @@ def main():
         "trace_plus_reintersection": {"ms": ms_di, "Mrays_per_s": Rt / ms_di / 1e3},
         "ray_trace_with_sampling": {"rays": R, "ms": ms_rt, "rays_per_s": R / ms_rt * 1e3},
         "full_forward": {"rays": R, "ms": ms_full, "rays_per_s": R / ms_full * 1e3},
+        "train_step": {"rays": R, "ms": ms_train, "rays_per_s": R / ms_train * 1e3,
+                       "note": "forward + backward w.r.t. all field parameters + Adam; IORs_pred gradient (through the "
+                               "path geometry) not included"},
     }))
 
 
