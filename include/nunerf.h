@@ -92,6 +92,9 @@ typedef struct {
   void* store; int ld_store;                 /* optional bf16 [M, pad64(N)] copy of y (TMA store) */
   float* out32; int ldo32; int n32;          /* optional fp32 copy of the first n32 columns */
   int keep;                                  /* y becomes the next layer's input */
+  int mask_perm;                             /* plain 256-wide ReLU layers: the mask (in or out) is in the kernel's thread
+                                                order -- 2-byte word j*4 + c holds columns c*64 + j*16 .. +15 -- so that
+                                                each thread moves its 64 bits with one 8-byte access */
 } nunerf_chain_layer_t;
 typedef struct {
   const void* x; int ldx; int K0;            /* bf16 [M, K0], K0 in {64,128,192,256} */

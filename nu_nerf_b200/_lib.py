@@ -41,7 +41,7 @@ class SdfInferT(C.Structure):
 class ChainLayerT(C.Structure):
     _fields_ = [("w", vp), ("ldw", ci), ("N", ci), ("K", ci), ("n_real", ci), ("bias", vp), ("act", ci),
                 ("mask_out", vp), ("ldmask_out", ci), ("mask_in", vp), ("ldmask_in", ci), ("store", vp), ("ld_store", ci),
-                ("out32", vp), ("ldo32", ci), ("n32", ci), ("keep", ci)]
+                ("out32", vp), ("ldo32", ci), ("n32", ci), ("keep", ci), ("mask_perm", ci)]
 
 
 class MlpChainT(C.Structure):

@@ -47,6 +47,8 @@ struct ChainLayer {
   int w_box_bytes;  // bytes of one weight TMA box: 128 B x min(128, N) rows
   int hot;          // plain 256-wide hidden layer with a specialised epilogue (ch_hot16 KIND 1..3), 0 = generic path
   const float* bias;
+  int mask_perm;    // hot layers only: mask words in THREAD order -- byte j*8 + c*2 holds the 16 bits of columns
+                    // c*64 + j*16 .. +15 (one 8-byte access per thread and tile instead of four 2-byte ones)
   uint8_t* mask_out; int ldmask_out;       // optional 1-bit (x > 0) mask, 32 bytes per row
   const uint8_t* mask_in; int ldmask_in;   // optional 1-bit multiplicative mask
   float* out32; int ldo32; int n32;        // optional fp32 copy of the first n32 columns
@@ -250,6 +252,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
         for (int t = 0; t < 2; ++t) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
           // the previous layer's epilogue of this tile has drained the accumulator and written the activation
+#if NUNERF_CHAIN_TIMELINE_DETAIL
+          if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[450 + t] = clock64();
+#endif
           if (g > 0) ptx::mbar_wait(&x_done[t], (uint32_t)((g - 1) & 1));
           if (l == 0) ptx::mbar_wait(&in_full[t], (uint32_t)(it & 1));
           ptx::tc_fence_after();
@@ -374,12 +379,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           // ReLU-backward layers: this thread's 4 x 16 mask bits, fetched while the tensor core is still busy
           unsigned long long hot_mask = 0ull;
           if (L.hot == 3) {
-            const uint8_t* mrow = L.mask_in + (row_ok ? row : 0) * L.ldmask_in + 2 * j;
+            if (L.mask_perm) {
+              hot_mask = __ldg(reinterpret_cast<const unsigned long long*>(L.mask_in + (row_ok ? row : 0) * L.ldmask_in + 8 * j));
+            } else {
+              const uint8_t* mrow = L.mask_in + (row_ok ? row : 0) * L.ldmask_in + 2 * j;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              hot_mask |= (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(mrow + 8 * c)) << (16 * c);
+              for (int c = 0; c < 4; ++c)
+                hot_mask |= (unsigned long long)__ldg(reinterpret_cast<const uint16_t*>(mrow + 8 * c)) << (16 * c);
+            }
             if (!row_ok) hot_mask = 0ull;
           }
+          unsigned long long out_mask = 0ull;
           // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier
           if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[t], (uint32_t)(g & 1));
           asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -395,7 +405,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               if (L.hot == 1) ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
               else if (L.hot == 2) {
                 ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
-                if (L.mask_out && row_ok)
+                if (L.mask_perm) out_mask |= (unsigned long long)ob << (16 * c);
+                else if (L.mask_out && row_ok)
                   *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
               } else {
                 ch_hot16<3>(taddr, nullptr, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu,
@@ -484,6 +495,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               }
             }
           }
+          if (L.hot == 2 && L.mask_perm && L.mask_out && row_ok)
+            *reinterpret_cast<unsigned long long*>(L.mask_out + row * L.ldmask_out + 8 * j) = out_mask;
           // publish: generic-proxy writes of this warp -> visible to the tensor core / TMA (async proxy)
           ptx::fence_proxy_async();
           ptx::tc_fence_before();
@@ -514,6 +527,7 @@ static int chain_launch(ChainParams& P, cudaStream_t stream) {
   int stages = (int)((227 * 1024 - fixed - xbytes) / CH_WSTAGE_BYTES);
   if (stages > 8) stages = 8;
   NUNERF_REQUIRE(stages >= 2, "chain: input too wide for shared memory");
+  { const int s_env = env_int("NUNERF_CHAIN_STAGES", 0); if (s_env >= 2 && s_env < stages) stages = s_env; }   // experiments
   for (int l = 0; l < P.n_layers; ++l) P.layer[l].w_box_bytes = 128 * (P.layer[l].N < CH_WROWS ? P.layer[l].N : CH_WROWS);
   P.w_stages = stages;
   P.num_tiles = cdiv(P.M, 128);
@@ -543,6 +557,7 @@ static int chain_launch(ChainParams& P, cudaStream_t stream) {
   if (grid > num_sms()) grid = num_sms() / cluster * cluster;
   const int need = (num_pairs + cluster - 1) / cluster * cluster;
   if (grid > need) grid = need;
+  { const int g_env = env_int("NUNERF_CHAIN_GRID", 0); if (g_env >= cluster && g_env < grid) grid = g_env / cluster * cluster; }
   cfg.gridDim = dim3(grid);
   cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_chain_kernel, P);
   if (e != cudaSuccess) return fail("chain: cudaLaunchKernelEx: %s", cudaGetErrorString(e), -2);
@@ -621,6 +636,11 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
     if (plain && s.bias && s.act == 2 && !s.mask_in && !s.mask_out) L.hot = 1;
     else if (plain && s.bias && s.act == 1 && !s.mask_in) L.hot = 2;
     else if (plain && !s.bias && s.act == 0 && s.mask_in && !s.mask_out) L.hot = 3;
+    L.mask_perm = s.mask_perm;
+    if (s.mask_perm)
+      NUNERF_REQUIRE((L.hot == 2 || L.hot == 3) && ((s.mask_in ? s.ldmask_in : s.ldmask_out) % 8 == 0) &&
+                         (((uintptr_t)(s.mask_in ? (const void*)s.mask_in : (const void*)s.mask_out)) & 7) == 0,
+                     "mlp_chain: mask_perm needs a plain 256-wide ReLU layer and 8-byte aligned mask rows");
     if (s.mask_in) NUNERF_REQUIRE(s.ldmask_in >= s.N / 8, "mlp_chain: mask_in pitch");
     if (s.mask_out) NUNERF_REQUIRE(s.ldmask_out >= s.N / 8, "mlp_chain: mask_out pitch");
   }

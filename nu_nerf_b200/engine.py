@@ -262,9 +262,14 @@ def pred_forward(w: PredW, x: P, M, K0, planes):
     t.H = [P(M, 256, planes, dev) for _ in range(3)]
     t.Mk = [torch.empty(M, 32, dtype=torch.uint8, device=dev) for _ in range(3)]     # 1-bit ReLU masks
     t.head = _f(M, 16, dev=dev)
-    if _fused(planes):
+    t.fused = _fused(planes)
+    t.perm = [0, 0, 0]           # masks written by the chain kernel are in its thread order (mask_perm)
+    if t.fused:
         # one launch: hidden activations stay on the SM, each is written out once (dW needs it) with its ReLU mask
-        hidden = lambda i, K: dict(W=w.L[i].Wk, N=256, K=K, bias=w.L[i].b, act=1, mask_out=t.Mk[i], store=t.H[i], keep=1)
+        def hidden(i, K):
+            t.perm[i] = 1
+            return dict(W=w.L[i].Wk, N=256, K=K, bias=w.L[i].b, act=1, mask_out=t.Mk[i], store=t.H[i], keep=1,
+                        mask_perm=1)
         head = dict(W=w.L[3].Wk, N=16, K=256, bias=w.L[3].b, out32=t.head, n32=16)
         if K0 <= 256:
             chain(x, M, K0, [hidden(0, K0), hidden(1, 256), hidden(2, 256), head])
@@ -285,12 +290,12 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
     M, dev = t.M, t.x.t.device
     gW = [w.L[i].dW for i in range(4)]
     gb = [w.L[i].db for i in range(4)]
-    if _fused(planes):
+    if t.fused:
         # dX chain in one launch: dZ_l = (dZ_{l+1} W_{l+1}) . relu'(z_l), each dZ_l written once for its dW GEMM
         d2, d1, d0 = P(M, 256, planes, dev), P(M, 256, planes, dev), P(M, 256, planes, dev)
-        lays = [dict(W=w.L[3].WTk, N=256, K=64, mask_in=t.Mk[2], store=d2, keep=1),
-                dict(W=w.L[2].WTk, N=256, K=256, mask_in=t.Mk[1], store=d1, keep=1),
-                dict(W=w.L[1].WTk, N=256, K=256, mask_in=t.Mk[0], store=d0, keep=1)]
+        lays = [dict(W=w.L[3].WTk, N=256, K=64, mask_in=t.Mk[2], store=d2, keep=1, mask_perm=t.perm[2]),
+                dict(W=w.L[2].WTk, N=256, K=256, mask_in=t.Mk[1], store=d1, keep=1, mask_perm=t.perm[1]),
+                dict(W=w.L[1].WTk, N=256, K=256, mask_in=t.Mk[0], store=d0, keep=1, mask_perm=t.perm[0])]
         if dx_f32 is not None and dx_n % 16 == 0 and dx_n <= 256:
             lays.append(dict(W=w.L[0].WTk, N=dx_n, K=256, out32=dx_f32, n32=dx_n))
             dx_f32 = None

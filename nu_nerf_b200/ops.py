@@ -138,6 +138,7 @@ def chain(X: P, M, K0, layers, x_col=0, timeline=None):
         o32 = d.get("out32")
         L.out32, L.ldo32, L.n32 = (o32.data_ptr(), o32.stride(0), d.get("n32", d["N"])) if o32 is not None else (None, 0, 0)
         L.keep = int(d.get("keep", 0))
+        L.mask_perm = int(d.get("mask_perm", 0))
     a.timeline = ptr(timeline)
     call("nunerf_mlp_chain", C.byref(a))
 

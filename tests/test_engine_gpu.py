@@ -105,8 +105,11 @@ def test_fused_predictor_chain_matches_layerwise(M, name, K0):
                 eng.pred_backward(pw, t, dz, 1, dx_planes=dxp, dx_add=False, dx_n=256)
                 dx = dxp.t[:M, :256].float()
             torch.cuda.synchronize()
+            # masks written by the chain kernel are in its thread order: 2-byte word j*4 + c <-> standard word c*4 + j
+            Mk = [m.view(M, 4, 4, 2).transpose(1, 2).reshape(M, 32).clone() if t.perm[i] else m.clone()
+                  for i, m in enumerate(t.Mk)]
             res[fused] = dict(head=t.head[:, :pw.n_out].clone(), H=[h.t[:M].float().clone() for h in t.H],
-                              Mk=[m.clone() for m in t.Mk], dx=dx.clone(), g=w.bank.gflat.clone())
+                              Mk=Mk, dx=dx.clone(), g=w.bank.gflat.clone())
         finally:
             eng.FUSED_CHAINS = True
     a, b = res[False], res[True]

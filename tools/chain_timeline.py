@@ -31,6 +31,6 @@ for l in range(9):
 
 print("layer 5 detail: producer saw w_empty (tile, kb) | MMA: x_done seen, per kb: w_full seen -> issued")
 for tt in range(2):
-    print(f" tile{tt}: x_done seen {rel(t[420 + tt])}")
+    print(f" tile{tt}: x_done wait begins {rel(t[450 + tt])} seen {rel(t[420 + tt])}")
     for kb in range(4):
         print(f"   kb{kb}: producer w_empty seen {rel(t[400 + tt * 4 + kb]):7d} | w_full seen {rel(t[430 + (tt * 4 + kb) * 2]):7d} -> issued {rel(t[430 + (tt * 4 + kb) * 2 + 1]):7d}")
