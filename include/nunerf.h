@@ -92,12 +92,20 @@ typedef struct {
   void* store; int ld_store;                 /* optional bf16 [M, pad64(N)] copy of y (TMA store) */
   float* out32; int ldo32; int n32;          /* optional fp32 copy of the first n32 columns */
   int keep;                                  /* y becomes the next layer's input */
+  int cat_pe;                                /* columns [n_real, 256) <- PE-6 columns of the point (SDF skip concat) */
+  /* epilogues of the SDF network's reverse passes (plain 256-wide layers, no bias / act / masks), s = 1 - exp(-100 aux1):
+   *   aux_mode 4: y = acc . s      5: y = acc . s, e_out = acc . aux2 . 100 (1 - s)      6: y = acc . s + aux2 */
+  int aux_mode;
+  const void* aux1; int ld_aux1;             /* bf16 [M, 256] */
+  const void* aux2; int ld_aux2;
+  void* e_out; int ld_e;
   int mask_perm;                             /* plain 256-wide ReLU layers: the mask (in or out) is in the kernel's thread
                                                 order -- 2-byte word j*4 + c holds columns c*64 + j*16 .. +15 -- so that
                                                 each thread moves its 64 bits with one 8-byte access */
 } nunerf_chain_layer_t;
 typedef struct {
-  const void* x; int ldx; int K0;            /* bf16 [M, K0], K0 in {64,128,192,256} */
+  const void* x; int ldx; int K0;            /* bf16 [M, K0], K0 in {64,128,192,256}; or NULL: */
+  const float* pts;                          /* [M,3]: x_0 = PE-6(pts) computed in-kernel (also feeds cat_pe layers) */
   int M, n_layers;
   nunerf_chain_layer_t layer[NUNERF_CHAIN_MAX_LAYERS];
   void* timeline;                            /* NULL, or 512 int64 (device) clock64 stamps (development aid) */

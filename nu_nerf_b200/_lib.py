@@ -41,11 +41,12 @@ class SdfInferT(C.Structure):
 class ChainLayerT(C.Structure):
     _fields_ = [("w", vp), ("ldw", ci), ("N", ci), ("K", ci), ("n_real", ci), ("bias", vp), ("act", ci),
                 ("mask_out", vp), ("ldmask_out", ci), ("mask_in", vp), ("ldmask_in", ci), ("store", vp), ("ld_store", ci),
-                ("out32", vp), ("ldo32", ci), ("n32", ci), ("keep", ci), ("mask_perm", ci)]
+                ("out32", vp), ("ldo32", ci), ("n32", ci), ("keep", ci), ("cat_pe", ci), ("aux_mode", ci),
+                ("aux1", vp), ("ld_aux1", ci), ("aux2", vp), ("ld_aux2", ci), ("e_out", vp), ("ld_e", ci), ("mask_perm", ci)]
 
 
 class MlpChainT(C.Structure):
-    _fields_ = [("x", vp), ("ldx", ci), ("K0", ci), ("M", ci), ("n_layers", ci), ("layer", ChainLayerT * 10), ("timeline", vp)]
+    _fields_ = [("x", vp), ("ldx", ci), ("K0", ci), ("pts", vp), ("M", ci), ("n_layers", ci), ("layer", ChainLayerT * 10), ("timeline", vp)]
 
 
 class SdfAlphaT(C.Structure):

@@ -47,6 +47,13 @@ struct ChainLayer {
   int w_box_bytes;  // bytes of one weight TMA box: 128 B x min(128, N) rows
   int hot;          // plain 256-wide hidden layer with a specialised epilogue (ch_hot16 KIND 1..3), 0 = generic path
   const float* bias;
+  // aux epilogues of the SDF network's reverse passes (hot kinds 4..6, plain 256-wide layers without bias):
+  //   4: y = acc . s                      s = 1 - exp(-100 aux1)   (softplus'(z) from the stored activation)
+  //   5: y = acc . s ;  e_out = acc . aux2 . 100 (1 - s)           (reverse-over-reverse glue, field.cu sdf_bwd2_ew)
+  //   6: y = acc . s + aux2
+  const __nv_bfloat16* aux1; int ld_aux1;
+  const __nv_bfloat16* aux2; int ld_aux2;
+  __nv_bfloat16* e_out; int ld_e;
   int mask_perm;    // hot layers only: mask words in THREAD order -- byte j*8 + c*2 holds the 16 bits of columns
                     // c*64 + j*16 .. +15 (one 8-byte access per thread and tile instead of four 2-byte ones)
   uint8_t* mask_out; int ldmask_out;       // optional 1-bit (x > 0) mask, 32 bytes per row
@@ -121,6 +128,48 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
   }
   *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+}
+
+__device__ __forceinline__ void ch_unpack16(const uint4& a, const uint4& b, float* f) {
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { f[2 * i] = bf16lo_to_f(w[i]); f[2 * i + 1] = bf16hi_to_f(w[i]); }
+}
+
+// Aux epilogues (kinds 4..6, see ChainLayer): 16 columns of one row; a0/a1 = the 16 bf16 of aux1, b0/b1 of aux2.
+template <int KIND>
+__device__ __forceinline__ void ch_aux16(uint32_t taddr, const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1,
+                                         uint8_t* dst, int j, uint32_t sw, __nv_bfloat16* e_dst, bool row_ok) {
+  uint32_t v[16];
+  ptx::tmem_ld16(taddr, v);
+  float av[16], s[16];
+  ch_unpack16(a0, a1, av);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s[i] = 1.0f - __expf(-100.0f * av[i]);
+  float bv[16];
+  if (KIND >= 5) ch_unpack16(b0, b1, bv);
+  ptx::tmem_ld_wait();
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float acc = __uint_as_float(v[i]);
+    x[i] = acc * s[i];
+    if (KIND == 6) x[i] += bv[i];
+    if (KIND == 5) bv[i] = acc * bv[i] * 100.0f * (1.0f - s[i]);
+    if (!row_ok) x[i] = 0.0f;
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+  if (KIND == 5 && row_ok) {
+    uint32_t e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] = pack_bf16x2(bv[2 * i], bv[2 * i + 1]);
+    reinterpret_cast<uint4*>(e_dst)[0] = make_uint4(e[0], e[1], e[2], e[3]);
+    reinterpret_cast<uint4*>(e_dst)[1] = make_uint4(e[4], e[5], e[6], e[7]);
+  }
 }
 
 __device__ __forceinline__ void ch_tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
@@ -390,12 +439,44 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             if (!row_ok) hot_mask = 0ull;
           }
           unsigned long long out_mask = 0ull;
+          uint4 aux_a[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, aux_b[2] = {aux_a[0], aux_a[0]};
+          const long long aux_row = row_ok ? row : 0;
+          if (L.hot >= 4) {
+            const uint4* pa = reinterpret_cast<const uint4*>(L.aux1 + aux_row * L.ld_aux1 + j * 16);
+            aux_a[0] = __ldg(pa); aux_a[1] = __ldg(pa + 1);
+            if (L.hot >= 5) {
+              const uint4* pb = reinterpret_cast<const uint4*>(L.aux2 + aux_row * L.ld_aux2 + j * 16);
+              aux_b[0] = __ldg(pb); aux_b[1] = __ldg(pb + 1);
+            }
+          }
           // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier
           if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[t], (uint32_t)(g & 1));
           asm volatile("bar.sync 1, 512;" ::: "memory");
           ptx::tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2] = clock64();
           uint8_t* xt = sX + (size_t)(t * 4) * CH_BLOCK_BYTES;
+          if (L.hot >= 4) {
+            // aux operands stream from global memory one 64-column chunk ahead of their use (32 bytes per thread, row
+            // and chunk: whole sectors); the first chunk was requested before the accumulator wait
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int c0 = c * 64 + j * 16;
+              const uint4 a0 = aux_a[0], a1 = aux_a[1], b0 = aux_b[0], b1 = aux_b[1];
+              if (c < 3) {
+                const uint4* pa = reinterpret_cast<const uint4*>(L.aux1 + aux_row * L.ld_aux1 + c0 + 64);
+                aux_a[0] = __ldg(pa); aux_a[1] = __ldg(pa + 1);
+                if (L.hot >= 5) {
+                  const uint4* pb = reinterpret_cast<const uint4*>(L.aux2 + aux_row * L.ld_aux2 + c0 + 64);
+                  aux_b[0] = __ldg(pb); aux_b[1] = __ldg(pb + 1);
+                }
+              }
+              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c0);
+              uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
+              if (L.hot == 4) ch_aux16<4>(taddr, a0, a1, b0, b1, dst, j, sw, nullptr, row_ok);
+              else if (L.hot == 5) ch_aux16<5>(taddr, a0, a1, b0, b1, dst, j, sw, L.e_out + aux_row * L.ld_e + c0, row_ok);
+              else ch_aux16<6>(taddr, a0, a1, b0, b1, dst, j, sw, nullptr, row_ok);
+            }
+          } else
           for (int c = 0; c < 4; ++c) {
             const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
             if (L.hot) {
@@ -598,15 +679,22 @@ extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
 
 extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  NUNERF_REQUIRE(a && a->x && a->M > 0, "mlp_chain: bad arguments");
+  NUNERF_REQUIRE(a && (a->x || a->pts) && a->M > 0, "mlp_chain: bad arguments");
   NUNERF_REQUIRE(a->n_layers >= 1 && a->n_layers <= CH_MAXL, "mlp_chain: 1..NUNERF_CHAIN_MAX_LAYERS layers");
-  NUNERF_REQUIRE(a->K0 >= 64 && a->K0 % 64 == 0 && a->K0 <= 256 && a->ldx % 8 == 0 && a->ldx >= a->K0,
-                 "mlp_chain: input must be 64..256 columns (multiple of 64), pitch % 8 == 0");
   ChainParams P;
   memset(&P, 0, sizeof(P));
-  P.n_layers = a->n_layers; P.M = a->M; P.in_mode = 0; P.in_blocks = a->K0 / 64;
-  if (int r = make_map(&P.in_map, a->x, a->M, a->K0, a->ldx, 64, 128)) return r;
-  int width = a->K0;                 // valid (written) columns of the activation blocks
+  P.n_layers = a->n_layers; P.M = a->M;
+  int width;                         // valid (written) columns of the activation blocks
+  if (a->x) {
+    NUNERF_REQUIRE(a->K0 >= 64 && a->K0 % 64 == 0 && a->K0 <= 256 && a->ldx % 8 == 0 && a->ldx >= a->K0,
+                   "mlp_chain: input must be 64..256 columns (multiple of 64), pitch % 8 == 0");
+    P.in_mode = 0; P.in_blocks = a->K0 / 64;
+    if (int r = make_map(&P.in_map, a->x, a->M, a->K0, a->ldx, 64, 128)) return r;
+    width = a->K0;
+  } else {
+    P.in_mode = 1; P.in_blocks = 1; width = 64;      // x_0 = PE-6 of pts (39 columns, zero padded to 64), in-kernel
+  }
+  P.pts = a->pts;
   for (int l = 0; l < a->n_layers; ++l) {
     const nunerf_chain_layer_t& s = a->layer[l];
     ChainLayer& L = P.layer[l];
@@ -618,6 +706,11 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
     L.N = s.N; L.n_real = s.n_real > 0 ? s.n_real : s.N;
     L.kb0 = 0; L.nkb = s.K / 64;
     L.act = s.act; L.bias = s.bias;
+    L.cat_pe = s.cat_pe;
+    if (s.cat_pe) NUNERF_REQUIRE(a->pts && L.n_real < 256 && 256 - L.n_real <= 39, "mlp_chain: cat_pe needs pts and n_real >= 217");
+    L.aux1 = (const __nv_bfloat16*)s.aux1; L.ld_aux1 = s.ld_aux1;
+    L.aux2 = (const __nv_bfloat16*)s.aux2; L.ld_aux2 = s.ld_aux2;
+    L.e_out = (__nv_bfloat16*)s.e_out; L.ld_e = s.ld_e;
     L.mask_out = s.mask_out; L.ldmask_out = s.ldmask_out;
     L.mask_in = s.mask_in; L.ldmask_in = s.ldmask_in;
     L.out32 = s.out32; L.ldo32 = s.ldo32; L.n32 = s.n32;
@@ -626,16 +719,27 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
     (void)last;
     if (s.store) {
       NUNERF_REQUIRE(s.ld_store % 8 == 0 && s.ld_store >= s.N, "mlp_chain: bad store pitch");
-      const int cols = (s.N + 63) / 64 * 64 <= s.ld_store ? (s.N + 63) / 64 * 64 : s.N;
-      L.store_chunks = (s.N + 63) / 64;
+      const int wide = s.cat_pe ? 256 : (s.N + 63) / 64 * 64;
+      const int cols = wide <= s.ld_store ? wide : s.N;
+      L.store_chunks = wide / 64;
       if (int r = make_map(&P.out_map[l], s.store, a->M, cols, s.ld_store, 64, 128)) return r;
     }
-    if (L.to_x) width = (s.N + 63) / 64 * 64;        // a layer that keeps nothing leaves the previous activation in place
+    if (L.to_x) width = s.cat_pe ? 256 : (s.N + 63) / 64 * 64;   // a layer that keeps nothing leaves the previous activation
     // specialised epilogues
     const bool plain = s.N == 256 && L.n_real == 256 && L.to_x && !s.out32;
     if (plain && s.bias && s.act == 2 && !s.mask_in && !s.mask_out) L.hot = 1;
     else if (plain && s.bias && s.act == 1 && !s.mask_in) L.hot = 2;
     else if (plain && !s.bias && s.act == 0 && s.mask_in && !s.mask_out) L.hot = 3;
+    if (s.aux_mode) {
+      NUNERF_REQUIRE(s.aux_mode >= 4 && s.aux_mode <= 6, "mlp_chain: aux_mode must be 0 or 4..6");
+      NUNERF_REQUIRE(plain && !s.bias && s.act == 0 && !s.mask_in && !s.mask_out, "mlp_chain: aux layers are plain 256-wide");
+      NUNERF_REQUIRE(s.aux1 && s.ld_aux1 % 8 == 0 && ((uintptr_t)s.aux1 & 15) == 0, "mlp_chain: aux1 must be 16-byte aligned");
+      if (s.aux_mode >= 5)
+        NUNERF_REQUIRE(s.aux2 && s.ld_aux2 % 8 == 0 && ((uintptr_t)s.aux2 & 15) == 0, "mlp_chain: aux2 must be 16-byte aligned");
+      if (s.aux_mode == 5)
+        NUNERF_REQUIRE(s.e_out && s.ld_e % 8 == 0 && ((uintptr_t)s.e_out & 15) == 0, "mlp_chain: e_out must be 16-byte aligned");
+      L.hot = s.aux_mode;
+    }
     L.mask_perm = s.mask_perm;
     if (s.mask_perm)
       NUNERF_REQUIRE((L.hot == 2 || L.hot == 3) && ((s.mask_in ? s.ldmask_in : s.ldmask_out) % 8 == 0) &&

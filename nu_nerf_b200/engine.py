@@ -166,6 +166,10 @@ def sdf_forward(w: SdfWeights, pts, planes, xm: P):
     call("nunerf_encode_pe", pts.data_ptr(), M, 3, 6, t.x0.ptr, t.x0.ld, t.x0.lo, 0, 0, 64)
     A = [P(M, 256, planes, dev) for _ in range(8)]
     t.A = A
+    Gs = [P(M, 256, planes, dev) for _ in range(8)]
+    t.Gs = Gs
+    if _fused(planes):
+        return _sdf_forward_fused(w, t, xm)
     linear(t.x0, w.L[0].Wk, M, 256, 64, bias=w.L[0].b, act=2, out=A[0])
     linear(A[0], w.L[1].Wk, M, 256, 256, bias=w.L[1].b, act=2, out=A[1])
     linear(A[1], w.L[2].Wk, M, 256, 256, bias=w.L[2].b, act=2, out=A[2])
@@ -177,8 +181,6 @@ def sdf_forward(w: SdfWeights, pts, planes, xm: P):
     t.sdf = _f(M, 16, dev=dev)
     linear(A[7], w.sdf_head.Wk, M, 16, 256, bias=w.sdf_head.b, out_f32=t.sdf, n_store=1)
     # ---- adjoint pass: gs_l = d sdf / d z_l
-    Gs = [P(M, 256, planes, dev) for _ in range(8)]
-    t.Gs = Gs
     call("nunerf_rowvec_mask", w.w_sdf.data_ptr(), A[7].ptr, A[7].ld, A[7].lo, M, 256, Gs[7].ptr, Gs[7].ld, Gs[7].lo)
     for l in (7, 6, 5):
         linear(Gs[l], w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, out=Gs[l - 1])
@@ -196,6 +198,36 @@ def sdf_forward(w: SdfWeights, pts, planes, xm: P):
     return t
 
 
+def _sdf_forward_fused(w: SdfWeights, t: SdfTape, xm: P):
+    """bf16 mode: the value pass is ONE launch (PE in-kernel, every activation written once for the backward), the adjoint
+    pass two (the softplus' factors come from the stored activations in the epilogue: chain aux_mode 4)."""
+    M, dev, pts, A, Gs = t.M, t.pts.device, t.pts, t.A, t.Gs
+    t.sdf = _f(M, 16, dev=dev)
+    lays = []
+    for l in range(8):
+        d = dict(W=w.L[l].Wk, N=256, K=64 if l == 0 else 256, bias=w.L[l].b, act=2, store=A[l], keep=1)
+        if l == 3:
+            d.update(N=224, n_real=217, cat_pe=1)          # A[3] = [a3 | PE]; lin4 carries the 1/sqrt(2)
+        lays.append(d)
+    lays.append(dict(W=w.sdf_head.Wk, N=16, K=256, bias=w.sdf_head.b, out32=t.sdf, n32=16))
+    lays.append(dict(W=w.feat.Wk, N=256, K=256, bias=w.feat.b, store=xm))
+    chain(None, M, 64, lays, pts=pts)
+    # ---- adjoint pass: gs_l = d sdf / d z_l
+    call("nunerf_rowvec_mask", w.w_sdf.data_ptr(), A[7].ptr, A[7].ld, A[7].lo, M, 256, Gs[7].ptr, Gs[7].ld, Gs[7].lo)
+    u4 = _f(M, 256, dev=dev)
+    chain(Gs[7], M, 256, [dict(W=w.L[l].WTk, N=256, K=256, aux_mode=4, aux1=A[l - 1], store=Gs[l - 1], keep=1)
+                          for l in (7, 6, 5)] + [dict(W=w.L[4].WTk, N=256, K=256, out32=u4, n32=256)])
+    t.g_skip = _f(M, 39, dev=dev)
+    call("nunerf_sdf_skip_split", u4.data_ptr(), A[3].ptr, A[3].ld, A[3].lo, M, Gs[3].ptr, Gs[3].ld, Gs[3].lo,
+         t.g_skip.data_ptr())
+    u0 = _f(M, 64, dev=dev)
+    chain(Gs[3], M, 256, [dict(W=w.L[l].WTk, N=256, K=256, aux_mode=4, aux1=A[l - 1], store=Gs[l - 1], keep=1)
+                          for l in (3, 2, 1)] + [dict(W=w.L[0].WTk, N=64, K=256, out32=u0, n32=64)])
+    t.grad = _f(M, 3, dev=dev)
+    call("nunerf_sdf_grad_pe", pts.data_ptr(), u0.data_ptr(), 64, t.g_skip.data_ptr(), 39, M, t.grad.data_ptr())
+    return t
+
+
 def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
     """Backward of sdf_forward.  dxm[:, 0:256] holds d feat (planes); d_sdf [M], d_grad [M,3] fp32.
     Weight / bias gradients accumulate in the Dense objects (w.L[l].dW / .db, w.feat, w.sdf_head)."""
@@ -203,6 +235,8 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
     A, Gs = t.A, t.Gs
     dW = [w.L[l].dW for l in range(8)]
     db = [w.L[l].db for l in range(8)]
+    if _fused(planes):
+        return _sdf_backward_fused(w, t, dxm, d_sdf, d_grad)
     # ---- (a) reverse of the adjoint pass (forward-like chain on u~), produces E_l and the gs (x) u~ weight terms
     E = [P(M, 256, planes, dev) for _ in range(8)]
     ut = P(M, 64, planes, dev)
@@ -248,6 +282,49 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
             linear(cur, w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, add=E[l - 1], out=other)
             cur, other = other, cur
     linear_dw(cur, t.x0, M, 256, 64, dW[0], db=db[0])
+
+
+def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad):
+    """bf16 mode: both reverse passes as fused chains (csrc/chain.cu aux_mode 5 / 6) -- the products gts_l and the
+    intermediate dZ never round-trip through HBM between the GEMM and its element-wise glue; every u~_l / dZ_l is written
+    once for its weight-gradient GEMM.  The two 217-wide layers around the skip concat keep the layer-by-layer path."""
+    M, dev, planes = t.M, t.pts.device, 1
+    A, Gs = t.A, t.Gs
+    dW = [w.L[l].dW for l in range(8)]
+    db = [w.L[l].db for l in range(8)]
+    E = [P(M, 256, planes, dev) for _ in range(8)]
+    U = [P(M, 256, planes, dev) for _ in range(8)]      # U[l] = u~_{l+1}: output of layer l of pass (a); U[3] = u~ cat
+    ut = P(M, 64, planes, dev)
+    call("nunerf_sdf_grad_pe_bwd", t.pts.data_ptr(), d_grad.data_ptr(), M, ut.ptr, ut.ld, ut.lo, 0, 64,
+         U[3].ptr, U[3].ld, U[3].lo, 217, 39)
+    # ---- (a) u~ chain: gts_l = u~_l W_l^T ; u~_{l+1} = gts_l . s_l ; E_l = gts_l . gs_l . 100 (1 - s_l)
+    ew5 = lambda l, K: dict(W=w.L[l].Wk, N=256, K=K, aux_mode=5, aux1=A[l], aux2=Gs[l], e_out=E[l], store=U[l], keep=1)
+    chain(ut, M, 64, [ew5(0, 64), ew5(1, 256), ew5(2, 256)])
+    gts = P(M, 256, planes, dev)
+    linear(U[2], w.L[3].Wk, M, 224, 256, out=gts)
+    call("nunerf_sdf_bwd2_ew", gts.ptr, gts.ld, gts.lo, A[3].ptr, A[3].ld, A[3].lo, Gs[3].ptr, Gs[3].ld, Gs[3].lo,
+         M, 256, 217, U[3].ptr, U[3].ld, U[3].lo, E[3].ptr, E[3].ld, E[3].lo)
+    chain(U[3], M, 256, [ew5(l, 256) for l in (4, 5, 6, 7)])
+    u_in, K_in = ut, 64
+    for l in range(8):
+        linear_dw(Gs[l], u_in, M, 217 if l == 3 else 256, K_in, dW[l])
+        u_in, K_in = U[l], 256
+    colsum(U[7], M, 256, w.sdf_head.dW[0])               # d w_sdf += sum_m gts_7 . s_7
+    # ---- (b) backward of the value network; dZ8 = [d feat (256) | d sdf | 0...]
+    f32_to_planes(d_sdf, dxm, M, 1, 64, col=256)
+    linear_dw(dxm, A[7], M, 256, 256, w.feat.dW, db=w.feat.db)
+    linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256, db=w.sdf_head.db)
+    DZ = [P(M, 256, planes, dev) for _ in range(8)]      # DZ[l] = d loss / d z_l
+    DZ[3] = P(M, 256, planes, dev, zero=True)
+    linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=DZ[7])
+    ew6 = lambda l: dict(W=w.L[l].WTk, N=256, K=256, aux_mode=6, aux1=A[l - 1], aux2=E[l - 1], store=DZ[l - 1], keep=1)
+    chain(DZ[7], M, 256, [ew6(7), ew6(6), ew6(5)])
+    # input of lin4 is [a3 | PE]: only the first 217 columns carry on (PE has no parameters upstream)
+    linear(DZ[4], w.L[4].WTk, M, 224, 256, aux=A[3], aux_mode=2, add=E[3], out=DZ[3], n_store=217)
+    chain(DZ[3], M, 256, [ew6(3), ew6(2), ew6(1)])
+    for l in range(7, 0, -1):
+        linear_dw(DZ[l], A[l - 1], M, 217 if l == 3 else 256, 256, dW[l], db=db[l])
+    linear_dw(DZ[0], t.x0, M, 256, 64, dW[0], db=db[0])
 
 
 # =============================================================================================== predictors

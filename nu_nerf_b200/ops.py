@@ -115,13 +115,17 @@ def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = 
         call("nunerf_linear", C.byref(p))
 
 
-def chain(X: P, M, K0, layers, x_col=0, timeline=None):
+def chain(X, M, K0, layers, x_col=0, timeline=None, pts=None):
     """Fused chain of dense layers (csrc/chain.cu, bf16 single-plane operands): `layers` is a list of dicts with keys
     W (P, K-major weight), N, K and optionally n_real, bias, act, mask_out, mask_in, store (P) / store_col, out32, n32,
     keep.  See nunerf_mlp_chain_t in include/nunerf.h."""
-    assert X.planes == 1 and len(layers) <= 10
+    assert len(layers) <= 10
     a = _lib.MlpChainT()
-    a.x, a.ldx, a.K0, a.M, a.n_layers = X.at(0, x_col), X.ld, K0, M, len(layers)
+    if X is not None:
+        assert X.planes == 1
+        a.x, a.ldx, a.K0 = X.at(0, x_col), X.ld, K0
+    a.pts = ptr(pts)
+    a.M, a.n_layers = M, len(layers)
     for l, d in enumerate(layers):
         L = a.layer[l]
         W = d["W"]
@@ -139,6 +143,13 @@ def chain(X: P, M, K0, layers, x_col=0, timeline=None):
         L.out32, L.ldo32, L.n32 = (o32.data_ptr(), o32.stride(0), d.get("n32", d["N"])) if o32 is not None else (None, 0, 0)
         L.keep = int(d.get("keep", 0))
         L.mask_perm = int(d.get("mask_perm", 0))
+        L.cat_pe, L.aux_mode = int(d.get("cat_pe", 0)), int(d.get("aux_mode", 0))
+        for k_, f_, l_ in (("aux1", "aux1", "ld_aux1"), ("aux2", "aux2", "ld_aux2"), ("e_out", "e_out", "ld_e")):
+            pl = d.get(k_)
+            if pl is not None:
+                assert pl.planes == 1
+                setattr(L, f_, pl.ptr)
+                setattr(L, l_, pl.ld)
     a.timeline = ptr(timeline)
     call("nunerf_mlp_chain", C.byref(a))
 

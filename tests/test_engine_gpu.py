@@ -126,6 +126,48 @@ def test_fused_predictor_chain_matches_layerwise(M, name, K0):
     assert (a["g"] - b["g"]).abs().max().item() < 5e-3 * gs
 
 
+@pytest.mark.parametrize("M", [300, 148 * 256 + 77])
+def test_fused_sdf_training_chains_match_layerwise(M):
+    """SDFNetwork forward + gradient (field.py:133-170) and their backward as fused chains (value pass with in-kernel
+    PE, adjoint pass with the softplus' epilogue, both reverse passes with the aux_mode 5 / 6 epilogues) against the
+    layer-by-layer bf16 path: same operands and rounding points up to fp32 accumulation order."""
+    from nu_nerf_b200 import engine as eng
+    net = _renderer("bf16")
+    w = net._prepare()
+    g = torch.Generator().manual_seed(M)
+    pts = (torch.rand(M, 3, generator=g) * 1.6 - 0.8).to(DEV).contiguous()
+    dfeat = (torch.randn(M, 256, generator=g) * 1e-2).to(DEV)
+    d_sdf = torch.randn(M, generator=g).to(DEV)
+    d_grad = torch.randn(M, 3, generator=g).to(DEV).contiguous()
+    res = {}
+    for fused in (False, True):
+        eng.FUSED_CHAINS = fused
+        try:
+            w.bank.zero_grads()
+            xm = eng.P(M, 320, 1, DEV, zero=True)
+            t = eng.sdf_forward(w.sdf, pts, 1, xm)
+            fwd = dict(sdf=t.sdf[:, 0].clone(), grad=t.grad.clone(), feat=xm.t[:M, :256].float().clone(),
+                       A=[a.t[:M].float().clone() for a in t.A], Gs=[a.t[:M].float().clone() for a in t.Gs])
+            dxm = eng.P(M, 320, 1, DEV, zero=True)
+            dxm.t[:M, :256] = dfeat.to(torch.bfloat16)
+            eng.sdf_backward(w.sdf, t, 1, dxm, d_sdf, d_grad)
+            torch.cuda.synchronize()
+            fwd["g"] = w.bank.gflat.clone()
+            res[fused] = fwd
+        finally:
+            eng.FUSED_CHAINS = True
+    a, b = res[False], res[True]
+    rel = lambda x, y: (x - y).abs().max().item() / max(x.abs().max().item(), 1e-6)
+    assert torch.isfinite(b["sdf"]).all() and torch.isfinite(b["g"]).all()
+    assert (a["sdf"] - b["sdf"]).abs().max().item() < 2e-4
+    assert rel(a["feat"], b["feat"]) < 1e-2
+    assert rel(a["grad"], b["grad"]) < 1e-2
+    for l in range(8):
+        assert rel(a["A"][l], b["A"][l]) < 2e-2, ("A", l, rel(a["A"][l], b["A"][l]))
+        assert rel(a["Gs"][l], b["Gs"][l]) < 2e-2, ("Gs", l, rel(a["Gs"][l], b["Gs"][l]))
+    assert rel(a["g"], b["g"]) < 1e-2, rel(a["g"], b["g"])
+
+
 def _run_core(net, o, d, z, gt, cos_anneal, step):
     net.zero_grad()
     out = net.render_core(o.to(DEV), d.to(DEV), z.to(DEV), None, cos_anneal_ratio=cos_anneal, step=step, is_train=True,
