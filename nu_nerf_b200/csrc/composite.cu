@@ -7,7 +7,6 @@ namespace nunerf {
 
 constexpr int WPB = 4;
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int MAX_BLK = 8;  // S <= 256
 
 __device__ __forceinline__ float scan_mul32(float x, int lane) {
 #pragma unroll
@@ -184,7 +183,11 @@ __global__ void composite_fwd_kernel(const float* __restrict__ a_in, const float
 }
 
 // d_alpha_i = g_i T_i - (sum_{k>i} g_k w_k) / (1 - a_i + eps),  g_k = d_rgb . c_k + d_acc - [is_nerf] sum(d_rgb)
-__global__ void composite_bwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
+// NBLK = ceil(S / 32) blocks of 32 samples are kept in registers between the forward and the reverse pass: the kernel is
+// instantiated for the product's S = 160 (5 blocks) and for the general S <= 256 (8 blocks) so that the common case does
+// not pay the register footprint (and the occupancy) of the largest one.
+template <int NBLK>
+__global__ void __launch_bounds__(32 * WPB) composite_bwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
                                      const float* __restrict__ a_out, const float* __restrict__ c_out,
                                      const int32_t* __restrict__ slot, int R, int S, int is_nerf,
                                      const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb,
@@ -204,11 +207,11 @@ __global__ void composite_bwd_kernel(const float* __restrict__ a_in, const float
         h2 = d_rgb_b ? d_rgb_b[3 * r + 2] : 0.f;
   const int nblk = (S + 31) >> 5;
   // pass 1 (forward): T per sample, kept in registers (S <= 256)
-  float T[MAX_BLK], Tb[MAX_BLK], gw[MAX_BLK], gwb[MAX_BLK], va[MAX_BLK], vab[MAX_BLK], gk[MAX_BLK], gkb[MAX_BLK];
-  int sl[MAX_BLK];
+  float T[NBLK], Tb[NBLK], gw[NBLK], gwb[NBLK], va[NBLK], vab[NBLK], gk[NBLK], gkb[NBLK];
+  int sl[NBLK];
   float carry = 1.f, carry_b = 1.f;
 #pragma unroll
-  for (int k = 0; k < MAX_BLK; ++k) {
+  for (int k = 0; k < NBLK; ++k) {
     if (k < nblk) {
       int s = k * 32 + lane;
       bool ok = s < S;
@@ -238,7 +241,7 @@ __global__ void composite_bwd_kernel(const float* __restrict__ a_in, const float
   // pass 2 (reverse): exclusive suffix sums of g*w
   float suf = 0.f, suf_b = 0.f;
 #pragma unroll
-  for (int k = MAX_BLK - 1; k >= 0; --k) {
+  for (int k = NBLK - 1; k >= 0; --k) {
     if (k < nblk) {
       int s = k * 32 + lane;
       bool ok = s < S;
@@ -307,10 +310,14 @@ extern "C" int nunerf_composite_bwd(const float* alpha_in, const float* color_in
                                     float* d_color_out, void* stream) {
   NUNERF_REQUIRE(slot && rgb_raw && d_alpha_in && d_color_in && d_alpha_out && d_color_out && R > 0 && S > 0 && S <= 256,
                  "composite_bwd: bad arguments");
-  composite_bwd_kernel<<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(alpha_in, color_in, alpha_out, color_out,
-                                                                          slot, R, S, is_nerf, rgb_raw, d_rgb, d_acc,
-                                                                          d_rgb_bkgr, d_alpha_in, d_color_in,
-                                                                          d_alpha_out, d_color_out);
+  if (S <= 160)
+    composite_bwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
+        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
+        d_color_in, d_alpha_out, d_color_out);
+  else
+    composite_bwd_kernel<8><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
+        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
+        d_color_in, d_alpha_out, d_color_out);
   NUNERF_CHECK_LAUNCH("composite_bwd_kernel");
   return 0;
 }

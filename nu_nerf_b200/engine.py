@@ -417,15 +417,27 @@ def nerf_forward(w: NerfW, pts, dirs, dists, planes):
     call("nunerf_encode_pe", pts4.data_ptr(), M, 4, 10, H[4].ptr, H[4].ld, H[4].lo, 256, 0, 128)
     t.Mk = [torch.empty(M, 32, dtype=torch.uint8, device=dev) for _ in range(8)]
     t.Mv = torch.empty(M, 16, dtype=torch.uint8, device=dev)
-    linear(t.x0, w.pts[0].Wk, M, 256, 128, bias=w.pts[0].b, act=1, out=H[0], mask_out=t.Mk[0])
-    for i in range(1, 8):
-        K = 384 if i == 5 else 256
-        linear(H[i - 1], w.pts[i].Wk, M, 256, K, bias=w.pts[i].b, act=1, out=H[i], mask_out=t.Mk[i])
     t.xv = P(M, 320, planes, dev)                 # [feature | PE4(view) (27) | 0]
-    linear(H[7], w.feat.Wk, M, 256, 256, bias=w.feat.b, out=t.xv)
-    call("nunerf_encode_pe", views.data_ptr(), M, 3, 4, t.xv.ptr, t.xv.ld, t.xv.lo, 256, 0, 64)
     t.sigma = _f(M, 16, dev=dev)
-    linear(H[7], w.alpha.Wk, M, 16, 256, bias=w.alpha.b, out_f32=t.sigma, n_store=1)
+    t.perm = [0] * 8                              # masks written by the chain kernel are in its thread order
+    if _fused(planes):
+        def hid(i, K):
+            t.perm[i] = 0 if i == 7 else 1        # Mk[7] is consumed by the layer kernel (K = 320 backward input)
+            return dict(W=w.pts[i].Wk, N=256, K=K, bias=w.pts[i].b, act=1, mask_out=t.Mk[i], store=H[i], keep=1,
+                        mask_perm=t.perm[i])
+        chain(t.x0, M, 128, [hid(0, 128)] + [hid(i, 256) for i in range(1, 5)])
+        linear(H[4], w.pts[5].Wk, M, 256, 384, bias=w.pts[5].b, act=1, out=H[5], mask_out=t.Mk[5])     # [h4 | PE]: K = 384
+        chain(H[5], M, 256, [hid(6, 256), hid(7, 256),
+                             dict(W=w.alpha.Wk, N=16, K=256, bias=w.alpha.b, out32=t.sigma, n32=16),
+                             dict(W=w.feat.Wk, N=256, K=256, bias=w.feat.b, store=t.xv)])
+    else:
+        linear(t.x0, w.pts[0].Wk, M, 256, 128, bias=w.pts[0].b, act=1, out=H[0], mask_out=t.Mk[0])
+        for i in range(1, 8):
+            K = 384 if i == 5 else 256
+            linear(H[i - 1], w.pts[i].Wk, M, 256, K, bias=w.pts[i].b, act=1, out=H[i], mask_out=t.Mk[i])
+        linear(H[7], w.feat.Wk, M, 256, 256, bias=w.feat.b, out=t.xv)
+        linear(H[7], w.alpha.Wk, M, 16, 256, bias=w.alpha.b, out_f32=t.sigma, n_store=1)
+    call("nunerf_encode_pe", views.data_ptr(), M, 3, 4, t.xv.ptr, t.xv.ld, t.xv.lo, 256, 0, 64)
     t.hv = P(M, 128, planes, dev)
     linear(t.xv, w.views.Wk, M, 128, 320, bias=w.views.b, act=1, out=t.hv, mask_out=t.Mv)
     t.rgb = _f(M, 16, dev=dev)
@@ -450,6 +462,16 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
     linear(dzv, w.views.WTk, M, 256, 128, out=dz8)                       # d feature -> dz8[:, :256]
     linear_dw(dz8, H[7], M, 256, 256, w.feat.dW, db=w.feat.db)
     linear_dw(dz8, H[7], M, 1, 256, w.alpha.dW, z_col=256, db=w.alpha.db)
+    if _fused(planes) and t.perm[0]:
+        # dZ_7 by the layer kernel (K = 320 input), then the whole dX chain of the 8 x 256 trunk in one launch
+        DZ = [P(M, 256, planes, dev) for _ in range(8)]
+        linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=DZ[7])
+        chain(DZ[7], M, 256, [dict(W=w.pts[i].WTk, N=256, K=256, mask_in=t.Mk[i - 1], mask_perm=t.perm[i - 1],
+                                   store=DZ[i - 1], keep=1) for i in range(7, 0, -1)])
+        for i in range(7, 0, -1):
+            linear_dw(DZ[i], H[i - 1], M, 256, 384 if i == 5 else 256, w.pts[i].dW, db=w.pts[i].db)
+        linear_dw(DZ[0], t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
+        return
     cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
     linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
     for i in range(7, 0, -1):

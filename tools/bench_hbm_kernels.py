@@ -1,0 +1,109 @@
+"""The HBM-bound kernels of the path at config-3 size (32 768 rays per GPU): ray set-up, the four up-sample rounds,
+points, sdf merge, render geometry + compaction, compositing forward / backward, and the BVH closest-hit trace
+(1 Mi rays, ~100k-triangle mesh).  CUDA-event time per launch and achieved algorithmic GB/s (byte model of bench.py
+`hbm_work`, SURVEY 8d conventions) against the measured HBM peak.  `python tools/bench_hbm_kernels.py once` launches
+every kernel a few times only (for `ncu --set full` captures)."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench  # noqa: E402
+from nu_nerf_b200 import engine as eng, ops  # noqa: E402
+from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg  # noqa: E402
+from conftest import uv_sphere  # noqa: E402
+from oracle import nunerf_oracle as orc  # noqa: E402  (seeded synthetic ray generator only)
+
+
+def main():
+    once = len(sys.argv) > 1 and sys.argv[1] == "once"
+    R = 32768
+    dev = "cuda"
+    cfg = load_default_cfg()
+    cfg["precision"] = "bf16"
+    torch.manual_seed(0)
+    net = NeROShapeRenderer(cfg, training=False).cuda()
+    w = net._prepare()
+    o, d = (t.cuda() for t in orc.synthetic_rays(R))
+    near, far = torch.full((R, 1), 0.8, device=dev), torch.full((R, 1), 4.5, device=dev)
+    rec = {}
+    orig = eng.call
+
+    def timed(name, *a):
+        nb = bench.hbm_work(name, a)
+        if not nb:
+            return orig(name, *a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *a)
+        e1.record()
+        key = name if name != "nunerf_upsample" else f"nunerf_upsample n={a[5]}"
+        rec.setdefault(key, []).append((e0, e1, nb))
+    eng.call = timed
+    iters = 2 if once else 12
+    try:
+        for it in range(iters):
+            with torch.no_grad():
+                z = net.sample_ray(o, d, near, far, 1.0, prepared=w)
+            # geometry + compaction, then compositing forward / backward on synthetic alpha / colour
+            R_, S = z.shape
+            i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+            f = lambda *s: torch.empty(*s, device=dev)
+            dists, pts = f(R, S), f(R, S, 3)
+            slot, counts, scratch = i32(R, S), i32(2), i32(2 * R)
+            cap = R * S
+            bufs = [f(cap, 3), f(cap), f(cap, 3), i32(cap), f(cap, 3), f(cap), f(cap, 3), i32(cap)]
+            eng.call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, dists.data_ptr(),
+                     pts.data_ptr(), slot.data_ptr(), counts.data_ptr(), scratch.data_ptr(), *[b.data_ptr() for b in bufs])
+            n_in, n_out = (int(v) for v in counts.tolist())
+            a_in, c_in = torch.rand(n_in, device=dev) * 0.1, torch.rand(n_in, 3, device=dev)
+            a_out, c_out = torch.rand(n_out, device=dev) * 0.05, torch.rand(n_out, 3, device=dev)
+            rgb, raw, acc, bk, wts = f(R, 3), f(R, 3), f(R), f(R, 3), f(R, S)
+            eng.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+                     slot.data_ptr(), R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), wts.data_ptr())
+            d_rgb, d_acc, d_bk = torch.randn(R, 3, device=dev), torch.randn(R, device=dev), torch.randn(R, 3, device=dev)
+            da_in, dc_in, da_out, dc_out = f(n_in), f(n_in, 3), f(n_out), f(n_out, 3)
+            eng.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+                     slot.data_ptr(), R, S, 1, raw.data_ptr(), d_rgb.data_ptr(), d_acc.data_ptr(), d_bk.data_ptr(),
+                     da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
+        torch.cuda.synchronize()
+    finally:
+        eng.call = orig
+    # BVH closest hit: 1 Mi rays against the ~100k-triangle UV sphere
+    from nu_nerf_b200.tracer import optix_mesh
+    V, Fc = uv_sphere(0.6, 224, 224)
+    om = optix_mesh()
+    om.update_mesh(torch.from_numpy(Fc).int().cuda(), torch.from_numpy(V).float().cuda())
+    Rt = 1 << 20
+    ot = 3.0 * torch.nn.functional.normalize(torch.randn(Rt, 3, device=dev), dim=-1)
+    dt = torch.nn.functional.normalize(-ot + 0.3 * torch.randn(Rt, 3, device=dev), dim=-1)
+    ev = []
+    for it in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        om.bvh.trace(ot, dt)
+        e1.record()
+        ev.append((e0, e1, 32.0 * Rt))
+    torch.cuda.synchronize()
+    rec["nunerf_bvh_trace (1Mi rays, 99 904 triangles)"] = ev
+    if once:
+        print("ok")
+        return
+    hbm = bench.peaks()[0]
+    out = {"rays": R, "hbm_peak_gbs": hbm, "kernels": {}}
+    for k, lst in rec.items():
+        lst = lst[len(lst) // 3:]                      # drop warm-up launches
+        per_iter = len(lst)
+        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in lst) / per_iter
+        nb = sum(b for *_, b in lst) / per_iter
+        out["kernels"][k] = {"us_per_launch": ms * 1e3, "algorithmic_bytes": nb, "GBs": nb / ms / 1e6,
+                             "frac_of_hbm_peak": nb / ms / 1e6 / hbm}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

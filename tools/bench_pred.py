@@ -18,6 +18,19 @@ def main():
     net = NeROShapeRenderer(cfg, training=False).cuda()
     w = net._prepare()
     pw = w.pred["outer_light"]
+    if len(sys.argv) > 1 and sys.argv[1] == "once":          # two launches only (ncu --set full captures)
+        M = 383_000
+        x = eng.P(M, 128, 1, "cuda", zero=True)
+        x.t[:, :72] = torch.randn(M, 72, device="cuda").to(torch.bfloat16)
+        dz = eng.P(M, 64, 1, "cuda", zero=True)
+        dz.t[:, :3] = torch.randn(M, 3, device="cuda").to(torch.bfloat16)
+        dx = torch.empty(M, 128, device="cuda")
+        for _ in range(2):
+            t = eng.pred_forward(pw, x, M, 128, 1)
+            eng.pred_backward(pw, t, dz, 1, dx_f32=dx, dx_n=128)
+        torch.cuda.synchronize()
+        print("ok")
+        return
     for M in (383_000, 3 * 383_000):
         x = eng.P(M, 128, 1, "cuda", zero=True)
         x.t[:, :72] = torch.randn(M, 72, device="cuda").to(torch.bfloat16)
