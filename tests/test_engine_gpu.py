@@ -367,3 +367,29 @@ def test_eval_outputs_depth_normal():
     assert (out["depth"].cpu() - depth).abs().max().item() < 1e-4
     assert (out["normal"].cpu() - normal).abs().max().item() < 1e-4
     assert (out["ray_rgb"].cpu() - ref["ray_rgb"]).abs().max().item() < 1e-4
+
+
+def test_forward_with_device_ray_feeder():
+    """forward(data) of the boundary class fed by the HBM-resident ray table (nu_nerf_b200/feeder.py): no per-step host
+    work; the outputs dict carries what network/loss.py reads."""
+    from nu_nerf_b200 import feeder
+    from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
+    torch.manual_seed(0)
+    cfg = load_default_cfg()
+    cfg.update(precision="bf16", train_ray_num=256, is_nerf=True)
+    net = NeROShapeRenderer(cfg, training=False).cuda()
+    g = torch.Generator().manual_seed(1)
+    imn, h, w = 2, 24, 32
+    imgs = torch.rand(imn, 3, h, w, generator=g).cuda()
+    Ks = torch.tensor([[40.0, 0, 16.0], [0, 40.0, 12.0], [0, 0, 1]]).repeat(imn, 1, 1).cuda()
+    poses = torch.eye(3, 4)[None].repeat(imn, 1, 1)
+    poses[:, 2, 3] = 3.0                                   # cameras on +z looking down -z (OpenGL axes)
+    poses[1, 0, 3] = 0.5
+    batch, rn, _, _ = feeder.construct_nerf_ray_batch(imgs, Ks, poses.cuda())
+    assert batch["rays_o"].is_cuda and rn == imn * h * w
+    net.set_ray_source(feeder.DeviceRayFeeder(batch, seed=0))
+    out = net({"step": 10000})
+    assert out["ray_rgb"].shape == (256, 3) and out["loss_rgb"].shape == (256,)
+    loss = out["loss_rgb"].mean() + (0.1 * out["gradient_error"]).mean()
+    loss.backward()
+    assert torch.isfinite(loss) and net.sdf_network.lin0.weight_v.grad is not None

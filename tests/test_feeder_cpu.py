@@ -1,0 +1,67 @@
+"""Device-side ray feeder (nu_nerf_b200/feeder.py) against the UNMODIFIED reference's ray-table code
+(tests/golden/feeder.npz, made by tests/golden/make_golden_feeder.py): ray construction for both dataset conventions,
+the shuffle (same CPU generator draw as ZT:195), training slices, reshuffle rule and the data-parallel sharding.
+Runs on CPU tensors (the feeder is device-agnostic torch indexing); on the GPU box the same code keeps the table in HBM."""
+import os
+
+import numpy as np
+import torch
+
+from conftest import GOLDEN
+
+
+def _g():
+    G = np.load(os.path.join(GOLDEN, "feeder.npz"))
+    return {k: torch.from_numpy(G[k]) for k in G.files}
+
+
+def test_nerf_ray_table_matches_reference():
+    from nu_nerf_b200 import feeder
+    G = _g()
+    batch, rn, h, w = feeder.construct_nerf_ray_batch(G["imgs"], G["Ks"], G["poses"], G["masks"])
+    assert (rn, h, w) == (60, 4, 5)
+    for k in ("rgbs", "idxs", "masks"):
+        assert torch.equal(batch[k], G["nerf_" + k]), k
+    for k in ("rays_o", "rays_d"):
+        assert (batch[k] - G["nerf_" + k]).abs().max().item() < 1e-6, k
+
+
+def test_plain_ray_table_and_world_rays_match_reference():
+    from nu_nerf_b200 import feeder
+    G = _g()
+    batch, rn, _, _ = feeder.construct_ray_batch(G["imgs"], G["Ks"])
+    assert torch.equal(batch["idxs"], G["plain_idxs"]) and torch.equal(batch["rgbs"], G["plain_rgbs"])
+    assert (batch["dirs"] - G["plain_dirs"]).abs().max().item() < 1e-6
+    ro, rd = feeder.world_rays(batch["dirs"], batch["idxs"], G["poses"])
+    assert (ro - G["plain_rays_o"]).abs().max().item() < 1e-6
+    assert (rd - G["plain_rays_d"]).abs().max().item() < 1e-6
+
+
+def test_shuffle_and_slices_match_reference():
+    from nu_nerf_b200 import feeder
+    G = _g()
+    batch, rn, _, _ = feeder.construct_nerf_ray_batch(G["imgs"], G["Ks"], G["poses"], G["masks"])
+    f = feeder.DeviceRayFeeder(batch, seed=7, perm_device="cpu")       # the reference's torch.manual_seed(7); randperm
+    assert torch.equal(f.perm, G["perm"])
+    b0 = f(0, 8)
+    b1 = f(1, 8)
+    assert torch.equal(b0["rays_o"], G["slice0_rays_o"]) and torch.equal(b1["rgbs"], G["slice1_rgbs"])
+    assert set(b0) == {"rgbs", "idxs", "rays_o", "rays_d", "masks"}
+
+
+def test_reshuffle_rule_and_rank_sharding():
+    from nu_nerf_b200 import feeder
+    G = _g()
+    batch, rn, _, _ = feeder.construct_nerf_ray_batch(G["imgs"], G["Ks"], G["poses"])
+    f = feeder.DeviceRayFeeder(batch, seed=3)
+    first = f.perm.clone()
+    for s in range(6):                      # 6 x 8 = 48 rays consumed; 48 + 8 < 60: no reshuffle yet
+        f(s, 8)
+    assert torch.equal(f.perm, first) and f.i == 48
+    f(6, 8)                                 # 56 + 8 >= 60 -> reshuffled (ZT:452)
+    assert f.i == 0 and not torch.equal(f.perm, first)
+    # two ranks see disjoint, interleaved halves of the single-process batch
+    one = feeder.DeviceRayFeeder(batch, seed=5)(0, 16)
+    r0 = feeder.DeviceRayFeeder(batch, rank=0, world=2, seed=5)(0, 8)
+    r1 = feeder.DeviceRayFeeder(batch, rank=1, world=2, seed=5)(0, 8)
+    assert torch.equal(one["rays_d"][0::2], r0["rays_d"]) and torch.equal(one["rays_d"][1::2], r1["rays_d"])
