@@ -62,30 +62,50 @@ __global__ void geometry_kernel(const float* __restrict__ o, const float* __rest
   if (lane == 0) ray_inner[r] = cnt;
 }
 
-// ---- geometry pass 2: exclusive scan of the per-ray counts (single block) -> ray_off[R], counts[2]
-__global__ void ray_scan_kernel(const int32_t* __restrict__ ray_inner, int R, int S, int32_t* ray_off, int32_t* counts) {
-  __shared__ int s_part[1024];
-  const int t = threadIdx.x, nt = blockDim.x;
-  const int per = (R + nt - 1) / nt;
-  const int b = t * per, e = min(R, b + per);
-  int sum = 0;
-  for (int i = b; i < e; ++i) sum += ray_inner[i];
-  s_part[t] = sum;
-  __syncthreads();
-  for (int off = 1; off < nt; off <<= 1) {
-    int v = t >= off ? s_part[t - off] : 0;
-    __syncthreads();
-    s_part[t] += v;
-    __syncthreads();
+// ---- geometry pass 2: exclusive scan of the per-ray inner counts, one block per 1024 rays (coalesced loads, shuffle
+//      scans).  ray_off[r] = offset inside the ray's block; the block total overwrites the block's own first count
+//      (ray_inner[b * 1024], already consumed) and pass 3 adds the totals of the preceding blocks.
+constexpr int SCAN_BLOCK = 1024;
+__global__ void __launch_bounds__(SCAN_BLOCK) ray_scan_kernel(int32_t* __restrict__ ray_inner, int R, int32_t* ray_off) {
+  __shared__ int s_warp[32];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int r = blockIdx.x * SCAN_BLOCK + t;
+  const int v = r < R ? ray_inner[r] : 0;
+  int incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    int u = __shfl_up_sync(FULL, incl, off);
+    if (lane >= off) incl += u;
   }
-  int run = s_part[t] - sum;
-  for (int i = b; i < e; ++i) { ray_off[i] = run; run += ray_inner[i]; }
-  if (t == nt - 1) { counts[0] = s_part[t]; counts[1] = R * S - s_part[t]; }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int w = s_warp[lane], wi = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      int u = __shfl_up_sync(FULL, wi, off);
+      if (lane >= off) wi += u;
+    }
+    s_warp[lane] = wi - w;                       // exclusive prefix of the warp totals
+    if (lane == 31) ray_inner[blockIdx.x * SCAN_BLOCK] = wi;     // block total (every count of the block was read above)
+  }
+  __syncthreads();
+  if (r < R) ray_off[r] = s_warp[wid] + incl - v;
+}
+
+// inner samples of all rays before block b of the scan (<= 64 blocks for R <= 65536: one warp-wide sum per warp)
+__device__ __forceinline__ int scan_block_base(const int32_t* __restrict__ ray_inner, int b, int lane) {
+  int acc = 0;
+  for (int i = lane; i < b; i += 32) acc += ray_inner[i * SCAN_BLOCK];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(FULL, acc, off);
+  return acc;
 }
 
 // ---- geometry pass 3: slots + compact gather of both sets (row-major mask order, as points[inner_mask])
 __global__ void compact_kernel(const float* __restrict__ d, const float* __restrict__ pts, const float* __restrict__ dists,
-                               const int32_t* __restrict__ ray_off, int R, int S, int32_t* slot, float* pts_in,
+                               const int32_t* __restrict__ ray_inner, const int32_t* __restrict__ ray_off,
+                               int32_t* __restrict__ counts, int R, int S, int32_t* slot, float* pts_in,
                                float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out,
                                float* dirs_out, int32_t* id_out) {
   const int lane = threadIdx.x & 31;
@@ -95,8 +115,12 @@ __global__ void compact_kernel(const float* __restrict__ d, const float* __restr
   float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
   float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
   dx /= nrm; dy /= nrm; dz /= nrm;
-  int in_run = ray_off[r];
+  int in_run = ray_off[r] + scan_block_base(ray_inner, r / SCAN_BLOCK, lane);
   int out_run = r * S - in_run;
+  if (r == 0) {                                 // totals for the host (the one sync of the step reads them)
+    const int n_in = scan_block_base(ray_inner, (R + SCAN_BLOCK - 1) / SCAN_BLOCK, lane);
+    if (lane == 0) { counts[0] = n_in; counts[1] = R * S - n_in; }
+  }
   for (int s0 = 0; s0 < S; s0 += 32) {
     int s = s0 + lane;
     bool ok = s < S;
@@ -144,31 +168,47 @@ __device__ __forceinline__ Sample fetch(const float* __restrict__ a_in, const fl
   return s;
 }
 
-__global__ void composite_fwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
+// NBLK = ceil(S / 32) blocks of 32 samples (5 for the product's S = 160, 8 for the general S <= 256).  All loads of a
+// ray are issued before the first scan: the prefix products are a dependent chain (shuffles + the carry between blocks),
+// so without this the kernel alternates between one block's memory latency and one block's scan latency.
+template <int NBLK>
+__global__ void __launch_bounds__(32 * WPB) composite_fwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
                                      const float* __restrict__ a_out, const float* __restrict__ c_out,
                                      const int32_t* __restrict__ slot, int R, int S, int is_nerf, float* rgb,
                                      float* rgb_raw, float* acc, float* rgb_b, float* weights) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
   if (r >= R) return;
+  int sl[NBLK];
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int s = k * 32 + lane;
+    sl[k] = s < S ? __ldg(slot + (long long)r * S + s) : 0;
+  }
+  Sample sm[NBLK];
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int s = k * 32 + lane;
+    sm[k] = Sample{0.f, 0.f, 0.f, 0.f, 0.f};
+    if (s < S) sm[k] = fetch(a_in, c_in, a_out, c_out, sl[k]);
+  }
   float carry = 1.f, carry_b = 1.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, sa = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  for (int base = 0; base < S; base += 32) {
-    int s = base + lane;
-    bool ok = s < S;
-    Sample sm = {0.f, 0.f, 0.f, 0.f, 0.f};
-    if (ok) sm = fetch(a_in, c_in, a_out, c_out, slot[(long long)r * S + s]);
-    float v = ok ? (1.0f - sm.a + 1e-7f) : 1.0f;
-    float vb = ok ? (1.0f - sm.ab + 1e-7f) : 1.0f;
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int s = k * 32 + lane;
+    const bool ok = s < S;
+    float v = ok ? (1.0f - sm[k].a + 1e-7f) : 1.0f;
+    float vb = ok ? (1.0f - sm[k].ab + 1e-7f) : 1.0f;
     float incl = scan_mul32(v, lane), incl_b = scan_mul32(vb, lane);
     float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, incl_b, 1);
     if (lane == 0) { ex = 1.f; exb = 1.f; }
-    float w = sm.a * (carry * ex), wb = sm.ab * (carry_b * exb);
+    float w = sm[k].a * (carry * ex), wb = sm[k].ab * (carry_b * exb);
     carry *= __shfl_sync(FULL, incl, 31);
     carry_b *= __shfl_sync(FULL, incl_b, 31);
     if (ok && weights) weights[(long long)r * S + s] = w;
-    s0 += w * sm.c0; s1 += w * sm.c1; s2 += w * sm.c2; sa += w;
-    b0 += wb * sm.c0; b1 += wb * sm.c1; b2 += wb * sm.c2;
+    s0 += w * sm[k].c0; s1 += w * sm[k].c1; s2 += w * sm[k].c2; sa += w;
+    b0 += wb * sm[k].c0; b1 += wb * sm[k].c1; b2 += wb * sm[k].c2;
   }
   s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sa = warp_sum(sa);
   b0 = warp_sum(b0); b1 = warp_sum(b1); b2 = warp_sum(b2);
@@ -210,14 +250,25 @@ __global__ void __launch_bounds__(32 * WPB) composite_bwd_kernel(const float* __
   float T[NBLK], Tb[NBLK], gw[NBLK], gwb[NBLK], va[NBLK], vab[NBLK], gk[NBLK], gkb[NBLK];
   int sl[NBLK];
   float carry = 1.f, carry_b = 1.f;
+  // all loads of the ray first (see composite_fwd_kernel)
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int s = k * 32 + lane;
+    sl[k] = (k < nblk && s < S) ? __ldg(slot + (long long)r * S + s) : 0;
+  }
+  Sample smp[NBLK];
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int s = k * 32 + lane;
+    smp[k] = Sample{0.f, 0.f, 0.f, 0.f, 0.f};
+    if (k < nblk && s < S) smp[k] = fetch(a_in, c_in, a_out, c_out, sl[k]);
+  }
 #pragma unroll
   for (int k = 0; k < NBLK; ++k) {
     if (k < nblk) {
       int s = k * 32 + lane;
       bool ok = s < S;
-      sl[k] = ok ? slot[(long long)r * S + s] : 0;
-      Sample sm = {0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ok) sm = fetch(a_in, c_in, a_out, c_out, sl[k]);
+      const Sample sm = smp[k];
       float v = ok ? (1.0f - sm.a + 1e-7f) : 1.0f, vb = ok ? (1.0f - sm.ab + 1e-7f) : 1.0f;
       float incl = scan_mul32(v, lane), incl_b = scan_mul32(vb, lane);
       float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, incl_b, 1);
@@ -284,10 +335,11 @@ extern "C" int nunerf_render_geometry(const float* o, const float* d, const floa
   NUNERF_REQUIRE(R > 0 && S >= 2 && S <= 256, "render_geometry: need 2 <= S <= 256");
   geometry_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, R, S, dists, pts, ray_scratch);
   NUNERF_CHECK_LAUNCH("geometry_kernel");
-  ray_scan_kernel<<<1, 1024, 0, stream>>>(ray_scratch, R, S, ray_scratch + R, counts);
+  ray_scan_kernel<<<cdiv(R, SCAN_BLOCK), SCAN_BLOCK, 0, stream>>>(ray_scratch, R, ray_scratch + R);
   NUNERF_CHECK_LAUNCH("ray_scan_kernel");
-  compact_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(d, pts, dists, ray_scratch + R, R, S, slot, pts_in, dists_in,
-                                                       dirs_in, id_in, pts_out, dists_out, dirs_out, id_out);
+  compact_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(d, pts, dists, ray_scratch, ray_scratch + R, counts, R, S, slot,
+                                                       pts_in, dists_in, dirs_in, id_in, pts_out, dists_out, dirs_out,
+                                                       id_out);
   NUNERF_CHECK_LAUNCH("compact_kernel");
   return 0;
 }
@@ -296,9 +348,12 @@ extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in
                                     const float* color_out, const int32_t* slot, int R, int S, int is_nerf, float* rgb,
                                     float* rgb_raw, float* acc, float* rgb_bkgr, float* weights, void* stream) {
   NUNERF_REQUIRE(slot && rgb && rgb_raw && acc && rgb_bkgr && R > 0 && S > 0 && S <= 256, "composite_fwd: bad arguments");
-  composite_fwd_kernel<<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(alpha_in, color_in, alpha_out, color_out,
-                                                                          slot, R, S, is_nerf, rgb, rgb_raw, acc,
-                                                                          rgb_bkgr, weights);
+  if (S <= 160)
+    composite_fwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
+        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
+  else
+    composite_fwd_kernel<8><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
+        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   NUNERF_CHECK_LAUNCH("composite_fwd_kernel");
   return 0;
 }

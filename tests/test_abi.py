@@ -39,3 +39,16 @@ def test_argument_validation_without_gpu():
     assert rc < 0 and b"linear" in _lib.lib.nunerf_last_error()
     rc = _lib.lib.nunerf_upsample(None, None, None, None, 4, 300, 16, None, 1.0, None, None, None, None, None, None)
     assert rc < 0
+
+
+def test_chain_argument_validation_without_gpu():
+    """nunerf_mlp_chain rejects malformed programs before any CUDA call (same error convention)."""
+    from nu_nerf_b200 import _lib
+    a = _lib.MlpChainT()
+    assert _lib.lib.nunerf_mlp_chain(ctypes.byref(a), None) < 0                      # no input
+    buf = (ctypes.c_char * 4096)()
+    a.x, a.ldx, a.K0, a.M, a.n_layers = ctypes.addressof(buf), 320, 320, 16, 1       # input wider than 256 columns
+    rc = _lib.lib.nunerf_mlp_chain(ctypes.byref(a), None)
+    assert rc < 0 and b"mlp_chain" in _lib.lib.nunerf_last_error()
+    a.ldx, a.K0, a.n_layers = 64, 64, 11                                              # too many layers
+    assert _lib.lib.nunerf_mlp_chain(ctypes.byref(a), None) < 0
