@@ -194,13 +194,23 @@ __device__ __forceinline__ float ch_pe_col(const float* x, int pc) {
   return __bfloat162float(__float2bfloat16_rn((t & 1) ? co : sn));
 }
 
+// PAIR = 1: one CTA per pair of tiles, cta_group::1 MMAs (M = 128).
+// PAIR = 2: clusters of two CTAs, cta_group::2 MMAs (M = 256 = one tile of each CTA): every CTA keeps its own tiles,
+//           accumulators, epilogue warps and activation stores, but holds only HALF of each weight block (N/2 rows) --
+//           the pair's tensor cores share the two halves, so per SM the operand reads drop from 12 KB to 8 KB per
+//           instruction and the weight bytes written into shared memory halve (the bound of PAIR = 1).
+//           Only the leader CTA (cluster rank 0) issues MMAs and commits; the peer's warp 1 replays the same schedule as a
+//           proxy: it waits for ITS local conditions (epilogue done, input / weight half landed, stores drained) and
+//           arrives on the leader's peer_go[stage] barrier, which the leader waits for before each K-block.
+template <int PAIR>
 __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int n_xblocks = 8;
   uint8_t* sX = smem;                                         // activation K-blocks of both tiles
   uint8_t* sW = sX + (size_t)n_xblocks * CH_BLOCK_BYTES;      // weight ring
-  uint64_t* bars = (uint64_t*)(sW + (size_t)p.w_stages * CH_WSTAGE_BYTES);
+  const int wstage_bytes = CH_WSTAGE_BYTES / PAIR;             // PAIR = 2: a stage holds this CTA's half of a weight block
+  uint64_t* bars = (uint64_t*)(sW + (size_t)p.w_stages * wstage_bytes);
   uint64_t* w_full = bars;                  // [w_stages]
   uint64_t* w_empty = bars + 8;             // [w_stages]
   uint64_t* x_done = bars + 16;             // [2]  epilogue of tile t finished (X written, accumulator drained)
@@ -208,14 +218,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
   uint64_t* in_full = bars + 20;            // [2]  tile input is in shared memory
   uint64_t* in_empty = bars + 22;           // [2]  X blocks of tile t may be refilled (TMA input mode)
   uint32_t* tmem_ptr = (uint32_t*)(bars + 24);
+  uint64_t* peer_go = bars + 32;            // [w_stages]  PAIR = 2, leader only: the peer CTA is ready for this K-block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_pairs = (p.num_tiles + 1) >> 1;
-  // Clusters: the CTAs of a cluster stream the SAME weight blocks, so each block is fetched from L2 once and multicast
-  // into every CTA's ring (weight traffic out of L2 is what bounds this kernel otherwise: 128 KB per tile-layer per
-  // SM).  Every CTA of a cluster therefore runs the same number of tile pairs (surplus pairs are all-masked).
-  const uint32_t cl_n = ptx::cluster_nctarank(), cl_rank = ptx::cluster_ctarank();
-  const uint16_t cl_mask = (uint16_t)((1u << cl_n) - 1u);
+  // PAIR = 2: both CTAs of a cluster run the same number of tile pairs (a surplus pair is all-masked rows)
+  const uint32_t cl_rank = PAIR == 2 ? ptx::cluster_ctarank() : 0u;
   const int num_iters = (num_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
@@ -224,7 +232,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
       if (p.layer[l].store_chunks > 0) ptx::prefetch_tmap(&p.out_map[l]);
     }
     if (p.in_mode == 0) ptx::prefetch_tmap(&p.in_map);
-    for (int i = 0; i < p.w_stages; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], cl_n); }
+    for (int i = 0; i < p.w_stages; ++i) {
+      ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); ptx::mbar_init(&peer_go[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&x_done[i], CH_EPI_WARPS);
       ptx::mbar_init(&t_full[i], 1);
@@ -234,12 +244,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_ptr, 512u);
-    ptx::tmem_relinquish();
+    if (PAIR == 2) { ptx::tmem_alloc2(tmem_ptr, 512u); ptx::tmem_relinquish2(); }
+    else { ptx::tmem_alloc(tmem_ptr, 512u); ptx::tmem_relinquish(); }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (cl_n > 1) ptx::cluster_sync();       // peers must not signal barriers that are not initialised yet
+  if (PAIR == 2) ptx::cluster_sync();      // the peer must not signal barriers that are not initialised yet
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -248,7 +258,6 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint32_t wblk = 0;         // running weight-block counter: block b is fetched by cluster rank b % cl_n
       for (int it = 0; it < num_iters; ++it) {
         const int pair = (int)blockIdx.x + it * (int)gridDim.x;
         if (p.in_mode == 0) {
@@ -261,20 +270,16 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           }
         }
         for (int l = 0; l < p.n_layers; ++l) {
-          const int nkb = p.layer[l].nkb, nh = (p.layer[l].N + CH_WROWS - 1) / CH_WROWS;
+          const int nkb = p.layer[l].nkb;
+          const int row0 = (int)cl_rank * (p.layer[l].N / PAIR);     // PAIR = 2: this CTA's half of the weight rows
           for (int t = 0; t < 2; ++t)
-           for (int h = 0; h < nh; ++h)
-            for (int kb = 0; kb < nkb; ++kb, ++wblk) {
-              // the stage is free once EVERY CTA of the cluster has consumed it (multicast commits, count cl_n)
+            for (int kb = 0; kb < nkb; ++kb) {
+              // the stage is free once the MMAs that read it have completed (tcgen05.commit, multicast to the pair)
               ptx::mbar_wait_parked(&w_empty[stage], phase ^ 1);
               if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[400 + (t * 4 + kb)] = clock64();
-              // box = 64 K-columns x min(128, N) rows; rows beyond N are zero filled but count as transferred bytes
+              // box = 64 K-columns x N / PAIR rows
               ptx::mbar_expect_tx(&w_full[stage], (uint32_t)p.layer[l].w_box_bytes);
-              if (cl_n == 1)
-                ptx::tma_load_2d(sW + (size_t)stage * CH_WSTAGE_BYTES, &p.w_map[l], &w_full[stage], kb * 64, h * CH_WROWS);
-              else if (wblk % cl_n == cl_rank)
-                ptx::tma_load_2d_mc(sW + (size_t)stage * CH_WSTAGE_BYTES, &p.w_map[l], &w_full[stage], kb * 64,
-                                    h * CH_WROWS, cl_mask);
+              ptx::tma_load_2d(sW + (size_t)stage * wstage_bytes, &p.w_map[l], &w_full[stage], kb * 64, row0);
               if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -286,7 +291,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     // registers, a handful of instructions per MMA); only MMA / commit / TMA-store are issued by lane 0.
     // Ping-pong: (layer l, tile 0), (layer l, tile 1), (layer l+1, tile 0), ... -- while the tensor core works on one
     // tile the 16 epilogue warps activate the other one.
-    const bool leader = lane == 0;
+    const bool leader = lane == 0;                          // the issuing lane of this warp
+    const bool cta_leader = PAIR == 1 || cl_rank == 0;      // the CTA that issues the pair's MMAs
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -319,37 +325,46 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             }
             stores_pending = true;
           }
-          const int nh = (L.N + CH_WROWS - 1) / CH_WROWS;
-          for (int h = 0; h < nh; ++h) {
-            const int n_h = L.N - h * CH_WROWS < CH_WROWS ? L.N - h * CH_WROWS : CH_WROWS;
-            const uint32_t idesc = ptx::idesc_bf16(128, n_h, 0, 0);
-            const uint32_t d_half = d_tmem + (uint32_t)(h * CH_WROWS);
-            for (int kb = 0; kb < L.nkb; ++kb) {
-              const int blk = ch_block(t, L.kb0 + kb);
-              ptx::mbar_wait(&w_full[stage], phase);
-              ptx::tc_fence_after();
+          const uint32_t idesc = ptx::idesc_bf16(128 * PAIR, L.N, 0, 0);
+          for (int kb = 0; kb < L.nkb; ++kb) {
+            const int blk = ch_block(t, L.kb0 + kb);
+            ptx::mbar_wait(&w_full[stage], phase);
+            ptx::tc_fence_after();
 #if NUNERF_CHAIN_TIMELINE_DETAIL
-              if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5 && h == 0) p.dbg[430 + (t * 4 + kb) * 2] = clock64();
+            if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[430 + (t * 4 + kb) * 2] = clock64();
 #endif
+            if (PAIR == 2 && !cta_leader) {
+              // proxy of the peer CTA: everything the pair's MMA on this K-block needs from THIS CTA is in place (the
+              // activation tile, the drained accumulator, this half of the weight block; before the last K-block also
+              // the TMA stores that still read the activation blocks) -> tell the leader
+              if (leader) {
+                if (kb == L.nkb - 1 && stores_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                ptx::mbar_arrive_remote(&peer_go[stage], 0u);
+              }
+            } else {
+              if (PAIR == 2) { ptx::mbar_wait_cluster(&peer_go[stage], phase); ptx::tc_fence_after(); }
               const uint64_t ad0 = desc_hi | (uint64_t)(((sx_base + (uint32_t)blk * CH_BLOCK_BYTES) >> 4) & 0x3fff);
-              const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * CH_WSTAGE_BYTES) >> 4) & 0x3fff);
+              const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * wstage_bytes) >> 4) & 0x3fff);
               if (leader) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)        // +32 bytes per K = 16 step: +2 in the (address >> 4) field
-                  ptx::umma_bf16(d_half, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
-                if (cl_n == 1) ptx::tc_commit(&w_empty[stage]);
-                else ptx::tc_commit_mc(&w_empty[stage], cl_mask);
+                for (int k = 0; k < 4; ++k) {      // +32 bytes per K = 16 step: +2 in the (address >> 4) field
+                  if (PAIR == 2) ptx::umma_bf16_2cta(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                  else ptx::umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                }
+                if (PAIR == 2) ptx::tc_commit2_mc(&w_empty[stage], (uint16_t)3);
+                else ptx::tc_commit(&w_empty[stage]);
 #if NUNERF_CHAIN_TIMELINE_DETAIL
-                if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5 && h == 0) p.dbg[430 + (t * 4 + kb) * 2 + 1] = clock64();
+                if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[430 + (t * 4 + kb) * 2 + 1] = clock64();
 #endif
               }
-              if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
             }
+            if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
           }
-          if (leader) {
+          if (leader && cta_leader) {
             // this layer's epilogue overwrites the X blocks: outstanding TMA stores must have read them
             if (stores_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            ptx::tc_commit(&t_full[t]);
+            if (PAIR == 2) ptx::tc_commit2_mc(&t_full[t], (uint16_t)3);
+            else ptx::tc_commit(&t_full[t]);
             if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 2 + t) * 2] = clock64();
           }
           __syncwarp();
@@ -590,33 +605,48 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (cl_n > 1) ptx::cluster_sync();       // no CTA leaves while a peer may still multicast into its ring
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512u);
+  if (PAIR == 2) ptx::cluster_sync();      // no CTA leaves while the pair's MMAs / commits may still touch it
+  if (warp == 1) {
+    if (PAIR == 2) ptx::tmem_dealloc2(tmem_base, 512u);
+    else ptx::tmem_dealloc(tmem_base, 512u);
+  }
 }
 
 // ------------------------------------------------------------------------------------------- host side
-static int chain_launch(ChainParams& P, cudaStream_t stream) {
+// 1 (default): cta_group::1 kernel.  2 (NUNERF_CHAIN_PAIR=2): CTA pairs sharing the weight operand (cta_group::2) --
+// functionally identical (tests/test_engine_gpu.py runs both) but measured SLOWER on B200 for these 256-wide layers
+// (fused SDF query 496 vs 570 TFLOP/s, gpurun_out/s22/s24: the pair's instruction takes ~300 cycles against ~210 for
+// one CTA's, and every tile-layer waits for the slower of two epilogues), so it stays an opt-in experiment.
+static int chain_pair() { return env_int("NUNERF_CHAIN_PAIR", 1) == 2 ? 2 : 1; }
+
+template <int PAIR>
+static int chain_launch_t(ChainParams& P, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail("chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e), -2);
+    if (PAIR == 2) {
+      e = cudaFuncSetAttribute(mlp_chain_kernel<PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+      (void)e; (void)cudaGetLastError();
+    }
     configured = true;
   }
   NUNERF_REQUIRE(P.in_mode == 1 || (P.in_blocks >= 1 && P.in_blocks <= 4), "chain: TMA input must be 1..4 K-blocks");
   const size_t xbytes = (size_t)8 * CH_BLOCK_BYTES;
   const size_t fixed = 1024 + 512;
-  int stages = (int)((227 * 1024 - fixed - xbytes) / CH_WSTAGE_BYTES);
+  const int stage_bytes = CH_WSTAGE_BYTES / PAIR;
+  int stages = (int)((227 * 1024 - fixed - xbytes) / stage_bytes);
   if (stages > 8) stages = 8;
   NUNERF_REQUIRE(stages >= 2, "chain: input too wide for shared memory");
   { const int s_env = env_int("NUNERF_CHAIN_STAGES", 0); if (s_env >= 2 && s_env < stages) stages = s_env; }   // experiments
-  for (int l = 0; l < P.n_layers; ++l) P.layer[l].w_box_bytes = 128 * (P.layer[l].N < CH_WROWS ? P.layer[l].N : CH_WROWS);
+  for (int l = 0; l < P.n_layers; ++l) {
+    P.layer[l].w_box_bytes = 128 * (P.layer[l].N / PAIR);
+  }
   P.w_stages = stages;
   P.num_tiles = cdiv(P.M, 128);
-  const size_t smem = fixed + xbytes + (size_t)stages * CH_WSTAGE_BYTES;
+  const size_t smem = fixed + xbytes + (size_t)stages * stage_bytes;
   const int num_pairs = (P.num_tiles + 1) / 2;
-  int cluster = env_int("NUNERF_CHAIN_CLUSTER", 1);
-  if (cluster != 1 && cluster != 2 && cluster != 4) cluster = 1;
-  while (cluster > 1 && (num_sms() % cluster != 0 || num_pairs < cluster)) cluster >>= 1;
+  const int cluster = PAIR;
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(CH_THREADS);
   cfg.dynamicSmemBytes = smem;
@@ -626,24 +656,28 @@ static int chain_launch(ChainParams& P, cudaStream_t stream) {
   attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   // persistent grid = the number of clusters that are co-resident (GPC sizes need not be multiples of the cluster)
-  static int max_clusters[5] = {0, 0, 0, 0, 0};
-  if (max_clusters[cluster] == 0) {
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
     cfg.gridDim = dim3(num_sms() / cluster * cluster);
     int n = 0;
-    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, mlp_chain_kernel, &cfg);
-    max_clusters[cluster] = (qe == cudaSuccess && n > 0) ? n : num_sms() / cluster;
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, mlp_chain_kernel<PAIR>, &cfg);
+    max_clusters = (qe == cudaSuccess && n > 0) ? n : num_sms() / cluster;
     (void)cudaGetLastError();
   }
-  int grid = max_clusters[cluster] * cluster;
+  int grid = max_clusters * cluster;
   if (grid > num_sms()) grid = num_sms() / cluster * cluster;
   const int need = (num_pairs + cluster - 1) / cluster * cluster;
   if (grid > need) grid = need;
   { const int g_env = env_int("NUNERF_CHAIN_GRID", 0); if (g_env >= cluster && g_env < grid) grid = g_env / cluster * cluster; }
   cfg.gridDim = dim3(grid);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_chain_kernel, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_chain_kernel<PAIR>, P);
   if (e != cudaSuccess) return fail("chain: cudaLaunchKernelEx: %s", cudaGetErrorString(e), -2);
   NUNERF_CHECK_LAUNCH("mlp_chain_kernel");
   return 0;
+}
+
+static int chain_launch(ChainParams& P, cudaStream_t stream) {
+  return chain_pair() == 2 ? chain_launch_t<2>(P, stream) : chain_launch_t<1>(P, stream);
 }
 
 }  // namespace nunerf
@@ -660,7 +694,7 @@ extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
   P.n_layers = 9; P.M = a->M; P.in_mode = 1; P.in_blocks = 1; P.in_release_layer = 0; P.pts = a->pts;
   for (int l = 0; l < 9; ++l) {
     NUNERF_REQUIRE(a->w[l] && a->ldw[l] >= Ks[l] && a->ldw[l] % 8 == 0, "sdf_infer: bad weight operand");
-    if (int r = make_map(&P.w_map[l], a->w[l], Ns[l], Ks[l], a->ldw[l], 64, Ns[l] < CH_WROWS ? Ns[l] : CH_WROWS)) return r;
+    if (int r = make_map(&P.w_map[l], a->w[l], Ns[l], Ks[l], a->ldw[l], 64, Ns[l] / chain_pair())) return r;
     ChainLayer& L = P.layer[l];
     L.N = Ns[l]; L.n_real = Ns[l];
     L.kb0 = 0; L.nkb = Ks[l] / 64;
@@ -702,7 +736,7 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
     NUNERF_REQUIRE(s.K >= 64 && s.K % 64 == 0 && s.K <= width, "mlp_chain: K exceeds the activation produced so far");
     NUNERF_REQUIRE(s.ldw % 8 == 0 && s.ldw >= s.K, "mlp_chain: bad weight pitch");
     NUNERF_REQUIRE(s.act >= 0 && s.act <= 2, "mlp_chain: act must be 0 (none), 1 (relu) or 2 (softplus 100)");
-    if (int r = make_map(&P.w_map[l], s.w, s.N, s.K, s.ldw, 64, s.N < CH_WROWS ? s.N : CH_WROWS)) return r;
+    if (int r = make_map(&P.w_map[l], s.w, s.N, s.K, s.ldw, 64, s.N / chain_pair())) return r;
     L.N = s.N; L.n_real = s.n_real > 0 ? s.n_real : s.N;
     L.kb0 = 0; L.nkb = s.K / 64;
     L.act = s.act; L.bias = s.bias;

@@ -393,3 +393,34 @@ def test_forward_with_device_ray_feeder():
     loss = out["loss_rgb"].mean() + (0.1 * out["gradient_error"]).mean()
     loss.backward()
     assert torch.isfinite(loss) and net.sdf_network.lin0.weight_v.grad is not None
+
+
+def test_cta_pair_variant_of_the_chain_kernel(monkeypatch):
+    """NUNERF_CHAIN_PAIR=2: the cta_group::2 variant of mlp_chain_kernel (CTA pairs sharing the weight operand, leader /
+    proxy MMA warps) must reproduce the default kernel -- same operands, same accumulation order per row."""
+    from nu_nerf_b200 import engine as eng
+    net = _renderer("bf16")
+    w = net._prepare()
+    g = torch.Generator().manual_seed(9)
+    for M in (1, 300, 148 * 256 + 77):
+        pts = (torch.rand(M, 3, generator=g) * 2.4 - 1.2).to(DEV).contiguous()
+        monkeypatch.setenv("NUNERF_CHAIN_PAIR", "1")
+        a = eng.sdf_infer(w.sdf, pts, 1, fused=True)
+        monkeypatch.setenv("NUNERF_CHAIN_PAIR", "2")
+        b = eng.sdf_infer(w.sdf, pts, 1, fused=True)
+        torch.cuda.synchronize()
+        assert torch.isfinite(b).all()
+        assert (a - b).abs().max().item() < 1e-5, (M, (a - b).abs().max().item())
+    # a training chain with stores, masks and an fp32 head (predictor forward) under the pair variant
+    pw = w.pred["outer_light"]
+    M = 5000
+    x = eng.P(M, 128, 1, DEV, zero=True)
+    x.t[:M, :72] = (torch.randn(M, 72, generator=g) * 0.7).to(DEV).to(torch.bfloat16)
+    monkeypatch.setenv("NUNERF_CHAIN_PAIR", "1")
+    t1 = eng.pred_forward(pw, x, M, 128, 1)
+    monkeypatch.setenv("NUNERF_CHAIN_PAIR", "2")
+    t2 = eng.pred_forward(pw, x, M, 128, 1)
+    torch.cuda.synchronize()
+    assert (t1.head[:, :3] - t2.head[:, :3]).abs().max().item() < 1e-5
+    for l in range(3):
+        assert torch.equal(t1.H[l].t[:M], t2.H[l].t[:M]) and torch.equal(t1.Mk[l], t2.Mk[l])
