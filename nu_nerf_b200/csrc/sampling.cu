@@ -87,7 +87,11 @@ __global__ void points_kernel(const float* __restrict__ o, const float* __restri
   for (int c = 0; c < 3; ++c) pts[3 * i + c] = det_add(o[3 * r + c], det_mul(d[3 * r + c], zz));
 }
 
-// One importance round.  n <= 128 samples in, n_new <= 32 out.
+// One importance round.  n <= 128 samples in, n_new <= 32 out.  NBLK = ceil(n / 32) blocks of 32 samples per lane: the
+// kernel is issue-bound (fixed-order scans, IEEE divisions and expf of the logistic CDF), so it is instantiated for 2, 3
+// and 4 blocks instead of always walking four (n = 64 is half of that); skipped blocks only ever contributed
+// identities (weight 0, factor 1), so the results are bit-identical.
+template <int NBLK>
 __global__ void upsample_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
                                 const float* __restrict__ sdf, int R, int n, int n_new,
                                 const float* __restrict__ inv_s_dev, float inv_s_cap, const float* __restrict__ u_tab,
@@ -101,14 +105,13 @@ __global__ void upsample_kernel(const float* __restrict__ o, const float* __rest
   const float inv_s = fminf(inv_s_dev[0], inv_s_cap);
   const float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
   const float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
-  const int nblk = (n + 31) >> 5;
 
   // ---- load + radius
-  float zv[4], sv[4], rad[4];
+  float zv[NBLK], sv[NBLK], rad[NBLK];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < NBLK; ++k) {
     int j = lane + 32 * k;
-    bool ok = k < nblk && j < n;
+    bool ok = j < n;
     zv[k] = ok ? z[(long long)r * n + j] : 0.f;
     sv[k] = ok ? sdf[(long long)r * n + j] : 0.f;
     float px = det_add(ox, det_mul(dx, zv[k])), py = det_add(oy, det_mul(dy, zv[k])), pz = det_add(oz, det_mul(dz, zv[k]));
@@ -117,19 +120,21 @@ __global__ void upsample_kernel(const float* __restrict__ o, const float* __rest
   }
   __syncwarp();
   // ---- per-section quantities; section j uses samples j, j+1 and the raw cosine of section j-1
-  float alpha[4], wgt[4];
+  float alpha[NBLK], wgt[NBLK];
   float carry_prev_cos = 0.f;  // raw cosine of the last section of the previous block
   float carryT = 1.0f;
   float lane_sum = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < NBLK; ++k) {
     int j = lane + 32 * k;
     // neighbour j+1: lane+1 of this block, or lane 0 of the next block
     float zn = __shfl_down_sync(FULL, zv[k], 1), sn = __shfl_down_sync(FULL, sv[k], 1),
           rn = __shfl_down_sync(FULL, rad[k], 1);
-    float zn2 = __shfl_sync(FULL, k < 3 ? zv[k + 1 > 3 ? 3 : k + 1] : 0.f, 0);
-    float sn2 = __shfl_sync(FULL, k < 3 ? sv[k + 1 > 3 ? 3 : k + 1] : 0.f, 0);
-    float rn2 = __shfl_sync(FULL, k < 3 ? rad[k + 1 > 3 ? 3 : k + 1] : 0.f, 0);
+    constexpr int LAST = NBLK - 1;
+    const int kn = k + 1 > LAST ? LAST : k + 1;
+    float zn2 = __shfl_sync(FULL, k < LAST ? zv[kn] : 0.f, 0);
+    float sn2 = __shfl_sync(FULL, k < LAST ? sv[kn] : 0.f, 0);
+    float rn2 = __shfl_sync(FULL, k < LAST ? rad[kn] : 0.f, 0);
     if (lane == 31) { zn = zn2; sn = sn2; rn = rn2; }
     const bool sec_ok = (j < n - 1);
     float dist = det_sub(zn, zv[k]);
@@ -161,7 +166,7 @@ __global__ void upsample_kernel(const float* __restrict__ o, const float* __rest
   float carryC = 0.f;
   if (lane == 0) s_cdf[w][0] = 0.f;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < NBLK; ++k) {
     int j = lane + 32 * k;
     float pdf = (j < n - 1) ? det_div(wgt[k], total) : 0.f;
     float incl = hs_scan_add(pdf, lane);
@@ -197,7 +202,7 @@ __global__ void upsample_kernel(const float* __restrict__ o, const float* __rest
   // ---- stable merge (old samples first on ties): equals a stable sort of cat(z, z_new) (ZT:560-561)
   const int nm = n + n_new;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < NBLK; ++k) {
     int j = lane + 32 * k;
     if (j < n) {
       int cnt = 0;
@@ -255,8 +260,14 @@ extern "C" int nunerf_upsample(const float* o, const float* d, const float* z, c
                                int32_t* inds, float* z_merged, int32_t* perm, void* stream) {
   NUNERF_REQUIRE(o && d && z && sdf && inv_s_dev && u_tab && z_new && inds && z_merged && perm, "upsample: null argument");
   NUNERF_REQUIRE(R > 0 && n >= 2 && n <= 128 && n_new >= 1 && n_new <= 32, "upsample: need 2<=n<=128, 1<=n_new<=32");
-  upsample_kernel<<<cdiv(R, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
-      o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
+  const dim3 grid(cdiv(R, WARPS_PER_BLOCK)), block(32 * WARPS_PER_BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 64)
+    upsample_kernel<2><<<grid, block, 0, st>>>(o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
+  else if (n <= 96)
+    upsample_kernel<3><<<grid, block, 0, st>>>(o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
+  else
+    upsample_kernel<4><<<grid, block, 0, st>>>(o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
   NUNERF_CHECK_LAUNCH("upsample_kernel");
   return 0;
 }
