@@ -267,7 +267,7 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
     linear_dw(dxm, A[7], M, 256, 256, w.feat.dW, db=w.feat.db)
     linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256, db=w.sdf_head.db)
     dz = P(M, 256, planes, dev)
-    dz2 = P(M, 256, planes, dev, zero=True)
+    dz2 = P(M, 256, planes, dev)
     linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=dz)
     cur, other = dz, dz2
     for l in range(7, 0, -1):
@@ -315,7 +315,7 @@ def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad):
     linear_dw(dxm, A[7], M, 256, 256, w.feat.dW, db=w.feat.db)
     linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256, db=w.sdf_head.db)
     DZ = [P(M, 256, planes, dev) for _ in range(8)]      # DZ[l] = d loss / d z_l
-    DZ[3] = P(M, 256, planes, dev, zero=True)
+    DZ[3].t[:, 217:].zero_()                             # lin3 has 217 outputs: the tail columns are read as K padding
     linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=DZ[7])
     ew6 = lambda l: dict(W=w.L[l].WTk, N=256, K=256, aux_mode=6, aux1=A[l - 1], aux2=E[l - 1], store=DZ[l - 1], keep=1)
     chain(DZ[7], M, 256, [ew6(7), ew6(6), ew6(5)])
@@ -452,7 +452,8 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
     M, dev = t.M, t.dists.device
     H = t.H
     dz_rgb = P(M, 64, planes, dev, zero=True)
-    dz8 = P(M, 320, planes, dev, zero=True)
+    dz8 = P(M, 320, planes, dev)
+    dz8.t[:, 256:].zero_()                               # [d feature (256, written below) | d sigma | zero K padding]
     call("nunerf_nerf_out_bwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M, d_alpha.data_ptr(),
          d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0)
     linear_dw(dz_rgb, t.hv, M, 3, 128, w.rgb.dW, db=w.rgb.db)

@@ -1,0 +1,28 @@
+import os, sys, json, torch
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests"); sys.path.insert(0, "/root/repo/tools")
+from conftest import make_stage2, uv_sphere
+R = 4096
+V, Fc = uv_sphere(0.6, 224, 224)
+net = make_stage2("bf16", mesh=(V, Fc)).cuda()
+g = torch.Generator().manual_seed(1)
+o = 3.0 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
+d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(R, 3, generator=g), dim=-1)
+o, d = o.cuda(), d.cuda()
+gt = torch.rand(R, 3, generator=g).cuda()
+def step():
+    net.zero_grad(set_to_none=True)
+    out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+    tm = out["tir_mask"].detach()
+    loss = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
+    loss.backward()
+for _ in range(3): step()
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step(); torch.cuda.synchronize()
+ev = prof.key_averages()
+rows = sorted(ev, key=lambda e: -e.device_time_total)[:28]
+tot = sum(e.device_time_total for e in ev)
+print("total device us", tot)
+for e in rows:
+    print(f"{e.device_time_total:10.0f} us {e.count:5d}x  {e.key[:90]}")
