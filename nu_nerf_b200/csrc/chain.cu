@@ -72,7 +72,8 @@ struct ChainParams {
   int in_release_layer;  // (unused)
   int w_stages;
   const float* pts;
-  int dbg_flags;         // timing experiments only (NUNERF_CHAIN_DEBUG): 1 = skip the TMEM load, 2 = skip the smem store
+  int dbg_flags;         // timing experiments only (NUNERF_CHAIN_DEBUG): 1 = skip the TMEM load, 2 = skip the smem store,
+                         // 8 = nanosleep in the epilogue, 16 = skip the MMAs, 32 = skip the weight loads, 64 = no bias loads
   long long* dbg;        // optional timeline buffer (NUNERF_CHAIN_TIMELINE): [2][256] clock64 stamps of CTA 0
 };
 
@@ -96,8 +97,13 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
     for (int i = 0; i < 16; ++i) x[i] = ((mbits >> i) & 1u) ? __uint_as_float(v[i]) : 0.0f;
   } else {
     float4 b[4];
+    if (dbg_flags & 64) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+      for (int i = 0; i < 4; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
+    }
     ptx::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -278,8 +284,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               ptx::mbar_wait_parked(&w_empty[stage], phase ^ 1);
               if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[400 + (t * 4 + kb)] = clock64();
               // box = 64 K-columns x N / PAIR rows
-              ptx::mbar_expect_tx(&w_full[stage], (uint32_t)p.layer[l].w_box_bytes);
-              ptx::tma_load_2d(sW + (size_t)stage * wstage_bytes, &p.w_map[l], &w_full[stage], kb * 64, row0);
+              if (p.dbg_flags & 32) {            // timing experiment: no weight traffic at all (stale weights)
+                ptx::mbar_arrive(&w_full[stage]);
+              } else {
+                ptx::mbar_expect_tx(&w_full[stage], (uint32_t)p.layer[l].w_box_bytes);
+                ptx::tma_load_2d(sW + (size_t)stage * wstage_bytes, &p.w_map[l], &w_full[stage], kb * 64, row0);
+              }
               if (++stage == p.w_stages) { stage = 0; phase ^= 1; }
             }
         }
@@ -346,10 +356,12 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               const uint64_t ad0 = desc_hi | (uint64_t)(((sx_base + (uint32_t)blk * CH_BLOCK_BYTES) >> 4) & 0x3fff);
               const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * wstage_bytes) >> 4) & 0x3fff);
               if (leader) {
+                if (!(p.dbg_flags & 16)) {         // (16: timing experiment without the MMAs themselves)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {      // +32 bytes per K = 16 step: +2 in the (address >> 4) field
-                  if (PAIR == 2) ptx::umma_bf16_2cta(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
-                  else ptx::umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                  for (int k = 0; k < 4; ++k) {    // +32 bytes per K = 16 step: +2 in the (address >> 4) field
+                    if (PAIR == 2) ptx::umma_bf16_2cta(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                    else ptx::umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                  }
                 }
                 if (PAIR == 2) ptx::tc_commit2_mc(&w_empty[stage], (uint16_t)3);
                 else ptx::tc_commit(&w_empty[stage]);
