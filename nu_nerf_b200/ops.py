@@ -175,28 +175,3 @@ def linear_dw(dZ: P, X: P, M, N, K, dW, *, z_col=0, x_col=0, db=None):
 
 def colsum(Z: P, M, N, out, z_col=0):
     call("nunerf_colsum", Z.at(0, z_col), Z.ld, Z.lo, M, N, out.data_ptr())
-
-
-class Dense:
-    """One dense layer's operands, re-materialised from the fp32 master weight every step:
-    Wk  [pad16(N), planes*pad64(K)]  K-major (forward:  Y = X W^T)
-    WTk [pad64(K), planes*pad64(N)]  K-major (backward: dX = dZ W)."""
-
-    def __init__(self, W, b, planes, scale=1.0, need_t=True):
-        W = W.detach().contiguous().float()
-        self.N, self.K = W.shape
-        self.Np, self.Kp, self.Np64 = pad(self.N, 16), pad(self.K, 64), pad(self.N, 64)
-        dev = W.device
-        self.Wk = P(self.Np, self.Kp, planes, dev)
-        to_planes(W, self.Wk, self.N, self.K, False, scale, self.Np, self.Kp)
-        self.WTk = None
-        if need_t:
-            self.WTk = P(self.Kp, self.Np64, planes, dev)
-            to_planes(W, self.WTk, self.N, self.K, True, scale, self.Kp, self.Np64)
-        self.b = b.detach().contiguous().float() if b is not None else None
-        self.scale = scale
-        if self.b is not None and self.Np != self.N:
-            self.b = torch.cat([self.b, torch.zeros(self.Np - self.N, device=dev)])
-
-    def new_grad(self):
-        return torch.zeros(self.Np, self.Kp, dtype=torch.float32, device=self.Wk.t.device)

@@ -424,3 +424,22 @@ def test_cta_pair_variant_of_the_chain_kernel(monkeypatch):
     assert (t1.head[:, :3] - t2.head[:, :3]).abs().max().item() < 1e-5
     for l in range(3):
         assert torch.equal(t1.H[l].t[:M], t2.H[l].t[:M]) and torch.equal(t1.Mk[l], t2.Mk[l])
+
+
+def test_training_steps_reduce_the_loss():
+    """System check beyond gradient parity: 12 steps of the product trainer (ray-sharded trainer on one rank: global
+    denominators, flat gradient buffer, CUDA Adam) on a fixed ray batch and fixed target colours lower the trainer loss."""
+    from nu_nerf_b200 import dist as nd
+    from oracle import nunerf_oracle as orc
+    net = _renderer("bf16")
+    R = 512
+    o, d = (t.to(DEV) for t in orc.synthetic_rays(R))
+    gt = torch.full((R, 3), 0.25, device=DEV)
+    near, far = torch.full((R, 1), 0.8, device=DEV), torch.full((R, 1), 4.5, device=DEV)
+
+    def render_fn(o_, d_, n_, f_, step):
+        return net.render(o_, d_, n_, f_, None, 0, 0.2, is_train=True, step=step, is_nerf=True)
+    tr = nd.DataParallelTrainer(net, render_fn, net.compute_rgb_loss, lr_fn=lambda s: 5e-4, eikonal_weight=0.1)
+    losses = [float(tr.step(o, d, gt, near, far, 10000, chunk=R)) for _ in range(12)]
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < 0.8 * losses[0], losses

@@ -1,5 +1,6 @@
-"""Config 5 of BASELINE.json: extract_fields N^3 SDF sweep (field.py:1286-1307) on the fused inference kernel.
-Prints device time (CUDA events), end-to-end time including the single D2H copy, and the tensor-pipe fraction."""
+"""Config 5 of BASELINE.json: stage-1 EVAL render (is_train=False, 4096-ray chunks: ray_rgb, depth, normal -- ZT:614-655)
+and the extract_fields N^3 SDF sweep (field.py:1286-1307) on the fused inference kernel.  Prints device times (CUDA
+events), the sweep's end-to-end time including the single D2H copy, and the tensor-pipe fraction."""
 import json
 import os
 import sys
@@ -32,12 +33,33 @@ def main():
     t0 = time.perf_counter()
     uh = extract_fields(bmin, bmax, res, net.sdf_network.sdf)
     wall = time.perf_counter() - t0
+    # eval render: sphere-bounded near/far, no perturbation, validation outputs (depth, normal)
+    from oracle import nunerf_oracle as orc            # seeded synthetic ray generator only
+    R = 4096
+    o, d = (t.cuda() for t in orc.synthetic_rays(R))
+    near, far = net.near_far_from_sphere(o, d)
+
+    def eval_render():
+        with torch.no_grad():
+            return net.render(o, d, near, far, None, 0, 0.2, is_train=False, step=10000, is_nerf=False)
+    for _ in range(3):
+        out = eval_render()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(10):
+        out = eval_render()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_eval = e0.elapsed_time(e1) / 10
+    assert out["depth"].shape == (R, 1) and out["normal"].shape == (R, 3)
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
         if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 1400.0
     tf = 2.0 * M_SDF_HEAD * res ** 3 / (ms * 1e-3) / 1e12
     print(json.dumps({"workload": f"extract_fields {res}^3 SDF sweep (bf16 fused chain)", "device_ms": ms,
                       "end_to_end_s_with_d2h": wall, "points": res ** 3, "Mpts_per_s": res ** 3 / ms / 1e3,
-                      "tflops": tf, "frac_of_tensor_peak": tf / peak, "inside_fraction": float((uh < 1.0).mean())}))
+                      "tflops": tf, "frac_of_tensor_peak": tf / peak, "inside_fraction": float((uh < 1.0).mean()),
+                      "eval_render": {"rays": R, "ms": ms_eval, "rays_per_s": R / ms_eval * 1e3,
+                                      "outputs": "ray_rgb, depth, normal, acc, color_bkgr, color_spec (is_train=False)"}}))
 
 
 if __name__ == "__main__":
