@@ -443,3 +443,42 @@ def test_training_steps_reduce_the_loss():
     losses = [float(tr.step(o, d, gt, near, far, 10000, chunk=R)) for _ in range(12)]
     assert all(np.isfinite(losses)), losses
     assert losses[-1] < 0.8 * losses[0], losses
+
+
+@pytest.mark.parametrize("precision,tol", [("split", 1e-4), ("bf16", 5e-3)])
+def test_edge_cases_single_ray_and_empty_inner_set(precision, tol):
+    """Ragged / empty inputs (the reference's boolean-mask indexing degenerates silently; the compacted engine must too):
+    a batch of one ray, and a batch whose rays all miss the unit sphere (no inner sample: no SDF / shading work, the
+    NeRF++ background alone composites), forward + backward against the oracle."""
+    from oracle import nunerf_oracle as orc
+    net = _renderer(precision)
+    sdp, _ = _oracle_params(net)
+    cases = []
+    o1, d1 = orc.synthetic_rays(1)
+    cases.append(("single ray", o1, d1))
+    o5 = torch.tensor([[3.0, 0.0, 0.0]]).repeat(5, 1) + 0.01 * torch.arange(5)[:, None]
+    d5 = torch.nn.functional.normalize(torch.tensor([[0.0, 1.0, 0.2]]).repeat(5, 1), dim=-1)     # tangent, 3 units away
+    cases.append(("all rays miss the sphere", o5, d5))
+    for name, o, d in cases:
+        R = o.shape[0]
+        U0, U1 = orc.synthetic_uniforms(R)
+        near, far = torch.full((R, 1), 0.8), torch.full((R, 1), 4.5)
+        gt = orc.synthetic_targets(R)
+        with torch.no_grad():
+            z = orc.sample_ray(sdp, o, d, near, far, U0, U1)
+            ref = orc.render_core(sdp, o, d, z, 0.2, 10000)
+        net.zero_grad()
+        out = net.render_core(o.to(DEV), d.to(DEV), z.to(DEV), None, cos_anneal_ratio=0.2, step=10000, is_train=True,
+                              is_nerf=True)
+        assert out["gradient_error"].shape == ref["gradient_error"].shape, name
+        if name.startswith("all rays miss"):
+            assert "transmission" not in out or out["transmission"].shape[0] == 0
+        for k in ("ray_rgb", "acc", "color_bkgr", "color_spec"):
+            err = (out[k].detach().cpu() - ref[k]).abs().max().item()
+            assert err < tol, (name, k, err)
+        loss = net.compute_rgb_loss(out["ray_rgb"], gt.to(DEV)).mean() + (0.1 * out["gradient_error"]).mean()
+        loss.backward()
+        g = net.outer_nerf.pts_linears[0].weight.grad
+        assert g is not None and torch.isfinite(g).all(), name
+        z_gpu = net.sample_ray(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), 1.0, uniforms=(U0.to(DEV), U1.to(DEV)))
+        assert z_gpu.shape == (R, 160) and torch.isfinite(z_gpu).all(), name
