@@ -203,7 +203,8 @@ def hbm_work(name, a):
         return R * (24.0 + 8.0 + 132.0 + 4.0 * 96)
     if name == "nunerf_render_geometry":
         R, S = a[3], a[4]
-        return R * (24.0 + 56.0 * S)
+        # o, d + z in; compact points / dists / dirs (28 B per sample) + the per-ray map (40 B) out
+        return R * (24.0 + 4.0 * S + 28.0 * S + 40.0)
     return 0.0
 
 

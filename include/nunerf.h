@@ -147,20 +147,25 @@ int nunerf_merge_sdf(const float* sdf, const float* sdf_new, const int32_t* perm
  *   inner / outer sample sets (the order of the reference's boolean-mask indexing): slot[R*S] >= 0 -> index in
  *   the inner list, < 0 -> -1 - index in the outer list; counts[2] = {N_in, N_out}; ray_scratch: 2R ints.
  *   The compact arrays (capacity R*S each) receive points, dists, normalised ray dirs and the flat sample id.
+ *   ray_map (optional, 10 ints per ray): the same map in compact form -- [0] / [1] index of the ray's first inner / outer
+ *   sample in its list, [2 + k] bit mask of the inner samples among samples 32k .. 32k+31; the compositing kernels take
+ *   either form.  dists, pts, slot, id_in, id_out may be NULL when not needed.
  * nunerf_composite_fwd/bwd (ZT:773-788): w = a * excl_cumprod(1-a+1e-7); rgb = clamp(sum w c (+1-acc)); acc;
  *   background-only composite.  Backward recomputes the transmittance instead of storing it.
  */
 int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists, float* pts,
                            int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in, float* dists_in,
                            float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out, float* dirs_out,
-                           int32_t* id_out, void* stream);
+                           int32_t* id_out, int32_t* ray_map, void* stream);
 int nunerf_composite_fwd(const float* alpha_in, const float* color_in, const float* alpha_out,
                          const float* color_out, const int32_t* slot, int R, int S, int is_nerf, float* rgb,
-                         float* rgb_raw, float* acc, float* rgb_bkgr, float* weights, void* stream);
+                         float* rgb_raw, float* acc, float* rgb_bkgr, float* weights, const int32_t* ray_map,
+                         void* stream);
 int nunerf_composite_bwd(const float* alpha_in, const float* color_in, const float* alpha_out,
                          const float* color_out, const int32_t* slot, int R, int S, int is_nerf, const float* rgb_raw,
                          const float* d_rgb, const float* d_acc, const float* d_rgb_bkgr, float* d_alpha_in,
-                         float* d_color_in, float* d_alpha_out, float* d_color_out, void* stream);
+                         float* d_color_in, float* d_alpha_out, float* d_color_out, const int32_t* ray_map,
+                         void* stream);
 int nunerf_scatter_rows(const float* src, int M, int C, const int32_t* sample_id, float* dst, void* stream);
 
 /* ------------------------------------------------------------------ encodings + pointwise field math */

@@ -102,9 +102,9 @@ _SIGS = {
     "nunerf_points": [vp, vp, vp, ci, ci, vp, vp],
     "nunerf_upsample": [vp, vp, vp, vp, ci, ci, ci, vp, cf, vp, vp, vp, vp, vp, vp],
     "nunerf_merge_sdf": [vp, vp, vp, ci, ci, ci, vp, vp],
-    "nunerf_render_geometry": [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
-    "nunerf_composite_fwd": [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp],
-    "nunerf_composite_bwd": [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "nunerf_render_geometry": [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    "nunerf_composite_fwd": [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp],
+    "nunerf_composite_bwd": [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "nunerf_scatter_rows": [vp, ci, ci, vp, vp, vp],
     "nunerf_encode_pe": [vp, ci, ci, ci, vp, ci, ci, ci, ci, ci, vp],
     "nunerf_sdf_grad_pe": [vp, vp, ci, vp, ci, ci, vp, vp],

@@ -52,8 +52,8 @@ __global__ void geometry_kernel(const float* __restrict__ o, const float* __rest
       float px = __fadd_rn(ox, __fmul_rn(dx, zm)), py = __fadd_rn(oy, __fmul_rn(dy, zm)),
             pz = __fadd_rn(oz, __fmul_rn(dz, zm));
       long long i = (long long)r * S + s;
-      dists[i] = dist;
-      pts[3 * i] = px; pts[3 * i + 1] = py; pts[3 * i + 2] = pz;
+      if (dists) dists[i] = dist;
+      if (pts) { pts[3 * i] = px; pts[3 * i + 1] = py; pts[3 * i + 2] = pz; }
       float nrm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
       ok = nrm <= 1.0f;
     }
@@ -102,17 +102,27 @@ __device__ __forceinline__ int scan_block_base(const int32_t* __restrict__ ray_i
   return acc;
 }
 
-// ---- geometry pass 3: slots + compact gather of both sets (row-major mask order, as points[inner_mask])
-__global__ void compact_kernel(const float* __restrict__ d, const float* __restrict__ pts, const float* __restrict__ dists,
+// The compaction map in its compact form, RAY_MAP ints per ray: [0] index of the ray's first inner sample in the inner
+// list, [1] of its first outer sample in the outer list, [2 + k] bit mask of the inner samples among samples 32k..32k+31.
+// (Boolean-mask indexing keeps the row-major order, so a ray's inner / outer samples are two contiguous runs.)  The
+// compositing kernels rebuild a sample's list index from it with two popcounts instead of reading a 4-byte slot per
+// sample.
+constexpr int RAY_MAP = 10;
+
+// ---- geometry pass 3: compact gather of both sets (row-major mask order, as points[inner_mask]); the per-sample
+//      geometry is recomputed from z with the arithmetic of pass 1 (bit-identical) instead of being re-read
+__global__ void compact_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
                                const int32_t* __restrict__ ray_inner, const int32_t* __restrict__ ray_off,
-                               int32_t* __restrict__ counts, int R, int S, int32_t* slot, float* pts_in,
-                               float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out,
-                               float* dirs_out, int32_t* id_out) {
+                               int32_t* __restrict__ counts, int R, int S, int32_t* slot, int32_t* ray_map,
+                               float* pts_in, float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out,
+                               float* dists_out, float* dirs_out, int32_t* id_out) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
   if (r >= R) return;
+  const float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
+  const float rdx = d[3 * r], rdy = d[3 * r + 1], rdz = d[3 * r + 2];
   // F.normalize(dirs) (ZT:740): d / max(||d||, 1e-12)
-  float dx = d[3 * r], dy = d[3 * r + 1], dz = d[3 * r + 2];
+  float dx = rdx, dy = rdy, dz = rdz;
   float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
   dx /= nrm; dy /= nrm; dz /= nrm;
   int in_run = ray_off[r] + scan_block_base(ray_inner, r / SCAN_BLOCK, lane);
@@ -121,34 +131,52 @@ __global__ void compact_kernel(const float* __restrict__ d, const float* __restr
     const int n_in = scan_block_base(ray_inner, (R + SCAN_BLOCK - 1) / SCAN_BLOCK, lane);
     if (lane == 0) { counts[0] = n_in; counts[1] = R * S - n_in; }
   }
+  if (ray_map && lane == 0) { ray_map[(long long)r * RAY_MAP] = in_run; ray_map[(long long)r * RAY_MAP + 1] = out_run; }
+  const float* zr = z + (long long)r * S;
   for (int s0 = 0; s0 < S; s0 += 32) {
     int s = s0 + lane;
     bool ok = s < S;
     long long i = (long long)r * S + (ok ? s : 0);
-    float px = pts[3 * i], py = pts[3 * i + 1], pz = pts[3 * i + 2];
+    float px = 0.f, py = 0.f, pz = 0.f, dist = 0.f;
+    if (ok) {
+      const float z0 = zr[s];
+      if (s + 1 < S) dist = __fsub_rn(zr[s + 1], z0);
+      else dist = __fsub_rn(z0, zr[s - 1]);
+      const float zm = __fadd_rn(z0, __fmul_rn(dist, 0.5f));
+      px = __fadd_rn(ox, __fmul_rn(rdx, zm)); py = __fadd_rn(oy, __fmul_rn(rdy, zm)); pz = __fadd_rn(oz, __fmul_rn(rdz, zm));
+    }
     float pn = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
     bool inner = ok && pn <= 1.0f;
     bool outer = ok && !inner;
     unsigned bi = __ballot_sync(FULL, inner), bo = __ballot_sync(FULL, outer);
     unsigned lt = (1u << lane) - 1u;
+    if (ray_map && lane == 0) ray_map[(long long)r * RAY_MAP + 2 + (s0 >> 5)] = (int32_t)bi;
     if (inner) {
       int k = in_run + __popc(bi & lt);
-      slot[i] = k;
+      if (slot) slot[i] = k;
       pts_in[3 * k] = px; pts_in[3 * k + 1] = py; pts_in[3 * k + 2] = pz;
-      dists_in[k] = dists[i];
+      dists_in[k] = dist;
       dirs_in[3 * k] = dx; dirs_in[3 * k + 1] = dy; dirs_in[3 * k + 2] = dz;
-      id_in[k] = (int32_t)i;
+      if (id_in) id_in[k] = (int32_t)i;
     } else if (outer) {
       int k = out_run + __popc(bo & lt);
-      slot[i] = -1 - k;
+      if (slot) slot[i] = -1 - k;
       pts_out[3 * k] = px; pts_out[3 * k + 1] = py; pts_out[3 * k + 2] = pz;
-      dists_out[k] = dists[i];
+      dists_out[k] = dist;
       dirs_out[3 * k] = dx; dirs_out[3 * k + 1] = dy; dirs_out[3 * k + 2] = dz;
-      id_out[k] = (int32_t)i;
+      if (id_out) id_out[k] = (int32_t)i;
     }
     in_run += __popc(bi);
     out_run += __popc(bo);
   }
+}
+
+// list index of sample (block k, lane) from the ray map: >= 0 inner, < 0 -> -1 - outer index (the slot convention)
+__device__ __forceinline__ int slot_from_map(int in_off, int out_off, unsigned mask, int inner_before, int k, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  const int in_lt = inner_before + __popc(mask & lt);
+  if ((mask >> lane) & 1u) return in_off + in_lt;
+  return -1 - (out_off + (k * 32 + lane) - in_lt);
 }
 
 // ---- compositing
@@ -174,16 +202,28 @@ __device__ __forceinline__ Sample fetch(const float* __restrict__ a_in, const fl
 template <int NBLK>
 __global__ void __launch_bounds__(32 * WPB) composite_fwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
                                      const float* __restrict__ a_out, const float* __restrict__ c_out,
-                                     const int32_t* __restrict__ slot, int R, int S, int is_nerf, float* rgb,
-                                     float* rgb_raw, float* acc, float* rgb_b, float* weights) {
+                                     const int32_t* __restrict__ slot, const int32_t* __restrict__ ray_map, int R, int S,
+                                     int is_nerf, float* rgb, float* rgb_raw, float* acc, float* rgb_b, float* weights) {
   const int lane = threadIdx.x & 31;
   const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
   if (r >= R) return;
   int sl[NBLK];
+  if (ray_map) {
+    const int32_t* rm = ray_map + (long long)r * RAY_MAP;
+    const int in_off = __ldg(rm), out_off = __ldg(rm + 1);
+    int before = 0;
 #pragma unroll
-  for (int k = 0; k < NBLK; ++k) {
-    const int s = k * 32 + lane;
-    sl[k] = s < S ? __ldg(slot + (long long)r * S + s) : 0;
+    for (int k = 0; k < NBLK; ++k) {
+      const unsigned m = (unsigned)__ldg(rm + 2 + k);
+      sl[k] = slot_from_map(in_off, out_off, m, before, k, lane);
+      before += __popc(m);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NBLK; ++k) {
+      const int s = k * 32 + lane;
+      sl[k] = s < S ? __ldg(slot + (long long)r * S + s) : 0;
+    }
   }
   Sample sm[NBLK];
 #pragma unroll
@@ -229,8 +269,8 @@ __global__ void __launch_bounds__(32 * WPB) composite_fwd_kernel(const float* __
 template <int NBLK>
 __global__ void __launch_bounds__(32 * WPB) composite_bwd_kernel(const float* __restrict__ a_in, const float* __restrict__ c_in,
                                      const float* __restrict__ a_out, const float* __restrict__ c_out,
-                                     const int32_t* __restrict__ slot, int R, int S, int is_nerf,
-                                     const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb,
+                                     const int32_t* __restrict__ slot, const int32_t* __restrict__ ray_map, int R, int S,
+                                     int is_nerf, const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb,
                                      const float* __restrict__ d_acc, const float* __restrict__ d_rgb_b,
                                      float* d_a_in, float* d_c_in, float* d_a_out, float* d_c_out) {
   const int lane = threadIdx.x & 31;
@@ -251,10 +291,22 @@ __global__ void __launch_bounds__(32 * WPB) composite_bwd_kernel(const float* __
   int sl[NBLK];
   float carry = 1.f, carry_b = 1.f;
   // all loads of the ray first (see composite_fwd_kernel)
+  if (ray_map) {
+    const int32_t* rm = ray_map + (long long)r * RAY_MAP;
+    const int in_off = __ldg(rm), out_off = __ldg(rm + 1);
+    int before = 0;
 #pragma unroll
-  for (int k = 0; k < NBLK; ++k) {
-    const int s = k * 32 + lane;
-    sl[k] = (k < nblk && s < S) ? __ldg(slot + (long long)r * S + s) : 0;
+    for (int k = 0; k < NBLK; ++k) {
+      const unsigned m = (unsigned)__ldg(rm + 2 + k);
+      sl[k] = slot_from_map(in_off, out_off, m, before, k, lane);
+      before += __popc(m);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NBLK; ++k) {
+      const int s = k * 32 + lane;
+      sl[k] = (k < nblk && s < S) ? __ldg(slot + (long long)r * S + s) : 0;
+    }
   }
   Sample smp[NBLK];
 #pragma unroll
@@ -327,17 +379,16 @@ using namespace nunerf;
 extern "C" int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists,
                                       float* pts, int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in,
                                       float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out,
-                                      float* dirs_out, int32_t* id_out, void* stream_) {
+                                      float* dirs_out, int32_t* id_out, int32_t* ray_map, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  NUNERF_REQUIRE(o && d && z && dists && pts && slot && counts && ray_scratch, "render_geometry: null argument");
-  NUNERF_REQUIRE(pts_in && dists_in && dirs_in && id_in && pts_out && dists_out && dirs_out && id_out,
-                 "render_geometry: null compact buffer");
+  NUNERF_REQUIRE(o && d && z && counts && ray_scratch && (slot || ray_map), "render_geometry: null argument");
+  NUNERF_REQUIRE(pts_in && dists_in && dirs_in && pts_out && dists_out && dirs_out, "render_geometry: null compact buffer");
   NUNERF_REQUIRE(R > 0 && S >= 2 && S <= 256, "render_geometry: need 2 <= S <= 256");
   geometry_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, R, S, dists, pts, ray_scratch);
   NUNERF_CHECK_LAUNCH("geometry_kernel");
   ray_scan_kernel<<<cdiv(R, SCAN_BLOCK), SCAN_BLOCK, 0, stream>>>(ray_scratch, R, ray_scratch + R);
   NUNERF_CHECK_LAUNCH("ray_scan_kernel");
-  compact_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(d, pts, dists, ray_scratch, ray_scratch + R, counts, R, S, slot,
+  compact_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, ray_scratch, ray_scratch + R, counts, R, S, slot, ray_map,
                                                        pts_in, dists_in, dirs_in, id_in, pts_out, dists_out, dirs_out,
                                                        id_out);
   NUNERF_CHECK_LAUNCH("compact_kernel");
@@ -346,14 +397,16 @@ extern "C" int nunerf_render_geometry(const float* o, const float* d, const floa
 
 extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in, const float* alpha_out,
                                     const float* color_out, const int32_t* slot, int R, int S, int is_nerf, float* rgb,
-                                    float* rgb_raw, float* acc, float* rgb_bkgr, float* weights, void* stream) {
-  NUNERF_REQUIRE(slot && rgb && rgb_raw && acc && rgb_bkgr && R > 0 && S > 0 && S <= 256, "composite_fwd: bad arguments");
+                                    float* rgb_raw, float* acc, float* rgb_bkgr, float* weights,
+                                    const int32_t* ray_map, void* stream) {
+  NUNERF_REQUIRE((slot || ray_map) && rgb && rgb_raw && acc && rgb_bkgr && R > 0 && S > 0 && S <= 256,
+                 "composite_fwd: bad arguments");
   if (S <= 160)
     composite_fwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
-        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
+        alpha_in, color_in, alpha_out, color_out, slot, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   else
     composite_fwd_kernel<8><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
-        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
+        alpha_in, color_in, alpha_out, color_out, slot, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   NUNERF_CHECK_LAUNCH("composite_fwd_kernel");
   return 0;
 }
@@ -362,17 +415,18 @@ extern "C" int nunerf_composite_bwd(const float* alpha_in, const float* color_in
                                     const float* color_out, const int32_t* slot, int R, int S, int is_nerf,
                                     const float* rgb_raw, const float* d_rgb, const float* d_acc,
                                     const float* d_rgb_bkgr, float* d_alpha_in, float* d_color_in, float* d_alpha_out,
-                                    float* d_color_out, void* stream) {
-  NUNERF_REQUIRE(slot && rgb_raw && d_alpha_in && d_color_in && d_alpha_out && d_color_out && R > 0 && S > 0 && S <= 256,
+                                    float* d_color_out, const int32_t* ray_map, void* stream) {
+  NUNERF_REQUIRE((slot || ray_map) && rgb_raw && d_alpha_in && d_color_in && d_alpha_out && d_color_out && R > 0 && S > 0 &&
+                     S <= 256,
                  "composite_bwd: bad arguments");
   if (S <= 160)
     composite_bwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
-        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
-        d_color_in, d_alpha_out, d_color_out);
+        alpha_in, color_in, alpha_out, color_out, slot, ray_map, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr,
+        d_alpha_in, d_color_in, d_alpha_out, d_color_out);
   else
     composite_bwd_kernel<8><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
-        alpha_in, color_in, alpha_out, color_out, slot, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
-        d_color_in, d_alpha_out, d_color_out);
+        alpha_in, color_in, alpha_out, color_out, slot, ray_map, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr,
+        d_alpha_in, d_color_in, d_alpha_out, d_color_out);
   NUNERF_CHECK_LAUNCH("composite_bwd_kernel");
   return 0;
 }

@@ -627,19 +627,18 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
     o, d = rays_o.contiguous().float(), rays_d.contiguous().float()
     z = z_vals.contiguous().float()
     i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
-    dists, pts = _f(R, S, dev=dev), _f(R, S, 3, dev=dev)
-    t.slot, counts, scratch = i32(R, S), i32(2), i32(2 * R)
+    # compaction map in its per-ray form (offsets + inner bit masks, csrc/composite.cu RAY_MAP); the per-sample slot
+    # array, the dense [R,S] dists / points and the flat sample ids are not needed by the step and are not written
+    t.ray_map, counts, scratch = i32(R, 10), i32(2), i32(2 * R)
     cap = R * S
-    pts_in, dists_in, dirs_in, id_in = _f(cap, 3, dev=dev), _f(cap, dev=dev), _f(cap, 3, dev=dev), i32(cap)
-    pts_out, dists_out, dirs_out, id_out = _f(cap, 3, dev=dev), _f(cap, dev=dev), _f(cap, 3, dev=dev), i32(cap)
-    call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, dists.data_ptr(), pts.data_ptr(),
-         t.slot.data_ptr(), counts.data_ptr(), scratch.data_ptr(), pts_in.data_ptr(), dists_in.data_ptr(),
-         dirs_in.data_ptr(), id_in.data_ptr(), pts_out.data_ptr(), dists_out.data_ptr(), dirs_out.data_ptr(),
-         id_out.data_ptr())
+    pts_in, dists_in, dirs_in = _f(cap, 3, dev=dev), _f(cap, dev=dev), _f(cap, 3, dev=dev)
+    pts_out, dists_out, dirs_out = _f(cap, 3, dev=dev), _f(cap, dev=dev), _f(cap, 3, dev=dev)
+    call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, None, None, None, counts.data_ptr(),
+         scratch.data_ptr(), pts_in.data_ptr(), dists_in.data_ptr(), dirs_in.data_ptr(), None, pts_out.data_ptr(),
+         dists_out.data_ptr(), dirs_out.data_ptr(), None, t.ray_map.data_ptr())
     n_in, n_out = (int(v) for v in counts.tolist())     # the one host sync of the step (output shapes need it)
     t.n_in, t.n_out = n_in, n_out
     t.pts_in, t.dists_in, t.dirs_in = pts_in[:n_in], dists_in[:n_in], dirs_in[:n_in]
-    t.pts, t.dists = pts, dists
 
     # ---- outer samples: NeRF++ (ZT:743-751)
     if n_out > 0:
@@ -657,8 +656,8 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
     rgb, t.rgb_raw, acc, bkgr = _f(R, 3, dev=dev), _f(R, 3, dev=dev), _f(R, dev=dev), _f(R, 3, dev=dev)
     weights = _f(R, S, dev=dev)
     call("nunerf_composite_fwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
-         t.slot.data_ptr(), R, S, t.is_nerf, rgb.data_ptr(), t.rgb_raw.data_ptr(), acc.data_ptr(), bkgr.data_ptr(),
-         weights.data_ptr())
+         None, R, S, t.is_nerf, rgb.data_ptr(), t.rgb_raw.data_ptr(), acc.data_ptr(), bkgr.data_ptr(),
+         weights.data_ptr(), t.ray_map.data_ptr())
     # ---- per-ray specular probe: outer_light(IDE(d, 0)) (ZT:780-781), activation applied by the caller
     t.xs = P(R, 128, planes, dev)
     t.dn = _norm_dirs(d)
@@ -701,14 +700,14 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
                   d_occ=None):
     """Reverse launch sequence of core_forward.  Returns {reference parameter name -> gradient of the EFFECTIVE
     weight / bias} (+ 'inv_s')."""
-    planes, dev = w.planes, t.slot.device
+    planes, dev = w.planes, t.ray_map.device
     R, S, M = t.R, t.S, t.n_in
     g = {}
     da_in, dc_in = _f(max(M, 1), dev=dev), _f(max(M, 1), 3, dev=dev)
     da_out, dc_out = _f(max(t.n_out, 1), dev=dev), _f(max(t.n_out, 1), 3, dev=dev)
     call("nunerf_composite_bwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
-         t.slot.data_ptr(), R, S, t.is_nerf, t.rgb_raw.data_ptr(), ptr(d_rgb), ptr(d_acc), ptr(d_bkgr),
-         da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
+         None, R, S, t.is_nerf, t.rgb_raw.data_ptr(), ptr(d_rgb), ptr(d_acc), ptr(d_bkgr),
+         da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr(), t.ray_map.data_ptr())
     if t.n_out > 0:
         nerf_backward(w.nerf, t.nerf, da_out, dc_out, planes)
 

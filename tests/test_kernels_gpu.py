@@ -209,11 +209,20 @@ def _geometry(o, d, z):
     i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=DEV)
     out = dict(dists=f(R, S), pts=f(R, S, 3), slot=i32(R, S), counts=i32(2), scratch=i32(2 * R),
                pts_in=f(R * S, 3), dists_in=f(R * S), dirs_in=f(R * S, 3), id_in=i32(R * S),
-               pts_out=f(R * S, 3), dists_out=f(R * S), dirs_out=f(R * S, 3), id_out=i32(R * S))
+               pts_out=f(R * S, 3), dists_out=f(R * S), dirs_out=f(R * S, 3), id_out=i32(R * S), ray_map=i32(R, 10))
     _lib.call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, *[out[k].data_ptr() for k in
               ("dists", "pts", "slot", "counts", "scratch", "pts_in", "dists_in", "dirs_in", "id_in", "pts_out",
-               "dists_out", "dirs_out", "id_out")])
+               "dists_out", "dirs_out", "id_out", "ray_map")])
     return out
+
+
+def _slot_from_ray_map(ray_map, R, S):
+    """The per-sample slot array rebuilt (on the CPU) from the compact per-ray map: offsets + inner bit masks."""
+    rm = ray_map.cpu().long()
+    bits = ((rm[:, 2:, None] >> torch.arange(32)) & 1).reshape(R, -1)[:, :S].bool()
+    in_idx = rm[:, 0:1] + torch.cumsum(bits.long(), 1) - bits.long()
+    out_idx = rm[:, 1:2] + torch.cumsum((~bits).long(), 1) - (~bits).long()
+    return torch.where(bits, in_idx, -1 - out_idx).int()
 
 
 def test_render_geometry_and_compaction_order():
@@ -243,6 +252,20 @@ def test_render_geometry_and_compaction_order():
     assert torch.equal(out["id_in"][:n_in].cpu().long(), torch.nonzero(gi.reshape(-1))[:, 0])
     dn = torch.nn.functional.normalize(d, dim=-1)[:, None, :].expand(R, S, 3)
     assert (out["dirs_in"][:n_in].cpu() - dn[gi]).abs().max().item() <= 2e-7
+    # the compact per-ray form of the map (what the engine passes to the compositing kernels) describes the same slots
+    assert torch.equal(_slot_from_ray_map(out["ray_map"], R, S), out["slot"].cpu())
+    # optional outputs: with dists / pts / slot / ids omitted the compact arrays and the map are unchanged
+    from nu_nerf_b200 import _lib
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=DEV)
+    lean = dict(counts=i32(2), scratch=i32(2 * R), pts_in=f(R * S, 3), dists_in=f(R * S), dirs_in=f(R * S, 3),
+                pts_out=f(R * S, 3), dists_out=f(R * S), dirs_out=f(R * S, 3), ray_map=i32(R, 10))
+    _lib.call("nunerf_render_geometry", do.data_ptr(), dd.data_ptr(), dzz.data_ptr(), R, S, None, None, None,
+              lean["counts"].data_ptr(), lean["scratch"].data_ptr(), lean["pts_in"].data_ptr(), lean["dists_in"].data_ptr(),
+              lean["dirs_in"].data_ptr(), None, lean["pts_out"].data_ptr(), lean["dists_out"].data_ptr(),
+              lean["dirs_out"].data_ptr(), None, lean["ray_map"].data_ptr())
+    for k in ("counts", "pts_in", "dists_in", "dirs_in", "pts_out", "dists_out", "dirs_out", "ray_map"):
+        assert torch.equal(lean[k], out[k]), k
 
 
 def test_composite_forward_and_backward():
@@ -264,7 +287,16 @@ def test_composite_forward_and_backward():
     rgb, raw, acc, bk, w = (torch.zeros(R, 3, device=DEV), torch.zeros(R, 3, device=DEV), torch.zeros(R, device=DEV),
                             torch.zeros(R, 3, device=DEV), torch.zeros(R, S, device=DEV))
     _lib.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
-              geo["slot"].data_ptr(), R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), w.data_ptr())
+              geo["slot"].data_ptr(), R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), w.data_ptr(),
+              None)
+    # same through the compact per-ray map: bit-identical
+    rgb2, raw2, acc2, bk2, w2 = (torch.zeros_like(rgb), torch.zeros_like(raw), torch.zeros_like(acc), torch.zeros_like(bk),
+                                 torch.zeros_like(w))
+    _lib.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+              None, R, S, 1, rgb2.data_ptr(), raw2.data_ptr(), acc2.data_ptr(), bk2.data_ptr(), w2.data_ptr(),
+              geo["ray_map"].data_ptr())
+    for a_, b_ in ((rgb, rgb2), (raw, raw2), (acc, acc2), (bk, bk2), (w, w2)):
+        assert torch.equal(a_, b_)
     # torch fp32 reference (ZT:773-788)
     alpha = torch.zeros(R, S, device=DEV).masked_scatter(inner, a_in).masked_scatter(~inner, a_out)
     color = torch.zeros(R, S, 3, device=DEV).masked_scatter(inner[..., None].expand(-1, -1, 3), c_in) \
@@ -289,10 +321,16 @@ def test_composite_forward_and_backward():
                                     torch.zeros_like(c_out))
     _lib.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
               geo["slot"].data_ptr(), R, S, 1, raw.data_ptr(), g_rgb.data_ptr(), g_acc.data_ptr(), g_bk.data_ptr(),
-              da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
+              da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr(), None)
     for mine, ref in ((da_in, a_in.grad), (dc_in, c_in.grad), (da_out, a_out.grad), (dc_out, c_out.grad)):
         scale = ref.abs().max().item()
         assert (mine - ref).abs().max().item() < 1e-4 * scale, ((mine - ref).abs().max().item(), scale)
+    m2 = [torch.zeros_like(x) for x in (da_in, dc_in, da_out, dc_out)]
+    _lib.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+              None, R, S, 1, raw.data_ptr(), g_rgb.data_ptr(), g_acc.data_ptr(), g_bk.data_ptr(),
+              m2[0].data_ptr(), m2[1].data_ptr(), m2[2].data_ptr(), m2[3].data_ptr(), geo["ray_map"].data_ptr())
+    for a_, b_ in zip((da_in, dc_in, da_out, dc_out), m2):
+        assert torch.equal(a_, b_)
 
 
 # ----------------------------------------------------------------------------------------- tracing

@@ -62,24 +62,25 @@ def main():
             R_, S = z.shape
             i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
             f = lambda *s: torch.empty(*s, device=dev)
-            dists, pts = f(R, S), f(R, S, 3)
-            slot, counts, scratch = i32(R, S), i32(2), i32(2 * R)
+            ray_map, counts, scratch = i32(R, 10), i32(2), i32(2 * R)
             cap = R * S
-            bufs = [f(cap, 3), f(cap), f(cap, 3), i32(cap), f(cap, 3), f(cap), f(cap, 3), i32(cap)]
-            eng.call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, dists.data_ptr(),
-                     pts.data_ptr(), slot.data_ptr(), counts.data_ptr(), scratch.data_ptr(), *[b.data_ptr() for b in bufs])
+            bufs = [f(cap, 3), f(cap), f(cap, 3), f(cap, 3), f(cap), f(cap, 3)]
+            eng.call("nunerf_render_geometry", o.data_ptr(), d.data_ptr(), z.data_ptr(), R, S, None, None, None,
+                     counts.data_ptr(), scratch.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), None,
+                     bufs[3].data_ptr(), bufs[4].data_ptr(), bufs[5].data_ptr(), None, ray_map.data_ptr())
             n_in, n_out = (int(v) for v in counts.tolist())
             blocker()
             a_in, c_in = torch.rand(n_in, device=dev) * 0.1, torch.rand(n_in, 3, device=dev)
             a_out, c_out = torch.rand(n_out, device=dev) * 0.05, torch.rand(n_out, 3, device=dev)
             rgb, raw, acc, bk, wts = f(R, 3), f(R, 3), f(R), f(R, 3), f(R, S)
             eng.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
-                     slot.data_ptr(), R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), wts.data_ptr())
+                     None, R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), wts.data_ptr(),
+                     ray_map.data_ptr())
             d_rgb, d_acc, d_bk = torch.randn(R, 3, device=dev), torch.randn(R, device=dev), torch.randn(R, 3, device=dev)
             da_in, dc_in, da_out, dc_out = f(n_in), f(n_in, 3), f(n_out), f(n_out, 3)
             eng.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
-                     slot.data_ptr(), R, S, 1, raw.data_ptr(), d_rgb.data_ptr(), d_acc.data_ptr(), d_bk.data_ptr(),
-                     da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr())
+                     None, R, S, 1, raw.data_ptr(), d_rgb.data_ptr(), d_acc.data_ptr(), d_bk.data_ptr(),
+                     da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr(), ray_map.data_ptr())
         torch.cuda.synchronize()
     finally:
         eng.call = orig
