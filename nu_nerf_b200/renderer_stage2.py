@@ -419,6 +419,23 @@ class Stage2Renderer(nn.Module):
         ret["tir_mask"] = tir_mask
         return ret
 
+    # ------------------------------------------------------------------ ZT:1090-1123
+    @torch.no_grad()
+    def nvs(self, pose, K, h, w, chunk=4096):
+        """Novel-view synthesis through the refraction path: `pose` [3,4] world-to-camera, `K` [3,3] -> ray_rgb [h,w,3]
+        numpy (eval settings of the reference: is_train=False, step 300000)."""
+        from . import feeder
+        dev = self.deviation_network_inner.variance.device
+        as_t = lambda a: (torch.from_numpy(np.asarray(a, dtype=np.float32)) if not torch.is_tensor(a) else a.float()).to(dev)
+        K_, pose_ = as_t(K).unsqueeze(0), as_t(pose).unsqueeze(0)
+        batch, rn, _, _ = feeder.construct_ray_batch(torch.zeros(1, 3, h, w, device=dev), K_)
+        colors = []
+        for ri in range(0, rn, chunk):
+            rays_o, rays_d = feeder.world_rays(batch["dirs"][ri:ri + chunk], batch["idxs"][ri:ri + chunk], pose_)
+            out = self.render(rays_o.contiguous(), rays_d.contiguous(), None, None, None, 0, 0, is_train=False, step=300000)
+            colors.append(out["ray_rgb"])
+        return torch.cat(colors, 0).reshape(h, w, 3).cpu().numpy()
+
     def forward(self, data):
         step = data["step"]
         if "eval" in data or self.ray_source is None:

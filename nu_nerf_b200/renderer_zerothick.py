@@ -352,6 +352,50 @@ class NeROShapeRenderer(nn.Module):
         return self.render_core(rays_o, rays_d, z_vals, human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step,
                                 is_train=is_train, is_nerf=is_nerf, prepared=prepared, occ_perm=occ_perm)
 
+    # ------------------------------------------------------------------ ZT:278-311
+    @torch.no_grad()
+    def nvs(self, pose, K, h, w, chunk=8192):
+        """Novel-view synthesis: `pose` [3,4] world-to-camera, `K` [3,3] (numpy or tensors) -> ray_rgb [h,w,3] numpy, with
+        the reference's eval settings (sphere-bounded near/far, no perturbation, cos_anneal 0, step 300000)."""
+        from . import feeder
+        dev = self.deviation_network.variance.device
+        as_t = lambda a: (torch.from_numpy(np.asarray(a, dtype=np.float32)) if not torch.is_tensor(a) else a.float()).to(dev)
+        K_, pose_ = as_t(K).unsqueeze(0), as_t(pose).unsqueeze(0)
+        batch, rn, _, _ = feeder.construct_ray_batch(torch.zeros(1, 3, h, w, device=dev), K_)
+        colors = []
+        for ri in range(0, rn, chunk):
+            rays_o, rays_d = feeder.world_rays(batch["dirs"][ri:ri + chunk], batch["idxs"][ri:ri + chunk], pose_)
+            near, far = self.near_far_from_sphere(rays_o, rays_d)
+            out = self.render(rays_o.contiguous(), rays_d.contiguous(), near, far, None, 0, 0, is_train=False, step=300000)
+            colors.append(out["ray_rgb"])
+        return torch.cat(colors, 0).reshape(h, w, 3).cpu().numpy()
+
+    # ------------------------------------------------------------------ ZT:846-864, field.py:779-783
+    @torch.no_grad()
+    def predict_materials(self, xyz=None, batch_size=8192 * 8):
+        """metallic / roughness / albedo of the material predictors at surface points.  The reference reads the vertices
+        of `data/meshes/{name}-300000.ply` (ZT:847-849); here `xyz` is an [N,3] tensor / array of points, or a mesh file
+        path (.ply / .npz, nu_nerf_b200.tracer.load_mesh), or None for the reference's default path."""
+        eng = _engine()
+        w = self._prepare()
+        dev = self.deviation_network.variance.device
+        if xyz is None or isinstance(xyz, str):
+            from .tracer import load_mesh
+            xyz = load_mesh(xyz if xyz is not None else f"data/meshes/{self.cfg['name']}-300000.ply")[0]
+        pts_all = torch.as_tensor(np.asarray(xyz, dtype=np.float32) if not torch.is_tensor(xyz) else xyz).float().to(dev)
+        res = {"metallic": [], "roughness": [], "albedo": []}
+        for vi in range(0, pts_all.shape[0], batch_size):
+            pts = pts_all[vi:vi + batch_size].contiguous()
+            M = pts.shape[0]
+            xm = eng.P(M, 320, w.planes, dev)
+            eng.f32_to_planes(pts, xm, M, 3, 64, col=256)
+            eng.sdf_forward(w.sdf, pts, w.planes, xm)                       # feature vector -> xm[:, :256]
+            for key, name, n in (("metallic", "metallic_predictor", 1), ("roughness", "roughness_predictor", 1),
+                                 ("albedo", "albedo_predictor", 3)):
+                head = eng.pred_forward(w.pred[name], xm, M, 320, w.planes).head[:, :n]
+                res[key].append(torch.sigmoid(head).cpu().numpy())
+        return {k: np.concatenate(v, 0) for k, v in res.items()}
+
     # ------------------------------------------------------------------ ZT:447-466
     def train_step(self, step):
         if self.ray_source is None:

@@ -482,3 +482,42 @@ def test_edge_cases_single_ray_and_empty_inner_set(precision, tol):
         assert g is not None and torch.isfinite(g).all(), name
         z_gpu = net.sample_ray(o.to(DEV), d.to(DEV), near.to(DEV), far.to(DEV), 1.0, uniforms=(U0.to(DEV), U1.to(DEV)))
         assert z_gpu.shape == (R, 160) and torch.isfinite(z_gpu).all(), name
+
+
+def test_helper_methods_nvs_and_predict_materials():
+    """The two helper entry points other scripts of the reference call on the renderer: predict_materials
+    (ZT:846-864, field.py:779-783) against the oracle's predictors, and nvs (ZT:278-311) against rendering the same
+    pixel rays through render() directly."""
+    from nu_nerf_b200 import feeder
+    from oracle import nunerf_oracle as orc
+    net = _renderer("split")
+    sdp, _ = _oracle_params(net)
+    g = torch.Generator().manual_seed(5)
+    xyz = torch.nn.functional.normalize(torch.randn(700, 3, generator=g), dim=-1) * 0.5
+    mats = net.predict_materials(xyz)
+    with torch.no_grad():
+        y = orc.sdf_forward(sdp, xyz)
+        x = torch.cat([y[:, 1:], xyz], -1)
+        ref = {"metallic": orc.predictor(sdp, "color_network.metallic_predictor", x, "sigmoid"),
+               "roughness": orc.predictor(sdp, "color_network.roughness_predictor", x, "sigmoid"),
+               "albedo": orc.predictor(sdp, "color_network.albedo_predictor", x, "sigmoid")}
+    for k in ref:
+        assert mats[k].shape == tuple(ref[k].shape), k
+        assert np.abs(mats[k] - ref[k].numpy()).max() < 1e-4, (k, np.abs(mats[k] - ref[k].numpy()).max())
+    # nvs: a camera at z = +3 looking at the origin (OpenCV axes: x right, y down, z forward), world-to-camera pose
+    h, w = 12, 16
+    K = np.array([[30.0, 0, 8.0], [0, 30.0, 6.0], [0, 0, 1]], dtype=np.float32)
+    Rm = np.diag([1.0, -1.0, -1.0]).astype(np.float32)
+    cam = np.array([0.0, 0.0, 3.0], dtype=np.float32)
+    pose = np.concatenate([Rm, (-Rm @ cam)[:, None]], 1)
+    img = net.nvs(pose, K, h, w)
+    assert img.shape == (h, w, 3) and np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0
+    batch, _, _, _ = feeder.construct_ray_batch(torch.zeros(1, 3, h, w, device=DEV), torch.from_numpy(K)[None].to(DEV))
+    ro, rd = feeder.world_rays(batch["dirs"], batch["idxs"], torch.from_numpy(pose)[None].to(DEV))
+    assert (ro - torch.tensor([0.0, 0.0, 3.0], device=DEV)).abs().max().item() < 1e-5
+    near, far = net.near_far_from_sphere(ro, rd)
+    with torch.no_grad():
+        out = net.render(ro.contiguous(), rd.contiguous(), near, far, None, 0, 0, is_train=False, step=300000)
+    assert np.abs(img.reshape(-1, 3) - out["ray_rgb"].cpu().numpy()).max() < 1e-5
+    # the central pixel looks at the (radius-0.5) initial sphere: the ray must accumulate opacity there
+    assert out["acc"].reshape(h, w)[6, 8].item() > 0.5

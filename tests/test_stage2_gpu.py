@@ -191,3 +191,14 @@ def test_bf16_mode_gradients_are_close(golden):
         if nrel > 2e-2:
             bad.append((name, nrel))
     assert len(bad) <= 0.15 * n, sorted(bad, key=lambda b: -b[1])[:8]
+
+
+def test_nvs_renders_an_image(net):
+    """Stage2Renderer.nvs (ZT:1090-1123): a view of the nested spheres from z = +3 (world-to-camera pose)."""
+    h, w = 8, 12
+    K = np.array([[24.0, 0, 6.0], [0, 24.0, 4.0], [0, 0, 1]], dtype=np.float32)
+    Rm = np.diag([1.0, -1.0, -1.0]).astype(np.float32)
+    cam = np.array([0.0, 0.0, 3.0], dtype=np.float32)
+    pose = np.concatenate([Rm, (-Rm @ cam)[:, None]], 1)
+    img = net.nvs(pose, K, h, w)
+    assert img.shape == (h, w, 3) and np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0
