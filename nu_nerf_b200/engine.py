@@ -906,6 +906,44 @@ def surface_backward(w1: Stage1Weights, t, d_color, d_trans):
     inner_backward(w1, t, None, d_color, None, d_trans, None, False, surface=True)
 
 
+def shading_buffers(w: Stage1Weights, t, exp_max):
+    """The intermediate results of AppShadingNetwork.forward(inter_results=True) (field.py:749-772) rebuilt from the
+    predictor heads of a shade_forward tape: per-ray tensors of the eval path only (ZT:646-654, network/metrics.py)."""
+    M = t.n_in
+    nov, trans = t.nov[:, None], t.trans[:, None]
+    tn = torch.clamp(1.0 - nov, 0.0, 1.0)
+    refl_w = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)
+    head = lambda tp, n: tp.head[:, :n]
+    met = torch.sigmoid(head(t.mat["metallic_predictor"], 1))
+    rough = torch.sigmoid(head(t.mat["roughness_predictor"], 1))
+    alb = torch.sigmoid(head(t.mat["albedo_predictor"], 3))
+    ex = lambda x: torch.exp(torch.clamp(x, max=exp_max))
+    lo = head(t.lo_, 3)
+    diffuse_light, direct, direct0 = ex(lo[:M]), ex(lo[M:2 * M]), ex(lo[2 * M:3 * M])
+    li = head(t.li_, 3)
+    ind, ind0 = ex(li[:M]), ex(li[M:2 * M])
+    occ = head(t.lw_, 1) * 0.5 + 0.5
+    occ_c = torch.clamp(occ, 0.0, 1.0)
+    light = ind * occ_c + direct * (1 - occ_c)
+    light0 = ind0 * occ_c + direct0 * (1 - occ_c)
+    refr = ex(head(t.lr_, 3))
+    diffuse_albedo = (1 - met) * alb
+    spec_albedo = 0.04 * (1 - met) + met * alb
+    fg = _fg_lookup_torch(w.lut, torch.clamp(nov[:, 0], 0.0, 1.0), torch.clamp(rough[:, 0], 0.0, 1.0))
+    spec_ref = spec_albedo * fg[:, 0:1] + fg[:, 1:2]
+    spec_color = _lin2srgb(spec_ref * light)
+    c01 = lambda x: torch.clamp(x, 0.0, 1.0)
+    return {
+        "specular_albedo": spec_albedo, "specular_ref": c01(spec_ref), "specular_light": c01(_lin2srgb(light0)),
+        "specular_color": c01(spec_color * (1 - trans) + refl_w * light0 * trans),
+        "diffuse_albedo": diffuse_albedo, "diffuse_light": c01(_lin2srgb(diffuse_light)),
+        "diffuse_color": c01(_lin2srgb(diffuse_albedo * diffuse_light)),
+        "metallic": met, "transmission_weight": trans, "roughness": rough, "occ_prob": c01(occ),
+        "indirect_light": ind, "refraction_light": c01(_lin2srgb((1 - refl_w) * refr * trans)),
+        "reflection_weight": refl_w,
+    }
+
+
 def surface_extras(w1: Stage1Weights, t, exp_max):
     """eval-mode buffers of field.py:981-1001, rebuilt from the predictor heads (per-ray tensors)."""
     M = t.n_in

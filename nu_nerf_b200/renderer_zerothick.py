@@ -329,17 +329,30 @@ class NeROShapeRenderer(nn.Module):
         return torch.sum(weights(z_new), -1, keepdim=True)
 
     def compute_validation_info(self, z_vals, rays_o, rays_d, weights, human_poses, step, prepared=None):
-        """ZT:636-655: depth = sum w z ; normal = (normalize(grad sdf(o + depth d)) + 1) / 2 inside the unit sphere."""
+        """ZT:636-655: depth = sum w z ; normal = (normalize(grad sdf(o + depth d)) + 1) / 2 inside the unit sphere; the
+        shading network's intermediate buffers at the depth point (field.py:749-772) and the probed occlusion
+        probability `occ_prob_gt` (get_intersection with 128 + 9 samples, field.py:524-554), all masked to the sphere."""
         eng = _engine()
         w = prepared if prepared is not None else self._prepare()
         with torch.no_grad():
             depth = torch.sum(weights * z_vals, -1, keepdim=True)
             points = (depth * rays_d + rays_o).contiguous()
-            xm = eng.P(points.shape[0], 320, w.planes, points.device)
-            tape = eng.sdf_forward(w.sdf, points, w.planes, xm)
+            R, dev = points.shape[0], points.device
+            t = eng.inner_tape(points, rays_d.contiguous().float(), None, 0.0, self.color_network.cfg["light_exp_max"])
+            t.xm = eng.P(R, 320, w.planes, dev)
+            eng.f32_to_planes(points, t.xm, R, 3, 64, col=256)
+            t.sdf = eng.sdf_forward(w.sdf, points, w.planes, t.xm)
             inner = torch.norm(points, dim=-1, keepdim=True) <= 1.0
-            normal = ((F.normalize(tape.grad, dim=-1) + 1.0) * 0.5) * inner
-        return {"depth": depth, "normal": normal}
+            outputs = {"depth": depth, "normal": ((F.normalize(t.sdf.grad, dim=-1) + 1.0) * 0.5) * inner}
+            eng.shade_forward(w, t, t.sdf.grad)
+            occ_gt = torch.zeros(R, 1, device=dev)
+            inside = torch.norm(points, dim=-1) < 0.999
+            if bool(inside.any()):
+                occ_gt[inside] = self.occ_probability(points[inside], t.refl[inside].contiguous(), w, sn0=128, sn1=9)
+            outputs["occ_prob_gt"] = occ_gt
+            for k, v in eng.shading_buffers(w, t, t.exp_max).items():
+                outputs[k] = v * inner
+        return outputs
 
     # ------------------------------------------------------------------ ZT:614-634
     def render(self, rays_o, rays_d, near, far, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,

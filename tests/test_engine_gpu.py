@@ -367,6 +367,35 @@ def test_eval_outputs_depth_normal():
     assert (out["depth"].cpu() - depth).abs().max().item() < 1e-4
     assert (out["normal"].cpu() - normal).abs().max().item() < 1e-4
     assert (out["ray_rgb"].cpu() - ref["ray_rgb"]).abs().max().item() < 1e-4
+    # the shading network's intermediate buffers at the depth point (field.py:749-772) and occ_prob_gt (ZT:646-654)
+    with torch.no_grad():
+        y = orc.sdf_forward(sdp, pts)
+        v = -torch.nn.functional.normalize(d, dim=-1)
+        _, info = orc.shading_forward(sdp, pts, grad, v, y[:, 1:], extras=True)
+        inner = (pts.norm(dim=-1, keepdim=True) <= 1.0).float()
+        met, rough, alb, trans = info["metallic"], info["roughness"], info["albedo"], info["transmission_weight"]
+        tn = torch.clamp(1 - info["nov"], 0.0, 1.0)
+        rw = torch.clamp(0.04 + 0.96 * tn ** 5, 0.0, 1.0)
+        spec_albedo = 0.04 * (1 - met) + met * alb
+        spec_ref = spec_albedo * info["fg"][:, 0:1] + info["fg"][:, 1:2]
+        c01 = lambda x: torch.clamp(x, 0.0, 1.0)
+        srgb = orc.linear_to_srgb
+        want = {
+            "specular_albedo": spec_albedo, "specular_ref": c01(spec_ref), "specular_light": c01(srgb(info["light0"])),
+            "specular_color": c01(srgb(spec_ref * info["light"]) * (1 - trans) + rw * info["light0"] * trans),
+            "diffuse_albedo": (1 - met) * alb, "diffuse_light": c01(srgb(info["diffuse_light"])),
+            "diffuse_color": c01(srgb((1 - met) * alb * info["diffuse_light"])),
+            "metallic": met, "transmission_weight": trans, "roughness": rough, "occ_prob": c01(info["occ_prob"]),
+            "refraction_light": c01(srgb((1 - rw) * info["refraction_light"] * trans)), "reflection_weight": rw,
+        }
+        inside = pts.norm(dim=-1) < 0.999
+        occ_gt = torch.zeros(R, 1)
+        occ_gt[inside] = orc.occ_probability(sdp, pts[inside], info["reflective"][inside], sn0=128, sn1=9)
+    for k, ref_v in want.items():
+        err = (out[k].cpu() - ref_v * inner).abs().max().item()
+        assert err < 2e-4, (k, err)
+    assert "indirect_light" in out and out["indirect_light"].shape == (R, 3)
+    assert (out["occ_prob_gt"].cpu() - occ_gt).abs().max().item() < 5e-3
 
 
 def test_forward_with_device_ray_feeder():
