@@ -89,6 +89,33 @@ class _RenderCoreFn(torch.autograd.Function):
                 *([None] * ctx.n_params))
 
 
+class _SdfValueFn(torch.autograd.Function):
+    """sdf_network.sdf(points) with a backward to the SDF network's parameters (the `sdf_vals` warm-up output of
+    ZT:804-807, regularised by InitSDFRegLoss, network/loss.py:115-148, during the first 1000 steps)."""
+
+    @staticmethod
+    def forward(ctx, pack, *params):
+        eng = _engine()
+        w, pts = pack
+        M = pts.shape[0]
+        xm = eng.P(M, 320, w.planes, pts.device)
+        tape = eng.sdf_forward(w.sdf, pts, w.planes, xm)
+        ctx.w, ctx.tape, ctx.n = w, tape, len(params)
+        return tape.sdf[:, 0].clone()
+
+    @staticmethod
+    def backward(ctx, d_sdf):
+        eng = _engine()
+        w, t = ctx.w, ctx.tape
+        M, dev = t.M, t.pts.device
+        w.bank.zero_grads()
+        dxm = eng.P(M, 320, w.planes, dev, zero=True)                # no gradient arrives through the feature columns
+        eng.sdf_backward(w.sdf, t, w.planes, dxm, d_sdf.contiguous().float(), torch.zeros(M, 3, device=dev))
+        w.bank.backward()
+        ctx.tape = None
+        return (None,) + (None,) * ctx.n
+
+
 class NeROShapeRenderer(nn.Module):
     default_cfg = {
         # standard deviation for opacity density
@@ -258,7 +285,16 @@ class NeROShapeRenderer(nn.Module):
             else:
                 outputs["loss_occ"] = torch.zeros(1, device=rgb.device)
         if step is not None and step < 1000:
-            raise NotImplementedError("sdf_pts / sdf_vals warm-up outputs (ZT:804-807, step < 1000)")
+            # warm-up outputs of ZT:804-807: every sample inside radius 1.2 and its (differentiable) SDF value.  Only the
+            # first 1000 of 200 000 steps take this branch; the mid points are rebuilt with torch indexing (ZT:730-736)
+            zf = z_vals.float()
+            dist = torch.cat([zf[:, 1:] - zf[:, :-1], zf[:, -1:] - zf[:, -2:-1]], -1)
+            pts_all = rays_o.float()[:, None, :] + rays_d.float()[:, None, :] * (zf + dist * 0.5)[..., None]
+            mask = torch.norm(pts_all, dim=-1) < 1.2
+            sdf_pts = pts_all[mask].contiguous()
+            outputs["sdf_pts"] = sdf_pts
+            outputs["sdf_vals"] = _SdfValueFn.apply((w, sdf_pts), *params) if sdf_pts.shape[0] > 0 else \
+                torch.zeros(0, device=rgb.device)
         if not is_train:
             outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=w))
         outputs["_weights"] = weights

@@ -550,3 +550,42 @@ def test_helper_methods_nvs_and_predict_materials():
     assert np.abs(img.reshape(-1, 3) - out["ray_rgb"].cpu().numpy()).max() < 1e-5
     # the central pixel looks at the (radius-0.5) initial sphere: the ray must accumulate opacity there
     assert out["acc"].reshape(h, w)[6, 8].item() > 0.5
+
+
+@pytest.mark.parametrize("precision,tol,gtol", [("split", 3e-5, 2e-3), ("bf16", 2e-2, 3e-2)])
+def test_warmup_outputs_sdf_pts_and_differentiable_sdf_vals(precision, tol, gtol):
+    """step < 1000 (ZT:804-807): `sdf_pts` = the samples inside radius 1.2, `sdf_vals` = their SDF values with a backward
+    to the SDF network, as InitSDFRegLoss (network/loss.py:115-148) needs; values and gradients against the oracle."""
+    from oracle import nunerf_oracle as orc
+    R = 48
+    net = _renderer(precision)
+    sdp, params = _oracle_params(net)
+    o, d = orc.synthetic_rays(R)
+    U0, U1 = orc.synthetic_uniforms(R)
+    near, far = torch.full((R, 1), 0.8), torch.full((R, 1), 4.5)
+    with torch.no_grad():
+        z = orc.sample_ray(sdp, o, d, near, far, U0, U1)
+    dist = torch.cat([z[:, 1:] - z[:, :-1], z[:, -1:] - z[:, -2:-1]], -1)
+    pts = o[:, None, :] + d[:, None, :] * (z + dist * 0.5)[..., None]
+    mask = pts.norm(dim=-1) < 1.2
+    ref_pts = pts[mask]
+    ref_vals = orc.sdf_forward(sdp, ref_pts)[:, 0]
+    coef = torch.linspace(-1.0, 1.0, ref_pts.shape[0])
+    (ref_vals * coef).mean().backward()
+    net.zero_grad()
+    out = net.render_core(o.to(DEV), d.to(DEV), z.to(DEV), None, cos_anneal_ratio=0.0, step=10, is_train=True, is_nerf=True)
+    assert out["sdf_pts"].shape == ref_pts.shape
+    assert (out["sdf_pts"].cpu() - ref_pts).abs().max().item() < 1e-5
+    assert (out["sdf_vals"].detach().cpu() - ref_vals.detach()).abs().max().item() < tol
+    (out["sdf_vals"] * coef.to(DEV)).mean().backward()
+    checked = 0
+    for name, p in net.named_parameters():
+        if not name.startswith("sdf_network."):
+            continue
+        gr = params[name].grad
+        if gr is None or gr.abs().max() == 0:
+            continue
+        rel = (p.grad.cpu() - gr).abs().max().item() / gr.abs().max().item()
+        assert rel < gtol, (name, rel)
+        checked += 1
+    assert checked >= 20
