@@ -202,3 +202,24 @@ def test_nvs_renders_an_image(net):
     pose = np.concatenate([Rm, (-Rm @ cam)[:, None]], 1)
     img = net.nvs(pose, K, h, w)
     assert img.shape == (h, w, 3) and np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0
+
+
+def test_edge_cases_all_rays_miss_and_single_ray(net):
+    """Ragged path lists: a batch whose rays all miss the outer mesh (one background segment, no bounce) and a batch of
+    one ray through the centre (three segments); forward + backward run and give finite colours / gradients."""
+    o_miss = torch.tensor([[3.0, 0.0, 0.0], [3.0, 0.1, 0.0], [0.0, 3.0, 0.2]], device=DEV)
+    d_miss = torch.nn.functional.normalize(torch.tensor([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]], device=DEV), dim=-1)
+    o_one = torch.tensor([[0.0, 0.0, 3.0]], device=DEV)
+    d_one = torch.tensor([[0.0, 0.0, -1.0]], device=DEV)
+    for name, o, d, n_seg in (("all miss", o_miss, d_miss, 1), ("single ray", o_one, d_one, 3)):
+        with torch.no_grad():
+            lists = net.ray_trace(o, d)
+        assert len(lists[0]) == n_seg, (name, len(lists[0]))
+        net.zero_grad()
+        out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+        assert out["ray_rgb"].shape == (o.shape[0], 3) and torch.isfinite(out["ray_rgb"]).all(), name
+        assert out["tir_mask"].shape == (o.shape[0], 1)
+        loss = out["ray_rgb"].sum() + (0.02 * out["gradient_error"]).mean()
+        loss.backward()
+        g = net.stage1_network.outer_nerf.pts_linears[0].weight.grad
+        assert g is not None and torch.isfinite(g).all(), name
