@@ -254,7 +254,7 @@ def run_ours(args):
     from nu_nerf_b200 import _lib, ops
     from nu_nerf_b200 import dist as nd
     from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
-    from oracle import nunerf_oracle as orc   # synthetic input generators only (seeded rays / targets)
+    from nu_nerf_b200 import synthetic as orc  # seeded synthetic rays / targets (the product arm never touches oracle/)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

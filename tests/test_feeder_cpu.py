@@ -65,3 +65,12 @@ def test_reshuffle_rule_and_rank_sharding():
     r0 = feeder.DeviceRayFeeder(batch, rank=0, world=2, seed=5)(0, 8)
     r1 = feeder.DeviceRayFeeder(batch, rank=1, world=2, seed=5)(0, 8)
     assert torch.equal(one["rays_d"][0::2], r0["rays_d"]) and torch.equal(one["rays_d"][1::2], r1["rays_d"])
+
+
+def test_product_synthetic_inputs_equal_the_oracles():
+    """bench.py's product arm draws its rays from nu_nerf_b200.synthetic; the oracle / goldens use their own copy."""
+    from nu_nerf_b200 import synthetic as syn
+    from oracle import nunerf_oracle as orc
+    for a, b in zip(syn.synthetic_rays(33) + syn.synthetic_uniforms(33) + (syn.synthetic_targets(33),),
+                    orc.synthetic_rays(33) + orc.synthetic_uniforms(33) + (orc.synthetic_targets(33),)):
+        assert torch.equal(a, b)

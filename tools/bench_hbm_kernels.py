@@ -16,7 +16,7 @@ import bench  # noqa: E402
 from nu_nerf_b200 import engine as eng, ops  # noqa: E402
 from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg  # noqa: E402
 from conftest import uv_sphere  # noqa: E402
-from oracle import nunerf_oracle as orc  # noqa: E402  (seeded synthetic ray generator only)
+from nu_nerf_b200 import synthetic as orc  # noqa: E402
 
 
 def main():

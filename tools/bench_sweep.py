@@ -34,7 +34,7 @@ def main():
     uh = extract_fields(bmin, bmax, res, net.sdf_network.sdf)
     wall = time.perf_counter() - t0
     # eval render: sphere-bounded near/far, no perturbation, validation outputs (depth, normal)
-    from oracle import nunerf_oracle as orc            # seeded synthetic ray generator only
+    from nu_nerf_b200 import synthetic as orc
     R = 4096
     o, d = (t.cuda() for t in orc.synthetic_rays(R))
     near, far = net.near_far_from_sphere(o, d)
