@@ -106,7 +106,7 @@ def cpu_step_fn(R):
         U0, U1 = torch.rand(R, 1), torch.rand(R, 32)
         opt.zero_grad(set_to_none=True)
         out = orc.render(sd, o, d, near, far, U0, U1, 0.2, STEP)
-        loss = orc.train_loss(out, gt, EIK_W)
+        loss = orc.train_loss(out, gt, EIK_W, step=STEP)
         loss.backward()
         opt.step()
         return float(loss)
@@ -275,7 +275,8 @@ def run_ours(args):
     def render_fn(o, d, near_, far_, step):
         return net.render(o, d, near_, far_, None, -1, anneal, is_train=True, step=step, is_nerf=True)
     # the product's ray-sharded trainer: global-denominator losses, one all-reduce of the flat gradient, CUDA Adam
-    trainer = nd.DataParallelTrainer(net, render_fn, net.compute_rgb_loss, lr_fn=lambda s: lr_at(s), eikonal_weight=EIK_W)
+    trainer = nd.DataParallelTrainer(net, render_fn, net.compute_rgb_loss, lr_fn=lambda s: lr_at(s), eikonal_weight=EIK_W,
+                                     occ_loss_step=cfg["occ_loss_step"])
     flat = trainer.fp.flat
     # rays: the same generator on every rank, rank-strided slices of one global batch
     o_all, d_all = orc.synthetic_rays(R * world, seed=1)
@@ -413,6 +414,7 @@ def run_ours(args):
 
 
 def main():
+    global STEP
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -421,10 +423,13 @@ def main():
     ap.add_argument("--rays-per-gpu", type=int, default=4096)
     ap.add_argument("--chunk", type=int, default=8192, help="rays per render call (memory bound)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "split"])
+    ap.add_argument("--step", type=int, default=STEP, help="training step the schedule is evaluated at (SURVEY 8d: 10000; "
+                    "20000 adds the occlusion-probe loss, outer_reg and the trainable inv_s)")
     ap.add_argument("--cpu-rays", type=int, default=128, help="bounded CPU sample (rays per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="print a per-entry-point device-time table to stderr")
     args = ap.parse_args()
+    STEP = args.step          # 10000 = the SURVEY 8(d) primary point; 20000 = occlusion-probe loss + outer_reg + trainable inv_s
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -141,6 +141,12 @@ int nunerf_upsample(const float* o, const float* d, const float* z, const float*
                     float* z_merged, int32_t* perm, void* stream);
 int nunerf_merge_sdf(const float* sdf, const float* sdf_new, const int32_t* perm, int R, int n, int n_new,
                      float* sdf_merged, void* stream);
+/* Occlusion probe along P rays (get_weights + sample_pdf of get_intersection, field.py:501-554; caller ZT:695-723):
+ * weights from n <= 64 samples z / sdf [P,n] with the probe's alpha (logistic CDF at the section ends, zero where the SDF
+ * does not decrease); z_new != NULL: CDF inversion of (weights + 1e-5) at the n_new <= 32 deterministic u's -> z_new
+ * [P,n_new]; wsum != NULL: sum of the weights [P] (the hit probability of the second pass). */
+int nunerf_probe_weights(const float* z, const float* sdf, int P, int n, const float* inv_s_dev, int n_new,
+                         const float* u_tab, float* z_new, float* wsum, void* stream);
 
 /* ------------------------------------------------------------------ render_core geometry + compositing
  * nunerf_render_geometry (ZT:730-741): dists, mid points, inner mask and the row-major compaction of the

@@ -222,6 +222,96 @@ __global__ void upsample_kernel(const float* __restrict__ o, const float* __rest
   }
 }
 
+// Occlusion probe (get_weights + sample_pdf of get_intersection, field.py:501-554): one warp per probe ray with n <= 64
+// samples z / sdf.  weights_j = alpha_j * prod_{k<j}(1 - alpha_k + 1e-7) with alpha from the logistic CDF at the section
+// ends, zeroed where the SDF does not decrease (surface_mask).  Either inverts the CDF of (weights + 1e-5) at n_new
+// deterministic u's (first pass -> z_new) or returns sum_j weights_j (second pass -> the hit probability).  Float
+// arithmetic only feeds a regression target, so no fixed operation order is imposed here.
+__global__ void probe_weights_kernel(const float* __restrict__ z, const float* __restrict__ sdf, int P, int n,
+                                     const float* __restrict__ inv_s_dev, int n_new, const float* __restrict__ u_tab,
+                                     float* z_new, float* wsum) {
+  __shared__ float s_z[WARPS_PER_BLOCK][64];
+  __shared__ float s_cdf[WARPS_PER_BLOCK][68];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + w;
+  if (r >= P) return;
+  const float inv_s = inv_s_dev[0];
+  float zv[2], sv[2], wgt[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int j = lane + 32 * k;
+    const bool ok = j < n;
+    zv[k] = ok ? z[(long long)r * n + j] : 0.f;
+    sv[k] = ok ? sdf[(long long)r * n + j] : 0.f;
+    if (ok) s_z[w][j] = zv[k];
+  }
+  float carryT = 1.0f, lane_sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int j = lane + 32 * k;
+    float zn = __shfl_down_sync(FULL, zv[k], 1), sn = __shfl_down_sync(FULL, sv[k], 1);
+    const float zn2 = __shfl_sync(FULL, k == 0 ? zv[1] : 0.f, 0), sn2 = __shfl_sync(FULL, k == 0 ? sv[1] : 0.f, 0);
+    if (lane == 31) { zn = zn2; sn = sn2; }
+    const bool sec_ok = j < n - 1;
+    const float dist = zn - zv[k];
+    float cosv = (sn - sv[k]) / (dist + 1e-5f);
+    const bool surf = cosv < 0.f;
+    cosv = fminf(cosv, 0.f);
+    const float mid = (sv[k] + sn) * 0.5f, half = cosv * dist * 0.5f;
+    const float pc = 1.0f / (1.0f + __expf(-(mid - half) * inv_s)), nc = 1.0f / (1.0f + __expf(-(mid + half) * inv_s));
+    float a = (pc - nc + 1e-5f) / (pc + 1e-5f);
+    a = (sec_ok && surf) ? a : 0.f;
+    float v = sec_ok ? (1.0f - a + 1e-7f) : 1.0f;
+    float incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float t = __shfl_up_sync(FULL, incl, off);
+      if (lane >= off) incl *= t;
+    }
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    wgt[k] = sec_ok ? a * (carryT * excl) : 0.f;
+    carryT *= __shfl_sync(FULL, incl, 31);
+    lane_sum += wgt[k];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) lane_sum += __shfl_xor_sync(FULL, lane_sum, off);
+  if (wsum && lane == 0) wsum[r] = lane_sum;
+  if (!z_new) return;
+  // cdf of (weights + 1e-5) over the n - 1 sections (sample_pdf, field.py:468-498)
+  const float total = lane_sum + 1e-5f * (float)(n - 1);
+  float carryC = 0.f;
+  if (lane == 0) s_cdf[w][0] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int j = lane + 32 * k;
+    float pdf = (j < n - 1) ? (wgt[k] + 1e-5f) / total : 0.f;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float t = __shfl_up_sync(FULL, pdf, off);
+      if (lane >= off) pdf += t;
+    }
+    const float c = carryC + pdf;
+    carryC = __shfl_sync(FULL, c, 31);
+    if (j < n - 1) s_cdf[w][j + 1] = c;
+  }
+  __syncwarp();
+  if (lane < n_new) {
+    const float u = u_tab[lane];
+    int lo = 0, hi = n;                      // first index with cdf > u (searchsorted right=True)
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (s_cdf[w][m] <= u) lo = m + 1; else hi = m;
+    }
+    const int below = lo - 1 < 0 ? 0 : lo - 1, above = lo > n - 1 ? n - 1 : lo;
+    const float c0 = s_cdf[w][below], c1 = s_cdf[w][above];
+    const float b0 = s_z[w][below], b1 = s_z[w][above];
+    float den = c1 - c0;
+    if (den < 1e-5f) den = 1.0f;
+    z_new[(long long)r * n_new + lane] = b0 + (u - c0) / den * (b1 - b0);
+  }
+}
+
 __global__ void merge_sdf_kernel(const float* __restrict__ sdf, const float* __restrict__ sdf_new,
                                  const int32_t* __restrict__ perm, long long total, int n, int n_new, float* out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -269,6 +359,16 @@ extern "C" int nunerf_upsample(const float* o, const float* d, const float* z, c
   else
     upsample_kernel<4><<<grid, block, 0, st>>>(o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
   NUNERF_CHECK_LAUNCH("upsample_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_probe_weights(const float* z, const float* sdf, int P, int n, const float* inv_s_dev, int n_new,
+                                    const float* u_tab, float* z_new, float* wsum, void* stream) {
+  NUNERF_REQUIRE(z && sdf && inv_s_dev && (z_new || wsum) && P > 0, "probe_weights: bad arguments");
+  NUNERF_REQUIRE(n >= 2 && n <= 64 && (!z_new || (u_tab && n_new >= 1 && n_new <= 32)), "probe_weights: need 2<=n<=64, n_new<=32");
+  probe_weights_kernel<<<cdiv(P, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, (cudaStream_t)stream>>>(
+      z, sdf, P, n, inv_s_dev, n_new, u_tab, z_new, wsum);
+  NUNERF_CHECK_LAUNCH("probe_weights_kernel");
   return 0;
 }
 

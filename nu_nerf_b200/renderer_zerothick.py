@@ -301,18 +301,37 @@ class NeROShapeRenderer(nn.Module):
         return outputs
 
     # ------------------------------------------------------------------ ZT:695-723, field.py:501-554
-    def compute_occ_loss(self, occ_info, points, sdf, gradients, dirs, step, prepared=None, perm=None):
+    def compute_occ_loss(self, occ_info, points, sdf, gradients, dirs, step, prepared=None, perm=None, sync_free=True):
         """L1 between the predicted occlusion probability and the hit probability of a 64 + 16 sample SDF probe along
         the reflected ray, on (at most occ_loss_max_pn) surface samples.  torch glue on <= 2048-row tensors around the
-        fused SDF-inference kernel; `perm` injects the torch.randperm draw of ZT:710 (parity tests)."""
+        fused SDF-inference kernel; `perm` injects the torch.randperm draw of ZT:710 (parity tests).
+
+        Default (perm is None and sync_free): the subset is drawn WITHOUT a host round trip -- every candidate gets a
+        uniform random key, the occ_loss_max_pn smallest keys are kept (a uniform random subset without replacement,
+        like randperm[:max_pn]; all candidates when there are fewer) and padding slots are masked out of the mean.  The
+        reference's `int(mask.sum())` / `nonzero` are host round trips in the middle of every step from occ_loss_step on
+        (92 % of training); they are avoided so that the launch queue never drains there."""
         dev = points.device
         if step < self.cfg["occ_loss_step"]:
             return torch.zeros(1, device=dev)
         occ_prob, reflective = occ_info["occ_prob"], occ_info["reflective"]
         mask = (torch.norm(points, dim=-1) < 0.999) & (torch.sum(gradients * dirs, -1) < 0) & \
                (torch.abs(sdf) < self.cfg["occ_sdf_thresh"])
-        n = int(mask.sum())
         max_pn = self.cfg["occ_loss_max_pn"]
+        if perm is None and sync_free:
+            k = min(max_pn, points.shape[0])
+            keys = torch.where(mask, torch.rand(points.shape[0], device=dev), torch.full((), 2.0, device=dev))
+            vals, idx = torch.topk(keys, k, largest=False, sorted=False)
+            valid = vals < 1.5
+            # padding slots probe a harmless ray from the origin (their weight in the mean is zero)
+            pts_sel = torch.where(valid[:, None], points[idx], torch.zeros(1, 3, device=dev))
+            dirs_sel = torch.where(valid[:, None], reflective[idx].detach(),
+                                   torch.tensor([[1.0, 0.0, 0.0]], device=dev)).contiguous()
+            w = prepared if prepared is not None else self._prepare()
+            occ_gt = self.occ_probability(pts_sel.contiguous(), dirs_sel, w)
+            diff = (occ_prob[idx] - occ_gt).abs() * valid[:, None]
+            return diff.sum() / torch.clamp(valid.sum() * occ_prob.shape[-1], min=1)
+        n = int(mask.sum())
         if n > max_pn:
             indices = torch.nonzero(mask)[:, 0]
             idx = perm.to(dev) if perm is not None else torch.randperm(indices.shape[0], device=dev)
@@ -326,7 +345,7 @@ class NeROShapeRenderer(nn.Module):
         return F.l1_loss(occ_prob[mask], occ_gt)
 
     @torch.no_grad()
-    def occ_probability(self, pts, dirs, w, sn0=64, sn1=16):
+    def occ_probability(self, pts, dirs, w, sn0=64, sn1=16, use_kernels=True):
         """get_intersection (field.py:524-554): probability that the ray pts + t dirs hits the surface before it
         leaves the unit sphere.  pts must lie inside radius 0.999 (the caller's mask)."""
         eng = _engine()
@@ -334,6 +353,26 @@ class NeROShapeRenderer(nn.Module):
         dtx = torch.sum(pts * dirs, dim=-1, keepdim=True)
         xtx = torch.sum(pts ** 2, dim=-1, keepdim=True)
         max_dist = -dtx + torch.sqrt(dtx ** 2 - xtx + 1 + 1e-6)                 # get_sphere_intersection :458-464
+
+        P = pts.shape[0]
+        dev = pts.device
+        if use_kernels and sn0 <= 64 and sn1 <= 32:
+            # kernels: points, fused SDF query, one warp-per-ray probe kernel per pass (csrc/sampling.cu)
+            pts_c, dirs_c = pts.contiguous().float(), dirs.contiguous().float()
+            inv_s_dev = inv_s.reshape(1).float().contiguous()
+            u_tab = eng._tables(dev)[1].get(sn1)
+            if u_tab is None:
+                u_tab = torch.linspace(0.5 / sn1, 1.0 - 0.5 / sn1, sn1, device=dev)
+            z = (max_dist * torch.linspace(0, 1, sn0, device=dev).unsqueeze(0)).contiguous()
+            sdf = eng.sdf_infer(w.sdf, eng.segment_points(pts_c, dirs_c, z).reshape(-1, 3), w.planes).reshape(P, sn0)
+            z_new = torch.empty(P, sn1, device=dev)
+            eng.call("nunerf_probe_weights", z.data_ptr(), sdf.contiguous().data_ptr(), P, sn0, inv_s_dev.data_ptr(), sn1,
+                     u_tab.data_ptr(), z_new.data_ptr(), None)
+            sdf2 = eng.sdf_infer(w.sdf, eng.segment_points(pts_c, dirs_c, z_new).reshape(-1, 3), w.planes).reshape(P, sn1)
+            wsum = torch.empty(P, device=dev)
+            eng.call("nunerf_probe_weights", z_new.data_ptr(), sdf2.contiguous().data_ptr(), P, sn1, inv_s_dev.data_ptr(), 0,
+                     None, None, wsum.data_ptr())
+            return wsum[:, None]
 
         def weights(z):                                                        # get_weights :501-521
             p = (z.unsqueeze(-1) * dirs.unsqueeze(-2) + pts.unsqueeze(-2)).reshape(-1, 3).contiguous()
@@ -350,6 +389,7 @@ class NeROShapeRenderer(nn.Module):
             T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
             return alpha * T
 
+        # wider probes (the eval path uses 128 + 9 samples): torch glue around the fused SDF query
         z = max_dist * torch.linspace(0, 1, sn0, device=pts.device).unsqueeze(0)
         wts = weights(z) + 1e-5                                                # sample_pdf(det) field.py:468-498
         pdf = wts / torch.sum(wts, -1, keepdim=True)
