@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr
-from .ops import P, linear, linear_dw, colsum, to_planes, f32_to_planes, pad, chain, GEMM_IMPL
+from .ops import P, linear, linear_dw, colsum, f32_to_planes, chain, GEMM_IMPL
 from .weights import Dense, WeightBank
 
 SQRT2 = math.sqrt(2.0)

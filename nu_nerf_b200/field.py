@@ -10,7 +10,6 @@ Reference: SDFNetwork field.py:64-131, SingleVarianceNetwork :191-195, NeRFNetwo
 make_predictor :371-408, AppShadingNetwork.__init__ :569-616, InfOutNetwork :1020-1036,
 IoRNetwork :1046-1059.
 """
-import math
 
 import numpy as np
 import torch

@@ -8,8 +8,6 @@ plus a zero-padded bias copy, and its fp32 gradient buffers dW [pad16(rows), pad
 `WeightBank.prepare()` refreshes all of them in ONE kernel launch; `WeightBank.backward()` turns the accumulated
 dW / db into gradients of the source parameters in ONE launch, added in place to `param.grad`.
 """
-import ctypes as C
-
 import torch
 
 from . import _lib

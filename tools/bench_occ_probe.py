@@ -1,5 +1,12 @@
-import torch, time
-dev="cuda"
+"""Micro-benchmark of the occlusion-probe path (ZT:695-723): candidate selection primitives on 383k samples and
+occl. probability of 2048 probe rays (points + fused SDF query + probe_weights_kernel, twice)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+dev = "cuda"
 M=383000
 keys=torch.rand(M,device=dev)
 def t(fn,n=20):
@@ -17,7 +24,6 @@ print("rand: %.0f us"%t(lambda: torch.rand(M,device=dev)))
 mask=keys<0.05
 print("nonzero: %.0f us"%t(lambda: torch.nonzero(mask)))
 print("cumsum: %.0f us"%t(lambda: torch.cumsum(mask.int(),0)))
-import sys; sys.path.insert(0,"/root/repo"); sys.path.insert(0,"/root/repo/tests")
 from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
 cfg=load_default_cfg(); cfg["precision"]="bf16"; torch.manual_seed(0)
 net=NeROShapeRenderer(cfg,training=False).cuda(); w=net._prepare()

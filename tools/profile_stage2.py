@@ -1,5 +1,12 @@
-import os, sys, json, torch
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests"); sys.path.insert(0, "/root/repo/tools")
+"""torch.profiler kernel table of one stage-2 training step (config 4 mesh, 4096 rays)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import make_stage2, uv_sphere
 R = 4096
 V, Fc = uv_sphere(0.6, 224, 224)
