@@ -133,6 +133,8 @@ _SIGS = {
     "nunerf_refract_bounce": [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp],
     "nunerf_grid_points": [ci, cll, ci, vp, vp, vp],
     "nunerf_grid_mask": [vp, vp, ci, ci, cf, vp, vp],
+    "nunerf_mc_count": [vp, ci, cf, vp, vp, vp],
+    "nunerf_mc_emit": [vp, ci, cf, vp, ci, vp, vp, vp, vp, vp, vp, vp],
 }
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)

@@ -48,11 +48,60 @@ def extract_fields(bound_min, bound_max, resolution, query_func, batch_size=64, 
     return u if return_device else u.cpu().numpy()
 
 
+_MC_TABLES = {}
+
+
+def _mc_tables(dev):
+    if dev not in _MC_TABLES:
+        from .mc_tables import build_tables
+        _MC_TABLES[dev] = tuple(torch.from_numpy(t).to(dev).contiguous() for t in build_tables())
+    return _MC_TABLES[dev]
+
+
+@torch.no_grad()
+def marching_cubes(u, isovalue):
+    """Device replacement of `mcubes.marching_cubes(u, isovalue)` (field.py:1312): u[res,res,res] float32 (a CUDA tensor
+    or a numpy array) -> (vertices float64 [V,3] in grid-index coordinates, triangles int64 [T,3]), numpy, as PyMCubes
+    returns them.  Count pass -> scan of the block totals -> emit pass (csrc/mcubes.cu); vertices that sit on the same grid
+    edge are merged by their edge id.  Triangles are oriented like PyMCubes': normals point towards DECREASING u (which
+    is why extract_mesh_stage1.py:41 flips the faces of an SDF grid).  PyMCubes is neither pinned by the reference nor
+    present here: the case tables are generated (mc_tables.py), so the triangulation of ambiguous cells may differ from
+    PyMCubes' while the surface is the same (parity unpinned; the tests check the surface properties instead)."""
+    if not torch.is_tensor(u):
+        u = torch.from_numpy(np.ascontiguousarray(u, dtype=np.float32)).cuda()
+    u = u.float().contiguous()
+    res = u.shape[0]
+    if u.dim() != 3 or u.shape[1] != res or u.shape[2] != res:
+        raise ValueError("marching_cubes: u must be a cube [res, res, res]")
+    if res < 2:
+        return np.zeros((0, 3)), np.zeros((0, 3), dtype=np.int64)
+    dev = u.device
+    tri_table, n_tris, edges, edge_axis = _mc_tables(dev)
+    cells = (res - 1) ** 3
+    n_blocks = (cells + 255) // 256
+    counts = torch.empty(n_blocks, dtype=torch.int32, device=dev)
+    call("nunerf_mc_count", u.data_ptr(), res, float(isovalue), n_tris.data_ptr(), counts.data_ptr())
+    incl = torch.cumsum(counts, 0, dtype=torch.int64)
+    offsets = (incl - counts).contiguous()
+    total = int(incl[-1])
+    if total == 0:
+        return np.zeros((0, 3)), np.zeros((0, 3), dtype=np.int64)
+    verts = torch.empty(3 * total, 3, dtype=torch.float32, device=dev)
+    keys = torch.empty(3 * total, dtype=torch.int64, device=dev)
+    call("nunerf_mc_emit", u.data_ptr(), res, float(isovalue), tri_table.data_ptr(), tri_table.shape[1] // 3,
+         n_tris.data_ptr(), edges.data_ptr(), edge_axis.data_ptr(), offsets.data_ptr(), verts.data_ptr(), keys.data_ptr())
+    uniq, inverse = torch.unique(keys, return_inverse=True)
+    vertices = torch.empty(uniq.numel(), 3, dtype=torch.float32, device=dev)
+    vertices[inverse] = verts                       # equal keys carry bit-identical positions
+    triangles = inverse.view(-1, 3)[:, [0, 2, 1]]   # tables wind towards larger u; PyMCubes towards smaller
+    return vertices.double().cpu().numpy(), triangles.contiguous().cpu().numpy()
+
+
 def extract_geometry(bound_min, bound_max, resolution, threshold, query_func, outside_val=1.0):
-    """field.py:1310-1319.  Marching cubes itself (PyMCubes) is outside the hot path."""
-    import mcubes
-    u = extract_fields(bound_min, bound_max, resolution, query_func, outside_val=outside_val)
-    vertices, triangles = mcubes.marching_cubes(u, threshold)
+    """field.py:1310-1319 with the grid and the marching cubes both on the device (one device->host copy of the
+    mesh instead of the res^3 field)."""
+    u = extract_fields(bound_min, bound_max, resolution, query_func, outside_val=outside_val, return_device=True)
+    vertices, triangles = marching_cubes(u, threshold)
     b_max, b_min = np.asarray(bound_max, dtype=np.float64), np.asarray(bound_min, dtype=np.float64)
     vertices = vertices / (resolution - 1.0) * (b_max - b_min)[None, :] + b_min[None, :]
     return vertices, triangles

@@ -10,7 +10,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg  # noqa: E402
-from nu_nerf_b200.sweep import extract_fields  # noqa: E402
+from nu_nerf_b200.sweep import extract_fields, marching_cubes  # noqa: E402
+from nu_nerf_b200._lib import call  # noqa: E402
 
 M_SDF_HEAD = 459008
 
@@ -33,6 +34,24 @@ def main():
     t0 = time.perf_counter()
     uh = extract_fields(bmin, bmax, res, net.sdf_network.sdf)
     wall = time.perf_counter() - t0
+    # marching cubes on the resident grid: the two kernels alone (HBM: the grid is read once per pass) and the whole call
+    from nu_nerf_b200 import sweep as sw
+    tri_table, n_tris, edges, edge_axis = sw._mc_tables(u.device)
+    counts = torch.empty(((res - 1) ** 3 + 255) // 256, dtype=torch.int32, device=u.device)
+    call("nunerf_mc_count", u.data_ptr(), res, 0.0, n_tris.data_ptr(), counts.data_ptr())
+    torch.cuda.synchronize()
+    e0.record()
+    call("nunerf_mc_count", u.data_ptr(), res, 0.0, n_tris.data_ptr(), counts.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_count = e0.elapsed_time(e1)
+    marching_cubes(u, 0.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    mv, mt = marching_cubes(u, 0.0)
+    mc_wall = time.perf_counter() - t0
+    mc = {"count_pass_ms": ms_count, "count_pass_GBps": 4.0 * res ** 3 / ms_count / 1e6,
+          "call_wall_s_incl_vertex_merge_and_d2h": mc_wall, "vertices": int(len(mv)), "triangles": int(len(mt))}
     # eval render: sphere-bounded near/far, no perturbation, validation outputs (depth, normal)
     from nu_nerf_b200 import synthetic as orc
     R = 4096
@@ -58,6 +77,7 @@ def main():
     print(json.dumps({"workload": f"extract_fields {res}^3 SDF sweep (bf16 fused chain)", "device_ms": ms,
                       "end_to_end_s_with_d2h": wall, "points": res ** 3, "Mpts_per_s": res ** 3 / ms / 1e3,
                       "tflops": tf, "frac_of_tensor_peak": tf / peak, "inside_fraction": float((uh < 1.0).mean()),
+                      "marching_cubes": mc,
                       "eval_render": {"rays": R, "ms": ms_eval, "rays_per_s": R / ms_eval * 1e3,
                                       "outputs": "ray_rgb, depth, normal, acc, color_bkgr, color_spec (is_train=False)"}}))
 
