@@ -2,6 +2,8 @@
 // (ZT:725-785).  One warp per ray; sample s lives in lane (s & 31), block (s >> 5): all [R,S] accesses are
 // coalesced.  Backward recomputes the transmittance with the same scan instead of reading a stored copy.
 #include "common.cuh"
+#include "ptx.cuh"
+#include <stdlib.h>
 
 namespace nunerf {
 
@@ -363,6 +365,288 @@ __global__ void __launch_bounds__(32 * WPB) composite_bwd_kernel(const float* __
   }
 }
 
+// =====================================================================================================================
+// Staged compositing (the product path: S <= 160, per-ray compaction map).  One warp per ray.  The ray's four contiguous
+// runs (inner alpha / colour, outer alpha / colour) are brought into shared memory as whole 16-byte chunks with
+// cp.async (6 per lane; no per-sample address arithmetic), and every lane then owns SPL = 5 CONSECUTIVE samples: the
+// transmittance is a 5-term product in registers plus ONE warp scan of the lane totals per composite (the lane-per-sample
+// form needs one scan per block of 32 samples, five per ray), and the seven per-ray sums go through one transposing
+// butterfly.  Stride-5 / stride-15 shared-memory reads are bank-conflict free.  The backward kernel overwrites the staged
+// alpha / colour in place with their gradients and writes the chunks back (16-byte stores inside the run, scalar stores
+// for the <= 3 elements of a boundary chunk, so nothing outside the ray's own run is written).  Loads may touch the
+// <= 3 neighbouring elements that share a 16-byte chunk with the run (always inside the same 16-byte aligned buffer).
+constexpr int CW = 8;            // warps (= rays in flight) per block
+constexpr int SPL = 5;           // samples per lane
+constexpr int A_ST = 176;        // staged floats per ray, alpha:  <= 43 chunks
+constexpr int C_ST = 496;        // staged floats per ray, colour: <= 123 chunks
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ptx::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// sums of 8 per-lane values over the warp with 9 shuffles: after the call lane l holds the total of value (l >> 2) & 7
+// (identical in the four lanes that share it)
+__device__ __forceinline__ float warp_sum8(float (&v)[8], int lane) {
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = h4 ? v[i] : v[i + 4], keep = h4 ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = h3 ? v[i] : v[i + 2], keep = h3 ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+  }
+  {
+    const float send = h2 ? v[0] : v[1], keep = h2 ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(FULL, send, 4);
+  }
+  v[0] += __shfl_xor_sync(FULL, v[0], 2);
+  v[0] += __shfl_xor_sync(FULL, v[0], 1);
+  return v[0];
+}
+
+struct RayStage {
+  int pa[SPL], pc[SPL];      // staged positions of the lane's samples (alpha / first colour component)
+  unsigned inner;            // bit j: sample j of the lane is an inner sample
+  unsigned valid;            // bit j: sample exists (s < S)
+  int in_off, n_in, out_off, n_out;
+  int nch_ai, nch_ao, nch_ci, nch_co;     // 16-byte chunks of the four runs
+};
+
+// decode the ray map for this lane and start the chunk loads (FULLS: S == 160, every sample of every lane exists)
+template <bool FULLS>
+__device__ __forceinline__ RayStage stage_ray(const int32_t* __restrict__ ray_map, int r, int S, int lane,
+                                              const float* __restrict__ a_in, const float* __restrict__ c_in,
+                                              const float* __restrict__ a_out, const float* __restrict__ c_out, float* sa,
+                                              float* sc) {
+  RayStage st;
+  const int32_t* rm = ray_map + (long long)r * RAY_MAP;
+  const int in_off = __ldg(rm), out_off = __ldg(rm + 1);
+  unsigned m[6];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) m[k] = (unsigned)__ldg(rm + 2 + k);
+  m[5] = 0u;
+  const int n_in = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]);
+  const int n_out = S - n_in;
+  st.in_off = in_off; st.out_off = out_off; st.n_in = n_in; st.n_out = n_out;
+  // staged layout: [inner chunks | outer chunks]; a run keeps its global alignment modulo 16 B
+  const int hi_a = in_off & 3, ho_a = out_off & 3, hi_c = (3 * in_off) & 3, ho_c = (3 * out_off) & 3;
+  st.nch_ai = n_in ? (hi_a + n_in + 3) >> 2 : 0;
+  st.nch_ao = n_out ? (ho_a + n_out + 3) >> 2 : 0;
+  st.nch_ci = n_in ? (hi_c + 3 * n_in + 3) >> 2 : 0;
+  st.nch_co = n_out ? (ho_c + 3 * n_out + 3) >> 2 : 0;
+  {
+    const float* gi = a_in + (in_off & ~3);
+    const float* go = a_out + (out_off & ~3) - 4 * st.nch_ai;
+#pragma unroll
+    for (int t = lane; t < 64; t += 32)
+      if (t < st.nch_ai + st.nch_ao) cp_async16(sa + 4 * t, (t < st.nch_ai ? gi : go) + 4 * t);
+  }
+  {
+    const float* gi = c_in + ((3ll * in_off) & ~3ll);
+    const float* go = c_out + ((3ll * out_off) & ~3ll) - 4 * st.nch_ci;
+#pragma unroll
+    for (int t = lane; t < 128; t += 32)
+      if (t < st.nch_ci + st.nch_co) cp_async16(sc + 4 * t, (t < st.nch_ci ? gi : go) + 4 * t);
+  }
+  // the lane's 5 mask bits and the number of inner samples in front of them
+  const int b0 = SPL * lane, w = b0 >> 5, sh = b0 & 31;
+  unsigned lo = m[0], hi = m[1];
+  int before = 0, run = 0;
+#pragma unroll
+  for (int k = 1; k < 5; ++k) {
+    run += __popc(m[k - 1]);
+    if (w == k) { lo = m[k]; hi = m[k + 1]; before = run; }
+  }
+  st.inner = __funnelshift_r(lo, hi, sh) & 31u;
+  before += __popc(lo & ((1u << sh) - 1u));
+  st.valid = 0;
+  const int qa = 4 * st.nch_ai + ho_a, qc = 4 * st.nch_ci + ho_c;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int s = b0 + j;
+    const int rin = before + __popc(st.inner & ((1u << j) - 1u));
+    const bool in = (st.inner >> j) & 1u;
+    st.pa[j] = in ? hi_a + rin : qa + (s - rin);
+    st.pc[j] = in ? hi_c + 3 * rin : qc + 3 * (s - rin);
+    if (FULLS || s < S) st.valid |= 1u << j;
+  }
+  if (FULLS) st.valid = 31u;
+  return st;
+}
+
+// write chunk t of a staged region back: elements [lo, hi) of the destination (global element indices relative to the
+// 16-byte aligned base g) belong to the ray
+__device__ __forceinline__ void unstage_chunk(float* __restrict__ g, int lo, int hi, const float* s, int t) {
+  const float4 v = *reinterpret_cast<const float4*>(s + 4 * t);
+  const int e = 4 * t;
+  if (e >= lo && e + 4 <= hi) {
+    *reinterpret_cast<float4*>(g + e) = v;
+  } else {
+    if (e >= lo && e < hi) g[e] = v.x;
+    if (e + 1 >= lo && e + 1 < hi) g[e + 1] = v.y;
+    if (e + 2 >= lo && e + 2 < hi) g[e + 2] = v.z;
+    if (e + 3 >= lo && e + 3 < hi) g[e + 3] = v.w;
+  }
+}
+
+template <bool FULLS>
+__global__ void __launch_bounds__(32 * CW, 5) composite_fwd_staged_kernel(
+    const float* __restrict__ a_in, const float* __restrict__ c_in, const float* __restrict__ a_out,
+    const float* __restrict__ c_out, const int32_t* __restrict__ ray_map, int R, int S, int is_nerf, float* rgb,
+    float* rgb_raw, float* acc, float* rgb_b, float* weights) {
+  __shared__ __align__(16) float s_a[CW][A_ST];
+  __shared__ __align__(16) float s_c[CW][C_ST];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * CW + wid;
+  if (r >= R) return;
+  float* sa = s_a[wid];
+  float* sc = s_c[wid];
+  const RayStage st = stage_ray<FULLS>(ray_map, r, S, lane, a_in, c_in, a_out, c_out, sa, sc);
+  cp_async_wait_all();
+  __syncwarp();
+  float a[SPL], ab[SPL], c0[SPL], c1[SPL], c2[SPL];
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const bool ok = (st.valid >> j) & 1u;
+    a[j] = ok ? sa[st.pa[j]] : 0.f;
+    c0[j] = ok ? sc[st.pc[j]] : 0.f;
+    c1[j] = ok ? sc[st.pc[j] + 1] : 0.f;
+    c2[j] = ok ? sc[st.pc[j] + 2] : 0.f;
+    ab[j] = ((st.inner >> j) & 1u) ? 0.f : a[j];
+  }
+  // transmittance: local exclusive products, one warp scan of the lane totals per composite
+  float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const bool ok = (st.valid >> j) & 1u;
+    p[j] = tot; pb[j] = totb;
+    tot *= ok ? (1.0f - a[j] + 1e-7f) : 1.0f;
+    totb *= ok ? (1.0f - ab[j] + 1e-7f) : 1.0f;
+  }
+  const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
+  float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, inclb, 1);
+  if (lane == 0) { ex = 1.f; exb = 1.f; }
+  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const float w = a[j] * (ex * p[j]), wb = ab[j] * (exb * pb[j]);
+    if (weights && ((st.valid >> j) & 1u)) weights[(long long)r * S + SPL * lane + j] = w;
+    v[0] += w * c0[j]; v[1] += w * c1[j]; v[2] += w * c2[j]; v[3] += w;
+    v[4] += wb * c0[j]; v[5] += wb * c1[j]; v[6] += wb * c2[j];
+  }
+  const float tsum = warp_sum8(v, lane);
+  const float sacc = __shfl_sync(FULL, tsum, 12);
+  if ((lane & 3) == 0) {
+    const int q = lane >> 2;
+    if (q < 3) {
+      const float x = tsum + (is_nerf ? 1.0f - sacc : 0.f);
+      rgb_raw[3 * r + q] = x;
+      rgb[3 * r + q] = fminf(fmaxf(x, 0.f), 1.f);
+    } else if (q == 3) {
+      acc[r] = tsum;
+    } else if (q < 7) {
+      rgb_b[3 * r + q - 4] = tsum;
+    }
+  }
+}
+
+template <bool FULLS>
+__global__ void __launch_bounds__(32 * CW, 4) composite_bwd_staged_kernel(
+    const float* __restrict__ a_in, const float* __restrict__ c_in, const float* __restrict__ a_out,
+    const float* __restrict__ c_out, const int32_t* __restrict__ ray_map, int R, int S, int is_nerf,
+    const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb, const float* __restrict__ d_acc,
+    const float* __restrict__ d_rgb_b, float* d_a_in, float* d_c_in, float* d_a_out, float* d_c_out) {
+  __shared__ __align__(16) float s_a[CW][A_ST];
+  __shared__ __align__(16) float s_c[CW][C_ST];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int r = blockIdx.x * CW + wid;
+  if (r >= R) return;
+  float* sa = s_a[wid];
+  float* sc = s_c[wid];
+  const RayStage st = stage_ray<FULLS>(ray_map, r, S, lane, a_in, c_in, a_out, c_out, sa, sc);
+  // per-ray upstream gradients while the copies fly
+  float g0 = d_rgb ? d_rgb[3 * r] : 0.f, g1 = d_rgb ? d_rgb[3 * r + 1] : 0.f, g2 = d_rgb ? d_rgb[3 * r + 2] : 0.f;
+  const float q0 = rgb_raw[3 * r], q1 = rgb_raw[3 * r + 1], q2 = rgb_raw[3 * r + 2];
+  if (!(q0 >= 0.f && q0 <= 1.f)) g0 = 0.f;       // clamp(color, 0, 1) passes the gradient on the closed interval
+  if (!(q1 >= 0.f && q1 <= 1.f)) g1 = 0.f;
+  if (!(q2 >= 0.f && q2 <= 1.f)) g2 = 0.f;
+  const float ga = (d_acc ? d_acc[r] : 0.f) - (is_nerf ? (g0 + g1 + g2) : 0.f);
+  const float h0 = d_rgb_b ? d_rgb_b[3 * r] : 0.f, h1 = d_rgb_b ? d_rgb_b[3 * r + 1] : 0.f,
+              h2 = d_rgb_b ? d_rgb_b[3 * r + 2] : 0.f;
+  cp_async_wait_all();
+  __syncwarp();
+  float a[SPL], gk[SPL], gkb[SPL], vv[SPL];
+  float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
+  const float v_in = 1.0f - 0.f + 1e-7f;          // 1 - alpha * outer_mask + 1e-7 of an inner sample in the bkgr composite
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const bool ok = (st.valid >> j) & 1u;
+    a[j] = ok ? sa[st.pa[j]] : 0.f;
+    const float c0 = ok ? sc[st.pc[j]] : 0.f, c1 = ok ? sc[st.pc[j] + 1] : 0.f, c2 = ok ? sc[st.pc[j] + 2] : 0.f;
+    gk[j] = ok ? (g0 * c0 + g1 * c1 + g2 * c2 + ga) : 0.f;
+    gkb[j] = ok ? (h0 * c0 + h1 * c1 + h2 * c2) : 0.f;
+    vv[j] = ok ? (1.0f - a[j] + 1e-7f) : 1.0f;
+    p[j] = tot; pb[j] = totb;
+    tot *= vv[j]; totb *= ok ? (((st.inner >> j) & 1u) ? v_in : vv[j]) : 1.0f;
+  }
+  const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
+  float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, inclb, 1);
+  if (lane == 0) { ex = 1.f; exb = 1.f; }
+  // forward quantities, colour gradient in place, local exclusive suffix sums of g * w
+  float q[SPL], qb[SPL], suf = 0.f, sufb = 0.f;
+#pragma unroll
+  for (int j = SPL - 1; j >= 0; --j) {
+    p[j] *= ex; pb[j] *= exb;                       // T, T_bkgr
+    const float w = a[j] * p[j], wb = ((st.inner >> j) & 1u) ? 0.f : a[j] * pb[j];
+    if ((st.valid >> j) & 1u) {
+      sc[st.pc[j]] = w * g0 + wb * h0; sc[st.pc[j] + 1] = w * g1 + wb * h1; sc[st.pc[j] + 2] = w * g2 + wb * h2;
+    }
+    q[j] = suf; qb[j] = sufb;
+    suf += gk[j] * w; sufb += gkb[j] * wb;
+  }
+  const float rin = scan_add32_rev(suf, lane), rinb = scan_add32_rev(sufb, lane);
+  float rex = __shfl_down_sync(FULL, rin, 1), rexb = __shfl_down_sync(FULL, rinb, 1);
+  if (lane == 31) { rex = 0.f; rexb = 0.f; }
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    if ((st.valid >> j) & 1u) {
+      float da = gk[j] * p[j] - __fdividef(rex + q[j], vv[j]);
+      if (!((st.inner >> j) & 1u)) da += gkb[j] * pb[j] - __fdividef(rexb + qb[j], vv[j]);
+      sa[st.pa[j]] = da;
+    }
+  }
+  __syncwarp();
+  // send the four runs back, chunk by chunk
+  {
+    const int hi = st.in_off & 3, ho = st.out_off & 3;
+    float* gi = d_a_in + (st.in_off & ~3);
+    float* go = d_a_out + (st.out_off & ~3);
+#pragma unroll
+    for (int t = lane; t < 64; t += 32) {
+      const bool in = t < st.nch_ai;
+      if (t < st.nch_ai + st.nch_ao)
+        unstage_chunk(in ? gi : go, in ? hi : ho, in ? hi + st.n_in : ho + st.n_out, sa + (in ? 0 : 4 * st.nch_ai),
+                      in ? t : t - st.nch_ai);
+    }
+  }
+  {
+    const int hi = (3 * st.in_off) & 3, ho = (3 * st.out_off) & 3;
+    float* gi = d_c_in + ((3ll * st.in_off) & ~3ll);
+    float* go = d_c_out + ((3ll * st.out_off) & ~3ll);
+#pragma unroll
+    for (int t = lane; t < 128; t += 32) {
+      const bool in = t < st.nch_ci;
+      if (t < st.nch_ci + st.nch_co)
+        unstage_chunk(in ? gi : go, in ? hi : ho, in ? hi + 3 * st.n_in : ho + 3 * st.n_out,
+                      sc + (in ? 0 : 4 * st.nch_ci), in ? t : t - st.nch_ci);
+    }
+  }
+}
+
 __global__ void scatter_rows_kernel(const float* __restrict__ src, long long M, int C, const int32_t* __restrict__ id,
                                     float* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -375,6 +659,9 @@ __global__ void scatter_rows_kernel(const float* __restrict__ src, long long M, 
 }  // namespace nunerf
 
 using namespace nunerf;
+
+// NUNERF_COMPOSITE_LEGACY=1 selects the lane-per-sample kernels also where the staged ones apply (A/B measurements)
+static const bool g_composite_legacy = [] { const char* e = getenv("NUNERF_COMPOSITE_LEGACY"); return e && e[0] == '1'; }();
 
 extern "C" int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists,
                                       float* pts, int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in,
@@ -401,7 +688,12 @@ extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in
                                     const int32_t* ray_map, void* stream) {
   NUNERF_REQUIRE((slot || ray_map) && rgb && rgb_raw && acc && rgb_bkgr && R > 0 && S > 0 && S <= 256,
                  "composite_fwd: bad arguments");
-  if (S <= 160)
+  const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out) & 15) == 0;
+  if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
+    (S == 32 * SPL ? composite_fwd_staged_kernel<true> : composite_fwd_staged_kernel<false>)<<<cdiv(R, CW), 32 * CW, 0,
+                                                                                             (cudaStream_t)stream>>>(
+        alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
+  else if (S <= 160)
     composite_fwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, slot, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   else
@@ -419,7 +711,14 @@ extern "C" int nunerf_composite_bwd(const float* alpha_in, const float* color_in
   NUNERF_REQUIRE((slot || ray_map) && rgb_raw && d_alpha_in && d_color_in && d_alpha_out && d_color_out && R > 0 && S > 0 &&
                      S <= 256,
                  "composite_bwd: bad arguments");
-  if (S <= 160)
+  const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out |
+                         (uintptr_t)d_alpha_in | (uintptr_t)d_color_in | (uintptr_t)d_alpha_out | (uintptr_t)d_color_out) & 15) == 0;
+  if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
+    (S == 32 * SPL ? composite_bwd_staged_kernel<true> : composite_bwd_staged_kernel<false>)<<<cdiv(R, CW), 32 * CW, 0,
+                                                                                             (cudaStream_t)stream>>>(
+        alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
+        d_color_in, d_alpha_out, d_color_out);
+  else if (S <= 160)
     composite_bwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, slot, ray_map, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr,
         d_alpha_in, d_color_in, d_alpha_out, d_color_out);

@@ -617,8 +617,10 @@ def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
     call("nunerf_shade_mix_fwd", C.byref(_mix_params(w, t)))
 
 
-def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max):
-    """ZT:725-793 forward.  Returns the tape and the output tensors."""
+def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_weights=True):
+    """ZT:725-793 forward.  Returns the tape and the output tensors.  The dense per-sample compositing weights [R,S]
+    are only needed by the validation outputs (depth / normal, ZT:657-693): a training step passes want_weights=False and
+    the compositing kernel does not write them."""
     planes = w.planes
     R, S = z_vals.shape
     dev = z_vals.device
@@ -654,10 +656,10 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
 
     # ---- compositing (ZT:773-788)
     rgb, t.rgb_raw, acc, bkgr = _f(R, 3, dev=dev), _f(R, 3, dev=dev), _f(R, dev=dev), _f(R, 3, dev=dev)
-    weights = _f(R, S, dev=dev)
+    weights = _f(R, S, dev=dev) if want_weights else _f(0, S, dev=dev)
     call("nunerf_composite_fwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
          None, R, S, t.is_nerf, rgb.data_ptr(), t.rgb_raw.data_ptr(), acc.data_ptr(), bkgr.data_ptr(),
-         weights.data_ptr(), t.ray_map.data_ptr())
+         weights.data_ptr() if want_weights else None, t.ray_map.data_ptr())
     # ---- per-ray specular probe: outer_light(IDE(d, 0)) (ZT:780-781), activation applied by the caller
     t.xs = P(R, 128, planes, dev)
     t.dn = _norm_dirs(d)

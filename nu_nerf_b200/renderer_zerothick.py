@@ -53,8 +53,9 @@ class _RenderCoreFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, pack, inv_s, *params):
         eng = _engine()
-        w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_inv_s = pack
-        t, rgb, acc, bkgr, wts = eng.core_forward(w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max)
+        w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_inv_s, want_weights = pack
+        t, rgb, acc, bkgr, wts = eng.core_forward(w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max,
+                                                  want_weights=want_weights)
         ctx.tape, ctx.w, ctx.n_params, ctx.want_inv_s = t, w, len(params), want_inv_s
         dev = rgb.device
         if t.n_in > 0:
@@ -263,7 +264,7 @@ class NeROShapeRenderer(nn.Module):
         frozen = freeze is not None and step is not None and step < freeze
         inv_s = torch.exp(self.deviation_network.variance * 10.0)
         exp_max = self.color_network.cfg["light_exp_max"]
-        pack = (w, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen)
+        pack = (w, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen, not is_train)
         (rgb, acc, bkgr, gerr, trans, met, spec, occ, weights, pts_in, sdf_in, grad_in, dirs_in,
          refl_in) = _RenderCoreFn.apply(pack, inv_s, *params)
         inv_s_c = inv_s.clip(1e-6, 1e6)

@@ -118,4 +118,4 @@ def test_extract_geometry_of_the_initial_field():
     V, E, F, boundary, nonmanifold, inconsistent = mco.mesh_stats(t)
     assert (boundary, nonmanifold, inconsistent) == (0, 0, 0) and V - E + F == 2
     rad = np.linalg.norm(v, axis=1)
-    assert 0.4 < rad.min() and rad.max() < 0.6
+    assert 0.3 < rad.min() and rad.max() < 0.7          # the geometric init is a bumpy sphere of radius ~0.5

@@ -74,8 +74,8 @@ def main():
             a_out, c_out = torch.rand(n_out, device=dev) * 0.05, torch.rand(n_out, 3, device=dev)
             rgb, raw, acc, bk, wts = f(R, 3), f(R, 3), f(R), f(R, 3), f(R, S)
             eng.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
-                     None, R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), wts.data_ptr(),
-                     ray_map.data_ptr())
+                     None, R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), None,
+                     ray_map.data_ptr())           # training form: the dense [R,S] weights are an eval-only output
             d_rgb, d_acc, d_bk = torch.randn(R, 3, device=dev), torch.randn(R, device=dev), torch.randn(R, 3, device=dev)
             da_in, dc_in, da_out, dc_out = f(n_in), f(n_in, 3), f(n_out), f(n_out, 3)
             eng.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
