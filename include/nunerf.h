@@ -315,13 +315,15 @@ int nunerf_grid_mask(const float* pts, const float* sdf, int ld_sdf, int count, 
 
 /* ------------------------------------------------------------------ marching cubes (field.py:1312, replaces the
  * host-side mcubes.marching_cubes(u, threshold) of extract_geometry)
- * Cells are numbered x-major over the (res-1)^3 cell grid and grouped in blocks of 256 consecutive cells.
- * mc_count : block_counts[b] = number of triangles of block b (int32, ceil(cells / 256) entries).
+ * Cells are visited in lexicographic (x, y, z) order; a block owns 8 consecutive (x, y) cell rows, blocks numbered
+ * row-major: nunerf_mc_blocks(res) = (res-1) * ceil((res-1) / 8) blocks.  res <= 2048.
+ * mc_count : block_counts[b] = number of triangles of block b (int32, nunerf_mc_blocks(res) entries).
  * mc_emit  : block_offsets = exclusive prefix sum of block_counts (int64, computed by the caller); writes the triangle
  *   soup verts [3 * T, 3] (grid-index coordinates, cell order) and keys [3 * T] = global id of the grid edge carrying
  *   the vertex (((x0 * res + y0) * res + z0) * 3 + axis), so that equal keys are the same vertex.
  * Tables (nu_nerf_b200/mc_tables.py): tri_table int8 [256, 3 * max_tris], n_tris int8 [256], edges int8 [12, 2],
  *   edge_axis int8 [12]; bit k of the case index is set when corner k (offset (k&1, k>>1&1, k>>2&1)) is < iso. */
+long long nunerf_mc_blocks(int res);
 int nunerf_mc_count(const float* u, int res, float iso, const int8_t* n_tris, int32_t* block_counts, void* stream);
 int nunerf_mc_emit(const float* u, int res, float iso, const int8_t* tri_table, int max_tris, const int8_t* n_tris,
                    const int8_t* edges, const int8_t* edge_axis, const long long* block_offsets, float* verts,

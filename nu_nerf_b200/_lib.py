@@ -88,6 +88,8 @@ class BvhNode(C.Structure):
 
 lib.nunerf_last_error.restype = C.c_char_p
 lib.nunerf_launch_count.restype = cll
+lib.nunerf_mc_blocks.argtypes = [ci]
+lib.nunerf_mc_blocks.restype = cll
 
 _SIGS = {
     "nunerf_linear": [C.POINTER(LinearT), vp],
@@ -141,7 +143,7 @@ for _name, _args in _SIGS.items():
     _fn.argtypes = _args
     _fn.restype = ci
 
-ALL_SYMBOLS = ["nunerf_last_error", "nunerf_version", "nunerf_launch_count"] + list(_SIGS)
+ALL_SYMBOLS = ["nunerf_last_error", "nunerf_version", "nunerf_launch_count", "nunerf_mc_blocks"] + list(_SIGS)
 
 
 def ptr(t):

@@ -111,6 +111,13 @@ __device__ __forceinline__ int scan_block_base(const int32_t* __restrict__ ray_i
 // sample.
 constexpr int RAY_MAP = 10;
 
+// F.normalize(dirs) (ZT:740): d / max(||d||, 1e-12) with explicitly rounded operations (both compaction kernels share it)
+__device__ __forceinline__ void normalized_dir(const float* __restrict__ d, int r, float& dx, float& dy, float& dz) {
+  dx = d[3 * r]; dy = d[3 * r + 1]; dz = d[3 * r + 2];
+  const float nrm = fmaxf(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-12f);
+  dx = __fdiv_rn(dx, nrm); dy = __fdiv_rn(dy, nrm); dz = __fdiv_rn(dz, nrm);
+}
+
 // ---- geometry pass 3: compact gather of both sets (row-major mask order, as points[inner_mask]); the per-sample
 //      geometry is recomputed from z with the arithmetic of pass 1 (bit-identical) instead of being re-read
 __global__ void compact_kernel(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
@@ -123,10 +130,8 @@ __global__ void compact_kernel(const float* __restrict__ o, const float* __restr
   if (r >= R) return;
   const float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
   const float rdx = d[3 * r], rdy = d[3 * r + 1], rdz = d[3 * r + 2];
-  // F.normalize(dirs) (ZT:740): d / max(||d||, 1e-12)
-  float dx = rdx, dy = rdy, dz = rdz;
-  float nrm = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-12f);
-  dx /= nrm; dy /= nrm; dz /= nrm;
+  float dx, dy, dz;
+  normalized_dir(d, r, dx, dy, dz);
   int in_run = ray_off[r] + scan_block_base(ray_inner, r / SCAN_BLOCK, lane);
   int out_run = r * S - in_run;
   if (r == 0) {                                 // totals for the host (the one sync of the step reads them)
@@ -408,6 +413,20 @@ __device__ __forceinline__ float warp_sum8(float (&v)[8], int lane) {
   return v[0];
 }
 
+// the per-ray compaction map in registers (loaded one ray ahead)
+struct RayMapRegs {
+  int in_off, out_off;
+  unsigned m[5];
+};
+__device__ __forceinline__ RayMapRegs load_ray_map(const int32_t* __restrict__ ray_map, int r) {
+  RayMapRegs mp;
+  const int32_t* rm = ray_map + (long long)r * RAY_MAP;
+  mp.in_off = __ldg(rm); mp.out_off = __ldg(rm + 1);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) mp.m[k] = (unsigned)__ldg(rm + 2 + k);
+  return mp;
+}
+
 struct RayStage {
   int pa[SPL], pc[SPL];      // staged positions of the lane's samples (alpha / first colour component)
   unsigned inner;            // bit j: sample j of the lane is an inner sample
@@ -416,50 +435,55 @@ struct RayStage {
   int nch_ai, nch_ao, nch_ci, nch_co;     // 16-byte chunks of the four runs
 };
 
-// decode the ray map for this lane and start the chunk loads (FULLS: S == 160, every sample of every lane exists)
-template <bool FULLS>
-__device__ __forceinline__ RayStage stage_ray(const int32_t* __restrict__ ray_map, int r, int S, int lane,
-                                              const float* __restrict__ a_in, const float* __restrict__ c_in,
-                                              const float* __restrict__ a_out, const float* __restrict__ c_out, float* sa,
-                                              float* sc) {
-  RayStage st;
-  const int32_t* rm = ray_map + (long long)r * RAY_MAP;
-  const int in_off = __ldg(rm), out_off = __ldg(rm + 1);
-  unsigned m[6];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) m[k] = (unsigned)__ldg(rm + 2 + k);
-  m[5] = 0u;
-  const int n_in = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]) + __popc(m[4]);
+// run lengths / chunk counts of a ray.  Staged layout: [inner chunks | outer chunks]; a run keeps its global alignment
+// modulo 16 B
+__device__ __forceinline__ void ray_runs(const RayMapRegs& mp, int S, RayStage& st) {
+  const int n_in = __popc(mp.m[0]) + __popc(mp.m[1]) + __popc(mp.m[2]) + __popc(mp.m[3]) + __popc(mp.m[4]);
   const int n_out = S - n_in;
-  st.in_off = in_off; st.out_off = out_off; st.n_in = n_in; st.n_out = n_out;
-  // staged layout: [inner chunks | outer chunks]; a run keeps its global alignment modulo 16 B
-  const int hi_a = in_off & 3, ho_a = out_off & 3, hi_c = (3 * in_off) & 3, ho_c = (3 * out_off) & 3;
-  st.nch_ai = n_in ? (hi_a + n_in + 3) >> 2 : 0;
-  st.nch_ao = n_out ? (ho_a + n_out + 3) >> 2 : 0;
-  st.nch_ci = n_in ? (hi_c + 3 * n_in + 3) >> 2 : 0;
-  st.nch_co = n_out ? (ho_c + 3 * n_out + 3) >> 2 : 0;
+  st.in_off = mp.in_off; st.out_off = mp.out_off; st.n_in = n_in; st.n_out = n_out;
+  st.nch_ai = n_in ? ((mp.in_off & 3) + n_in + 3) >> 2 : 0;
+  st.nch_ao = n_out ? ((mp.out_off & 3) + n_out + 3) >> 2 : 0;
+  st.nch_ci = n_in ? (((3 * mp.in_off) & 3) + 3 * n_in + 3) >> 2 : 0;
+  st.nch_co = n_out ? (((3 * mp.out_off) & 3) + 3 * n_out + 3) >> 2 : 0;
+}
+
+// start the chunk loads of a ray into its staging buffers (one commit group)
+__device__ __forceinline__ void issue_ray_loads(const RayMapRegs& mp, int S, int lane, const float* __restrict__ a_in,
+                                                const float* __restrict__ c_in, const float* __restrict__ a_out,
+                                                const float* __restrict__ c_out, float* sa, float* sc) {
+  RayStage st;
+  ray_runs(mp, S, st);
   {
-    const float* gi = a_in + (in_off & ~3);
-    const float* go = a_out + (out_off & ~3) - 4 * st.nch_ai;
+    const float* gi = a_in + (st.in_off & ~3);
+    const float* go = a_out + (st.out_off & ~3) - 4 * st.nch_ai;
 #pragma unroll
     for (int t = lane; t < 64; t += 32)
       if (t < st.nch_ai + st.nch_ao) cp_async16(sa + 4 * t, (t < st.nch_ai ? gi : go) + 4 * t);
   }
   {
-    const float* gi = c_in + ((3ll * in_off) & ~3ll);
-    const float* go = c_out + ((3ll * out_off) & ~3ll) - 4 * st.nch_ci;
+    const float* gi = c_in + ((3ll * st.in_off) & ~3ll);
+    const float* go = c_out + ((3ll * st.out_off) & ~3ll) - 4 * st.nch_ci;
 #pragma unroll
     for (int t = lane; t < 128; t += 32)
       if (t < st.nch_ci + st.nch_co) cp_async16(sc + 4 * t, (t < st.nch_ci ? gi : go) + 4 * t);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// staged positions of the lane's samples (FULLS: S == 160, every sample of every lane exists)
+template <bool FULLS>
+__device__ __forceinline__ RayStage decode_ray(const RayMapRegs& mp, int S, int lane) {
+  RayStage st;
+  ray_runs(mp, S, st);
+  const int hi_a = mp.in_off & 3, ho_a = mp.out_off & 3, hi_c = (3 * mp.in_off) & 3, ho_c = (3 * mp.out_off) & 3;
   // the lane's 5 mask bits and the number of inner samples in front of them
   const int b0 = SPL * lane, w = b0 >> 5, sh = b0 & 31;
-  unsigned lo = m[0], hi = m[1];
+  unsigned lo = mp.m[0], hi = mp.m[1];
   int before = 0, run = 0;
 #pragma unroll
   for (int k = 1; k < 5; ++k) {
-    run += __popc(m[k - 1]);
-    if (w == k) { lo = m[k]; hi = m[k + 1]; before = run; }
+    run += __popc(mp.m[k - 1]);
+    if (w == k) { lo = mp.m[k]; hi = k < 4 ? mp.m[k < 4 ? k + 1 : 4] : 0u; before = run; }
   }
   st.inner = __funnelshift_r(lo, hi, sh) & 31u;
   before += __popc(lo & ((1u << sh) - 1u));
@@ -493,158 +517,238 @@ __device__ __forceinline__ void unstage_chunk(float* __restrict__ g, int lo, int
   }
 }
 
+// Both kernels are persistent: a warp walks over rays r = w, w + W, ... with two staging buffers -- the map of ray i+2
+// is requested and the chunk loads of ray i+1 are in flight while ray i is computed, so neither the map's nor the data's
+// memory latency is exposed.
 template <bool FULLS>
-__global__ void __launch_bounds__(32 * CW, 5) composite_fwd_staged_kernel(
+__global__ void __launch_bounds__(32 * CW, 4) composite_fwd_staged_kernel(
     const float* __restrict__ a_in, const float* __restrict__ c_in, const float* __restrict__ a_out,
     const float* __restrict__ c_out, const int32_t* __restrict__ ray_map, int R, int S, int is_nerf, float* rgb,
     float* rgb_raw, float* acc, float* rgb_b, float* weights) {
-  __shared__ __align__(16) float s_a[CW][A_ST];
-  __shared__ __align__(16) float s_c[CW][C_ST];
+  __shared__ __align__(16) float s_a[2][CW][A_ST];
+  __shared__ __align__(16) float s_c[2][CW][C_ST];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int r = blockIdx.x * CW + wid;
+  const int stride = gridDim.x * CW;
+  int r = blockIdx.x * CW + wid;
   if (r >= R) return;
-  float* sa = s_a[wid];
-  float* sc = s_c[wid];
-  const RayStage st = stage_ray<FULLS>(ray_map, r, S, lane, a_in, c_in, a_out, c_out, sa, sc);
-  cp_async_wait_all();
-  __syncwarp();
-  float a[SPL], ab[SPL], c0[SPL], c1[SPL], c2[SPL];
+  RayMapRegs cur = load_ray_map(ray_map, r);
+  issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[0][wid], s_c[0][wid]);
+  RayMapRegs nxt = load_ray_map(ray_map, min(r + stride, R - 1));
+  for (int buf = 0; r < R; r += stride, buf ^= 1) {
+    float* sa = s_a[buf][wid];
+    float* sc = s_c[buf][wid];
+    cp_async_wait_all();
+    __syncwarp();
+    const RayStage st = decode_ray<FULLS>(cur, S, lane);
+    float a[SPL], ab[SPL], c0[SPL], c1[SPL], c2[SPL];
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    const bool ok = (st.valid >> j) & 1u;
-    a[j] = ok ? sa[st.pa[j]] : 0.f;
-    c0[j] = ok ? sc[st.pc[j]] : 0.f;
-    c1[j] = ok ? sc[st.pc[j] + 1] : 0.f;
-    c2[j] = ok ? sc[st.pc[j] + 2] : 0.f;
-    ab[j] = ((st.inner >> j) & 1u) ? 0.f : a[j];
-  }
-  // transmittance: local exclusive products, one warp scan of the lane totals per composite
-  float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
+    for (int j = 0; j < SPL; ++j) {
+      const bool ok = (st.valid >> j) & 1u;
+      a[j] = ok ? sa[st.pa[j]] : 0.f;
+      c0[j] = ok ? sc[st.pc[j]] : 0.f;
+      c1[j] = ok ? sc[st.pc[j] + 1] : 0.f;
+      c2[j] = ok ? sc[st.pc[j] + 2] : 0.f;
+      ab[j] = ((st.inner >> j) & 1u) ? 0.f : a[j];
+    }
+    // next ray: its map arrived during the previous iteration; start its loads, request the map after it
+    cur = nxt;
+    if (r + stride < R) {
+      issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[buf ^ 1][wid], s_c[buf ^ 1][wid]);
+      nxt = load_ray_map(ray_map, min(r + 2 * stride, R - 1));
+    }
+    // transmittance: local exclusive products, one warp scan of the lane totals per composite
+    float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    const bool ok = (st.valid >> j) & 1u;
-    p[j] = tot; pb[j] = totb;
-    tot *= ok ? (1.0f - a[j] + 1e-7f) : 1.0f;
-    totb *= ok ? (1.0f - ab[j] + 1e-7f) : 1.0f;
-  }
-  const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
-  float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, inclb, 1);
-  if (lane == 0) { ex = 1.f; exb = 1.f; }
-  float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < SPL; ++j) {
+      const bool ok = (st.valid >> j) & 1u;
+      p[j] = tot; pb[j] = totb;
+      tot *= ok ? (1.0f - a[j] + 1e-7f) : 1.0f;
+      totb *= ok ? (1.0f - ab[j] + 1e-7f) : 1.0f;
+    }
+    const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
+    float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, inclb, 1);
+    if (lane == 0) { ex = 1.f; exb = 1.f; }
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    const float w = a[j] * (ex * p[j]), wb = ab[j] * (exb * pb[j]);
-    if (weights && ((st.valid >> j) & 1u)) weights[(long long)r * S + SPL * lane + j] = w;
-    v[0] += w * c0[j]; v[1] += w * c1[j]; v[2] += w * c2[j]; v[3] += w;
-    v[4] += wb * c0[j]; v[5] += wb * c1[j]; v[6] += wb * c2[j];
-  }
-  const float tsum = warp_sum8(v, lane);
-  const float sacc = __shfl_sync(FULL, tsum, 12);
-  if ((lane & 3) == 0) {
-    const int q = lane >> 2;
-    if (q < 3) {
-      const float x = tsum + (is_nerf ? 1.0f - sacc : 0.f);
-      rgb_raw[3 * r + q] = x;
-      rgb[3 * r + q] = fminf(fmaxf(x, 0.f), 1.f);
-    } else if (q == 3) {
-      acc[r] = tsum;
-    } else if (q < 7) {
-      rgb_b[3 * r + q - 4] = tsum;
+    for (int j = 0; j < SPL; ++j) {
+      const float w = a[j] * (ex * p[j]), wb = ab[j] * (exb * pb[j]);
+      if (weights && ((st.valid >> j) & 1u)) weights[(long long)r * S + SPL * lane + j] = w;
+      v[0] += w * c0[j]; v[1] += w * c1[j]; v[2] += w * c2[j]; v[3] += w;
+      v[4] += wb * c0[j]; v[5] += wb * c1[j]; v[6] += wb * c2[j];
+    }
+    const float tsum = warp_sum8(v, lane);
+    const float sacc = __shfl_sync(FULL, tsum, 12);
+    if ((lane & 3) == 0) {
+      const int q = lane >> 2;
+      if (q < 3) {
+        const float x = tsum + (is_nerf ? 1.0f - sacc : 0.f);
+        rgb_raw[3 * r + q] = x;
+        rgb[3 * r + q] = fminf(fmaxf(x, 0.f), 1.f);
+      } else if (q == 3) {
+        acc[r] = tsum;
+      } else if (q < 7) {
+        rgb_b[3 * r + q - 4] = tsum;
+      }
     }
   }
 }
 
 template <bool FULLS>
-__global__ void __launch_bounds__(32 * CW, 4) composite_bwd_staged_kernel(
+__global__ void __launch_bounds__(32 * CW, 3) composite_bwd_staged_kernel(
     const float* __restrict__ a_in, const float* __restrict__ c_in, const float* __restrict__ a_out,
     const float* __restrict__ c_out, const int32_t* __restrict__ ray_map, int R, int S, int is_nerf,
     const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb, const float* __restrict__ d_acc,
     const float* __restrict__ d_rgb_b, float* d_a_in, float* d_c_in, float* d_a_out, float* d_c_out) {
-  __shared__ __align__(16) float s_a[CW][A_ST];
-  __shared__ __align__(16) float s_c[CW][C_ST];
+  __shared__ __align__(16) float s_a[2][CW][A_ST];
+  __shared__ __align__(16) float s_c[2][CW][C_ST];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int r = blockIdx.x * CW + wid;
+  const int stride = gridDim.x * CW;
+  int r = blockIdx.x * CW + wid;
   if (r >= R) return;
-  float* sa = s_a[wid];
-  float* sc = s_c[wid];
-  const RayStage st = stage_ray<FULLS>(ray_map, r, S, lane, a_in, c_in, a_out, c_out, sa, sc);
-  // per-ray upstream gradients while the copies fly
-  float g0 = d_rgb ? d_rgb[3 * r] : 0.f, g1 = d_rgb ? d_rgb[3 * r + 1] : 0.f, g2 = d_rgb ? d_rgb[3 * r + 2] : 0.f;
-  const float q0 = rgb_raw[3 * r], q1 = rgb_raw[3 * r + 1], q2 = rgb_raw[3 * r + 2];
-  if (!(q0 >= 0.f && q0 <= 1.f)) g0 = 0.f;       // clamp(color, 0, 1) passes the gradient on the closed interval
-  if (!(q1 >= 0.f && q1 <= 1.f)) g1 = 0.f;
-  if (!(q2 >= 0.f && q2 <= 1.f)) g2 = 0.f;
-  const float ga = (d_acc ? d_acc[r] : 0.f) - (is_nerf ? (g0 + g1 + g2) : 0.f);
-  const float h0 = d_rgb_b ? d_rgb_b[3 * r] : 0.f, h1 = d_rgb_b ? d_rgb_b[3 * r + 1] : 0.f,
-              h2 = d_rgb_b ? d_rgb_b[3 * r + 2] : 0.f;
-  cp_async_wait_all();
-  __syncwarp();
-  float a[SPL], gk[SPL], gkb[SPL], vv[SPL];
-  float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
-  const float v_in = 1.0f - 0.f + 1e-7f;          // 1 - alpha * outer_mask + 1e-7 of an inner sample in the bkgr composite
+  RayMapRegs cur = load_ray_map(ray_map, r);
+  issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[0][wid], s_c[0][wid]);
+  RayMapRegs nxt = load_ray_map(ray_map, min(r + stride, R - 1));
+  for (int buf = 0; r < R; r += stride, buf ^= 1) {
+    float* sa = s_a[buf][wid];
+    float* sc = s_c[buf][wid];
+    // per-ray upstream gradients
+    float g0 = d_rgb ? d_rgb[3 * r] : 0.f, g1 = d_rgb ? d_rgb[3 * r + 1] : 0.f, g2 = d_rgb ? d_rgb[3 * r + 2] : 0.f;
+    const float q0 = rgb_raw[3 * r], q1 = rgb_raw[3 * r + 1], q2 = rgb_raw[3 * r + 2];
+    if (!(q0 >= 0.f && q0 <= 1.f)) g0 = 0.f;       // clamp(color, 0, 1) passes the gradient on the closed interval
+    if (!(q1 >= 0.f && q1 <= 1.f)) g1 = 0.f;
+    if (!(q2 >= 0.f && q2 <= 1.f)) g2 = 0.f;
+    const float ga = (d_acc ? d_acc[r] : 0.f) - (is_nerf ? (g0 + g1 + g2) : 0.f);
+    const float h0 = d_rgb_b ? d_rgb_b[3 * r] : 0.f, h1 = d_rgb_b ? d_rgb_b[3 * r + 1] : 0.f,
+                h2 = d_rgb_b ? d_rgb_b[3 * r + 2] : 0.f;
+    cp_async_wait_all();
+    __syncwarp();
+    const RayStage st = decode_ray<FULLS>(cur, S, lane);
+    float a[SPL], gk[SPL], gkb[SPL], vv[SPL];
+    float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
+    const float v_in = 1.0f - 0.f + 1e-7f;        // 1 - alpha * outer_mask + 1e-7 of an inner sample in the bkgr composite
 #pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    const bool ok = (st.valid >> j) & 1u;
-    a[j] = ok ? sa[st.pa[j]] : 0.f;
-    const float c0 = ok ? sc[st.pc[j]] : 0.f, c1 = ok ? sc[st.pc[j] + 1] : 0.f, c2 = ok ? sc[st.pc[j] + 2] : 0.f;
-    gk[j] = ok ? (g0 * c0 + g1 * c1 + g2 * c2 + ga) : 0.f;
-    gkb[j] = ok ? (h0 * c0 + h1 * c1 + h2 * c2) : 0.f;
-    vv[j] = ok ? (1.0f - a[j] + 1e-7f) : 1.0f;
-    p[j] = tot; pb[j] = totb;
-    tot *= vv[j]; totb *= ok ? (((st.inner >> j) & 1u) ? v_in : vv[j]) : 1.0f;
-  }
-  const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
-  float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, inclb, 1);
-  if (lane == 0) { ex = 1.f; exb = 1.f; }
-  // forward quantities, colour gradient in place, local exclusive suffix sums of g * w
-  float q[SPL], qb[SPL], suf = 0.f, sufb = 0.f;
-#pragma unroll
-  for (int j = SPL - 1; j >= 0; --j) {
-    p[j] *= ex; pb[j] *= exb;                       // T, T_bkgr
-    const float w = a[j] * p[j], wb = ((st.inner >> j) & 1u) ? 0.f : a[j] * pb[j];
-    if ((st.valid >> j) & 1u) {
-      sc[st.pc[j]] = w * g0 + wb * h0; sc[st.pc[j] + 1] = w * g1 + wb * h1; sc[st.pc[j] + 2] = w * g2 + wb * h2;
+    for (int j = 0; j < SPL; ++j) {
+      const bool ok = (st.valid >> j) & 1u;
+      a[j] = ok ? sa[st.pa[j]] : 0.f;
+      const float c0 = ok ? sc[st.pc[j]] : 0.f, c1 = ok ? sc[st.pc[j] + 1] : 0.f, c2 = ok ? sc[st.pc[j] + 2] : 0.f;
+      gk[j] = ok ? (g0 * c0 + g1 * c1 + g2 * c2 + ga) : 0.f;
+      gkb[j] = ok ? (h0 * c0 + h1 * c1 + h2 * c2) : 0.f;
+      vv[j] = ok ? (1.0f - a[j] + 1e-7f) : 1.0f;
+      p[j] = tot; pb[j] = totb;
+      tot *= vv[j]; totb *= ok ? (((st.inner >> j) & 1u) ? v_in : vv[j]) : 1.0f;
     }
-    q[j] = suf; qb[j] = sufb;
-    suf += gk[j] * w; sufb += gkb[j] * wb;
-  }
-  const float rin = scan_add32_rev(suf, lane), rinb = scan_add32_rev(sufb, lane);
-  float rex = __shfl_down_sync(FULL, rin, 1), rexb = __shfl_down_sync(FULL, rinb, 1);
-  if (lane == 31) { rex = 0.f; rexb = 0.f; }
-#pragma unroll
-  for (int j = 0; j < SPL; ++j) {
-    if ((st.valid >> j) & 1u) {
-      float da = gk[j] * p[j] - __fdividef(rex + q[j], vv[j]);
-      if (!((st.inner >> j) & 1u)) da += gkb[j] * pb[j] - __fdividef(rexb + qb[j], vv[j]);
-      sa[st.pa[j]] = da;
+    // next ray: start its loads into the other buffer, request the map after it
+    cur = nxt;
+    if (r + stride < R) {
+      issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[buf ^ 1][wid], s_c[buf ^ 1][wid]);
+      nxt = load_ray_map(ray_map, min(r + 2 * stride, R - 1));
     }
-  }
-  __syncwarp();
-  // send the four runs back, chunk by chunk
-  {
-    const int hi = st.in_off & 3, ho = st.out_off & 3;
-    float* gi = d_a_in + (st.in_off & ~3);
-    float* go = d_a_out + (st.out_off & ~3);
+    const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
+    float ex = __shfl_up_sync(FULL, incl, 1), exb = __shfl_up_sync(FULL, inclb, 1);
+    if (lane == 0) { ex = 1.f; exb = 1.f; }
+    // forward quantities, colour gradient in place, local exclusive suffix sums of g * w
+    float q[SPL], qb[SPL], suf = 0.f, sufb = 0.f;
 #pragma unroll
-    for (int t = lane; t < 64; t += 32) {
-      const bool in = t < st.nch_ai;
-      if (t < st.nch_ai + st.nch_ao)
-        unstage_chunk(in ? gi : go, in ? hi : ho, in ? hi + st.n_in : ho + st.n_out, sa + (in ? 0 : 4 * st.nch_ai),
-                      in ? t : t - st.nch_ai);
+    for (int j = SPL - 1; j >= 0; --j) {
+      p[j] *= ex; pb[j] *= exb;                       // T, T_bkgr
+      const float w = a[j] * p[j], wb = ((st.inner >> j) & 1u) ? 0.f : a[j] * pb[j];
+      if ((st.valid >> j) & 1u) {
+        sc[st.pc[j]] = w * g0 + wb * h0; sc[st.pc[j] + 1] = w * g1 + wb * h1; sc[st.pc[j] + 2] = w * g2 + wb * h2;
+      }
+      q[j] = suf; qb[j] = sufb;
+      suf += gk[j] * w; sufb += gkb[j] * wb;
     }
-  }
-  {
-    const int hi = (3 * st.in_off) & 3, ho = (3 * st.out_off) & 3;
-    float* gi = d_c_in + ((3ll * st.in_off) & ~3ll);
-    float* go = d_c_out + ((3ll * st.out_off) & ~3ll);
+    const float rin = scan_add32_rev(suf, lane), rinb = scan_add32_rev(sufb, lane);
+    float rex = __shfl_down_sync(FULL, rin, 1), rexb = __shfl_down_sync(FULL, rinb, 1);
+    if (lane == 31) { rex = 0.f; rexb = 0.f; }
 #pragma unroll
-    for (int t = lane; t < 128; t += 32) {
-      const bool in = t < st.nch_ci;
-      if (t < st.nch_ci + st.nch_co)
-        unstage_chunk(in ? gi : go, in ? hi : ho, in ? hi + 3 * st.n_in : ho + 3 * st.n_out,
-                      sc + (in ? 0 : 4 * st.nch_ci), in ? t : t - st.nch_ci);
+    for (int j = 0; j < SPL; ++j) {
+      if ((st.valid >> j) & 1u) {
+        float da = gk[j] * p[j] - __fdividef(rex + q[j], vv[j]);
+        if (!((st.inner >> j) & 1u)) da += gkb[j] * pb[j] - __fdividef(rexb + qb[j], vv[j]);
+        sa[st.pa[j]] = da;
+      }
     }
+    __syncwarp();
+    // send the four runs back, chunk by chunk
+    {
+      const int hi = st.in_off & 3, ho = st.out_off & 3;
+      float* gi = d_a_in + (st.in_off & ~3);
+      float* go = d_a_out + (st.out_off & ~3);
+#pragma unroll
+      for (int t = lane; t < 64; t += 32) {
+        const bool in = t < st.nch_ai;
+        if (t < st.nch_ai + st.nch_ao)
+          unstage_chunk(in ? gi : go, in ? hi : ho, in ? hi + st.n_in : ho + st.n_out, sa + (in ? 0 : 4 * st.nch_ai),
+                        in ? t : t - st.nch_ai);
+      }
+    }
+    {
+      const int hi = (3 * st.in_off) & 3, ho = (3 * st.out_off) & 3;
+      float* gi = d_c_in + ((3ll * st.in_off) & ~3ll);
+      float* go = d_c_out + ((3ll * st.out_off) & ~3ll);
+#pragma unroll
+      for (int t = lane; t < 128; t += 32) {
+        const bool in = t < st.nch_ci;
+        if (t < st.nch_ci + st.nch_co)
+          unstage_chunk(in ? gi : go, in ? hi : ho, in ? hi + 3 * st.n_in : ho + 3 * st.n_out,
+                        sc + (in ? 0 : 4 * st.nch_ci), in ? t : t - st.nch_ci);
+      }
+    }
+    __syncwarp();
   }
+}
+
+// =====================================================================================================================
+// Lean count pass of the geometry (the product path: only the compact lists and the per-ray map are wanted, S <= 160):
+// instantiated for 5 sample blocks, no optional outputs, and the inner test without the square root (192 instead of
+// ~1000 warp instructions per ray).  Two further variants were built and measured at 32 768 rays and are NOT kept:
+// a single-pass kernel with a decoupled look-back over tiles of 8 rays (96 us against 69 us for the three-kernel form:
+// a block's 8 warps idle through the look-back), and a compaction pass that stages the lists through shared memory into
+// 16-byte stores (53 us against 48 us for the scalar-store kernel: 926 warp instructions per ray, issue-bound).
+constexpr int GT = 8;                                      // rays (= warps) per block
+
+// the samples of a ray, lane-per-sample (ZT:730-736): mid points, dists and the inner bit masks; returns the inner count
+template <int NBLK>
+__device__ __forceinline__ int ray_samples(const float* __restrict__ o, const float* __restrict__ d,
+                                           const float* __restrict__ z, int r, int S, int lane, float (&px)[NBLK],
+                                           float (&py)[NBLK], float (&pz)[NBLK], float (&ds)[NBLK], unsigned (&m)[NBLK]) {
+  const float ox = o[3 * r], oy = o[3 * r + 1], oz = o[3 * r + 2];
+  const float rdx = d[3 * r], rdy = d[3 * r + 1], rdz = d[3 * r + 2];
+  const float* zr = z + (long long)r * S;
+  int n_in = 0;
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int s = 32 * k + lane;
+    const bool ok = s < S;
+    px[k] = py[k] = pz[k] = ds[k] = 0.f;
+    if (ok) {
+      const float z0 = zr[s];
+      const float dist = (s + 1 < S) ? __fsub_rn(zr[s + 1], z0) : __fsub_rn(z0, zr[s - 1]);
+      const float zm = __fadd_rn(z0, __fmul_rn(dist, 0.5f));
+      px[k] = __fadd_rn(ox, __fmul_rn(rdx, zm)); py[k] = __fadd_rn(oy, __fmul_rn(rdy, zm));
+      pz[k] = __fadd_rn(oz, __fmul_rn(rdz, zm));
+      ds[k] = dist;
+    }
+    // ||p|| <= 1 with ||p|| = sqrt_rn(q)  <=>  q <= 1 + 2^-23 (sqrt_rn maps (1, 1 + 2^-23] onto 1): no square root needed
+    const float q = __fadd_rn(__fadd_rn(__fmul_rn(px[k], px[k]), __fmul_rn(py[k], py[k])), __fmul_rn(pz[k], pz[k]));
+    m[k] = __ballot_sync(FULL, ok && q <= 1.00000011920928955078125f);
+    n_in += __popc(m[k]);
+  }
+  return n_in;
+}
+
+template <int NBLK>
+__global__ void __launch_bounds__(32 * GT) geometry_count_kernel(const float* __restrict__ o, const float* __restrict__ d,
+                                                                 const float* __restrict__ z, int R, int S,
+                                                                 int32_t* __restrict__ ray_inner) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * GT + (threadIdx.x >> 5);
+  if (r >= R) return;
+  float px[NBLK], py[NBLK], pz[NBLK], ds[NBLK];
+  unsigned m[NBLK];
+  const int n_in = ray_samples<NBLK>(o, d, z, r, S, lane, px, py, pz, ds, m);
+  if (lane == 0) ray_inner[r] = n_in;
 }
 
 __global__ void scatter_rows_kernel(const float* __restrict__ src, long long M, int C, const int32_t* __restrict__ id,
@@ -663,6 +767,12 @@ using namespace nunerf;
 // NUNERF_COMPOSITE_LEGACY=1 selects the lane-per-sample kernels also where the staged ones apply (A/B measurements)
 static const bool g_composite_legacy = [] { const char* e = getenv("NUNERF_COMPOSITE_LEGACY"); return e && e[0] == '1'; }();
 
+// persistent grid of the staged compositing kernels: `per_sm` resident blocks on every SM (or fewer when R is small)
+static int staged_grid(int R, int per_sm) {
+  static int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  return min(cdiv(R, CW), sms * per_sm);
+}
+
 extern "C" int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists,
                                       float* pts, int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in,
                                       float* dists_in, float* dirs_in, int32_t* id_in, float* pts_out, float* dists_out,
@@ -671,8 +781,13 @@ extern "C" int nunerf_render_geometry(const float* o, const float* d, const floa
   NUNERF_REQUIRE(o && d && z && counts && ray_scratch && (slot || ray_map), "render_geometry: null argument");
   NUNERF_REQUIRE(pts_in && dists_in && dirs_in && pts_out && dists_out && dirs_out, "render_geometry: null compact buffer");
   NUNERF_REQUIRE(R > 0 && S >= 2 && S <= 256, "render_geometry: need 2 <= S <= 256");
-  geometry_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, R, S, dists, pts, ray_scratch);
-  NUNERF_CHECK_LAUNCH("geometry_kernel");
+  if (!dists && !pts && S <= 160 && !g_composite_legacy) {
+    geometry_count_kernel<5><<<cdiv(R, GT), 32 * GT, 0, stream>>>(o, d, z, R, S, ray_scratch);
+    NUNERF_CHECK_LAUNCH("geometry_count_kernel");
+  } else {
+    geometry_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, R, S, dists, pts, ray_scratch);
+    NUNERF_CHECK_LAUNCH("geometry_kernel");
+  }
   ray_scan_kernel<<<cdiv(R, SCAN_BLOCK), SCAN_BLOCK, 0, stream>>>(ray_scratch, R, ray_scratch + R);
   NUNERF_CHECK_LAUNCH("ray_scan_kernel");
   compact_kernel<<<cdiv(R, WPB), 32 * WPB, 0, stream>>>(o, d, z, ray_scratch, ray_scratch + R, counts, R, S, slot, ray_map,
@@ -690,7 +805,7 @@ extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in
                  "composite_fwd: bad arguments");
   const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out) & 15) == 0;
   if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
-    (S == 32 * SPL ? composite_fwd_staged_kernel<true> : composite_fwd_staged_kernel<false>)<<<cdiv(R, CW), 32 * CW, 0,
+    (S == 32 * SPL ? composite_fwd_staged_kernel<true> : composite_fwd_staged_kernel<false>)<<<staged_grid(R, 4), 32 * CW, 0,
                                                                                              (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   else if (S <= 160)
@@ -714,7 +829,7 @@ extern "C" int nunerf_composite_bwd(const float* alpha_in, const float* color_in
   const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out |
                          (uintptr_t)d_alpha_in | (uintptr_t)d_color_in | (uintptr_t)d_alpha_out | (uintptr_t)d_color_out) & 15) == 0;
   if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
-    (S == 32 * SPL ? composite_bwd_staged_kernel<true> : composite_bwd_staged_kernel<false>)<<<cdiv(R, CW), 32 * CW, 0,
+    (S == 32 * SPL ? composite_bwd_staged_kernel<true> : composite_bwd_staged_kernel<false>)<<<staged_grid(R, 3), 32 * CW, 0,
                                                                                              (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
         d_color_in, d_alpha_out, d_color_out);

@@ -77,8 +77,7 @@ def marching_cubes(u, isovalue):
         return np.zeros((0, 3)), np.zeros((0, 3), dtype=np.int64)
     dev = u.device
     tri_table, n_tris, edges, edge_axis = _mc_tables(dev)
-    cells = (res - 1) ** 3
-    n_blocks = (cells + 255) // 256
+    n_blocks = int(_lib.lib.nunerf_mc_blocks(res))
     counts = torch.empty(n_blocks, dtype=torch.int32, device=dev)
     call("nunerf_mc_count", u.data_ptr(), res, float(isovalue), n_tris.data_ptr(), counts.data_ptr())
     incl = torch.cumsum(counts, 0, dtype=torch.int64)

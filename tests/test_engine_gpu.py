@@ -613,7 +613,7 @@ def test_sync_free_occlusion_loss_equals_the_reference_selection():
     inv_s = torch.exp(net.deviation_network.variance * 10.0)
     params = [p for dd in w.bank.denses if dd.has_grad for p in (dd.v, dd.g, dd.bias) if p is not None]
     params = list({id(p): p for p in params}.values())
-    pack = (w, args[0], args[1], args[2], 0.4, True, net.color_network.cfg["light_exp_max"], True)
+    pack = (w, args[0], args[1], args[2], 0.4, True, net.color_network.cfg["light_exp_max"], True, False)
     with torch.no_grad():
         res = _RenderCoreFn.apply(pack, inv_s, *params)
     occ, pts_in, sdf_in, grad_in, dirs_in, refl_in = res[7], res[9], res[10], res[11], res[12], res[13]

@@ -68,7 +68,8 @@ def test_device_soup_bit_exact_vs_oracle(case):
     ud = torch.from_numpy(u).cuda()
     res = u.shape[0]
     tri_table, n_tris, edges, edge_axis = sweep._mc_tables(ud.device)
-    n_blocks = ((res - 1) ** 3 + 255) // 256
+    from nu_nerf_b200 import _lib
+    n_blocks = int(_lib.lib.nunerf_mc_blocks(res))
     counts = torch.empty(n_blocks, dtype=torch.int32, device="cuda")
     call("nunerf_mc_count", ud.data_ptr(), res, float(iso), n_tris.data_ptr(), counts.data_ptr())
     assert int(counts.sum()) == len(soup_ref)

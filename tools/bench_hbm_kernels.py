@@ -69,18 +69,36 @@ def main():
                      counts.data_ptr(), scratch.data_ptr(), bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), None,
                      bufs[3].data_ptr(), bufs[4].data_ptr(), bufs[5].data_ptr(), None, ray_map.data_ptr())
             n_in, n_out = (int(v) for v in counts.tolist())
+            # compositing: NSET independent buffer sets (NSET x 84 MB > the 126 MB L2), launched back to back inside ONE
+            # event pair, so that neither a warm L2 nor the ~3 us event/launch gap of a lone 25 us kernel is in the number
+            NSET = 4
+            if it == 0:
+                sets = []
+                for _ in range(NSET):
+                    sets.append(dict(
+                        a_in=torch.rand(n_in, device=dev) * 0.1, c_in=torch.rand(n_in, 3, device=dev),
+                        a_out=torch.rand(n_out, device=dev) * 0.05, c_out=torch.rand(n_out, 3, device=dev),
+                        rgb=f(R, 3), raw=f(R, 3), acc=f(R), bk=f(R, 3), d_rgb=torch.randn(R, 3, device=dev),
+                        d_acc=torch.randn(R, device=dev), d_bk=torch.randn(R, 3, device=dev), da_in=f(n_in),
+                        dc_in=f(n_in, 3), da_out=f(n_out), dc_out=f(n_out, 3)))
             blocker()
-            a_in, c_in = torch.rand(n_in, device=dev) * 0.1, torch.rand(n_in, 3, device=dev)
-            a_out, c_out = torch.rand(n_out, device=dev) * 0.05, torch.rand(n_out, 3, device=dev)
-            rgb, raw, acc, bk, wts = f(R, 3), f(R, 3), f(R), f(R, 3), f(R, S)
-            eng.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
-                     None, R, S, 1, rgb.data_ptr(), raw.data_ptr(), acc.data_ptr(), bk.data_ptr(), None,
-                     ray_map.data_ptr())           # training form: the dense [R,S] weights are an eval-only output
-            d_rgb, d_acc, d_bk = torch.randn(R, 3, device=dev), torch.randn(R, device=dev), torch.randn(R, 3, device=dev)
-            da_in, dc_in, da_out, dc_out = f(n_in), f(n_in, 3), f(n_out), f(n_out, 3)
-            eng.call("nunerf_composite_bwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
-                     None, R, S, 1, raw.data_ptr(), d_rgb.data_ptr(), d_acc.data_ptr(), d_bk.data_ptr(),
-                     da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr(), ray_map.data_ptr())
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            for b in sets:
+                orig("nunerf_composite_fwd", b["a_in"].data_ptr(), b["c_in"].data_ptr(), b["a_out"].data_ptr(),
+                     b["c_out"].data_ptr(), None, R, S, 1, b["rgb"].data_ptr(), b["raw"].data_ptr(), b["acc"].data_ptr(),
+                     b["bk"].data_ptr(), None, ray_map.data_ptr())     # training form: no dense [R,S] weights output
+            e1.record()
+            for b in sets:
+                orig("nunerf_composite_bwd", b["a_in"].data_ptr(), b["c_in"].data_ptr(), b["a_out"].data_ptr(),
+                     b["c_out"].data_ptr(), None, R, S, 1, b["raw"].data_ptr(), b["d_rgb"].data_ptr(),
+                     b["d_acc"].data_ptr(), b["d_bk"].data_ptr(), b["da_in"].data_ptr(), b["dc_in"].data_ptr(),
+                     b["da_out"].data_ptr(), b["dc_out"].data_ptr(), ray_map.data_ptr())
+            e2.record()
+            fw = bench.hbm_work("nunerf_composite_fwd", (0, 0, 0, 0, 0, R, S))
+            bw = bench.hbm_work("nunerf_composite_bwd", (0, 0, 0, 0, 0, R, S))
+            rec.setdefault("nunerf_composite_fwd", []).append((e0, e1, fw * NSET, NSET))
+            rec.setdefault("nunerf_composite_bwd", []).append((e1, e2, bw * NSET, NSET))
         torch.cuda.synchronize()
     finally:
         eng.call = orig
@@ -109,9 +127,9 @@ def main():
     out = {"rays": R, "hbm_peak_gbs": hbm, "kernels": {}}
     for k, lst in rec.items():
         lst = lst[len(lst) // 3:]                      # drop warm-up launches
-        per_iter = len(lst)
-        ms = sum(e0.elapsed_time(e1) for e0, e1, _ in lst) / per_iter
-        nb = sum(b for *_, b in lst) / per_iter
+        launches = sum(t[3] if len(t) > 3 else 1 for t in lst)
+        ms = sum(t[0].elapsed_time(t[1]) for t in lst) / launches
+        nb = sum(t[2] for t in lst) / launches
         out["kernels"][k] = {"us_per_launch": ms * 1e3, "algorithmic_bytes": nb, "GBs": nb / ms / 1e6,
                              "frac_of_hbm_peak": nb / ms / 1e6 / hbm}
     print(json.dumps(out, indent=1))

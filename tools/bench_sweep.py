@@ -37,7 +37,8 @@ def main():
     # marching cubes on the resident grid: the two kernels alone (HBM: the grid is read once per pass) and the whole call
     from nu_nerf_b200 import sweep as sw
     tri_table, n_tris, edges, edge_axis = sw._mc_tables(u.device)
-    counts = torch.empty(((res - 1) ** 3 + 255) // 256, dtype=torch.int32, device=u.device)
+    from nu_nerf_b200 import _lib
+    counts = torch.empty(int(_lib.lib.nunerf_mc_blocks(res)), dtype=torch.int32, device=u.device)
     call("nunerf_mc_count", u.data_ptr(), res, 0.0, n_tris.data_ptr(), counts.data_ptr())
     torch.cuda.synchronize()
     e0.record()
