@@ -113,8 +113,10 @@ __host__ __device__ __forceinline__ float det_sqrt(float a) {
 }
 // exp(x) for x <= 0 (and moderately positive): Cody-Waite reduction + degree-7 Taylor/Horner, all rounded fp32 ops.
 __host__ __device__ __forceinline__ float det_exp(float x) {
-  if (x < -87.0f) return 0.0f;
-  if (x > 88.0f) x = 88.0f;
+  // branch-free (selects instead of early returns: a warp never runs the polynomial twice); same bits as the early-return
+  // form for every input
+  const bool under = x < -87.0f;
+  x = fminf(fmaxf(x, -87.0f), 88.0f);
   float t = det_mul(x, 1.44269504088896341f);
   float n = (t >= 0.0f) ? (float)(int)(det_add(t, 0.5f)) : (float)(int)(det_sub(t, 0.5f));
   float r = det_sub(x, det_mul(n, 0.693359375f));
@@ -128,16 +130,16 @@ __host__ __device__ __forceinline__ float det_exp(float x) {
   p = det_add(det_mul(p, r), 1.0f);
   p = det_add(det_mul(p, r), 1.0f);
   int e = (int)n + 127;
-  if (e <= 0) return 0.0f;
   union { uint32_t u; float f; } s;
-  s.u = (uint32_t)e << 23;
-  return det_mul(p, s.f);
+  s.u = (uint32_t)(e > 0 ? e : 0) << 23;
+  const float v = det_mul(p, s.f);
+  return (under || e <= 0) ? 0.0f : v;
 }
 __host__ __device__ __forceinline__ float det_sigmoid(float x) {
-  // 1/(1+exp(-x)) evaluated on the non-overflowing branch
-  if (x >= 0.0f) return det_div(1.0f, det_add(1.0f, det_exp(-x)));
-  float e = det_exp(x);
-  return det_div(e, det_add(1.0f, e));
+  // 1/(1+exp(-x)) for x >= 0, exp(x)/(1+exp(x)) for x < 0: both need e = exp(-|x|) only, so one evaluation serves a warp
+  // with mixed signs
+  const float e = det_exp(-fabsf(x));
+  return det_div(x >= 0.0f ? 1.0f : e, det_add(1.0f, e));
 }
 
 }  // namespace nunerf

@@ -447,8 +447,9 @@ __device__ __forceinline__ void ray_runs(const RayMapRegs& mp, int S, RayStage& 
   st.nch_co = n_out ? (((3 * mp.out_off) & 3) + 3 * n_out + 3) >> 2 : 0;
 }
 
-// start the chunk loads of a ray into its staging buffers (one commit group)
-__device__ __forceinline__ void issue_ray_loads(const RayMapRegs& mp, int S, int lane, const float* __restrict__ a_in,
+// start the chunk loads of a ray into its staging buffers (one commit group); returns the ray's run lengths / chunk
+// counts packed into one word (n_in | nch_ai << 8 | nch_ci << 16 -- the outer ones follow from S) for decode_ray
+__device__ __forceinline__ unsigned issue_ray_loads(const RayMapRegs& mp, int S, int lane, const float* __restrict__ a_in,
                                                 const float* __restrict__ c_in, const float* __restrict__ a_out,
                                                 const float* __restrict__ c_out, float* sa, float* sc) {
   RayStage st;
@@ -468,13 +469,18 @@ __device__ __forceinline__ void issue_ray_loads(const RayMapRegs& mp, int S, int
       if (t < st.nch_ci + st.nch_co) cp_async16(sc + 4 * t, (t < st.nch_ci ? gi : go) + 4 * t);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  return (unsigned)st.n_in | ((unsigned)st.nch_ai << 8) | ((unsigned)st.nch_ci << 16);
 }
 
 // staged positions of the lane's samples (FULLS: S == 160, every sample of every lane exists)
 template <bool FULLS>
-__device__ __forceinline__ RayStage decode_ray(const RayMapRegs& mp, int S, int lane) {
+__device__ __forceinline__ RayStage decode_ray(const RayMapRegs& mp, unsigned runs, int S, int lane) {
   RayStage st;
-  ray_runs(mp, S, st);
+  st.in_off = mp.in_off; st.out_off = mp.out_off;
+  st.n_in = (int)(runs & 255u); st.n_out = S - st.n_in;
+  st.nch_ai = (int)((runs >> 8) & 255u); st.nch_ci = (int)(runs >> 16);
+  st.nch_ao = st.n_out ? ((mp.out_off & 3) + st.n_out + 3) >> 2 : 0;
+  st.nch_co = st.n_out ? (((3 * mp.out_off) & 3) + 3 * st.n_out + 3) >> 2 : 0;
   const int hi_a = mp.in_off & 3, ho_a = mp.out_off & 3, hi_c = (3 * mp.in_off) & 3, ho_c = (3 * mp.out_off) & 3;
   // the lane's 5 mask bits and the number of inner samples in front of them
   const int b0 = SPL * lane, w = b0 >> 5, sh = b0 & 31;
@@ -520,7 +526,7 @@ __device__ __forceinline__ void unstage_chunk(float* __restrict__ g, int lo, int
 // Both kernels are persistent: a warp walks over rays r = w, w + W, ... with two staging buffers -- the map of ray i+2
 // is requested and the chunk loads of ray i+1 are in flight while ray i is computed, so neither the map's nor the data's
 // memory latency is exposed.
-template <bool FULLS>
+template <bool FULLS, bool WEIGHTS>
 __global__ void __launch_bounds__(32 * CW, 4) composite_fwd_staged_kernel(
     const float* __restrict__ a_in, const float* __restrict__ c_in, const float* __restrict__ a_out,
     const float* __restrict__ c_out, const int32_t* __restrict__ ray_map, int R, int S, int is_nerf, float* rgb,
@@ -532,14 +538,14 @@ __global__ void __launch_bounds__(32 * CW, 4) composite_fwd_staged_kernel(
   int r = blockIdx.x * CW + wid;
   if (r >= R) return;
   RayMapRegs cur = load_ray_map(ray_map, r);
-  issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[0][wid], s_c[0][wid]);
+  unsigned cur_runs = issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[0][wid], s_c[0][wid]);
   RayMapRegs nxt = load_ray_map(ray_map, min(r + stride, R - 1));
   for (int buf = 0; r < R; r += stride, buf ^= 1) {
     float* sa = s_a[buf][wid];
     float* sc = s_c[buf][wid];
     cp_async_wait_all();
     __syncwarp();
-    const RayStage st = decode_ray<FULLS>(cur, S, lane);
+    const RayStage st = decode_ray<FULLS>(cur, cur_runs, S, lane);
     float a[SPL], ab[SPL], c0[SPL], c1[SPL], c2[SPL];
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(32 * CW, 4) composite_fwd_staged_kernel(
     // next ray: its map arrived during the previous iteration; start its loads, request the map after it
     cur = nxt;
     if (r + stride < R) {
-      issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[buf ^ 1][wid], s_c[buf ^ 1][wid]);
+      cur_runs = issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[buf ^ 1][wid], s_c[buf ^ 1][wid]);
       nxt = load_ray_map(ray_map, min(r + 2 * stride, R - 1));
     }
     // transmittance: local exclusive products, one warp scan of the lane totals per composite
@@ -572,29 +578,25 @@ __global__ void __launch_bounds__(32 * CW, 4) composite_fwd_staged_kernel(
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const float w = a[j] * (ex * p[j]), wb = ab[j] * (exb * pb[j]);
-      if (weights && ((st.valid >> j) & 1u)) weights[(long long)r * S + SPL * lane + j] = w;
+      if (WEIGHTS && ((st.valid >> j) & 1u)) weights[(long long)r * S + SPL * lane + j] = w;
       v[0] += w * c0[j]; v[1] += w * c1[j]; v[2] += w * c2[j]; v[3] += w;
       v[4] += wb * c0[j]; v[5] += wb * c1[j]; v[6] += wb * c2[j];
     }
     const float tsum = warp_sum8(v, lane);
     const float sacc = __shfl_sync(FULL, tsum, 12);
-    if ((lane & 3) == 0) {
-      const int q = lane >> 2;
-      if (q < 3) {
-        const float x = tsum + (is_nerf ? 1.0f - sacc : 0.f);
-        rgb_raw[3 * r + q] = x;
-        rgb[3 * r + q] = fminf(fmaxf(x, 0.f), 1.f);
-      } else if (q == 3) {
-        acc[r] = tsum;
-      } else if (q < 7) {
-        rgb_b[3 * r + q - 4] = tsum;
-      }
+    // value q = lane >> 2: 0..2 rgb, 3 acc, 4..6 bkgr; lane 4q writes it (lanes 4q+1 of the rgb values write the clamped copy)
+    {
+      const int q = lane >> 2, sub = lane & 3;
+      const float x = tsum + ((is_nerf && q < 3) ? 1.0f - sacc : 0.f);
+      float* dst = q < 3 ? (sub == 0 ? rgb_raw : rgb) + 3 * r + q : (q == 3 ? acc + r : rgb_b + 3 * r + (q - 4));
+      const bool wr = q < 3 ? sub < 2 : (q < 7 && sub == 0);
+      if (wr) *dst = (q < 3 && sub == 1) ? fminf(fmaxf(x, 0.f), 1.f) : x;
     }
   }
 }
 
 template <bool FULLS>
-__global__ void __launch_bounds__(32 * CW, 3) composite_bwd_staged_kernel(
+__global__ void __launch_bounds__(32 * CW, 2) composite_bwd_staged_kernel(
     const float* __restrict__ a_in, const float* __restrict__ c_in, const float* __restrict__ a_out,
     const float* __restrict__ c_out, const int32_t* __restrict__ ray_map, int R, int S, int is_nerf,
     const float* __restrict__ rgb_raw, const float* __restrict__ d_rgb, const float* __restrict__ d_acc,
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(32 * CW, 3) composite_bwd_staged_kernel(
   int r = blockIdx.x * CW + wid;
   if (r >= R) return;
   RayMapRegs cur = load_ray_map(ray_map, r);
-  issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[0][wid], s_c[0][wid]);
+  unsigned cur_runs = issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[0][wid], s_c[0][wid]);
   RayMapRegs nxt = load_ray_map(ray_map, min(r + stride, R - 1));
   for (int buf = 0; r < R; r += stride, buf ^= 1) {
     float* sa = s_a[buf][wid];
@@ -622,7 +624,7 @@ __global__ void __launch_bounds__(32 * CW, 3) composite_bwd_staged_kernel(
                 h2 = d_rgb_b ? d_rgb_b[3 * r + 2] : 0.f;
     cp_async_wait_all();
     __syncwarp();
-    const RayStage st = decode_ray<FULLS>(cur, S, lane);
+    const RayStage st = decode_ray<FULLS>(cur, cur_runs, S, lane);
     float a[SPL], gk[SPL], gkb[SPL], vv[SPL];
     float p[SPL], pb[SPL], tot = 1.f, totb = 1.f;
     const float v_in = 1.0f - 0.f + 1e-7f;        // 1 - alpha * outer_mask + 1e-7 of an inner sample in the bkgr composite
@@ -640,7 +642,7 @@ __global__ void __launch_bounds__(32 * CW, 3) composite_bwd_staged_kernel(
     // next ray: start its loads into the other buffer, request the map after it
     cur = nxt;
     if (r + stride < R) {
-      issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[buf ^ 1][wid], s_c[buf ^ 1][wid]);
+      cur_runs = issue_ray_loads(cur, S, lane, a_in, c_in, a_out, c_out, s_a[buf ^ 1][wid], s_c[buf ^ 1][wid]);
       nxt = load_ray_map(ray_map, min(r + 2 * stride, R - 1));
     }
     const float incl = scan_mul32(tot, lane), inclb = scan_mul32(totb, lane);
@@ -805,8 +807,8 @@ extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in
                  "composite_fwd: bad arguments");
   const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out) & 15) == 0;
   if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
-    (S == 32 * SPL ? composite_fwd_staged_kernel<true> : composite_fwd_staged_kernel<false>)<<<staged_grid(R, 4), 32 * CW, 0,
-                                                                                             (cudaStream_t)stream>>>(
+    (S == 32 * SPL ? (weights ? composite_fwd_staged_kernel<true, true> : composite_fwd_staged_kernel<true, false>)
+                   : composite_fwd_staged_kernel<false, true>)<<<staged_grid(R, 4), 32 * CW, 0, (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   else if (S <= 160)
     composite_fwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(
@@ -829,7 +831,7 @@ extern "C" int nunerf_composite_bwd(const float* alpha_in, const float* color_in
   const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out |
                          (uintptr_t)d_alpha_in | (uintptr_t)d_color_in | (uintptr_t)d_alpha_out | (uintptr_t)d_color_out) & 15) == 0;
   if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
-    (S == 32 * SPL ? composite_bwd_staged_kernel<true> : composite_bwd_staged_kernel<false>)<<<staged_grid(R, 3), 32 * CW, 0,
+    (S == 32 * SPL ? composite_bwd_staged_kernel<true> : composite_bwd_staged_kernel<false>)<<<staged_grid(R, 2), 32 * CW, 0,
                                                                                              (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb_raw, d_rgb, d_acc, d_rgb_bkgr, d_alpha_in,
         d_color_in, d_alpha_out, d_color_out);
