@@ -59,7 +59,7 @@ def main():
         loss.backward()
         opt.step()
         return loss
-    ms_train = timeit(train_step, iters=5, warm=3)
+    ms_train = timeit(train_step, iters=10, warm=6)      # the caching allocator needs a few steps to settle
     print(json.dumps({
         "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
                     f"{R} rays, bf16 mode",
