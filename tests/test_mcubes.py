@@ -107,6 +107,26 @@ def test_marching_cubes_sphere_128_properties():
 
 
 @pytest.mark.gpu
+def test_marching_cubes_rows_longer_than_one_block():
+    """res - 1 > 256: a cell row spans two z-chunks of a block (running offsets across chunks and rows); off-centre
+    ellipsoid so that the surface crosses the chunk boundary obliquely."""
+    from nu_nerf_b200.sweep import marching_cubes
+    n = 300
+    g = torch.linspace(-1, 1, n, device="cuda")
+    X, Y, Z = torch.meshgrid(g, g, g, indexing="ij")
+    u = torch.sqrt(((X - 0.1) / 0.7) ** 2 + ((Y + 0.05) / 0.5) ** 2 + ((Z - 0.2) / 0.6) ** 2) - 1.0
+    v, t = marching_cubes(u.contiguous(), 0.0)
+    V, E, F, boundary, nonmanifold, inconsistent = mco.mesh_stats(t)
+    assert (boundary, nonmanifold, inconsistent) == (0, 0, 0) and V - E + F == 2 and V == len(v)
+    # every vertex sits on a grid edge (two integer coordinates) and on the linearly interpolated surface
+    frac = np.abs(v - np.round(v))
+    assert ((frac > 1e-6).sum(axis=1) <= 1).all()
+    w = v / (n - 1) * 2 - 1
+    f = np.sqrt(((w[:, 0] - 0.1) / 0.7) ** 2 + ((w[:, 1] + 0.05) / 0.5) ** 2 + ((w[:, 2] - 0.2) / 0.6) ** 2) - 1.0
+    assert np.abs(f).max() < 2e-4
+
+
+@pytest.mark.gpu
 def test_extract_geometry_of_the_initial_field():
     """extract_geometry (field.py:1310-1319) end to end on the geometric-init field (an approximate sphere, radius 0.5)."""
     from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
