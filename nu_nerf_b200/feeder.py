@@ -97,3 +97,24 @@ class DeviceRayFeeder:
         if "dirs" in out:
             out["rays_o"], out["rays_d"] = world_rays(out.pop("dirs"), out["idxs"], self.poses)
         return out
+
+
+def image_eval_source(imgs, Ks, poses, is_nerf=True, depths=None, masks=None):
+    """Eval source for `renderer.set_eval_source` from image tensors (test_step, ZT:397-411): imgs [imn,3,h,w] at the
+    evaluation resolution, Ks [imn,3,3], poses [imn,3,4] (camera-to-world for is_nerf datasets, world-to-camera
+    otherwise), optional depths / masks [imn,h,w].  Returns fn(index) -> the rays and ground truth of that view."""
+    def fn(index):
+        sl = slice(index, index + 1)
+        if is_nerf:
+            batch, rn, h, w = construct_nerf_ray_batch(imgs[sl], Ks[sl], poses[sl])
+            rays_o, rays_d = batch["rays_o"], batch["rays_d"]
+        else:
+            batch, rn, h, w = construct_ray_batch(imgs[sl], Ks[sl])
+            rays_o, rays_d = world_rays(batch["dirs"], batch["idxs"], poses[sl].to(imgs.device))
+        out = {"rays_o": rays_o, "rays_d": rays_d, "rgbs": batch["rgbs"], "h": h, "w": w}
+        if depths is not None:
+            out["gt_depth"] = depths[index]
+        if masks is not None:
+            out["gt_mask"] = masks[index].to(torch.int32)
+        return out
+    return fn

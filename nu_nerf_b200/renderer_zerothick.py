@@ -160,6 +160,7 @@ class NeROShapeRenderer(nn.Module):
         self.infinity_far_bkgr = InfOutNetwork()
         self.sdf_network._query = self._sdf_query
         self.ray_source = None       # callable(step, n) -> dict(rays_o, rays_d, rgbs) ; replaces the image database
+        self.eval_source = None      # callable(index) -> rays + ground truth of one test view (see set_eval_source)
         if training:
             self._init_dataset()
 
@@ -173,6 +174,12 @@ class NeROShapeRenderer(nn.Module):
         self.ray_source = fn
 
     # ------------------------------------------------------------------ helpers identical to the reference
+    def set_eval_source(self, fn):
+        """fn(index) -> {'rays_o' [h*w,3], 'rays_d' [h*w,3], 'rgbs' [h*w,3], 'h', 'w'[, 'gt_depth' [h,w], 'gt_mask' [h,w]]}:
+        the rays and ground truth of test view `index`, already at the evaluation resolution (what ZT:398-411 reads from the
+        image database and down-samples; `nu_nerf_b200.feeder.image_eval_source` builds it from image tensors)."""
+        self.eval_source = fn
+
     def get_anneal_val(self, step):
         if self.cfg["anneal_end"] < 0:
             return 1.0
@@ -504,11 +511,46 @@ class NeROShapeRenderer(nn.Module):
         outputs["loss_rgb"] = self.compute_rgb_loss(outputs["ray_rgb"], batch["rgbs"])
         return outputs
 
+    # ------------------------------------------------------------------ ZT:397-445
+    TEST_KEYS = ("ray_rgb", "gradient_error", "normal", "depth", "diffuse_albedo", "diffuse_light", "diffuse_color",
+                 "refraction_light", "specular_albedo", "specular_light", "specular_color", "specular_ref",
+                 "transmission_weight", "roughness", "occ_prob", "indirect_light", "occ_prob_gt")
+
+    def test_step(self, index, step):
+        """One test view in chunks of cfg['test_ray_num'] rays through render(..., perturb 0, anneal 0, is_train=False);
+        same output keys and shapes as the reference (ray_rgb / gt_rgb [h,w,3], the buffers [h*w, .], loss_rgb [h*w])."""
+        if self.eval_source is None:
+            raise RuntimeError("no eval source attached: call set_eval_source(fn) (the image database is outside the hot path)")
+        src = self.eval_source(index)
+        rays_o, rays_d = src["rays_o"].float(), F.normalize(src["rays_d"].float(), dim=-1)
+        h, w = int(src["h"]), int(src["w"])
+        rn, trn = rays_o.shape[0], self.cfg["test_ray_num"]
+        outputs = {k: [] for k in self.TEST_KEYS}
+        with torch.no_grad():
+            for ri in range(0, rn, trn):
+                o, d = rays_o[ri:ri + trn].contiguous(), rays_d[ri:ri + trn].contiguous()
+                if self.is_nerf:                                            # _process_nerf_ray_batch ZT:363-374
+                    near = torch.full((o.shape[0], 1), 0.8, device=o.device)
+                    far = torch.full((o.shape[0], 1), 4.5, device=o.device)
+                else:
+                    near, far = self.near_far_from_sphere(o, d)
+                cur = self.render(o, d, near, far, None, 0, 0, is_train=False, step=step, is_nerf=self.is_nerf)
+                for k in self.TEST_KEYS:
+                    outputs[k].append(cur[k].detach())
+        outputs = {k: torch.cat(v, 0) for k, v in outputs.items()}
+        outputs["loss_rgb"] = self.compute_rgb_loss(outputs["ray_rgb"], src["rgbs"])
+        outputs["gt_rgb"] = src["rgbs"].reshape(h, w, 3)
+        outputs["ray_rgb"] = outputs["ray_rgb"].reshape(h, w, 3)
+        for k in ("gt_depth", "gt_mask"):                                   # used by the evaluation metrics (metrics.py:55-84)
+            if k in src:
+                outputs[k] = torch.as_tensor(src[k]).unsqueeze(-1)
+        self.zero_grad()
+        return outputs
+
     def forward(self, data):
         step = data["step"]
         if "eval" in data:
-            raise NotImplementedError("test_step needs the image database (dataset ingest is outside the hot path); "
-                                      "use render(..., is_train=False) on rays")
+            return self.test_step(data["index"], step)
         out = self.train_step(step)
         out.pop("_weights", None)
         return out

@@ -647,3 +647,37 @@ def test_occlusion_probe_kernel_matches_torch_glue_and_oracle():
     assert (a - b).abs().max().item() < 2e-3, (a - b).abs().max().item()
     assert (a.cpu() - ref).abs().max().item() < 5e-3
     assert 0.05 < ref.mean().item() < 0.95            # the probe set mixes hits and misses
+
+
+def test_forward_eval_is_test_step():
+    """forward({'eval': ..., 'index': i, 'step': s}) -> test_step (ZT:397-445): one test view in chunks of test_ray_num,
+    reference output keys / shapes, equal to rendering the same rays directly."""
+    from nu_nerf_b200 import feeder
+    net = _renderer("bf16")
+    net.cfg["test_ray_num"] = 100                       # ragged chunks over the 12 x 16 view
+    h, w = 12, 16
+    g = torch.Generator().manual_seed(9)
+    imgs = torch.rand(2, 3, h, w, generator=g).to(DEV)
+    K = torch.tensor([[30.0, 0, 8.0], [0, 30.0, 6.0], [0, 0, 1]])[None].repeat(2, 1, 1).to(DEV)
+    c2w = torch.eye(3, 4)[None].repeat(2, 1, 1)         # OpenGL camera at z = +3 / +2.5 looking down -z
+    c2w[0, 2, 3], c2w[1, 2, 3] = 3.0, 2.5
+    depth = torch.rand(2, h, w, generator=g)
+    mask = torch.rand(2, h, w, generator=g) > 0.5
+    net.set_eval_source(feeder.image_eval_source(imgs, K, c2w.to(DEV), is_nerf=True, depths=depth, masks=mask))
+    net.is_nerf = True
+    out = net({"eval": True, "index": 1, "step": 20000})
+    rn = h * w
+    assert out["ray_rgb"].shape == (h, w, 3) and out["gt_rgb"].shape == (h, w, 3) and out["loss_rgb"].shape[0] == rn
+    assert out["gt_depth"].shape == (h, w, 1) and out["gt_mask"].shape == (h, w, 1) and out["gt_mask"].dtype == torch.int32
+    assert torch.equal(out["gt_rgb"], imgs[1].permute(1, 2, 0))
+    for k in net.TEST_KEYS:
+        assert k in out and torch.isfinite(out[k]).all(), k
+        assert k == "gradient_error" or out[k].shape[0] in (rn, h), k      # gradient_error: one value per inner sample
+    src = net.eval_source(1)
+    o, d = src["rays_o"].contiguous(), torch.nn.functional.normalize(src["rays_d"], dim=-1).contiguous()
+    near, far = torch.full((rn, 1), 0.8, device=DEV), torch.full((rn, 1), 4.5, device=DEV)
+    with torch.no_grad():
+        ref = net.render(o, d, near, far, None, 0, 0, is_train=False, step=20000, is_nerf=True)
+    assert torch.equal(out["ray_rgb"].reshape(rn, 3), ref["ray_rgb"])           # rays are independent of the chunking
+    assert torch.equal(out["depth"], ref["depth"]) and torch.equal(out["normal"], ref["normal"])
+    assert out["ray_rgb"][6, 8].sum().item() != out["ray_rgb"][0, 0].sum().item()
