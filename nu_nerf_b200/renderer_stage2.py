@@ -436,9 +436,46 @@ class Stage2Renderer(nn.Module):
             colors.append(out["ray_rgb"])
         return torch.cat(colors, 0).reshape(h, w, 3).cpu().numpy()
 
+    # ------------------------------------------------------------------ ZT:1209-1257
+    TEST_KEYS = ("ray_rgb", "gradient_error", "normal", "tir_mask", "specular_light", "specular_color", "specular_ref")
+
+    def set_eval_source(self, fn):
+        """fn(index) -> {'rays_o', 'rays_d', 'rgbs' [h*w,3], 'h', 'w'[, 'gt_depth', 'gt_mask']} (see
+        NeROShapeRenderer.set_eval_source / feeder.image_eval_source)."""
+        self.eval_source = fn
+
+    def test_step(self, index, step):
+        """One test view through the refraction path in chunks of cfg['test_ray_num'] rays; ray_rgb / gt_rgb are masked by
+        the total-internal-reflection mask like the reference's (ZT:1247-1249)."""
+        if getattr(self, "eval_source", None) is None:
+            raise RuntimeError("no eval source attached: call set_eval_source(fn) (the image database is outside the hot path)")
+        src = self.eval_source(index)
+        rays_o, rays_d = src["rays_o"].float(), F.normalize(src["rays_d"].float(), dim=-1)
+        h, w = int(src["h"]), int(src["w"])
+        rn, trn = rays_o.shape[0], self.cfg["test_ray_num"]
+        outputs = {k: [] for k in self.TEST_KEYS}
+        with torch.no_grad():
+            for ri in range(0, rn, trn):
+                cur = self.render(rays_o[ri:ri + trn].contiguous(), rays_d[ri:ri + trn].contiguous(), None, None, None, 0, 0,
+                                  is_train=False, step=step, is_nerf=self.is_nerf)
+                for k in self.TEST_KEYS:
+                    outputs[k].append(cur[k].detach())
+        outputs = {k: torch.cat(v, 0) for k, v in outputs.items()}
+        tm = outputs["tir_mask"]
+        outputs["loss_rgb"] = self.compute_rgb_loss(outputs["ray_rgb"] * tm, src["rgbs"] * tm)
+        outputs["gt_rgb"] = (src["rgbs"] * tm).reshape(h, w, 3)
+        outputs["ray_rgb"] = (outputs["ray_rgb"] * tm).reshape(h, w, 3)
+        for k in ("gt_depth", "gt_mask"):
+            if k in src:
+                outputs[k] = torch.as_tensor(src[k]).unsqueeze(-1)
+        self.zero_grad()
+        return outputs
+
     def forward(self, data):
         step = data["step"]
-        if "eval" in data or self.ray_source is None:
+        if "eval" in data:
+            return self.test_step(data["index"], step)
+        if self.ray_source is None:
             raise NotImplementedError("dataset ingest is outside the hot path: attach a ray source and call render()")
         batch = self.ray_source(step, self.cfg["train_ray_num"])
         rays_d = F.normalize(batch["rays_d"], dim=-1)

@@ -223,3 +223,34 @@ def test_edge_cases_all_rays_miss_and_single_ray(net):
         loss.backward()
         g = net.stage1_network.outer_nerf.pts_linears[0].weight.grad
         assert g is not None and torch.isfinite(g).all(), name
+
+
+def test_forward_eval_is_test_step(net):
+    """Stage2Renderer.forward({'eval', 'index', 'step'}) -> test_step (ZT:1209-1257): reference keys, ray_rgb / gt_rgb
+    masked by tir_mask, equal to rendering the view's rays directly."""
+    from nu_nerf_b200 import feeder
+    h, w = 6, 10
+    g = torch.Generator().manual_seed(2)
+    imgs = torch.rand(1, 3, h, w, generator=g).to(DEV)
+    K = torch.tensor([[20.0, 0, 5.0], [0, 20.0, 3.0], [0, 0, 1]])[None].to(DEV)
+    c2w = torch.eye(3, 4)[None].clone()
+    c2w[0, 2, 3] = 3.0                                        # OpenGL camera at z = +3 looking down -z
+    net.set_eval_source(feeder.image_eval_source(imgs, K, c2w.to(DEV), is_nerf=True))
+    old = net.cfg["test_ray_num"]
+    net.cfg["test_ray_num"] = 25
+    try:
+        out = net({"eval": True, "index": 0, "step": 10000})
+    finally:
+        net.cfg["test_ray_num"] = old
+    rn = h * w
+    assert out["ray_rgb"].shape == (h, w, 3) and out["gt_rgb"].shape == (h, w, 3) and out["loss_rgb"].shape == (rn,)
+    assert out["tir_mask"].shape == (rn, 1) and out["tir_mask"].dtype == torch.bool
+    for k in net.TEST_KEYS:
+        assert torch.isfinite(out[k].float()).all(), k
+    src = net.eval_source(0)
+    with torch.no_grad():
+        ref = net.render(src["rays_o"].contiguous(), torch.nn.functional.normalize(src["rays_d"], dim=-1).contiguous(), None,
+                         None, None, 0, 0, is_train=False, step=10000, is_nerf=net.is_nerf)
+    assert torch.equal(out["tir_mask"], ref["tir_mask"])
+    assert (out["ray_rgb"].reshape(rn, 3) - ref["ray_rgb"] * ref["tir_mask"]).abs().max().item() < 1e-5
+    assert torch.equal(out["gt_rgb"].reshape(rn, 3), imgs[0].permute(1, 2, 0).reshape(rn, 3) * ref["tir_mask"])
