@@ -88,7 +88,8 @@ def warm_up_cos_lr(step, lr=5e-4, warm=5000, end=300000, alpha=0.05):
 
 def global_count(n_local, device, group=None):
     """Sum of a per-rank integer count over the group (one scalar all-reduce)."""
-    t = torch.tensor([float(n_local)], device=device)
+    # torch.full is a fill kernel: no pageable host->device copy (which would stall the host until the stream drains)
+    t = torch.full((1,), float(n_local), device=device)
     _, world = world_info(group)
     if world > 1:
         dist.all_reduce(t, group=group)

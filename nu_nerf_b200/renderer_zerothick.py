@@ -333,8 +333,9 @@ class NeROShapeRenderer(nn.Module):
             valid = vals < 1.5
             # padding slots probe a harmless ray from the origin (their weight in the mean is zero)
             pts_sel = torch.where(valid[:, None], points[idx], torch.zeros(1, 3, device=dev))
-            dirs_sel = torch.where(valid[:, None], reflective[idx].detach(),
-                                   torch.tensor([[1.0, 0.0, 0.0]], device=dev)).contiguous()
+            e_x = torch.eye(1, 3, device=dev)                    # [[1, 0, 0]] built on the device: a host->device copy
+                                                                 # (torch.tensor / item assignment) would drain the stream
+            dirs_sel = torch.where(valid[:, None], reflective[idx].detach(), e_x).contiguous()
             w = prepared if prepared is not None else self._prepare()
             occ_gt = self.occ_probability(pts_sel.contiguous(), dirs_sel, w)
             diff = (occ_prob[idx] - occ_gt).abs() * valid[:, None]
