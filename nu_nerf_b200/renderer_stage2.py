@@ -235,6 +235,7 @@ class Stage2Renderer(nn.Module):
         next_start, next_dir = o, d
         starts, directions = [o], [d]
         intersections, converges, infinity_bkgr, ior_ratios, gradient_mesh, tirs = [], [], [], [], [], []
+        hit_idxs, conv_idxs = [], []
         inside = False
         for i in range(3):
             N = next_start.shape[0]
@@ -242,19 +243,22 @@ class Stage2Renderer(nn.Module):
             if trace is not None:
                 trace[f"trace_hit_{i}"], trace[f"trace_tri_{i}"] = hit.float(), info["faces_ind"]
             converged = hit.reshape(-1, 1)
-            x_c = info["x"][hit].contiguous()
-            n_c = F.normalize(info["n"][hit], dim=-1)
+            # index tensors instead of boolean-mask indexing: ONE host sync (nonzero) per mask instead of one per use
+            hit_idx = hit.nonzero().squeeze(1)
+            x_c = info["x"][hit_idx].contiguous()
+            n_raw = info["n"][hit_idx].contiguous()
+            n_c = F.normalize(n_raw, dim=-1)
             if inside:
                 n_c = -n_c
-            d_c = next_dir[hit].contiguous()
+            d_c = next_dir[hit_idx].contiguous()
             infinity_bkgr.append(~converged)
             M = x_c.shape[0]
             if M > 0:
                 eta = 1.0 / (eng.ior_forward(wior, x_c) + 1.0)                 # ZT:1642-1643
                 d_out, o_out = torch.empty(M, 3, device=dev), torch.empty(M, 3, device=dev)
                 ok = torch.empty(M, dtype=torch.uint8, device=dev)
-                tri_c = info["faces_ind"][hit].contiguous()
-                eng.call("nunerf_refract_bounce", x_c.data_ptr(), info["n"][hit].contiguous().data_ptr(),
+                tri_c = info["faces_ind"][hit_idx].contiguous()
+                eng.call("nunerf_refract_bounce", x_c.data_ptr(), n_raw.data_ptr(),
                          d_c.data_ptr(), eta.contiguous().data_ptr(), tri_c.data_ptr(), M, int(inside),
                          d_out.data_ptr(), o_out.data_ptr(), ok.data_ptr())
                 ok = ok.bool()
@@ -263,49 +267,54 @@ class Stage2Renderer(nn.Module):
                 d_out = o_out = torch.zeros(0, 3, device=dev)
                 ok = torch.zeros(0, dtype=torch.bool, device=dev)
                 ratio = torch.zeros(0, 1, device=dev)
+            ok_idx = ok.nonzero().squeeze(1)
             converged_out = converged.clone()
-            converged_out[hit] = ok.reshape(-1, 1)
+            converged_out[hit_idx] = ok.reshape(-1, 1)
             tir = torch.ones(N, 1, dtype=torch.bool, device=dev)
-            tir[hit] = ok.reshape(-1, 1)
+            tir[hit_idx] = ok.reshape(-1, 1)
             tirs.append(tir)
-            next_dir, next_start = d_out[ok].contiguous(), o_out[ok].contiguous()
+            next_dir, next_start = d_out[ok_idx].contiguous(), o_out[ok_idx].contiguous()
             directions.append(next_dir)
             starts.append(next_start)
             converges.append(converged_out)
             intersections.append(x_c)
-            if not bool(converged_out.any()):
+            hit_idxs.append(hit_idx)
+            conv_idxs.append(hit_idx[ok_idx])                 # rays of this segment that continue into the next one
+            if ok_idx.numel() == 0:
                 break
-            gradient_mesh.append(n_c[ok])
-            ior_ratios.append(ratio[ok])
+            gradient_mesh.append(n_c[ok_idx])
+            ior_ratios.append(ratio[ok_idx])
             inside = not inside
         for i in range(len(tirs) - 1, 0, -1):
-            m = converges[i - 1].flatten()
+            m = conv_idxs[i - 1]
             tirs[i - 1][m] = tirs[i - 1][m] & tirs[i]
         # ---- per-segment sample generation (ZT:1719-1813)
         pathes = []
         for k in range(len(converges)):
             start, dk = starts[k], directions[k]
-            bk = infinity_bkgr[k].flatten()
+            h_idx = hit_idxs[k]                                   # rays of the segment that hit the mesh (~bk)
+            n_hit, n_seg = h_idx.numel(), start.shape[0]
             end = start + dk * 4.5
-            if bool((~bk).any()):
-                end[~bk] = intersections[k]
+            if n_hit > 0:
+                end[h_idx] = intersections[k]
             n_pts = 256 if k != 1 else 128
             lin = torch.linspace(0, 1, n_pts, device=dev)
             pts = eng.segment_points(start, end - start, lin.unsqueeze(0).expand(start.shape[0], n_pts).contiguous())
-            if k == 1 and bool((~bk).any()):
+            if k == 1 and n_hit > 0:
                 # inside the outer mesh: 64 uniform samples to the hit, 2 rounds of SDF-guided up-sampling with 32 new
                 # samples each on the inner field; z is the unit parameter of the segment while the SDF is queried at
                 # start + dir * z -- the reference's mixed parametrisation, reproduced as written (ZT:1742-1760)
-                s_h, e_h, d_h = start[~bk].contiguous(), end[~bk].contiguous(), dk[~bk].contiguous()
+                s_h, e_h, d_h = start[h_idx].contiguous(), end[h_idx].contiguous(), dk[h_idx].contiguous()
                 Rh = s_h.shape[0]
                 z = torch.linspace(0, 1, 64, device=dev).unsqueeze(0).expand(Rh, 64).contiguous()
                 p64 = eng.segment_points(s_h, e_h - s_h, z)
                 sdf = eng.sdf_infer(wi.sdf, p64.reshape(-1, 3), wi.planes).reshape(Rh, 64).contiguous()
                 z = eng.upsample_rounds(wi, s_h, d_h, z, sdf, n_new=32, rounds=2)
-                pts[~bk] = eng.segment_points(s_h, e_h - s_h, z)
-            if k != 1 and bool(bk.any()):
+                pts[h_idx] = eng.segment_points(s_h, e_h - s_h, z)
+            if k != 1 and n_hit < n_seg:
                 # rays that leave the scene: 192 samples on [0.1, 64] + 64 NeRF++-guided ones (ZT:1762-1799)
-                s_m, d_m = start[bk].contiguous(), dk[bk].contiguous()
+                m_idx = infinity_bkgr[k].flatten().nonzero().squeeze(1)
+                s_m, d_m = start[m_idx].contiguous(), dk[m_idx].contiguous()
                 Rm = s_m.shape[0]
                 z = torch.linspace(0.1, 64.0, 192, device=dev).unsqueeze(0).expand(Rm, 192).contiguous()
                 p = eng.segment_points(s_m, d_m, z)
@@ -314,7 +323,7 @@ class Stage2Renderer(nn.Module):
                 alpha = eng.nerf_alpha(w1.nerf, p.reshape(-1, 3), d_m.repeat_interleave(192, 0), dists.reshape(-1),
                                        w1.planes).reshape(Rm, 192)
                 z = eng.importance_merge(z, alpha, 64)
-                pts[bk] = eng.segment_points(s_m, d_m, z)
+                pts[m_idx] = eng.segment_points(s_m, d_m, z)
             pathes.append(pts)
         return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
 
@@ -328,7 +337,7 @@ class Stage2Renderer(nn.Module):
         T = torch.ones(R, 3, device=dev)
         normals_out = torch.zeros(R, 3, device=dev)
         spec_color_out, spec_light_out, spec_ref_out = (torch.zeros(R, 3, device=dev) for _ in range(3))
-        colors, tmp = [], {}
+        colors, tmp, conv_idxs = [], {}, []
         exp_max1 = self.stage1_network.color_network.cfg["light_exp_max"]
         exp_maxi = self.color_network_inner.cfg["light_exp_max"]
         p1, p_in = _bank_params(w1), _bank_params(wi)
@@ -337,66 +346,67 @@ class Stage2Renderer(nn.Module):
         for i in range(len(pathes)):
             cand = pathes[i].detach()
             N, S = cand.shape[0], cand.shape[1] - 1
-            conv = converges[i].flatten()
+            conv_idx = converges[i].flatten().nonzero().squeeze(1)        # one host sync per segment for this mask
+            conv_idxs.append(conv_idx)
             dirs_i = directions[i].detach()
             with torch.no_grad():
                 pts, dists, inner = eng.segment_geometry(cand)
-                outer = ~inner
                 dirs_e = dirs_i[:, None, :].expand(N, S, 3)
-            alpha = torch.zeros(N, S, device=dev)
-            color = torch.zeros(N, S, 3, device=dev)
-            if bool(outer.any()):
+                inner_f = inner.reshape(-1)
+                outer_idx = (~inner_f).nonzero().squeeze(1)
+                inner_idx = inner_f.nonzero().squeeze(1) if i == 1 else None
+                pts_f, dists_f = pts.reshape(-1, 3), dists.reshape(-1)
+                ray_of = lambda idx: torch.div(idx, S, rounding_mode="floor")      # sample -> ray (view dir)
+            alpha = torch.zeros(N * S, device=dev)
+            color = torch.zeros(N * S, 3, device=dev)
+            if outer_idx.numel() > 0:
                 # NeRF++ of the STAGE-1 network on the samples outside the unit sphere (ZT:1876-1880)
-                a_o, c_o = _NerfFn.apply((w1, pts[outer].contiguous(), dirs_e[outer].contiguous(),
-                                          dists[outer].contiguous()), *p1)
-                alpha[outer] = a_o
-                color[outer] = c_o
-            if i == 1 and bool(inner.any()):
+                a_o, c_o = _NerfFn.apply((w1, pts_f[outer_idx].contiguous(), dirs_i[ray_of(outer_idx)].contiguous(),
+                                          dists_f[outer_idx].contiguous()), *p1)
+                alpha = alpha.index_put((outer_idx,), a_o)
+                color = color.index_put((outer_idx,), c_o)
+            if i == 1 and inner_idx.numel() > 0:
                 # inner SDF field + inner shading on segment 1 (ZT:1883-1906)
                 inv_s = torch.exp(self.deviation_network_inner.variance * 10.0)
-                a_i, c_i, gerr = _InnerFn.apply((wi, pts[inner].contiguous(), dirs_e[inner].contiguous(),
-                                                 dists[inner].contiguous(), float(cos_anneal_ratio), exp_maxi,
+                a_i, c_i, gerr = _InnerFn.apply((wi, pts_f[inner_idx].contiguous(), dirs_i[ray_of(inner_idx)].contiguous(),
+                                                 dists_f[inner_idx].contiguous(), float(cos_anneal_ratio), exp_maxi,
                                                  not frozen), inv_s, *p_in)
-                alpha[inner] = a_i
-                color[inner] = c_i
+                alpha = alpha.index_put((inner_idx,), a_i)
+                color = color.index_put((inner_idx,), c_i)
                 inv_s_c = inv_s.clip(1e-6, 1e6)
                 tmp["std"] = torch.mean(1.0 / (inv_s_c.detach() if frozen else inv_s_c))
                 tmp["gradient_error"] = gerr
+            alpha, color = alpha.view(N, S), color.view(N, S, 3)
             # linear-space compositing (ZT:1942-1951)
             Tc = torch.cumprod(torch.cat([torch.ones(N, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)
             wts = alpha * Tc[:, :-1]
             color_now = (srgb_to_linear(color) * wts[..., None]).sum(dim=1) * T
             T = T * Tc[:, -1:]
-            n_hit = int(conv.sum())
+            n_hit = conv_idx.numel()
             if n_hit > 0:
-                p_hit = cand[conv][:, -1, :].contiguous()
+                p_hit = cand[conv_idx][:, -1, :].contiguous()
                 holder = {}
                 c_s, trans, nov = _SurfaceFn.apply((w1, p_hit, gradient_mesh[i].detach().contiguous(),
-                                                    dirs_i[conv].contiguous(), exp_max1, holder), *p1)
+                                                    dirs_i[conv_idx].contiguous(), exp_max1, holder), *p1)
                 if i % 2 != 0:
                     c_s = torch.zeros_like(c_s)                    # inside the object: field.py:969
                 tn = torch.clamp(1.0 - nov[:, None], 0.0, 1.0)
                 rw = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)
-                hit_add = torch.zeros_like(color_now)
-                hit_add[conv] = srgb_to_linear(c_s) * T[conv]
-                color_now = color_now + hit_add
+                color_now = color_now.index_add(0, conv_idx, srgb_to_linear(c_s) * T[conv_idx])
                 if i == 0 and not is_train:
                     with torch.no_grad():
                         ex = eng.surface_extras(w1, holder["tape"], exp_max1)
-                        normals_out[conv] = (F.normalize(gradient_mesh[i].reshape(-1, 3), dim=-1) + 1.0) * 0.5
-                        spec_color_out[conv], spec_light_out[conv], spec_ref_out[conv] = \
+                        normals_out[conv_idx] = (F.normalize(gradient_mesh[i].reshape(-1, 3), dim=-1) + 1.0) * 0.5
+                        spec_color_out[conv_idx], spec_light_out[conv_idx], spec_ref_out[conv_idx] = \
                             ex["specular_color"], ex["specular_light"], ex["specular_ref"]
-                T = T[conv] * ((1.0 - rw) * trans[:, None])        # refraction_coefficient, ZT:1966
+                T = T[conv_idx] * ((1.0 - rw) * trans[:, None])        # refraction_coefficient, ZT:1966
                 colors.append(color_now)
             else:
                 colors.append(color_now)
                 break
         total = colors[-1]
         for i in range(len(colors) - 1, 0, -1):
-            m = converges[i - 1].flatten()
-            up = torch.zeros_like(colors[i - 1])
-            up[m] = total
-            total = colors[i - 1] + up
+            total = colors[i - 1].index_add(0, conv_idxs[i - 1], total)
         ray_rgb = torch.clamp(linear_to_srgb(total), min=0.0, max=1.0)
         return {
             "ray_rgb": ray_rgb,
