@@ -95,12 +95,26 @@ class WeightBank:
                 h.dW, h.lddw, h.dw_row_off, h.db = d.dW.data_ptr(), d.Kp, 0, d.db.data_ptr()
 
     def _upload(self):
+        """Descriptor table -> device through one of two pinned staging buffers (asynchronous copy: a pageable copy would
+        stall the host until the stream drains, in the middle of a step)."""
         raw = bytes(self._host)
-        t = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+        if torch.device(self.device).type != "cuda":       # (host-side construction in CPU-only tests)
+            self._descs = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+            return
         if self._descs is None:
-            self._descs = t.to(self.device)
-        else:
-            self._descs.copy_(t)
+            self._descs = torch.empty(len(raw), dtype=torch.uint8, device=self.device)
+            self._pin = [torch.empty(len(raw), dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._pin_ev = [None, None]
+            self._pin_i = 0
+        i = self._pin_i
+        self._pin_i ^= 1
+        if self._pin_ev[i] is not None:
+            self._pin_ev[i].synchronize()                  # the copy that last used this staging buffer has completed
+        self._pin[i].copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+        self._descs.copy_(self._pin[i], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pin_ev[i] = ev
 
     def source_ptrs(self):
         return tuple(d.v.data_ptr() for d in self.denses)
@@ -128,7 +142,14 @@ class WeightBank:
                         missing.append(p)
         if missing:
             sizes = [(p.numel() + 3) // 4 * 4 for p in missing]          # keep every view 16-byte aligned
-            flat = torch.zeros(sum(sizes), dtype=missing[0].dtype, device=missing[0].device)
+            key = tuple(id(p) for p in missing)
+            pool = getattr(self, "_grad_pool", None)
+            if pool is not None and pool[0] == key:
+                flat = pool[1]                                           # same parameters as last time: same storage, so
+                flat.zero_()                                             # the descriptor table needs no new upload
+            else:
+                flat = torch.zeros(sum(sizes), dtype=missing[0].dtype, device=missing[0].device)
+                self._grad_pool = (key, flat)
             off = 0
             for p, n in zip(missing, sizes):
                 p.grad = flat[off:off + p.numel()].view_as(p)
