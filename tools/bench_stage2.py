@@ -13,10 +13,20 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 from conftest import make_stage2, uv_sphere  # noqa: E402
 
 
-def timeit(fn, iters=10, warm=3):
+def timeit(fn, iters=10, warm=3, per_iter=False):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if per_iter:
+        # one event pair per iteration: the training step draws new sample positions every iteration, its list sizes
+        # change, and an iteration that makes the caching allocator call cudaMalloc costs several times a normal one
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return sorted(a.elapsed_time(b) for a, b in ev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -59,7 +69,8 @@ def main():
         loss.backward()
         opt.step()
         return loss
-    ms_train = timeit(train_step, iters=10, warm=6)      # the caching allocator needs a few steps to settle
+    t_train = timeit(train_step, iters=20, warm=6, per_iter=True)
+    ms_train, ms_train_mean = t_train[len(t_train) // 2], sum(t_train) / len(t_train)
     print(json.dumps({
         "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
                     f"{R} rays, bf16 mode",
@@ -68,7 +79,8 @@ def main():
         "trace_plus_reintersection": {"ms": ms_di, "Mrays_per_s": Rt / ms_di / 1e3},
         "ray_trace_with_sampling": {"rays": R, "ms": ms_rt, "rays_per_s": R / ms_rt * 1e3},
         "full_forward": {"rays": R, "ms": ms_full, "rays_per_s": R / ms_full * 1e3},
-        "train_step": {"rays": R, "ms": ms_train, "rays_per_s": R / ms_train * 1e3,
+        "train_step": {"rays": R, "ms": ms_train, "rays_per_s": R / ms_train * 1e3, "ms_mean": ms_train_mean,
+                       "ms_min_max": [t_train[0], t_train[-1]], "timing": "median of 20 per-step CUDA-event timings",
                        "note": "forward + backward w.r.t. all field parameters + Adam; IORs_pred gradient (through the "
                                "path geometry) not included"},
     }))
