@@ -158,6 +158,11 @@ int nunerf_probe_weights(const float* z, const float* sdf, int P, int n, const f
  *   either form.  dists, pts, slot, id_in, id_out may be NULL when not needed.
  * nunerf_composite_fwd/bwd (ZT:773-788): w = a * excl_cumprod(1-a+1e-7); rgb = clamp(sum w c (+1-acc)); acc;
  *   background-only composite.  Backward recomputes the transmittance instead of storing it.
+ *   With the per-ray map, S <= 160 and all list pointers 16-byte aligned the persistent shared-memory-staged kernels
+ *   run (a ray's list runs are fetched as whole 16-byte chunks: reads may touch the <= 3 elements that share a chunk
+ *   with the run -- always inside the same aligned buffer --, writes never leave the run); any other case (slot form,
+ *   S > 160, unaligned views) takes the lane-per-sample kernels.  `weights` (dense [R,S], optional) is only needed by
+ *   the validation outputs; pass NULL in training.  NUNERF_COMPOSITE_LEGACY=1 forces the lane-per-sample kernels.
  */
 int nunerf_render_geometry(const float* o, const float* d, const float* z, int R, int S, float* dists, float* pts,
                            int32_t* slot, int32_t* counts, int32_t* ray_scratch, float* pts_in, float* dists_in,

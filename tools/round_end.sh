@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-end measurement set (run on the GPU box: gpurun -- 'bash tools/round_end.sh r1n').  Everything lands in
+# Round-end measurement set (run on the GPU box: gpurun -- 'bash tools/round_end.sh r1p').  Everything lands in
 # gpurun_out/<tag>_*; numbers are taken WITHOUT a profiler attached, the ncu passes run afterwards on the same commands.
 tag=${1:-rN}
 out=gpurun_out
