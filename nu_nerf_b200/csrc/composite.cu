@@ -808,7 +808,8 @@ extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in
   const bool aligned = (((uintptr_t)alpha_in | (uintptr_t)color_in | (uintptr_t)alpha_out | (uintptr_t)color_out) & 15) == 0;
   if (ray_map && S <= 32 * SPL && aligned && !g_composite_legacy)
     (S == 32 * SPL ? (weights ? composite_fwd_staged_kernel<true, true> : composite_fwd_staged_kernel<true, false>)
-                   : composite_fwd_staged_kernel<false, true>)<<<staged_grid(R, 4), 32 * CW, 0, (cudaStream_t)stream>>>(
+                   : (weights ? composite_fwd_staged_kernel<false, true> : composite_fwd_staged_kernel<false, false>))
+        <<<staged_grid(R, 4), 32 * CW, 0, (cudaStream_t)stream>>>(
         alpha_in, color_in, alpha_out, color_out, ray_map, R, S, is_nerf, rgb, rgb_raw, acc, rgb_bkgr, weights);
   else if (S <= 160)
     composite_fwd_kernel<5><<<cdiv(R, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(

@@ -300,6 +300,13 @@ def test_composite_forward_and_backward(S):
               geo["ray_map"].data_ptr())
     for a_, b_ in ((rgb, rgb2), (raw, raw2), (acc, acc2), (bk, bk2), (w, w2)):
         assert (a_ - b_).abs().max().item() < 2e-6
+    # training form: no dense weights output (NULL) -- same per-ray results, bit for bit
+    rgb3, raw3, acc3, bk3 = torch.zeros_like(rgb), torch.zeros_like(raw), torch.zeros_like(acc), torch.zeros_like(bk)
+    _lib.call("nunerf_composite_fwd", a_in.data_ptr(), c_in.data_ptr(), a_out.data_ptr(), c_out.data_ptr(),
+              None, R, S, 1, rgb3.data_ptr(), raw3.data_ptr(), acc3.data_ptr(), bk3.data_ptr(), None,
+              geo["ray_map"].data_ptr())
+    for a_, b_ in ((rgb2, rgb3), (raw2, raw3), (acc2, acc3), (bk2, bk3)):
+        assert torch.equal(a_, b_)
     # torch fp32 reference (ZT:773-788)
     alpha = torch.zeros(R, S, device=DEV).masked_scatter(inner, a_in).masked_scatter(~inner, a_out)
     color = torch.zeros(R, S, 3, device=DEV).masked_scatter(inner[..., None].expand(-1, -1, 3), c_in) \
