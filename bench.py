@@ -425,7 +425,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "split"])
     ap.add_argument("--step", type=int, default=STEP, help="training step the schedule is evaluated at (SURVEY 8d: 10000; "
                     "20000 adds the occlusion-probe loss, outer_reg and the trainable inv_s)")
-    ap.add_argument("--cpu-rays", type=int, default=128, help="bounded CPU sample (rays per step)")
+    ap.add_argument("--cpu-rays", type=int, default=512, help="bounded CPU sample (rays per step; config 1 of BASELINE.json)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="print a per-entry-point device-time table to stderr")
     args = ap.parse_args()
