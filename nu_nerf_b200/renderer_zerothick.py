@@ -431,8 +431,8 @@ class NeROShapeRenderer(nn.Module):
             outputs = {"depth": depth, "normal": ((F.normalize(t.sdf.grad, dim=-1) + 1.0) * 0.5) * inner}
             eng.shade_forward(w, t, t.sdf.grad)
             occ_gt = torch.zeros(R, 1, device=dev)
-            inside = torch.norm(points, dim=-1) < 0.999
-            if bool(inside.any()):
+            inside = (torch.norm(points, dim=-1) < 0.999).nonzero().squeeze(1)      # one host sync for the mask
+            if inside.numel() > 0:
                 occ_gt[inside] = self.occ_probability(points[inside], t.refl[inside].contiguous(), w, sn0=128, sn1=9)
             outputs["occ_prob_gt"] = occ_gt
             for k, v in eng.shading_buffers(w, t, t.exp_max).items():
