@@ -1,6 +1,14 @@
-import collections, os, sys, time, warnings
+"""Synchronising calls and wall time of one stage-1 eval render (is_train=False: depth, normal, shading buffers,
+occ_prob_gt) of 4096 rays."""
+import collections
+import os
+import sys
+import time
+import warnings
+
 import torch
-sys.path.insert(0, "/root/repo")
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
 from nu_nerf_b200 import synthetic as syn
 cfg = load_default_cfg(); cfg["precision"] = "bf16"
