@@ -74,3 +74,32 @@ def test_product_synthetic_inputs_equal_the_oracles():
     for a, b in zip(syn.synthetic_rays(33) + syn.synthetic_uniforms(33) + (syn.synthetic_targets(33),),
                     orc.synthetic_rays(33) + orc.synthetic_uniforms(33) + (orc.synthetic_targets(33),)):
         assert torch.equal(a, b)
+
+
+def test_image_eval_source_views():
+    """feeder.image_eval_source (the per-view source of test_step, ZT:397-411): the rays of view i are exactly the rows of
+    the all-view ray table that belong to image i, for both dataset conventions."""
+    from nu_nerf_b200 import feeder
+    g = torch.Generator().manual_seed(4)
+    imn, h, w = 3, 5, 7
+    imgs = torch.rand(imn, 3, h, w, generator=g)
+    K = torch.tensor([[20.0, 0, 3.5], [0, 20.0, 2.5], [0, 0, 1]])[None].repeat(imn, 1, 1)
+    poses = torch.cat([torch.linalg.qr(torch.randn(imn, 3, 3, generator=g))[0], torch.randn(imn, 3, 1, generator=g)], -1)
+    depth, mask = torch.rand(imn, h, w, generator=g), torch.rand(imn, h, w, generator=g) > 0.5
+    full, rn, _, _ = feeder.construct_nerf_ray_batch(imgs, K, poses)
+    src = feeder.image_eval_source(imgs, K, poses, is_nerf=True, depths=depth, masks=mask)
+    for i in range(imn):
+        v = src(i)
+        rows = slice(i * h * w, (i + 1) * h * w)
+        assert (v["h"], v["w"]) == (h, w) and v["gt_mask"].dtype == torch.int32
+        assert torch.equal(v["rays_o"], full["rays_o"][rows]) and torch.equal(v["rays_d"], full["rays_d"][rows])
+        assert torch.equal(v["rgbs"], full["rgbs"][rows]) and torch.equal(v["gt_depth"], depth[i])
+    full2, _, _, _ = feeder.construct_ray_batch(imgs, K)
+    src2 = feeder.image_eval_source(imgs, K, poses, is_nerf=False)
+    for i in range(imn):
+        v = src2(i)
+        rows = slice(i * h * w, (i + 1) * h * w)
+        ro, rd = feeder.world_rays(full2["dirs"][rows], full2["idxs"][rows], poses)
+        assert torch.allclose(v["rays_o"], ro, atol=1e-6) and torch.allclose(v["rays_d"], rd, atol=1e-6)
+        assert "gt_depth" not in v
+
