@@ -145,6 +145,7 @@ class WeightBank:
             key = tuple(id(p) for p in missing)
             pool = getattr(self, "_grad_pool", None)
             if pool is not None and pool[0] == key:
+                # (a caller that keeps last step's .grad tensors after zero_grad(set_to_none=True) must clone them)
                 flat = pool[1]                                           # same parameters as last time: same storage, so
                 flat.zero_()                                             # the descriptor table needs no new upload
             else:
