@@ -420,6 +420,11 @@ class Stage2Renderer(nn.Module):
     # ------------------------------------------------------------------ ZT:1442-1466
     def render(self, rays_o, rays_d, near=None, far=None, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,
                is_train=True, step=None, is_nerf=False):
+        if is_train and torch.is_grad_enabled() and not getattr(self, "_warned_ior", False):
+            import warnings
+            warnings.warn("nu_nerf_b200.Stage2Renderer: the path geometry is a constant of the backward pass -- IORs_pred "
+                          "receives no gradient (every other parameter's gradient is complete); see DESIGN.md section 7")
+            self._warned_ior = True
         prepared = self._prepare()
         pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = \
             self.ray_trace(rays_o, rays_d, prepared=prepared)
