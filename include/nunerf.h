@@ -112,6 +112,11 @@ typedef struct {
 } nunerf_mlp_chain_t;
 int nunerf_mlp_chain(const nunerf_mlp_chain_t* p, void* stream);
 
+/* Development aid (tools/mma_probe.py): issue rate of tcgen05.mma on this part.  One thread per CTA issues `iters` groups
+ * of four M128 x N x K16 instructions (mode 0: both operands from shared memory, 1: A from tensor memory) on `b_stages`
+ * rotating weight blocks (dmode: how consecutive instructions rotate over accumulator regions); out[2*cta] = cycles until issued, out[2*cta+1] = cycles until complete. */
+int nunerf_mma_probe(int mode, int N, int iters, int grid, int b_stages, int dmode, long long* out, void* stream);
+
 /* out[n] += sum_m Z[m,n] (hi + lo) -- the bias gradient */
 int nunerf_colsum(const void* Z, int ldz, int z_lo_off, int M, int N, float* out, void* stream);
 /* fp32 [rows, cols] (ld_src) -> the block dst[row_off:+dst_rows, col_off:+dst_cols] of a bf16 plane matrix, zero

@@ -137,6 +137,7 @@ _SIGS = {
     "nunerf_grid_mask": [vp, vp, ci, ci, cf, vp, vp],
     "nunerf_mc_count": [vp, ci, cf, vp, vp, vp],
     "nunerf_mc_emit": [vp, ci, cf, vp, ci, vp, vp, vp, vp, vp, vp, vp],
+    "nunerf_mma_probe": [ci, ci, ci, ci, ci, ci, vp, vp],
 }
 for _name, _args in _SIGS.items():
     _fn = getattr(lib, _name)

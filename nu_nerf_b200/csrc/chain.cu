@@ -18,9 +18,7 @@
 //                      concat at layer 4, 1-row sdf head -- the no-grad SDF queries of sample_ray (ZT:598, :563),
 //                      extract_fields (field.py:1286-1307) and the occlusion probes (field.py:524-554)
 //   nunerf_mlp_chain   generic ReLU / Softplus chains with optional per-layer stores (predictors, NeRF++)
-#include "common.cuh"
-#include "ptx.cuh"
-#include "tma_host.cuh"
+#include "chain_common.cuh"
 
 // timeline stamps inside the MMA / producer loops cost issue slots on a starved warp: compile them in only on demand
 #ifndef NUNERF_CHAIN_TIMELINE_DETAIL
@@ -28,54 +26,6 @@
 #endif
 
 namespace nunerf {
-
-constexpr int CH_BLOCK_BYTES = 128 * 64 * 2;     // one activation K-block: 128 rows x 64 bf16
-constexpr int CH_WROWS = 256;                    // output rows per weight block (128 = half layers: measured slower)
-constexpr int CH_WSTAGE_BYTES = CH_WROWS * 64 * 2;   // one weight block: <= CH_WROWS output rows x 64 bf16 of K
-constexpr int CH_EPI_WARPS = 16;
-constexpr int CH_THREADS = 32 * (2 + CH_EPI_WARPS);
-constexpr int CH_MAXL = NUNERF_CHAIN_MAX_LAYERS;
-
-struct ChainLayer {
-  int N;            // MMA N (multiple of 16, 16..256)
-  int n_real;       // produced columns >= n_real are replaced (zeros, or the PE side block when cat_pe)
-  int kb0, nkb;     // input K-blocks [kb0, kb0 + nkb) of the tile's four activation blocks
-  int act;          // 0 none, 1 relu, 2 softplus(beta = 100)
-  int cat_pe;       // columns [n_real, 256) <- PE-6 columns [0, 256 - n_real) of the point (SDF skip concat)
-  int to_x;         // write the activation back to X blocks 0..3 (a next layer or a TMA store consumes it)
-  int store_chunks; // > 0: TMA-store that many 64-column chunks of the activation through out_map
-  int w_box_bytes;  // bytes of one weight TMA box: 128 B x min(128, N) rows
-  int hot;          // plain 256-wide hidden layer with a specialised epilogue (ch_hot16 KIND 1..3), 0 = generic path
-  const float* bias;
-  // aux epilogues of the SDF network's reverse passes (hot kinds 4..6, plain 256-wide layers without bias):
-  //   4: y = acc . s                      s = 1 - exp(-100 aux1)   (softplus'(z) from the stored activation)
-  //   5: y = acc . s ;  e_out = acc . aux2 . 100 (1 - s)           (reverse-over-reverse glue, field.cu sdf_bwd2_ew)
-  //   6: y = acc . s + aux2
-  const __nv_bfloat16* aux1; int ld_aux1;
-  const __nv_bfloat16* aux2; int ld_aux2;
-  __nv_bfloat16* e_out; int ld_e;
-  int mask_perm;    // hot layers only: mask words in THREAD order -- byte j*8 + c*2 holds the 16 bits of columns
-                    // c*64 + j*16 .. +15 (one 8-byte access per thread and tile instead of four 2-byte ones)
-  uint8_t* mask_out; int ldmask_out;       // optional 1-bit (x > 0) mask, 32 bytes per row
-  const uint8_t* mask_in; int ldmask_in;   // optional 1-bit multiplicative mask
-  float* out32; int ldo32; int n32;        // optional fp32 copy of the first n32 columns
-};
-
-struct ChainParams {
-  CUtensorMap in_map;
-  CUtensorMap w_map[CH_MAXL];
-  CUtensorMap out_map[CH_MAXL];
-  ChainLayer layer[CH_MAXL];
-  int n_layers, M, num_tiles;
-  int in_mode;           // 0: X0 = rows of a bf16 matrix (TMA, into the activation blocks), 1: X0 = PE-6 of pts
-  int in_blocks;         // K-blocks of the TMA input (1..4)
-  int in_release_layer;  // (unused)
-  int w_stages;
-  const float* pts;
-  int dbg_flags;         // timing experiments only (NUNERF_CHAIN_DEBUG): 1 = skip the TMEM load, 2 = skip the smem store,
-                         // 8 = nanosleep in the epilogue, 16 = skip the MMAs, 32 = skip the weight loads, 64 = no bias loads
-  long long* dbg;        // optional timeline buffer (NUNERF_CHAIN_TIMELINE): [2][256] clock64 stamps of CTA 0
-};
 
 // Hot epilogue of a plain 256-wide hidden layer -> bf16 -> shared memory: 16 columns of one row.
 //   KIND 1: bias + Softplus(beta = 100)              (SDF network)
@@ -105,6 +55,24 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
       for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
     }
     ptx::tmem_ld_wait();
+#if NUNERF_PACKED_EPI
+    if (KIND == 1) {
+      // bias + Softplus two lanes per instruction (FADD2 / FMUL2 / FFMA2): the fma pipe bounds this epilogue
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        x[4 * i] = __uint_as_float(v[4 * i]); x[4 * i + 1] = __uint_as_float(v[4 * i + 1]);
+        x[4 * i + 2] = __uint_as_float(v[4 * i + 2]); x[4 * i + 3] = __uint_as_float(v[4 * i + 3]);
+        softplus100_x2(x[4 * i], x[4 * i + 1], b[i].x, b[i].y);
+        softplus100_x2(x[4 * i + 2], x[4 * i + 3], b[i].z, b[i].w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1])), f2_pack(b[i].x, b[i].y)), x[4 * i], x[4 * i + 1]);
+        f2_unpack(f2_add(f2_pack(__uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])), f2_pack(b[i].z, b[i].w)), x[4 * i + 2], x[4 * i + 3]);
+      }
+    }
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       x[4 * i] = __uint_as_float(v[4 * i]) + b[i].x;
@@ -112,9 +80,12 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
       x[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + b[i].z;
       x[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + b[i].w;
     }
+#endif
     if (KIND == 1) {
+#if !NUNERF_PACKED_EPI
 #pragma unroll
       for (int i = 0; i < 16; ++i) x[i] = softplus100(x[i]);
+#endif
     } else {
       uint32_t ob = 0;
 #pragma unroll
@@ -134,12 +105,6 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
   }
   *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
   *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
-}
-
-__device__ __forceinline__ void ch_unpack16(const uint4& a, const uint4& b, float* f) {
-  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { f[2 * i] = bf16lo_to_f(w[i]); f[2 * i + 1] = bf16hi_to_f(w[i]); }
 }
 
 // Aux epilogues (kinds 4..6, see ChainLayer): 16 columns of one row; a0/a1 = the 16 bf16 of aux1, b0/b1 of aux2.
@@ -189,17 +154,6 @@ __device__ __forceinline__ void ch_tma_store_2d(const CUtensorMap* m, const void
 // PE) is written into those same blocks: they are free between the last layer of one pair and the first of the next.
 __device__ __forceinline__ int ch_block(int t, int id) { return t * 4 + id; }
 
-// PE-6 value of column pc (0..38) of [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] (field.py:14-61), rounded to bf16
-// exactly as the tile-input writer does (the SDF skip concat re-creates these columns instead of keeping a copy in
-// shared memory: the 32 KB go to a third weight stage, which the L2 latency of the weight stream needs).
-__device__ __forceinline__ float ch_pe_col(const float* x, int pc) {
-  if (pc < 3) return __bfloat162float(__float2bfloat16_rn(x[pc]));
-  const int t = (pc - 3) / 3, c = (pc - 3) % 3;
-  float sn, co;
-  sincosf(x[c] * (float)(1 << (t >> 1)), &sn, &co);
-  return __bfloat162float(__float2bfloat16_rn((t & 1) ? co : sn));
-}
-
 // PAIR = 1: one CTA per pair of tiles, cta_group::1 MMAs (M = 128).
 // PAIR = 2: clusters of two CTAs, cta_group::2 MMAs (M = 256 = one tile of each CTA): every CTA keeps its own tiles,
 //           accumulators, epilogue warps and activation stores, but holds only HALF of each weight block (N/2 rows) --
@@ -227,12 +181,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
   uint64_t* peer_go = bars + 32;            // [w_stages]  PAIR = 2, leader only: the peer CTA is ready for this K-block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // service warps: the two lowest warp ids, or (role_hi) the two highest -- the issue arbiter serves the highest warp id of
+  // a scheduler first, so the single MMA-issuing thread is no longer starved by the epilogue warps it shares it with
+  const int w_prod = p.role_hi ? CH_EPI_WARPS : 0, w_mma = p.role_hi ? CH_EPI_WARPS + 1 : 1;
   const int num_pairs = (p.num_tiles + 1) >> 1;
   // PAIR = 2: both CTAs of a cluster run the same number of tile pairs (a surplus pair is all-masked rows)
   const uint32_t cl_rank = PAIR == 2 ? ptx::cluster_ctarank() : 0u;
   const int num_iters = (num_pairs + (int)gridDim.x - 1) / (int)gridDim.x;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == w_prod && lane == 0) {
     for (int l = 0; l < p.n_layers; ++l) {
       ptx::prefetch_tmap(&p.w_map[l]);
       if (p.layer[l].store_chunks > 0) ptx::prefetch_tmap(&p.out_map[l]);
@@ -249,7 +206,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == w_mma) {
     if (PAIR == 2) { ptx::tmem_alloc2(tmem_ptr, 512u); ptx::tmem_relinquish2(); }
     else { ptx::tmem_alloc(tmem_ptr, 512u); ptx::tmem_relinquish(); }
   }
@@ -259,7 +216,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == w_prod) {
     // ================================================================ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -295,13 +252,15 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == w_mma) {
     // ================================================================ MMA issuer
     // The WHOLE warp runs this control flow (every value is warp-uniform: descriptors and counters live in uniform
     // registers, a handful of instructions per MMA); only MMA / commit / TMA-store are issued by lane 0.
     // Ping-pong: (layer l, tile 0), (layer l, tile 1), (layer l+1, tile 0), ... -- while the tensor core works on one
     // tile the 16 epilogue warps activate the other one.
-    const bool leader = lane == 0;                          // the issuing lane of this warp
+    // the issuing lane of this warp, chosen by elect.sync: ptxas then keeps the MMA operands in uniform registers; from a
+    // `lane == 0` branch it wraps every tcgen05.mma in an elect / broadcast loop (200+ cycles per instruction)
+    const bool leader = ptx::elect_one();
     const bool cta_leader = PAIR == 1 || cl_rank == 0;      // the CTA that issues the pair's MMAs
     int stage = 0;
     uint32_t phase = 0;
@@ -357,10 +316,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * wstage_bytes) >> 4) & 0x3fff);
               if (leader) {
                 if (!(p.dbg_flags & 16)) {         // (16: timing experiment without the MMAs themselves)
+                  if (PAIR == 2) {
 #pragma unroll
-                  for (int k = 0; k < 4; ++k) {    // +32 bytes per K = 16 step: +2 in the (address >> 4) field
-                    if (PAIR == 2) ptx::umma_bf16_2cta(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
-                    else ptx::umma_bf16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                    for (int k = 0; k < 4; ++k)    // +32 bytes per K = 16 step: +2 in the (address >> 4) field
+                      ptx::umma_bf16_2cta(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, (uint32_t)(kb | k));
+                  } else {
+                    // the four K steps as one statement on 32-bit descriptor words (ptx.cuh)
+                    ptx::umma_bf16_ss_x4(d_tmem, (uint32_t)ad0, (uint32_t)bd0, (uint32_t)(desc_hi >> 32), idesc, (uint32_t)kb);
                   }
                 }
                 if (PAIR == 2) ptx::tc_commit2_mc(&w_empty[stage], (uint16_t)3);
@@ -404,7 +366,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else {
     // ================================================================ epilogue warps
-    const int ew = warp - 2;
+    const int ew = p.role_hi ? warp : warp - 2;
     const int q = warp & 3;      // TMEM lane quarter this warp may access
     const int j = ew >> 2;       // its 16 columns inside every 64-column chunk
     const int r = q * 32 + lane; // row inside the tile
@@ -618,7 +580,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   if (PAIR == 2) ptx::cluster_sync();      // no CTA leaves while the pair's MMAs / commits may still touch it
-  if (warp == 1) {
+  if (warp == w_mma) {
     if (PAIR == 2) ptx::tmem_dealloc2(tmem_base, 512u);
     else ptx::tmem_dealloc(tmem_base, 512u);
   }
@@ -688,7 +650,18 @@ static int chain_launch_t(ChainParams& P, cudaStream_t stream) {
   return 0;
 }
 
+// NUNERF_CHAIN_IMPL: "ss" (default) = this file's kernel (two tiles per CTA in ping-pong, activations in shared memory);
+// "ts" = activations in tensor memory, TS-mode MMAs, one tile per CTA (chain_ts.cu).  Both pass the same parity tests; on
+// B200 the SS kernel is the faster one for every chain of the step (DESIGN.md 4 has the measurements and the reasons).
+static bool chain_use_ts() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NUNERF_CHAIN_IMPL"); v = (e && e[0] == 't') ? 1 : 0; }
+  return v == 1 && chain_pair() == 1;
+}
+
 static int chain_launch(ChainParams& P, cudaStream_t stream) {
+  if (chain_use_ts()) return chain_ts_launch(P, stream);
+  P.role_hi = env_int("NUNERF_CHAIN_HIPRIO", 1);
   return chain_pair() == 2 ? chain_launch_t<2>(P, stream) : chain_launch_t<1>(P, stream);
 }
 
@@ -710,7 +683,7 @@ extern "C" int nunerf_sdf_infer(const nunerf_sdf_infer_t* a, void* stream_) {
     ChainLayer& L = P.layer[l];
     L.N = Ns[l]; L.n_real = Ns[l];
     L.kb0 = 0; L.nkb = Ks[l] / 64;
-    L.act = l < 8 ? 2 : 0; L.to_x = l < 8 ? 1 : 0;
+    L.act = l < 8 ? 2 : 0; L.to_x = l < 8 ? 1 : 0; L.keep = L.to_x;
     L.bias = a->bias[l];
     L.hot = (l < 8 && l != 3) ? 1 : 0;             // KIND 1: bias + softplus
   }
@@ -762,13 +735,15 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
     L.out32 = s.out32; L.ldo32 = s.ldo32; L.n32 = s.n32;
     const bool last = l + 1 == a->n_layers;
     L.to_x = (s.keep || s.store) ? 1 : 0;
-    (void)last;
+    L.keep = (L.to_x && !last) ? 1 : 0;
     if (s.store) {
       NUNERF_REQUIRE(s.ld_store % 8 == 0 && s.ld_store >= s.N, "mlp_chain: bad store pitch");
       const int wide = s.cat_pe ? 256 : (s.N + 63) / 64 * 64;
       const int cols = wide <= s.ld_store ? wide : s.N;
       L.store_chunks = wide / 64;
-      if (int r = make_map(&P.out_map[l], s.store, a->M, cols, s.ld_store, 64, 128)) return r;
+      L.store = (__nv_bfloat16*)s.store; L.ld_store = s.ld_store; L.store_cols = cols;
+      if (!chain_use_ts())
+        if (int r = make_map(&P.out_map[l], s.store, a->M, cols, s.ld_store, 64, 128)) return r;
     }
     if (L.to_x) width = s.cat_pe ? 256 : (s.N + 63) / 64 * 64;   // a layer that keeps nothing leaves the previous activation
     // specialised epilogues

@@ -73,6 +73,49 @@ __device__ __forceinline__ float softplus100(float x) {
   return fmaf(e, q, fmaxf(x, 0.0f));
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2)
+// The fma pipe issues one three-register FFMA per two cycles and scheduler; the packed forms do two lanes of work per
+// issue slot, which is what bounds the activation epilogues of the fused chains.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float a, float b) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// softplus100 of the pair (a + ba, b + bb), same arithmetic as softplus100 (bit-identical results: every step is the same
+// correctly rounded fp32 operation, only issued two lanes at a time)
+__device__ __forceinline__ void softplus100_x2(float& a, float& b, float ba, float bb) {
+  const f32x2_t x2 = f2_add(f2_pack(a, b), f2_pack(ba, bb));
+  float x0, x1, t0, t1;
+  f2_unpack(x2, x0, x1);
+  f2_unpack(f2_mul(x2, f2_pack(144.26950408889634f, 144.26950408889634f)), t0, t1);
+  float e0, e1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(t0, -t0)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(t1, -t1)));
+  const f32x2_t e2 = f2_pack(e0, e1);
+  f32x2_t q = f2_fma(f2_pack(3.215121477842331e-4f, 3.215121477842331e-4f), e2, f2_pack(-1.3604211807250977e-3f, -1.3604211807250977e-3f));
+  q = f2_fma(q, e2, f2_pack(2.8945398330688477e-3f, 2.8945398330688477e-3f));
+  q = f2_fma(q, e2, f2_pack(-4.9190032482147217e-3f, -4.9190032482147217e-3f));
+  q = f2_fma(q, e2, f2_pack(9.994943737983704e-3f, 9.994943737983704e-3f));
+  f2_unpack(f2_fma(e2, q, f2_pack(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), a, b);
+}
+
 // ---------------------------------------------------------------- deterministic fp32 math (sampling path)
 // The sampling kernels and the C oracle (oracle/sampling_oracle.c) must agree bit for bit, so every
 // operation is an explicitly rounded fp32 op (no FMA contraction) and exp() is our own polynomial.

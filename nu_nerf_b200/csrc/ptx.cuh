@@ -141,6 +141,74 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows on the 128 lanes, K = 16 bf16 packed two per 32-bit
+// column -> 8 columns starting at tmem_a) is read from tensor memory, only B streams from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// The four K = 16 steps of one 64-wide K-block as ONE asm statement: operand k is 32 bytes (+2 in the descriptor's
+// address field) / 8 TMEM columns further.  A single statement matters: ptxas wraps every tcgen05.mma issued from
+// divergent code in an elect / broadcast loop (R2UR.BROADCAST of each operand, VOTEU, BRA.U.ANY -- 15-20 dependent
+// instructions, 200-280 cycles measured per MMA when each is its own statement); here the wrapper is paid once per four
+// MMAs and the per-step operand arithmetic stays in the statement's own registers.
+// accum0: whether the FIRST step accumulates (steps 1..3 always do).
+__device__ __forceinline__ void umma_bf16_ts_x4(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                                uint32_t accum0) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t.reg .b64 bd;\n\t.reg .b32 bl, ta;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t"
+      "add.u32 bl, %2, 2;\n\tadd.u32 ta, %1, 8;\n\tmov.b64 bd, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], bd, %4, t;\n\t"
+      "add.u32 bl, %2, 4;\n\tadd.u32 ta, %1, 16;\n\tmov.b64 bd, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], bd, %4, t;\n\t"
+      "add.u32 bl, %2, 6;\n\tadd.u32 ta, %1, 24;\n\tmov.b64 bd, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [ta], bd, %4, t;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accum0)
+      : "memory");
+}
+// same with both operands in shared memory (descriptor low words a_lo / b_lo, common high word)
+__device__ __forceinline__ void umma_bf16_ss_x4(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                                uint32_t accum0) {
+  asm volatile(
+      "{\n\t.reg .pred p, t;\n\t.reg .b64 ad, bd;\n\t.reg .b32 al, bl;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\tsetp.eq.b32 t, 0, 0;\n\t"
+      "mov.b64 ad, {%1, %3};\n\tmov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, p;\n\t"
+      "add.u32 al, %1, 2;\n\tadd.u32 bl, %2, 2;\n\tmov.b64 ad, {al, %3};\n\tmov.b64 bd, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, t;\n\t"
+      "add.u32 al, %1, 4;\n\tadd.u32 bl, %2, 4;\n\tmov.b64 ad, {al, %3};\n\tmov.b64 bd, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, t;\n\t"
+      "add.u32 al, %1, 6;\n\tadd.u32 bl, %2, 6;\n\tmov.b64 ad, {al, %3};\n\tmov.b64 bd, {bl, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %4, t;\n\t}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accum0)
+      : "memory");
+}
+// 32 lanes x 8 consecutive 32-bit columns, registers -> tensor memory (thread t of the warp writes lane base_lane + t)
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32-byte global store (sm_100: STG.256), address 32-byte aligned
+__device__ __forceinline__ void st_global_v8(void* gptr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(gptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 // ---- cta_group::2 (CTA pair: M = 256 split over the two CTAs' A tiles and TMEM, each CTA holds half of B's rows)
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
@@ -183,6 +251,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+      "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+        "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+        "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr)
       : "memory");
 }
