@@ -32,17 +32,10 @@ namespace nunerf {
 //   KIND 2: bias + ReLU, emits the 16 (x > 0) bits    (predictor / NeRF++ forward)
 //   KIND 3: multiply by the 16 mask bits `mbits`      (ReLU backward: dZ_l = (dZ_{l+1} W_{l+1}) . [z_l > 0])
 template <int KIND>
-__device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict__ bias, uint8_t* dst, int j, uint32_t sw,
+__device__ __forceinline__ void ch_hot16(const uint32_t* v, const float* __restrict__ bias, uint8_t* dst, int j, uint32_t sw,
                                          uint32_t* obits, uint32_t mbits, int dbg_flags) {
-  uint32_t v[16];
-  if (dbg_flags & 1) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = taddr + i;
-  } else
-  ptx::tmem_ld16(taddr, v);
   float x[16];
   if (KIND == 3) {
-    ptx::tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = ((mbits >> i) & 1u) ? __uint_as_float(v[i]) : 0.0f;
   } else {
@@ -54,7 +47,6 @@ __device__ __forceinline__ void ch_hot16(uint32_t taddr, const float* __restrict
 #pragma unroll
       for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
     }
-    ptx::tmem_ld_wait();
 #if NUNERF_PACKED_EPI
     if (KIND == 1) {
       // bias + Softplus two lanes per instruction (FADD2 / FMUL2 / FFMA2): the fma pipe bounds this epilogue
@@ -465,26 +457,33 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               else if (L.hot == 5) ch_aux16<5>(taddr, a0, a1, b0, b1, dst, j, sw, L.e_out + aux_row * L.ld_e + c0, row_ok);
               else ch_aux16<6>(taddr, a0, a1, b0, b1, dst, j, sw, nullptr, row_ok);
             }
-          } else
-          for (int c = 0; c < 4; ++c) {
-            const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
-            if (L.hot) {
+          } else if (L.hot) {
+            // ---- plain 256-wide hidden layers: the accumulator read of chunk c + 1 is in flight while chunk c is activated
+            // (one exposed TMEM round trip per tile instead of four)
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + j * 16);
+            uint32_t va[16], vb[16];
+            ptx::tmem_ld16(taddr0, va);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
+              uint32_t* cur = (c & 1) ? vb : va;
+              ptx::tmem_ld_wait();
+              if (c < 3) ptx::tmem_ld16(taddr0 + (uint32_t)((c + 1) * 64), (c & 1) ? va : vb);
               uint32_t ob = 0;
-              const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c0);
               uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
-              if (L.hot == 1) ch_hot16<1>(taddr, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
+              if (L.hot == 1) ch_hot16<1>(cur, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
               else if (L.hot == 2) {
-                ch_hot16<2>(taddr, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
+                ch_hot16<2>(cur, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
                 if (L.mask_perm) out_mask |= (unsigned long long)ob << (16 * c);
                 else if (L.mask_out && row_ok)
                   *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
               } else {
-                ch_hot16<3>(taddr, nullptr, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu,
-                            p.dbg_flags);
+                ch_hot16<3>(cur, nullptr, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu, p.dbg_flags);
               }
-              if (p.dbg_flags & 8) __nanosleep(p.dbg_flags >> 4);   // experiment: yield issue slots to the MMA warp
-              continue;
             }
+          } else
+          for (int c = 0; c < 4; ++c) {
+            const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
             const bool in_acc = c0 < L.N;       // columns the MMA produced
             // columns that must be (re)written in shared memory: the produced ones, the concatenated PE columns,
             // and the zero tail of a partially produced K-block (the next layer reads whole 64-column blocks)
