@@ -289,6 +289,11 @@ int nunerf_weights_backward(const nunerf_wdesc_t* descs, const int32_t* blk_desc
 int nunerf_adam(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
                 int step, void* stream);
 
+/* Traversal-stack pushes dropped since the library was loaded: always 0 for trees built by nunerf_bvh_build_host (which
+ * refuses trees deeper than the stack allows); synchronises the device.  Replaces the silent clamp of the reference's
+ * fixed-size stack (raytracing/src/bvh.cu:526-602). */
+int nunerf_bvh_overflow_count(unsigned int* out);
+
 /* ------------------------------------------------------------------ tracing (DiffRender.py:410-416, :61-125;
  * cuda/triangle.cu:48-99; raytracing/src/bvh.cu:259-301,526-602,694-713)
  * nunerf_bvh_build_host: host build of a 4-wide BVH (recursive median split on the axis of largest centroid

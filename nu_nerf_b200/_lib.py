@@ -144,7 +144,11 @@ for _name, _args in _SIGS.items():
     _fn.argtypes = _args
     _fn.restype = ci
 
-ALL_SYMBOLS = ["nunerf_last_error", "nunerf_version", "nunerf_launch_count", "nunerf_mc_blocks"] + list(_SIGS)
+lib.nunerf_bvh_overflow_count.argtypes = [C.POINTER(C.c_uint)]
+lib.nunerf_bvh_overflow_count.restype = ci
+
+ALL_SYMBOLS = ["nunerf_last_error", "nunerf_version", "nunerf_launch_count", "nunerf_mc_blocks",
+               "nunerf_bvh_overflow_count"] + list(_SIGS)
 
 
 def ptr(t):

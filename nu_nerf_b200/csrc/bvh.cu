@@ -56,6 +56,10 @@ __device__ __forceinline__ void consider(const float* o, const float* d, const f
 // ------------------------------------------------------------------------------------------- traversal
 constexpr int TRACE_THREADS = 128;
 constexpr int STACK_DEPTH = 48;
+// A pop pushes at most the four children of the node, so a tree of depth D needs 3 (D - 1) + 4 entries.  The builder
+// splits at the median (depth <= 15 for any int32 triangle count) and REFUSES trees that would not fit; should a foreign
+// node array overflow anyway, the push is counted here (nunerf_bvh_overflow_count) instead of vanishing silently.
+__device__ unsigned int g_bvh_overflow = 0;
 
 __global__ void __launch_bounds__(TRACE_THREADS)
 bvh_trace_kernel(const nunerf_bvh_node_t* __restrict__ nodes, const float* __restrict__ tri_verts,
@@ -111,6 +115,7 @@ bvh_trace_kernel(const nunerf_bvh_node_t* __restrict__ nodes, const float* __res
       if (tn[k] == INFINITY || nd->count[k] != 0) continue;
       if (tn[k] > best.t) continue;
       if (sp < STACK_DEPTH) s_stack[sp++][tid] = nd->child[k];
+      else atomicAdd(&g_bvh_overflow, 1u);
     }
   }
   hit[i] = best.id != MISS_ID ? 1.0f : 0.0f;
@@ -191,6 +196,7 @@ struct BuildCtx {
   std::vector<float> cent;  // [F,3]
   std::vector<int> order;
   nunerf_bvh_node_t* nodes; int max_nodes; int n_nodes;
+  int depth;                // deepest node level reached (root = 1)
 };
 
 static void tri_bounds(const BuildCtx& c, int b, int e, float* lo, float* hi) {
@@ -223,9 +229,10 @@ static int split_median(BuildCtx& c, int b, int e) {
   return mid;
 }
 
-static int build_node(BuildCtx& c, int b, int e) {
+static int build_node(BuildCtx& c, int b, int e, int level = 1) {
   if (c.n_nodes >= c.max_nodes) return -1;
   int me = c.n_nodes++;
+  c.depth = std::max(c.depth, level);
   int rb[4], re[4], nr = 0;
   if (e - b <= 4) { rb[0] = b; re[0] = e; nr = 1; }
   else {
@@ -244,7 +251,7 @@ static int build_node(BuildCtx& c, int b, int e) {
     for (int j = 0; j < 3; ++j) { c.nodes[me].lo[k][j] = lo[j]; c.nodes[me].hi[k][j] = hi[j]; }
     if (re[k] - rb[k] <= 4) { c.nodes[me].count[k] = re[k] - rb[k]; c.nodes[me].child[k] = rb[k]; }
     else {
-      int ch = build_node(c, rb[k], re[k]);
+      int ch = build_node(c, rb[k], re[k], level + 1);
       if (ch < 0) return -1;
       c.nodes[me].count[k] = 0; c.nodes[me].child[k] = ch;
     }
@@ -261,7 +268,7 @@ extern "C" int nunerf_bvh_build_host(const float* verts, int V, const int32_t* f
   NUNERF_REQUIRE(verts && faces && nodes && tri_order && V > 0 && F > 0 && max_nodes > 0, "bvh_build: bad arguments");
   for (int i = 0; i < 3 * F; ++i) NUNERF_REQUIRE(faces[i] >= 0 && faces[i] < V, "bvh_build: face index out of range");
   BuildCtx c;
-  c.verts = verts; c.faces = faces; c.nodes = nodes; c.max_nodes = max_nodes; c.n_nodes = 0;
+  c.verts = verts; c.faces = faces; c.nodes = nodes; c.max_nodes = max_nodes; c.n_nodes = 0; c.depth = 0;
   c.cent.resize(3 * (size_t)F);
   c.order.resize(F);
   for (int f = 0; f < F; ++f) {
@@ -271,6 +278,7 @@ extern "C" int nunerf_bvh_build_host(const float* verts, int V, const int32_t* f
   }
   int root = build_node(c, 0, F);
   NUNERF_REQUIRE(root == 0, "bvh_build: node capacity exceeded");
+  NUNERF_REQUIRE(3 * (c.depth - 1) + 4 <= STACK_DEPTH, "bvh_build: tree too deep for the traversal stack");
   for (int f = 0; f < F; ++f) tri_order[f] = c.order[f];
   return c.n_nodes;
 }
@@ -282,6 +290,15 @@ extern "C" int nunerf_bvh_trace(const nunerf_bvh_node_t* nodes, const float* tri
   bvh_trace_kernel<<<cdiv(N, TRACE_THREADS), TRACE_THREADS, 0, (cudaStream_t)stream>>>(nodes, tri_verts, tri_order,
                                                                                      rays_o, rays_d, N, tmax, hit, tri, t);
   NUNERF_CHECK_LAUNCH("bvh_trace_kernel");
+  return 0;
+}
+
+// number of traversal-stack pushes dropped since the library was loaded (0 for every tree nunerf_bvh_build_host accepts);
+// synchronises the device
+extern "C" int nunerf_bvh_overflow_count(unsigned int* out) {
+  NUNERF_REQUIRE(out, "bvh_overflow_count: bad arguments");
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_bvh_overflow, sizeof(unsigned int));
+  if (e != cudaSuccess) return fail("bvh_overflow_count: %s", cudaGetErrorString(e), -2);
   return 0;
 }
 

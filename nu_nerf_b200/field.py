@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from .fg_lut import make_fg_lut
+from .fg_lut import load_fg_lut
 
 
 class WNLinear(nn.Module):
@@ -159,7 +159,7 @@ class AppShadingNetwork(nn.Module):
         if self.cfg["roughness_init"] != 0:
             nn.init.constant_(self.roughness_predictor[-2].bias, self.cfg["roughness_init"])
         self.albedo_predictor = make_predictor(feats_dim + 3, 3)
-        self.register_buffer("FG_LUT", torch.from_numpy(make_fg_lut()).clone())
+        self.register_buffer("FG_LUT", torch.from_numpy(load_fg_lut()))
         pos_dim = pe_dim(self.cfg["light_pos_freq"])
         dir_dim = pe_dim(6)
         rf = pe_dim(self.cfg["refrac_freq"])

@@ -58,6 +58,13 @@ class TriangleBVH:
                  o.data_ptr(), d.data_ptr(), N, float(tmax), hit.data_ptr(), tri.data_ptr(), t.data_ptr())
         return (hit, tri, t) if return_t else (hit, tri)
 
+    @staticmethod
+    def overflow_count():
+        """Traversal-stack pushes dropped so far (always 0 for trees built here; synchronises the device)."""
+        n = C.c_uint(0)
+        _lib.check(_lib.lib.nunerf_bvh_overflow_count(C.byref(n)), "nunerf_bvh_overflow_count")
+        return int(n.value)
+
     def trace_brute(self, rays_o, rays_d, tmax=1e16):
         N = rays_o.shape[0]
         o = rays_o.detach().float().contiguous()

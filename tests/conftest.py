@@ -26,6 +26,23 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(scope="session", autouse=True)
+def reference_fg_lut(tmp_path_factory):
+    """Every renderer built by the tests registers the REFERENCE's split-sum table (tests/golden/fg_lut_reference.npz =
+    its asset assets/bsdf_256_256.bin, which the goldens were generated with) through the product's own search order
+    (nu_nerf_b200/fg_lut.load_fg_lut: $NUNERF_FG_LUT first)."""
+    lut = np.load(os.path.join(GOLDEN, "fg_lut_reference.npz"))["FG_LUT"].astype(np.float32)
+    path = str(tmp_path_factory.mktemp("lut") / "bsdf_256_256.bin")
+    lut.tofile(path)
+    old = os.environ.get("NUNERF_FG_LUT")
+    os.environ["NUNERF_FG_LUT"] = path
+    yield lut
+    if old is None:
+        os.environ.pop("NUNERF_FG_LUT", None)
+    else:
+        os.environ["NUNERF_FG_LUT"] = old
+
+
 def _make(target):
     subprocess.run(["make", "-s", target], cwd=ROOT, check=True)
 

@@ -8,6 +8,7 @@ Fixtures (all small):
                        synthetic rays: z_vals, every searchsorted index / sort permutation of sample_ray,
                        outputs dict, and strided samples of every parameter gradient of the trainer loss.
   stage1_sphere_R64.npz same with near/far from the unit sphere and perturb=0 (eval-style sampling).
+  fg_lut_reference.npz the reference's FG_LUT buffer (its asset assets/bsdf_256_256.bin as loaded by field.py:583)
   stage1_occ_R64.npz   same rays at step 20000: occlusion-probe loss (ZT:695-723) with its recorded randperm draw,
                        outer_reg, trainable inv_s.
 """
@@ -20,7 +21,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh  # noqa: E402
-from nu_nerf_b200.fg_lut import make_fg_lut  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 GRAD_STRIDE_SAMPLES = 64
@@ -138,9 +138,11 @@ def run_case(net, R, sphere, perturb, step=10000):
 
 
 def main():
-    lut = make_fg_lut()
-    net, cfg = rh.load_stage1(seed=0, fg_lut=lut)
+    # the reference loads ITS OWN split-sum table (assets/bsdf_256_256.bin, field.py:583); the table is committed as a
+    # fixture so that the GPU box (no /root/reference) shades with exactly the values these goldens were produced with
+    net, cfg = rh.load_stage1(seed=0)
     sd = net.state_dict()
+    np.savez_compressed(os.path.join(OUT, "fg_lut_reference.npz"), FG_LUT=sd["color_network.FG_LUT"].numpy())
     np.savez_compressed(os.path.join(OUT, "stage1_init.npz"),
                         **{k: fingerprint(v) for k, v in sd.items() if k != "color_network.FG_LUT"})
     np.savez_compressed(os.path.join(OUT, "stage1_train_R64.npz"), **run_case(net, 64, sphere=False, perturb=True))

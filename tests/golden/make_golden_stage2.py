@@ -21,7 +21,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh  # noqa: E402
-from nu_nerf_b200.fg_lut import make_fg_lut  # noqa: E402
 from make_golden import fingerprint, strided  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -30,7 +29,7 @@ MESH = dict(radius=0.6, nu=48, nv=24)
 
 def main():
     V, Fc = rh.uv_sphere(**MESH)
-    net, cfg = rh.load_stage2(V, Fc, fg_lut=make_fg_lut())
+    net, cfg = rh.load_stage2(V, Fc)          # with the reference's own FG_LUT asset (fg_lut_reference.npz)
     sd = net.state_dict()
     np.savez_compressed(os.path.join(OUT, "stage2_init.npz"),
                         **{k: fingerprint(v) for k, v in sd.items() if not k.endswith("FG_LUT")})
