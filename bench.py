@@ -2,12 +2,18 @@
 """bench.py -- stage-1 training-step throughput (rays/s) of the NU-NeRF hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K ...  the reference algorithm's CPU implementation (oracle port)
+  python bench.py --impl reference --gpus N --steps K ...  the UNMODIFIED reference on the host cores (oracle/_ref staged by
+                                                           oracle/make_ref.py; the oracle port only if that tree is absent)
 
 A step = sample_ray + render_core forward + trainer loss + backward + (NCCL grad all-reduce) + Adam on one batch of
 synthetic rays (spherepot field, random init, step 10000, rays on a radius-3 sphere).  `value` is measured
 with the ray batch already resident in HBM; `e2e` repeats the measurement through the renderer's public API with the
 batch in pinned host memory (H2D of rays/targets and a D2H read of the loss inside the timed region).
+
+At N = 1 the line also carries `configs`: the other BASELINE.json configurations measured inside the same command --
+the fp32-accurate split mode on config 2, config 3's 32 768-ray batch on one GPU, config 4 (stage-2 trace + training
+step on the 99 904-triangle mesh) and config 5 (eval render, 512^3 sweep, marching cubes).  At N > 1 the default batch is
+config 3's 32 768 rays per GPU and the 4096-ray measurement is kept as `configs.config2_rays4096`.
 """
 import argparse
 import json
@@ -87,12 +93,48 @@ class ClockSampler:
 
 
 # =============================================================================================== reference arm
+def _reference_root():
+    """The unmodified reference's files: /root/reference in the build container, oracle/_ref (staged by
+    oracle/make_ref.py at build time, git-ignored, shipped with the working tree) on the GPU box."""
+    for r in (os.environ.get("NUNERF_REFERENCE_ROOT"), os.path.join(ROOT, "oracle", "_ref"), "/root/reference"):
+        if r and os.path.isdir(os.path.join(r, "network")):
+            return r
+    return None
+
+
 def cpu_step_fn(R):
-    """One training step of the oracle port (torch CPU, all host threads) on R rays; returns a callable."""
+    """One training step of the reference's CPU implementation on R rays (all host threads); returns (callable, kind).
+    kind "reference": the UNMODIFIED reference module (network/renderer_zerothick.py NeROShapeRenderer.render + the
+    trainer's loss + torch Adam) imported through the shim layer of oracle/ref_harness.py; kind "port": the oracle
+    restatement, only when no reference tree is available."""
     import torch
+    torch.set_num_threads(os.cpu_count())
+    root = _reference_root()
+    if root is not None:
+        os.environ["NUNERF_REFERENCE_ROOT"] = root
+        from oracle import ref_harness as rh
+        rh.REF_ROOT = root
+        net, _ = rh.load_stage1(seed=0)
+        o, d = rh.synthetic_rays(R)
+        gt = rh.synthetic_targets(R)
+        near, far = torch.full((R, 1), 0.8), torch.full((R, 1), 4.5)
+        poses = torch.eye(3, 4)[None].repeat(R, 1, 1)
+        opt = torch.optim.Adam(net.parameters(), lr=lr_at(STEP))
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with rh.in_ref_dir():
+                out = net.render(o, d, near, far, poses, -1, net.get_anneal_val(STEP), is_train=True, step=STEP, is_nerf=True)
+            loss = net.compute_rgb_loss(out["ray_rgb"], gt).mean() + (EIK_W * out["gradient_error"]).mean()
+            if STEP >= net.cfg["occ_loss_step"]:
+                loss = loss + out["loss_occ"].mean() + 0.5 * torch.nn.functional.mse_loss(out["color_bkgr"].flatten(),
+                                                                                          out["color_spec"].flatten())
+            loss.backward()
+            opt.step()
+            return float(loss)
+        return step, "reference"
     from oracle import nunerf_oracle as orc
     from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
-    torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     net = NeROShapeRenderer(load_default_cfg(), training=False)
     sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
@@ -110,7 +152,12 @@ def cpu_step_fn(R):
         loss.backward()
         opt.step()
         return float(loss)
-    return step
+    return step, "port"
+
+
+def _cpu_what(kind):
+    return ("unmodified reference (network/renderer_zerothick.py through oracle/ref_harness.py shims) on torch CPU"
+            if kind == "reference" else "oracle port (oracle/nunerf_oracle.py) on torch CPU")
 
 
 def run_reference(args):
@@ -118,7 +165,7 @@ def run_reference(args):
     if rank != 0:
         return
     R = args.cpu_rays
-    step = cpu_step_fn(R)
+    step, kind = cpu_step_fn(R)
     for _ in range(max(1, min(args.warmup, 2))):
         step()
     t0 = time.perf_counter()
@@ -132,9 +179,9 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"stage-1 spherepot training step (sample_ray + render_core fwd+bwd + Adam), step {STEP}, "
-                               f"bounded sample of {R} rays per step, oracle port on host cores"},
-        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"{R} rays x {args.steps} steps, torch CPU {cores} threads (oracle/nunerf_oracle.py)"},
+                               f"bounded sample of {R} rays per step, {_cpu_what(kind)}"},
+        "cpu_baseline": {"value": val, "unit": "rays/s", "cores": cores, "kind": kind,
+                         "sample": f"{R} rays x {args.steps} steps, {cores} threads, {_cpu_what(kind)}"},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -144,7 +191,7 @@ def run_reference(args):
 # =============================================================================================== our arm
 def ncu_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel` from the committed `ncu --set full`
-    capture (profiles/ncu_traffic.json: written by hand from tools/ncu_metrics.py output, names the capture)."""
+    capture (profiles/ncu_traffic.json: written by tools/ncu_traffic.py from the .ncu-rep, names the capture)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if not os.path.exists(path):
         return None
@@ -248,6 +295,79 @@ def profile_step(train_step, inputs, ops, torch):
         print(f"[profile] {ms:8.3f} ms {n:4d}x  {key} {gbs}", file=sys.stderr)
 
 
+def stage1_quick(args, torch, dist, dev, precision, R, steps, world=1, rank=0):
+    """A short measurement of the stage-1 training step at another precision / batch size (sub-records of the line)."""
+    from nu_nerf_b200 import dist as nd
+    from nu_nerf_b200 import synthetic as syn
+    from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
+    cfg = load_default_cfg()
+    cfg["precision"] = precision
+    cfg["train_ray_num"] = R
+    torch.manual_seed(0)
+    net = NeROShapeRenderer(cfg, training=False).to(dev)
+    anneal = float(net.get_anneal_val(STEP))
+    trainer = nd.DataParallelTrainer(net, lambda o, d, n_, f_, st: net.render(o, d, n_, f_, None, -1, anneal, is_train=True,
+                                                                             step=st, is_nerf=True),
+                                     net.compute_rgb_loss, lr_fn=lambda s_: lr_at(s_), eikonal_weight=EIK_W,
+                                     occ_loss_step=cfg["occ_loss_step"])
+    o_all, d_all = syn.synthetic_rays(R * world, seed=1)
+    gt_all = syn.synthetic_targets(R * world, seed=3)
+    sel = nd.shard_batch(torch.arange(R * world), rank, world)
+    o, d, gt = (t[sel].contiguous().to(dev) for t in (o_all, d_all, gt_all))
+    near, far = torch.full((R, 1), 0.8, device=dev), torch.full((R, 1), 4.5, device=dev)
+    chunk = min(args.chunk, R)
+    for _ in range(3):
+        trainer.step(o, d, gt, near, far, STEP, chunk=chunk)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        trainer.step(o, d, gt, near, far, STEP, chunk=chunk)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item() / steps
+    n_in = trainer.last["n_in"]
+    flops = (R / chunk) * (2.0 * chunk * 112 * M_SDF_HEAD + n_in * 2.0 * (3 * M_SDF + 3 * M_SDF_HEAD + 3 * M_COL)
+                           + (chunk * 160 - n_in) * 2.0 * 3 * M_NERF + chunk * 2.0 * 3 * M_OL)
+    del trainer, net
+    torch.cuda.empty_cache()
+    return {"precision": precision, "rays_per_gpu": R, "n_gpus": world, "steps": steps, "ms_per_step": ms,
+            "value": R * world / (ms * 1e-3), "unit": "rays/s", "step_algorithmic_tflops_per_gpu": flops / (ms * 1e-3) / 1e12}
+
+
+def sub_records(args, torch, dev, hbm, tf_sus):
+    """The other BASELINE.json configurations, measured inside the same command (N = 1)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    out = {}
+    try:
+        sp = stage1_quick(args, torch, None, dev, "split", args.rays_per_gpu, steps=3)
+        sp["frac_of_tensor_peak"] = sp["step_algorithmic_tflops_per_gpu"] / tf_sus
+        sp["note"] = ("fp32-accurate mode (bf16 hi + lo planes, 3 MMAs per product, layer-by-layer kernels): the mode "
+                      "that meets the 1e-4 rgb / 1e-3 gradient gates")
+        out["split"] = sp
+        c3 = stage1_quick(args, torch, None, dev, "bf16", 32768, steps=3)
+        c3["frac_of_tensor_peak"] = c3["step_algorithmic_tflops_per_gpu"] / tf_sus
+        out["config3_rays32768_1gpu"] = c3
+        import bench_stage2
+        c4 = bench_stage2.run(4096, train_iters=12)
+        c4["trace_only"]["hbm_frac_algorithmic"] = c4["trace_only"]["algorithmic_GBs"] / hbm
+        out["config4_stage2"] = c4
+        torch.cuda.empty_cache()
+        import bench_sweep
+        out["config5_sweep_eval"] = bench_sweep.run(512)
+        torch.cuda.empty_cache()
+    except Exception as e:            # a sub-record must never take the headline down with it
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -263,6 +383,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if args.rays_per_gpu <= 0:          # default: config 2 on one GPU, config 3 (32 768 rays per GPU) on several
+        args.rays_per_gpu = 4096 if world == 1 else 32768
     R = args.rays_per_gpu
     chunk = min(args.chunk, R)
     cfg = load_default_cfg()
@@ -397,17 +519,23 @@ def run_ours(args):
                      "step_algorithmic_tflops": flops_step / (ms * 1e-3) / 1e12,
                      "step_frac_of_tensor_peak": flops_step / (ms * 1e-3) / 1e12 / tf_sus},
     }
+    if world == 1 and not args.no_subrecords:
+        line["configs"] = sub_records(args, torch, dev, hbm, tf_sus)
+    if world > 1 and R != 4096 and not args.no_subrecords:
+        # the 4096-ray batch of config 2 on the same N GPUs, kept beside the config-3 headline
+        sub = stage1_quick(args, torch, dist, dev, "bf16", 4096, steps=max(3, args.steps // 2), world=world, rank=rank)
+        line["configs"] = {"config2_rays4096": sub}
     if world == 1 and not args.no_cpu_baseline:
         Rc = args.cpu_rays
-        step = cpu_step_fn(Rc)
+        step, kind = cpu_step_fn(Rc)
         step()
         t0 = time.perf_counter()
         n = 2
         for _ in range(n):
             step()
         dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": Rc / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{Rc} rays x {n} steps (1 warm-up), oracle port on torch CPU, {os.cpu_count()} threads"}
+        line["cpu_baseline"] = {"value": Rc / dt, "unit": "rays/s", "cores": os.cpu_count(), "kind": kind,
+                                "sample": f"{Rc} rays x {n} steps (1 warm-up), {os.cpu_count()} threads, {_cpu_what(kind)}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -420,13 +548,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rays-per-gpu", type=int, default=4096)
+    ap.add_argument("--rays-per-gpu", type=int, default=0, help="default: 4096 (config 2) at N = 1, 32768 (config 3) at N > 1")
     ap.add_argument("--chunk", type=int, default=8192, help="rays per render call (memory bound)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "split"])
     ap.add_argument("--step", type=int, default=STEP, help="training step the schedule is evaluated at (SURVEY 8d: 10000; "
                     "20000 adds the occlusion-probe loss, outer_reg and the trainable inv_s)")
-    ap.add_argument("--cpu-rays", type=int, default=512, help="bounded CPU sample (rays per step; config 1 of BASELINE.json)")
+    ap.add_argument("--cpu-rays", type=int, default=256, help="bounded CPU sample (rays per step; config 1 of BASELINE.json "
+                    "is 512: per-ray cost is flat in the batch size, SURVEY 6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-subrecords", action="store_true", help="skip the `configs` sub-records (split mode, configs 3-5)")
     ap.add_argument("--profile", action="store_true", help="print a per-entry-point device-time table to stderr")
     args = ap.parse_args()
     STEP = args.step          # 10000 = the SURVEY 8(d) primary point; 20000 = occlusion-probe loss + outer_reg + trainable inv_s

@@ -87,6 +87,46 @@ def linear_to_srgb(x):
 
 
 # ----------------------------------------------------------------------------- networks
+# Test aid: emulate the ENGINE's tensor-core operand precision inside this fp32 oracle.  None = plain fp32 (the reference's
+# arithmetic); "split" = operands carried as bf16 hi + lo planes (16 mantissa bits), "bf16" = one bf16 plane.  Both matmul
+# operands and the gradient entering the matmul (the engine's dZ planes) are rounded, with straight-through derivatives.
+# tests/test_engine_gpu.py uses it to show that the parameter gradients which differ from the fp32 reference by more than
+# 1e-3 do so because of this operand rounding (ReLU / clamp decisions of a few samples flip), not because of the kernels.
+OPERAND_PRECISION = None
+
+
+def _rnd(x):
+    if OPERAND_PRECISION is None or not x.dtype.is_floating_point:
+        return x
+    hi = x.to(torch.bfloat16).to(x.dtype)
+    if OPERAND_PRECISION == "bf16":
+        return hi
+    return hi + (x - hi).to(torch.bfloat16).to(x.dtype)
+
+
+class _Operand(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _rnd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _mm(h, Wt, b=None):
+    """h @ Wt (+ b), `Wt` already transposed to [in, out]."""
+    if OPERAND_PRECISION is None:
+        z = h @ Wt
+    else:
+        z = _Operand.apply(h) @ _Operand.apply(Wt)
+    if b is not None:
+        z = z + b
+    if OPERAND_PRECISION is not None and z.requires_grad:
+        z.register_hook(_rnd)
+    return z
+
+
 def wn_weight(sd, prefix):
     """nn.utils.weight_norm(dim=0): W = g * v / ||v||_row."""
     v, g = sd[prefix + ".weight_v"], sd[prefix + ".weight_g"]
@@ -108,7 +148,7 @@ def sdf_forward(sd, x, prefix="sdf_network", with_grad=False):
         b = sd[f"{prefix}.lin{l}.bias"]
         if l == 4:
             h = torch.cat([h, pe], -1) / SQRT2
-        z = h @ W.t() + b
+        z = _mm(h, W.t(), b)
         W_list.append(W)
         if l < 8:
             h = softplus100(z)
@@ -121,7 +161,7 @@ def sdf_forward(sd, x, prefix="sdf_network", with_grad=False):
     g_pe_skip = None
     for l in range(7, -1, -1):
         g = g * s_list[l]                                      # through softplus of layer l
-        g = g @ W_list[l]                                      # to the input of layer l
+        g = _mm(g, W_list[l])                                  # to the input of layer l
         if l == 4:
             g = g / SQRT2
             g_pe_skip = g[:, 217:]
@@ -140,7 +180,7 @@ def predictor(sd, prefix, x, act, exp_max=3.0):
     """make_predictor (field.py:371-408): 4 weight-normed layers, ReLU, output activation."""
     h = x
     for i, l in enumerate((0, 2, 4, 6)):
-        h = h @ wn_weight(sd, f"{prefix}.{l}").t() + sd[f"{prefix}.{l}.bias"]
+        h = _mm(h, wn_weight(sd, f"{prefix}.{l}").t(), sd[f"{prefix}.{l}.bias"])
         if i < 3:
             h = F.relu(h)
     if act == "sigmoid":
@@ -156,14 +196,14 @@ def nerfpp_forward(sd, pts4, views, prefix="outer_nerf"):
     vpe = pos_enc(views, 4)
     h = xpe
     for i in range(8):
-        h = F.relu(h @ sd[f"{prefix}.pts_linears.{i}.weight"].t() + sd[f"{prefix}.pts_linears.{i}.bias"])
+        h = F.relu(_mm(h, sd[f"{prefix}.pts_linears.{i}.weight"].t(), sd[f"{prefix}.pts_linears.{i}.bias"]))
         if i == 4:
             h = torch.cat([xpe, h], -1)
-    alpha = h @ sd[f"{prefix}.alpha_linear.weight"].t() + sd[f"{prefix}.alpha_linear.bias"]
-    feat = h @ sd[f"{prefix}.feature_linear.weight"].t() + sd[f"{prefix}.feature_linear.bias"]
+    alpha = _mm(h, sd[f"{prefix}.alpha_linear.weight"].t(), sd[f"{prefix}.alpha_linear.bias"])
+    feat = _mm(h, sd[f"{prefix}.feature_linear.weight"].t(), sd[f"{prefix}.feature_linear.bias"])
     h = torch.cat([feat, vpe], -1)
-    h = F.relu(h @ sd[f"{prefix}.views_linears.0.weight"].t() + sd[f"{prefix}.views_linears.0.bias"])
-    rgb = h @ sd[f"{prefix}.rgb_linear.weight"].t() + sd[f"{prefix}.rgb_linear.bias"]
+    h = F.relu(_mm(h, sd[f"{prefix}.views_linears.0.weight"].t(), sd[f"{prefix}.views_linears.0.bias"]))
+    rgb = _mm(h, sd[f"{prefix}.rgb_linear.weight"].t(), sd[f"{prefix}.rgb_linear.bias"])
     return alpha, rgb
 
 

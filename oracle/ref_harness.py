@@ -81,7 +81,10 @@ def install():
     dr.texture = _dr_texture
     sys.modules["nvdiffrast.torch"] = dr
     sys.modules["nvdiffrast"].torch = dr
+    import importlib.machinery
+    dr.__spec__ = importlib.machinery.ModuleSpec("nvdiffrast.torch", None)
     tq = types.ModuleType("tqdm")
+    tq.__spec__ = importlib.machinery.ModuleSpec("tqdm", None)     # torch._dynamo walks sys.modules with find_spec
     tq.tqdm = lambda x, *a, **k: x
     tq.trange = lambda *a, **k: range(*a)
     sys.modules["tqdm"] = tq

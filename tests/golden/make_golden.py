@@ -8,6 +8,8 @@ Fixtures (all small):
                        synthetic rays: z_vals, every searchsorted index / sort permutation of sample_ray,
                        outputs dict, and strided samples of every parameter gradient of the trainer loss.
   stage1_sphere_R64.npz same with near/far from the unit sphere and perturb=0 (eval-style sampling).
+  stage1_invs300_R64.npz the training case with deviation_network.variance set so that inv_s = 300 (a trained-like field:
+                       the sdf -> alpha map is 15x sharper than at initialisation)
   fg_lut_reference.npz the reference's FG_LUT buffer (its asset assets/bsdf_256_256.bin as loaded by field.py:583)
   stage1_occ_R64.npz   same rays at step 20000: occlusion-probe loss (ZT:695-723) with its recorded randperm draw,
                        outer_reg, trainable inv_s.
@@ -153,6 +155,12 @@ def main():
     np.savez_compressed(os.path.join(OUT, "stage1_occ_R64.npz"), **run_case(net, 64, sphere=False, perturb=True,
                                                                             step=20000))
     net.cfg["occ_loss_max_pn"] = 2048
+    # a trained-like sharpness: inv_s = exp(10 variance) = 300 (ZT:657-685; random init has inv_s ~ 20), same rays
+    import math
+    v0 = net.deviation_network.variance.data.clone()
+    net.deviation_network.variance.data.fill_(math.log(300.0) / 10.0)
+    np.savez_compressed(os.path.join(OUT, "stage1_invs300_R64.npz"), **run_case(net, 64, sphere=False, perturb=True))
+    net.deviation_network.variance.data.copy_(v0)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(OUT, f)))

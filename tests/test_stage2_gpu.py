@@ -173,7 +173,8 @@ def test_parameter_gradients_match_reference(net, golden):
 
 
 def test_bf16_mode_gradients_are_close(golden):
-    """Fast mode: gradient norms within 2e-2 + the fp32 tolerance for >= 85 % of the tensors."""
+    """Fast mode: gradient norms within 2e-2 of the reference's for >= 85 % of the tensors and within 0.1 for every tensor
+    (measured worst printed; the tail is the same kink-conditioned set as in stage 1, tests/test_engine_gpu.py)."""
     GG = np.load(os.path.join(GOLDEN, "stage2_grads_R64.npz"))
     net16 = make_stage2("bf16").cuda()
     out, loss = _stage2_loss_backward(net16, golden, GG)
@@ -190,7 +191,10 @@ def test_bf16_mode_gradients_are_close(golden):
         nrel = abs(named[name].grad.double().norm().item() - ref_norm) / ref_norm
         if nrel > 2e-2:
             bad.append((name, nrel))
-    assert len(bad) <= 0.15 * n, sorted(bad, key=lambda b: -b[1])[:8]
+    bad.sort(key=lambda b: -b[1])
+    print(f"[stage 2, bf16] {n - len(bad)}/{n} gradient norms within 2e-2; worst:", [(b[0], round(b[1], 4)) for b in bad[:5]])
+    assert len(bad) <= 0.15 * n, bad[:8]
+    assert not bad or bad[0][1] < 0.1, bad[:4]
 
 
 def test_nvs_renders_an_image(net):

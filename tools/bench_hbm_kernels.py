@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench  # noqa: E402
 from nu_nerf_b200 import engine as eng  # noqa: E402
 from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg  # noqa: E402
-from conftest import uv_sphere  # noqa: E402
+from nu_nerf_b200.synthetic import uv_sphere  # noqa: E402
 from nu_nerf_b200 import synthetic as orc  # noqa: E402
 
 

@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
-from conftest import make_stage2, uv_sphere  # noqa: E402
+from nu_nerf_b200.synthetic import make_stage2, uv_sphere  # noqa: E402
 
 
 def timeit(fn, iters=10, warm=3, per_iter=False):
@@ -36,8 +36,7 @@ def timeit(fn, iters=10, warm=3, per_iter=False):
     return e0.elapsed_time(e1) / iters
 
 
-def main():
-    R = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+def run(R=4096, train_iters=20):
     V, Fc = uv_sphere(0.6, 224, 224)
     net = make_stage2("bf16", mesh=(V, Fc)).cuda()
     g = torch.Generator().manual_seed(1)
@@ -69,9 +68,9 @@ def main():
         loss.backward()
         opt.step()
         return loss
-    t_train = timeit(train_step, iters=20, warm=6, per_iter=True)
+    t_train = timeit(train_step, iters=train_iters, warm=6, per_iter=True)
     ms_train, ms_train_mean = t_train[len(t_train) // 2], sum(t_train) / len(t_train)
-    print(json.dumps({
+    return {
         "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
                     f"{R} rays, bf16 mode",
         "trace_only": {"rays": Rt, "ms": ms_trace, "Mrays_per_s": Rt / ms_trace / 1e3,
@@ -80,11 +79,11 @@ def main():
         "ray_trace_with_sampling": {"rays": R, "ms": ms_rt, "rays_per_s": R / ms_rt * 1e3},
         "full_forward": {"rays": R, "ms": ms_full, "rays_per_s": R / ms_full * 1e3},
         "train_step": {"rays": R, "ms": ms_train, "rays_per_s": R / ms_train * 1e3, "ms_mean": ms_train_mean,
-                       "ms_min_max": [t_train[0], t_train[-1]], "timing": "median of 20 per-step CUDA-event timings",
+                       "ms_min_max": [t_train[0], t_train[-1]], "timing": f"median of {train_iters} per-step CUDA-event timings",
                        "note": "forward + backward w.r.t. all field parameters + Adam; IORs_pred gradient (through the "
                                "path geometry) not included"},
-    }))
+    }
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 4096)))

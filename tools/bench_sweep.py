@@ -16,8 +16,7 @@ from nu_nerf_b200._lib import call  # noqa: E402
 M_SDF_HEAD = 459008
 
 
-def main():
-    res = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+def run(res=512):
     cfg = load_default_cfg()
     cfg["precision"] = "bf16"
     torch.manual_seed(0)
@@ -75,13 +74,13 @@ def main():
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["bf16_tflops_sustained"] \
         if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 1400.0
     tf = 2.0 * M_SDF_HEAD * res ** 3 / (ms * 1e-3) / 1e12
-    print(json.dumps({"workload": f"extract_fields {res}^3 SDF sweep (bf16 fused chain)", "device_ms": ms,
+    return {"workload": f"extract_fields {res}^3 SDF sweep (bf16 fused chain)", "device_ms": ms,
                       "end_to_end_s_with_d2h": wall, "points": res ** 3, "Mpts_per_s": res ** 3 / ms / 1e3,
                       "tflops": tf, "frac_of_tensor_peak": tf / peak, "inside_fraction": float((uh < 1.0).mean()),
                       "marching_cubes": mc,
                       "eval_render": {"rays": R, "ms": ms_eval, "rays_per_s": R / ms_eval * 1e3,
-                                      "outputs": "ray_rgb, depth, normal, acc, color_bkgr, color_spec (is_train=False)"}}))
+                                      "outputs": "ray_rgb, depth, normal, acc, color_bkgr, color_spec (is_train=False)"}}
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 512)))
