@@ -295,6 +295,15 @@ def profile_step(train_step, inputs, ops, torch):
         print(f"[profile] {ms:8.3f} ms {n:4d}x  {key} {gbs}", file=sys.stderr)
 
 
+def two_phase_fns(net, anneal):
+    """Callbacks that let the trainer know the step's global inner-sample count before differentiating a chunk (exact
+    eikonal mean for chunked / sharded steps, nu_nerf_b200/dist.py)."""
+    return {"sample_fn": lambda o, d, n_, f_, st: net.sample_ray(o, d, n_, f_, net.cfg["perturb"]),
+            "core_fn": lambda o, d, z, st: net.render_core(o, d, z, None, cos_anneal_ratio=anneal, step=st, is_train=True,
+                                                           is_nerf=True),
+            "count_fn": lambda o, d, z: net.count_inner(o, d, z)}
+
+
 def stage1_quick(args, torch, dist, dev, precision, R, steps, world=1, rank=0):
     """A short measurement of the stage-1 training step at another precision / batch size (sub-records of the line)."""
     from nu_nerf_b200 import dist as nd
@@ -309,7 +318,7 @@ def stage1_quick(args, torch, dist, dev, precision, R, steps, world=1, rank=0):
     trainer = nd.DataParallelTrainer(net, lambda o, d, n_, f_, st: net.render(o, d, n_, f_, None, -1, anneal, is_train=True,
                                                                              step=st, is_nerf=True),
                                      net.compute_rgb_loss, lr_fn=lambda s_: lr_at(s_), eikonal_weight=EIK_W,
-                                     occ_loss_step=cfg["occ_loss_step"])
+                                     occ_loss_step=cfg["occ_loss_step"], **two_phase_fns(net, anneal))
     o_all, d_all = syn.synthetic_rays(R * world, seed=1)
     gt_all = syn.synthetic_targets(R * world, seed=3)
     sel = nd.shard_batch(torch.arange(R * world), rank, world)
@@ -398,7 +407,7 @@ def run_ours(args):
         return net.render(o, d, near_, far_, None, -1, anneal, is_train=True, step=step, is_nerf=True)
     # the product's ray-sharded trainer: global-denominator losses, one all-reduce of the flat gradient, CUDA Adam
     trainer = nd.DataParallelTrainer(net, render_fn, net.compute_rgb_loss, lr_fn=lambda s: lr_at(s), eikonal_weight=EIK_W,
-                                     occ_loss_step=cfg["occ_loss_step"])
+                                     occ_loss_step=cfg["occ_loss_step"], **two_phase_fns(net, anneal))
     flat = trainer.fp.flat
     # rays: the same generator on every rank, rank-strided slices of one global batch
     o_all, d_all = orc.synthetic_rays(R * world, seed=1)
@@ -488,7 +497,13 @@ def run_ours(args):
     n_in, n_out = stats["n_in"], chunk * 160 - stats["n_in"]
     flops_step = (R / chunk) * (2.0 * chunk * 112 * M_SDF_HEAD + n_in * 2.0 * (3 * M_SDF + 3 * M_SDF_HEAD + 3 * M_COL)
                                 + n_out * 2.0 * 3 * M_NERF + chunk * 2.0 * 3 * M_OL)
+    sub4096 = None
+    if world > 1 and R != 4096 and not args.no_subrecords:
+        # the 4096-ray batch of config 2 on the same N GPUs, kept beside the config-3 headline (a collective measurement:
+        # every rank takes part before the non-zero ranks leave)
+        sub4096 = stage1_quick(args, torch, dist, dev, "bf16", 4096, steps=max(3, args.steps // 2), world=world, rank=rank)
     if rank != 0:
+        dist.destroy_process_group()
         return
     value = R * world / (ms * 1e-3)
     h2d = int(o_h.numel() + d_h.numel() + gt_h.numel()) * 4
@@ -521,10 +536,8 @@ def run_ours(args):
     }
     if world == 1 and not args.no_subrecords:
         line["configs"] = sub_records(args, torch, dev, hbm, tf_sus)
-    if world > 1 and R != 4096 and not args.no_subrecords:
-        # the 4096-ray batch of config 2 on the same N GPUs, kept beside the config-3 headline
-        sub = stage1_quick(args, torch, dist, dev, "bf16", 4096, steps=max(3, args.steps // 2), world=world, rank=rank)
-        line["configs"] = {"config2_rays4096": sub}
+    if sub4096 is not None:
+        line["configs"] = {"config2_rays4096": sub4096}
     if world == 1 and not args.no_cpu_baseline:
         Rc = args.cpu_rays
         step, kind = cpu_step_fn(Rc)

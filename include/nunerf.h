@@ -153,6 +153,10 @@ int nunerf_merge_sdf(const float* sdf, const float* sdf_new, const int32_t* perm
 int nunerf_probe_weights(const float* z, const float* sdf, int P, int n, const float* inv_s_dev, int n_new,
                          const float* u_tab, float* z_new, float* wsum, void* stream);
 
+/* ray_inner[r] = number of samples of ray r whose mid-point lies inside the unit sphere (ZT:730-741: the inner mask of
+ * render_core), computed by the geometry code of nunerf_render_geometry without the compaction.  S <= 160. */
+int nunerf_inner_counts(const float* o, const float* d, const float* z, int R, int S, int32_t* ray_inner, void* stream);
+
 /* ------------------------------------------------------------------ render_core geometry + compositing
  * nunerf_render_geometry (ZT:730-741): dists, mid points, inner mask and the row-major compaction of the
  *   inner / outer sample sets (the order of the reference's boolean-mask indexing): slot[R*S] >= 0 -> index in

@@ -799,6 +799,17 @@ extern "C" int nunerf_render_geometry(const float* o, const float* d, const floa
   return 0;
 }
 
+// per-ray number of samples inside the unit sphere (the same geometry code as nunerf_render_geometry, no compaction): lets
+// a chunked / sharded trainer know the global eikonal denominator before any chunk is differentiated
+extern "C" int nunerf_inner_counts(const float* o, const float* d, const float* z, int R, int S, int32_t* ray_inner,
+                                   void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  NUNERF_REQUIRE(o && d && z && ray_inner && R > 0 && S >= 2 && S <= 160, "inner_counts: bad arguments");
+  geometry_count_kernel<5><<<cdiv(R, GT), 32 * GT, 0, stream>>>(o, d, z, R, S, ray_inner);
+  NUNERF_CHECK_LAUNCH("geometry_count_kernel");
+  return 0;
+}
+
 extern "C" int nunerf_composite_fwd(const float* alpha_in, const float* color_in, const float* alpha_out,
                                     const float* color_out, const int32_t* slot, int R, int S, int is_nerf, float* rgb,
                                     float* rgb_raw, float* acc, float* rgb_bkgr, float* weights,

@@ -97,7 +97,7 @@ def global_count(n_local, device, group=None):
 
 
 def stage1_loss(out, loss_rgb, r_global, group=None, eikonal_weight=0.1, step=0, occ_loss_step=None,
-                outer_reg_weight=0.5, share=1.0):
+                outer_reg_weight=0.5, share=1.0, n_in_global=None):
     """Trainer loss (trainer_zero.py:157-161 over the loss.py adapters of spherepot.yaml) with global denominators.
     `out` is the renderer's outputs dict of THIS rank (or of one chunk of its rays: `share` = the chunk's fraction of
     the rank's rays), `loss_rgb` [R_chunk]; returns the local share whose SUM over ranks (and chunks) is the global
@@ -107,10 +107,15 @@ def stage1_loss(out, loss_rgb, r_global, group=None, eikonal_weight=0.1, step=0,
     loss = loss_rgb.sum() / r_global
     gerr = out["gradient_error"]
     has_inner = "transmission" in out            # the reference emits a zeros(1) placeholder when no sample is inside
-    # every rank takes part in the count all-reduce, also the ones without inner samples
-    n_in = global_count(gerr.shape[0] if has_inner else 0, dev, group)
-    if has_inner:
-        loss = loss + eikonal_weight * share * gerr.sum() / torch.clamp(n_in, min=1.0)
+    if n_in_global is not None:
+        # the caller knows the number of inner samples of the WHOLE step (all chunks, all ranks): exact global mean
+        if has_inner:
+            loss = loss + eikonal_weight * gerr.sum() / torch.clamp(n_in_global, min=1.0)
+    else:
+        # every rank takes part in the count all-reduce, also the ones without inner samples
+        n_in = global_count(gerr.shape[0] if has_inner else 0, dev, group)
+        if has_inner:
+            loss = loss + eikonal_weight * share * gerr.sum() / torch.clamp(n_in, min=1.0)
     if occ_loss_step is not None and step >= occ_loss_step:
         # OccLoss (loss.py:97-98) is a mean over the probed samples of one rank; ranks (and chunks) are averaged
         loss = loss + share * out["loss_occ"].mean() / world
@@ -134,9 +139,16 @@ class DataParallelTrainer:
     """
 
     def __init__(self, module, render_fn, rgb_loss_fn, adam_fn=cuda_adam, lr_fn=warm_up_cos_lr, group=None,
-                 eikonal_weight=0.1, occ_loss_step=None):
+                 eikonal_weight=0.1, occ_loss_step=None, sample_fn=None, core_fn=None, count_fn=None):
+        """sample_fn(rays_o, rays_d, near, far, step) -> z_vals; count_fn(rays_o, rays_d, z_vals) -> number of inner samples
+        (a 0-d device tensor); core_fn(rays_o, rays_d, z_vals, step) -> outputs dict.  When the three are given and a step
+        is split into several chunks, the step runs in two phases -- sample every chunk and count its inner samples
+        (no gradient), all-reduce the total once, then render / differentiate chunk by chunk with the eikonal term divided
+        by that GLOBAL count -- so that chunking does not change the loss (without them the eikonal mean of a chunked step
+        is the ray-share weighted mean of per-chunk means)."""
         self.fp = FlatParameters(module)
         self.render_fn, self.rgb_loss_fn, self.adam_fn, self.lr_fn = render_fn, rgb_loss_fn, adam_fn, lr_fn
+        self.sample_fn, self.core_fn, self.count_fn = sample_fn, core_fn, count_fn
         self.group = group
         self.eikonal_weight, self.occ_loss_step = eikonal_weight, occ_loss_step
         self.last = {}
@@ -148,17 +160,32 @@ class DataParallelTrainer:
         chunk = r_local if chunk is None else min(chunk, r_local)
         self.fp.zero_grad()
         total = torch.zeros((), device=rays_o.device)
-        for c0 in range(0, r_local, chunk):
-            sl = slice(c0, min(r_local, c0 + chunk))
-            out = self.render_fn(rays_o[sl], rays_d[sl], near[sl], far[sl], step)
+        slices = [slice(c0, min(r_local, c0 + chunk)) for c0 in range(0, r_local, chunk)]
+        two_phase = len(slices) > 1 and self.sample_fn is not None and self.core_fn is not None and self.count_fn is not None
+        zs, n_in_global = None, None
+        if two_phase:
+            with torch.no_grad():
+                zs = [self.sample_fn(rays_o[sl], rays_d[sl], near[sl], far[sl], step) for sl in slices]
+                n_loc = torch.stack([self.count_fn(rays_o[sl], rays_d[sl], z) for sl, z in zip(slices, zs)]).sum().float()
+            n_in_global = n_loc.reshape(1).clone()
+            if world > 1:
+                dist.all_reduce(n_in_global, group=self.group)
+            n_in_global = n_in_global[0]
+        n_in_seen = 0
+        for ci, sl in enumerate(slices):
+            if two_phase:
+                out = self.core_fn(rays_o[sl], rays_d[sl], zs[ci], step)
+            else:
+                out = self.render_fn(rays_o[sl], rays_d[sl], near[sl], far[sl], step)
             loss_rgb = self.rgb_loss_fn(out["ray_rgb"], rgbs[sl])
-            # with chunk < R_local the eikonal mean becomes the ray-share weighted mean of per-chunk means
             share = (sl.stop - sl.start) / r_local
             loss = stage1_loss(out, loss_rgb, r_global, self.group, self.eikonal_weight, step, self.occ_loss_step,
-                               share=share)
+                               share=share, n_in_global=n_in_global)
             loss.backward()
             total = total + loss.detach()
+            n_in_seen += int(out["gradient_error"].shape[0]) if "transmission" in out else 0
             self.last = {"n_in": int(out["gradient_error"].shape[0]) if "transmission" in out else 0}
+        self.last["n_in_step"] = n_in_seen
         all_reduce_gradients(self.fp, self.group)
         self.adam_fn(self.fp, self.lr_fn(step))
         return total

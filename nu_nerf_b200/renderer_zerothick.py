@@ -261,6 +261,18 @@ class NeROShapeRenderer(nn.Module):
         return eng.sample_ray(w.sdf, w.inv_s, w.planes, rays_o, rays_d, near, far, perturb > 0, U0, U1, sphere=sphere,
                               trace=trace)
 
+    @torch.no_grad()
+    def count_inner(self, rays_o, rays_d, z_vals):
+        """Number of samples whose mid-point lies inside the unit sphere (the inner mask of render_core, ZT:730-741) as a
+        0-d device tensor, without rendering: the length `gradient_error` WILL have.  A chunked / ray-sharded trainer
+        needs it before any chunk is differentiated (nu_nerf_b200/dist.py)."""
+        eng = _engine()
+        R, S = z_vals.shape
+        counts = torch.empty(R, dtype=torch.int32, device=z_vals.device)
+        eng.call("nunerf_inner_counts", rays_o.contiguous().float().data_ptr(), rays_d.contiguous().float().data_ptr(),
+                 z_vals.contiguous().float().data_ptr(), R, S, counts.data_ptr())
+        return counts.sum()
+
     # ------------------------------------------------------------------ ZT:725-820
     def render_core(self, rays_o, rays_d, z_vals, human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True,
                     is_nerf=False, prepared=None, occ_perm=None):
