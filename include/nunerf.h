@@ -157,6 +157,17 @@ int nunerf_probe_weights(const float* z, const float* sdf, int P, int n, const f
  * render_core), computed by the geometry code of nunerf_render_geometry without the compaction.  S <= 160. */
 int nunerf_inner_counts(const float* o, const float* d, const float* z, int R, int S, int32_t* ray_inner, void* stream);
 
+/* Stage-2 per-segment compositing in linear colour (ZT:1942-1951) on dense rows alpha[N,S], sRGB colour[N,S,3], S <= 256:
+ *   rgb_lin[N,3] = sum_j alpha_j prod_{i<j}(1 - alpha_i + 1e-7) srgb_to_linear(colour_j),  t_end[N] = prod_j(1 - alpha_j + 1e-7)
+ * and the backward w.r.t. alpha / colour given dL/d rgb_lin and dL/d t_end (the transmittance is recomputed). */
+int nunerf_seg_composite_fwd(const float* alpha, const float* color, int N, int S, float* rgb_lin, float* t_end, void* stream);
+int nunerf_seg_composite_bwd(const float* alpha, const float* color, int N, int S, const float* g_rgb, const float* g_t,
+                             float* d_alpha, float* d_color, void* stream);
+/* NeRF-guided importance sampling of the rays that leave the scene (upsample_nerf + cat_z_vals_nerf, ZT:1367-1397):
+ * z_merged[R, n + n_new] = sorted merge of z[R,n] with sample_pdf(z, (alpha T)[:, :-1], n_new, det); n <= 256, n_new <= 64 */
+int nunerf_alpha_importance(const float* z, const float* alpha, int R, int n, int n_new, const float* u_tab,
+                            float* z_merged, void* stream);
+
 /* ------------------------------------------------------------------ render_core geometry + compositing
  * nunerf_render_geometry (ZT:730-741): dists, mid points, inner mask and the row-major compaction of the
  *   inner / outer sample sets (the order of the reference's boolean-mask indexing): slot[R*S] >= 0 -> index in

@@ -107,6 +107,9 @@ _SIGS = {
     "nunerf_probe_weights": [vp, vp, ci, ci, vp, ci, vp, vp, vp, vp],
     "nunerf_render_geometry": [vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "nunerf_inner_counts": [vp, vp, vp, ci, ci, vp, vp],
+    "nunerf_seg_composite_fwd": [vp, vp, ci, ci, vp, vp, vp],
+    "nunerf_seg_composite_bwd": [vp, vp, ci, ci, vp, vp, vp, vp, vp],
+    "nunerf_alpha_importance": [vp, vp, ci, ci, ci, vp, vp, vp],
     "nunerf_composite_fwd": [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp],
     "nunerf_composite_bwd": [vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "nunerf_scatter_rows": [vp, ci, ci, vp, vp, vp],

@@ -753,6 +753,112 @@ __global__ void __launch_bounds__(32 * GT) geometry_count_kernel(const float* __
   if (lane == 0) ray_inner[r] = n_in;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stage-2 per-segment compositing in LINEAR colour (ZT:1942-1951): dense rows alpha[N,S], sRGB colour[N,S,3], S <= 256.
+//   w_j = alpha_j prod_{i<j}(1 - alpha_i + 1e-7);   rgb_lin = sum_j w_j srgb_to_linear(c_j);   T_end = prod_j(1 - alpha_j + 1e-7)
+// One warp per ray, sample j in lane j & 31 of block j >> 5 (coalesced rows); the backward recomputes the transmittance
+// with the same scans instead of reading a stored copy.
+__device__ __forceinline__ float srgb_to_linear_f(float x) {        // utils/raw_utils.py:21-27
+  const float eps = 1.1920928955078125e-07f;
+  return x <= 0.04045f ? (25.0f / 323.0f) * x : powf(fmaxf((200.0f * x + 11.0f) / 211.0f, eps), 12.0f / 5.0f);
+}
+__device__ __forceinline__ float srgb_to_linear_df(float x) {
+  const float eps = 1.1920928955078125e-07f;
+  if (x <= 0.04045f) return 25.0f / 323.0f;
+  const float b = (200.0f * x + 11.0f) / 211.0f;
+  return b < eps ? 0.0f : (12.0f / 5.0f) * powf(b, 7.0f / 5.0f) * (200.0f / 211.0f);
+}
+
+constexpr int SEG_NBLK = 8;
+
+__global__ void __launch_bounds__(32 * WPB) seg_composite_fwd_kernel(const float* __restrict__ alpha,
+                                                                    const float* __restrict__ color, int N, int S,
+                                                                    float* __restrict__ rgb_lin, float* __restrict__ t_end) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const float* a_row = alpha + (long long)r * S;
+  const float* c_row = color + (long long)r * S * 3;
+  float carry = 1.0f, acc[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < SEG_NBLK; ++k) {
+    if (k * 32 >= S) break;
+    const int j = lane + 32 * k;
+    const bool ok = j < S;
+    const float a = ok ? a_row[j] : 0.0f;
+    const float incl = scan_mul32(ok ? 1.0f - a + 1e-7f : 1.0f, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float w = a * carry * excl;
+    carry *= __shfl_sync(FULL, incl, 31);
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] = fmaf(w, srgb_to_linear_f(c_row[3 * j + c]), acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+    rgb_lin[3 * r] = acc[0]; rgb_lin[3 * r + 1] = acc[1]; rgb_lin[3 * r + 2] = acc[2];
+    t_end[r] = carry;
+  }
+}
+
+__global__ void __launch_bounds__(32 * WPB) seg_composite_bwd_kernel(const float* __restrict__ alpha,
+                                                                    const float* __restrict__ color, int N, int S,
+                                                                    const float* __restrict__ g_rgb,
+                                                                    const float* __restrict__ g_t,
+                                                                    float* __restrict__ d_alpha, float* __restrict__ d_color) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * WPB + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const float* a_row = alpha + (long long)r * S;
+  const float* c_row = color + (long long)r * S * 3;
+  const float g[3] = {g_rgb[3 * r], g_rgb[3 * r + 1], g_rgb[3 * r + 2]};
+  float av[SEG_NBLK], Tv[SEG_NBLK], sv[SEG_NBLK], qin[SEG_NBLK];
+  float carry = 1.0f;
+#pragma unroll
+  for (int k = 0; k < SEG_NBLK; ++k) {
+    av[k] = 0.f; Tv[k] = 0.f; sv[k] = 0.f; qin[k] = 0.f;
+    if (k * 32 >= S) continue;
+    const int j = lane + 32 * k;
+    const bool ok = j < S;
+    const float a = ok ? a_row[j] : 0.0f;
+    const float incl = scan_mul32(ok ? 1.0f - a + 1e-7f : 1.0f, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = carry * excl;
+    carry *= __shfl_sync(FULL, incl, 31);
+    float s = 0.0f;                                   // d L / d w_j = <srgb_to_linear(c_j), g>
+    if (ok) {
+      const float w = a * T;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float cs = c_row[3 * j + c];
+        s = fmaf(srgb_to_linear_f(cs), g[c], s);
+        d_color[((long long)r * S + j) * 3 + c] = w * g[c] * srgb_to_linear_df(cs);
+      }
+    }
+    av[k] = a; Tv[k] = T; sv[k] = s;
+    qin[k] = ok ? a * T * s : 0.0f;                    // q_j = w_j s_j
+  }
+  // exclusive SUFFIX sums of q, accumulated from the far end (a prefix-sum difference would cancel catastrophically
+  // behind an opaque sample, where it is divided by 1 - alpha ~ 1e-4)
+  const float gt_end = g_t[r] * carry;
+  float carry_rev = 0.0f;
+#pragma unroll
+  for (int k = SEG_NBLK - 1; k >= 0; --k) {
+    if (k * 32 >= S) continue;
+    const int j = lane + 32 * k;
+    const float incl = scan_add32_rev(qin[k], lane);
+    const float suffix = carry_rev + (incl - qin[k]);
+    carry_rev += __shfl_sync(FULL, incl, 0);
+    if (j < S)       // d/d alpha_j: T_j s_j - (sum_{i>j} w_i s_i + g_T T_end) / (1 - alpha_j + 1e-7)
+      d_alpha[(long long)r * S + j] = Tv[k] * sv[k] - (suffix + gt_end) / (1.0f - av[k] + 1e-7f);
+  }
+}
+
 __global__ void scatter_rows_kernel(const float* __restrict__ src, long long M, int C, const int32_t* __restrict__ id,
                                     float* dst) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -807,6 +913,24 @@ extern "C" int nunerf_inner_counts(const float* o, const float* d, const float* 
   NUNERF_REQUIRE(o && d && z && ray_inner && R > 0 && S >= 2 && S <= 160, "inner_counts: bad arguments");
   geometry_count_kernel<5><<<cdiv(R, GT), 32 * GT, 0, stream>>>(o, d, z, R, S, ray_inner);
   NUNERF_CHECK_LAUNCH("geometry_count_kernel");
+  return 0;
+}
+
+// stage-2 segment compositing (ZT:1942-1951): rgb_lin[N,3] = sum_j w_j srgb_to_linear(colour_j), t_end[N] = prod_j(1 - alpha_j + 1e-7)
+extern "C" int nunerf_seg_composite_fwd(const float* alpha, const float* color, int N, int S, float* rgb_lin, float* t_end,
+                                        void* stream) {
+  NUNERF_REQUIRE(alpha && color && rgb_lin && t_end && N > 0 && S > 0 && S <= 32 * SEG_NBLK, "seg_composite_fwd: bad arguments");
+  seg_composite_fwd_kernel<<<cdiv(N, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(alpha, color, N, S, rgb_lin, t_end);
+  NUNERF_CHECK_LAUNCH("seg_composite_fwd_kernel");
+  return 0;
+}
+// its backward: g_rgb[N,3] = dL/d rgb_lin, g_t[N] = dL/d t_end -> d_alpha[N,S], d_color[N,S,3] (transmittance recomputed)
+extern "C" int nunerf_seg_composite_bwd(const float* alpha, const float* color, int N, int S, const float* g_rgb,
+                                        const float* g_t, float* d_alpha, float* d_color, void* stream) {
+  NUNERF_REQUIRE(alpha && color && g_rgb && g_t && d_alpha && d_color && N > 0 && S > 0 && S <= 32 * SEG_NBLK,
+                 "seg_composite_bwd: bad arguments");
+  seg_composite_bwd_kernel<<<cdiv(N, WPB), 32 * WPB, 0, (cudaStream_t)stream>>>(alpha, color, N, S, g_rgb, g_t, d_alpha, d_color);
+  NUNERF_CHECK_LAUNCH("seg_composite_bwd_kernel");
   return 0;
 }
 

@@ -222,6 +222,87 @@ __global__ void upsample_kernel(const float* __restrict__ o, const float* __rest
   }
 }
 
+
+// NeRF-guided importance sampling of the stage-2 miss rays (upsample_nerf + cat_z_vals_nerf, ZT:1367-1397, called at
+// ZT:1762-1799): weights_j = alpha_j prod_{i<j}(1 - alpha_i + 1e-7) over the n samples, sample_pdf(z, weights[:-1], n_new,
+// det) (field.py:468-498) and the sorted merge of z with the new samples.  One warp per ray, n <= 32 NBLK, n_new <= 64.
+// Same fixed scan order / explicitly rounded fp32 arithmetic as upsample_kernel.
+template <int NBLK>
+__global__ void alpha_importance_kernel(const float* __restrict__ z, const float* __restrict__ alpha, int R, int n, int n_new,
+                                        const float* __restrict__ u_tab, float* __restrict__ z_merged) {
+  __shared__ float s_z[WARPS_PER_BLOCK][32 * NBLK];
+  __shared__ float s_cdf[WARPS_PER_BLOCK][32 * NBLK + 4];
+  __shared__ float s_new[WARPS_PER_BLOCK][64];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = blockIdx.x * WARPS_PER_BLOCK + w;
+  if (r >= R) return;
+  float zv[NBLK], wgt[NBLK];
+  float carryT = 1.0f, lane_sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int j = lane + 32 * k;
+    const bool ok = j < n;
+    zv[k] = ok ? z[(long long)r * n + j] : 0.f;
+    const float a = ok ? alpha[(long long)r * n + j] : 0.f;
+    if (ok) s_z[w][j] = zv[k];
+    const float incl = hs_scan_mul(ok ? det_add(det_sub(1.0f, a), 1e-7f) : 1.0f, lane);
+    float excl = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    const float T = det_mul(carryT, excl);
+    carryT = det_mul(carryT, __shfl_sync(FULL, incl, 31));
+    wgt[k] = (j < n - 1) ? det_add(det_mul(a, T), 1e-5f) : 0.f;       // weights[:, :-1] + 1e-5 (field.py:471)
+    lane_sum = det_add(lane_sum, wgt[k]);
+  }
+  const float total = xor_reduce_add(lane_sum);
+  float carryC = 0.f;
+  if (lane == 0) s_cdf[w][0] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int j = lane + 32 * k;
+    const float pdf = (j < n - 1) ? det_div(wgt[k], total) : 0.f;
+    const float c = det_add(carryC, hs_scan_add(pdf, lane));
+    carryC = __shfl_sync(FULL, c, 31);
+    if (j < n - 1) s_cdf[w][j + 1] = c;
+  }
+  __syncwarp();
+  for (int t = lane; t < n_new; t += 32) {
+    const float u = u_tab[t];
+    int lo = 0, hi = n;                         // first index with cdf > u (searchsorted right=True) over the n cdf entries
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (s_cdf[w][m] <= u) lo = m + 1; else hi = m;
+    }
+    const int below = lo - 1 < 0 ? 0 : lo - 1, above = lo > n - 1 ? n - 1 : lo;
+    const float c0 = s_cdf[w][below], c1 = s_cdf[w][above];
+    const float b0 = s_z[w][below], b1 = s_z[w][above];
+    float den = det_sub(c1, c0);
+    if (den < 1e-5f) den = 1.0f;
+    s_new[w][t] = det_add(b0, det_mul(det_div(det_sub(u, c0), den), det_sub(b1, b0)));
+  }
+  __syncwarp();
+  // sorted merge (values only): old sample j moves up by the number of new samples below it, new sample t by the number of
+  // old samples <= it (both sequences are non-decreasing)
+  const int nm = n + n_new;
+#pragma unroll
+  for (int k = 0; k < NBLK; ++k) {
+    const int j = lane + 32 * k;
+    if (j < n) {
+      int cnt = 0;
+      for (int t = 0; t < n_new; ++t) cnt += (s_new[w][t] < zv[k]) ? 1 : 0;
+      z_merged[(long long)r * nm + j + cnt] = zv[k];
+    }
+  }
+  for (int t = lane; t < n_new; t += 32) {
+    const float zs = s_new[w][t];
+    int lo = 0, hi = n;
+    while (lo < hi) {
+      const int m = (lo + hi) >> 1;
+      if (s_z[w][m] <= zs) lo = m + 1; else hi = m;
+    }
+    z_merged[(long long)r * nm + t + lo] = zs;
+  }
+}
+
 // Occlusion probe (get_weights + sample_pdf of get_intersection, field.py:501-554): one warp per probe ray with n <= 64
 // samples z / sdf.  weights_j = alpha_j * prod_{k<j}(1 - alpha_k + 1e-7) with alpha from the logistic CDF at the section
 // ends, zeroed where the SDF does not decrease (surface_mask).  Either inverts the CDF of (weights + 1e-5) at n_new
@@ -359,6 +440,20 @@ extern "C" int nunerf_upsample(const float* o, const float* d, const float* z, c
   else
     upsample_kernel<4><<<grid, block, 0, st>>>(o, d, z, sdf, R, n, n_new, inv_s_dev, inv_s_cap, u_tab, z_new, inds, z_merged, perm);
   NUNERF_CHECK_LAUNCH("upsample_kernel");
+  return 0;
+}
+
+// z_merged[R, n + n_new] = sort(cat(z, sample_pdf(z, (alpha T)[:-1], n_new)))  (ZT:1367-1397); u_tab[n_new] = the det. u's
+extern "C" int nunerf_alpha_importance(const float* z, const float* alpha, int R, int n, int n_new, const float* u_tab,
+                                       float* z_merged, void* stream) {
+  NUNERF_REQUIRE(z && alpha && u_tab && z_merged && R > 0 && n >= 2 && n <= 256 && n_new >= 1 && n_new <= 64,
+                 "alpha_importance: need 2 <= n <= 256, 1 <= n_new <= 64");
+  const dim3 grid(cdiv(R, WARPS_PER_BLOCK)), block(32 * WARPS_PER_BLOCK);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 128) alpha_importance_kernel<4><<<grid, block, 0, st>>>(z, alpha, R, n, n_new, u_tab, z_merged);
+  else if (n <= 192) alpha_importance_kernel<6><<<grid, block, 0, st>>>(z, alpha, R, n, n_new, u_tab, z_merged);
+  else alpha_importance_kernel<8><<<grid, block, 0, st>>>(z, alpha, R, n, n_new, u_tab, z_merged);
+  NUNERF_CHECK_LAUNCH("alpha_importance_kernel");
   return 0;
 }
 

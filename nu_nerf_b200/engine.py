@@ -852,20 +852,45 @@ def nerf_alpha(w: NerfW, pts, dirs, dists, planes):
 @torch.no_grad()
 def importance_merge(z, alpha, n_new):
     """upsample_nerf + cat_z_vals_nerf (ZT:1367-1397): weights = alpha * T, sample_pdf(z, weights[:, :-1], n_new, det),
-    sorted merge.  Only the rays that miss the outer mesh take this path ([R_miss, 192] tensors): torch glue."""
-    T = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-7], -1), -1)[:, :-1]
-    w = (alpha * T)[:, :-1] + 1e-5
-    pdf = w / torch.sum(w, -1, keepdim=True)
-    cdf = torch.cat([torch.zeros_like(pdf[:, :1]), torch.cumsum(pdf, -1)], -1)
-    u = torch.linspace(0.5 / n_new, 1.0 - 0.5 / n_new, n_new, device=z.device).expand(cdf.shape[0], n_new).contiguous()
-    inds = torch.searchsorted(cdf, u, right=True)
-    lo, hi = torch.clamp(inds - 1, min=0), torch.clamp(inds, max=cdf.shape[-1] - 1)
-    c0, c1 = torch.gather(cdf, 1, lo), torch.gather(cdf, 1, hi)
-    b0, b1 = torch.gather(z, 1, lo), torch.gather(z, 1, hi)
-    den = c1 - c0
-    den = torch.where(den < 1e-5, torch.ones_like(den), den)
-    z_new = b0 + (u - c0) / den * (b1 - b0)
-    return torch.sort(torch.cat([z, z_new], -1), dim=-1)[0].contiguous()
+    sorted merge -- one launch of `alpha_importance_kernel` (csrc/sampling.cu) on the [R_miss, n] rows."""
+    R, n = z.shape
+    dev = z.device
+    _, utabs = _tables(dev)
+    if n_new not in utabs:
+        utabs[n_new] = torch.linspace(0.5 / n_new, 1.0 - 0.5 / n_new, n_new).to(dev)
+    out = _f(R, n + n_new, dev=dev)
+    if R > 0:
+        call("nunerf_alpha_importance", z.contiguous().float().data_ptr(), alpha.contiguous().float().data_ptr(), R, n, n_new,
+             utabs[n_new].data_ptr(), out.data_ptr())
+    return out
+
+
+class SegCompositeFn(torch.autograd.Function):
+    """Stage-2 per-segment compositing in linear colour (ZT:1942-1951) on dense [N, S] rows:
+    (alpha [N,S], sRGB colour [N,S,3]) -> (rgb_lin [N,3] = sum_j w_j srgb_to_linear(c_j), t_end [N] = prod_j(1 - alpha_j + 1e-7)).
+    Forward and backward are one kernel each (csrc/composite.cu); the backward recomputes the transmittance."""
+
+    @staticmethod
+    def forward(ctx, alpha, color):
+        N, S = alpha.shape
+        a, c = alpha.contiguous().float(), color.contiguous().float()
+        rgb, t_end = _f(N, 3, dev=a.device), _f(N, dev=a.device)
+        if N > 0:
+            call("nunerf_seg_composite_fwd", a.data_ptr(), c.data_ptr(), N, S, rgb.data_ptr(), t_end.data_ptr())
+        ctx.save_for_backward(a, c)
+        return rgb, t_end
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_t):
+        a, c = ctx.saved_tensors
+        N, S = a.shape
+        da, dc = _f(N, S, dev=a.device), _f(N, S, 3, dev=a.device)
+        if N > 0:
+            g_rgb = (torch.zeros(N, 3, device=a.device) if g_rgb is None else g_rgb).contiguous().float()
+            g_t = (torch.zeros(N, device=a.device) if g_t is None else g_t).contiguous().float()
+            call("nunerf_seg_composite_bwd", a.data_ptr(), c.data_ptr(), N, S, g_rgb.data_ptr(), g_t.data_ptr(),
+                 da.data_ptr(), dc.data_ptr())
+        return da, dc
 
 
 def _srgb_to_linear(x):

@@ -377,11 +377,10 @@ class Stage2Renderer(nn.Module):
                 tmp["std"] = torch.mean(1.0 / (inv_s_c.detach() if frozen else inv_s_c))
                 tmp["gradient_error"] = gerr
             alpha, color = alpha.view(N, S), color.view(N, S, 3)
-            # linear-space compositing (ZT:1942-1951)
-            Tc = torch.cumprod(torch.cat([torch.ones(N, 1, device=dev), 1.0 - alpha + 1e-7], -1), -1)
-            wts = alpha * Tc[:, :-1]
-            color_now = (srgb_to_linear(color) * wts[..., None]).sum(dim=1) * T
-            T = T * Tc[:, -1:]
+            # linear-space compositing (ZT:1942-1951): one kernel forward, one backward (transmittance recomputed)
+            rgb_lin, t_end = eng.SegCompositeFn.apply(alpha, color)
+            color_now = rgb_lin * T
+            T = T * t_end[:, None]
             n_hit = conv_idx.numel()
             if n_hit > 0:
                 p_hit = cand[conv_idx][:, -1, :].contiguous()
