@@ -209,12 +209,27 @@ int nunerf_sdf_grad_pe(const float* x, const float* ga, int lda, const float* gb
 int nunerf_sdf_grad_pe_bwd(const float* x, const float* dgrad, int M, void* d1, int ld1, int lo1, int col1, int width1,
                            void* d2, int ld2, int lo2, int col2, int width2, void* stream);
 
+/* Input gradients of the encodings (the reference gets them from autograd; stage 2 needs them because the sample
+ * positions depend on IORs_pred through the refracted path, ZT:1633-1684):
+ *   nunerf_pe_bwd      dx[M,d] (+)= J_pe(x)^T (ga + gb) for a d-dimensional input (d <= 4) with nfreq frequencies
+ *   nunerf_sdf_pe_hess dx[M,3] += d_grad . d/dx [J_pe6(x)^T (ga + gb)]: the x-dependence of SDFNetwork.gradient through
+ *                      the Jacobian of the encoding itself (field.py:158-170, create_graph=True)
+ *   nunerf_nerf_prep_bwd backward of (p / |p|, 1 / |p|) and views = -dirs (ZT:688-689) */
+int nunerf_pe_bwd(const float* x, int d, int nfreq, const float* ga, int lda, const float* gb, int ldb, int M, float* dx,
+                  int accumulate, void* stream);
+int nunerf_sdf_pe_hess(const float* x, const float* ga, int lda, const float* gb, int ldb, const float* d_grad, int M,
+                       float* dx, void* stream);
+int nunerf_nerf_prep_bwd(const float* pts, const float* d_pts4, const float* d_views, int M, float* d_pts, float* d_dirs,
+                         void* stream);
+
 /* compute_sdf_alpha ZT:657-685 + eikonal term ZT:769 */
 typedef struct {
   int M; float cos_anneal; const float* inv_s_dev;       /* exp(10*variance), clipped to [1e-6,1e6] in-kernel */
   const float* sdf; int ld_sdf; const float* grad; const float* dists; const float* dirs;
   float* alpha; float* grad_err;
   const float* d_alpha; const float* d_grad_err; float* d_sdf; float* d_grad; float* d_inv_s; /* d_inv_s NULL: frozen */
+  float* d_dists; float* d_dirs;                         /* optional backward outputs [M], [M,3]: d alpha / d (dist, dir) --
+                                                            stage 2, where the sample positions depend on the IoR network */
 } nunerf_sdf_alpha_t;
 int nunerf_sdf_alpha_fwd(const nunerf_sdf_alpha_t* p, void* stream);
 int nunerf_sdf_alpha_bwd(const nunerf_sdf_alpha_t* p, void* stream);
@@ -226,6 +241,10 @@ int nunerf_nerf_out_fwd(const float* sigma, int ld_s, const float* rgb, int ld_c
 int nunerf_nerf_out_bwd(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
                         const float* d_alpha, const float* d_color, void* d_sig, int ld_ds, int lo_ds, int col_ds,
                         void* d_rgb, int ld_dr, int lo_dr, int col_dr, void* stream);
+/* same + d alpha / d dist -> d_dists[M] */
+int nunerf_nerf_out_bwd_geo(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
+                            const float* d_alpha, const float* d_color, void* d_sig, int ld_ds, int lo_ds, int col_ds,
+                            void* d_rgb, int ld_dr, int lo_dr, int col_dr, float* d_dists, void* stream);
 
 /* AppShadingNetwork.forward field.py:684-741: directions + encodings (IDE utils/ref_utils.py:85-114) */
 typedef struct {
@@ -245,6 +264,10 @@ typedef struct {
   float* d_rough_raw; int ld_drough;                         /* accumulated */
   float* refl;                                               /* optional forward output [M,3]: reflected direction
                                                                 (occ_info['reflective'], field.py:688, :744) */
+  /* optional position-gradient part of the backward (stage 2): with d_pts set, d p through PE6(p) of the inner- and
+   * refraction-light inputs is ADDED to d_pts[M,3] and d ray-direction (reflected direction, NoV, PE6(v)) to d_dirs[M,3] */
+  const float* d_x_refrac; int ld_dxr;                       /* fp32 [M, ld] (78 cols used) or NULL */
+  float* d_pts; float* d_dirs;
 } nunerf_shade_encode_t;
 int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* stream);
 /* IDE(x, kinv) of M unit directions at one constant roughness -> planes (per-ray specular probe, ZT:780) */

@@ -52,7 +52,7 @@ class MlpChainT(C.Structure):
 class SdfAlphaT(C.Structure):
     _fields_ = [("M", ci), ("cos_anneal", cf), ("inv_s_dev", vp), ("sdf", vp), ("ld_sdf", ci), ("grad", vp),
                 ("dists", vp), ("dirs", vp), ("alpha", vp), ("grad_err", vp), ("d_alpha", vp), ("d_grad_err", vp),
-                ("d_sdf", vp), ("d_grad", vp), ("d_inv_s", vp)]
+                ("d_sdf", vp), ("d_grad", vp), ("d_inv_s", vp), ("d_dists", vp), ("d_dirs", vp)]
 
 
 class ShadeEncodeT(C.Structure):
@@ -60,7 +60,8 @@ class ShadeEncodeT(C.Structure):
                 ("x_outer", vp), ("ld_outer", ci), ("lo_outer", ci), ("x_inner", vp), ("ld_inner", ci), ("lo_inner", ci),
                 ("x_weight", vp), ("ld_weight", ci), ("lo_weight", ci), ("x_refrac", vp), ("ld_refrac", ci),
                 ("lo_refrac", ci), ("nov", vp), ("d_x_outer", vp), ("ld_dxo", ci), ("d_x_inner", vp), ("ld_dxi", ci),
-                ("d_nov", vp), ("d_grad", vp), ("d_rough_raw", vp), ("ld_drough", ci), ("refl", vp)]
+                ("d_nov", vp), ("d_grad", vp), ("d_rough_raw", vp), ("ld_drough", ci), ("refl", vp),
+                ("d_x_refrac", vp), ("ld_dxr", ci), ("d_pts", vp), ("d_dirs", vp)]
 
 
 class ShadeMixT(C.Structure):
@@ -121,6 +122,10 @@ _SIGS = {
     "nunerf_nerf_prep": [vp, vp, ci, vp, vp, vp],
     "nunerf_nerf_out_fwd": [vp, ci, vp, ci, vp, ci, vp, vp, vp],
     "nunerf_nerf_out_bwd": [vp, ci, vp, ci, vp, ci, vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, vp],
+    "nunerf_nerf_out_bwd_geo": [vp, ci, vp, ci, vp, ci, vp, vp, vp, ci, ci, ci, vp, ci, ci, ci, vp, vp],
+    "nunerf_pe_bwd": [vp, ci, ci, vp, ci, vp, ci, ci, vp, ci, vp],
+    "nunerf_sdf_pe_hess": [vp, vp, ci, vp, ci, vp, ci, vp, vp],
+    "nunerf_nerf_prep_bwd": [vp, vp, vp, ci, vp, vp, vp],
     "nunerf_shade_encode_fwd": [C.POINTER(ShadeEncodeT), vp],
     "nunerf_shade_encode_bwd": [C.POINTER(ShadeEncodeT), vp],
     "nunerf_ide_encode": [vp, ci, cf, vp, ci, ci, ci, vp],

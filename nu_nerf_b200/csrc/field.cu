@@ -125,6 +125,70 @@ __global__ void sdf_grad_pe_bwd_kernel(const float* __restrict__ x, const float*
   if (d2 && j < width2) store_planes(d2, m * ld2 + col2 + j, lo2, v);
 }
 
+// dx[m, c] (+)= [J_pe(x)^T (ga + gb)]_c for a d-dimensional input with F frequencies (d <= 4): the input gradient of any
+// positional encoding (PE-6 of points / directions, PE-10 of the NeRF++ 4-vector, PE-4 of its view direction)
+__global__ void pe_bwd_kernel(const float* __restrict__ x, int d, int F, const float* __restrict__ ga, int lda,
+                              const float* __restrict__ gb, int ldb, long long M, float* dx, int accumulate) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * d) return;
+  const long long m = idx / d;
+  const int c = (int)(idx % d);
+  const int W = d * (1 + 2 * F);
+  const float* a = ga + m * lda;
+  const float* b = gb ? gb + m * ldb : nullptr;
+  const float xc = x[m * d + c];
+  float acc = a[c] + (b ? b[c] : 0.f);
+  for (int k = 0; k < F; ++k) {
+    const float f = (float)(1 << k);
+    float sn, co;
+    sincosf(xc * f, &sn, &co);
+    const int is = pw::pe_index(d, k, 0, c), ic = pw::pe_index(d, k, 1, c);
+    acc += f * (co * (a[is] + (b ? b[is] : 0.f)) - sn * (a[ic] + (b ? b[ic] : 0.f)));
+  }
+  (void)W;
+  dx[idx] = accumulate ? dx[idx] + acc : acc;
+}
+
+// dx[m, c] += d_grad[m, c] * d/dx_c [J_pe(x)^T (ga + gb)]_c  (PE-6 of a 3-vector): the explicit x-dependence of
+// SDFNetwork.gradient through the Jacobian of the encoding (field.py:158-170 differentiated once more)
+__global__ void sdf_pe_hess_kernel(const float* __restrict__ x, const float* __restrict__ ga, int lda,
+                                   const float* __restrict__ gb, int ldb, const float* __restrict__ d_grad, long long M,
+                                   float* dx) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * 3) return;
+  const long long m = idx / 3;
+  const int c = (int)(idx % 3);
+  const float* a = ga + m * lda;
+  const float* b = gb ? gb + m * ldb : nullptr;
+  const float xc = x[idx];
+  float acc = 0.f;
+  for (int k = 0; k < 6; ++k) {
+    const float f = (float)(1 << k);
+    float sn, co;
+    sincosf(xc * f, &sn, &co);
+    const int is = 3 + 6 * k + c, ic = 6 + 6 * k + c;
+    acc -= f * f * (sn * (a[is] + (b ? b[is] : 0.f)) + co * (a[ic] + (b ? b[ic] : 0.f)));
+  }
+  dx[idx] += d_grad[idx] * acc;
+}
+
+// backward of nerf_prep_kernel: pts4 = (p / |p|, 1 / |p|), views = -dirs
+__global__ void nerf_prep_bwd_kernel(const float* __restrict__ pts, const float* __restrict__ d_pts4,
+                                     const float* __restrict__ d_views, long long M, float* d_pts, float* d_dirs) {
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float p[3] = {pts[3 * m], pts[3 * m + 1], pts[3 * m + 2]};
+  const float n = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  const float q[3] = {p[0] / n, p[1] / n, p[2] / n};
+  const float dq[3] = {d_pts4[4 * m], d_pts4[4 * m + 1], d_pts4[4 * m + 2]};
+  const float dw = d_pts4[4 * m + 3];
+  const float qdq = q[0] * dq[0] + q[1] * dq[1] + q[2] * dq[2];
+  for (int c = 0; c < 3; ++c) {
+    d_pts[3 * m + c] = (dq[c] - q[c] * qdq) / n - dw * q[c] / (n * n);
+    d_dirs[3 * m + c] = -d_views[3 * m + c];
+  }
+}
+
 // ------------------------------------------------------------------------------------------- sdf -> alpha
 __global__ void sdf_alpha_fwd_kernel(nunerf_sdf_alpha_t p) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,9 +209,11 @@ __global__ void sdf_alpha_bwd_kernel(nunerf_sdf_alpha_t p) {
     float inv_s = fminf(fmaxf(raw, 1e-6f), 1e6f);
     float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
     float dr[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
-    float dsdf, dg[3];
+    float dsdf, dg[3], ddist, ddir[3];
     pw::sdf_alpha_bwd(p.sdf[m * p.ld_sdf], g, p.dists[m], dr, inv_s, p.cos_anneal, p.d_alpha[m],
-                      p.d_grad_err ? p.d_grad_err[m] : 0.f, &dsdf, dg, &dinv);
+                      p.d_grad_err ? p.d_grad_err[m] : 0.f, &dsdf, dg, &dinv, &ddist, ddir);
+    if (p.d_dists) p.d_dists[m] = ddist;
+    if (p.d_dirs) { p.d_dirs[3 * m] = ddir[0]; p.d_dirs[3 * m + 1] = ddir[1]; p.d_dirs[3 * m + 2] = ddir[2]; }
     if (!(raw >= 1e-6f && raw <= 1e6f)) dinv = 0.f;
     p.d_sdf[m] = dsdf;
     p.d_grad[3 * m] = dg[0]; p.d_grad[3 * m + 1] = dg[1]; p.d_grad[3 * m + 2] = dg[2];
@@ -184,13 +250,14 @@ __global__ void nerf_out_fwd_kernel(const float* __restrict__ sigma, int ld_s, c
 __global__ void nerf_out_bwd_kernel(const float* __restrict__ sigma, int ld_s, const float* __restrict__ rgb, int ld_c,
                                     const float* __restrict__ dists, long long M, const float* __restrict__ d_alpha,
                                     const float* __restrict__ d_color, __nv_bfloat16* d_sig, int ld_ds, int lo_ds,
-                                    int col_ds, __nv_bfloat16* d_rgb, int ld_dr, int lo_dr, int col_dr) {
+                                    int col_ds, __nv_bfloat16* d_rgb, int ld_dr, int lo_dr, int col_dr, float* d_dists) {
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float c[3] = {rgb[m * ld_c], rgb[m * ld_c + 1], rgb[m * ld_c + 2]};
   float dc[3] = {d_color[3 * m], d_color[3 * m + 1], d_color[3 * m + 2]};
-  float ds, drgb[3];
-  pw::nerf_out_bwd(sigma[m * ld_s], c, dists[m], d_alpha[m], dc, &ds, drgb);
+  float ds, drgb[3], dd;
+  pw::nerf_out_bwd(sigma[m * ld_s], c, dists[m], d_alpha[m], dc, &ds, drgb, &dd);
+  if (d_dists) d_dists[m] = dd;
   store_planes(d_sig, m * ld_ds + col_ds, lo_ds, ds);
   for (int k = 0; k < 3; ++k) store_planes(d_rgb, m * ld_dr + col_dr + k, lo_dr, drgb[k]);
 }
@@ -278,7 +345,27 @@ __global__ void shade_encode_bwd_kernel(nunerf_shade_encode_t p) {
   pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], 0.0f, dout, &gx, &gy, &gz, &gk);
   dr[0] += gx; dr[1] += gy; dr[2] += gz;
   float dg[3];
-  pw::shade_dirs_bwd(s, dr, dn, p.d_nov[m], dg);
+  if (p.d_pts) {
+    // position-gradient outputs (stage 2): d p through PE6(p) of both inner-light inputs and of the refraction-light input;
+    // d ray direction through the reflected direction, NoV and PE6(v) of the refraction-light input (the occlusion weight
+    // network sees detached encodings, field.py:657)
+    const float* gi0 = p.d_x_inner + m * p.ld_dxi;
+    const float* gi1 = p.d_x_inner + (M + m) * p.ld_dxi;
+    const float* gr = p.d_x_refrac ? p.d_x_refrac + m * p.ld_dxr : nullptr;
+    float gpe[39];
+    for (int j = 0; j < 39; ++j) gpe[j] = gi0[j] + gi1[j] + (gr ? gr[j] : 0.f);
+    float dvd[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < 3; ++c) {
+      p.d_pts[3 * m + c] += pw::pe_bwd_coord(gpe, 3, 6, c, p.pts[3 * m + c]);
+      if (gr) dvd[c] = pw::pe_bwd_coord(gr + 39, 3, 6, c, s.v[c]);
+    }
+    const float vn = fmaxf(sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]), 1e-12f);
+    float drd[3];
+    pw::shade_dirs_bwd(s, dr, dn, p.d_nov[m], dg, dvd, vn, drd);
+    p.d_dirs[3 * m] += drd[0]; p.d_dirs[3 * m + 1] += drd[1]; p.d_dirs[3 * m + 2] += drd[2];
+  } else {
+    pw::shade_dirs_bwd(s, dr, dn, p.d_nov[m], dg);
+  }
   p.d_grad[3 * m] += dg[0]; p.d_grad[3 * m + 1] += dg[1]; p.d_grad[3 * m + 2] += dg[2];
   p.d_rough_raw[m * p.ld_drough] += drough * rough * (1.0f - rough);
 }
@@ -543,6 +630,29 @@ extern "C" int nunerf_sdf_grad_pe_bwd(const float* x, const float* dgrad, int M,
   return 0;
 }
 
+extern "C" int nunerf_pe_bwd(const float* x, int d, int nfreq, const float* ga, int lda, const float* gb, int ldb, int M,
+                             float* dx, int accumulate, void* stream) {
+  NUNERF_REQUIRE(x && ga && dx && M > 0 && d >= 1 && d <= 4 && nfreq >= 0 && nfreq <= 12 && lda >= d * (1 + 2 * nfreq) &&
+                     (!gb || ldb >= d * (1 + 2 * nfreq)), "pe_bwd: bad arguments");
+  pe_bwd_kernel<<<G1((long long)M * d), 0, ST(stream)>>>(x, d, nfreq, ga, lda, gb, ldb, M, dx, accumulate);
+  NUNERF_CHECK_LAUNCH("pe_bwd_kernel");
+  return 0;
+}
+extern "C" int nunerf_sdf_pe_hess(const float* x, const float* ga, int lda, const float* gb, int ldb, const float* d_grad,
+                                  int M, float* dx, void* stream) {
+  NUNERF_REQUIRE(x && ga && d_grad && dx && M > 0 && lda >= 39 && (!gb || ldb >= 39), "sdf_pe_hess: bad arguments");
+  sdf_pe_hess_kernel<<<G1((long long)M * 3), 0, ST(stream)>>>(x, ga, lda, gb, ldb, d_grad, M, dx);
+  NUNERF_CHECK_LAUNCH("sdf_pe_hess_kernel");
+  return 0;
+}
+extern "C" int nunerf_nerf_prep_bwd(const float* pts, const float* d_pts4, const float* d_views, int M, float* d_pts,
+                                    float* d_dirs, void* stream) {
+  NUNERF_REQUIRE(pts && d_pts4 && d_views && d_pts && d_dirs && M > 0, "nerf_prep_bwd: bad arguments");
+  nerf_prep_bwd_kernel<<<G1(M), 0, ST(stream)>>>(pts, d_pts4, d_views, M, d_pts, d_dirs);
+  NUNERF_CHECK_LAUNCH("nerf_prep_bwd_kernel");
+  return 0;
+}
+
 extern "C" int nunerf_sdf_alpha_fwd(const nunerf_sdf_alpha_t* p, void* stream) {
   NUNERF_REQUIRE(p && p->M > 0 && p->sdf && p->grad && p->dists && p->dirs && p->alpha && p->grad_err && p->inv_s_dev,
                  "sdf_alpha_fwd: bad arguments");
@@ -578,7 +688,19 @@ extern "C" int nunerf_nerf_out_bwd(const float* sigma, int ld_s, const float* rg
   NUNERF_REQUIRE(sigma && rgb && dists && d_alpha && d_color && d_sig && d_rgb && M > 0, "nerf_out_bwd: bad arguments");
   nerf_out_bwd_kernel<<<G1(M), 0, ST(stream)>>>(sigma, ld_s, rgb, ld_c, dists, M, d_alpha, d_color,
                                                (__nv_bfloat16*)d_sig, ld_ds, lo_ds, col_ds, (__nv_bfloat16*)d_rgb, ld_dr,
-                                               lo_dr, col_dr);
+                                               lo_dr, col_dr, nullptr);
+  NUNERF_CHECK_LAUNCH("nerf_out_bwd_kernel");
+  return 0;
+}
+// same, additionally d alpha / d dist -> d_dists[M] (stage 2: the sample spacing depends on the refracted path)
+extern "C" int nunerf_nerf_out_bwd_geo(const float* sigma, int ld_s, const float* rgb, int ld_c, const float* dists, int M,
+                                       const float* d_alpha, const float* d_color, void* d_sig, int ld_ds, int lo_ds,
+                                       int col_ds, void* d_rgb, int ld_dr, int lo_dr, int col_dr, float* d_dists,
+                                       void* stream) {
+  NUNERF_REQUIRE(sigma && rgb && dists && d_alpha && d_color && d_sig && d_rgb && d_dists && M > 0, "nerf_out_bwd_geo: bad arguments");
+  nerf_out_bwd_kernel<<<G1(M), 0, ST(stream)>>>(sigma, ld_s, rgb, ld_c, dists, M, d_alpha, d_color,
+                                               (__nv_bfloat16*)d_sig, ld_ds, lo_ds, col_ds, (__nv_bfloat16*)d_rgb, ld_dr,
+                                               lo_dr, col_dr, d_dists);
   NUNERF_CHECK_LAUNCH("nerf_out_bwd_kernel");
   return 0;
 }
@@ -600,6 +722,7 @@ extern "C" int nunerf_shade_encode_bwd(const nunerf_shade_encode_t* p, void* str
   NUNERF_REQUIRE(p && p->M > 0 && p->grad && p->dirs && p->rough_raw && p->d_x_outer && p->d_x_inner && p->d_nov &&
                      p->d_grad && p->d_rough_raw,
                  "shade_encode_bwd: bad arguments");
+  NUNERF_REQUIRE(!p->d_pts || (p->pts && p->d_dirs), "shade_encode_bwd: d_pts needs pts and d_dirs");
   if (int r = ensure_ide()) return r;
   shade_encode_bwd_kernel<<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
   NUNERF_CHECK_LAUNCH("shade_encode_bwd_kernel");

@@ -126,6 +126,25 @@ PW_HD float srgb_bwd(float x) {
 //   [x (d)] [sin(2^0 x) (d)] [cos(2^0 x) (d)] [sin(2^1 x) (d)] ...
 PW_HD int pe_index(int d, int k, int is_cos, int c) { return d + (2 * k + is_cos) * d + c; }
 
+// J_pe(x)^T g for one coordinate c of a d-dimensional input with F frequencies (layout of pe_index): g points at the PE row
+PW_HD float pe_bwd_coord(const float* g, int d, int F, int c, float xc) {
+  float acc = g[c];
+  for (int k = 0; k < F; ++k) {
+    float f = (float)(1 << k), sn = sinf(xc * f), co = cosf(xc * f);
+    acc += f * (co * g[pe_index(d, k, 0, c)] - sn * g[pe_index(d, k, 1, c)]);
+  }
+  return acc;
+}
+// d/dx_c of [J_pe(x)^T a]_c = sum_k f^2 (-sin(f x_c) a_sin - cos(f x_c) a_cos)   (second derivative of the encoding)
+PW_HD float pe_hess_coord(const float* a, int d, int F, int c, float xc) {
+  float acc = 0.f;
+  for (int k = 0; k < F; ++k) {
+    float f = (float)(1 << k), sn = sinf(xc * f), co = cosf(xc * f);
+    acc -= f * f * (sn * a[pe_index(d, k, 0, c)] + co * a[pe_index(d, k, 1, c)]);
+  }
+  return acc;
+}
+
 // ----------------------------------------------------------------------------- sdf -> alpha (ZT:657-685, :769)
 struct SdfAlphaOut { float alpha, gerr; };
 PW_HD SdfAlphaOut sdf_alpha_fwd(float sdf, const float* g, float dist, const float* dir, float inv_s, float anneal) {
@@ -142,7 +161,8 @@ PW_HD SdfAlphaOut sdf_alpha_fwd(float sdf, const float* g, float dist, const flo
   return o;
 }
 PW_HD void sdf_alpha_bwd(float sdf, const float* g, float dist, const float* dir, float inv_s, float anneal,
-                         float d_alpha, float d_gerr, float* d_sdf, float* d_g, float* d_inv_s) {
+                         float d_alpha, float d_gerr, float* d_sdf, float* d_g, float* d_inv_s, float* d_dist = nullptr,
+                         float* d_dir = nullptr) {
   float tc = dir[0] * g[0] + dir[1] * g[1] + dir[2] * g[2];
   float q1 = -tc * 0.5f + 0.5f, q2 = -tc;
   float r1 = fmaxf(q1, 0.f), r2 = fmaxf(q2, 0.f);
@@ -164,6 +184,10 @@ PW_HD void sdf_alpha_bwd(float sdf, const float* g, float dist, const float* dir
   float gn = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
   float ge = gn > 0.f ? d_gerr * 2.0f * (gn - 1.0f) / gn : 0.f;
   for (int c = 0; c < 3; ++c) d_g[c] = dtc * dir[c] + ge * g[c];
+  // position-gradient outputs (stage 2: the sample positions depend on the refracted path): distance and ray direction
+  if (d_dist) *d_dist = (den_ - dep) * ic * 0.5f;
+  if (d_dir)
+    for (int c = 0; c < 3; ++c) d_dir[c] = dtc * g[c];
 }
 
 // ----------------------------------------------------------------------------- NeRF++ output (ZT:515-516, :691-692)
@@ -173,9 +197,10 @@ PW_HD void nerf_out_fwd(float sigma, const float* rgb, float dist, float* alpha,
   for (int c = 0; c < 3; ++c) color[c] = srgb_fwd(expf(fminf(rgb[c], 5.0f)));
 }
 PW_HD void nerf_out_bwd(float sigma, const float* rgb, float dist, float d_alpha, const float* d_color, float* d_sigma,
-                        float* d_rgb) {
+                        float* d_rgb, float* d_dist = nullptr) {
   float sp = softplus1(sigma);
   float dsp = d_alpha * expf(-sp * dist) * dist;
+  if (d_dist) *d_dist = d_alpha * expf(-sp * dist) * sp;
   *d_sigma = dsp * (sigma > 20.f ? 1.0f : sigmoidf_(sigma));
   for (int c = 0; c < 3; ++c) {
     float e = expf(fminf(rgb[c], 5.0f));
@@ -194,9 +219,18 @@ PW_HD ShadeDirs shade_dirs(const float* g, const float* raydir) {
   for (int c = 0; c < 3; ++c) s.r[c] = s.nov * s.n[c] * 2.0f - s.v[c];
   return s;
 }
-// given d_r, d_n (direct), d_nov -> d_g
-PW_HD void shade_dirs_bwd(const ShadeDirs& s, const float* d_r, const float* d_n_direct, float d_nov, float* d_g) {
+// given d_r, d_n (direct), d_nov -> d_g; optionally also d_raydir (v = -raydir / |raydir|; d_v_direct = gradient that
+// reaches v directly, e.g. through PE(v)), |raydir| = vn
+PW_HD void shade_dirs_bwd(const ShadeDirs& s, const float* d_r, const float* d_n_direct, float d_nov, float* d_g,
+                          const float* d_v_direct = nullptr, float vn = 1.0f, float* d_raydir = nullptr) {
   float ndr = s.n[0] * d_r[0] + s.n[1] * d_r[1] + s.n[2] * d_r[2];
+  if (d_raydir) {
+    // r = 2 (n.v) n - v  ->  d_v = 2 n (n.d_r) - d_r ; nov = n.v -> d_v += d_nov n
+    float dv[3];
+    for (int c = 0; c < 3; ++c) dv[c] = 2.0f * s.n[c] * ndr - d_r[c] + d_nov * s.n[c] + (d_v_direct ? d_v_direct[c] : 0.f);
+    float vdv = s.v[0] * dv[0] + s.v[1] * dv[1] + s.v[2] * dv[2];
+    for (int c = 0; c < 3; ++c) d_raydir[c] = -(dv[c] - s.v[c] * vdv) / vn;
+  }
   float dn[3];
   for (int c = 0; c < 3; ++c) dn[c] = d_n_direct[c] + 2.0f * s.v[c] * ndr + 2.0f * s.nov * d_r[c] + d_nov * s.v[c];
   float ndn = s.n[0] * dn[0] + s.n[1] * dn[1] + s.n[2] * dn[2];

@@ -11,6 +11,8 @@ Run in the build container only:  python tests/golden/make_golden_stage2.py
   stage2_grads_R64.npz  same case with autograd on: trainer loss of configs/stage2/nerf/spherepot.yaml
                     (mean(loss_rgb with the TIR mask, ZT:1272) + mean(0.02 * gradient_error)) and strided samples + norms of
                     every parameter gradient (incl. IORs_pred, whose gradient flows through the path geometry).
+  stage2_geomgrads_R64.npz  d loss / d (path points, segment directions, mesh normals, IoR ratios) of the same backward
+                    pass (the reference's autograd; intermediate fixtures for the position-gradient kernels).
 """
 import os
 import sys
@@ -74,6 +76,20 @@ def main():
     gt = rh.synthetic_targets(R)
     net.zero_grad()
     pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = net.ray_trace(o, d)
+    # gradients w.r.t. the path geometry (what carries the loss to IORs_pred): keep them for the fixture
+    geo = {}
+    for k, t in enumerate(pathes):
+        if t.requires_grad:
+            t.retain_grad(); geo[f"d_path_{k}"] = t
+    for k, t in enumerate(directions):
+        if t.requires_grad:
+            t.retain_grad(); geo[f"d_dir_{k}"] = t
+    for k, t in enumerate(gradient_mesh):
+        if t.requires_grad:
+            t.retain_grad(); geo[f"d_nmesh_{k}"] = t
+    for k, t in enumerate(ior_ratios):
+        if t.requires_grad:
+            t.retain_grad(); geo[f"d_ior_{k}"] = t
     out = net.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
                           cos_anneal_ratio=0.2, step=10000, is_train=True, is_nerf=True)
     tm = tir_mask.detach()
@@ -81,6 +97,9 @@ def main():
     loss = loss_rgb.mean() + (0.02 * out["gradient_error"]).mean()
     loss.backward()
     gres = {"gt": gt.numpy(), "loss": loss.detach().numpy(), "ray_rgb": out["ray_rgb"].detach().numpy()}
+    ggeo = {k: (t.grad if t.grad is not None else torch.zeros_like(t)).detach().numpy() for k, t in geo.items()}
+    np.savez_compressed(os.path.join(OUT, "stage2_geomgrads_R64.npz"), **ggeo)
+    print("geometry gradients:", {k: (v.shape, float(np.abs(v).max()) if v.size else 0.0) for k, v in ggeo.items()})
     for name, p_ in net.named_parameters():
         if p_.grad is None:
             continue
