@@ -97,7 +97,7 @@ class NerfW:
         self.pts = []
         for i in range(8):
             v, g, b = _wn(net.pts_linears[i])
-            self.pts.append(Dense(bank, v, g, b, col_rot=(84 if i == 5 else 0), need_t=(i > 0)))
+            self.pts.append(Dense(bank, v, g, b, col_rot=(84 if i == 5 else 0)))     # WTk of layer 0: position gradient
         vf, _, bf = _wn(net.feature_linear)
         va, _, ba = _wn(net.alpha_linear)
         self.feat = Dense(bank, vf, None, bf, need_t=False)
@@ -191,7 +191,7 @@ def sdf_forward(w: SdfWeights, pts, planes, xm: P):
          t.g_skip.data_ptr())
     for l in (3, 2, 1):
         linear(Gs[l], w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, out=Gs[l - 1])
-    u0 = _f(M, 64, dev=dev)
+    u0 = t.u0 = _f(M, 64, dev=dev)
     linear(Gs[0], w.L[0].WTk, M, 64, 256, out_f32=u0)
     t.grad = _f(M, 3, dev=dev)
     call("nunerf_sdf_grad_pe", pts.data_ptr(), u0.data_ptr(), 64, t.g_skip.data_ptr(), 39, M, t.grad.data_ptr())
@@ -220,7 +220,7 @@ def _sdf_forward_fused(w: SdfWeights, t: SdfTape, xm: P):
     t.g_skip = _f(M, 39, dev=dev)
     call("nunerf_sdf_skip_split", u4.data_ptr(), A[3].ptr, A[3].ld, A[3].lo, M, Gs[3].ptr, Gs[3].ld, Gs[3].lo,
          t.g_skip.data_ptr())
-    u0 = _f(M, 64, dev=dev)
+    u0 = t.u0 = _f(M, 64, dev=dev)
     chain(Gs[3], M, 256, [dict(W=w.L[l].WTk, N=256, K=256, aux_mode=4, aux1=A[l - 1], store=Gs[l - 1], keep=1)
                           for l in (3, 2, 1)] + [dict(W=w.L[0].WTk, N=64, K=256, out32=u0, n32=64)])
     t.grad = _f(M, 3, dev=dev)
@@ -228,15 +228,31 @@ def _sdf_forward_fused(w: SdfWeights, t: SdfTape, xm: P):
     return t
 
 
-def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
+def _sdf_position_grad(w: SdfWeights, t: SdfTape, g_pe0, g_pe4, d_grad):
+    """d loss / d x of the SDF network's input point: the value network's two PE inputs (layer 0 and the skip concat of
+    layer 4; g_pe4[:, 25:64] are the 39 skip columns, i.e. rows 217..255 of lin4's transposed operand read from row 192)
+    plus the x-dependence of SDFNetwork.gradient itself (field.py:155-167): grad = J_pe(x)^T (u0 + g_skip), whose
+    derivative with u held fixed is the PE Hessian term; the dependence of u on x is already inside g_pe0 / g_pe4
+    because the reverse-over-reverse pass added E_l to every dZ_l."""
+    M, dev = t.M, t.pts.device
+    dx = _f(M, 3, dev=dev)
+    call("nunerf_pe_bwd", t.pts.data_ptr(), 3, 6, g_pe0.data_ptr(), 64, g_pe4.data_ptr() + 25 * 4, 64, M, dx.data_ptr(), 0)
+    call("nunerf_sdf_pe_hess", t.pts.data_ptr(), t.u0.data_ptr(), 64, t.g_skip.data_ptr(), 39, d_grad.data_ptr(), M,
+         dx.data_ptr())
+    return dx
+
+
+def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad, want_dx=False):
     """Backward of sdf_forward.  dxm[:, 0:256] holds d feat (planes); d_sdf [M], d_grad [M,3] fp32.
-    Weight / bias gradients accumulate in the Dense objects (w.L[l].dW / .db, w.feat, w.sdf_head)."""
+    Weight / bias gradients accumulate in the Dense objects (w.L[l].dW / .db, w.feat, w.sdf_head).
+    want_dx: returns d loss / d pts [M,3] (the stage-2 path geometry is a function of the IoR network)."""
     M, dev = t.M, t.pts.device
     A, Gs = t.A, t.Gs
     dW = [w.L[l].dW for l in range(8)]
     db = [w.L[l].db for l in range(8)]
     if _fused(planes):
-        return _sdf_backward_fused(w, t, dxm, d_sdf, d_grad)
+        return _sdf_backward_fused(w, t, dxm, d_sdf, d_grad, want_dx)
+    g_pe0 = g_pe4 = None
     # ---- (a) reverse of the adjoint pass (forward-like chain on u~), produces E_l and the gs (x) u~ weight terms
     E = [P(M, 256, planes, dev) for _ in range(8)]
     ut = P(M, 64, planes, dev)
@@ -274,6 +290,9 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
         n_l = 217 if l == 3 else 256
         linear_dw(cur, A[l - 1], M, n_l, 256, dW[l], db=db[l])
         if l == 4:
+            if want_dx:
+                g_pe4 = _f(M, 64, dev=dev)
+                linear(cur, w.L[4].WTk, M, 64, 256, b_row=192, out_f32=g_pe4)
             # input of lin4 is [a3 | PE]: only the first 217 columns carry on (PE has no parameters upstream)
             nxt = P(M, 256, planes, dev, zero=True)
             linear(cur, w.L[l].WTk, M, 224, 256, aux=A[3], aux_mode=2, add=E[3], out=nxt, n_store=217)
@@ -282,9 +301,13 @@ def sdf_backward(w: SdfWeights, t: SdfTape, planes, dxm: P, d_sdf, d_grad):
             linear(cur, w.L[l].WTk, M, 256, 256, aux=A[l - 1], aux_mode=2, add=E[l - 1], out=other)
             cur, other = other, cur
     linear_dw(cur, t.x0, M, 256, 64, dW[0], db=db[0])
+    if want_dx:
+        g_pe0 = _f(M, 64, dev=dev)
+        linear(cur, w.L[0].WTk, M, 64, 256, out_f32=g_pe0)
+        return _sdf_position_grad(w, t, g_pe0, g_pe4, d_grad)
 
 
-def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad):
+def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad, want_dx=False):
     """bf16 mode: both reverse passes as fused chains (csrc/chain.cu aux_mode 5 / 6) -- the products gts_l and the
     intermediate dZ never round-trip through HBM between the GEMM and its element-wise glue; every u~_l / dZ_l is written
     once for its weight-gradient GEMM.  The two 217-wide layers around the skip concat keep the layer-by-layer path."""
@@ -325,6 +348,11 @@ def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad):
     for l in range(7, 0, -1):
         linear_dw(DZ[l], A[l - 1], M, 217 if l == 3 else 256, 256, dW[l], db=db[l])
     linear_dw(DZ[0], t.x0, M, 256, 64, dW[0], db=db[0])
+    if want_dx:
+        g_pe0, g_pe4 = _f(M, 64, dev=dev), _f(M, 64, dev=dev)
+        linear(DZ[4], w.L[4].WTk, M, 64, 256, b_row=192, out_f32=g_pe4)
+        linear(DZ[0], w.L[0].WTk, M, 64, 256, out_f32=g_pe0)
+        return _sdf_position_grad(w, t, g_pe0, g_pe4, d_grad)
 
 
 # =============================================================================================== predictors
@@ -361,9 +389,11 @@ def pred_forward(w: PredW, x: P, M, K0, planes):
     return t
 
 
-def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None, dx_add=False, dx_f32=None, dx_n=0):
+def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None, dx_add=False, dx_f32=None, dx_n=0,
+                  dx_tail=None):
     """dz_head: planes [M,64] (n_out real columns).  Optionally produces dX of the first layer either as planes
-    (accumulating when dx_add) or as fp32."""
+    (accumulating when dx_add) or as fp32.  dx_tail = (b_row, fp32 [M,64]): additionally the 64 input columns starting
+    at b_row (the position columns of the material predictors' [feature | p] input)."""
     M, dev = t.M, t.x.t.device
     gW = [w.L[i].dW for i in range(4)]
     gb = [w.L[i].db for i in range(4)]
@@ -395,6 +425,8 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
         linear(d2, w.L[0].WTk, M, dx_n, 256, out=dx_planes, add=dx_planes if dx_add else None)
     if dx_f32 is not None:
         linear(d2, w.L[0].WTk, M, dx_n, 256, out_f32=dx_f32)
+    if dx_tail is not None:
+        linear(d2, w.L[0].WTk, M, 64, 256, b_row=dx_tail[0], out_f32=dx_tail[1])
 
 
 # =============================================================================================== NeRF++
@@ -406,8 +438,9 @@ def nerf_forward(w: NerfW, pts, dirs, dists, planes):
     """compute_density_alpha (ZT:687-693) on the compact outer samples -> alpha [M], colour [M,3]."""
     M, dev = pts.shape[0], pts.device
     t = NerfTape()
-    t.M, t.dists = M, dists
+    t.M, t.dists, t.pts = M, dists, pts
     pts4, views = _f(M, 4, dev=dev), _f(M, 3, dev=dev)
+    t.pts4, t.views = pts4, views
     call("nunerf_nerf_prep", pts.data_ptr(), dirs.data_ptr(), M, pts4.data_ptr(), views.data_ptr())
     t.x0 = P(M, 128, planes, dev)
     call("nunerf_encode_pe", pts4.data_ptr(), M, 4, 10, t.x0.ptr, t.x0.ld, t.x0.lo, 0, 0, 128)
@@ -448,19 +481,33 @@ def nerf_forward(w: NerfW, pts, dirs, dists, planes):
     return t, alpha, color
 
 
-def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
+def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes, want_geo=False):
+    """Reverse of nerf_forward.  want_geo: also returns (d_pts [M,3], d_dirs [M,3], d_dists [M]) -- the gradient with
+    respect to the sample positions / ray directions / interval lengths (the stage-2 path geometry, ZT:1531-1539):
+    dX GEMMs of the first trunk layer, the skip layer's PE rows and the view layer's PE rows, then the PE and
+    inverted-sphere reverse kernels."""
     M, dev = t.M, t.dists.device
     H = t.H
     dz_rgb = P(M, 64, planes, dev, zero=True)
     dz8 = P(M, 320, planes, dev)
     dz8.t[:, 256:].zero_()                               # [d feature (256, written below) | d sigma | zero K padding]
-    call("nunerf_nerf_out_bwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M, d_alpha.data_ptr(),
-         d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0)
+    d_dists = _f(M, dev=dev) if want_geo else None
+    if want_geo:
+        call("nunerf_nerf_out_bwd_geo", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M,
+             d_alpha.data_ptr(), d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0,
+             d_dists.data_ptr())
+    else:
+        call("nunerf_nerf_out_bwd", t.sigma.data_ptr(), 16, t.rgb.data_ptr(), 16, t.dists.data_ptr(), M,
+             d_alpha.data_ptr(), d_color.data_ptr(), dz8.ptr, dz8.ld, dz8.lo, 256, dz_rgb.ptr, dz_rgb.ld, dz_rgb.lo, 0)
     linear_dw(dz_rgb, t.hv, M, 3, 128, w.rgb.dW, db=w.rgb.db)
     dzv = P(M, 128, planes, dev)
     linear(dz_rgb, w.rgb.WTk, M, 128, 64, mask_in=t.Mv, out=dzv)
     linear_dw(dzv, t.xv, M, 128, 320, w.views.dW, db=w.views.db)
     linear(dzv, w.views.WTk, M, 256, 128, out=dz8)                       # d feature -> dz8[:, :256]
+    g_view = g_pe0 = g_pe5 = None
+    if want_geo:
+        g_view, g_pe0, g_pe5 = _f(M, 64, dev=dev), _f(M, 128, dev=dev), _f(M, 128, dev=dev)
+        linear(dzv, w.views.WTk, M, 64, 128, b_row=256, out_f32=g_view)   # d PE4(view): rows 256.. of the view layer
     linear_dw(dz8, H[7], M, 256, 256, w.feat.dW, db=w.feat.db)
     linear_dw(dz8, H[7], M, 1, 256, w.alpha.dW, z_col=256, db=w.alpha.db)
     if _fused(planes) and t.perm[0]:
@@ -472,15 +519,31 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes):
         for i in range(7, 0, -1):
             linear_dw(DZ[i], H[i - 1], M, 256, 384 if i == 5 else 256, w.pts[i].dW, db=w.pts[i].db)
         linear_dw(DZ[0], t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
-        return
-    cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
-    linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
-    for i in range(7, 0, -1):
-        K = 384 if i == 5 else 256
-        linear_dw(cur, H[i - 1], M, 256, K, w.pts[i].dW, db=w.pts[i].db)
-        linear(cur, w.pts[i].WTk, M, 256, 256, mask_in=t.Mk[i - 1], out=other)
-        cur, other = other, cur
-    linear_dw(cur, t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
+        if want_geo:
+            linear(DZ[5], w.pts[5].WTk, M, 128, 256, b_row=256, out_f32=g_pe5)   # skip input is stored [h | PE]
+            linear(DZ[0], w.pts[0].WTk, M, 128, 256, out_f32=g_pe0)
+    else:
+        cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
+        linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
+        for i in range(7, 0, -1):
+            K = 384 if i == 5 else 256
+            linear_dw(cur, H[i - 1], M, 256, K, w.pts[i].dW, db=w.pts[i].db)
+            if want_geo and i == 5:
+                linear(cur, w.pts[5].WTk, M, 128, 256, b_row=256, out_f32=g_pe5)
+            linear(cur, w.pts[i].WTk, M, 256, 256, mask_in=t.Mk[i - 1], out=other)
+            cur, other = other, cur
+        linear_dw(cur, t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
+        if want_geo:
+            linear(cur, w.pts[0].WTk, M, 128, 256, out_f32=g_pe0)
+    if not want_geo:
+        return None
+    d_pts4, d_views = _f(M, 4, dev=dev), _f(M, 3, dev=dev)
+    call("nunerf_pe_bwd", t.pts4.data_ptr(), 4, 10, g_pe0.data_ptr(), 128, g_pe5.data_ptr(), 128, M, d_pts4.data_ptr(), 0)
+    call("nunerf_pe_bwd", t.views.data_ptr(), 3, 4, g_view.data_ptr(), 64, None, 0, M, d_views.data_ptr(), 0)
+    d_pts, d_dirs = _f(M, 3, dev=dev), _f(M, 3, dev=dev)
+    call("nunerf_nerf_prep_bwd", t.pts.data_ptr(), d_pts4.data_ptr(), d_views.data_ptr(), M, d_pts.data_ptr(),
+         d_dirs.data_ptr())
+    return d_pts, d_dirs, d_dists
 
 
 # =============================================================================================== sampling
@@ -496,7 +559,7 @@ class Stage1Weights:
         self.pred = {}
         for name, need_dx0 in (("metallic_predictor", True), ("roughness_predictor", True), ("albedo_predictor", True),
                                ("transmisstion_weight", True), ("outer_light", True), ("inner_light", True),
-                               ("inner_weight", False), ("refrac_light", False)):
+                               ("inner_weight", False), ("refrac_light", True)):
             self.pred[name] = PredW(self.bank, getattr(net.color_network, name), need_dx0=need_dx0)
         self.bank.finalize()
         self._variance = net.deviation_network.variance
@@ -725,11 +788,13 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
 
 
 def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, want_inv_s, d_occ=None, g=None,
-                   surface=False):
+                   surface=False, want_geo=False, d_nov_ext=None):
     """Reverse of inner_forward on the M = t.n_in compact samples: shading mix, the light / material predictors,
     sdf -> alpha, the direction encodings and the SDF network (value pass + reverse-over-reverse of its gradient).
     surface=True is the reverse of the stage-2 surface shading (shade_forward with the MESH normal, no refraction
-    light, no sdf -> alpha): the normal is a constant there, so only the feature path reaches the SDF network."""
+    light, no sdf -> alpha): the normal is a constant of the FIELD there, so only the feature path reaches the SDF
+    network.  want_geo (stage 2): g["d_pts"], g["d_dirs"] [M,3] and g["d_dists"] [M] (inner) / g["d_normals"] [M,3]
+    (surface) -- the gradient with respect to the sample geometry, which the IoR network moves."""
     planes, dev, M = w.planes, t.pts_in.device, t.n_in
     g = {} if g is None else g
     # ---- shading mix
@@ -737,14 +802,24 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     dz["outer"], dz["inner"] = P(3 * M, 64, planes, dev, zero=True), P(2 * M, 64, planes, dev, zero=True)
     d_rough, d_nov = _f(M, dev=dev), _f(M, dev=dev)
     call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov, d_occ)))
+    if d_nov_ext is not None:
+        d_nov += d_nov_ext
     dxo, dxi = _f(3 * M, 128, dev=dev), _f(2 * M, 128, dev=dev)
     pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128)
     pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128)
     pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes)
+    dxr = None
     if not surface:
-        pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes)
+        if want_geo:
+            dxr = _f(M, 128, dev=dev)
+            pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes, dx_f32=dxr, dx_n=128)
+        else:
+            pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes)
     # ---- sdf -> alpha
     d_sdf, d_grad = _z(M, dev=dev), _z(M, 3, dev=dev)
+    d_pts = _z(M, 3, dev=dev) if want_geo else None
+    d_dirs = _z(M, 3, dev=dev) if want_geo else None
+    d_dists = _z(M, dev=dev) if want_geo else None
     if not surface:
         d_inv = _z(1, dev=dev) if want_inv_s else None
         sa = _lib.SdfAlphaT()
@@ -753,17 +828,23 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
             t.dists_in.data_ptr(), t.dirs_in.data_ptr()
         sa.d_alpha, sa.d_grad_err = da_in.data_ptr(), ptr(d_gerr)
         sa.d_sdf, sa.d_grad, sa.d_inv_s = d_sdf.data_ptr(), d_grad.data_ptr(), ptr(d_inv)
+        sa.d_dists, sa.d_dirs = ptr(d_dists), ptr(d_dirs)
         call("nunerf_sdf_alpha_bwd", C.byref(sa))
         if want_inv_s:
             g["inv_s"] = d_inv
-    # ---- directions / encodings (adds into d_grad and d_rough)
+    # ---- directions / encodings (adds into d_grad and d_rough; with want_geo also into d_pts / d_dirs)
     se = _lib.ShadeEncodeT()
     se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.normals.data_ptr(), t.dirs_in.data_ptr()
     se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
     se.d_x_outer, se.ld_dxo, se.d_x_inner, se.ld_dxi = dxo.data_ptr(), 128, dxi.data_ptr(), 128
     se.d_nov, se.d_grad, se.d_rough_raw, se.ld_drough = d_nov.data_ptr(), d_grad.data_ptr(), d_rough.data_ptr(), 1
+    if want_geo:
+        se.d_x_refrac, se.ld_dxr = ptr(dxr), 128
+        se.d_pts, se.d_dirs = d_pts.data_ptr(), d_dirs.data_ptr()
     call("nunerf_shade_encode_bwd", C.byref(se))
     if surface:
+        if want_geo:
+            g["d_normals"] = d_grad
         d_grad = _z(M, 3, dev=dev)                                  # the mesh normal is not a function of the field
     dz["rough"] = P(M, 64, planes, dev)
     f32_to_planes(d_rough, dz["rough"], M, 1, 64)
@@ -772,10 +853,15 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     first = True
     for name, key in (("metallic_predictor", "metallic"), ("roughness_predictor", "rough"),
                       ("albedo_predictor", "albedo"), ("transmisstion_weight", "trans")):
-        pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first, dx_n=256)
+        tail = (256, _f(M, 64, dev=dev)) if want_geo else None       # d of the p columns of [feature | p]
+        pred_backward(w.pred[name], t.mat[name], dz[key], planes, dx_planes=dxm, dx_add=not first, dx_n=256, dx_tail=tail)
+        if want_geo:
+            d_pts += tail[1][:, :3]
         first = False
     # ---- SDF network
-    sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad)
+    dx = sdf_backward(w.sdf, t.sdf, planes, dxm, d_sdf, d_grad, want_dx=want_geo)
+    if want_geo:
+        g["d_pts"], g["d_dirs"], g["d_dists"] = d_pts + dx, d_dirs, d_dists
     return g
 
 
@@ -929,8 +1015,11 @@ def surface_forward(w1: Stage1Weights, pts, normals, dirs, exp_max):
     return t
 
 
-def surface_backward(w1: Stage1Weights, t, d_color, d_trans):
-    inner_backward(w1, t, None, d_color, None, d_trans, None, False, surface=True)
+def surface_backward(w1: Stage1Weights, t, d_color, d_trans, want_geo=False, d_nov=None):
+    """Reverse of surface_forward; want_geo: g["d_pts"], g["d_normals"], g["d_dirs"] (d_nov = gradient arriving at the
+    NoV output, which only the geometry moves)."""
+    return inner_backward(w1, t, None, d_color, None, d_trans, None, False, surface=True, want_geo=want_geo,
+                          d_nov_ext=d_nov)
 
 
 def shading_buffers(w: Stage1Weights, t, exp_max):

@@ -1,9 +1,8 @@
 """Stage2Renderer -- the zero-thickness nested-refraction renderer of network/renderer_zerothick.py:868-2011 ("ZT")
-on the sm_100a engine: forward (ray_trace + render_core, train- and eval-mode outputs) and the backward of render_core
-with respect to every FIELD parameter (stage-1 NeRF++ / SDF feature / predictors at the surface hits, inner SDF, inner
-shading, inner variance).  The path geometry is a constant of the backward: the gradient of IORs_pred, which in the
-reference flows through the refracted sample positions into every field's input, is not built yet (its parameters get
-no .grad; every other parameter's gradient is unaffected because no other parameter moves the positions).
+on the sm_100a engine: forward (ray_trace + render_core, train- and eval-mode outputs) and the backward of the trainer
+loss with respect to every parameter: the FIELD parameters (stage-1 NeRF++ / SDF feature / predictors at the surface
+hits, inner SDF, inner shading, inner variance) and IORs_pred, whose gradient flows through the refracted sample
+positions into every field's input.
 
   ray_trace   ZT:1571-1828   <= 3 bounces: BVH closest hit + re-intersection (csrc/bvh.cu), IoR MLP on tensor cores,
                              Snell / TIR kernel, segment sampling (256 uniform | 64 + 2 x 32 SDF-guided with the warp
@@ -11,12 +10,17 @@ no .grad; every other parameter's gradient is unaffected because no other parame
   render_core ZT:1835-2011   per segment: NeRF++ on the outer samples, inner SDF + shading on segment 1, surface
                              shading at the hit with the mesh normal and the stage-1 predictors, linear-space
                              compositing with the throughput chain T *= T_end (1 - schlick) transmission
+  _replay_geometry           the trace again as a differentiable function of IORs_pred (per-ray work on <= R rows per
+                             bounce: Moeller-Trumbore on the recorded triangle, IoR MLP, Snell), values straight-through
 
 Each field evaluation is one autograd node (forward = explicit launch sequence, backward = hand-derived reverse sequence
-of engine.py, gradients added in place to .grad by the WeightBank); the per-ray / per-segment bookkeeping between them
-(mask compaction, linear-space compositing of [N, 255] rows, throughput chain, reverse scatter-add) is torch indexing,
-as in the reference.  Lists returned by ray_trace have the reference's exact structure (per-segment compacted rows in
-boolean-mask order), so render_core accepts the reference's ray_trace output and vice versa.
+of engine.py, gradients added in place to .grad by the WeightBank).  When the geometry carries a graph the same nodes
+also return the gradient with respect to their sample positions / directions / interval lengths / normals
+(position-gradient kernels: PE backward, PE Hessian of the SDF gradient, NeRF++ inverted-sphere backward, csrc/field.cu).
+The per-ray / per-segment bookkeeping between the nodes (mask compaction, throughput chain, reverse scatter-add) is torch
+indexing, as in the reference.  Lists returned by ray_trace have the reference's exact structure (per-segment compacted
+rows in boolean-mask order), so render_core accepts the reference's ray_trace output and vice versa.
+cfg['frozen_ior'] = True keeps the geometry constant (no replay, no position gradients: IORs_pred gets no gradient).
 """
 import numpy as np
 import torch
@@ -43,18 +47,28 @@ def linear_to_srgb(x):
     return torch.where(x <= 0.0031308, 323.0 / 25.0 * x, (211.0 * torch.clamp(x, min=eps) ** (5.0 / 12.0) - 11.0) / 200.0)
 
 
+def starts_k(rec, k, what):
+    """start / direction of segment k as the (no-grad) trace produced them."""
+    return rec["segments"][k][what]
+
+
 def _bank_params(w):
     ps = [p for d in w.bank.denses if d.has_grad for p in (d.v, d.g, d.bias) if p is not None]
     return list({id(p): p for p in ps}.values())
 
 
+def _zf(g, dev, *shape):
+    return torch.zeros(*shape, device=dev) if g is None else g.contiguous().float()
+
+
 class _NerfFn(torch.autograd.Function):
-    """compute_density_alpha (ZT:1531-1539) on a flat list of outer samples with the stage-1 NeRF++."""
+    """compute_density_alpha (ZT:1531-1539) on a flat list of outer samples with the stage-1 NeRF++.  pts / dirs / dists
+    are differentiable inputs: when the path geometry carries a graph (IORs_pred is being trained) the backward also runs
+    the position-gradient kernels (engine.nerf_backward(want_geo=True))."""
 
     @staticmethod
-    def forward(ctx, pack, *params):
+    def forward(ctx, w, pts, dirs, dists, *params):
         eng = _engine()
-        w, pts, dirs, dists = pack
         tape, alpha, color = eng.nerf_forward(w.nerf, pts, dirs, dists, w.planes)
         ctx.w, ctx.tape, ctx.n = w, tape, len(params)
         return alpha, color
@@ -63,21 +77,23 @@ class _NerfFn(torch.autograd.Function):
     def backward(ctx, d_alpha, d_color):
         eng = _engine()
         w, t = ctx.w, ctx.tape
-        z = lambda g, *shape: torch.zeros(*shape, device=t.dists.device) if g is None else g.contiguous().float()
+        dev = t.dists.device
+        geo = any(ctx.needs_input_grad[1:4])
         w.bank.zero_grads()
-        eng.nerf_backward(w.nerf, t, z(d_alpha, t.M), z(d_color, t.M, 3), w.planes)
+        g = eng.nerf_backward(w.nerf, t, _zf(d_alpha, dev, t.M), _zf(d_color, dev, t.M, 3), w.planes, want_geo=geo)
         w.bank.backward()
         ctx.tape = None
-        return (None,) + (None,) * ctx.n
+        d_pts, d_dirs, d_dists = g if geo else (None, None, None)
+        return (None, d_pts, d_dirs, d_dists) + (None,) * ctx.n
 
 
 class _InnerFn(torch.autograd.Function):
     """compute_sdf_alpha + color_network_inner (ZT:1887-1906) on the compact inner samples of segment 1."""
 
     @staticmethod
-    def forward(ctx, pack, inv_s, *params):
+    def forward(ctx, pack, inv_s, pts, dirs, dists, *params):
         eng = _engine()
-        w, pts, dirs, dists, cos_anneal, exp_max, want_inv_s = pack
+        w, cos_anneal, exp_max, want_inv_s = pack
         t = eng.inner_tape(pts, dirs, dists, cos_anneal, exp_max)
         eng.inner_forward(w, t)
         ctx.w, ctx.tape, ctx.n, ctx.want_inv_s = w, t, len(params), want_inv_s
@@ -88,39 +104,43 @@ class _InnerFn(torch.autograd.Function):
         eng = _engine()
         w, t = ctx.w, ctx.tape
         dev, M = t.pts_in.device, t.n_in
-        z = lambda g, *shape: torch.zeros(*shape, device=dev) if g is None else g.contiguous().float()
+        geo = any(ctx.needs_input_grad[2:5])
         w.bank.zero_grads()
-        g = eng.inner_backward(w, t, z(d_alpha, M), z(d_color, M, 3), z(d_gerr, M), None, None, ctx.want_inv_s)
+        g = eng.inner_backward(w, t, _zf(d_alpha, dev, M), _zf(d_color, dev, M, 3), _zf(d_gerr, dev, M), None, None,
+                               ctx.want_inv_s, want_geo=geo)
         w.bank.backward()
         ctx.tape = None
         d_inv = g["inv_s"].reshape(()) if ctx.want_inv_s and "inv_s" in g else None
-        return (None, d_inv) + (None,) * ctx.n
+        return (None, d_inv, g.get("d_pts"), g.get("d_dirs"), g.get("d_dists")) + (None,) * ctx.n
 
 
 class _SurfaceFn(torch.autograd.Function):
-    """AppShadingNetwork_S2 at the mesh hits (ZT:1908-1925): sRGB colour, transmission weight, NoV."""
+    """AppShadingNetwork_S2 at the mesh hits (ZT:1908-1925): sRGB colour, transmission weight, NoV.  The hit points,
+    mesh normals and incoming directions are differentiable inputs (they move with IORs_pred from the second hit on)."""
 
     @staticmethod
-    def forward(ctx, pack, *params):
+    def forward(ctx, pack, pts, normals, dirs, *params):
         eng = _engine()
-        w, pts, normals, dirs, exp_max, holder = pack
+        w, exp_max, holder = pack
         t = eng.surface_forward(w, pts, normals, dirs, exp_max)
         holder["tape"] = t                      # eval-mode extras are rebuilt from the predictor heads
         ctx.w, ctx.tape, ctx.n = w, t, len(params)
-        ctx.mark_non_differentiable(t.nov)
+        ctx.geo = any(ctx.needs_input_grad[1:4])
+        if not ctx.geo:
+            ctx.mark_non_differentiable(t.nov)  # NoV only depends on the geometry
         return t.c_in, t.trans, t.nov
 
     @staticmethod
-    def backward(ctx, d_color, d_trans, _d_nov):
+    def backward(ctx, d_color, d_trans, d_nov):
         eng = _engine()
         w, t = ctx.w, ctx.tape
         dev, M = t.pts_in.device, t.n_in
-        z = lambda g, *shape: torch.zeros(*shape, device=dev) if g is None else g.contiguous().float()
         w.bank.zero_grads()
-        eng.surface_backward(w, t, z(d_color, M, 3), z(d_trans, M))
+        g = eng.surface_backward(w, t, _zf(d_color, dev, M, 3), _zf(d_trans, dev, M), want_geo=ctx.geo,
+                                 d_nov=_zf(d_nov, dev, M) if ctx.geo else None)
         w.bank.backward()
         ctx.tape = None
-        return (None,) + (None,) * ctx.n
+        return (None, g.get("d_pts"), g.get("d_normals"), g.get("d_dirs")) + (None,) * ctx.n
 
 
 class _InnerField:
@@ -227,7 +247,10 @@ class Stage2Renderer(nn.Module):
 
     # ------------------------------------------------------------------ ZT:1571-1828
     @torch.no_grad()
-    def ray_trace(self, rays_o, rays_d, prepared=None, trace=None):
+    def ray_trace(self, rays_o, rays_d, prepared=None, trace=None, rec=None):
+        """rec (dict): filled with the discrete decisions and per-sample parameters of the trace (hit / pass index lists,
+        triangle ids, sample parameters z) for _replay_geometry, which rebuilds the same geometry as a differentiable
+        function of IORs_pred."""
         eng = _engine()
         w1, wi, wior = prepared if prepared is not None else self._prepare()
         dev = rays_o.device
@@ -280,6 +303,10 @@ class Stage2Renderer(nn.Module):
             intersections.append(x_c)
             hit_idxs.append(hit_idx)
             conv_idxs.append(hit_idx[ok_idx])                 # rays of this segment that continue into the next one
+            if rec is not None:
+                rec.setdefault("bounces", []).append(dict(hit_idx=hit_idx, ok_idx=ok_idx, inside=inside, x=x_c, n=n_c,
+                                                          tri=info["faces_ind"][hit_idx].long(),
+                                                          eta=eta if M > 0 else torch.zeros(0, device=dev)))
             if ok_idx.numel() == 0:
                 break
             gradient_mesh.append(n_c[ok_idx])
@@ -300,6 +327,8 @@ class Stage2Renderer(nn.Module):
             n_pts = 256 if k != 1 else 128
             lin = torch.linspace(0, 1, n_pts, device=dev)
             pts = eng.segment_points(start, end - start, lin.unsqueeze(0).expand(start.shape[0], n_pts).contiguous())
+            Z = lin.unsqueeze(0).repeat(n_seg, 1) if rec is not None else None
+            m_idx = None
             if k == 1 and n_hit > 0:
                 # inside the outer mesh: 64 uniform samples to the hit, 2 rounds of SDF-guided up-sampling with 32 new
                 # samples each on the inner field; z is the unit parameter of the segment while the SDF is queried at
@@ -311,6 +340,8 @@ class Stage2Renderer(nn.Module):
                 sdf = eng.sdf_infer(wi.sdf, p64.reshape(-1, 3), wi.planes).reshape(Rh, 64).contiguous()
                 z = eng.upsample_rounds(wi, s_h, d_h, z, sdf, n_new=32, rounds=2)
                 pts[h_idx] = eng.segment_points(s_h, e_h - s_h, z)
+                if Z is not None:
+                    Z[h_idx] = z
             if k != 1 and n_hit < n_seg:
                 # rays that leave the scene: 192 samples on [0.1, 64] + 64 NeRF++-guided ones (ZT:1762-1799)
                 m_idx = infinity_bkgr[k].flatten().nonzero().squeeze(1)
@@ -324,8 +355,107 @@ class Stage2Renderer(nn.Module):
                                        w1.planes).reshape(Rm, 192)
                 z = eng.importance_merge(z, alpha, 64)
                 pts[m_idx] = eng.segment_points(s_m, d_m, z)
+                if Z is not None:
+                    Z[m_idx] = z
+            if rec is not None:
+                rec.setdefault("segments", []).append(dict(Z=Z, h_idx=h_idx, m_idx=m_idx, start=start, dir=dk))
             pathes.append(pts)
         return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
+
+    # ------------------------------------------------------------------ gradient of IORs_pred
+    def _ior_torch(self, x):
+        """IoRNetwork.forward (field.py:1046-1065) as a differentiable fp32 torch expression on the [M,3] hit points
+        (M <= rays per bounce: a few thousand rows; the trace itself evaluates it on the tensor cores)."""
+        pe = [x]
+        for k in range(6):
+            pe += [torch.sin(x * (2.0 ** k)), torch.cos(x * (2.0 ** k))]
+        h = torch.cat(pe, -1)
+        seq = self.IORs_pred.module0
+        for i, act in ((0, True), (2, True), (4, False), (5, False)):
+            h = F.linear(h, seq[i].effective_weight(), seq[i].bias)
+            h = F.relu(h) if act else h
+        return torch.sigmoid(h)
+
+    def _replay_geometry(self, rays_o, rays_d, rec, pathes, directions, gradient_mesh, straight_through=True):
+        """ray_trace (ZT:1571-1720) again as a differentiable function of IORs_pred, with every discrete decision (hit
+        triangle, pass / total-internal-reflection mask, sample parameters z -- no_grad in the reference too) taken from
+        the recorded trace: Moeller-Trumbore on the recorded triangle (DiffRender.py:61-124), interpolated vertex
+        normal, IoR network, Snell.  Values are the trace's own (straight-through: v_trace + (v - v.detach())), so the
+        forward outputs do not change; only the graph is added.  Returns (pathes, directions, gradient_mesh).
+        straight_through=False returns the replayed values themselves (tests: they must reproduce the trace)."""
+        if straight_through:
+            st = lambda kernel, replay: replay if kernel is None else kernel + (replay - replay.detach())
+        else:
+            st = lambda kernel, replay: replay
+        sc = self.scene
+        verts, faces, vnorm = sc.vertices.float(), sc.faces, sc.normals.float()
+        start_r, dir_r = rays_o.float(), rays_d.float()
+        starts, dirs, xs, gm = [start_r], [dir_r], [], []
+        for i, b in enumerate(rec["bounces"]):
+            hit_idx, ok_idx = b["hit_idx"], b["ok_idx"]
+            o_c, d_c = start_r[hit_idx], dir_r[hit_idx]
+            f = faces[b["tri"]]
+            tv, tn = verts[f], vnorm[f]
+            v0, e1, e2 = tv[:, 0], tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0]
+            pvec = torch.cross(d_c, e2, dim=-1)
+            inv_det = 1.0 / (e1 * pvec).sum(-1)
+            tvec = o_c - v0
+            u = (tvec * pvec).sum(-1) * inv_det
+            qvec = torch.cross(tvec, e1, dim=-1)
+            v = (d_c * qvec).sum(-1) * inv_det
+            t = (e2 * qvec).sum(-1) * inv_det
+            x = st(b.get("x"), o_c + t[:, None] * d_c)
+            n = (1 - u - v)[:, None] * tn[:, 0] + u[:, None] * tn[:, 1] + v[:, None] * tn[:, 2]
+            n = F.normalize(n / n.norm(dim=1, keepdim=True), dim=-1)
+            normal = st(b.get("n"), -n if b["inside"] else n)
+            xs.append(x)
+            if ok_idx.numel() == 0:
+                break
+            gm.append(normal[ok_idx])
+            if i + 1 >= len(rec["segments"]):
+                break                                   # the ray leaving the third hit is not rendered
+            cos_i = (normal * -d_c).sum(-1, keepdim=True)
+            sin2 = 1.0 - cos_i * cos_i
+            eta = 1.0 / (self._ior_torch(x).reshape(-1, 1) * 1.0 + 1.0)
+            eta = st(b["eta"].reshape(-1, 1) if b.get("eta") is not None else None, eta)
+            if b["inside"]:
+                eta = 1.0 / eta
+            eta, cos_k, n_k = eta[ok_idx], cos_i[ok_idx], normal[ok_idx]
+            sin_t2 = sin2[ok_idx] * eta * eta
+            d_tmp = eta * d_c[ok_idx] + (eta * cos_k - torch.sqrt(1.0 - sin_t2)) * n_k
+            s_next = x[ok_idx] + d_tmp * 1e-5
+            d_next = d_tmp / (torch.linalg.norm(d_tmp, dim=-1, keepdim=True) + 0.0001)
+            start_r, dir_r = st(starts_k(rec, i + 1, "start"), s_next), st(starts_k(rec, i + 1, "dir"), d_next)
+            starts.append(start_r)
+            dirs.append(dir_r)
+        new_pathes = []
+        for k, sg in enumerate(rec["segments"]):
+            s_k, d_k = starts[k], dirs[k]
+            if not (s_k.requires_grad or d_k.requires_grad):
+                new_pathes.append(pathes[k])
+                continue
+            end = s_k + d_k * 4.5
+            if sg["h_idx"].numel() > 0:
+                end = end.index_put((sg["h_idx"],), xs[k])
+            delta = end - s_k
+            if sg["m_idx"] is not None:
+                delta = delta.index_put((sg["m_idx"],), d_k[sg["m_idx"]])
+            pts = s_k[:, None, :] + delta[:, None, :] * sg["Z"][:, :, None]
+            new_pathes.append(st(pathes[k], pts))
+        if not straight_through:
+            new_pathes = [p_ if p_.requires_grad else None for p_ in new_pathes]
+        new_dirs = [dirs[k] if k < len(dirs) else directions[k] for k in range(len(directions))]
+        new_gm = [gm[k] if k < len(gm) else gradient_mesh[k] for k in range(len(gradient_mesh))]
+        if self.cfg.get("debug_geometry_grads"):
+            for t_ in new_pathes + new_dirs + new_gm:
+                if t_.requires_grad:
+                    t_.retain_grad()
+            self._geo_debug = dict(pathes=new_pathes, directions=new_dirs, gradient_mesh=new_gm)
+        return new_pathes, new_dirs, new_gm
+
+    def _train_ior(self):
+        return torch.is_grad_enabled() and not self.cfg.get("frozen_ior", False) and \
+            any(p.requires_grad for p in self.IORs_pred.parameters())
 
     # ------------------------------------------------------------------ ZT:1835-2011
     def render_core(self, rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
@@ -343,34 +473,45 @@ class Stage2Renderer(nn.Module):
         p1, p_in = _bank_params(w1), _bank_params(wi)
         freeze = self.cfg["freeze_inv_s_step"]
         frozen = freeze is not None and step is not None and step < freeze
+        # geometry tensors that carry a graph (IORs_pred being trained, see _replay_geometry) stay attached
+        geo_grad = torch.is_grad_enabled() and any(t_.requires_grad for t_ in list(pathes) + list(directions))
+        keep = (lambda t_: t_) if geo_grad else (lambda t_: t_.detach())
         for i in range(len(pathes)):
-            cand = pathes[i].detach()
+            cand = keep(pathes[i])
             N, S = cand.shape[0], cand.shape[1] - 1
             conv_idx = converges[i].flatten().nonzero().squeeze(1)        # one host sync per segment for this mask
             conv_idxs.append(conv_idx)
-            dirs_i = directions[i].detach()
+            dirs_i = keep(directions[i])
+            if cand.requires_grad:
+                # the path carries the IoR network's graph: points / interval lengths as differentiable torch expressions
+                # (ZT:1853-1858), the inside-the-unit-sphere mask from their values
+                pts = cand[:, :-1, :]
+                dists = torch.linalg.norm(pts[:, 1:] - pts[:, :-1], dim=-1)
+                dists = torch.cat([dists, dists[:, -1:]], -1)
+                inner = torch.norm(pts.detach(), dim=-1) <= 1.0
+            else:
+                with torch.no_grad():
+                    pts, dists, inner = eng.segment_geometry(cand)
             with torch.no_grad():
-                pts, dists, inner = eng.segment_geometry(cand)
-                dirs_e = dirs_i[:, None, :].expand(N, S, 3)
                 inner_f = inner.reshape(-1)
                 outer_idx = (~inner_f).nonzero().squeeze(1)
                 inner_idx = inner_f.nonzero().squeeze(1) if i == 1 else None
-                pts_f, dists_f = pts.reshape(-1, 3), dists.reshape(-1)
                 ray_of = lambda idx: torch.div(idx, S, rounding_mode="floor")      # sample -> ray (view dir)
+            pts_f, dists_f = pts.reshape(-1, 3), dists.reshape(-1)
             alpha = torch.zeros(N * S, device=dev)
             color = torch.zeros(N * S, 3, device=dev)
             if outer_idx.numel() > 0:
                 # NeRF++ of the STAGE-1 network on the samples outside the unit sphere (ZT:1876-1880)
-                a_o, c_o = _NerfFn.apply((w1, pts_f[outer_idx].contiguous(), dirs_i[ray_of(outer_idx)].contiguous(),
-                                          dists_f[outer_idx].contiguous()), *p1)
+                a_o, c_o = _NerfFn.apply(w1, pts_f[outer_idx].contiguous(), dirs_i[ray_of(outer_idx)].contiguous(),
+                                         dists_f[outer_idx].contiguous(), *p1)
                 alpha = alpha.index_put((outer_idx,), a_o)
                 color = color.index_put((outer_idx,), c_o)
             if i == 1 and inner_idx.numel() > 0:
                 # inner SDF field + inner shading on segment 1 (ZT:1883-1906)
                 inv_s = torch.exp(self.deviation_network_inner.variance * 10.0)
-                a_i, c_i, gerr = _InnerFn.apply((wi, pts_f[inner_idx].contiguous(), dirs_i[ray_of(inner_idx)].contiguous(),
-                                                 dists_f[inner_idx].contiguous(), float(cos_anneal_ratio), exp_maxi,
-                                                 not frozen), inv_s, *p_in)
+                a_i, c_i, gerr = _InnerFn.apply((wi, float(cos_anneal_ratio), exp_maxi, not frozen), inv_s,
+                                                pts_f[inner_idx].contiguous(), dirs_i[ray_of(inner_idx)].contiguous(),
+                                                dists_f[inner_idx].contiguous(), *p_in)
                 alpha = alpha.index_put((inner_idx,), a_i)
                 color = color.index_put((inner_idx,), c_i)
                 inv_s_c = inv_s.clip(1e-6, 1e6)
@@ -383,10 +524,10 @@ class Stage2Renderer(nn.Module):
             T = T * t_end[:, None]
             n_hit = conv_idx.numel()
             if n_hit > 0:
-                p_hit = cand[conv_idx][:, -1, :].contiguous()
+                p_hit = cand[conv_idx, -1, :].contiguous()
                 holder = {}
-                c_s, trans, nov = _SurfaceFn.apply((w1, p_hit, gradient_mesh[i].detach().contiguous(),
-                                                    dirs_i[conv_idx].contiguous(), exp_max1, holder), *p1)
+                c_s, trans, nov = _SurfaceFn.apply((w1, exp_max1, holder), p_hit, keep(gradient_mesh[i]).contiguous(),
+                                                   dirs_i[conv_idx].contiguous(), *p1)
                 if i % 2 != 0:
                     c_s = torch.zeros_like(c_s)                    # inside the object: field.py:969
                 tn = torch.clamp(1.0 - nov[:, None], 0.0, 1.0)
@@ -419,14 +560,13 @@ class Stage2Renderer(nn.Module):
     # ------------------------------------------------------------------ ZT:1442-1466
     def render(self, rays_o, rays_d, near=None, far=None, human_poses=None, perturb_overwrite=-1, cos_anneal_ratio=0.0,
                is_train=True, step=None, is_nerf=False):
-        if is_train and torch.is_grad_enabled() and not getattr(self, "_warned_ior", False):
-            import warnings
-            warnings.warn("nu_nerf_b200.Stage2Renderer: the path geometry is a constant of the backward pass -- IORs_pred "
-                          "receives no gradient (every other parameter's gradient is complete); see DESIGN.md section 7")
-            self._warned_ior = True
         prepared = self._prepare()
+        rec = {} if (is_train and self._train_ior()) else None
         pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = \
-            self.ray_trace(rays_o, rays_d, prepared=prepared)
+            self.ray_trace(rays_o, rays_d, prepared=prepared, rec=rec)
+        if rec is not None and rec.get("bounces"):
+            # IORs_pred is trained through the path geometry (ZT:1642-1684): rebuild it with a graph
+            pathes, directions, gradient_mesh = self._replay_geometry(rays_o, rays_d, rec, pathes, directions, gradient_mesh)
         ret = self.render_core(rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
                                human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train,
                                is_nerf=is_nerf, prepared=prepared)

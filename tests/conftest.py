@@ -80,3 +80,33 @@ def sampling_tables():
 
 
 from nu_nerf_b200.synthetic import make_stage2, uv_sphere  # noqa: E402,F401  (the synthetic nested-sphere scene of config 4)
+
+
+def stage2_rec_from_golden(G, device):
+    """The trace record Stage2Renderer._replay_geometry takes (hit / pass index lists, triangle ids, per-sample
+    parameters z), rebuilt from the reference's own ray_trace lists in tests/golden/stage2_R64.npz: z is recovered from the
+    sampled points (z = <p - start, delta> / |delta|^2 in float64)."""
+    T = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(device) if dt is None else \
+        torch.from_numpy(np.ascontiguousarray(a)).to(device).to(dt)
+    n = int(G["n_segments"])
+    rec = {"bounces": [], "segments": []}
+    for k in range(n):
+        hit = G[f"trace_hit_{k}"].reshape(-1) > 0
+        conv = G[f"converge_{k}"].reshape(-1)
+        path = G[f"path_{k}"].astype(np.float64)
+        start, dirs = path[:, 0].copy(), G[f"dir_{k}"].astype(np.float64)
+        if k != 1:
+            start[~hit] -= 0.1 * dirs[~hit]          # rays that leave the scene are sampled on [0.1, 64] (ZT:1764)
+        end = start + dirs * 4.5
+        end[hit] = path[hit, -1]
+        delta = end - start
+        m_idx = None
+        if k != 1 and (~hit).any():
+            delta[~hit] = dirs[~hit]
+            m_idx = T(np.nonzero(~hit)[0])
+        Z = ((path - start[:, None]) * delta[:, None]).sum(-1) / (delta * delta).sum(-1)[:, None]
+        rec["bounces"].append(dict(hit_idx=T(np.nonzero(hit)[0]), ok_idx=T(np.nonzero(conv[hit])[0]), inside=(k % 2 == 1),
+                                   tri=T(G[f"trace_tri_{k}"].reshape(-1)[hit], torch.long)))
+        rec["segments"].append(dict(Z=T(Z, torch.float32), h_idx=T(np.nonzero(hit)[0]), m_idx=m_idx,
+                                    start=T(start, torch.float32), dir=T(dirs, torch.float32)))
+    return rec

@@ -8,8 +8,9 @@ of the stage-2 trainer loss against the reference's autograd (tests/golden/stage
 2e-3 relative and strided samples within 1e-3 of the tensor's largest sampled magnitude for >= 80 % of the tensors (all
 within 1e-2), in the fp32-accurate mode -- measured: 220 / 259 tensors within 1e-3, worst 8.7e-3; the tail sits in the
 stage-1 SDF / material layers whose gradient comes from only ~110 surface-hit points, where a single ReLU mask flipped
-by the 1e-5 forward error of the bf16x3 products moves the sum by ~1e-3 (same effect as in the stage-1 gate).  IORs_pred is excluded: its gradient flows through the path geometry, which the
-backward treats as a constant (documented in renderer_stage2.py / DESIGN.md).
+by the 1e-5 forward error of the bf16x3 products moves the sum by ~1e-3 (same effect as in the stage-1 gate).
+The gradient of IORs_pred flows through the path geometry: test_ior_network_gradient_through_the_path_geometry checks it
+(and the position gradients of every field that carry it) against the reference's autograd.
 """
 import os
 
@@ -17,7 +18,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, make_stage2
+from conftest import GOLDEN, make_stage2, stage2_rec_from_golden
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -146,7 +147,7 @@ def test_parameter_gradients_match_reference(net, golden):
             continue
         name = key[5:]
         if name.startswith("IORs_pred"):
-            continue
+            continue            # render_core on the reference's constant lists: no geometry graph (see the IoR test below)
         ref = torch.from_numpy(GG[key])
         ref_norm = float(GG["gradnorm/" + name])
         p = named[name]
@@ -170,6 +171,108 @@ def test_parameter_gradients_match_reference(net, golden):
         print("   %-60s %.2e %.2e" % r)
     assert checked >= 250, checked
     assert len(bad) <= 0.20 * checked, bad[:8]
+
+
+def _ior_backward(net, G, GG):
+    """Trainer loss backward with the path geometry rebuilt as a function of IORs_pred (Stage2Renderer._replay_geometry on
+    the reference's own discrete trace decisions)."""
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    pathes, converges, directions, iors, bkgr, nmesh = _lists(G)
+    net._prepare()
+    rec = stage2_rec_from_golden(G, DEV)
+    net.cfg["debug_geometry_grads"] = True
+    try:
+        p2, d2, n2 = net._replay_geometry(o, d, rec, pathes, directions, nmesh)
+    finally:
+        net.cfg["debug_geometry_grads"] = False
+    for k in range(len(pathes)):
+        assert torch.equal(p2[k].detach(), pathes[k])              # straight-through: values are the trace's own
+    gt = torch.from_numpy(GG["gt"]).to(DEV)
+    tm = torch.from_numpy(G["tir_mask"]).to(DEV)
+    net.zero_grad()
+    out = net.render_core(o, d, p2, converges, d2, bkgr, n2, iors, None, cos_anneal_ratio=0.2, step=10000, is_train=True,
+                          is_nerf=True)
+    loss = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
+    loss.backward()
+    return loss, net._geo_debug
+
+
+@pytest.mark.parametrize("precision,tol_geo,tol_par", [("split", 2e-3, 1e-3), ("bf16", 0.1, 2e-2)])
+def test_ior_network_gradient_through_the_path_geometry(golden, precision, tol_geo, tol_par):
+    """d loss / d IORs_pred flows through the refracted sample positions into every field's input (ZT:1642-1684).
+    Checked against the reference's autograd: (1) the gradient arriving at the path points, segment directions and mesh
+    normals (tests/golden/stage2_geomgrads_R64.npz: position-gradient kernels of NeRF++, the inner SDF + shading, the
+    surface shading and the compositing) in relative L2 norm -- measured 1.2e-3 / 6.8e-2 (split / bf16) on the inner
+    segment, whose points go through the PE-6 Hessian of the SDF gradient; (2) the gradient of every IoR-network
+    parameter (strided samples + norm, tests/golden/stage2_grads_R64.npz) at the 1e-3 (fp32-accurate mode) / 2e-2 (bf16)
+    gradient gates -- measured worst 2.5e-4 / 1.5e-2."""
+    GG = np.load(os.path.join(GOLDEN, "stage2_grads_R64.npz"))
+    GE = np.load(os.path.join(GOLDEN, "stage2_geomgrads_R64.npz"))
+    net_ = make_stage2(precision).cuda()
+    loss, geo = _ior_backward(net_, golden, GG)
+    assert abs(loss.item() - float(GG["loss"])) < (1e-4 if precision == "split" else 5e-3)
+    worst = []
+    for key, lst in (("d_path", geo["pathes"]), ("d_dir", geo["directions"]), ("d_nmesh", geo["gradient_mesh"])):
+        for k, t_ in enumerate(lst):
+            name = f"{key}_{k}"
+            if name not in GE.files:
+                continue
+            ref = torch.from_numpy(GE[name])
+            if ref.numel() == 0 or ref.abs().max().item() == 0.0:
+                continue
+            assert t_.grad is not None, name
+            got = t_.grad.cpu()
+            assert got.shape == ref.shape, (name, got.shape, ref.shape)
+            rel = (got - ref).abs().max().item() / ref.abs().max().item()
+            worst.append((name, rel, ((got - ref).double().norm() / ref.double().norm()).item()))
+    print(f"[stage 2, {precision}] geometry gradients (tensor, worst element / largest entry, relative L2 error):",
+          [(n_, round(r, 5), round(l2, 5)) for n_, r, l2 in worst])
+    assert len(worst) >= 5, worst
+    named = dict(net_.named_parameters())
+    rep = []
+    for key in GG.files:
+        if not key.startswith("grad/IORs_pred"):
+            continue
+        name = key[5:]
+        ref, ref_norm = torch.from_numpy(GG[key]), float(GG["gradnorm/" + name])
+        p = named[name]
+        assert p.grad is not None and ref_norm > 0, name
+        g = p.grad.detach().reshape(-1).cpu()
+        idx = torch.linspace(0, g.numel() - 1, min(g.numel(), 64)).long()
+        scale = max(ref.abs().max().item(), ref_norm / max(g.numel(), 1) ** 0.5)
+        rep.append((name, (g[idx] - ref).abs().max().item() / scale, abs(p.grad.double().norm().item() - ref_norm) / ref_norm))
+    print(f"[stage 2, {precision}] IORs_pred gradients (name, sampled rel. error, norm rel. error):")
+    for r in rep:
+        print("   %-40s %.2e %.2e" % r)
+    assert len(rep) == 12, len(rep)
+    for name, rel, l2 in worst:
+        assert l2 < tol_geo, (name, rel, l2)
+    for name, rel, nrel in rep:
+        assert rel < tol_par and nrel < tol_par, (name, rel, nrel)
+
+
+def test_render_trains_the_ior_network_end_to_end(net, golden):
+    """Stage2Renderer.render (own ray_trace + replay): IORs_pred receives a finite, non-zero gradient, the forward
+    colours are those of the no-grad render, and cfg['frozen_ior'] switches the geometry graph off."""
+    G = golden
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    with torch.no_grad():
+        ref = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+    net.zero_grad()
+    out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+    assert (out["ray_rgb"] - ref["ray_rgb"]).abs().max().item() < 1e-6
+    (out["ray_rgb"].sum() + out["gradient_error"].mean()).backward()
+    for name, p in net.IORs_pred.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.abs().max().item() > 0, name
+    net.zero_grad()
+    net.cfg["frozen_ior"] = True
+    try:
+        out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+        out["ray_rgb"].sum().backward()
+    finally:
+        net.cfg["frozen_ior"] = False
+    assert all(p.grad is None or p.grad.abs().max().item() == 0 for p in net.IORs_pred.parameters())
+    assert net.stage1_network.outer_nerf.pts_linears[0].weight.grad is not None
 
 
 def test_bf16_mode_gradients_are_close(golden):

@@ -70,6 +70,10 @@ def run(R=4096, train_iters=20):
         return loss
     t_train = timeit(train_step, iters=train_iters, warm=6, per_iter=True)
     ms_train, ms_train_mean = t_train[len(t_train) // 2], sum(t_train) / len(t_train)
+    net.cfg["frozen_ior"] = True            # geometry constant: no replay, no position-gradient kernels
+    t_frozen = timeit(train_step, iters=train_iters, warm=3, per_iter=True)
+    net.cfg["frozen_ior"] = False
+    ms_frozen = t_frozen[len(t_frozen) // 2]
     return {
         "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
                     f"{R} rays, bf16 mode",
@@ -80,8 +84,9 @@ def run(R=4096, train_iters=20):
         "full_forward": {"rays": R, "ms": ms_full, "rays_per_s": R / ms_full * 1e3},
         "train_step": {"rays": R, "ms": ms_train, "rays_per_s": R / ms_train * 1e3, "ms_mean": ms_train_mean,
                        "ms_min_max": [t_train[0], t_train[-1]], "timing": f"median of {train_iters} per-step CUDA-event timings",
-                       "note": "forward + backward w.r.t. all field parameters + Adam; IORs_pred gradient (through the "
-                               "path geometry) not included"},
+                       "note": "forward + backward w.r.t. all parameters (incl. IORs_pred through the path geometry) + Adam"},
+        "train_step_frozen_ior": {"rays": R, "ms": ms_frozen, "rays_per_s": R / ms_frozen * 1e3,
+                                  "note": "cfg['frozen_ior']: path geometry constant, IORs_pred not trained"},
     }
 
 
