@@ -96,9 +96,29 @@ def global_count(n_local, device, group=None):
     return t[0]
 
 
+def init_sdf_reg(out, step, reg_step=1000, small_threshold=0.1, large_threshold=1.05):
+    """InitSDFRegLoss (network/loss.py:111-140) on the renderer's `sdf_pts` / `sdf_vals` warm-up outputs (emitted while
+    step < 1000): pushes the SDF below |x| - 0.1 near the origin and above |x| - 1.05 outside the unit sphere, annealed by
+    (cos(pi step / 1000) + 1) / 2.  The reference's normalisations are reproduced as written (the `small` term divides
+    its mean by (mean > 1e-5) + 1e-3).  Returns loss_sdf_large + loss_sdf_small (0-d), or None outside the warm-up."""
+    if "sdf_vals" not in out or "sdf_pts" not in out or step >= reg_step:
+        return None
+    norm = torch.norm(out["sdf_pts"], dim=-1)
+    sdf = out["sdf_vals"]
+    # masked sums instead of boolean indexing: no host synchronisation (an empty mask gives 0, as in the reference)
+    m_s = (norm < small_threshold).float()
+    small = (torch.clamp(sdf - (norm - small_threshold), min=0.0) * m_s).sum() / m_s.sum().clamp_min(1.0)
+    small = small / ((small > 1e-5).float() + 1e-3)
+    m_l = (norm > large_threshold).float()
+    large = torch.clamp((norm - large_threshold) - sdf, min=0.0) * m_l
+    large = large.sum() / ((large > 1e-5).float().sum() + 1e-3)
+    return (large + small) * ((math.cos(step / reg_step * math.pi) + 1.0) / 2.0)
+
+
 def stage1_loss(out, loss_rgb, r_global, group=None, eikonal_weight=0.1, step=0, occ_loss_step=None,
-                outer_reg_weight=0.5, share=1.0, n_in_global=None):
-    """Trainer loss (trainer_zero.py:157-161 over the loss.py adapters of spherepot.yaml) with global denominators.
+                outer_reg_weight=0.5, share=1.0, n_in_global=None, outer_reg_step=15000, sdf_reg=True):
+    """Trainer loss (trainer_zero.py:157-161 over the loss.py adapters of spherepot.yaml: nerf_render, eikonal, std,
+    init_sdf_reg, occ, mask, outer_reg) with global denominators.
     `out` is the renderer's outputs dict of THIS rank (or of one chunk of its rays: `share` = the chunk's fraction of
     the rank's rays), `loss_rgb` [R_chunk]; returns the local share whose SUM over ranks (and chunks) is the global
     loss, so gradients are summed, not averaged, across ranks."""
@@ -116,10 +136,17 @@ def stage1_loss(out, loss_rgb, r_global, group=None, eikonal_weight=0.1, step=0,
         n_in = global_count(gerr.shape[0] if has_inner else 0, dev, group)
         if has_inner:
             loss = loss + eikonal_weight * share * gerr.sum() / torch.clamp(n_in, min=1.0)
-    if occ_loss_step is not None and step >= occ_loss_step:
+    if occ_loss_step is not None and step >= occ_loss_step and "loss_occ" in out:
         # OccLoss (loss.py:97-98) is a mean over the probed samples of one rank; ranks (and chunks) are averaged
         loss = loss + share * out["loss_occ"].mean() / world
+    if step >= outer_reg_step and "color_bkgr" in out:
+        # OuterRegLoss has its own hard-coded gate (loss.py:206: step >= 15000), independent of occ_loss_step
         loss = loss + outer_reg_weight * ((out["color_bkgr"] - out["color_spec"]) ** 2).sum() / (3.0 * r_global)
+    if sdf_reg:
+        # InitSDFRegLoss (first 1000 steps): its count-based denominators are per batch; ranks / chunks are averaged
+        reg = init_sdf_reg(out, step)
+        if reg is not None:
+            loss = loss + share * reg / world
     return loss
 
 
@@ -139,7 +166,7 @@ class DataParallelTrainer:
     """
 
     def __init__(self, module, render_fn, rgb_loss_fn, adam_fn=cuda_adam, lr_fn=warm_up_cos_lr, group=None,
-                 eikonal_weight=0.1, occ_loss_step=None, sample_fn=None, core_fn=None, count_fn=None):
+                 eikonal_weight=0.1, occ_loss_step=None, sample_fn=None, core_fn=None, count_fn=None, outer_reg_step=15000):
         """sample_fn(rays_o, rays_d, near, far, step) -> z_vals; count_fn(rays_o, rays_d, z_vals) -> number of inner samples
         (a 0-d device tensor); core_fn(rays_o, rays_d, z_vals, step) -> outputs dict.  When the three are given and a step
         is split into several chunks, the step runs in two phases -- sample every chunk and count its inner samples
@@ -150,7 +177,7 @@ class DataParallelTrainer:
         self.render_fn, self.rgb_loss_fn, self.adam_fn, self.lr_fn = render_fn, rgb_loss_fn, adam_fn, lr_fn
         self.sample_fn, self.core_fn, self.count_fn = sample_fn, core_fn, count_fn
         self.group = group
-        self.eikonal_weight, self.occ_loss_step = eikonal_weight, occ_loss_step
+        self.eikonal_weight, self.occ_loss_step, self.outer_reg_step = eikonal_weight, occ_loss_step, outer_reg_step
         self.last = {}
 
     def step(self, rays_o, rays_d, rgbs, near, far, step, chunk=None):
@@ -180,7 +207,7 @@ class DataParallelTrainer:
             loss_rgb = self.rgb_loss_fn(out["ray_rgb"], rgbs[sl])
             share = (sl.stop - sl.start) / r_local
             loss = stage1_loss(out, loss_rgb, r_global, self.group, self.eikonal_weight, step, self.occ_loss_step,
-                               share=share, n_in_global=n_in_global)
+                               share=share, n_in_global=n_in_global, outer_reg_step=self.outer_reg_step)
             loss.backward()
             total = total + loss.detach()
             n_in_seen += int(out["gradient_error"].shape[0]) if "transmission" in out else 0

@@ -35,7 +35,8 @@ _STUBS = [
     "open3d", "trimesh", "trimesh.exchange", "trimesh.exchange.export", "trimesh.curvature", "pymesh",
     "skimage", "skimage.io", "skimage.metrics", "skimage.transform", "h5py", "plyfile", "transforms3d",
     "transforms3d.axangles", "transforms3d.euler", "transforms3d.quaternions", "imageio", "optix", "cupy",
-    "mcubes", "nvdiffrast", "nvdiffrast.torch", "matplotlib", "matplotlib.pyplot", "matplotlib.cm",
+    "mcubes", "nvdiffrast", "nvdiffrast.torch", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.lines",
+    "matplotlib.backends", "matplotlib.backends.backend_agg", "matplotlib.figure",
     "tensorboardX", "pymeshlab", "tqdm", "lpips", "kornia", "pyexr", "OpenEXR", "Imath",
 ]
 
