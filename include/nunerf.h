@@ -180,7 +180,11 @@ int nunerf_alpha_importance(const float* z, const float* alpha, int R, int n, in
  *   background-only composite.  Backward recomputes the transmittance instead of storing it.
  *   With the per-ray map, S <= 160 and all list pointers 16-byte aligned the persistent shared-memory-staged kernels
  *   run (a ray's list runs are fetched as whole 16-byte chunks: reads may touch the <= 3 elements that share a chunk
- *   with the run -- always inside the same aligned buffer --, writes never leave the run); any other case (slot form,
+ *   with the run, writes never leave the run.  BUFFER CONTRACT: alpha_in / color_in / alpha_out / color_out (and the
+ *   gradient lists of the backward) must be ALLOCATED with a size that is a multiple of 16 bytes -- the last chunk of the
+ *   last ray is read whole, i.e. up to 12 bytes past the logical end of a list whose length is not a multiple of 4
+ *   floats; the entry points cannot check allocation sizes.  Callers with exact-size buffers set
+ *   NUNERF_COMPOSITE_LEGACY=1 or pad); any other case (slot form,
  *   S > 160, unaligned views) takes the lane-per-sample kernels.  `weights` (dense [R,S], optional) is only needed by
  *   the validation outputs; pass NULL in training.  NUNERF_COMPOSITE_LEGACY=1 forces the lane-per-sample kernels.
  */

@@ -171,6 +171,20 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def on_device(t):
+    """Context for launching on the device (and current stream of the device) that owns tensor `t`: the entry points
+    take raw pointers, so a launch from a process whose current device differs from the tensors' would run on the wrong
+    GPU.  One process per GPU (torchrun + torch.cuda.set_device(LOCAL_RANK)) never needs it; the renderers use it once
+    per call."""
+    return torch.cuda.device(t.device)
+
+
+def require_current_device(t):
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"nu_nerf_b200: tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                           "-- call torch.cuda.set_device() first (one process per GPU) or wrap the call in torch.cuda.device()")
+
+
 def check(rc, name):
     if rc != 0:
         raise RuntimeError(f"{name} failed ({rc}): {lib.nunerf_last_error().decode()}")

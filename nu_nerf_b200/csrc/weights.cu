@@ -80,7 +80,7 @@ weights_backward_kernel(const nunerf_wdesc_t* __restrict__ descs, const int32_t*
   const int src_row = (d.src_row0 + r_dst + d.row_rot) % d.N;
   const float* vrow = d.v + (long long)src_row * d.ld;
   const float* grow = d.dW + (long long)(d.dw_row_off + r_dst) * d.lddw;
-  float* dvrow = d.dv + (long long)src_row * d.ld;
+  float* dvrow = d.dv ? d.dv + (long long)src_row * d.ld : nullptr;   // null: the parameter is frozen (requires_grad=False)
   if (d.g) {
     // W = (g / |v|) v  ->  dg = (dW . v) / |v| ;  dv = (g / |v|) (dW - v (dW . v) / |v|^2)
     // (the two terms of dv nearly cancel for some layers: accumulate the row reductions in fp64)
@@ -95,15 +95,15 @@ weights_backward_kernel(const nunerf_wdesc_t* __restrict__ descs, const int32_t*
     ss = block_sum_d(ss, red);
     const double inv = 1.0 / sqrt(ss);
     const double gi = (double)d.g[src_row] * inv;
-    if (threadIdx.x == 0) d.dg[src_row] += (float)(dot * inv);
+    if (threadIdx.x == 0 && d.dg) d.dg[src_row] += (float)(dot * inv);
     const double proj = dot / ss;
-    for (int c = threadIdx.x; c < d.K; c += WTHREADS) {
+    for (int c = threadIdx.x; dvrow && c < d.K; c += WTHREADS) {
       int sc = c + d.col_rot;
       if (sc >= d.K) sc -= d.K;
       dvrow[sc] += (float)(gi * ((double)grow[c] * (double)d.scale - (double)vrow[sc] * proj));
     }
   } else {
-    for (int c = threadIdx.x; c < d.K; c += WTHREADS) {
+    for (int c = threadIdx.x; dvrow && c < d.K; c += WTHREADS) {
       int sc = c + d.col_rot;
       if (sc >= d.K) sc -= d.K;
       dvrow[sc] += grow[c] * d.scale;

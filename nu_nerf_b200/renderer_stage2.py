@@ -223,6 +223,8 @@ class Stage2Renderer(nn.Module):
         dev = self.deviation_network_inner.variance.device
         if not torch.cuda.is_available() or dev.type != "cuda":
             raise RuntimeError("nu_nerf_b200 renders on a CUDA device only (no CPU fallback): move the module with .cuda()")
+        from ._lib import require_current_device
+        require_current_device(self.deviation_network_inner.variance)       # the C entry points launch on the current device's stream
         eng = _engine()
         self.stage1_network.cfg["precision"] = self.cfg["precision"]
         w1 = self.stage1_network._prepare()

@@ -231,6 +231,8 @@ class NeROShapeRenderer(nn.Module):
         dev = self.deviation_network.variance.device
         if not torch.cuda.is_available() or dev.type != "cuda":
             raise RuntimeError("nu_nerf_b200 renders on a CUDA device only (no CPU fallback): move the module with .cuda()")
+        from ._lib import require_current_device
+        require_current_device(self.deviation_network.variance)       # the C entry points launch on the current device's stream
         eng = _engine()
         key = (self._planes(),) + tuple(p.data_ptr() for p in self.parameters())
         if getattr(self, "_w", None) is None or self._w_key != key:

@@ -129,7 +129,16 @@ class WeightBank:
         self.gflat.zero_()
 
     def backward(self):
-        """One launch: accumulated dW / db -> += into the source parameters' .grad (allocated if missing)."""
+        """One launch: accumulated dW / db -> += into the source parameters' .grad (allocated if missing).
+        Parameters with requires_grad=False are skipped (null gradient pointers in the descriptor table).
+
+        Autograd contract of the engine's nodes (renderer_zerothick._RenderCoreFn / _SdfValueFn, renderer_stage2._NerfFn /
+        _InnerFn / _SurfaceFn): parameter gradients are ADDED to .grad here, from inside backward, and the nodes return
+        None for their parameter inputs.  Supported: loss.backward() with any optimiser reading .grad (what the
+        reference trainer does).  Not supported: torch.autograd.grad() w.r.t. parameters, per-parameter grad hooks /
+        DistributedDataParallel bucket hooks (use nu_nerf_b200.dist for data parallelism), retain_graph double
+        backward.  The .grad tensors allocated here are views of one pooled buffer reused across steps: a caller that
+        keeps last step's .grad after zero_grad(set_to_none=True) must clone it."""
         ptrs = []
         # parameters without a .grad (first step, or after zero_grad(set_to_none=True)) get views of ONE zero-filled
         # buffer: one fill launch instead of one per tensor (~300 for a stage-2 renderer)
@@ -137,7 +146,7 @@ class WeightBank:
         for d in self.denses:
             if d.has_grad:
                 for p in (d.v, d.g, d.bias):
-                    if p is not None and p.grad is None and id(p) not in seen:
+                    if p is not None and p.requires_grad and p.grad is None and id(p) not in seen:
                         seen.add(id(p))
                         missing.append(p)
         if missing:
@@ -158,8 +167,8 @@ class WeightBank:
         for d in self.denses:
             if not d.has_grad:
                 continue
-            ptrs.append((d.v.grad.data_ptr(), d.g.grad.data_ptr() if d.g is not None else 0,
-                         d.bias.grad.data_ptr() if d.bias is not None else 0))
+            gp = lambda p: p.grad.data_ptr() if (p is not None and p.requires_grad) else 0
+            ptrs.append((gp(d.v), gp(d.g), gp(d.bias)))
         ptrs = tuple(ptrs)
         if ptrs != self._grad_ptrs:
             j = 0
@@ -169,7 +178,7 @@ class WeightBank:
                 h = self._host[i]
                 dv, dg, dbias = ptrs[j]
                 j += 1
-                h.dv, h.dg, h.dbias = dv, (dg or None), (dbias or None)
+                h.dv, h.dg, h.dbias = (dv or None), (dg or None), (dbias or None)
                 if d.bias is None:
                     h.db = None
             self._upload()

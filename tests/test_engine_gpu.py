@@ -591,6 +591,39 @@ def test_training_steps_reduce_the_loss():
     assert losses[-1] < 0.8 * losses[0], losses
 
 
+def test_frozen_parameters_receive_no_gradient():
+    """requires_grad=False on field parameters (e.g. a frozen NeRF++ background): the weight bank skips them (null
+    gradient pointers), every other gradient is unchanged; a tensor on another device than the current one is refused."""
+    from oracle import nunerf_oracle as orc
+    R = 128
+    o, d = (t.to(DEV) for t in orc.synthetic_rays(R))
+    near, far = torch.full((R, 1), 0.8, device=DEV), torch.full((R, 1), 4.5, device=DEV)
+    grads = []
+    for freeze in (False, True):
+        net = _renderer("bf16")
+        if freeze:
+            for p in net.outer_nerf.parameters():
+                p.requires_grad_(False)
+            net.sdf_network.layers()[2].weight_g.requires_grad_(False)
+        out = net.render(o, d, near, far, None, 0, 0.2, is_train=True, step=10000, is_nerf=True)
+        (out["ray_rgb"].sum() + out["gradient_error"].mean()).backward()
+        grads.append({k: (None if p.grad is None else p.grad.clone()) for k, p in net.named_parameters()})
+    free, frozen = grads
+    n_frozen = 0
+    for k, g in frozen.items():
+        if k.startswith("outer_nerf.") or k.endswith("lin2.weight_g") and k.startswith("sdf_network"):
+            assert g is None, k
+            n_frozen += 1
+        elif free[k] is not None:
+            assert g is not None and torch.equal(g, free[k]), k
+    assert n_frozen >= 20
+    if torch.cuda.device_count() > 1:
+        net = _renderer("bf16").to("cuda:1")
+        with pytest.raises(RuntimeError, match="current CUDA device"):
+            net.render(o.to("cuda:1"), d.to("cuda:1"), near.to("cuda:1"), far.to("cuda:1"), None, 0, 0.2, is_train=True,
+                       step=10000, is_nerf=True)
+
+
 @pytest.mark.parametrize("precision,tol", [("split", 1e-4), ("bf16", 5e-3)])
 def test_edge_cases_single_ray_and_empty_inner_set(precision, tol):
     """Ragged / empty inputs (the reference's boolean-mask indexing degenerates silently; the compacted engine must too):
