@@ -615,7 +615,8 @@ def test_frozen_parameters_receive_no_gradient():
             assert g is None, k
             n_frozen += 1
         elif free[k] is not None:
-            assert g is not None and torch.equal(g, free[k]), k
+            # (the weight-gradient GEMMs accumulate with atomics: equal up to summation order)
+            assert g is not None and (g - free[k]).abs().max().item() <= 1e-4 * max(free[k].abs().max().item(), 1e-6), k
     assert n_frozen >= 20
     if torch.cuda.device_count() > 1:
         net = _renderer("bf16").to("cuda:1")
