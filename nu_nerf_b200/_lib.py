@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnunerf_b200.so")
+LIB_PATH = os.environ.get("NUNERF_LIB", os.path.join(_HERE, "libnunerf_b200.so"))     # NUNERF_LIB: A/B builds of the library
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(f"{LIB_PATH} not found: build it with `make` (or __graft_entry__.build()); "

@@ -166,9 +166,65 @@ class NeROShapeRenderer(nn.Module):
 
     # ------------------------------------------------------------------ data
     def _init_dataset(self):
-        """The reference builds the ray table from an image database here (ZT:167-197).  Dataset ingest is outside
-        the hot path: attach a ray source with `set_ray_source` (bench.py / the trainer adapter do)."""
+        """ZT:167-197.  Dataset ingest (image decoding, pose files) is outside the hot path and stays the reference's own
+        host code: when this module runs inside the reference tree (the one-line import swap of INTEGRATION.md) and
+        cfg['database_name'] is set, the reference's `dataset.database` loads the views and `attach_database` turns
+        them into the device-side ray table; anywhere else attach sources with set_ray_source / set_eval_source /
+        attach_database."""
         self.ray_source = None
+        if not self.cfg.get("database_name"):
+            return
+        try:
+            from dataset.database import parse_database_name, get_database_split     # the reference's package
+        except ImportError:
+            return
+        database = parse_database_name(self.cfg["database_name"], self.cfg.get("dataset_dir"))
+        train_ids, test_ids = get_database_split(database)
+        self.attach_database(database, train_ids, test_ids)
+
+    def attach_database(self, database, train_ids, test_ids=()):
+        """Ray sources from any object with the reference's BaseDatabase interface (get_image -> uint8 [h,w,3], get_pose
+        [3,4], get_K [3,3], get_depth -> (depth, mask)): build_imgs_info + _construct_(nerf_)ray_batch + the shuffled
+        slicing of train_step (ZT:20-55, :199-255, :447-466) on the device-side feeder, and the per-view source of
+        test_step (ZT:397-411, without the optional test_downsample_ratio blur).  The tables are built on first use, on
+        the device the module lives on then."""
+        self.database = database
+        self.train_ids, self.test_ids = np.asarray(train_ids), list(test_ids)
+        self.train_num, self.test_num = len(self.train_ids), len(self.test_ids)
+        self._tables = None
+
+        def info(ids, with_depth):
+            imgs = np.stack([database.get_image(i) for i in ids], 0).astype(np.float32) / 255.0     # color_map_forward
+            out = {"imgs": torch.from_numpy(imgs).permute(0, 3, 1, 2),
+                   "Ks": torch.from_numpy(np.stack([database.get_K(i) for i in ids], 0).astype(np.float32)),
+                   "poses": torch.from_numpy(np.stack([database.get_pose(i) for i in ids], 0).astype(np.float32))}
+            if self.is_nerf or with_depth:
+                dm = [database.get_depth(i) for i in ids]
+                out["depths"] = torch.from_numpy(np.stack([d_[0] for d_ in dm], 0).astype(np.float32))
+                out["masks"] = torch.from_numpy(np.stack([d_[1] for d_ in dm], 0))
+            return out
+
+        def tables():
+            if self._tables is None:
+                from . import feeder
+                dev = self.deviation_network.variance.device
+                tr = {k: v.to(dev) for k, v in info(self.train_ids, False).items()}
+                if self.is_nerf:
+                    batch, _, _, _ = feeder.construct_nerf_ray_batch(tr["imgs"], tr["Ks"], tr["poses"], tr["masks"])
+                    train = feeder.DeviceRayFeeder(batch, perm_device="cpu")
+                else:
+                    batch, _, _, _ = feeder.construct_ray_batch(tr["imgs"], tr["Ks"])
+                    train = feeder.DeviceRayFeeder(batch, poses=tr["poses"], perm_device="cpu")
+                ev = None
+                if self.test_num:
+                    te = {k: v.to(dev) for k, v in info(self.test_ids, True).items()}
+                    ev = feeder.image_eval_source(te["imgs"], te["Ks"], te["poses"], is_nerf=self.is_nerf,
+                                                  depths=te["depths"], masks=te["masks"])
+                self._tables = (train, ev)
+            return self._tables
+        self.ray_source = lambda step, n: tables()[0](step, n)
+        if self.test_num:
+            self.eval_source = lambda index: tables()[1](index)
 
     def set_ray_source(self, fn):
         self.ray_source = fn
@@ -319,7 +375,6 @@ class NeROShapeRenderer(nn.Module):
                 torch.zeros(0, device=rgb.device)
         if not is_train:
             outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=w))
-        outputs["_weights"] = weights
         return outputs
 
     # ------------------------------------------------------------------ ZT:695-723, field.py:501-554
@@ -566,9 +621,7 @@ class NeROShapeRenderer(nn.Module):
         step = data["step"]
         if "eval" in data:
             return self.test_step(data["index"], step)
-        out = self.train_step(step)
-        out.pop("_weights", None)
-        return out
+        return self.train_step(step)
 
 
 from .renderer_stage2 import Stage2Renderer  # noqa: E402  (ZT:868-2011)

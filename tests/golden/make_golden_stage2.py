@@ -106,6 +106,49 @@ def main():
         vals, idx = strided(p_.grad)
         gres["grad/" + name] = vals
         gres["gradnorm/" + name] = np.array(p_.grad.double().norm().item())
+    # ---- conditioning of every parameter gradient: the reference's OWN gradient under operand rounding at the precision
+    # of the product's fp32-accurate mode (bf16 hi + lo planes = 16 mantissa bits: relative rounding <= 2^-17).  Two
+    # trials with every weight multiplied by 1 + 2^-17 u, u ~ U(-1, 1); recorded with the metrics of the parity test.
+    base = {n_: p_.grad.detach().clone() for n_, p_ in net.named_parameters() if p_.grad is not None}
+    saved = {n_: p_.detach().clone() for n_, p_ in net.named_parameters()}
+    floors = {n_: [0.0, 0.0] for n_ in base}
+    gen = torch.Generator().manual_seed(11)
+    for trial in range(2):
+        with torch.no_grad():
+            for n_, p_ in net.named_parameters():
+                if p_.dtype.is_floating_point and p_.numel() > 1:
+                    p_.copy_(saved[n_] * (1.0 + 2.0 ** -17 * (2.0 * torch.rand(p_.shape, generator=gen) - 1.0)))
+        net.zero_grad()
+        lists = net.ray_trace(o, d)
+        # same discrete trace as the unperturbed run is required for a like-for-like comparison: re-run ray_trace (the
+        # geometry depends on IORs_pred) and keep the trial only if the hit / TIR masks are unchanged
+        p2, c2, d2, i2, b2, g2, t2 = lists
+        same = len(p2) == len(pathes) and all(torch.equal(a_, b_) for a_, b_ in zip(c2, converges)) and torch.equal(t2, tir_mask)
+        if not same:
+            print("trial", trial, "changed the discrete trace: skipped")
+            continue
+        out_t = net.render_core(o, d, p2, c2, d2, b2, g2, i2, None, cos_anneal_ratio=0.2, step=10000, is_train=True,
+                                is_nerf=True)
+        tm_t = t2.detach()
+        (net.compute_rgb_loss(out_t["ray_rgb"] * tm_t, gt * tm_t).mean() + (0.02 * out_t["gradient_error"]).mean()).backward()
+        for n_, p_ in net.named_parameters():
+            if n_ not in base or p_.grad is None:
+                continue
+            g0, g1 = base[n_].reshape(-1), p_.grad.detach().reshape(-1)
+            idx = torch.linspace(0, g0.numel() - 1, min(g0.numel(), 64)).long()
+            nrm = g0.double().norm().item()
+            if nrm == 0.0:
+                continue
+            scale = max(g0[idx].abs().max().item(), nrm / max(g0.numel(), 1) ** 0.5)
+            floors[n_][0] = max(floors[n_][0], (g1[idx] - g0[idx]).abs().max().item() / scale)
+            floors[n_][1] = max(floors[n_][1], abs(g1.double().norm().item() - nrm) / nrm)
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            p_.copy_(saved[n_])
+    for n_, (f_s, f_n) in floors.items():
+        gres["floor/" + n_] = np.array([f_s, f_n])
+    worst = sorted(floors.items(), key=lambda kv: -kv[1][0])[:8]
+    print("largest operand-rounding floors (sampled, norm):", [(k_, round(v_[0], 5), round(v_[1], 5)) for k_, v_ in worst])
     np.savez_compressed(os.path.join(OUT, "stage2_grads_R64.npz"), **gres)
     print("params with grad:", sum(1 for k in gres if k.startswith("grad/")), "loss", float(loss))
     for f in ("stage2_init.npz", "stage2_R64.npz", "stage2_grads_R64.npz"):

@@ -49,6 +49,7 @@ def _run(trainer, o, d, gt, near, far, chunk, steps=2):
         trainer.step(o, d, gt, near, far, STEP + s, chunk=chunk)
         if s == 0:
             grads = trainer.fp.grad.clone()
+            trainer.n_in_first = trainer.last["n_in_step"]      # (later steps see weights that differ by Adam's sign noise)
     torch.cuda.synchronize()
     return grads.cpu(), trainer.fp.flat.clone().cpu()
 
@@ -71,7 +72,7 @@ def test_chunked_step_equals_the_unsplit_step():
     g1, w1 = _run(t1, o, d, gt, near, far, chunk=R)
     _, t2 = _build(dev)
     g2, w2 = _run(t2, o, d, gt, near, far, chunk=R // 4)
-    assert t2.last["n_in_step"] == t1.last["n_in_step"] > 0
+    assert t2.n_in_first == t1.n_in_first > 0
     _compare(g2, w2, g1, w1, 2 * nd.warm_up_cos_lr(STEP))
 
 

@@ -5,6 +5,7 @@ Runs on CPU tensors (the feeder is device-agnostic torch indexing); on the GPU b
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from conftest import GOLDEN
@@ -103,3 +104,65 @@ def test_image_eval_source_views():
         assert torch.allclose(v["rays_o"], ro, atol=1e-6) and torch.allclose(v["rays_d"], rd, atol=1e-6)
         assert "gt_depth" not in v
 
+
+
+class _FakeDatabase:
+    """The subset of the reference's BaseDatabase interface the renderer reads (dataset/database.py): uint8 images,
+    [3,4] poses, [3,3] intrinsics, (depth, mask)."""
+
+    def __init__(self, n, h, w, seed=6):
+        g = np.random.default_rng(seed)
+        self.imgs = g.integers(0, 256, size=(n, h, w, 3), dtype=np.uint8)
+        self.K = np.array([[20.0, 0, w / 2], [0, 20.0, h / 2], [0, 0, 1]], np.float32)
+        q = np.linalg.qr(g.standard_normal((n, 3, 3)))[0]
+        self.poses = np.concatenate([q, g.standard_normal((n, 3, 1))], -1).astype(np.float32)
+        self.depth = g.random((n, h, w)).astype(np.float32)
+        self.mask = g.random((n, h, w)) > 0.5
+
+    def get_image(self, i): return self.imgs[i]
+    def get_pose(self, i): return self.poses[i]
+    def get_K(self, i): return self.K
+    def get_depth(self, i): return self.depth[i], self.mask[i]
+
+
+@pytest.mark.parametrize("is_nerf", [True, False])
+def test_attach_database_builds_the_ray_sources(is_nerf):
+    """NeROShapeRenderer.attach_database (the dataset half of _init_dataset, ZT:167-197): a BaseDatabase-like object
+    becomes the shuffled train ray source and the per-view eval source -- every served ray is a row of the all-view ray
+    table with its own pixel colour, and batches do not repeat rays within an epoch."""
+    from nu_nerf_b200 import feeder
+    from nu_nerf_b200.renderer_zerothick import NeROShapeRenderer, load_default_cfg
+    n, h, w = 4, 5, 6
+    db = _FakeDatabase(n, h, w)
+    cfg = load_default_cfg()
+    cfg["database_name"] = None                      # no reference database package here: attach explicitly
+    cfg["is_nerf"] = is_nerf
+    torch.manual_seed(0)
+    net = NeROShapeRenderer(cfg, training=True)
+    assert net.ray_source is None
+    net.attach_database(db, train_ids=[0, 1, 2], test_ids=[3])
+    imgs = torch.from_numpy(db.imgs[:3].astype(np.float32) / 255.0).permute(0, 3, 1, 2)
+    Ks, poses = torch.from_numpy(np.stack([db.K] * 3)), torch.from_numpy(db.poses[:3])
+    if is_nerf:
+        full, rn, _, _ = feeder.construct_nerf_ray_batch(imgs, Ks, poses)
+        table_d = torch.nn.functional.normalize(full["rays_d"], dim=-1)
+    else:
+        full, rn, _, _ = feeder.construct_ray_batch(imgs, Ks)
+        o_, d_ = feeder.world_rays(full["dirs"], full["idxs"], poses)
+        full["rays_o"], table_d = o_, d_
+    seen = []
+    for step in range(3):
+        b = net.ray_source(step, 20)
+        assert b["rays_o"].shape == (20, 3) and b["rgbs"].shape == (20, 3)
+        d = torch.nn.functional.normalize(b["rays_d"], dim=-1)
+        for r in range(20):
+            m = ((full["rays_o"] - b["rays_o"][r]).abs().sum(-1) < 1e-5) & ((table_d - d[r]).abs().sum(-1) < 1e-5)
+            idx = m.nonzero().flatten()
+            assert idx.numel() >= 1, (step, r)
+            assert any(torch.allclose(full["rgbs"][i], b["rgbs"][r]) for i in idx.tolist())
+            seen.append(int(idx[0]))
+    assert len(set(seen)) == len(seen)               # one epoch: no ray twice
+    v = net.eval_source(0)
+    assert (v["h"], v["w"]) == (h, w) and v["rays_o"].shape == (h * w, 3)
+    assert torch.allclose(v["rgbs"], torch.from_numpy(db.imgs[3].astype(np.float32) / 255.0).reshape(-1, 3))
+    assert torch.equal(v["gt_depth"], torch.from_numpy(db.depth[3]))

@@ -27,7 +27,17 @@ torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
+import time
+t0 = time.perf_counter()
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+wall_ms = (time.perf_counter() - t0) / 5 * 1e3
 ev = prof.key_averages()
+kern = sum(e.self_device_time_total for e in ev)
+syncs = {k: sum(e.count for e in ev if e.key == k) for k in ("aten::nonzero", "aten::item", "aten::_local_scalar_dense",
+                                                             "cudaStreamSynchronize", "cudaMemcpyAsync", "cudaLaunchKernel")}
+print(f"wall per step {wall_ms:.2f} ms; sum of kernel (self device) time {kern / 1e3:.2f} ms; host-side counts {syncs}")
 rows = sorted(ev, key=lambda e: -e.device_time_total)[:28]
 tot = sum(e.device_time_total for e in ev)
 print("total device us", tot)
