@@ -76,9 +76,6 @@ __device__ __forceinline__ float softplus100(float x) {
 // ---------------------------------------------------------------- packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2)
 // The fma pipe issues one three-register FFMA per two cycles and scheduler; the packed forms do two lanes of work per
 // issue slot, which is what bounds the activation epilogues of the fused chains.
-#ifndef NUNERF_SOFTPLUS_F16X2
-#define NUNERF_SOFTPLUS_F16X2 0
-#endif
 typedef unsigned long long f32x2_t;
 __device__ __forceinline__ f32x2_t f2_pack(float a, float b) {
   f32x2_t r;
@@ -109,18 +106,8 @@ __device__ __forceinline__ void softplus100_x2(float& a, float& b, float ba, flo
   f2_unpack(x2, x0, x1);
   f2_unpack(f2_mul(x2, f2_pack(144.26950408889634f, 144.26950408889634f)), t0, t1);
   float e0, e1;
-#if NUNERF_SOFTPLUS_F16X2
-  // experiment: both exponentials in ONE MUFU operation (ex2.approx.f16x2; 11-bit results, inputs rounded to f16)
-  {
-    uint32_t h, r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(fminf(t1, -t1)), "f"(fminf(t0, -t0)));
-    asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
-    asm("{ .reg .b16 l, u; mov.b32 {l, u}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, u; }" : "=f"(e0), "=f"(e1) : "r"(r));
-  }
-#else
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(t0, -t0)));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(t1, -t1)));
-#endif
   const f32x2_t e2 = f2_pack(e0, e1);
   f32x2_t q = f2_fma(f2_pack(3.215121477842331e-4f, 3.215121477842331e-4f), e2, f2_pack(-1.3604211807250977e-3f, -1.3604211807250977e-3f));
   q = f2_fma(q, e2, f2_pack(2.8945398330688477e-3f, 2.8945398330688477e-3f));
