@@ -149,6 +149,28 @@ def angle_weighted_vertex_normals(V, F):
     return (vn / vn.norm(dim=1, keepdim=True)).float()
 
 
+def discrete_gaussian_curvature(V, F, clip=10.0):
+    """Per-vertex discrete Gaussian curvature, the replacement for PyMesh's `vertex_gaussian_curvature` attribute that
+    DiffRender.Scene reads (DiffRender.py:331, :360, clipped to [-10, 10] there).  DEFINITION (stated and pinned here,
+    because the PyMesh fork the reference builds against is not available -- parity against PyMesh itself is unpinned):
+    the angle defect 2 pi - sum of the corner angles at the vertex, divided by the barycentric vertex area (one third of
+    the area of the incident triangles).  The angle defects sum to 2 pi chi exactly (Gauss-Bonnet), and on a sphere of
+    radius r the value tends to 1 / r^2.  V [V,3], F long [F,3] -> float32 [V,1]."""
+    V = V.double()
+    tri = V[F.long()]
+    e = [tri[:, (i + 1) % 3] - tri[:, i] for i in range(3)]
+    area = 0.5 * torch.cross(e[0], -e[2], dim=-1).norm(dim=1)
+    defect = torch.full((V.shape[0],), 2.0 * np.pi, dtype=torch.float64, device=V.device)
+    varea = torch.zeros(V.shape[0], dtype=torch.float64, device=V.device)
+    for i in range(3):
+        a, b = e[i], -e[(i + 2) % 3]
+        cosv = (a * b).sum(-1) / (a.norm(dim=1) * b.norm(dim=1))
+        defect.index_add_(0, F[:, i].long(), -torch.acos(cosv.clamp(-1, 1)))
+        varea.index_add_(0, F[:, i].long(), area / 3.0)
+    k = defect / varea.clamp_min(1e-30)
+    return k.clamp(-clip, clip).float().reshape(-1, 1)
+
+
 def load_mesh(path):
     """Vertices [V,3] float64 and faces [F,3] int64 of a triangle mesh file: .npz (arrays `vertices`, `faces`) or .ply
     (ascii / binary_little_endian, as written by trimesh for data/meshes/*_simplified.ply, extract_mesh_stage1.py:43-52)."""
@@ -227,6 +249,7 @@ class Scene:
         self.optix_mesh.update_mesh(self.faces.to(torch.int32), self.vertices.to(torch.float32))
         self.normals = angle_weighted_vertex_normals(self.vertices, self.faces)
         self.tri_normals = self.normals[self.faces].reshape(-1, 9).contiguous()
+        self.gaussian_curvatures = discrete_gaussian_curvature(self.vertices, self.faces)          # [V,1]
 
     def optix_intersect(self, origin, direction):
         ray = torch.cat([origin.float(), direction.float()], dim=1)
@@ -234,7 +257,8 @@ class Scene:
         return idx.to(torch.long), T > 0
 
     def Dintersect(self, origin, direction):
-        """-> dict(u, v, t, n, x) for every ray (zeros where missed) and the hit mask."""
+        """-> dict(u, v, t, n, x, g_k) for every ray (zeros where missed) and the hit mask; g_k = the vertex Gaussian
+        curvatures interpolated with the hit's barycentric coordinates (DiffRender.py:113-116)."""
         N = origin.shape[0]
         o = origin.detach().float().contiguous()
         d = direction.detach().float().contiguous()
@@ -245,4 +269,8 @@ class Scene:
         bvh = self.optix_mesh.bvh
         call("nunerf_hit_interp", bvh.tri_verts.data_ptr(), self.tri_normals.data_ptr(), tri.data_ptr(), o.data_ptr(),
              d.data_ptr(), N, uvt.data_ptr(), x.data_ptr(), n.data_ptr())
-        return {"u": uvt[:, 0], "v": uvt[:, 1], "t": uvt[:, 2], "n": n, "x": x, "faces_ind": tri}, hit > 0
+        u, v = uvt[:, 0:1], uvt[:, 1:2]
+        hmask = hit > 0
+        kf = self.gaussian_curvatures[self.faces[tri.long().clamp(0, self.faces.shape[0] - 1)]].squeeze(-1)     # [N,3]
+        g_k = ((1.0 - u - v) * kf[:, 0:1] + u * kf[:, 1:2] + v * kf[:, 2:3]) * hmask[:, None]
+        return {"u": uvt[:, 0], "v": uvt[:, 1], "t": uvt[:, 2], "n": n, "x": x, "g_k": g_k, "faces_ind": tri}, hmask

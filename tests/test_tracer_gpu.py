@@ -103,3 +103,24 @@ def test_bvh_builder_refuses_what_the_traversal_cannot_hold():
     hit, _ = bvh.trace(o.to(DEV), d.to(DEV))
     assert hit.sum().item() > 5000
     assert TriangleBVH.overflow_count() == 0
+
+
+def test_dintersect_interpolates_the_vertex_curvature():
+    """Scene.Dintersect (DiffRender.py:539-549): u, v, t, interpolated normal AND the interpolated vertex Gaussian
+    curvature g_k (DiffRender.py:113-116) -- on a sphere of radius r every hit sees 1 / r^2 and the unit normal x / r."""
+    from nu_nerf_b200.tracer import Scene
+    r = 0.6
+    V, Fc = uv_sphere(r, 96, 48)
+    sc = Scene(V, Fc, device=DEV)
+    g = torch.Generator().manual_seed(3)
+    o = 3.0 * torch.nn.functional.normalize(torch.randn(512, 3, generator=g), dim=-1)
+    d = torch.nn.functional.normalize(-o + 0.1 * torch.randn(512, 3, generator=g), dim=-1)
+    o[:, 2] *= 0.3                                               # stay away from the poles of the UV grid
+    d = torch.nn.functional.normalize(-o + 0.05 * torch.randn(512, 3, generator=g), dim=-1)
+    info, hit = sc.Dintersect(o.to(DEV), d.to(DEV))
+    assert hit.float().mean().item() > 0.9
+    gk = info["g_k"][hit].flatten()
+    assert info["g_k"].shape == (512, 1) and (info["g_k"][~hit] == 0).all()
+    assert (gk * r * r - 1.0).abs().max().item() < 0.03
+    x, n = info["x"][hit], torch.nn.functional.normalize(info["n"][hit], dim=-1)
+    assert (x.norm(dim=-1) - r).abs().max().item() < 2e-3 and (n - x / r).abs().max().item() < 5e-3
