@@ -271,7 +271,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
 #if NUNERF_CHAIN_TIMELINE_DETAIL
           if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[450 + t] = clock64();
 #endif
-          if (g > 0) ptx::mbar_wait(&x_done[t], (uint32_t)((g - 1) & 1));
+          if (g > 0) {
+            if (p.epi_wait & 2) ptx::mbar_wait_parked(&x_done[t], (uint32_t)((g - 1) & 1));
+            else ptx::mbar_wait(&x_done[t], (uint32_t)((g - 1) & 1));
+          }
           if (l == 0) ptx::mbar_wait(&in_full[t], (uint32_t)(it & 1));
           ptx::tc_fence_after();
 #if NUNERF_CHAIN_TIMELINE_DETAIL
@@ -430,9 +433,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               aux_b[0] = __ldg(pb); aux_b[1] = __ldg(pb + 1);
             }
           }
-          // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier
-          if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[t], (uint32_t)(g & 1));
-          asm volatile("bar.sync 1, 512;" ::: "memory");
+          if ((p.epi_wait & 1) == 0) {
+            // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier (all 16 warps start a
+            // tile's epilogue together)
+            if (ew == 0 && lane == 0) ptx::mbar_wait(&t_full[t], (uint32_t)(g & 1));
+            asm volatile("bar.sync 1, 512;" ::: "memory");
+          } else {
+            // every warp waits for the accumulator on its own (parked try_wait): no rendezvous between the warps, so a
+            // warp that is done with one tile moves on to the other while its neighbours still work
+            if (lane == 0) ptx::mbar_wait_parked(&t_full[t], (uint32_t)(g & 1));
+            __syncwarp();
+          }
           ptx::tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2] = clock64();
           uint8_t* xt = sX + (size_t)(t * 4) * CH_BLOCK_BYTES;
@@ -661,6 +672,7 @@ static bool chain_use_ts() {
 static int chain_launch(ChainParams& P, cudaStream_t stream) {
   if (chain_use_ts()) return chain_ts_launch(P, stream);
   P.role_hi = env_int("NUNERF_CHAIN_HIPRIO", 1);
+  P.epi_wait = env_int("NUNERF_CHAIN_EPIWAIT", 1);
   return chain_pair() == 2 ? chain_launch_t<2>(P, stream) : chain_launch_t<1>(P, stream);
 }
 
