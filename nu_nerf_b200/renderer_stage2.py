@@ -47,6 +47,19 @@ def linear_to_srgb(x):
     return torch.where(x <= 0.0031308, 323.0 / 25.0 * x, (211.0 * torch.clamp(x, min=eps) ** (5.0 / 12.0) - 11.0) / 200.0)
 
 
+class _StraightThrough(torch.autograd.Function):
+    """value of `traced` (the no-grad kernel trace), gradient to `replayed` (the same quantity as a differentiable
+    expression): no arithmetic in the forward, the incoming gradient is handed through in the backward."""
+
+    @staticmethod
+    def forward(ctx, traced, replayed):
+        return traced.view_as(traced)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, g
+
+
 def starts_k(rec, k, what):
     """start / direction of segment k as the (no-grad) trace produced them."""
     return rec["segments"][k][what]
@@ -386,7 +399,7 @@ class Stage2Renderer(nn.Module):
         forward outputs do not change; only the graph is added.  Returns (pathes, directions, gradient_mesh).
         straight_through=False returns the replayed values themselves (tests: they must reproduce the trace)."""
         if straight_through:
-            st = lambda kernel, replay: replay if kernel is None else kernel + (replay - replay.detach())
+            st = lambda kernel, replay: replay if kernel is None else _StraightThrough.apply(kernel.detach(), replay)
         else:
             st = lambda kernel, replay: replay
         sc = self.scene
@@ -504,16 +517,17 @@ class Stage2Renderer(nn.Module):
             color = torch.zeros(N * S, 3, device=dev)
             if outer_idx.numel() > 0:
                 # NeRF++ of the STAGE-1 network on the samples outside the unit sphere (ZT:1876-1880)
-                a_o, c_o = _NerfFn.apply(w1, pts_f[outer_idx].contiguous(), dirs_i[ray_of(outer_idx)].contiguous(),
-                                         dists_f[outer_idx].contiguous(), *p1)
+                # (index_select: its backward is an atomic index_add, not the sort-based scatter of tensor[idx])
+                a_o, c_o = _NerfFn.apply(w1, pts_f.index_select(0, outer_idx), dirs_i.index_select(0, ray_of(outer_idx)),
+                                         dists_f.index_select(0, outer_idx), *p1)
                 alpha = alpha.index_put((outer_idx,), a_o)
                 color = color.index_put((outer_idx,), c_o)
             if i == 1 and inner_idx.numel() > 0:
                 # inner SDF field + inner shading on segment 1 (ZT:1883-1906)
                 inv_s = torch.exp(self.deviation_network_inner.variance * 10.0)
                 a_i, c_i, gerr = _InnerFn.apply((wi, float(cos_anneal_ratio), exp_maxi, not frozen), inv_s,
-                                                pts_f[inner_idx].contiguous(), dirs_i[ray_of(inner_idx)].contiguous(),
-                                                dists_f[inner_idx].contiguous(), *p_in)
+                                                pts_f.index_select(0, inner_idx), dirs_i.index_select(0, ray_of(inner_idx)),
+                                                dists_f.index_select(0, inner_idx), *p_in)
                 alpha = alpha.index_put((inner_idx,), a_i)
                 color = color.index_put((inner_idx,), c_i)
                 inv_s_c = inv_s.clip(1e-6, 1e6)
@@ -526,22 +540,22 @@ class Stage2Renderer(nn.Module):
             T = T * t_end[:, None]
             n_hit = conv_idx.numel()
             if n_hit > 0:
-                p_hit = cand[conv_idx, -1, :].contiguous()
+                p_hit = cand[:, -1, :].index_select(0, conv_idx)
                 holder = {}
                 c_s, trans, nov = _SurfaceFn.apply((w1, exp_max1, holder), p_hit, keep(gradient_mesh[i]).contiguous(),
-                                                   dirs_i[conv_idx].contiguous(), *p1)
+                                                   dirs_i.index_select(0, conv_idx), *p1)
                 if i % 2 != 0:
                     c_s = torch.zeros_like(c_s)                    # inside the object: field.py:969
                 tn = torch.clamp(1.0 - nov[:, None], 0.0, 1.0)
                 rw = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)
-                color_now = color_now.index_add(0, conv_idx, srgb_to_linear(c_s) * T[conv_idx])
+                color_now = color_now.index_add(0, conv_idx, srgb_to_linear(c_s) * T.index_select(0, conv_idx))
                 if i == 0 and not is_train:
                     with torch.no_grad():
                         ex = eng.surface_extras(w1, holder["tape"], exp_max1)
                         normals_out[conv_idx] = (F.normalize(gradient_mesh[i].reshape(-1, 3), dim=-1) + 1.0) * 0.5
                         spec_color_out[conv_idx], spec_light_out[conv_idx], spec_ref_out[conv_idx] = \
                             ex["specular_color"], ex["specular_light"], ex["specular_ref"]
-                T = T[conv_idx] * ((1.0 - rw) * trans[:, None])        # refraction_coefficient, ZT:1966
+                T = T.index_select(0, conv_idx) * ((1.0 - rw) * trans[:, None])        # refraction_coefficient, ZT:1966
                 colors.append(color_now)
             else:
                 colors.append(color_now)
