@@ -141,6 +141,9 @@ int nunerf_f32_to_planes(const float* a, int lda, const float* b, int ldb, int M
 int nunerf_ray_setup(const float* o, const float* d, float* near, float* far, const float* U0, const float* U1,
                      const float* tables, int R, int sphere, int perturb, float* z, float* z_bg, void* stream);
 int nunerf_points(const float* o, const float* d, const float* z, int R, int n, float* pts, void* stream);
+/* reverse of nunerf_points (stage-2 path points as a function of the refracted segment start / direction):
+ * g_o[R,3] = sum_j g_pts[r,j], g_d[R,3] = sum_j z[r,j] g_pts[r,j] */
+int nunerf_points_bwd(const float* g_pts, const float* z, int R, int n, float* g_o, float* g_d, void* stream);
 int nunerf_upsample(const float* o, const float* d, const float* z, const float* sdf, int R, int n, int n_new,
                     const float* inv_s_dev, float inv_s_cap, const float* u_tab, float* z_new, int32_t* inds,
                     float* z_merged, int32_t* perm, void* stream);
@@ -347,6 +350,12 @@ int nunerf_bvh_overflow_count(unsigned int* out);
  *   unit vertex normal (tri_normals [F,9] = per-corner angle-weighted vertex normals, DiffRender.py:342-359).
  * nunerf_refract_bounce: zero-thickness bounce ZT:1633-1684: eta = 1/(IoR(x)+1) (inverted when inside), TIR test
  *   eta^2 sin^2 > 0.999, Snell direction, next origin x + 1e-5 d', d' / (|d'| + 1e-4).
+ * nunerf_hit_interp_bwd / nunerf_refract_bounce_bwd: the reverse of those two steps (the reference keeps them inside
+ *   autograd, DiffRender.py:61-124 / ZT:1633-1684, so that IORs_pred is trained through the path geometry).
+ *   hit_interp_bwd: rows with a valid `tri`; g_x = d loss / d (o + t d), g_n = d loss / d (signed unit normal, negated
+ *   when `inside`) -> g_o, g_d.  refract_bounce_bwd: rows that PASSED the TIR test, compact; n_signed = the signed unit
+ *   normal, eta_eff = the effective ratio (inverted when inside); g_onext / g_dnext = d loss / d (next origin,
+ *   next direction) -> g_x, g_n, g_d [N,3] and g_eta [N].
  */
 typedef struct { float lo[4][3]; float hi[4][3]; int32_t child[4]; int32_t count[4]; } nunerf_bvh_node_t;
 int nunerf_bvh_build_host(const float* verts_host, int V, const int32_t* faces_host, int F,
@@ -358,6 +367,11 @@ int nunerf_trace_brute(const float* tri_verts, int F, const float* rays_o, const
                        float* hit, int32_t* tri, float* t, void* stream);
 int nunerf_hit_interp(const float* tri_verts, const float* tri_normals, const int32_t* tri, const float* rays_o,
                       const float* rays_d, int N, float* uvt, float* x_hit, float* n_hit, void* stream);
+int nunerf_hit_interp_bwd(const float* tri_verts, const float* tri_normals, const int32_t* tri, const float* rays_o,
+                          const float* rays_d, int N, int inside, const float* g_x, const float* g_n, float* g_o, float* g_d,
+                          void* stream);
+int nunerf_refract_bounce_bwd(const float* n_signed, const float* rays_d, const float* eta_eff, int N, const float* g_onext,
+                              const float* g_dnext, float* g_x, float* g_n, float* g_d, float* g_eta, void* stream);
 int nunerf_refract_bounce(const float* x_hit, const float* n_hit, const float* rays_d, const float* eta,
                           const int32_t* tri, int N, int inside, float* d_out, float* o_out, uint8_t* pass,
                           void* stream);

@@ -103,6 +103,7 @@ _SIGS = {
     "nunerf_f32_to_planes": [vp, ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp],
     "nunerf_ray_setup": [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, vp, vp, vp],
     "nunerf_points": [vp, vp, vp, ci, ci, vp, vp],
+    "nunerf_points_bwd": [vp, vp, ci, ci, vp, vp, vp],
     "nunerf_upsample": [vp, vp, vp, vp, ci, ci, ci, vp, cf, vp, vp, vp, vp, vp, vp],
     "nunerf_merge_sdf": [vp, vp, vp, ci, ci, ci, vp, vp],
     "nunerf_probe_weights": [vp, vp, ci, ci, vp, ci, vp, vp, vp, vp],
@@ -142,6 +143,8 @@ _SIGS = {
     "nunerf_trace_brute": [vp, ci, vp, vp, ci, cf, vp, vp, vp, vp],
     "nunerf_hit_interp": [vp, vp, vp, vp, vp, ci, vp, vp, vp, vp],
     "nunerf_refract_bounce": [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp],
+    "nunerf_hit_interp_bwd": [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp],
+    "nunerf_refract_bounce_bwd": [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp],
     "nunerf_grid_points": [ci, cll, ci, vp, vp, vp],
     "nunerf_grid_mask": [vp, vp, ci, ci, cf, vp, vp],
     "nunerf_mc_count": [vp, ci, cf, vp, vp, vp],

@@ -190,6 +190,98 @@ __global__ void refract_bounce_kernel(const float* __restrict__ x_hit, const flo
   }
 }
 
+// ---- reverse of hit_interp_kernel (the differentiable ray-triangle intersection of DiffRender.py:61-124, which the
+// reference keeps inside autograd so that the IoR network is trained through the refracted path geometry).
+// Inputs: gradient arriving at x = o + t d and at the signed unit normal sign * normalize(interp(u, v)); outputs:
+// gradient with respect to the ray origin and direction (the triangle is a constant).
+__global__ void hit_interp_bwd_kernel(const float* __restrict__ tri_verts, const float* __restrict__ tri_normals,
+                                      const int32_t* __restrict__ tri, const float* __restrict__ rays_o,
+                                      const float* __restrict__ rays_d, int N, float sign, const float* __restrict__ g_x,
+                                      const float* __restrict__ g_n, float* g_o, float* g_d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int f = tri[i];
+  if (f < 0 || f >= MISS_ID) {
+    for (int c = 0; c < 3; ++c) { g_o[3 * i + c] = 0.f; g_d[3 * i + c] = 0.f; }
+    return;
+  }
+  const float* tv = tri_verts + 9 * (long long)f;
+  const float* nn = tri_normals + 9 * (long long)f;
+  const float o[3] = {rays_o[3 * i], rays_o[3 * i + 1], rays_o[3 * i + 2]};
+  const float d[3] = {rays_d[3 * i], rays_d[3 * i + 1], rays_d[3 * i + 2]};
+  float e1[3], e2[3], p[3], q[3], s[3];
+  for (int c = 0; c < 3; ++c) { e1[c] = tv[3 + c] - tv[c]; e2[c] = tv[6 + c] - tv[c]; s[c] = o[c] - tv[c]; }
+  cross3(d, e2, p);
+  const float inv = 1.0f / dot3(e1, p);
+  cross3(s, e1, q);
+  const float sp = dot3(s, p), dq = dot3(d, q), eq = dot3(e2, q);
+  const float u = sp * inv, v = dq * inv, t = eq * inv;
+  // ---- interpolated normal n = ni / |ni| (the second F.normalize of the reference is the identity)
+  float ni[3], n[3];
+  for (int c = 0; c < 3; ++c) ni[c] = (1.0f - u - v) * nn[c] + u * nn[3 + c] + v * nn[6 + c];
+  const float len = sqrtf(dot3(ni, ni));
+  for (int c = 0; c < 3; ++c) n[c] = ni[c] / len;
+  const float gx[3] = {g_x[3 * i], g_x[3 * i + 1], g_x[3 * i + 2]};
+  const float gn[3] = {sign * g_n[3 * i], sign * g_n[3 * i + 1], sign * g_n[3 * i + 2]};
+  const float ngn = dot3(n, gn);
+  float gni[3];
+  for (int c = 0; c < 3; ++c) gni[c] = (gn[c] - n[c] * ngn) / len;
+  float gu = 0.f, gv = 0.f;
+  for (int c = 0; c < 3; ++c) { gu += gni[c] * (nn[3 + c] - nn[c]); gv += gni[c] * (nn[6 + c] - nn[c]); }
+  // ---- x = o + t d
+  const float gt = dot3(gx, d);
+  float go[3] = {gx[0], gx[1], gx[2]}, gd[3] = {t * gx[0], t * gx[1], t * gx[2]};
+  // ---- Moeller-Trumbore: u = (s . p) inv, v = (d . q) inv, t = (e2 . q) inv, p = d x e2, q = s x e1, inv = 1 / (e1 . p)
+  const float g_inv = gu * sp + gv * dq + gt * eq;
+  const float g_det = -g_inv * inv * inv;
+  float gp[3], gq[3], tmp[3];
+  for (int c = 0; c < 3; ++c) {
+    gp[c] = gu * inv * s[c] + g_det * e1[c];
+    gq[c] = gv * inv * d[c] + gt * inv * e2[c];
+  }
+  cross3(e1, gq, tmp);                       // q = s x e1  ->  g_s += e1 x g_q
+  for (int c = 0; c < 3; ++c) go[c] += gu * inv * p[c] + tmp[c];
+  cross3(e2, gp, tmp);                       // p = d x e2  ->  g_d += e2 x g_p
+  for (int c = 0; c < 3; ++c) gd[c] += gv * inv * q[c] + tmp[c];
+  for (int c = 0; c < 3; ++c) { g_o[3 * i + c] = go[c]; g_d[3 * i + c] = gd[c]; }
+}
+
+// ---- reverse of the Snell step of refract_bounce_kernel (ZT:1633-1684) for rays that pass the TIR test:
+//   d' = eta d + (eta cos_i - sqrt(1 - (1 - cos_i^2) eta^2)) n,  o_next = x + 1e-5 d',  d_next = d' / (|d'| + 1e-4)
+// with n the signed unit normal, cos_i = -n . d and eta the effective ratio (already inverted when inside).
+// Outputs: gradient with respect to x, n, d and eta.
+__global__ void refract_bounce_bwd_kernel(const float* __restrict__ n_in, const float* __restrict__ rays_d,
+                                          const float* __restrict__ eta_in, int N, const float* __restrict__ g_onext,
+                                          const float* __restrict__ g_dnext, float* g_x, float* g_n, float* g_d,
+                                          float* g_eta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float n[3] = {n_in[3 * i], n_in[3 * i + 1], n_in[3 * i + 2]};
+  const float d[3] = {rays_d[3 * i], rays_d[3 * i + 1], rays_d[3 * i + 2]};
+  const float eta = eta_in[i];
+  const float cosi = -dot3(n, d);
+  const float sin2 = 1.0f - cosi * cosi;
+  const float r = sqrtf(1.0f - sin2 * eta * eta);
+  const float k = eta * cosi - r;
+  float nd[3];
+  for (int c = 0; c < 3; ++c) nd[c] = eta * d[c] + k * n[c];
+  const float L = sqrtf(dot3(nd, nd)), Le = L + 0.0001f;
+  const float gs[3] = {g_onext[3 * i], g_onext[3 * i + 1], g_onext[3 * i + 2]};
+  const float gdn[3] = {g_dnext[3 * i], g_dnext[3 * i + 1], g_dnext[3 * i + 2]};
+  const float proj = dot3(gdn, nd) / (Le * Le * L);
+  float gnd[3];
+  for (int c = 0; c < 3; ++c) gnd[c] = gdn[c] / Le - nd[c] * proj + 1e-5f * gs[c];
+  const float gk = dot3(gnd, n);
+  const float ge = dot3(gnd, d) + gk * (cosi + sin2 * eta / r);
+  const float gcos = gk * (eta - cosi * eta * eta / r);
+  for (int c = 0; c < 3; ++c) {
+    g_x[3 * i + c] = gs[c];
+    g_n[3 * i + c] = k * gnd[c] - gcos * d[c];
+    g_d[3 * i + c] = eta * gnd[c] - gcos * n[c];
+  }
+  g_eta[i] = ge;
+}
+
 // ------------------------------------------------------------------------------------------- host build
 struct BuildCtx {
   const float* verts; const int32_t* faces;
@@ -318,6 +410,28 @@ extern "C" int nunerf_hit_interp(const float* tri_verts, const float* tri_normal
   hit_interp_kernel<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(tri_verts, tri_normals, tri, rays_o, rays_d, N, uvt,
                                                                    x_hit, n_hit);
   NUNERF_CHECK_LAUNCH("hit_interp_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_hit_interp_bwd(const float* tri_verts, const float* tri_normals, const int32_t* tri, const float* rays_o,
+                                     const float* rays_d, int N, int inside, const float* g_x, const float* g_n, float* g_o,
+                                     float* g_d, void* stream) {
+  NUNERF_REQUIRE(tri_verts && tri_normals && tri && rays_o && rays_d && g_x && g_n && g_o && g_d && N > 0,
+                 "hit_interp_bwd: bad arguments");
+  hit_interp_bwd_kernel<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(tri_verts, tri_normals, tri, rays_o, rays_d, N,
+                                                                       inside ? -1.0f : 1.0f, g_x, g_n, g_o, g_d);
+  NUNERF_CHECK_LAUNCH("hit_interp_bwd_kernel");
+  return 0;
+}
+
+extern "C" int nunerf_refract_bounce_bwd(const float* n_signed, const float* rays_d, const float* eta_eff, int N,
+                                         const float* g_onext, const float* g_dnext, float* g_x, float* g_n, float* g_d,
+                                         float* g_eta, void* stream) {
+  NUNERF_REQUIRE(n_signed && rays_d && eta_eff && g_onext && g_dnext && g_x && g_n && g_d && g_eta && N > 0,
+                 "refract_bounce_bwd: bad arguments");
+  refract_bounce_bwd_kernel<<<cdiv(N, 128), 128, 0, (cudaStream_t)stream>>>(n_signed, rays_d, eta_eff, N, g_onext, g_dnext,
+                                                                           g_x, g_n, g_d, g_eta);
+  NUNERF_CHECK_LAUNCH("refract_bounce_bwd_kernel");
   return 0;
 }
 

@@ -418,6 +418,38 @@ extern "C" int nunerf_ray_setup(const float* o, const float* d, float* near, flo
   return 0;
 }
 
+// reverse of points_kernel: pts[r, j] = o[r] + d[r] z[r, j]  ->  g_o[r] = sum_j g[r, j],  g_d[r] = sum_j z[r, j] g[r, j]
+// (one warp per ray, lanes stride over the samples, shuffle reduction)
+__global__ void points_bwd_kernel(const float* __restrict__ g_pts, const float* __restrict__ z, int R, int n, float* g_o,
+                                  float* g_d) {
+  const int ray = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ray >= R) return;
+  float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
+  for (int j = lane; j < n; j += 32) {
+    const float zz = z[(long long)ray * n + j];
+    const float* g = g_pts + ((long long)ray * n + j) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { a[c] += g[c]; b[c] += zz * g[c]; }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a[c] += __shfl_xor_sync(0xffffffffu, a[c], off);
+      b[c] += __shfl_xor_sync(0xffffffffu, b[c], off);
+    }
+  if (lane == 0)
+    for (int c = 0; c < 3; ++c) { g_o[3 * ray + c] = a[c]; g_d[3 * ray + c] = b[c]; }
+}
+
+extern "C" int nunerf_points_bwd(const float* g_pts, const float* z, int R, int n, float* g_o, float* g_d, void* stream) {
+  NUNERF_REQUIRE(g_pts && z && g_o && g_d && R > 0 && n > 0, "points_bwd: bad arguments");
+  points_bwd_kernel<<<cdiv((long long)R * 32, 256), 256, 0, (cudaStream_t)stream>>>(g_pts, z, R, n, g_o, g_d);
+  NUNERF_CHECK_LAUNCH("points_bwd_kernel");
+  return 0;
+}
+
 extern "C" int nunerf_points(const float* o, const float* d, const float* z, int R, int n, float* pts, void* stream) {
   NUNERF_REQUIRE(o && d && z && pts && R > 0 && n > 0, "points: bad arguments");
   long long total = (long long)R * n;

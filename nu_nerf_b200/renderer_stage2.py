@@ -10,8 +10,9 @@ positions into every field's input.
   render_core ZT:1835-2011   per segment: NeRF++ on the outer samples, inner SDF + shading on segment 1, surface
                              shading at the hit with the mesh normal and the stage-1 predictors, linear-space
                              compositing with the throughput chain T *= T_end (1 - schlick) transmission
-  _replay_geometry           the trace again as a differentiable function of IORs_pred (per-ray work on <= R rows per
-                             bounce: Moeller-Trumbore on the recorded triangle, IoR MLP, Snell), values straight-through
+  _replay_geometry           the trace again as a differentiable function of IORs_pred: nodes with the trace's own
+                             values in the forward and reverse kernels in the backward (hit_interp_bwd, refract_bounce_bwd,
+                             points_bwd); the IoR MLP (<= R rows per bounce) is the only torch-autograd part
 
 Each field evaluation is one autograd node (forward = explicit launch sequence, backward = hand-derived reverse sequence
 of engine.py, gradients added in place to .grad by the WeightBank).  When the geometry carries a graph the same nodes
@@ -58,6 +59,94 @@ class _StraightThrough(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return None, g
+
+
+class _HitFn(torch.autograd.Function):
+    """Scene.Dintersect on the recorded triangles as a differentiable node (DiffRender.py:61-124): (o, d) of the rays
+    that hit -> hit point x = o + t d and the signed, interpolated unit normal.  Forward values are the trace's own when
+    given (else `nunerf_hit_interp` is run again); backward = `hit_interp_bwd_kernel`."""
+
+    @staticmethod
+    def forward(ctx, o_c, d_c, pack):
+        eng = _engine()
+        scene, tri, inside, x, n = pack
+        o_c, d_c = o_c.contiguous(), d_c.contiguous()
+        N = o_c.shape[0]
+        if x is None or n is None:
+            uvt, x, n = (torch.empty(N, 3, device=o_c.device) for _ in range(3))
+            if N > 0:
+                eng.call("nunerf_hit_interp", scene.optix_mesh.bvh.tri_verts.data_ptr(), scene.tri_normals.data_ptr(),
+                         tri.data_ptr(), o_c.data_ptr(), d_c.data_ptr(), N, uvt.data_ptr(), x.data_ptr(), n.data_ptr())
+            n = -n if inside else n
+        ctx.save_for_backward(o_c, d_c)
+        ctx.pack = (scene, tri, inside)
+        return x.view_as(x), n.view_as(n)
+
+    @staticmethod
+    def backward(ctx, g_x, g_n):
+        eng = _engine()
+        o_c, d_c = ctx.saved_tensors
+        scene, tri, inside = ctx.pack
+        N = o_c.shape[0]
+        g_o, g_d = torch.empty_like(o_c), torch.empty_like(d_c)
+        zero = lambda g: torch.zeros(N, 3, device=o_c.device) if g is None else g.contiguous().float()
+        if N > 0:
+            eng.call("nunerf_hit_interp_bwd", scene.optix_mesh.bvh.tri_verts.data_ptr(), scene.tri_normals.data_ptr(),
+                     tri.data_ptr(), o_c.data_ptr(), d_c.data_ptr(), N, int(inside), zero(g_x).data_ptr(),
+                     zero(g_n).data_ptr(), g_o.data_ptr(), g_d.data_ptr())
+        return g_o, g_d, None
+
+
+class _RefractFn(torch.autograd.Function):
+    """Snell step of the zero-thickness bounce (ZT:1655-1684) on the rays that passed the TIR test: (x, signed normal,
+    incoming direction, effective ratio) -> (next origin, next direction).  Forward values are the trace's own when
+    given; backward = `refract_bounce_bwd_kernel`."""
+
+    @staticmethod
+    def forward(ctx, x, n, d, eta, pack):
+        o_next, d_next = pack
+        n, d, eta = n.contiguous(), d.contiguous(), eta.contiguous()
+        if o_next is None or d_next is None:
+            cos_i = -(n * d).sum(-1, keepdim=True)
+            e = eta.reshape(-1, 1)
+            d_tmp = e * d + (e * cos_i - torch.sqrt(1.0 - (1.0 - cos_i * cos_i) * e * e)) * n
+            o_next = x + d_tmp * 1e-5
+            d_next = d_tmp / (torch.linalg.norm(d_tmp, dim=-1, keepdim=True) + 0.0001)
+        ctx.save_for_backward(n, d, eta)
+        return o_next.view_as(o_next), d_next.view_as(d_next)
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        eng = _engine()
+        n, d, eta = ctx.saved_tensors
+        N = n.shape[0]
+        zero = lambda g: torch.zeros(N, 3, device=n.device) if g is None else g.contiguous().float()
+        g_x, g_n, g_dd, g_eta = torch.empty_like(n), torch.empty_like(n), torch.empty_like(n), torch.empty(N, device=n.device)
+        if N > 0:
+            eng.call("nunerf_refract_bounce_bwd", n.data_ptr(), d.data_ptr(), eta.data_ptr(), N, zero(g_o).data_ptr(),
+                     zero(g_d).data_ptr(), g_x.data_ptr(), g_n.data_ptr(), g_dd.data_ptr(), g_eta.data_ptr())
+        return g_x, g_n, g_dd, g_eta.view_as(eta), None
+
+
+class _SegPointsFn(torch.autograd.Function):
+    """Path points start + delta * z of one segment (ZT:1727-1731, :1760, :1799) with the values of the trace and the
+    reverse reduction over the samples as a kernel (`points_bwd_kernel`)."""
+
+    @staticmethod
+    def forward(ctx, start, delta, z, traced):
+        ctx.save_for_backward(z)
+        return traced.view_as(traced)
+
+    @staticmethod
+    def backward(ctx, g):
+        eng = _engine()
+        (z,) = ctx.saved_tensors
+        R, n = z.shape
+        g_s, g_d = torch.empty(R, 3, device=z.device), torch.empty(R, 3, device=z.device)
+        if R > 0:
+            eng.call("nunerf_points_bwd", g.contiguous().float().data_ptr(), z.contiguous().data_ptr(), R, n,
+                     g_s.data_ptr(), g_d.data_ptr())
+        return g_s, g_d, None, None
 
 
 def starts_k(rec, k, what):
@@ -403,44 +492,57 @@ class Stage2Renderer(nn.Module):
         else:
             st = lambda kernel, replay: replay
         sc = self.scene
+        # kernels: the two reverse kernels of csrc/bvh.cu + the path-point reduction; torch: the same chain as plain
+        # differentiable torch expressions (CPU tests, cfg['replay_impl'] = 'torch' -- the two are tested against each other)
+        kernels = straight_through and rays_o.is_cuda and self.cfg.get("replay_impl", "kernels") == "kernels"
         verts, faces, vnorm = sc.vertices.float(), sc.faces, sc.normals.float()
         start_r, dir_r = rays_o.float(), rays_d.float()
         starts, dirs, xs, gm = [start_r], [dir_r], [], []
         for i, b in enumerate(rec["bounces"]):
             hit_idx, ok_idx = b["hit_idx"], b["ok_idx"]
-            o_c, d_c = start_r[hit_idx], dir_r[hit_idx]
-            f = faces[b["tri"]]
-            tv, tn = verts[f], vnorm[f]
-            v0, e1, e2 = tv[:, 0], tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0]
-            pvec = torch.cross(d_c, e2, dim=-1)
-            inv_det = 1.0 / (e1 * pvec).sum(-1)
-            tvec = o_c - v0
-            u = (tvec * pvec).sum(-1) * inv_det
-            qvec = torch.cross(tvec, e1, dim=-1)
-            v = (d_c * qvec).sum(-1) * inv_det
-            t = (e2 * qvec).sum(-1) * inv_det
-            x = st(b.get("x"), o_c + t[:, None] * d_c)
-            n = (1 - u - v)[:, None] * tn[:, 0] + u[:, None] * tn[:, 1] + v[:, None] * tn[:, 2]
-            n = F.normalize(n / n.norm(dim=1, keepdim=True), dim=-1)
-            normal = st(b.get("n"), -n if b["inside"] else n)
+            o_c, d_c = start_r.index_select(0, hit_idx), dir_r.index_select(0, hit_idx)
+            if kernels:
+                x, normal = _HitFn.apply(o_c, d_c, (sc, b["tri"].to(torch.int32).contiguous(), b["inside"], b.get("x"),
+                                                    b.get("n")))
+            else:
+                f = faces[b["tri"]]
+                tv, tn = verts[f], vnorm[f]
+                v0, e1, e2 = tv[:, 0], tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0]
+                pvec = torch.cross(d_c, e2, dim=-1)
+                inv_det = 1.0 / (e1 * pvec).sum(-1)
+                tvec = o_c - v0
+                u = (tvec * pvec).sum(-1) * inv_det
+                qvec = torch.cross(tvec, e1, dim=-1)
+                v = (d_c * qvec).sum(-1) * inv_det
+                t = (e2 * qvec).sum(-1) * inv_det
+                x = st(b.get("x"), o_c + t[:, None] * d_c)
+                n = (1 - u - v)[:, None] * tn[:, 0] + u[:, None] * tn[:, 1] + v[:, None] * tn[:, 2]
+                n = F.normalize(n / n.norm(dim=1, keepdim=True), dim=-1)
+                normal = st(b.get("n"), -n if b["inside"] else n)
             xs.append(x)
             if ok_idx.numel() == 0:
                 break
-            gm.append(normal[ok_idx])
+            gm.append(normal.index_select(0, ok_idx))
             if i + 1 >= len(rec["segments"]):
                 break                                   # the ray leaving the third hit is not rendered
-            cos_i = (normal * -d_c).sum(-1, keepdim=True)
-            sin2 = 1.0 - cos_i * cos_i
             eta = 1.0 / (self._ior_torch(x).reshape(-1, 1) * 1.0 + 1.0)
             eta = st(b["eta"].reshape(-1, 1) if b.get("eta") is not None else None, eta)
             if b["inside"]:
                 eta = 1.0 / eta
-            eta, cos_k, n_k = eta[ok_idx], cos_i[ok_idx], normal[ok_idx]
-            sin_t2 = sin2[ok_idx] * eta * eta
-            d_tmp = eta * d_c[ok_idx] + (eta * cos_k - torch.sqrt(1.0 - sin_t2)) * n_k
-            s_next = x[ok_idx] + d_tmp * 1e-5
-            d_next = d_tmp / (torch.linalg.norm(d_tmp, dim=-1, keepdim=True) + 0.0001)
-            start_r, dir_r = st(starts_k(rec, i + 1, "start"), s_next), st(starts_k(rec, i + 1, "dir"), d_next)
+            if kernels:
+                s_next, d_next = _RefractFn.apply(x.index_select(0, ok_idx), normal.index_select(0, ok_idx),
+                                                  d_c.index_select(0, ok_idx), eta.index_select(0, ok_idx).reshape(-1),
+                                                  (starts_k(rec, i + 1, "start"), starts_k(rec, i + 1, "dir")))
+                start_r, dir_r = s_next, d_next
+            else:
+                cos_i = (normal * -d_c).sum(-1, keepdim=True)
+                sin2 = 1.0 - cos_i * cos_i
+                eta, cos_k, n_k = eta[ok_idx], cos_i[ok_idx], normal[ok_idx]
+                sin_t2 = sin2[ok_idx] * eta * eta
+                d_tmp = eta * d_c[ok_idx] + (eta * cos_k - torch.sqrt(1.0 - sin_t2)) * n_k
+                s_next = x[ok_idx] + d_tmp * 1e-5
+                d_next = d_tmp / (torch.linalg.norm(d_tmp, dim=-1, keepdim=True) + 0.0001)
+                start_r, dir_r = st(starts_k(rec, i + 1, "start"), s_next), st(starts_k(rec, i + 1, "dir"), d_next)
             starts.append(start_r)
             dirs.append(dir_r)
         new_pathes = []
@@ -454,9 +556,12 @@ class Stage2Renderer(nn.Module):
                 end = end.index_put((sg["h_idx"],), xs[k])
             delta = end - s_k
             if sg["m_idx"] is not None:
-                delta = delta.index_put((sg["m_idx"],), d_k[sg["m_idx"]])
-            pts = s_k[:, None, :] + delta[:, None, :] * sg["Z"][:, :, None]
-            new_pathes.append(st(pathes[k], pts))
+                delta = delta.index_put((sg["m_idx"],), d_k.index_select(0, sg["m_idx"]))
+            if kernels:
+                new_pathes.append(_SegPointsFn.apply(s_k, delta, sg["Z"], pathes[k]))
+            else:
+                pts = s_k[:, None, :] + delta[:, None, :] * sg["Z"][:, :, None]
+                new_pathes.append(st(pathes[k], pts))
         if not straight_through:
             new_pathes = [p_ if p_.requires_grad else None for p_ in new_pathes]
         new_dirs = [dirs[k] if k < len(dirs) else directions[k] for k in range(len(directions))]

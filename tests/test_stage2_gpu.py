@@ -266,6 +266,32 @@ def test_ior_network_gradient_through_the_path_geometry(golden, precision, tol_g
         assert rel < tol_par and nrel < tol_par, (name, rel, nrel)
 
 
+def test_replay_kernels_match_the_torch_restatement(golden):
+    """The reverse kernels of the bounce (`hit_interp_bwd_kernel`, `refract_bounce_bwd_kernel`, `points_bwd_kernel`,
+    csrc/bvh.cu / sampling.cu) against the same chain written as differentiable torch expressions
+    (cfg['replay_impl'] = 'torch', itself checked against the reference's autograd above): geometry gradients and the
+    gradient of every IoR-network parameter agree to fp32 rounding."""
+    GG = np.load(os.path.join(GOLDEN, "stage2_grads_R64.npz"))
+    res = {}
+    for impl in ("kernels", "torch"):
+        net_ = make_stage2("split").cuda()
+        net_.cfg["replay_impl"] = impl
+        _, geo = _ior_backward(net_, golden, GG)
+        res[impl] = ({k: [None if t_.grad is None else t_.grad.clone() for t_ in v] for k, v in geo.items()},
+                     {n_: p.grad.clone() for n_, p in net_.IORs_pred.named_parameters()})
+    (gk, pk), (gt_, pt) = res["kernels"], res["torch"]
+    n_cmp = 0
+    for key in gk:
+        for a, b in zip(gk[key], gt_[key]):
+            assert (a is None) == (b is None), key
+            if a is not None and b.abs().max().item() > 0:
+                assert (a - b).abs().max().item() < 2e-4 * b.abs().max().item(), (key, (a - b).abs().max().item())
+                n_cmp += 1
+    assert n_cmp >= 5
+    for n_ in pt:
+        assert (pk[n_] - pt[n_]).abs().max().item() < 2e-4 * pt[n_].abs().max().item(), n_
+
+
 def test_render_trains_the_ior_network_end_to_end(net, golden):
     """Stage2Renderer.render (own ray_trace + replay): IORs_pred receives a finite, non-zero gradient, the forward
     colours are those of the no-grad render, and cfg['frozen_ior'] switches the geometry graph off."""
