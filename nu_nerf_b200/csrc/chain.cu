@@ -32,21 +32,13 @@ namespace nunerf {
 //   KIND 2: bias + ReLU, emits the 16 (x > 0) bits    (predictor / NeRF++ forward)
 //   KIND 3: multiply by the 16 mask bits `mbits`      (ReLU backward: dZ_l = (dZ_{l+1} W_{l+1}) . [z_l > 0])
 template <int KIND>
-__device__ __forceinline__ void ch_hot16(const uint32_t* v, const float* __restrict__ bias, uint8_t* dst, int j, uint32_t sw,
+__device__ __forceinline__ void ch_hot16(const uint32_t* v, const float4* b, uint8_t* dst, int j, uint32_t sw,
                                          uint32_t* obits, uint32_t mbits, int dbg_flags) {
   float x[16];
   if (KIND == 3) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = ((mbits >> i) & 1u) ? __uint_as_float(v[i]) : 0.0f;
   } else {
-    float4 b[4];
-    if (dbg_flags & 64) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(bias) + i);
-    }
 #if NUNERF_PACKED_EPI
     if (KIND == 1) {
       // bias + Softplus two lanes per instruction (FADD2 / FMUL2 / FFMA2): the fma pipe bounds this epilogue
@@ -478,18 +470,28 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             for (int c = 0; c < 4; ++c) {
               const int c0 = c * 64 + j * 16;     // first of this thread's 16 columns
               uint32_t* cur = (c & 1) ? vb : va;
+              // this chunk's 16 biases are requested BEFORE the accumulator wait: their (L1) latency hides behind it
+              // instead of being exposed at the first add (ncu: 7 % of all stall samples sat there)
+              float4 b[4];
+              if (L.hot != 3 && !(p.dbg_flags & 64)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(L.bias + c0) + i);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              }
               ptx::tmem_ld_wait();
               if (c < 3) ptx::tmem_ld16(taddr0 + (uint32_t)((c + 1) * 64), (c & 1) ? va : vb);
               uint32_t ob = 0;
               uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
-              if (L.hot == 1) ch_hot16<1>(cur, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
+              if (L.hot == 1) ch_hot16<1>(cur, b, dst, j, sw, &ob, 0u, p.dbg_flags);
               else if (L.hot == 2) {
-                ch_hot16<2>(cur, L.bias + c0, dst, j, sw, &ob, 0u, p.dbg_flags);
+                ch_hot16<2>(cur, b, dst, j, sw, &ob, 0u, p.dbg_flags);
                 if (L.mask_perm) out_mask |= (unsigned long long)ob << (16 * c);
                 else if (L.mask_out && row_ok)
                   *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
               } else {
-                ch_hot16<3>(cur, nullptr, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu, p.dbg_flags);
+                ch_hot16<3>(cur, b, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu, p.dbg_flags);
               }
             }
           } else
