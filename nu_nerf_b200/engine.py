@@ -341,17 +341,20 @@ def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad, want_d
     DZ[3].t[:, 217:].zero_()                             # lin3 has 217 outputs: the tail columns are read as K padding
     linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=DZ[7])
     ew6 = lambda l: dict(W=w.L[l].WTk, N=256, K=256, aux_mode=6, aux1=A[l - 1], aux2=E[l - 1], store=DZ[l - 1], keep=1)
-    chain(DZ[7], M, 256, [ew6(7), ew6(6), ew6(5)])
+    g_pe0 = g_pe4 = None
+    if want_dx:
+        g_pe0, g_pe4 = _f(M, 64, dev=dev), _f(M, 64, dev=dev)
+    # (want_dx: the PE-input gradients are narrow heads on the resident dZ_4 / dZ_0 of the two chains)
+    chain(DZ[7], M, 256, [ew6(7), ew6(6), ew6(5)] +
+          ([dict(W=w.L[4].WTk, w_row=192, N=64, K=256, out32=g_pe4, n32=64)] if want_dx else []))
     # input of lin4 is [a3 | PE]: only the first 217 columns carry on (PE has no parameters upstream)
     linear(DZ[4], w.L[4].WTk, M, 224, 256, aux=A[3], aux_mode=2, add=E[3], out=DZ[3], n_store=217)
-    chain(DZ[3], M, 256, [ew6(3), ew6(2), ew6(1)])
+    chain(DZ[3], M, 256, [ew6(3), ew6(2), ew6(1)] +
+          ([dict(W=w.L[0].WTk, N=64, K=256, out32=g_pe0, n32=64)] if want_dx else []))
     for l in range(7, 0, -1):
         linear_dw(DZ[l], A[l - 1], M, 217 if l == 3 else 256, 256, dW[l], db=db[l])
     linear_dw(DZ[0], t.x0, M, 256, 64, dW[0], db=db[0])
     if want_dx:
-        g_pe0, g_pe4 = _f(M, 64, dev=dev), _f(M, 64, dev=dev)
-        linear(DZ[4], w.L[4].WTk, M, 64, 256, b_row=192, out_f32=g_pe4)
-        linear(DZ[0], w.L[0].WTk, M, 64, 256, out_f32=g_pe0)
         return _sdf_position_grad(w, t, g_pe0, g_pe4, d_grad)
 
 
@@ -406,6 +409,10 @@ def pred_backward(w: PredW, t: PredTape, dz_head: P, planes, dx_planes: P = None
         if dx_f32 is not None and dx_n % 16 == 0 and dx_n <= 256:
             lays.append(dict(W=w.L[0].WTk, N=dx_n, K=256, out32=dx_f32, n32=dx_n))
             dx_f32 = None
+        if dx_tail is not None:
+            # narrow head on the resident dZ_0 (keep = store = 0 leaves the activation in place)
+            lays.append(dict(W=w.L[0].WTk, w_row=dx_tail[0], N=64, K=256, out32=dx_tail[1], n32=64))
+            dx_tail = None
         chain(dz_head, M, 64, lays)
         linear_dw(dz_head, t.H[2], M, w.n_out, 256, gW[3], db=gb[3])
         linear_dw(d2, t.H[1], M, 256, 256, gW[2], db=gb[2])
@@ -514,14 +521,19 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes, want_geo=Fals
         # dZ_7 by the layer kernel (K = 320 input), then the whole dX chain of the 8 x 256 trunk in one launch
         DZ = [P(M, 256, planes, dev) for _ in range(8)]
         linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=DZ[7])
-        chain(DZ[7], M, 256, [dict(W=w.pts[i].WTk, N=256, K=256, mask_in=t.Mk[i - 1], mask_perm=t.perm[i - 1],
-                                   store=DZ[i - 1], keep=1) for i in range(7, 0, -1)])
+        lays = []
+        for i in range(7, 0, -1):
+            lays.append(dict(W=w.pts[i].WTk, N=256, K=256, mask_in=t.Mk[i - 1], mask_perm=t.perm[i - 1], store=DZ[i - 1],
+                             keep=1))
+            if want_geo and i == 6:
+                # narrow head on the resident dZ_5: the PE rows of the skip layer (its input is stored [h | PE])
+                lays.append(dict(W=w.pts[5].WTk, w_row=256, N=128, K=256, out32=g_pe5, n32=128))
+        if want_geo:
+            lays.append(dict(W=w.pts[0].WTk, N=128, K=256, out32=g_pe0, n32=128))          # ... and on dZ_0
+        chain(DZ[7], M, 256, lays)
         for i in range(7, 0, -1):
             linear_dw(DZ[i], H[i - 1], M, 256, 384 if i == 5 else 256, w.pts[i].dW, db=w.pts[i].db)
         linear_dw(DZ[0], t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
-        if want_geo:
-            linear(DZ[5], w.pts[5].WTk, M, 128, 256, b_row=256, out_f32=g_pe5)   # skip input is stored [h | PE]
-            linear(DZ[0], w.pts[0].WTk, M, 128, 256, out_f32=g_pe0)
     else:
         cur, other = P(M, 256, planes, dev), P(M, 256, planes, dev)
         linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=cur)
