@@ -217,13 +217,17 @@ def tc_work(name, a):
         for l in range(p.n_layers):
             L = p.layer[l]
             fl += 2.0 * p.M * L.N * L.K
+            # stores, masks, fp32 heads and -- SDF reverse-pass layers -- the stored activation / adjoint they read back
+            # (aux1, aux2) and the E term they write: all of it is traffic the algorithm requires of the launch
             by += p.M * ((2.0 * L.N if L.store else 0.0) + (L.N / 8.0 if L.mask_out else 0.0)
-                         + (L.N / 8.0 if L.mask_in else 0.0) + (4.0 * L.n32 if L.out32 else 0.0))
-            desc.append(f"{L.K}>{L.N}")
-        return "mlp_chain_kernel", "chain " + " ".join(desc), fl, by
+                         + (L.N / 8.0 if L.mask_in else 0.0) + (4.0 * L.n32 if L.out32 else 0.0)
+                         + 2.0 * L.N * (int(bool(L.aux1)) + int(bool(L.aux2)) + int(bool(L.e_out))))
+            desc.append(f"{L.K}>{L.N}" + ("" if not L.aux_mode else f"[aux{L.aux_mode}]"))
+        cls = "sdf_reverse_chains" if any(p.layer[l].aux_mode >= 4 for l in range(p.n_layers)) else "plain_chains"
+        return "mlp_chain_kernel", "chain " + " ".join(desc), fl, by, cls
     if name == "nunerf_sdf_infer":
         p = a[0]._obj
-        return "mlp_chain_kernel", "chain sdf_infer (PE + 9 layers)", 2.0 * p.M * M_SDF_HEAD, 16.0 * p.M
+        return "mlp_chain_kernel", "chain sdf_infer (PE + 9 layers)", 2.0 * p.M * M_SDF_HEAD, 16.0 * p.M, "sdf_infer"
     return None
 
 
@@ -476,7 +480,7 @@ def run_ours(args):
         e0.record()
         orig_call(name, *a)
         e1.record()
-        rec.append((w[0], e0, e1, w[2], w[3]))
+        rec.append((w[0], e0, e1, w[2], w[3], w[4] if len(w) > 4 else None))
     ops.call = timed_call
     eng.call = timed_call
     try:
@@ -487,10 +491,14 @@ def run_ours(args):
         eng.call = orig_call
     if args.profile:
         profile_step(train_step, (o_d, d_d, gt_d), ops, torch)
-    fam = {}
-    for k, e0, e1, fl, by in rec:
+    fam, chain_cls = {}, {}
+    for k, e0, e1, fl, by, cls in rec:
+        dt = e0.elapsed_time(e1)
         f = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
-        f["ms"] += e0.elapsed_time(e1); f["flops"] += fl; f["bytes"] += by; f["launches"] += 1
+        f["ms"] += dt; f["flops"] += fl; f["bytes"] += by; f["launches"] += 1
+        if cls is not None:
+            c = chain_cls.setdefault(cls, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            c["ms"] += dt; c["flops"] += fl; c["bytes"] += by; c["launches"] += 1
     top = max(fam, key=lambda k: fam[k]["ms"])
     t_lin, fl_lin, by_lin, n_lin = fam[top]["ms"] * 1e-3, fam[top]["flops"], fam[top]["bytes"], fam[top]["launches"]
     hbm, tf_burst, tf_sus, which = peaks()
@@ -529,6 +537,14 @@ def run_ours(args):
                      "kernels": {k: {"ms_per_step": v["ms"], "launches": v["launches"], "share_of_step": v["ms"] / ms,
                                      "tflops": v["flops"] / v["ms"] / 1e9, "frac_of_tensor_peak": v["flops"] / v["ms"] / 1e9 / tf_sus,
                                      "algorithmic_hbm_gbs": v["bytes"] / v["ms"] / 1e6} for k, v in fam.items()},
+                     # the chain launches by what bounds them: the fused SDF query (no stores: tensor / epilogue), plain
+                     # forward and ReLU-backward chains (one store per layer), the SDF reverse-pass chains (1.5-2 KB per
+                     # row and layer in and out: closer to the HBM roofline than to the tensor one)
+                     "chain_classes": {k: {"ms_per_step": v["ms"], "launches": v["launches"],
+                                           "tflops": v["flops"] / v["ms"] / 1e9,
+                                           "frac_of_tensor_peak": v["flops"] / v["ms"] / 1e9 / tf_sus,
+                                           "algorithmic_hbm_gbs": v["bytes"] / v["ms"] / 1e6,
+                                           "frac_of_hbm_peak": v["bytes"] / v["ms"] / 1e6 / hbm} for k, v in chain_cls.items()},
                      "hbm_achieved_gbs": by_lin / t_lin / 1e9 if t_lin > 0 else None,
                      "hbm_frac": by_lin / t_lin / 1e9 / hbm if t_lin > 0 else None,
                      "step_algorithmic_tflops": flops_step / (ms * 1e-3) / 1e12,
