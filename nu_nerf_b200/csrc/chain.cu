@@ -460,6 +460,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               else if (L.hot == 5) ch_aux16<5>(taddr, a0, a1, b0, b1, dst, j, sw, L.e_out + aux_row * L.ld_e + c0, row_ok);
               else ch_aux16<6>(taddr, a0, a1, b0, b1, dst, j, sw, nullptr, row_ok);
             }
+          } else if (L.hot == 3 && (p.epi_wait & 8)) {
+            // ---- ReLU-backward layers do ~40 instructions per 16-column chunk: too little to hide a TMEM round trip
+            // behind, so all four chunk loads of the row go out together and are awaited once
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + j * 16);
+            uint32_t v0[16], v1[16], v2[16], v3[16];
+            ptx::tmem_ld16(taddr0, v0);
+            ptx::tmem_ld16(taddr0 + 64u, v1);
+            ptx::tmem_ld16(taddr0 + 128u, v2);
+            ptx::tmem_ld16(taddr0 + 192u, v3);
+            ptx::tmem_ld_wait();
+            uint32_t ob = 0;
+            const float4 b[4] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f),
+                                 make_float4(0.f, 0.f, 0.f, 0.f)};
+            ch_hot16<3>(v0, b, xt + row_off, j, sw, &ob, (uint32_t)hot_mask & 0xffffu, p.dbg_flags);
+            ch_hot16<3>(v1, b, xt + (size_t)CH_BLOCK_BYTES + row_off, j, sw, &ob, (uint32_t)(hot_mask >> 16) & 0xffffu, p.dbg_flags);
+            ch_hot16<3>(v2, b, xt + (size_t)2 * CH_BLOCK_BYTES + row_off, j, sw, &ob, (uint32_t)(hot_mask >> 32) & 0xffffu, p.dbg_flags);
+            ch_hot16<3>(v3, b, xt + (size_t)3 * CH_BLOCK_BYTES + row_off, j, sw, &ob, (uint32_t)(hot_mask >> 48) & 0xffffu, p.dbg_flags);
           } else if (L.hot) {
             // ---- plain 256-wide hidden layers: the accumulator read of chunk c + 1 is in flight while chunk c is activated
             // (one exposed TMEM round trip per tile instead of four)
@@ -674,7 +691,7 @@ static bool chain_use_ts() {
 static int chain_launch(ChainParams& P, cudaStream_t stream) {
   if (chain_use_ts()) return chain_ts_launch(P, stream);
   P.role_hi = env_int("NUNERF_CHAIN_HIPRIO", 1);
-  P.epi_wait = env_int("NUNERF_CHAIN_EPIWAIT", 1);
+  P.epi_wait = env_int("NUNERF_CHAIN_EPIWAIT", 9);
   return chain_pair() == 2 ? chain_launch_t<2>(P, stream) : chain_launch_t<1>(P, stream);
 }
 

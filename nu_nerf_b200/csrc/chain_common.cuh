@@ -66,7 +66,11 @@ struct ChainParams {
                          // highest warp id first, B300_MICROARCH.md), 0 = warps 0 / 1
   int epi_wait;          // chain.cu (NUNERF_CHAIN_EPIWAIT, default 1): bit 0 = every epilogue warp waits for the accumulator
                          // barrier on its own (0: the 16 warps start each tile together, one waiter + bar.sync -- measured
-                         // 6 % slower on the fused SDF query); bit 1 = the issuer parks on x_done instead of spinning
+                         // 6 % slower on the fused SDF query); bit 1 = the issuer parks on x_done instead of spinning (no
+                         // effect); bit 3 (default on) = ReLU-backward layers issue their four accumulator loads together
+                         // and wait once (their ~40 instructions per chunk cannot hide a TMEM round trip; -2.5 % on the
+                         // plain chains).  The same burst for ReLU-forward layers costs 3 registers + spills and slowed
+                         // every path by 3-4 %: not kept
 };
 
 
