@@ -146,7 +146,11 @@ __device__ __forceinline__ int ch_block(int t, int id) { return t * 4 + id; }
 //           Only the leader CTA (cluster rank 0) issues MMAs and commits; the peer's warp 1 replays the same schedule as a
 //           proxy: it waits for ITS local conditions (epilogue done, input / weight half landed, stores drained) and
 //           arrives on the leader's peer_go[stage] barrier, which the leader waits for before each K-block.
-template <int PAIR>
+// KM = the epilogue kinds this instantiation carries (bit 0: Softplus layers, bit 1: ReLU-forward, bit 2: ReLU-backward,
+//      bit 3: the SDF reverse-pass kinds 4..6; the generic path is always present).  A launch picks the instantiation that
+//      matches the kinds of its layers: smaller code (fewer instruction-cache misses and branches) and a register
+//      allocation that is not the maximum over every epilogue of the file.
+template <int PAIR, int KM>
 __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           const bool row_ok = row < p.M;
           // ReLU-backward layers: this thread's 4 x 16 mask bits, fetched while the tensor core is still busy
           unsigned long long hot_mask = 0ull;
-          if (L.hot == 3) {
+          if ((KM & 4) && L.hot == 3) {
             if (L.mask_perm) {
               hot_mask = __ldg(reinterpret_cast<const unsigned long long*>(L.mask_in + (row_ok ? row : 0) * L.ldmask_in + 8 * j));
             } else {
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           unsigned long long out_mask = 0ull;
           uint4 aux_a[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, aux_b[2] = {aux_a[0], aux_a[0]};
           const long long aux_row = row_ok ? row : 0;
-          if (L.hot >= 4) {
+          if ((KM & 8) && L.hot >= 4) {
             const uint4* pa = reinterpret_cast<const uint4*>(L.aux1 + aux_row * L.ld_aux1 + j * 16);
             aux_a[0] = __ldg(pa); aux_a[1] = __ldg(pa + 1);
             if (L.hot >= 5) {
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           ptx::tc_fence_after();
           if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2] = clock64();
           uint8_t* xt = sX + (size_t)(t * 4) * CH_BLOCK_BYTES;
-          if (L.hot >= 4) {
+          if ((KM & 8) && L.hot >= 4) {
             // aux operands stream from global memory one 64-column chunk ahead of their use (32 bytes per thread, row
             // and chunk: whole sectors); the first chunk was requested before the accumulator wait
 #pragma unroll
@@ -460,7 +464,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               else if (L.hot == 5) ch_aux16<5>(taddr, a0, a1, b0, b1, dst, j, sw, L.e_out + aux_row * L.ld_e + c0, row_ok);
               else ch_aux16<6>(taddr, a0, a1, b0, b1, dst, j, sw, nullptr, row_ok);
             }
-          } else if (L.hot == 3 && (p.epi_wait & 8)) {
+          } else if ((KM & 4) && L.hot == 3 && (p.epi_wait & 8)) {
             // ---- ReLU-backward layers do ~40 instructions per 16-column chunk: too little to hide a TMEM round trip
             // behind, so all four chunk loads of the row go out together and are awaited once
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + j * 16);
@@ -477,7 +481,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             ch_hot16<3>(v1, b, xt + (size_t)CH_BLOCK_BYTES + row_off, j, sw, &ob, (uint32_t)(hot_mask >> 16) & 0xffffu, p.dbg_flags);
             ch_hot16<3>(v2, b, xt + (size_t)2 * CH_BLOCK_BYTES + row_off, j, sw, &ob, (uint32_t)(hot_mask >> 32) & 0xffffu, p.dbg_flags);
             ch_hot16<3>(v3, b, xt + (size_t)3 * CH_BLOCK_BYTES + row_off, j, sw, &ob, (uint32_t)(hot_mask >> 48) & 0xffffu, p.dbg_flags);
-          } else if (L.hot) {
+          } else if ((KM & 7) && L.hot >= 1 && L.hot <= 3) {
             // ---- plain 256-wide hidden layers: the accumulator read of chunk c + 1 is in flight while chunk c is activated
             // (one exposed TMEM round trip per tile instead of four)
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + j * 16);
@@ -501,13 +505,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               if (c < 3) ptx::tmem_ld16(taddr0 + (uint32_t)((c + 1) * 64), (c & 1) ? va : vb);
               uint32_t ob = 0;
               uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
-              if (L.hot == 1) ch_hot16<1>(cur, b, dst, j, sw, &ob, 0u, p.dbg_flags);
-              else if (L.hot == 2) {
+              if ((KM & 1) && L.hot == 1) ch_hot16<1>(cur, b, dst, j, sw, &ob, 0u, p.dbg_flags);
+              else if ((KM & 2) && L.hot == 2) {
                 ch_hot16<2>(cur, b, dst, j, sw, &ob, 0u, p.dbg_flags);
                 if (L.mask_perm) out_mask |= (unsigned long long)ob << (16 * c);
                 else if (L.mask_out && row_ok)
                   *reinterpret_cast<uint16_t*>(L.mask_out + row * L.ldmask_out + (c0 >> 3)) = (uint16_t)ob;
-              } else {
+              } else if (KM & 4) {
                 ch_hot16<3>(cur, b, dst, j, sw, &ob, (uint32_t)(hot_mask >> (16 * c)) & 0xffffu, p.dbg_flags);
               }
             }
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               }
             }
           }
-          if (L.hot == 2 && L.mask_perm && L.mask_out && row_ok)
+          if ((KM & 2) && L.hot == 2 && L.mask_perm && L.mask_out && row_ok)
             *reinterpret_cast<unsigned long long*>(L.mask_out + row * L.ldmask_out + 8 * j) = out_mask;
           // publish: generic-proxy writes of this warp -> visible to the tensor core / TMA (async proxy)
           ptx::fence_proxy_async();
@@ -622,14 +626,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
 // one CTA's, and every tile-layer waits for the slower of two epilogues), so it stays an opt-in experiment.
 static int chain_pair() { return env_int("NUNERF_CHAIN_PAIR", 1) == 2 ? 2 : 1; }
 
-template <int PAIR>
+template <int PAIR, int KM>
 static int chain_launch_t(ChainParams& P, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mlp_chain_kernel<PAIR, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail("chain: cudaFuncSetAttribute: %s", cudaGetErrorString(e), -2);
     if (PAIR == 2) {
-      e = cudaFuncSetAttribute(mlp_chain_kernel<PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+      e = cudaFuncSetAttribute(mlp_chain_kernel<PAIR, KM>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
       (void)e; (void)cudaGetLastError();
     }
     configured = true;
@@ -663,7 +667,7 @@ static int chain_launch_t(ChainParams& P, cudaStream_t stream) {
   if (max_clusters == 0) {
     cfg.gridDim = dim3(num_sms() / cluster * cluster);
     int n = 0;
-    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, mlp_chain_kernel<PAIR>, &cfg);
+    cudaError_t qe = cudaOccupancyMaxActiveClusters(&n, mlp_chain_kernel<PAIR, KM>, &cfg);
     max_clusters = (qe == cudaSuccess && n > 0) ? n : num_sms() / cluster;
     (void)cudaGetLastError();
   }
@@ -673,7 +677,7 @@ static int chain_launch_t(ChainParams& P, cudaStream_t stream) {
   if (grid > need) grid = need;
   { const int g_env = env_int("NUNERF_CHAIN_GRID", 0); if (g_env >= cluster && g_env < grid) grid = g_env / cluster * cluster; }
   cfg.gridDim = dim3(grid);
-  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_chain_kernel<PAIR>, P);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, mlp_chain_kernel<PAIR, KM>, P);
   if (e != cudaSuccess) return fail("chain: cudaLaunchKernelEx: %s", cudaGetErrorString(e), -2);
   NUNERF_CHECK_LAUNCH("mlp_chain_kernel");
   return 0;
@@ -692,7 +696,21 @@ static int chain_launch(ChainParams& P, cudaStream_t stream) {
   if (chain_use_ts()) return chain_ts_launch(P, stream);
   P.role_hi = env_int("NUNERF_CHAIN_HIPRIO", 1);
   P.epi_wait = env_int("NUNERF_CHAIN_EPIWAIT", 9);
-  return chain_pair() == 2 ? chain_launch_t<2>(P, stream) : chain_launch_t<1>(P, stream);
+  if (chain_pair() == 2) return chain_launch_t<2, 15>(P, stream);
+  // the kinds of this chain's layers pick the instantiation (NUNERF_CHAIN_SPECIALISE=0: always the full kernel)
+  int km = 0;
+  for (int l = 0; l < P.n_layers; ++l) {
+    const int h = P.layer[l].hot;
+    km |= h == 1 ? 1 : h == 2 ? 2 : h == 3 ? 4 : h >= 4 ? 8 : 0;
+  }
+  if (!env_int("NUNERF_CHAIN_SPECIALISE", 1)) km = 15;
+  switch (km) {
+    case 0: case 1: return chain_launch_t<1, 1>(P, stream);
+    case 2: return chain_launch_t<1, 2>(P, stream);
+    case 4: return chain_launch_t<1, 4>(P, stream);
+    case 8: return chain_launch_t<1, 8>(P, stream);
+    default: return chain_launch_t<1, 15>(P, stream);
+  }
 }
 
 }  // namespace nunerf
