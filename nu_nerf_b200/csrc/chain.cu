@@ -256,6 +256,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
     long long g = 0;             // layer counter per tile (both tiles advance together): x_done / t_full phase g
     const uint64_t desc_hi = ptx::smem_desc(0, 16, 1024);
     const uint32_t sx_base = ptx::smem_u32(sX), sw_base = ptx::smem_u32(sW);
+    const bool early_in = PAIR == 1 && p.in_mode == 0 && p.layer[p.n_layers - 1].store_chunks == 0 &&
+                          !p.layer[p.n_layers - 1].to_x && !(p.epi_wait & 32);
     for (it = 0; it < num_iters; ++it) {
       const int pair = (int)blockIdx.x + it * (int)gridDim.x;
       for (int l = 0; l < p.n_layers; ++l, ++g) {
@@ -330,6 +332,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             if (stores_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
             if (PAIR == 2) ptx::tc_commit2_mc(&t_full[t], (uint16_t)3);
             else ptx::tc_commit(&t_full[t]);
+            // a chain that ends in a narrow head (nothing written back to X, no store of it): the tile's X blocks are free
+            // as soon as these MMAs have read them -- the producer fetches the next pair's input while the head's epilogue
+            // still runs, instead of after it (short chains lost ~10 % to that bubble)
+            if (early_in && l == p.n_layers - 1) ptx::tc_commit(&in_empty[t]);
             if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 2 + t) * 2] = clock64();
           }
           __syncwarp();
@@ -337,7 +343,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
       }
       // end of the pair: store a kept last layer, then hand the X blocks back to the producer (TMA input mode)
       const int last_store = p.layer[p.n_layers - 1].store_chunks;
-      if (last_store > 0 || p.in_mode == 0) {
+      if (!early_in && (last_store > 0 || p.in_mode == 0)) {
         for (int t = 0; t < 2; ++t) {
           ptx::mbar_wait(&x_done[t], (uint32_t)((g - 1) & 1));
           if (leader) {

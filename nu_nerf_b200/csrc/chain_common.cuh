@@ -70,7 +70,8 @@ struct ChainParams {
                          // effect); bit 3 (default on) = ReLU-backward layers issue their four accumulator loads together
                          // and wait once (their ~40 instructions per chunk cannot hide a TMEM round trip; -2.5 % on the
                          // plain chains).  The same burst for ReLU-forward layers costs 3 registers + spills and slowed
-                         // every path by 3-4 %: not kept
+                         // every path by 3-4 %: not kept; bit 5 = DISABLE the early hand-back of a tile's input blocks in
+                         // chains that end in a narrow head (on by default: predictor forward chains +5 %)
 };
 
 
