@@ -136,7 +136,9 @@ __device__ __forceinline__ void ch_tma_store_2d(const CUtensorMap* m, const void
 
 // Block ids inside sX: tile t in {0,1} owns activation blocks t*4 + (0..3).  The tile input (TMA rows or the in-kernel
 // PE) is written into those same blocks: they are free between the last layer of one pair and the first of the next.
-__device__ __forceinline__ int ch_block(int t, int id) { return t * 4 + id; }
+// A 320-column input (the [feature | p] rows of the material predictors) has a fifth K-block per tile: blocks 8 + t, which
+// exist only in that configuration (ChainParams::x_blocks = 10, one weight stage less).
+__device__ __forceinline__ int ch_block(int t, int id) { return id < 4 ? t * 4 + id : 8 + t; }
 
 // PAIR = 1: one CTA per pair of tiles, cta_group::1 MMAs (M = 128).
 // PAIR = 2: clusters of two CTAs, cta_group::2 MMAs (M = 256 = one tile of each CTA): every CTA keeps its own tiles,
@@ -154,7 +156,7 @@ template <int PAIR, int KM>
 __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  const int n_xblocks = 8;
+  const int n_xblocks = p.x_blocks;
   uint8_t* sX = smem;                                         // activation K-blocks of both tiles
   uint8_t* sW = sX + (size_t)n_xblocks * CH_BLOCK_BYTES;      // weight ring
   const int wstage_bytes = CH_WSTAGE_BYTES / PAIR;             // PAIR = 2: a stage holds this CTA's half of a weight block
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             ptx::mbar_wait_parked(&in_empty[t], (uint32_t)(it & 1) ^ 1);
             ptx::mbar_expect_tx(&in_full[t], (uint32_t)(p.in_blocks * CH_BLOCK_BYTES));
             for (int b = 0; b < p.in_blocks; ++b)      // rows beyond M (or a missing second tile) are zero filled
-              ptx::tma_load_2d(sX + (size_t)(t * 4 + b) * CH_BLOCK_BYTES, &p.in_map, &in_full[t], b * 64,
+              ptx::tma_load_2d(sX + (size_t)ch_block(t, b) * CH_BLOCK_BYTES, &p.in_map, &in_full[t], b * 64,
                                (pair * 2 + t) * 128);
           }
         }
@@ -644,8 +646,10 @@ static int chain_launch_t(ChainParams& P, cudaStream_t stream) {
     }
     configured = true;
   }
-  NUNERF_REQUIRE(P.in_mode == 1 || (P.in_blocks >= 1 && P.in_blocks <= 4), "chain: TMA input must be 1..4 K-blocks");
-  const size_t xbytes = (size_t)8 * CH_BLOCK_BYTES;
+  NUNERF_REQUIRE(P.in_mode == 1 || (P.in_blocks >= 1 && P.in_blocks <= (PAIR == 1 ? 5 : 4)),
+                 "chain: TMA input must be 1..4 K-blocks (5 with the single-CTA kernel)");
+  P.x_blocks = (P.in_mode == 0 && P.in_blocks == 5) ? 10 : 8;
+  const size_t xbytes = (size_t)P.x_blocks * CH_BLOCK_BYTES;
   const size_t fixed = 1024 + 512;
   const int stage_bytes = CH_WSTAGE_BYTES / PAIR;
   int stages = (int)((227 * 1024 - fixed - xbytes) / stage_bytes);
@@ -759,8 +763,9 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
   P.n_layers = a->n_layers; P.M = a->M;
   int width;                         // valid (written) columns of the activation blocks
   if (a->x) {
-    NUNERF_REQUIRE(a->K0 >= 64 && a->K0 % 64 == 0 && a->K0 <= 256 && a->ldx % 8 == 0 && a->ldx >= a->K0,
-                   "mlp_chain: input must be 64..256 columns (multiple of 64), pitch % 8 == 0");
+    const int k0_max = (chain_use_ts() || chain_pair() == 2) ? 256 : 320;
+    NUNERF_REQUIRE(a->K0 >= 64 && a->K0 % 64 == 0 && a->K0 <= k0_max && a->ldx % 8 == 0 && a->ldx >= a->K0,
+                   "mlp_chain: input must be 64..256 columns (320 with the default kernel; multiple of 64), pitch % 8 == 0");
     P.in_mode = 0; P.in_blocks = a->K0 / 64;
     if (int r = make_map(&P.in_map, a->x, a->M, a->K0, a->ldx, 64, 128)) return r;
     width = a->K0;

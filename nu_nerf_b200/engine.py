@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from ._lib import call, ptr
-from .ops import P, linear, linear_dw, colsum, f32_to_planes, chain, GEMM_IMPL
+from .ops import P, linear, linear_dw, colsum, f32_to_planes, chain, GEMM_IMPL, CHAIN_K0_MAX
 from .weights import Dense, WeightBank
 
 SQRT2 = math.sqrt(2.0)
@@ -379,7 +379,7 @@ def pred_forward(w: PredW, x: P, M, K0, planes):
             return dict(W=w.L[i].Wk, N=256, K=K, bias=w.L[i].b, act=1, mask_out=t.Mk[i], store=t.H[i], keep=1,
                         mask_perm=1)
         head = dict(W=w.L[3].Wk, N=16, K=256, bias=w.L[3].b, out32=t.head, n32=16)
-        if K0 <= 256:
+        if K0 <= CHAIN_K0_MAX:
             chain(x, M, K0, [hidden(0, K0), hidden(1, 256), hidden(2, 256), head])
         else:
             linear(x, w.L[0].Wk, M, 256, K0, bias=w.L[0].b, act=1, out=t.H[0], mask_out=t.Mk[0])

@@ -115,6 +115,13 @@ def linear(A: P, B: P, M, N, K, *, a_col=0, b_row=0, bias=None, act=0, aux: P = 
         call("nunerf_linear", C.byref(p))
 
 
+# widest input the fused chain takes: 320 columns (5 K-blocks; the [feature | p] rows of the material predictors) with the
+# default single-CTA kernel, 256 with the opt-in TS / CTA-pair variants (csrc/chain.cu)
+CHAIN_K0_MAX = 256 if (os.environ.get("NUNERF_CHAIN_IMPL", "ss").startswith("t") or
+                       os.environ.get("NUNERF_CHAIN_PAIR", "1") == "2" or
+                       os.environ.get("NUNERF_CHAIN_K0_MAX", "") == "256") else 320
+
+
 def chain(X, M, K0, layers, x_col=0, timeline=None, pts=None):
     """Fused chain of dense layers (csrc/chain.cu, bf16 single-plane operands): `layers` is a list of dicts with keys
     W (P, K-major weight), N, K and optionally n_real, bias, act, mask_out, mask_in, store (P) / store_col, out32, n32,
