@@ -339,13 +339,19 @@ def _sdf_backward_fused(w: SdfWeights, t: SdfTape, dxm: P, d_sdf, d_grad, want_d
     linear_dw(dxm, A[7], M, 1, 256, w.sdf_head.dW, z_col=256, db=w.sdf_head.db)
     DZ = [P(M, 256, planes, dev) for _ in range(8)]      # DZ[l] = d loss / d z_l
     DZ[3].t[:, 217:].zero_()                             # lin3 has 217 outputs: the tail columns are read as K padding
-    linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=DZ[7])
     ew6 = lambda l: dict(W=w.L[l].WTk, N=256, K=256, aux_mode=6, aux1=A[l - 1], aux2=E[l - 1], store=DZ[l - 1], keep=1)
+    # dZ_7 = (dZ_8 [feat | sdf] W_8) . s_7 + E_7: the same glue as the layers below, as the chain's first layer on the
+    # 320-column input when the kernel takes it (else one layer-kernel launch)
+    head7 = []
+    if CHAIN_K0_MAX >= 320:
+        head7 = [dict(W=w.cat8.WTk, N=256, K=320, aux_mode=6, aux1=A[7], aux2=E[7], store=DZ[7], keep=1)]
+    else:
+        linear(dxm, w.cat8.WTk, M, 256, 320, aux=A[7], aux_mode=2, add=E[7], out=DZ[7])
     g_pe0 = g_pe4 = None
     if want_dx:
         g_pe0, g_pe4 = _f(M, 64, dev=dev), _f(M, 64, dev=dev)
     # (want_dx: the PE-input gradients are narrow heads on the resident dZ_4 / dZ_0 of the two chains)
-    chain(DZ[7], M, 256, [ew6(7), ew6(6), ew6(5)] +
+    chain(dxm if head7 else DZ[7], M, 320 if head7 else 256, head7 + [ew6(7), ew6(6), ew6(5)] +
           ([dict(W=w.L[4].WTk, w_row=192, N=64, K=256, out32=g_pe4, n32=64)] if want_dx else []))
     # input of lin4 is [a3 | PE]: only the first 217 columns carry on (PE has no parameters upstream)
     linear(DZ[4], w.L[4].WTk, M, 224, 256, aux=A[3], aux_mode=2, add=E[3], out=DZ[3], n_store=217)
@@ -520,8 +526,12 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes, want_geo=Fals
     if _fused(planes) and t.perm[0]:
         # dZ_7 by the layer kernel (K = 320 input), then the whole dX chain of the 8 x 256 trunk in one launch
         DZ = [P(M, 256, planes, dev) for _ in range(8)]
-        linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=DZ[7])
         lays = []
+        if CHAIN_K0_MAX >= 320:
+            # dZ_7 from the 320-column [d feature | d sigma] rows as the chain's first layer
+            lays.append(dict(W=w.cat8.WTk, N=256, K=320, mask_in=t.Mk[7], mask_perm=t.perm[7], store=DZ[7], keep=1))
+        else:
+            linear(dz8, w.cat8.WTk, M, 256, 320, mask_in=t.Mk[7], out=DZ[7])
         for i in range(7, 0, -1):
             lays.append(dict(W=w.pts[i].WTk, N=256, K=256, mask_in=t.Mk[i - 1], mask_perm=t.perm[i - 1], store=DZ[i - 1],
                              keep=1))
@@ -530,7 +540,10 @@ def nerf_backward(w: NerfW, t: NerfTape, d_alpha, d_color, planes, want_geo=Fals
                 lays.append(dict(W=w.pts[5].WTk, w_row=256, N=128, K=256, out32=g_pe5, n32=128))
         if want_geo:
             lays.append(dict(W=w.pts[0].WTk, N=128, K=256, out32=g_pe0, n32=128))          # ... and on dZ_0
-        chain(DZ[7], M, 256, lays)
+        if CHAIN_K0_MAX >= 320:
+            chain(dz8, M, 320, lays)
+        else:
+            chain(DZ[7], M, 256, lays)
         for i in range(7, 0, -1):
             linear_dw(DZ[i], H[i - 1], M, 256, 384 if i == 5 else 256, w.pts[i].dW, db=w.pts[i].db)
         linear_dw(DZ[0], t.x0, M, 256, 128, w.pts[0].dW, db=w.pts[0].db)
