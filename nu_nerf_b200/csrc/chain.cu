@@ -122,8 +122,7 @@ __device__ __forceinline__ void ch_aux16(uint32_t taddr, const uint4& a0, const 
     uint32_t e[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) e[i] = pack_bf16x2(bv[2 * i], bv[2 * i + 1]);
-    reinterpret_cast<uint4*>(e_dst)[0] = make_uint4(e[0], e[1], e[2], e[3]);
-    reinterpret_cast<uint4*>(e_dst)[1] = make_uint4(e[4], e[5], e[6], e[7]);
+    ptx::st_global_v8(e_dst, e);
   }
 }
 
@@ -430,12 +429,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           uint4 aux_a[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, aux_b[2] = {aux_a[0], aux_a[0]};
           const long long aux_row = row_ok ? row : 0;
           if ((KM & 8) && L.hot >= 4) {
-            const uint4* pa = reinterpret_cast<const uint4*>(L.aux1 + aux_row * L.ld_aux1 + j * 16);
-            aux_a[0] = __ldg(pa); aux_a[1] = __ldg(pa + 1);
-            if (L.hot >= 5) {
-              const uint4* pb = reinterpret_cast<const uint4*>(L.aux2 + aux_row * L.ld_aux2 + j * 16);
-              aux_b[0] = __ldg(pb); aux_b[1] = __ldg(pb + 1);
-            }
+            // (32-byte loads: each lane reads one whole sector of its row with one request)
+            ptx::ld_global_nc_v8(L.aux1 + aux_row * L.ld_aux1 + j * 16, aux_a[0], aux_a[1]);
+            if (L.hot >= 5) ptx::ld_global_nc_v8(L.aux2 + aux_row * L.ld_aux2 + j * 16, aux_b[0], aux_b[1]);
           }
           if ((p.epi_wait & 1) == 0) {
             // one spinning waiter per CTA; the other 15 epilogue warps sleep on a hardware barrier (all 16 warps start a
@@ -459,12 +455,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               const int c0 = c * 64 + j * 16;
               const uint4 a0 = aux_a[0], a1 = aux_a[1], b0 = aux_b[0], b1 = aux_b[1];
               if (c < 3) {
-                const uint4* pa = reinterpret_cast<const uint4*>(L.aux1 + aux_row * L.ld_aux1 + c0 + 64);
-                aux_a[0] = __ldg(pa); aux_a[1] = __ldg(pa + 1);
-                if (L.hot >= 5) {
-                  const uint4* pb = reinterpret_cast<const uint4*>(L.aux2 + aux_row * L.ld_aux2 + c0 + 64);
-                  aux_b[0] = __ldg(pb); aux_b[1] = __ldg(pb + 1);
-                }
+                ptx::ld_global_nc_v8(L.aux1 + aux_row * L.ld_aux1 + c0 + 64, aux_a[0], aux_a[1]);
+                if (L.hot >= 5) ptx::ld_global_nc_v8(L.aux2 + aux_row * L.ld_aux2 + c0 + 64, aux_b[0], aux_b[1]);
               }
               const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(t * 256 + c0);
               uint8_t* dst = xt + (size_t)c * CH_BLOCK_BYTES + row_off;
@@ -813,11 +805,11 @@ extern "C" int nunerf_mlp_chain(const nunerf_mlp_chain_t* a, void* stream_) {
     if (s.aux_mode) {
       NUNERF_REQUIRE(s.aux_mode >= 4 && s.aux_mode <= 6, "mlp_chain: aux_mode must be 0 or 4..6");
       NUNERF_REQUIRE(plain && !s.bias && s.act == 0 && !s.mask_in && !s.mask_out, "mlp_chain: aux layers are plain 256-wide");
-      NUNERF_REQUIRE(s.aux1 && s.ld_aux1 % 8 == 0 && ((uintptr_t)s.aux1 & 15) == 0, "mlp_chain: aux1 must be 16-byte aligned");
+      NUNERF_REQUIRE(s.aux1 && s.ld_aux1 % 16 == 0 && ((uintptr_t)s.aux1 & 31) == 0, "mlp_chain: aux1 must be 32-byte aligned (pitch % 16)");
       if (s.aux_mode >= 5)
-        NUNERF_REQUIRE(s.aux2 && s.ld_aux2 % 8 == 0 && ((uintptr_t)s.aux2 & 15) == 0, "mlp_chain: aux2 must be 16-byte aligned");
+        NUNERF_REQUIRE(s.aux2 && s.ld_aux2 % 16 == 0 && ((uintptr_t)s.aux2 & 31) == 0, "mlp_chain: aux2 must be 32-byte aligned (pitch % 16)");
       if (s.aux_mode == 5)
-        NUNERF_REQUIRE(s.e_out && s.ld_e % 8 == 0 && ((uintptr_t)s.e_out & 15) == 0, "mlp_chain: e_out must be 16-byte aligned");
+        NUNERF_REQUIRE(s.e_out && s.ld_e % 16 == 0 && ((uintptr_t)s.e_out & 31) == 0, "mlp_chain: e_out must be 32-byte aligned (pitch % 16)");
       L.hot = s.aux_mode;
     }
     L.mask_perm = s.mask_perm;

@@ -209,6 +209,12 @@ __device__ __forceinline__ void st_global_v8(void* gptr, const uint32_t* v) {
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// 32-byte read-only global load (LDG.256): one request and one sector per lane instead of two half-sector requests
+__device__ __forceinline__ void ld_global_nc_v8(const void* gptr, uint4& lo, uint4& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(gptr));
+}
 // ---- cta_group::2 (CTA pair: M = 256 split over the two CTAs' A tiles and TMEM, each CTA holds half of B's rows)
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
