@@ -35,6 +35,30 @@ __device__ __forceinline__ void store8(__nv_bfloat16* dst, long long idx, int lo
   }
 }
 
+// 16 columns as ONE 32-byte store per plane (STG.256: a whole sector per lane and half the store requests of two store8)
+// when the address allows it
+__device__ __forceinline__ void store16(__nv_bfloat16* dst, long long idx, int lo, const float* v) {
+  if ((((uintptr_t)(dst + idx)) & 31) != 0 || (lo & 15) != 0) {
+    store8(dst, idx, lo, v);
+    store8(dst, idx + 8, lo, v + 8);
+    return;
+  }
+  uint32_t h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + idx), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]),
+               "r"(h[4]), "r"(h[5]), "r"(h[6]), "r"(h[7])
+               : "memory");
+  if (lo) {
+    uint32_t l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) l[j] = pack_bf16x2(v[2 * j] - bf16lo_to_f(h[j]), v[2 * j + 1] - bf16hi_to_f(h[j]));
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + idx + lo), "r"(l[0]), "r"(l[1]), "r"(l[2]),
+                 "r"(l[3]), "r"(l[4]), "r"(l[5]), "r"(l[6]), "r"(l[7])
+                 : "memory");
+  }
+}
+
 // [x (D), sin(2^0 x) (D), cos(2^0 x) (D), sin(2^1 x) (D), ...] (field.py:14-61) -> row[0 .. D(1+2F))
 template <int D, int F>
 __device__ __forceinline__ void fill_pe(float* row, const float* x) {
@@ -287,9 +311,11 @@ __global__ void __launch_bounds__(128) shade_encode_fwd_kernel(nunerf_shade_enco
     for (int j = 112; j < 128; ++j) row[j] = 0.f;
     const long long ro = ((long long)job * M + m) * p.ld_outer;
 #pragma unroll
-    for (int c = 0; c < 9; ++c) store8(xo, ro + c * 8, p.lo_outer, out + c * 8);
+    for (int c = 0; c < 4; ++c) store16(xo, ro + c * 16, p.lo_outer, out + c * 16);
+    store8(xo, ro + 64, p.lo_outer, out + 64);
+    store8(xo, ro + 72, p.lo_outer, row + 112);
 #pragma unroll
-    for (int c = 9; c < 16; ++c) store8(xo, ro + c * 8, p.lo_outer, row + 112);
+    for (int c = 5; c < 8; ++c) store16(xo, ro + c * 16, p.lo_outer, row + 112);
     if (job >= 1) {
       // inner input row = [PE6(p) (39) | IDE (72) | 0]: shift the IDE block down by one column
 #pragma unroll
@@ -298,7 +324,7 @@ __global__ void __launch_bounds__(128) shade_encode_fwd_kernel(nunerf_shade_enco
       fill_pe<3, 6>(row, pt);
       const long long ri = ((long long)(job - 1) * M + m) * p.ld_inner;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) store8(xi, ri + c * 8, p.lo_inner, row + c * 8);
+      for (int c = 0; c < 8; ++c) store16(xi, ri + c * 16, p.lo_inner, row + c * 16);
     }
   } else {
     __nv_bfloat16* xw = (__nv_bfloat16*)p.x_weight;
@@ -308,10 +334,10 @@ __global__ void __launch_bounds__(128) shade_encode_fwd_kernel(nunerf_shade_enco
 #pragma unroll
     for (int j = 78; j < 128; ++j) row[j] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) store8(xw, m * p.ld_weight + c * 8, p.lo_weight, row + c * 8);
+    for (int c = 0; c < 8; ++c) store16(xw, m * p.ld_weight + c * 16, p.lo_weight, row + c * 16);
     fill_pe<3, 6>(row + 39, s.v);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) store8(xr, m * p.ld_refrac + c * 8, p.lo_refrac, row + c * 8);
+    for (int c = 0; c < 8; ++c) store16(xr, m * p.ld_refrac + c * 16, p.lo_refrac, row + c * 16);
     p.nov[m] = s.nov;
     if (p.refl) { p.refl[3 * m] = s.r[0]; p.refl[3 * m + 1] = s.r[1]; p.refl[3 * m + 2] = s.r[2]; }
   }
