@@ -93,11 +93,22 @@ encode_pe_kernel(const float* __restrict__ x, long long M, __nv_bfloat16* dst, i
   for (int j = REAL; j < PADW; ++j) row[j] = 0.f;
   const long long base = (row_off + m) * ld + col_off;
   if (((col_off | ld | lo_off) & 7) == 0 && (width & 7) == 0) {
+    // 16 columns per store where a pair of 8-column groups is available (32-byte stores), 8 for an odd tail group
+    const float zero[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    constexpr int G = PADW / 8;                 // 8-column groups that hold real values
 #pragma unroll
-    for (int c = 0; c < PADW / 8; ++c)
-      if (c * 8 < width) store8(dst, base + c * 8, lo_off, row + c * 8);
-    const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int c = PADW / 8; c * 8 < width; ++c) store8(dst, base + c * 8, lo_off, zero);
+    for (int c = 0; c + 1 < G; c += 2)
+      if (c * 8 + 16 <= width) store16(dst, base + c * 8, lo_off, row + c * 8);
+      else if (c * 8 < width) store8(dst, base + c * 8, lo_off, row + c * 8);
+    int c_next = G & ~1;
+    if (G & 1) {
+      if ((G - 1) * 8 < width) store8(dst, base + (G - 1) * 8, lo_off, row + (G - 1) * 8);
+      c_next = G;
+    }
+    for (int c = c_next; c * 8 < width;) {
+      if ((c & 1) == 0 && c * 8 + 16 <= width) { store16(dst, base + c * 8, lo_off, zero); c += 2; }
+      else { store8(dst, base + c * 8, lo_off, zero); c += 1; }
+    }
   } else {
 #pragma unroll
     for (int j = 0; j < PADW; ++j)
@@ -433,11 +444,13 @@ ide_encode_kernel(const float* __restrict__ x, long long M, float kinv, __nv_bfl
   if (m >= M) return;
   float out[72];
   pw::ide_fwd(c_ide, x[3 * m], x[3 * m + 1], x[3 * m + 2], kinv, out);
-  const float zero[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float zero[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int c = 0; c < 9; ++c) store8(dst, m * ld + col + c * 8, lo, out + c * 8);
+  for (int c = 0; c < 4; ++c) store16(dst, m * ld + col + c * 16, lo, out + c * 16);
+  store8(dst, m * ld + col + 64, lo, out + 64);
+  store8(dst, m * ld + col + 72, lo, zero);
 #pragma unroll
-  for (int c = 9; c < 16; ++c) store8(dst, m * ld + col + c * 8, lo, zero);
+  for (int c = 5; c < 8; ++c) store16(dst, m * ld + col + c * 16, lo, zero);
 }
 
 // ------------------------------------------------------------------------------------------- shading mix
