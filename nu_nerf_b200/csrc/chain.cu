@@ -87,8 +87,8 @@ __device__ __forceinline__ void ch_hot16(const uint32_t* v, const float4* b, uin
     if (h[0] == 0x12345678u && h[5] == 0x9abcdef0u) *obits = h[3];   // keep the math alive without the store
     return;
   }
-  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+  ptx::st_shared_v4(dst + (((uint32_t)(2 * j) ^ sw) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+  ptx::st_shared_v4(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4), make_uint4(h[4], h[5], h[6], h[7]));
 }
 
 // Aux epilogues (kinds 4..6, see ChainLayer): 16 columns of one row; a0/a1 = the 16 bf16 of aux1, b0/b1 of aux2.
@@ -116,8 +116,8 @@ __device__ __forceinline__ void ch_aux16(uint32_t taddr, const uint4& a0, const 
   uint32_t h[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+  ptx::st_shared_v4(dst + (((uint32_t)(2 * j) ^ sw) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+  ptx::st_shared_v4(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4), make_uint4(h[4], h[5], h[6], h[7]));
   if (KIND == 5 && row_ok) {
     uint32_t e[8];
 #pragma unroll
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             for (int ch = 0; ch < 8; ++ch) {
               uint4 v = make_uint4(pack_bf16x2(pe[8 * ch], pe[8 * ch + 1]), pack_bf16x2(pe[8 * ch + 2], pe[8 * ch + 3]),
                                    pack_bf16x2(pe[8 * ch + 4], pe[8 * ch + 5]), pack_bf16x2(pe[8 * ch + 6], pe[8 * ch + 7]));
-              *reinterpret_cast<uint4*>(dst + (((uint32_t)ch ^ sw) << 4)) = v;
+              ptx::st_shared_v4(dst + (((uint32_t)ch ^ sw) << 4), v);
             }
           }
           ptx::fence_proxy_async();
@@ -495,8 +495,13 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               // instead of being exposed at the first add (ncu: 7 % of all stall samples sat there)
               float4 b[4];
               if (L.hot != 3 && !(p.dbg_flags & 64)) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) b[i] = __ldg(reinterpret_cast<const float4*>(L.bias + c0) + i);
+                {
+                  uint4 q0, q1, q2, q3;        // 2 x 32-byte loads (c0 is a multiple of 16 floats)
+                  ptx::ld_global_nc_v8(L.bias + c0, q0, q1);
+                  ptx::ld_global_nc_v8(L.bias + c0 + 8, q2, q3);
+                  b[0] = *reinterpret_cast<float4*>(&q0); b[1] = *reinterpret_cast<float4*>(&q1);
+                  b[2] = *reinterpret_cast<float4*>(&q2); b[3] = *reinterpret_cast<float4*>(&q3);
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -581,8 +586,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
                 uint32_t h[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-                *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j) ^ sw) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+                ptx::st_shared_v4(dst + (((uint32_t)(2 * j) ^ sw) << 4), make_uint4(h[0], h[1], h[2], h[3]));
+                ptx::st_shared_v4(dst + (((uint32_t)(2 * j + 1) ^ sw) << 4), make_uint4(h[4], h[5], h[6], h[7]));
               }
               if (in_acc && L.out32 && row_ok) {
                 float* o = L.out32 + row * L.ldo32 + c0;

@@ -209,6 +209,11 @@ __device__ __forceinline__ void st_global_v8(void* gptr, const uint32_t* v) {
                "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
+// 16-byte store to shared memory through its 32-bit window address (STS.128; a store through a generic pointer compiles to
+// the generic ST with 64-bit address arithmetic)
+__device__ __forceinline__ void st_shared_v4(void* smem_ptr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(smem_u32(smem_ptr)), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // 32-byte read-only global load (LDG.256): one request and one sector per lane instead of two half-sector requests
 __device__ __forceinline__ void ld_global_nc_v8(const void* gptr, uint4& lo, uint4& hi) {
   asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
