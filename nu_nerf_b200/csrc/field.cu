@@ -631,6 +631,21 @@ __global__ void f32_to_planes_kernel(const float* __restrict__ a, int lda, const
   store_planes(dst, m * ld + col + c, lo, v);
 }
 
+__global__ void f32_to_planes8_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, long long M,
+                                      int C, int groups, __nv_bfloat16* dst, int ld, int lo, int col) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * groups) return;
+  const long long m = idx / groups;
+  const int c0 = (int)(idx % groups) << 3;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c0 + j;
+    v[j] = c < C ? a[m * lda + c] + (b ? b[m * ldb + c] : 0.f) : 0.f;
+  }
+  store8(dst, m * ld + col + c0, lo, v);
+}
+
 __global__ void adam_kernel(float* p, const float* __restrict__ g, float* m, float* v, long long n, float lr, float b1,
                             float b2, float eps, float bc1, float bc2) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -854,6 +869,13 @@ extern "C" int nunerf_sdf_bwd2_ew(const void* gts, int ldt, int t_lo, const void
 extern "C" int nunerf_f32_to_planes(const float* a, int lda, const float* b, int ldb, int M, int C, int width, void* dst,
                                     int ld, int lo, int col, void* stream) {
   NUNERF_REQUIRE(a && dst && M > 0 && C > 0 && width >= C, "f32_to_planes: bad arguments");
+  if (((width | col | ld | lo) & 7) == 0 && (((uintptr_t)dst) & 15) == 0) {
+    // 8 columns per thread, one 16-byte store per plane (the usual case: a few real columns + zero padding to 64)
+    f32_to_planes8_kernel<<<G1((long long)M * (width >> 3)), 0, ST(stream)>>>(a, lda, b, ldb, M, C, width >> 3,
+                                                                             (__nv_bfloat16*)dst, ld, lo, col);
+    NUNERF_CHECK_LAUNCH("f32_to_planes8_kernel");
+    return 0;
+  }
   f32_to_planes_kernel<<<G1((long long)M * width), 0, ST(stream)>>>(a, lda, b, ldb, M, C, width, (__nv_bfloat16*)dst,
                                                                    ld, lo, col);
   NUNERF_CHECK_LAUNCH("f32_to_planes_kernel");
