@@ -47,7 +47,7 @@ def test_chain_argument_validation_without_gpu():
     a = _lib.MlpChainT()
     assert _lib.lib.nunerf_mlp_chain(ctypes.byref(a), None) < 0                      # no input
     buf = (ctypes.c_char * 4096)()
-    a.x, a.ldx, a.K0, a.M, a.n_layers = ctypes.addressof(buf), 320, 320, 16, 1       # input wider than 256 columns
+    a.x, a.ldx, a.K0, a.M, a.n_layers = ctypes.addressof(buf), 384, 384, 16, 1       # input wider than 320 columns
     rc = _lib.lib.nunerf_mlp_chain(ctypes.byref(a), None)
     assert rc < 0 and b"mlp_chain" in _lib.lib.nunerf_last_error()
     a.ldx, a.K0, a.n_layers = 64, 64, 11                                              # too many layers
