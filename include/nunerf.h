@@ -291,7 +291,8 @@ typedef struct {
   const float* refrac; int ld_refrac;     /* [M, ld] */
   const float* nov; const float* lut;     /* [M]; FG LUT [256,256,2] */
   float* color; float* trans_out; float* metallic_out; float* occ_prob;
-  /* backward: dZ operands of the head layers as bf16 planes [*, ld_dz] (zero padded by the caller) */
+  /* backward: dZ operands of the head layers as bf16 planes [*, ld_dz >= 64]: the kernel writes 64 columns of every row
+   * (the values + zero padding), the buffers need no prior fill */
   const float* d_color; const float* d_trans_out; const float* d_metallic_out;
   void* dz_metallic; void* dz_albedo; void* dz_trans; void* dz_outer; void* dz_inner; void* dz_weight; void* dz_refrac;
   int ld_dz; int lo_dz;

@@ -591,7 +591,14 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               }
               if (in_acc && L.out32 && row_ok) {
                 float* o = L.out32 + row * L.ldo32 + c0;
-                if (c0 + 16 <= L.n32 && (L.ldo32 & 3) == 0) {
+                if (c0 + 16 <= L.n32 && (L.ldo32 & 7) == 0 && (((uintptr_t)L.out32) & 31) == 0) {
+                  // two 32-byte stores: whole sectors of the thread's own row
+                  uint32_t w[16];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) w[i] = __float_as_uint(x[i]);
+                  ptx::st_global_v8(o, w);
+                  ptx::st_global_v8(o + 8, w + 8);
+                } else if (c0 + 16 <= L.n32 && (L.ldo32 & 3) == 0) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i)
                     reinterpret_cast<float4*>(o)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);

@@ -495,18 +495,25 @@ __global__ void shade_mix_bwd_kernel(nunerf_shade_mix_t p) {
                     p.d_metallic_out ? p.d_metallic_out[m] : 0.f, &d);
   if (p.d_occ_prob) d.occ += 0.5f * p.d_occ_prob[m];   // occ_prob = raw * 0.5 + 0.5 (field.py:659), unclipped output
   const int ld = p.ld_dz, lo = p.lo_dz;
-  store_planes((__nv_bfloat16*)p.dz_metallic, m * ld, lo, d.metallic);
-  store_planes((__nv_bfloat16*)p.dz_trans, m * ld, lo, d.trans);
-  store_planes((__nv_bfloat16*)p.dz_weight, m * ld, lo, d.occ);
-  for (int c = 0; c < 3; ++c) {
-    store_planes((__nv_bfloat16*)p.dz_albedo, m * ld + c, lo, d.albedo[c]);
-    store_planes((__nv_bfloat16*)p.dz_outer, m * ld + c, lo, d.diffuse_l[c]);
-    store_planes((__nv_bfloat16*)p.dz_outer, (M + m) * ld + c, lo, d.direct[c]);
-    store_planes((__nv_bfloat16*)p.dz_outer, (2 * M + m) * ld + c, lo, d.direct0[c]);
-    store_planes((__nv_bfloat16*)p.dz_inner, m * ld + c, lo, d.indirect[c]);
-    store_planes((__nv_bfloat16*)p.dz_inner, (M + m) * ld + c, lo, d.indirect0[c]);
-    store_planes((__nv_bfloat16*)p.dz_refrac, m * ld + c, lo, d.refrac[c]);
-  }
+  // every head row is written WHOLE (64 columns: up to 3 values + zero padding) with 32-byte stores, so the dZ operand
+  // buffers need no prior zero fill and no 2-byte partial-sector writes
+  auto row64 = [&](void* dst, long long row, float a, float b, float c) {
+    float v[16] = {a, b, c, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float z[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    __nv_bfloat16* d_ = (__nv_bfloat16*)dst;
+    store16(d_, row * ld, lo, v);
+    if (ld >= 64) { store16(d_, row * ld + 16, lo, z); store16(d_, row * ld + 32, lo, z); store16(d_, row * ld + 48, lo, z); }
+  };
+  row64(p.dz_metallic, m, d.metallic, 0.f, 0.f);
+  row64(p.dz_trans, m, d.trans, 0.f, 0.f);
+  row64(p.dz_weight, m, d.occ, 0.f, 0.f);
+  row64(p.dz_albedo, m, d.albedo[0], d.albedo[1], d.albedo[2]);
+  row64(p.dz_outer, m, d.diffuse_l[0], d.diffuse_l[1], d.diffuse_l[2]);
+  row64(p.dz_outer, M + m, d.direct[0], d.direct[1], d.direct[2]);
+  row64(p.dz_outer, 2 * M + m, d.direct0[0], d.direct0[1], d.direct0[2]);
+  row64(p.dz_inner, m, d.indirect[0], d.indirect[1], d.indirect[2]);
+  row64(p.dz_inner, M + m, d.indirect0[0], d.indirect0[1], d.indirect0[2]);
+  row64(p.dz_refrac, m, d.refrac[0], d.refrac[1], d.refrac[2]);
   p.d_rough_raw[m] = d.rough;  // completed (and turned into planes) after shade_encode_bwd adds its share
   p.d_nov[m] = d.nov;
 }

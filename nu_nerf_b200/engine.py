@@ -823,8 +823,9 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     planes, dev, M = w.planes, t.pts_in.device, t.n_in
     g = {} if g is None else g
     # ---- shading mix
-    dz = {k: P(M, 64, planes, dev, zero=True) for k in ("metallic", "albedo", "trans", "weight", "refrac")}
-    dz["outer"], dz["inner"] = P(3 * M, 64, planes, dev, zero=True), P(2 * M, 64, planes, dev, zero=True)
+    # (shade_mix_bwd writes every row of these dZ operands whole, zero padding included: no prior fill)
+    dz = {k: P(M, 64, planes, dev) for k in ("metallic", "albedo", "trans", "weight", "refrac")}
+    dz["outer"], dz["inner"] = P(3 * M, 64, planes, dev), P(2 * M, 64, planes, dev)
     d_rough, d_nov = _f(M, dev=dev), _f(M, dev=dev)
     call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov, d_occ)))
     if d_nov_ext is not None:
