@@ -709,9 +709,50 @@ extern "C" int nunerf_sdf_grad_pe(const float* x, const float* ga, int lda, cons
   return 0;
 }
 
+// one thread per row: the 39 values once, written as 32-byte stores (the 64-wide destination whole; the 39-wide one -- the
+// skip columns 217..255 of a 256-wide row -- as 7 single columns up to the next 16-column boundary + two 32-byte stores)
+__global__ void sdf_grad_pe_bwd_row_kernel(const float* __restrict__ x, const float* __restrict__ dgrad, long long M,
+                                           __nv_bfloat16* d1, int ld1, int lo1, __nv_bfloat16* d2, int ld2, int lo2) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float v[64];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float g = dgrad[3 * m + c], xc = x[3 * m + c];
+    v[c] = g;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float f = (float)(1 << k);
+      float s, co;
+      sincosf(xc * f, &s, &co);
+      v[3 + 6 * k + c] = g * f * co;
+      v[6 + 6 * k + c] = -g * f * s;
+    }
+  }
+#pragma unroll
+  for (int j = 39; j < 64; ++j) v[j] = 0.f;
+  if (d1) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) store16(d1, m * ld1 + c * 16, lo1, v + c * 16);
+  }
+  if (d2) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) store_planes(d2, m * ld2 + 217 + j, lo2, v[j]);
+    store16(d2, m * ld2 + 224, lo2, v + 7);
+    store16(d2, m * ld2 + 240, lo2, v + 23);
+  }
+}
+
 extern "C" int nunerf_sdf_grad_pe_bwd(const float* x, const float* dgrad, int M, void* d1, int ld1, int lo1, int col1,
                                       int width1, void* d2, int ld2, int lo2, int col2, int width2, void* stream) {
   NUNERF_REQUIRE(x && dgrad && M > 0 && (d1 || d2), "sdf_grad_pe_bwd: bad arguments");
+  if ((!d1 || (col1 == 0 && width1 == 64 && (ld1 & 15) == 0 && (lo1 & 15) == 0 && (((uintptr_t)d1) & 31) == 0)) &&
+      (!d2 || (col2 == 217 && width2 == 39 && (ld2 & 15) == 0 && (lo2 & 15) == 0 && (((uintptr_t)d2) & 31) == 0))) {
+    sdf_grad_pe_bwd_row_kernel<<<G1(M), 0, ST(stream)>>>(x, dgrad, M, (__nv_bfloat16*)d1, ld1, lo1, (__nv_bfloat16*)d2, ld2,
+                                                        lo2);
+    NUNERF_CHECK_LAUNCH("sdf_grad_pe_bwd_row_kernel");
+    return 0;
+  }
   int wmax = width1 > width2 ? width1 : width2;
   long long total = (long long)M * wmax;
   sdf_grad_pe_bwd_kernel<<<G1(total), 0, ST(stream)>>>(x, dgrad, M, (__nv_bfloat16*)d1, ld1, lo1, col1, width1,
