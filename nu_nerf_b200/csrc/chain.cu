@@ -27,6 +27,15 @@
 
 namespace nunerf {
 
+// Timing experiments (NUNERF_CHAIN_DEBUG bits) and the per-layer timeline stamps are compiled in only with
+// -DNUNERF_CHAIN_DEBUG_BUILD=1 (`make EXTRA=-DNUNERF_CHAIN_DEBUG_BUILD=1`, tools/chain_timeline.py / tools/gpu_d.sh): in the
+// product build the flag tests and the keep-alive compares they need cost ~4 % of the epilogue instructions.
+#ifndef NUNERF_CHAIN_DEBUG_BUILD
+#define NUNERF_CHAIN_DEBUG_BUILD 0
+#endif
+#define CH_DBGF(flags) (NUNERF_CHAIN_DEBUG_BUILD ? (flags) : 0)
+#define CH_TL(ptr) (NUNERF_CHAIN_DEBUG_BUILD ? (ptr) : (long long*)nullptr)
+
 // Hot epilogue of a plain 256-wide hidden layer -> bf16 -> shared memory: 16 columns of one row.
 //   KIND 1: bias + Softplus(beta = 100)              (SDF network)
 //   KIND 2: bias + ReLU, emits the 16 (x > 0) bits    (predictor / NeRF++ forward)
@@ -83,7 +92,7 @@ __device__ __forceinline__ void ch_hot16(const uint32_t* v, const float4* b, uin
   uint32_t h[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-  if (dbg_flags & 2) {
+  if (CH_DBGF(dbg_flags) & 2) {
     if (h[0] == 0x12345678u && h[5] == 0x9abcdef0u) *obits = h[3];   // keep the math alive without the store
     return;
   }
@@ -228,9 +237,9 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             for (int kb = 0; kb < nkb; ++kb) {
               // the stage is free once the MMAs that read it have completed (tcgen05.commit, multicast to the pair)
               ptx::mbar_wait_parked(&w_empty[stage], phase ^ 1);
-              if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[400 + (t * 4 + kb)] = clock64();
+              if (CH_TL(p.dbg) && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[400 + (t * 4 + kb)] = clock64();
               // box = 64 K-columns x N / PAIR rows
-              if (p.dbg_flags & 32) {            // timing experiment: no weight traffic at all (stale weights)
+              if (CH_DBGF(p.dbg_flags) & 32) {            // timing experiment: no weight traffic at all (stale weights)
                 ptx::mbar_arrive(&w_full[stage]);
               } else {
                 ptx::mbar_expect_tx(&w_full[stage], (uint32_t)p.layer[l].w_box_bytes);
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
           // the previous layer's epilogue of this tile has drained the accumulator and written the activation
 #if NUNERF_CHAIN_TIMELINE_DETAIL
-          if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[450 + t] = clock64();
+          if (CH_TL(p.dbg) && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[450 + t] = clock64();
 #endif
           if (g > 0) {
             if (p.epi_wait & 2) ptx::mbar_wait_parked(&x_done[t], (uint32_t)((g - 1) & 1));
@@ -277,7 +286,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           if (l == 0) ptx::mbar_wait(&in_full[t], (uint32_t)(it & 1));
           ptx::tc_fence_after();
 #if NUNERF_CHAIN_TIMELINE_DETAIL
-          if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[420 + t] = clock64();
+          if (CH_TL(p.dbg) && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[420 + t] = clock64();
 #endif
           bool stores_pending = false;
           if (prev_store > 0) {
@@ -294,7 +303,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             ptx::mbar_wait(&w_full[stage], phase);
             ptx::tc_fence_after();
 #if NUNERF_CHAIN_TIMELINE_DETAIL
-            if (p.dbg && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[430 + (t * 4 + kb) * 2] = clock64();
+            if (CH_TL(p.dbg) && leader && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[430 + (t * 4 + kb) * 2] = clock64();
 #endif
             if (PAIR == 2 && !cta_leader) {
               // proxy of the peer CTA: everything the pair's MMA on this K-block needs from THIS CTA is in place (the
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               const uint64_t ad0 = desc_hi | (uint64_t)(((sx_base + (uint32_t)blk * CH_BLOCK_BYTES) >> 4) & 0x3fff);
               const uint64_t bd0 = desc_hi | (uint64_t)(((sw_base + (uint32_t)stage * wstage_bytes) >> 4) & 0x3fff);
               if (leader) {
-                if (!(p.dbg_flags & 16)) {         // (16: timing experiment without the MMAs themselves)
+                if (!(CH_DBGF(p.dbg_flags) & 16)) {         // (16: timing experiment without the MMAs themselves)
                   if (PAIR == 2) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)    // +32 bytes per K = 16 step: +2 in the (address >> 4) field
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
                 if (PAIR == 2) ptx::tc_commit2_mc(&w_empty[stage], (uint16_t)3);
                 else ptx::tc_commit(&w_empty[stage]);
 #if NUNERF_CHAIN_TIMELINE_DETAIL
-                if (p.dbg && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[430 + (t * 4 + kb) * 2 + 1] = clock64();
+                if (CH_TL(p.dbg) && blockIdx.x == 0 && it == 1 && l == 5) p.dbg[430 + (t * 4 + kb) * 2 + 1] = clock64();
 #endif
               }
             }
@@ -337,7 +346,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             // as soon as these MMAs have read them -- the producer fetches the next pair's input while the head's epilogue
             // still runs, instead of after it (short chains lost ~10 % to that bubble)
             if (early_in && l == p.n_layers - 1) ptx::tc_commit(&in_empty[t]);
-            if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 2 + t) * 2] = clock64();
+            if (CH_TL(p.dbg) && blockIdx.x == 0 && it == 1 && l < 12) p.dbg[(l * 2 + t) * 2] = clock64();
           }
           __syncwarp();
         }
@@ -445,7 +454,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
             __syncwarp();
           }
           ptx::tc_fence_after();
-          if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2] = clock64();
+          if (CH_TL(p.dbg) && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2] = clock64();
           uint8_t* xt = sX + (size_t)(t * 4) * CH_BLOCK_BYTES;
           if ((KM & 8) && L.hot >= 4) {
             // aux operands stream from global memory one 64-column chunk ahead of their use (32 bytes per thread, row
@@ -494,7 +503,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
               // this chunk's 16 biases are requested BEFORE the accumulator wait: their (L1) latency hides behind it
               // instead of being exposed at the first add (ncu: 7 % of all stall samples sat there)
               float4 b[4];
-              if (L.hot != 3 && !(p.dbg_flags & 64)) {
+              if (L.hot != 3 && !(CH_DBGF(p.dbg_flags) & 64)) {
                 {
                   uint4 q0, q1, q2, q3;        // 2 x 32-byte loads (c0 is a multiple of 16 floats)
                   ptx::ld_global_nc_v8(L.bias + c0, q0, q1);
@@ -617,7 +626,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) mlp_chain_kernel(const __grid_c
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&x_done[t]);
-          if (p.dbg && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2 + 1] = clock64();
+          if (CH_TL(p.dbg) && blockIdx.x == 0 && it == 1 && l < 12 && lane == 0 && ew == 0) p.dbg[256 + (l * 2 + t) * 2 + 1] = clock64();
         }
       }
     }
