@@ -222,18 +222,66 @@ def brute_force_closest_hit(V, Fc, o, d, chunk=256):
     return hit, idx
 
 
-def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tmp"):
-    """Stage2Renderer(cfg, training=False) of renderer_zerothick with configs/stage2/nerf/spherepot.yaml, a stage-1
-    checkpoint made from a seeded random-init NeROShapeRenderer, and the in-memory mesh (shim 5: Scene built from V, F
-    with the reference's own corner-angle vertex normals; curvature zero -- unused by the zero-thickness path)."""
+def angle_defect_curvature(V, Fc, clip=10.0):
+    """The stated replacement for PyMesh's vertex_gaussian_curvature (DiffRender.py:331, :360; clipped to [-10, 10] there),
+    restated in numpy for the oracle side: (2 pi - sum of corner angles) / (one third of the incident triangle area).
+    Parity against PyMesh itself is unpinned (the fork the reference builds against is not available)."""
+    V = np.asarray(V, np.float64)
+    Fc = np.asarray(Fc, np.int64)
+    tri = V[Fc]
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    defect = np.full(V.shape[0], 2.0 * np.pi)
+    varea = np.zeros(V.shape[0])
+    for i in range(3):
+        a = tri[:, (i + 1) % 3] - tri[:, i]
+        b = tri[:, (i + 2) % 3] - tri[:, i]
+        cosv = (a * b).sum(-1) / (np.linalg.norm(a, axis=1) * np.linalg.norm(b, axis=1))
+        np.add.at(defect, Fc[:, i], -np.arccos(np.clip(cosv, -1.0, 1.0)))
+        np.add.at(varea, Fc[:, i], area / 3.0)
+    return np.clip(defect / np.maximum(varea, 1e-30), -clip, clip).astype(np.float32).reshape(-1, 1)
+
+
+def torus(R=0.55, r=0.22, nu=40, nv=20):
+    """Closed torus around the z axis (both curvature signs: the non-zero-thickness shell offset has a branch per sign).
+    float64 vertices [nu*nv,3], int64 faces [2*nu*nv,3], counter-clockwise seen from outside."""
+    verts, faces = [], []
+    for i in range(nu):
+        ph = 2.0 * math.pi * i / nu
+        for j in range(nv):
+            th = 2.0 * math.pi * j / nv
+            verts.append([(R + r * math.cos(th)) * math.cos(ph), (R + r * math.cos(th)) * math.sin(ph), r * math.sin(th)])
+    idx = lambda i, j: (i % nu) * nv + (j % nv)
+    for i in range(nu):
+        for j in range(nv):
+            a, b, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+            faces.append([a, b, c])
+            faces.append([a, c, d])
+    return np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int64)
+
+
+def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tmp", thick=False):
+    """Stage2Renderer(cfg, training=False) of renderer_zerothick (thick=False) or of the non-zero-thickness
+    network/renderer.py (thick=True) with configs/stage2/nerf/spherepot.yaml, a stage-1
+    checkpoint made from a seeded random-init NeROShapeRenderer of the same module, and the in-memory mesh (shim 5: Scene
+    built from V, F with the reference's own corner-angle vertex normals; vertex Gaussian curvature = zero for the
+    zero-thickness path, which never reads it, and angle_defect_curvature() for the non-zero-thickness one)."""
     install()
-    net1, _ = load_stage1(seed=stage1_seed, fg_lut=fg_lut)
-    ckpt = os.path.join(tmp_dir, "nunerf_stage1_ckpt.pth")
-    torch.save({"network_state_dict": net1.state_dict(), "step": 0}, ckpt)
     with in_ref_dir():
         from utils.base_utils import load_cfg
         import network.DiffRender as DR
-        import network.renderer_zerothick as ZT
+        if thick:
+            import network.renderer as ZT
+        else:
+            import network.renderer_zerothick as ZT
+        cfg1 = load_cfg("configs/shape/nerf/spherepot.yaml")
+        torch.manual_seed(stage1_seed)
+        net1 = ZT.NeROShapeRenderer(cfg1, training=False)
+    if fg_lut is not None:
+        net1.color_network.FG_LUT.copy_(torch.as_tensor(fg_lut).reshape(1, 256, 256, 2))
+    ckpt = os.path.join(tmp_dir, "nunerf_stage1_ckpt_nz.pth" if thick else "nunerf_stage1_ckpt.pth")
+    torch.save({"network_state_dict": net1.state_dict(), "step": 0}, ckpt)
+    curv = angle_defect_curvature(mesh_V, mesh_F) if thick else np.zeros((len(mesh_V), 1), np.float32)
+    with in_ref_dir():
 
         class ShimOptix:
             def update_mesh(self, F_, V_):
@@ -252,7 +300,7 @@ def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tm
                 self.faces = torch.tensor(mesh_F, dtype=torch.long)
                 self.triangles = self.vertices[self.faces]
                 self.optix_mesh.update_mesh(self.faces.to(torch.int32), self.vertices.to(torch.float32))
-                # init_VN (DiffRender.py:342-359) with the reference's JIT_corner_angles; curvature unused (ZT)
+                # init_VN (DiffRender.py:342-359) with the reference's JIT_corner_angles
                 corner_angles, face_N = DR.JIT_corner_angles(self.triangles)
                 row = self.faces.view(-1)
                 col = torch.arange(len(self.faces)).unsqueeze(1).expand(-1, 3).reshape(-1)
@@ -260,7 +308,7 @@ def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tm
                                             (len(self.vertices), len(self.faces)))
                 vert_N = torch.sparse.mm(M, face_N)
                 self.normals = vert_N / vert_N.norm(dim=1, p=2, keepdim=True)
-                self.gaussian_curvatures = torch.zeros(len(self.vertices), 1, dtype=torch.float64)
+                self.gaussian_curvatures = torch.tensor(curv).reshape(-1, 1)          # DiffRender.py:360
 
         DR.device = "cpu"            # module-level placement constant of DiffRender.py:16 (shim 3)
         ZT.Scene = ShimScene
