@@ -275,6 +275,11 @@ typedef struct {
    * refraction-light inputs is ADDED to d_pts[M,3] and d ray-direction (reflected direction, NoV, PE6(v)) to d_dirs[M,3] */
   const float* d_x_refrac; int ld_dxr;                       /* fp32 [M, ld] (78 cols used) or NULL */
   float* d_pts; float* d_dirs;
+  /* encoding frequencies of the network evaluated: 0 = the AppShadingNetwork defaults (6 / 6, field.py:562-567).  The
+   * inner field of the non-zero-thickness stage 2, AppShadingNetwork_SpecInner (field.py:1320-1330), has
+   * light_pos_freq 8 (the PE(p) block of x_inner / x_weight is 51 columns, the IDE block starts at column 51) and
+   * refrac_freq 2 (x_refrac = PE2(p) ++ PE2(v), 30 columns).  Supported pairs: (6, 6) and (8, 2). */
+  int pos_freq; int refrac_freq;
 } nunerf_shade_encode_t;
 int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* stream);
 /* IDE(x, kinv) of M unit directions at one constant roughness -> planes (per-ray specular probe, ZT:780) */
@@ -298,6 +303,8 @@ typedef struct {
   int ld_dz; int lo_dz;
   float* d_rough_raw; float* d_nov;       /* fp32 [M] */
   const float* d_occ_prob;                /* optional [M]: gradient w.r.t. the occ_prob output (occlusion loss) */
+  /* clamp of the refraction-light head when it differs from exp_max (AppShadingNetwork_SpecInner: -0.2, field.py:1373) */
+  float exp_max_refrac; int use_exp_max_refrac;
 } nunerf_shade_mix_t;
 int nunerf_shade_mix_fwd(const nunerf_shade_mix_t* p, void* stream);
 int nunerf_shade_mix_bwd(const nunerf_shade_mix_t* p, void* stream);

@@ -61,7 +61,7 @@ class ShadeEncodeT(C.Structure):
                 ("x_weight", vp), ("ld_weight", ci), ("lo_weight", ci), ("x_refrac", vp), ("ld_refrac", ci),
                 ("lo_refrac", ci), ("nov", vp), ("d_x_outer", vp), ("ld_dxo", ci), ("d_x_inner", vp), ("ld_dxi", ci),
                 ("d_nov", vp), ("d_grad", vp), ("d_rough_raw", vp), ("ld_drough", ci), ("refl", vp),
-                ("d_x_refrac", vp), ("ld_dxr", ci), ("d_pts", vp), ("d_dirs", vp)]
+                ("d_x_refrac", vp), ("ld_dxr", ci), ("d_pts", vp), ("d_dirs", vp), ("pos_freq", ci), ("refrac_freq", ci)]
 
 
 class ShadeMixT(C.Structure):
@@ -71,7 +71,7 @@ class ShadeMixT(C.Structure):
                 ("trans_out", vp), ("metallic_out", vp), ("occ_prob", vp), ("d_color", vp), ("d_trans_out", vp),
                 ("d_metallic_out", vp), ("dz_metallic", vp), ("dz_albedo", vp), ("dz_trans", vp), ("dz_outer", vp),
                 ("dz_inner", vp), ("dz_weight", vp), ("dz_refrac", vp), ("ld_dz", ci), ("lo_dz", ci),
-                ("d_rough_raw", vp), ("d_nov", vp), ("d_occ_prob", vp)]
+                ("d_rough_raw", vp), ("d_nov", vp), ("d_occ_prob", vp), ("exp_max_refrac", cf), ("use_exp_max_refrac", ci)]
 
 
 class WDesc(C.Structure):

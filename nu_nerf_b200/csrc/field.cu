@@ -436,6 +436,124 @@ __global__ void shade_encode_bwd_kernel(nunerf_shade_encode_t p) {
   p.d_rough_raw[m * p.ld_drough] += drough * rough * (1.0f - rough);
 }
 
+// ---- the same two kernels for other encoding frequencies (AppShadingNetwork_SpecInner, field.py:1320-1330: light_pos_freq
+// PF = 8, refrac_freq RF = 2).  Kept apart from the (6, 6) kernels above, which are on the measured stage-1 path: these run
+// on the inner field of the non-zero-thickness stage 2 only.  Row layouts: x_inner = [PE_PF(p) | IDE | 0],
+// x_weight = [PE_PF(p) | PE6(r) | 0], x_refrac = [PE_RF(p) | PE_RF(v) | 0], all 128 columns.
+template <int PF, int RF>
+__global__ void __launch_bounds__(128) shade_encode_fwd_var_kernel(nunerf_shade_encode_t p) {
+  constexpr int PD = 3 + 6 * PF, RD = 3 + 6 * RF;
+  static_assert(PD <= 56 && PD + 72 <= 128 && PD + 39 <= 128 && 2 * RD <= 128, "row layout");
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = p.M;
+  if (idx >= 4 * M) return;
+  int job = (int)(idx / M);
+  long long m = idx % M;
+  float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
+  float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  float pt[3] = {p.pts[3 * m], p.pts[3 * m + 1], p.pts[3 * m + 2]};
+  pw::ShadeDirs s = pw::shade_dirs(g, rd);
+  const float zero[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float row[128];
+  if (job < 3) {
+    __nv_bfloat16* xo = (__nv_bfloat16*)p.x_outer;
+    __nv_bfloat16* xi = (__nv_bfloat16*)p.x_inner;
+    float* out = row + 56;     // IDE block at the top of the row buffer (16-byte aligned), moved down to column PD below
+    if (job == 0) pw::ide_fwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, out);
+    else pw::ide_fwd(c_ide, s.r[0], s.r[1], s.r[2], job == 1 ? pw::sigmoidf_(p.rough_raw[m * p.ld_rough]) : 0.0f, out);
+    const long long ro = ((long long)job * M + m) * p.ld_outer;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) store16(xo, ro + c * 16, p.lo_outer, out + c * 16);
+    store8(xo, ro + 64, p.lo_outer, out + 64);
+    store8(xo, ro + 72, p.lo_outer, zero);
+#pragma unroll
+    for (int c = 5; c < 8; ++c) store16(xo, ro + c * 16, p.lo_outer, zero);
+    if (job >= 1) {
+#pragma unroll
+      for (int j = PD; j < PD + 72; ++j) row[j] = row[j + 56 - PD];
+#pragma unroll
+      for (int j = PD + 72; j < 128; ++j) row[j] = 0.f;
+      fill_pe<3, PF>(row, pt);
+      const long long ri = ((long long)(job - 1) * M + m) * p.ld_inner;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) store16(xi, ri + c * 16, p.lo_inner, row + c * 16);
+    }
+  } else {
+    __nv_bfloat16* xw = (__nv_bfloat16*)p.x_weight;
+    __nv_bfloat16* xr = (__nv_bfloat16*)p.x_refrac;
+    fill_pe<3, PF>(row, pt);
+    fill_pe<3, 6>(row + PD, s.r);
+#pragma unroll
+    for (int j = PD + 39; j < 128; ++j) row[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) store16(xw, m * p.ld_weight + c * 16, p.lo_weight, row + c * 16);
+    fill_pe<3, RF>(row, pt);
+    fill_pe<3, RF>(row + RD, s.v);
+#pragma unroll
+    for (int j = 2 * RD; j < 128; ++j) row[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) store16(xr, m * p.ld_refrac + c * 16, p.lo_refrac, row + c * 16);
+    p.nov[m] = s.nov;
+    if (p.refl) { p.refl[3 * m] = s.r[0]; p.refl[3 * m + 1] = s.r[1]; p.refl[3 * m + 2] = s.r[2]; }
+  }
+}
+
+template <int PF, int RF>
+__global__ void shade_encode_bwd_var_kernel(nunerf_shade_encode_t p) {
+  constexpr int PD = 3 + 6 * PF, RD = 3 + 6 * RF;
+  long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = p.M;
+  if (m >= M) return;
+  float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
+  float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  pw::ShadeDirs s = pw::shade_dirs(g, rd);
+  float rough = pw::sigmoidf_(p.rough_raw[m * p.ld_rough]);
+  float dn[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f}, drough = 0.f;
+  float dout[72], gx, gy, gz, gk;
+  auto load = [&](long long orow, long long irow) {       // IDE gradient = outer-light row (+ inner-light row, columns PD..)
+    const float* src = p.d_x_outer + orow * p.ld_dxo;
+    for (int j = 0; j < 72; ++j) dout[j] = src[j];
+    if (irow >= 0) {
+      const float* src2 = p.d_x_inner + irow * p.ld_dxi + PD;
+      for (int j = 0; j < 72; ++j) dout[j] += src2[j];
+    }
+  };
+  load(m, -1);
+  pw::ide_bwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, dout, &gx, &gy, &gz, &gk);
+  dn[0] += gx; dn[1] += gy; dn[2] += gz;
+  load(M + m, m);
+  pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], rough, dout, &gx, &gy, &gz, &gk);
+  dr[0] += gx; dr[1] += gy; dr[2] += gz; drough += gk;
+  load(2 * M + m, M + m);
+  pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], 0.0f, dout, &gx, &gy, &gz, &gk);
+  dr[0] += gx; dr[1] += gy; dr[2] += gz;
+  float dg[3];
+  if (p.d_pts) {
+    const float* gi0 = p.d_x_inner + m * p.ld_dxi;
+    const float* gi1 = p.d_x_inner + (M + m) * p.ld_dxi;
+    const float* gr = p.d_x_refrac ? p.d_x_refrac + m * p.ld_dxr : nullptr;
+    float gpe[PD];
+    for (int j = 0; j < PD; ++j) gpe[j] = gi0[j] + gi1[j];
+    float dvd[3] = {0.f, 0.f, 0.f};
+    for (int c = 0; c < 3; ++c) {
+      float acc = pw::pe_bwd_coord(gpe, 3, PF, c, p.pts[3 * m + c]);
+      if (gr) {
+        acc += pw::pe_bwd_coord(gr, 3, RF, c, p.pts[3 * m + c]);
+        dvd[c] = pw::pe_bwd_coord(gr + RD, 3, RF, c, s.v[c]);
+      }
+      p.d_pts[3 * m + c] += acc;
+    }
+    const float vn = fmaxf(sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]), 1e-12f);
+    float drd[3];
+    pw::shade_dirs_bwd(s, dr, dn, p.d_nov[m], dg, dvd, vn, drd);
+    p.d_dirs[3 * m] += drd[0]; p.d_dirs[3 * m + 1] += drd[1]; p.d_dirs[3 * m + 2] += drd[2];
+  } else {
+    pw::shade_dirs_bwd(s, dr, dn, p.d_nov[m], dg);
+  }
+  p.d_grad[3 * m] += dg[0]; p.d_grad[3 * m + 1] += dg[1]; p.d_grad[3 * m + 2] += dg[2];
+  p.d_rough_raw[m * p.ld_drough] += drough * rough * (1.0f - rough);
+}
+
 // IDE of M unit directions at a constant roughness (the per-ray specular probe, ZT:780); writes 128 columns
 // (72 real + zero padding) starting at the 8-aligned column `col`.
 __global__ void __launch_bounds__(128)
@@ -477,7 +595,7 @@ __global__ void shade_mix_fwd_kernel(nunerf_shade_mix_t p) {
   if (m >= p.M) return;
   pw::ShadeMixIn in;
   load_mix(p, m, &in);
-  pw::ShadeMixOut o = pw::shade_mix_fwd(in, p.lut, p.exp_max);
+  pw::ShadeMixOut o = pw::shade_mix_fwd(in, p.lut, p.exp_max, p.use_exp_max_refrac ? p.exp_max_refrac : p.exp_max);
   p.color[3 * m] = o.color[0]; p.color[3 * m + 1] = o.color[1]; p.color[3 * m + 2] = o.color[2];
   p.trans_out[m] = o.trans; p.metallic_out[m] = o.metallic; p.occ_prob[m] = o.occ_prob;
 }
@@ -491,7 +609,8 @@ __global__ void shade_mix_bwd_kernel(nunerf_shade_mix_t p) {
   pw::ShadeMixIn in, d;
   load_mix(p, m, &in);
   float dc[3] = {p.d_color[3 * m], p.d_color[3 * m + 1], p.d_color[3 * m + 2]};
-  pw::shade_mix_bwd(in, p.lut, p.exp_max, dc, p.d_trans_out ? p.d_trans_out[m] : 0.f,
+  pw::shade_mix_bwd(in, p.lut, p.exp_max, p.use_exp_max_refrac ? p.exp_max_refrac : p.exp_max, dc,
+                    p.d_trans_out ? p.d_trans_out[m] : 0.f,
                     p.d_metallic_out ? p.d_metallic_out[m] : 0.f, &d);
   if (p.d_occ_prob) d.occ += 0.5f * p.d_occ_prob[m];   // occ_prob = raw * 0.5 + 0.5 (field.py:659), unclipped output
   const int ld = p.ld_dz, lo = p.lo_dz;
@@ -845,7 +964,10 @@ extern "C" int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* str
                    p->lo_refrac) & 7) == 0 && p->ld_outer >= 128 && p->ld_inner >= 128 && p->ld_weight >= 128 &&
                      p->ld_refrac >= 128,
                  "shade_encode_fwd: operand rows must be >= 128 columns with 8-column aligned pitches");
-  shade_encode_fwd_kernel<<<cdiv(4LL * p->M, 128), 128, 0, ST(stream)>>>(*p);
+  const int pf = p->pos_freq ? p->pos_freq : 6, rf = p->refrac_freq ? p->refrac_freq : 6;
+  if (pf == 6 && rf == 6) shade_encode_fwd_kernel<<<cdiv(4LL * p->M, 128), 128, 0, ST(stream)>>>(*p);
+  else if (pf == 8 && rf == 2) shade_encode_fwd_var_kernel<8, 2><<<cdiv(4LL * p->M, 128), 128, 0, ST(stream)>>>(*p);
+  else return fail("%s", "shade_encode_fwd: supported (pos_freq, refrac_freq) are (6, 6) and (8, 2)");
   NUNERF_CHECK_LAUNCH("shade_encode_fwd_kernel");
   return 0;
 }
@@ -855,7 +977,10 @@ extern "C" int nunerf_shade_encode_bwd(const nunerf_shade_encode_t* p, void* str
                  "shade_encode_bwd: bad arguments");
   NUNERF_REQUIRE(!p->d_pts || (p->pts && p->d_dirs), "shade_encode_bwd: d_pts needs pts and d_dirs");
   if (int r = ensure_ide()) return r;
-  shade_encode_bwd_kernel<<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
+  const int pf = p->pos_freq ? p->pos_freq : 6, rf = p->refrac_freq ? p->refrac_freq : 6;
+  if (pf == 6 && rf == 6) shade_encode_bwd_kernel<<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
+  else if (pf == 8 && rf == 2) shade_encode_bwd_var_kernel<8, 2><<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
+  else return fail("%s", "shade_encode_bwd: supported (pos_freq, refrac_freq) are (6, 6) and (8, 2)");
   NUNERF_CHECK_LAUNCH("shade_encode_bwd_kernel");
   return 0;
 }

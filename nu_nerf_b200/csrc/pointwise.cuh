@@ -269,7 +269,9 @@ struct ShadeMixOut { float color[3], trans, metallic, occ_prob; };
 
 PW_HD float exp_act(float x, float mx) { return expf(fminf(x, mx)); }
 
-PW_HD ShadeMixOut shade_mix_fwd(const ShadeMixIn& in, const float* lut, float exp_max) {
+// exp_max_r: clamp of the refraction-light head (AppShadingNetwork: = exp_max, field.py:602; AppShadingNetwork_SpecInner: -0.2,
+// field.py:1373)
+PW_HD ShadeMixOut shade_mix_fwd(const ShadeMixIn& in, const float* lut, float exp_max, float exp_max_r) {
   ShadeMixOut o;
   float met = sigmoidf_(in.metallic), rough = sigmoidf_(in.rough), T = sigmoidf_(in.trans);
   float occ = in.occ * 0.5f + 0.5f, oc = clamp01(occ);
@@ -281,7 +283,7 @@ PW_HD ShadeMixOut shade_mix_fwd(const ShadeMixIn& in, const float* lut, float ex
     float alb = sigmoidf_(in.albedo[c]);
     float dl = exp_act(in.diffuse_l[c], exp_max), dr = exp_act(in.direct[c], exp_max),
           d0 = exp_act(in.direct0[c], exp_max), il = exp_act(in.indirect[c], exp_max),
-          i0 = exp_act(in.indirect0[c], exp_max), rf = exp_act(in.refrac[c], exp_max);
+          i0 = exp_act(in.indirect0[c], exp_max), rf = exp_act(in.refrac[c], exp_max_r);
     float diffuse = (1.0f - met) * alb * dl;
     float sa = 0.04f * (1.0f - met) + met * alb;
     float light = il * oc + dr * (1.0f - oc), light0 = i0 * oc + d0 * (1.0f - oc);
@@ -294,8 +296,8 @@ PW_HD ShadeMixOut shade_mix_fwd(const ShadeMixIn& in, const float* lut, float ex
 }
 
 // d_in receives gradients w.r.t. every raw head and nov
-PW_HD void shade_mix_bwd(const ShadeMixIn& in, const float* lut, float exp_max, const float* d_color, float d_trans_out,
-                         float d_met_out, ShadeMixIn* d_in) {
+PW_HD void shade_mix_bwd(const ShadeMixIn& in, const float* lut, float exp_max, float exp_max_r, const float* d_color,
+                         float d_trans_out, float d_met_out, ShadeMixIn* d_in) {
   float met = sigmoidf_(in.metallic), rough = sigmoidf_(in.rough), T = sigmoidf_(in.trans);
   float occ = in.occ * 0.5f + 0.5f, oc = clamp01(occ);
   float t1 = 1.0f - in.nov, t = clamp01(t1);
@@ -308,7 +310,7 @@ PW_HD void shade_mix_bwd(const ShadeMixIn& in, const float* lut, float exp_max, 
     float alb = sigmoidf_(in.albedo[c]);
     float dl = exp_act(in.diffuse_l[c], exp_max), dr = exp_act(in.direct[c], exp_max),
           d0 = exp_act(in.direct0[c], exp_max), il = exp_act(in.indirect[c], exp_max),
-          i0 = exp_act(in.indirect0[c], exp_max), rf = exp_act(in.refrac[c], exp_max);
+          i0 = exp_act(in.indirect0[c], exp_max), rf = exp_act(in.refrac[c], exp_max_r);
     float diffuse = (1.0f - met) * alb * dl;
     float sa = 0.04f * (1.0f - met) + met * alb;
     float light = il * oc + dr * (1.0f - oc), light0 = i0 * oc + d0 * (1.0f - oc);
@@ -343,7 +345,7 @@ PW_HD void shade_mix_bwd(const ShadeMixIn& in, const float* lut, float exp_max, 
     d_in->direct0[c] = in.direct0[c] <= exp_max ? d_d0 * d0 : 0.f;
     d_in->indirect[c] = in.indirect[c] <= exp_max ? d_il * il : 0.f;
     d_in->indirect0[c] = in.indirect0[c] <= exp_max ? d_i0 * i0 : 0.f;
-    d_in->refrac[c] = in.refrac[c] <= exp_max ? d_rf * rf : 0.f;
+    d_in->refrac[c] = in.refrac[c] <= exp_max_r ? d_rf * rf : 0.f;
   }
   d_met += d_met_out;
   d_T += d_trans_out;

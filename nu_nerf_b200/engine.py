@@ -588,6 +588,13 @@ class Stage1Weights:
             self.pred[name] = PredW(self.bank, getattr(net.color_network, name), need_dx0=need_dx0)
         self.bank.finalize()
         self._variance = net.deviation_network.variance
+        # encoding frequencies / refraction-light clamp of the shading network (AppShadingNetwork: 6 / 6 / light_exp_max;
+        # AppShadingNetwork_SpecInner, field.py:1320-1330, :1373: 8 / 2 / -0.2)
+        ccfg = getattr(net.color_network, "cfg", {})
+        self.pos_freq, self.refrac_freq = int(ccfg.get("light_pos_freq", 6)), int(ccfg.get("refrac_freq", 6))
+        if (self.pos_freq, self.refrac_freq) not in ((6, 6), (8, 2)):
+            raise NotImplementedError("shading encode kernels: (light_pos_freq, refrac_freq) must be (6, 6) or (8, 2)")
+        self.exp_max_refrac = float(getattr(net.color_network.refrac_light, "exp_max", ccfg.get("light_exp_max", 3.0)))
         self.lut = net.color_network.FG_LUT.detach().float().contiguous()
         self.inv_s = torch.zeros(1, device=device)
 
@@ -690,6 +697,7 @@ def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
     se.x_weight, se.ld_weight, se.lo_weight = t.xw.ptr, t.xw.ld, t.xw.lo
     se.x_refrac, se.ld_refrac, se.lo_refrac = t.xr.ptr, t.xr.ld, t.xr.lo
     se.nov = t.nov.data_ptr()
+    se.pos_freq, se.refrac_freq = w.pos_freq, w.refrac_freq
     t.refl = _f(M, 3, dev=dev)
     se.refl = t.refl.data_ptr()
     call("nunerf_shade_encode_fwd", C.byref(se))
@@ -700,7 +708,8 @@ def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
         t.lr_ = PredTape()
         t.lr_.head = torch.full((M, 16), float("-inf"), device=dev)
     else:
-        t.lr_ = pred_forward(w.pred["refrac_light"], t.xr, M, 128, planes)
+        # (first-layer K padded to 64: 128 columns for the PE-6 inputs, 64 for the PE-2 ones of AppShadingNetwork_SpecInner)
+        t.lr_ = pred_forward(w.pred["refrac_light"], t.xr, M, w.pred["refrac_light"].L[0].Kp, planes)
     t.c_in, t.trans, t.metallic, t.occ = _f(M, 3, dev=dev), _f(M, dev=dev), _f(M, dev=dev), _f(M, dev=dev)
     call("nunerf_shade_mix_fwd", C.byref(_mix_params(w, t)))
 
@@ -765,6 +774,7 @@ def _mix_params(w, t, d_color=None, d_trans=None, d_met=None, dz=None, d_rough=N
     M = t.n_in
     mp = _lib.ShadeMixT()
     mp.M, mp.exp_max = M, t.exp_max
+    mp.exp_max_refrac, mp.use_exp_max_refrac = w.exp_max_refrac, int(w.exp_max_refrac != t.exp_max)
     mp.metallic, mp.rough = t.mat["metallic_predictor"].head.data_ptr(), t.mat["roughness_predictor"].head.data_ptr()
     mp.albedo, mp.trans, mp.ld_mat = t.mat["albedo_predictor"].head.data_ptr(), \
         t.mat["transmisstion_weight"].head.data_ptr(), 16
@@ -837,8 +847,9 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     dxr = None
     if not surface:
         if want_geo:
-            dxr = _f(M, 128, dev=dev)
-            pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes, dx_f32=dxr, dx_n=128)
+            kr = w.pred["refrac_light"].L[0].Kp
+            dxr = _f(M, kr, dev=dev)
+            pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes, dx_f32=dxr, dx_n=kr)
         else:
             pred_backward(w.pred["refrac_light"], t.lr_, dz["refrac"], planes)
     # ---- sdf -> alpha
@@ -864,8 +875,9 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
     se.d_x_outer, se.ld_dxo, se.d_x_inner, se.ld_dxi = dxo.data_ptr(), 128, dxi.data_ptr(), 128
     se.d_nov, se.d_grad, se.d_rough_raw, se.ld_drough = d_nov.data_ptr(), d_grad.data_ptr(), d_rough.data_ptr(), 1
+    se.pos_freq, se.refrac_freq = w.pos_freq, w.refrac_freq
     if want_geo:
-        se.d_x_refrac, se.ld_dxr = ptr(dxr), 128
+        se.d_x_refrac, se.ld_dxr = ptr(dxr), (dxr.stride(0) if dxr is not None else 0)
         se.d_pts, se.d_dirs = d_pts.data_ptr(), d_dirs.data_ptr()
     call("nunerf_shade_encode_bwd", C.byref(se))
     if surface:

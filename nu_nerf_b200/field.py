@@ -141,6 +141,7 @@ def make_predictor(feats_dim, output_dim, activation="sigmoid", exp_max=0.0):
 
 class AppShadingNetwork(nn.Module):
     """field.py:557-616 (parameters only)."""
+    refrac_exp_max = None          # the refraction-light head shares light_exp_max (field.py:602)
     default_cfg = {
         "human_light": False, "sphere_direction": False, "light_pos_freq": 6, "inner_init": -0.95,
         "roughness_init": 0.0, "metallic_init": 0.0, "light_exp_max": 3.0, "refrac_freq": 6,
@@ -172,8 +173,20 @@ class AppShadingNetwork(nn.Module):
         nn.init.constant_(self.inner_weight[-2].bias, self.cfg["inner_init"])
         self.transmisstion_weight = make_predictor(feats_dim + 3, 1)
         self.iors = make_predictor(feats_dim + 3, 1)
-        self.refrac_light = make_predictor(rf + rf, 3, activation="exp", exp_max=exp_max)
+        self.refrac_light = make_predictor(rf + rf, 3, activation="exp",
+                                           exp_max=exp_max if self.refrac_exp_max is None else self.refrac_exp_max)
         nn.init.constant_(self.refrac_light[-2].bias, np.log(0.5))
+
+
+class AppShadingNetwork_SpecInner(AppShadingNetwork):
+    """field.py:1320-1379 -- the inner-field shader of the non-zero-thickness stage 2 (network/renderer.py:1017): the same
+    predictors in the same construction order as AppShadingNetwork with light_pos_freq 8, refrac_freq 2, light_exp_max 5 and
+    the refraction-light head clamped at -0.2 (field.py:1373)."""
+    default_cfg = {
+        "human_light": False, "sphere_direction": False, "light_pos_freq": 8, "inner_init": -0.95,
+        "roughness_init": 0.0, "metallic_init": 0.0, "light_exp_max": 5.0, "refrac_freq": 2,
+    }
+    refrac_exp_max = -0.2
 
 
 class InfOutNetwork(nn.Module):

@@ -1,0 +1,322 @@
+"""Drop-in boundary for the reference's network/renderer.py ("NZ"): the NON-zero-thickness stage-2 renderer (SURVEY 8f
+row 1), i.e. the refraction path through a thin glass shell of learned thickness around the outer mesh.
+
+    - from network.renderer import name2renderer
+    + from nu_nerf_b200.renderer import name2renderer          # run_training.py:17-20 picks this module when
+                                                               # cfg['zero_thickness'] is False
+
+What differs from the zero-thickness renderer (nu_nerf_b200/renderer_stage2.py) and is built here:
+  * ray_trace (NZ:1610-2148): per bounce the curvature-radius shell offset with two refractions (nu_nerf_b200/shell.py,
+    pinned bounce by bounce to the reference), the interpolated Gaussian curvature of the hit (Scene.Dintersect()['g_k'],
+    tracer.discrete_gaussian_curvature -- the stated replacement of the PyMesh attribute, parity against PyMesh unpinned),
+    IoR = 1 / (IORs_pred + 0.6), ThicknessNetwork * 0.01, retro-active un-convergence of rays that miss the mesh from the
+    inside (NZ:1662-1672), 64 / 128 (64 + 2 x 32 SDF-guided) / 64 samples per segment, 64 inverse-depth samples for rays
+    that leave the scene (NZ:2140-2143).  Kernels: BVH closest hit + re-intersection, IoR / thickness MLPs, inner-SDF
+    queries + up-sampling rounds, path points.  The closed-form bounce itself runs as fused-by-autograd torch expressions on
+    the [M, .] tensors of the hit rays (M <= rays per bounce; ~1 % of a step) so that the loss reaches IORs_pred AND
+    thickness_pred through it.
+  * the inner field's shader is AppShadingNetwork_SpecInner (field.py:1320: PE-8 positions, PE-2 refraction inputs,
+    refraction light clamped at exp(-0.2)) -- shade_encode_*_var_kernel<8, 2>, exp_max_refrac of the mixing kernels.
+  * render_core (NZ:2155-2353): surface shading flagged `inner` for every segment but the first (NZ:2244), `loss_occ` key.
+  * render(rays_o, rays_d, mask, near, far, ...) (NZ:1482) and the masked losses of train_step / test_step (NZ:1297-1299,
+    :1364).
+Not built (raises NotImplementedError): the stage-1 twin of this module (NeROShapeRenderer with loss_normal / loss_mask,
+NZ:478, :784-793 -- 'shape' maps to the zero-thickness class, whose modules and checkpoints are identical), the
+sphere_direction / human_light shader variants, and the inner-field occlusion loss (NZ:2222-2230; the reference's real-data
+configs of this renderer all set apply_occ_loss: false).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .field import (SDFNetwork, SingleVarianceNetwork, NeRFNetwork, AppShadingNetwork_SpecInner, AppShadingNetwork_S2,
+                    IoRNetwork, ThicknessNetwork)
+from .renderer_stage2 import Stage2Renderer as _ZTStage2Renderer, _HitFn, _engine
+from .renderer_zerothick import NeROShapeRenderer, load_cfg
+from .shell import shell_bounce, signed_normal, outside_depths
+
+
+class Stage2Renderer(_ZTStage2Renderer):
+    """network/renderer.py:907-2378."""
+    default_cfg = {**_ZTStage2Renderer.default_cfg, "downsample_ratio": 1.0, "get_mask": False}
+
+    def __init__(self, cfg, training=True):
+        nn.Module.__init__(self)
+        from .tracer import Scene
+        self.cfg = {**self.default_cfg, **cfg}
+        self.is_nerf = self.cfg["is_nerf"]
+        self.get_mask = self.cfg["get_mask"]
+        if (self.cfg["sdf_n_layers"], self.cfg["sdf_freq"], self.cfg["sdf_d_out"]) != (8, 6, 257) or \
+                not self.cfg["clip_sample_variance"]:
+            raise NotImplementedError("the B200 engine is built for the 8x256 / PE-6 / 257-output SDF network")
+        # construction order = the reference's (NZ:958-1019): same seed => bit-identical initial parameters
+        self.nerf_network = NeRFNetwork(D=8, d_in=4, d_in_view=3, W=256, multires=10, multires_view=4, skips=(4,))
+        self.IORs = nn.Parameter(torch.zeros(10))
+        cfg1 = cfg["stage1_cfg_dir"]
+        cfg1 = dict(cfg1) if isinstance(cfg1, dict) else load_cfg(cfg1)
+        cfg1.setdefault("precision", self.cfg["precision"])
+        self.stage1_network = NeROShapeRenderer(cfg1, training=False)
+        ckpt = cfg["stage1_ckpt_dir"]
+        ckpt = ckpt if isinstance(ckpt, dict) else torch.load(ckpt, map_location="cpu")
+        self.stage1_network.load_state_dict(ckpt["network_state_dict"], strict=False)
+        self.infinity_far_bkgr = self.stage1_network.infinity_far_bkgr        # NZ:992 (registered a second time)
+        self._mesh = cfg["stage1_mesh_dir"]
+        self.scene = None
+        self._scene_cls = Scene
+        self.IORs_pred = IoRNetwork()
+        self.IoRint_pred = IoRNetwork()
+        self.thickness_pred = ThicknessNetwork()
+        self.color_network = AppShadingNetwork_S2(self.cfg["shader_config"], self.stage1_network)
+        self.sdf_network_inner = SDFNetwork(d_out=257, d_in=3, d_hidden=256, n_layers=8, skip_in=(4,), multires=6,
+                                            bias=self.cfg["sdf_bias"], scale=1.0,
+                                            geometric_init=self.cfg["geometry_init"])
+        self.deviation_network_inner = SingleVarianceNetwork(init_val=self.cfg["inv_s_init"],
+                                                             activation=self.cfg["std_act"])
+        self.color_network_inner = AppShadingNetwork_SpecInner(self.cfg["shader_config"])
+        self.sdf_network_inner._query = self._sdf_inner_query
+        self.ray_source = None
+
+    # ------------------------------------------------------------------ engine operands
+    def _prepare(self):
+        prepared = super()._prepare()
+        eng = _engine()
+        key = (self._planes(),) + tuple(p.data_ptr() for p in self.thickness_pred.parameters())
+        if getattr(self, "_w_thick", None) is None or self._w_thick_key != key:
+            dev = self.deviation_network_inner.variance.device
+            self._w_thick, self._w_thick_key = eng.IorWeights(self.thickness_pred, self._planes(), dev), key
+        self._w_thick.refresh()
+        return prepared
+
+    @staticmethod
+    def _hit_from_inside(i):
+        return i != 0                                            # NZ:2244
+
+    def _train_ior(self):
+        return torch.is_grad_enabled() and not self.cfg.get("frozen_ior", False) and \
+            any(p.requires_grad for m in (self.IORs_pred, self.thickness_pred) for p in m.parameters())
+
+    @staticmethod
+    def _sigmoid_mlp(net, x):
+        """IoRNetwork / ThicknessNetwork.forward (field.py:1046-1081) as a differentiable fp32 torch expression on the
+        [M,3] hit points (M <= rays per bounce)."""
+        pe = [x]
+        for k in range(6):
+            pe += [torch.sin(x * (2.0 ** k)), torch.cos(x * (2.0 ** k))]
+        h = torch.cat(pe, -1)
+        seq = net.module0
+        for i, act in ((0, True), (2, True), (4, False), (5, False)):
+            h = F.linear(h, seq[i].effective_weight(), seq[i].bias)
+            h = F.relu(h) if act else h
+        return torch.sigmoid(h)
+
+    # ------------------------------------------------------------------ NZ:1610-2148
+    def ray_trace(self, rays_o, rays_d, mask=None, prepared=None, trace=None):
+        """-> (pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask) as the reference's.
+        Under autograd with trainable IoR / thickness networks the returned geometry carries their graph (hit points
+        through hit_interp_bwd_kernel, the two MLPs as fp32 torch expressions, the bounce through shell_bounce); every
+        discrete decision (hit triangle, pass masks, sample parameters) is taken without one, as in the reference.
+        trace (dict, tests): receives the hit records per bounce; a "z_1" entry replaces the up-sampled parameters of
+        segment 1 (the CDF inversion amplifies MLP rounding, SURVEY 7.3: parity of what follows is checked on equal z)."""
+        eng = _engine()
+        w1, wi, wior = prepared if prepared is not None else self._prepare()
+        wth = self._w_thick
+        grad = self._train_ior()
+        dev = rays_o.device
+        o, d = rays_o.float().contiguous(), rays_d.float().contiguous()
+        next_start, next_dir = o, d
+        starts, directions = [o], [d]
+        intersections, converges, infinity_bkgr, ior_ratios, gradient_mesh, tirs = [], [], [], [], [], []
+        hit_idxs, conv_idxs = [], []
+        inside = False
+        for i in range(3):
+            with torch.no_grad():
+                info, hit = self.scene.Dintersect(next_start.detach().contiguous(), next_dir.detach().contiguous())
+            if trace is not None:
+                trace[f"trace_hit_{i}"], trace[f"trace_tri_{i}"] = hit.float(), info["faces_ind"]
+            hit_idx = hit.nonzero().squeeze(1)
+            if i == 1 and hit_idx.numel() < next_start.shape[0]:
+                # rays that entered the object and find no way out (open / leaking mesh) are taken back: their first hit
+                # no longer counts as converged and they leave every per-ray list of segment 1 (NZ:1662-1672).  The
+                # reference forgets ior_ratios[0] there and fails later in render_core; it is filtered here as well.
+                keep = hit_idx
+                conv0 = torch.zeros_like(converges[0])
+                conv0[conv_idxs[0][keep]] = True
+                converges[0] = conv0
+                conv_idxs[0] = conv_idxs[0][keep]
+                next_start, next_dir = next_start[keep], next_dir[keep]
+                gradient_mesh[0], ior_ratios[0] = gradient_mesh[0][keep], ior_ratios[0][keep]
+                starts[1], directions[1] = next_start, next_dir
+                info = {k_: v[keep] for k_, v in info.items()}
+                hit = hit[keep]
+                hit_idx = torch.arange(keep.numel(), device=dev)
+            N = next_start.shape[0]
+            converged = hit.reshape(-1, 1)
+            infinity_bkgr.append(~converged)
+            x_c = info["x"].index_select(0, hit_idx).contiguous()
+            n_c = signed_normal(info["n"].index_select(0, hit_idx), inside).contiguous()
+            g_k = info["g_k"].index_select(0, hit_idx).reshape(-1, 1)
+            d_c = next_dir.index_select(0, hit_idx).contiguous()
+            M = hit_idx.numel()
+            if M > 0 and grad:
+                tri = info["faces_ind"].index_select(0, hit_idx).to(torch.int32).contiguous()
+                x_c, n_c = _HitFn.apply(next_start.index_select(0, hit_idx), d_c, (self.scene, tri, inside, x_c, n_c))
+                ior_sig = self._sigmoid_mlp(self.IORs_pred, x_c)
+                th_sig = self._sigmoid_mlp(self.thickness_pred, x_c)
+            elif M > 0:
+                with torch.no_grad():
+                    ior_sig = eng.ior_forward(wior, x_c).reshape(-1, 1)
+                    th_sig = eng.ior_forward(wth, x_c).reshape(-1, 1)
+            else:
+                ior_sig = th_sig = torch.zeros(0, 1, device=dev)
+            b = shell_bounce(x_c, n_c, d_c, g_k, ior_sig, th_sig, inside)
+            ok_idx = b["ok_idx"]
+            converged_out = torch.zeros(N, 1, dtype=torch.bool, device=dev)
+            converged_out[hit_idx[ok_idx]] = True
+            tir = torch.ones(N, 1, dtype=torch.bool, device=dev)
+            tir[hit_idx] = b["tir"].reshape(-1, 1)
+            tirs.append(tir)
+            next_dir, next_start = b["dir"], b["start"]
+            directions.append(next_dir)
+            starts.append(next_start)
+            converges.append(converged_out)
+            intersections.append(b["x_mod"])
+            hit_idxs.append(hit_idx)
+            conv_idxs.append(hit_idx[ok_idx])
+            if ok_idx.numel() == 0:
+                break
+            gradient_mesh.append(b["normal"])
+            ior_ratios.append(b["ratio"])
+            inside = not inside
+        for i in range(len(tirs) - 1, 0, -1):                                # NZ:2063-2064
+            m = conv_idxs[i - 1]
+            tirs[i - 1][m] = tirs[i - 1][m] & tirs[i]
+        # ---- per-segment sample generation (NZ:2067-2146)
+        pathes = []
+        for k in range(len(converges)):
+            start, dk = starts[k], directions[k]
+            h_idx = hit_idxs[k]
+            n_hit, n_seg = h_idx.numel(), start.shape[0]
+            n_pts = 64 if k != 1 else 128
+            end = start + dk * 4.5
+            if n_hit > 0:
+                end = end.index_copy(0, h_idx, intersections[k])
+            delta = end - start
+            Z = torch.linspace(0, 1, n_pts, device=dev).unsqueeze(0).repeat(n_seg, 1)
+            if k == 1 and n_hit > 0:
+                # inside the outer mesh: 64 uniform samples to the hit + 2 rounds of 32 SDF-guided ones on the inner field,
+                # with the reference's mixed parametrisation (unit parameter z, SDF queried at start + dir * z; NZ:2098-2117)
+                with torch.no_grad():
+                    s_h = start.detach().index_select(0, h_idx).contiguous()
+                    e_h = end.detach().index_select(0, h_idx).contiguous()
+                    d_h = dk.detach().index_select(0, h_idx).contiguous()
+                    Rh = s_h.shape[0]
+                    z = torch.linspace(0, 1, 64, device=dev).unsqueeze(0).expand(Rh, 64).contiguous()
+                    p64 = eng.segment_points(s_h, e_h - s_h, z)
+                    sdf = eng.sdf_infer(wi.sdf, p64.reshape(-1, 3), wi.planes).reshape(Rh, 64).contiguous()
+                    z = eng.upsample_rounds(wi, s_h, d_h, z, sdf, n_new=32, rounds=2)
+                    if trace is not None and "z_1" in trace:       # tests: the sample parameters of a recorded trace
+                        z = trace["z_1"]
+                    Z[h_idx] = z
+            if n_hit < n_seg:
+                if k == 1:
+                    raise RuntimeError("non-zero-thickness trace: a ray of segment 1 has no exit hit after the filter")
+                # rays that leave the scene: 64 inverse-depth samples along the direction (NZ:2140-2143)
+                m_idx = infinity_bkgr[k].flatten().nonzero().squeeze(1)
+                Z[m_idx] = outside_depths(dev)
+                delta = delta.index_copy(0, m_idx, dk.index_select(0, m_idx))
+            if start.requires_grad or delta.requires_grad:
+                pts = start[:, None, :] + delta[:, None, :] * Z[:, :, None]
+            else:
+                pts = eng.segment_points(start.contiguous(), delta.contiguous(), Z.contiguous())
+            pathes.append(pts)
+        return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
+
+    # ------------------------------------------------------------------ NZ:2155-2353
+    def render_core(self, rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
+                    human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True, is_nerf=False, prepared=None):
+        if self.cfg["apply_occ_loss"] and is_train and step is not None and step >= self.cfg["occ_loss_step"]:
+            raise NotImplementedError("non-zero-thickness stage 2: the inner-field occlusion loss (NZ:2222-2230) is not "
+                                      "built; set apply_occ_loss: false (as the reference's configs of this renderer do)")
+        out = super().render_core(rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
+                                  human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train,
+                                  is_nerf=is_nerf, prepared=prepared)
+        out["loss_occ"] = torch.zeros(1, device=rays_o.device)            # NZ:1584-1585 before occ_loss_step / disabled
+        return out
+
+    # ------------------------------------------------------------------ NZ:1482-1506
+    def render(self, rays_o, rays_d, mask=None, near=None, far=None, human_poses=None, perturb_overwrite=-1,
+               cos_anneal_ratio=0.0, is_train=True, step=None, is_nerf=False):
+        prepared = self._prepare()
+        pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = \
+            self.ray_trace(rays_o, rays_d, mask, prepared=prepared)
+        ret = self.render_core(rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
+                               human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train,
+                               is_nerf=is_nerf, prepared=prepared)
+        ret["tir_mask"] = tir_mask
+        return ret
+
+    @torch.no_grad()
+    def nvs(self, pose, K, h, w, chunk=4096):
+        from . import feeder
+        dev = self.deviation_network_inner.variance.device
+        as_t = lambda a: (torch.from_numpy(np.asarray(a, dtype=np.float32)) if not torch.is_tensor(a) else a.float()).to(dev)
+        K_, pose_ = as_t(K).unsqueeze(0), as_t(pose).unsqueeze(0)
+        batch, rn, _, _ = feeder.construct_ray_batch(torch.zeros(1, 3, h, w, device=dev), K_)
+        colors = []
+        for ri in range(0, rn, chunk):
+            rays_o, rays_d = feeder.world_rays(batch["dirs"][ri:ri + chunk], batch["idxs"][ri:ri + chunk], pose_)
+            out = self.render(rays_o.contiguous(), rays_d.contiguous(), None, None, None, None, 0, 0, is_train=False,
+                              step=300000)
+            colors.append(out["ray_rgb"])
+        return torch.cat(colors, 0).reshape(h, w, 3).cpu().numpy()
+
+    def test_step(self, index, step):
+        """NZ:1264-1313: as the zero-thickness test_step with the image's foreground mask (src['mask'], optional: ones)
+        multiplied into ray_rgb / gt_rgb / loss_rgb (NZ:1297-1299)."""
+        if getattr(self, "eval_source", None) is None:
+            raise RuntimeError("no eval source attached: call set_eval_source(fn) (the image database is outside the hot path)")
+        src = self.eval_source(index)
+        rays_o, rays_d = src["rays_o"].float(), F.normalize(src["rays_d"].float(), dim=-1)
+        h, w = int(src["h"]), int(src["w"])
+        rn, trn = rays_o.shape[0], self.cfg["test_ray_num"]
+        outputs = {k: [] for k in self.TEST_KEYS}
+        with torch.no_grad():
+            for ri in range(0, rn, trn):
+                cur = self.render(rays_o[ri:ri + trn].contiguous(), rays_d[ri:ri + trn].contiguous(), None, None, None, None,
+                                  0, 0, is_train=False, step=step, is_nerf=self.is_nerf)
+                for k in self.TEST_KEYS:
+                    outputs[k].append(cur[k].detach())
+        outputs = {k: torch.cat(v, 0) for k, v in outputs.items()}
+        m = outputs["tir_mask"].float()
+        if "mask" in src:
+            m = m * torch.as_tensor(src["mask"], device=m.device).float().reshape(-1, 1)
+        outputs["loss_rgb"] = self.compute_rgb_loss(outputs["ray_rgb"] * m, src["rgbs"] * m)
+        outputs["gt_rgb"] = (src["rgbs"] * m).reshape(h, w, 3)
+        outputs["ray_rgb"] = (outputs["ray_rgb"] * m).reshape(h, w, 3)
+        for k in ("gt_depth", "gt_mask"):
+            if k in src:
+                outputs[k] = torch.as_tensor(src[k]).unsqueeze(-1)
+        self.zero_grad()
+        return outputs
+
+    def forward(self, data):
+        step = data["step"]
+        if "eval" in data:
+            return self.test_step(data["index"], step)
+        if self.ray_source is None:
+            raise NotImplementedError("dataset ingest is outside the hot path: attach a ray source and call render()")
+        batch = self.ray_source(step, self.cfg["train_ray_num"])
+        rays_d = F.normalize(batch["rays_d"], dim=-1)
+        mask = batch["masks"].reshape(-1, 1).float() if "masks" in batch else torch.ones_like(rays_d[:, :1])
+        out = self.render(batch["rays_o"], rays_d, mask, None, None, None, -1, self.get_anneal_val(step), is_train=True,
+                          step=step, is_nerf=self.is_nerf)
+        tm = out["tir_mask"].detach() * mask
+        out["loss_rgb"] = self.compute_rgb_loss(out["ray_rgb"] * tm, batch["rgbs"] * tm)         # NZ:1364
+        return out
+
+
+name2renderer = {
+    "shape": NeROShapeRenderer,         # modules / checkpoints identical to NZ:102-905; its loss_normal / loss_mask not built
+    "stage2": Stage2Renderer,
+}

@@ -250,7 +250,10 @@ class _InnerField:
 
     def __init__(self, r):
         self.sdf_network, self.deviation_network = r.sdf_network_inner, r.deviation_network_inner
-        self.color_network, self.outer_nerf = r.color_network_inner, r.outer_nerf
+        # the NeRF++ slot of the field is never evaluated for the inner field; the non-zero-thickness renderer has no
+        # stage-2 level outer_nerf module (network/renderer.py:975-1017), there the slot holds the stage-1 one
+        self.color_network = r.color_network_inner
+        self.outer_nerf = r.outer_nerf if hasattr(r, "outer_nerf") else r.stage1_network.outer_nerf
 
 
 class Stage2Renderer(nn.Module):
@@ -573,6 +576,11 @@ class Stage2Renderer(nn.Module):
             self._geo_debug = dict(pathes=new_pathes, directions=new_dirs, gradient_mesh=new_gm)
         return new_pathes, new_dirs, new_gm
 
+    @staticmethod
+    def _hit_from_inside(i):
+        """The `inner` flag of the surface shader at the hits of segment i (ZT:1915: i % 2 != 0)."""
+        return i % 2 != 0
+
     def _train_ior(self):
         return torch.is_grad_enabled() and not self.cfg.get("frozen_ior", False) and \
             any(p.requires_grad for p in self.IORs_pred.parameters())
@@ -649,7 +657,7 @@ class Stage2Renderer(nn.Module):
                 holder = {}
                 c_s, trans, nov = _SurfaceFn.apply((w1, exp_max1, holder), p_hit, keep(gradient_mesh[i]).contiguous(),
                                                    dirs_i.index_select(0, conv_idx), *p1)
-                if i % 2 != 0:
+                if self._hit_from_inside(i):
                     c_s = torch.zeros_like(c_s)                    # inside the object: field.py:969
                 tn = torch.clamp(1.0 - nov[:, None], 0.0, 1.0)
                 rw = torch.clamp(0.04 + 0.96 * tn * tn * tn * tn * tn, 0.0, 1.0)

@@ -23,9 +23,15 @@ def _unit(v):
     return v / (torch.linalg.norm(v, dim=-1, keepdim=True) + 0.0001)
 
 
-def shell_bounce(x, n_raw, d, g_k, ior_sig, thick_sig, inside):
+def signed_normal(n_raw, inside):
+    """NZ:1648, :1659: unit mesh normal, pointing against the ray that travels inside the object."""
+    n = F.normalize(n_raw, dim=-1)
+    return -n if inside else n
+
+
+def shell_bounce(x, normal, d, g_k, ior_sig, thick_sig, inside):
     """One bounce of NZ:1690-2009 on the M rays that hit the mesh.
-      x [M,3] hit point, n_raw [M,3] interpolated vertex normal (not signed), d [M,3] incoming direction,
+      x [M,3] hit point, normal [M,3] signed unit mesh normal (signed_normal), d [M,3] incoming direction,
       g_k [M,1] interpolated Gaussian curvature, ior_sig / thick_sig [M,1] sigmoid outputs of IORs_pred / thickness_pred,
       inside: the ray travels inside the object (leaving it).
     Returns a dict:
@@ -36,9 +42,6 @@ def shell_bounce(x, n_raw, d, g_k, ior_sig, thick_sig, inside):
       normal [K,3]         signed unit mesh normal (`gradient_mesh`)
       ratio [K,1]          the effective IoR ratio of the first refraction (`ior_ratios`)
       start, dir [K,3]     origin and direction of the next segment."""
-    normal = F.normalize(n_raw, dim=-1)
-    if inside:
-        normal = -normal
     cos_i = torch.sum(normal * -d, dim=-1, keepdim=True)
     sin2_i = 1 - (cos_i * cos_i)
     ior = 1 / (ior_sig * 1.0 + 0.6)                                       # NZ:1733-1734

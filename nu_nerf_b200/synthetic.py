@@ -1,6 +1,8 @@
 """Seeded synthetic inputs of SURVEY 8(d) for benchmarks and tools (no dataset, no network access): rays on a radius-3
 sphere looking at the origin with 0.3 jitter, the two uniform draws of sample_ray, random target colours.  Pure torch CPU
 generators, so every rank / run draws the same values (the test oracle keeps its own copy of these three functions)."""
+import math
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -50,7 +52,24 @@ def uv_sphere(radius=0.6, nu=48, nv=24):
     return np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int64)
 
 
-def make_stage2(precision="split", mesh=None):
+def torus(R=0.55, r=0.22, nu=40, nv=20):
+    """Closed torus around the z axis (both signs of Gaussian curvature; the non-zero-thickness test mesh)."""
+    verts, faces = [], []
+    for i in range(nu):
+        ph = 2.0 * math.pi * i / nu
+        for j in range(nv):
+            th = 2.0 * math.pi * j / nv
+            verts.append([(R + r * math.cos(th)) * math.cos(ph), (R + r * math.cos(th)) * math.sin(ph), r * math.sin(th)])
+    idx = lambda i, j: (i % nu) * nv + (j % nv)
+    for i in range(nu):
+        for j in range(nv):
+            a, b, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+            faces.append([a, b, c])
+            faces.append([a, c, d])
+    return np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int64)
+
+
+def make_stage2(precision="split", mesh=None, thick=False):
     """Stage2Renderer on the synthetic nested-sphere scene, built the way tests/golden/make_golden_stage2.py builds the
     reference's: stage-1 checkpoint
     from a seed-0 random-init NeROShapeRenderer, stage-2 modules from seed 5, in-memory UV-sphere outer mesh."""
@@ -66,4 +85,8 @@ def make_stage2(precision="split", mesh=None):
            "stage1_ckpt_dir": {"network_state_dict": net1.state_dict()}, "stage1_cfg_dir": cfg1,
            "stage1_mesh_dir": mesh if mesh is not None else uv_sphere()}
     torch.manual_seed(5)
+    if thick:                       # network/renderer.py: the non-zero-thickness renderer (glass shell of learned thickness)
+        from nu_nerf_b200.renderer import name2renderer as nz
+        cfg["zero_thickness"], cfg["get_mask"] = False, False
+        return nz["stage2"](cfg, training=False)
     return name2renderer["stage2"](cfg, training=False)

@@ -8,6 +8,8 @@ Run in the build container only:  python tests/golden/make_golden_nz.py
                            interpolated Gaussian curvature, IoR / thickness network outputs, incoming direction) and its
                            outputs (pass masks, next origin / direction, IoR ratios, mesh normals, TIR mask, every sampled
                            path point) -- plus the render_core outputs dict (NZ:2155-2353) in train and eval mode.
+  stage2nz_grads_R64.npz   sphere case with autograd on: trainer loss (mean charbonnier with the TIR mask + 0.02 * eikonal) and
+                           strided samples + norms of every parameter gradient, incl. IORs_pred and thickness_pred.
   stage2nz_torus_R96.npz   the same ray_trace record on a torus (both curvature signs, re-entering rays).
 
 Vertex Gaussian curvature: oracle/ref_harness.angle_defect_curvature (the stated replacement for the PyMesh attribute;
@@ -22,7 +24,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import ref_harness as rh  # noqa: E402
-from make_golden import fingerprint  # noqa: E402
+from make_golden import fingerprint, strided  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -95,6 +97,26 @@ def main():
             for kk, v in r.items():
                 res[f"{mode}_{kk}"] = v.detach().float().numpy()
     np.savez_compressed(os.path.join(OUT, "stage2nz_sphere_R64.npz"), **res)
+    # ---- gradients of the stage-2 trainer loss through ray_trace + render_core (autograd of the reference): the IoR AND
+    # the thickness network receive theirs through the shell geometry
+    gt = rh.synthetic_targets(64)
+    net.zero_grad()
+    pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = net.ray_trace(o, d, None)
+    r = net.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
+                        cos_anneal_ratio=0.2, step=10000, is_train=True, is_nerf=True)
+    tm = tir_mask.detach()
+    loss = net.compute_rgb_loss(r["ray_rgb"] * tm, gt * tm).mean() + (0.02 * r["gradient_error"]).mean()
+    loss.backward()
+    gres = {"gt": gt.numpy(), "loss": loss.detach().numpy(), "ray_rgb": r["ray_rgb"].detach().numpy()}
+    for name, p_ in net.named_parameters():
+        if p_.grad is None:
+            continue
+        vals, idx = strided(p_.grad)
+        gres["grad/" + name] = vals
+        gres["gradnorm/" + name] = np.array(p_.grad.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, "stage2nz_grads_R64.npz"), **gres)
+    print("grad norms:", {k: float(v) for k, v in gres.items() if k.startswith("gradnorm/") and
+                          ("IORs_pred" in k or "thickness" in k) and k.endswith("bias")})
     print("sphere:", [p.shape for p in pathes], [int(c.sum()) for c in converges], int(tir_mask.sum()),
           "rgb", res["train_ray_rgb"].mean(0))
 

@@ -1,0 +1,183 @@
+"""GPU parity of the non-zero-thickness Stage2Renderer (nu_nerf_b200/renderer.py; network/renderer.py:907-2378) against
+outputs of the UNMODIFIED reference run through oracle/ref_harness.py (tests/golden/stage2nz_*.npz, made by
+tests/golden/make_golden_nz.py; vertex curvature = the stated angle-defect definition on both sides).
+
+Bars: hit masks, hit triangle ids, pass masks and the TIR mask bit-exact; interpolated curvature 1e-4 relative; directions /
+IoR ratios / mesh normals 1e-5; path points 1e-4 on the uniformly sampled segments and the quantile gate of the CDF
+inversion on the up-sampled one; rendered colour 1e-4 in the fp32-accurate mode when render_core (with the PE-8 / PE-2
+AppShadingNetwork_SpecInner kernels) is fed the reference's own lists, 2e-3 end to end; parameter gradients of the trainer
+loss -- including IORs_pred and thickness_pred, which receive theirs through the shell geometry -- against the reference's
+autograd on equal sample parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, make_stage2
+from nu_nerf_b200.synthetic import torus
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(GOLDEN, "stage2nz_sphere_R64.npz"))
+
+
+@pytest.fixture(scope="module")
+def net():
+    return make_stage2("split", thick=True).cuda()
+
+
+def _lists(G):
+    T = lambda k: torch.from_numpy(G[k]).to(DEV)
+    n = int(G["n_segments"])
+    return ([T(f"path_{k}") for k in range(n)], [T(f"converge_{k}") for k in range(n)],
+            [T(f"dir_{k}") for k in range(n + 1)], [T(f"ior_{k}") for k in range(n) if f"ior_{k}" in G.files],
+            [T(f"bkgr_{k}") for k in range(n)], [T(f"nmesh_{k}") for k in range(n) if f"nmesh_{k}" in G.files])
+
+
+def _check_trace(net_, G):
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    tr = {}
+    with torch.no_grad():
+        pathes, converges, directions, iors, bkgr, nmesh, tir = net_.ray_trace(o, d, None, trace=tr)
+    n = int(G["n_segments"])
+    assert len(pathes) == n and len(converges) == n and len(directions) == n + 1
+    for k in range(int(G["n_bounces"])):
+        hit_ref = torch.from_numpy(G[f"in_hit_{k}"]).float().flatten()
+        assert torch.equal(tr[f"trace_hit_{k}"].cpu().float().flatten(), hit_ref), k
+        got_tri = tr[f"trace_tri_{k}"].cpu().int().flatten()[hit_ref.bool()]
+        assert torch.equal(got_tri, torch.from_numpy(G[f"in_tri_{k}"]).int().flatten()), k
+    for k in range(n):
+        assert torch.equal(converges[k].cpu(), torch.from_numpy(G[f"converge_{k}"])), k
+        assert torch.equal(bkgr[k].cpu(), torch.from_numpy(G[f"bkgr_{k}"])), k
+    for k in range(n + 1):
+        ref = torch.from_numpy(G[f"dir_{k}"])
+        assert directions[k].shape == ref.shape and (ref.numel() == 0 or (directions[k].cpu() - ref).abs().max().item() < 1e-5), k
+    for k in range(len(iors)):
+        assert (iors[k].cpu() - torch.from_numpy(G[f"ior_{k}"])).abs().max().item() < 1e-5, k
+        assert (nmesh[k].cpu() - torch.from_numpy(G[f"nmesh_{k}"])).abs().max().item() < 1e-5, k
+    assert torch.equal(tir.cpu(), torch.from_numpy(G["tir_mask"]))
+    for k in range(n):
+        ref, got = torch.from_numpy(G[f"path_{k}"]), pathes[k].cpu()
+        assert got.shape == ref.shape, k
+        err = (got - ref).norm(dim=-1)
+        if k != 1:
+            assert (err / ref.norm(dim=-1).clamp_min(1.0)).max().item() < 1e-4, (k, err.max().item())
+        else:
+            e = err.flatten()             # SDF-guided up-sampling: CDF inversion on the inner field (quantile gate)
+            assert torch.quantile(e, 0.95).item() < 2e-2 and e.max().item() < 0.5, (torch.quantile(e, 0.95).item(), e.max().item())
+            assert (got[:, [0, -1]] - ref[:, [0, -1]]).abs().max().item() < 1e-5
+
+
+def test_ray_trace_matches_reference_sphere(net, golden):
+    _check_trace(net, golden)
+
+
+def test_ray_trace_matches_reference_torus():
+    """Both curvature signs, rays that re-enter the object (third bounce with hits)."""
+    G = np.load(os.path.join(GOLDEN, "stage2nz_torus_R96.npz"))
+    net_ = make_stage2("split", mesh=torus(), thick=True).cuda()
+    net_._prepare()
+    # the interpolated curvature the shell geometry consumes: product definition vs the oracle-side one the reference was fed
+    o, d = torch.from_numpy(G["in_o_0"]).to(DEV), torch.from_numpy(G["in_d_0"]).to(DEV)
+    info, hit = net_.scene.Dintersect(o.contiguous(), d.contiguous())
+    gk = info["g_k"][hit].cpu().flatten()
+    ref = torch.from_numpy(G["in_gk_0"]).flatten()
+    assert (gk - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+    assert (ref > 0).any() and (ref < 0).any()
+    _check_trace(net_, G)
+
+
+def test_render_core_matches_reference(net, golden):
+    G = golden
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    pathes, converges, directions, iors, bkgr, nmesh = _lists(G)
+    for mode, is_train in (("train", True), ("eval", False)):
+        with torch.no_grad():
+            out = net.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2,
+                                  step=10000, is_train=is_train, is_nerf=True)
+        err = (out["ray_rgb"].cpu() - torch.from_numpy(G[f"{mode}_ray_rgb"])).abs().max().item()
+        print(f"[NZ render_core, {mode}] max |d rgb| = {err:.2e}")
+        assert err < 1e-4, (mode, err)
+        assert abs(out["std"].item() - float(G[f"{mode}_std"])) < 1e-6
+        ge = torch.from_numpy(G[f"{mode}_gradient_error"])
+        assert out["gradient_error"].shape == ge.shape and (out["gradient_error"].cpu() - ge).abs().max().item() < 1e-4
+        assert out["loss_occ"].shape == (1,) and out["loss_occ"].item() == 0.0
+        if not is_train:
+            for key in ("normal", "specular_color", "specular_light", "specular_ref"):
+                e = (out[key].cpu() - torch.from_numpy(G[f"eval_{key}"])).abs().max().item()
+                assert e < 2e-4, (key, e)
+
+
+def test_render_end_to_end_and_bf16(net, golden):
+    G = golden
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    with torch.no_grad():
+        out = net.render(o, d, None, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+    ref = torch.from_numpy(G["train_ray_rgb"])
+    err = (out["ray_rgb"].cpu() - ref).abs().max().item()
+    print(f"[NZ render end to end, split] max |d rgb| = {err:.2e}")
+    assert err < 2e-3, err
+    assert torch.equal(out["tir_mask"].cpu(), torch.from_numpy(G["tir_mask"]))
+    net16 = make_stage2("bf16", thick=True).cuda()
+    with torch.no_grad():
+        out16 = net16.render(o, d, None, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+    e16 = (out16["ray_rgb"].cpu() - ref).abs().max().item()
+    print(f"[NZ render end to end, bf16] max |d rgb| = {e16:.2e}")
+    assert e16 < 2e-2, e16
+
+
+def test_parameter_gradients_match_reference(golden):
+    """Trainer loss backward through the product's own trace (hit kernels, IoR / thickness MLPs, shell geometry) and
+    render_core on the sample parameters of the reference's trace, against the reference's autograd: every parameter
+    tensor, strided samples relative to the tensor's largest entry and the norm.  Gates: 1e-2 on every tensor, 2e-3 on at
+    least 90 % of them (the stage-1 material layers see ~55 surface hits behind ReLU / clamp kinks, cf. the zero-thickness
+    test), and the IoR / thickness networks -- whose gradient exists only through the path geometry -- within 5e-3."""
+    G = golden
+    GG = np.load(os.path.join(GOLDEN, "stage2nz_grads_R64.npz"))
+    net_ = make_stage2("split", thick=True).cuda()
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    # sample parameters of segment 1 as the reference drew them: z = |p - start| / |end - start|
+    p1 = torch.from_numpy(G["path_1"]).to(DEV)
+    z1 = ((p1 - p1[:, :1]).norm(dim=-1) / (p1[:, -1:] - p1[:, :1]).norm(dim=-1)).contiguous()
+    net_.zero_grad()
+    prepared = net_._prepare()
+    pathes, converges, directions, iors, bkgr, nmesh, tir = net_.ray_trace(o, d, None, prepared=prepared, trace={"z_1": z1})
+    assert pathes[1].requires_grad and directions[1].requires_grad
+    assert (pathes[1].detach() - p1).abs().max().item() < 2e-5
+    out = net_.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2, step=10000,
+                           is_train=True, is_nerf=True, prepared=prepared)
+    gt, tm = torch.from_numpy(GG["gt"]).to(DEV), tir
+    loss = net_.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
+    loss.backward()
+    assert abs(loss.item() - float(GG["loss"])) < 1e-4, (loss.item(), float(GG["loss"]))
+    named = dict(net_.named_parameters())
+    rep = []
+    for key in GG.files:
+        if not key.startswith("grad/"):
+            continue
+        name = key[5:]
+        ref, ref_norm = torch.from_numpy(GG[key]), float(GG["gradnorm/" + name])
+        p = named[name]
+        if ref_norm == 0.0:
+            assert p.grad is None or p.grad.abs().max().item() < 1e-9, name
+            continue
+        assert p.grad is not None, f"no gradient for {name}"
+        g = p.grad.detach().reshape(-1).cpu()
+        idx = torch.linspace(0, g.numel() - 1, min(g.numel(), 64)).long()
+        scale = max(ref.abs().max().item(), ref_norm / max(g.numel(), 1) ** 0.5)
+        rep.append((name, (g[idx] - ref).abs().max().item() / scale, abs(p.grad.double().norm().item() - ref_norm) / ref_norm))
+    rep.sort(key=lambda r: -r[1])
+    geo = [r for r in rep if r[0].startswith(("IORs_pred", "thickness_pred"))]
+    print(f"[NZ gradients, split] {len(rep)} tensors; worst (name, sampled rel. error, norm rel. error):")
+    for r in rep[:6]:
+        print("   %-60s %.2e %.2e" % r)
+    print("   IoR / thickness networks:", [(n_, round(a, 6), round(b, 6)) for n_, a, b in geo])
+    assert len(rep) >= 250 and len(geo) == 24, (len(rep), len(geo))
+    assert all(a < 5e-3 and b < 1e-2 for _, a, b in geo), geo
+    assert all(a < 1e-2 and b < 2e-2 for _, a, b in rep), rep[:4]
+    assert sum(a < 2e-3 for _, a, _ in rep) >= 0.9 * len(rep)

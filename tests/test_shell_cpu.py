@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from nu_nerf_b200.shell import shell_bounce, outside_depths
+from nu_nerf_b200.shell import shell_bounce, signed_normal, outside_depths
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 2e-6
@@ -32,7 +32,7 @@ def test_shell_bounce_matches_reference_trace(name):
         hit_idx = hit.nonzero().squeeze(1)
         d_all = _t(g[f"in_d_{k}"])
         inside = k % 2 == 1
-        out = shell_bounce(_t(g[f"in_x_{k}"]), _t(g[f"in_n_{k}"]), d_all[hit_idx], _t(g[f"in_gk_{k}"]),
+        out = shell_bounce(_t(g[f"in_x_{k}"]), signed_normal(_t(g[f"in_n_{k}"]), inside), d_all[hit_idx], _t(g[f"in_gk_{k}"]),
                            _t(g[f"in_ior_{k}"]).reshape(-1, 1), _t(g[f"in_thick_{k}"]).reshape(-1, 1), inside)
         seen_signs |= set(np.sign(g[f"in_gk_{k}"]).flatten().tolist())
         conv = torch.zeros(hit.shape[0], dtype=torch.bool)
@@ -65,7 +65,7 @@ def test_shell_bounce_is_differentiable_and_handles_empty():
     ior = _t(g["in_ior_1"]).reshape(-1, 1).clone().requires_grad_(True)
     th = _t(g["in_thick_1"]).reshape(-1, 1).clone().requires_grad_(True)
     x = _t(g["in_x_1"]).clone().requires_grad_(True)
-    out = shell_bounce(x, _t(g["in_n_1"]), _t(g["in_d_1"])[hit_idx], _t(g["in_gk_1"]), ior, th, True)
+    out = shell_bounce(x, signed_normal(_t(g["in_n_1"]), True), _t(g["in_d_1"])[hit_idx], _t(g["in_gk_1"]), ior, th, True)
     (out["dir"].sum() + out["start"].square().sum()).backward()
     for t in (ior, th, x):
         assert t.grad is not None and torch.isfinite(t.grad).all() and t.grad.abs().sum() > 0
