@@ -280,6 +280,10 @@ typedef struct {
    * light_pos_freq 8 (the PE(p) block of x_inner / x_weight is 51 columns, the IDE block starts at column 51) and
    * refrac_freq 2 (x_refrac = PE2(p) ++ PE2(v), 30 columns).  Supported pairs: (6, 6) and (8, 2). */
   int pos_freq; int refrac_freq;
+  /* the `sphere_direction` shader variant (field.py:594-597, :641-651, :675-680): x_outer rows are 192 columns,
+   * [IDE(u, k) | IDE(q(p, u), k') | 0] with q the exit point of the ray (p, u) on the unit sphere; d_x_outer carries 144
+   * gradient columns and the backward needs pts */
+  int sphere_direction;
 } nunerf_shade_encode_t;
 int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* stream);
 /* IDE(x, kinv) of M unit directions at one constant roughness -> planes (per-ray specular probe, ZT:780) */

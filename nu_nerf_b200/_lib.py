@@ -61,7 +61,7 @@ class ShadeEncodeT(C.Structure):
                 ("x_weight", vp), ("ld_weight", ci), ("lo_weight", ci), ("x_refrac", vp), ("ld_refrac", ci),
                 ("lo_refrac", ci), ("nov", vp), ("d_x_outer", vp), ("ld_dxo", ci), ("d_x_inner", vp), ("ld_dxi", ci),
                 ("d_nov", vp), ("d_grad", vp), ("d_rough_raw", vp), ("ld_drough", ci), ("refl", vp),
-                ("d_x_refrac", vp), ("ld_dxr", ci), ("d_pts", vp), ("d_dirs", vp), ("pos_freq", ci), ("refrac_freq", ci)]
+                ("d_x_refrac", vp), ("ld_dxr", ci), ("d_pts", vp), ("d_dirs", vp), ("pos_freq", ci), ("refrac_freq", ci), ("sphere_direction", ci)]
 
 
 class ShadeMixT(C.Structure):

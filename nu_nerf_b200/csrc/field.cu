@@ -436,14 +436,17 @@ __global__ void shade_encode_bwd_kernel(nunerf_shade_encode_t p) {
   p.d_rough_raw[m * p.ld_drough] += drough * rough * (1.0f - rough);
 }
 
-// ---- the same two kernels for other encoding frequencies (AppShadingNetwork_SpecInner, field.py:1320-1330: light_pos_freq
-// PF = 8, refrac_freq RF = 2).  Kept apart from the (6, 6) kernels above, which are on the measured stage-1 path: these run
-// on the inner field of the non-zero-thickness stage 2 only.  Row layouts: x_inner = [PE_PF(p) | IDE | 0],
-// x_weight = [PE_PF(p) | PE6(r) | 0], x_refrac = [PE_RF(p) | PE_RF(v) | 0], all 128 columns.
-template <int PF, int RF>
+// ---- the same two kernels for the other shading-network variants.  Kept apart from the (6, 6) kernels above, which are on
+// the measured stage-1 path.
+//   PF / RF: light_pos_freq / refrac_freq (AppShadingNetwork_SpecInner, field.py:1320-1330: 8 / 2).  Row layouts:
+//     x_inner = [PE_PF(p) | IDE | 0], x_weight = [PE_PF(p) | PE6(r) | 0], x_refrac = [PE_RF(p) | PE_RF(v) | 0], 128 columns.
+//   SPH: the `sphere_direction` variant (field.py:594-597, :641-651, :675-680): the outer-light input is 144 wide,
+//     x_outer = [IDE(u, k) | IDE(q(p, u), k') | 0] in 192-column rows, q = where the ray (p, u) leaves the unit sphere
+//     (pw::sphere_dir_fwd); (u, k, k') = (n, 1, 1) | (r, rough, rough) | (r, 0, rough) for the three row blocks.
+template <int PF, int RF, bool SPH>
 __global__ void __launch_bounds__(128) shade_encode_fwd_var_kernel(nunerf_shade_encode_t p) {
-  constexpr int PD = 3 + 6 * PF, RD = 3 + 6 * RF;
-  static_assert(PD <= 56 && PD + 72 <= 128 && PD + 39 <= 128 && 2 * RD <= 128, "row layout");
+  constexpr int PD = 3 + 6 * PF, RD = 3 + 6 * RF, OW = SPH ? 192 : 128;
+  static_assert(PD + 72 <= 128 && PD + 39 <= 128 && 2 * RD <= 128, "row layout");
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long M = p.M;
   if (idx >= 4 * M) return;
@@ -453,24 +456,27 @@ __global__ void __launch_bounds__(128) shade_encode_fwd_var_kernel(nunerf_shade_
   float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
   float pt[3] = {p.pts[3 * m], p.pts[3 * m + 1], p.pts[3 * m + 2]};
   pw::ShadeDirs s = pw::shade_dirs(g, rd);
-  const float zero[16] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float row[128];
   if (job < 3) {
     __nv_bfloat16* xo = (__nv_bfloat16*)p.x_outer;
     __nv_bfloat16* xi = (__nv_bfloat16*)p.x_inner;
-    float* out = row + 56;     // IDE block at the top of the row buffer (16-byte aligned), moved down to column PD below
-    if (job == 0) pw::ide_fwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, out);
-    else pw::ide_fwd(c_ide, s.r[0], s.r[1], s.r[2], job == 1 ? pw::sigmoidf_(p.rough_raw[m * p.ld_rough]) : 0.0f, out);
+    float orow[OW];
+    const float* u = job == 0 ? s.n : s.r;
+    const float rough = job == 0 ? 1.0f : pw::sigmoidf_(p.rough_raw[m * p.ld_rough]);
+    pw::ide_fwd(c_ide, u[0], u[1], u[2], job == 2 ? 0.0f : rough, orow);
+    if (SPH) {
+      float q[3];
+      pw::sphere_dir_fwd(pt, u, q);
+      pw::ide_fwd(c_ide, q[0], q[1], q[2], rough, orow + 72);
+    }
+#pragma unroll
+    for (int j = SPH ? 144 : 72; j < OW; ++j) orow[j] = 0.f;
     const long long ro = ((long long)job * M + m) * p.ld_outer;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) store16(xo, ro + c * 16, p.lo_outer, out + c * 16);
-    store8(xo, ro + 64, p.lo_outer, out + 64);
-    store8(xo, ro + 72, p.lo_outer, zero);
-#pragma unroll
-    for (int c = 5; c < 8; ++c) store16(xo, ro + c * 16, p.lo_outer, zero);
+    for (int c = 0; c < OW / 16; ++c) store16(xo, ro + c * 16, p.lo_outer, orow + c * 16);
     if (job >= 1) {
 #pragma unroll
-      for (int j = PD; j < PD + 72; ++j) row[j] = row[j + 56 - PD];
+      for (int j = 0; j < 72; ++j) row[PD + j] = orow[j];
 #pragma unroll
       for (int j = PD + 72; j < 128; ++j) row[j] = 0.f;
       fill_pe<3, PF>(row, pt);
@@ -498,7 +504,7 @@ __global__ void __launch_bounds__(128) shade_encode_fwd_var_kernel(nunerf_shade_
   }
 }
 
-template <int PF, int RF>
+template <int PF, int RF, bool SPH>
 __global__ void shade_encode_bwd_var_kernel(nunerf_shade_encode_t p) {
   constexpr int PD = 3 + 6 * PF, RD = 3 + 6 * RF;
   long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -506,27 +512,36 @@ __global__ void shade_encode_bwd_var_kernel(nunerf_shade_encode_t p) {
   if (m >= M) return;
   float g[3] = {p.grad[3 * m], p.grad[3 * m + 1], p.grad[3 * m + 2]};
   float rd[3] = {p.dirs[3 * m], p.dirs[3 * m + 1], p.dirs[3 * m + 2]};
+  float pt[3] = {p.pts[3 * m], p.pts[3 * m + 1], p.pts[3 * m + 2]};
   pw::ShadeDirs s = pw::shade_dirs(g, rd);
   float rough = pw::sigmoidf_(p.rough_raw[m * p.ld_rough]);
-  float dn[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f}, drough = 0.f;
+  float dn[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f}, dpt[3] = {0.f, 0.f, 0.f}, drough = 0.f;
   float dout[72], gx, gy, gz, gk;
-  auto load = [&](long long orow, long long irow) {       // IDE gradient = outer-light row (+ inner-light row, columns PD..)
+  // one row block: IDE(u, k) gradient = outer-light columns 0..71 (+ inner-light columns PD..PD+71), and with SPH the
+  // second IDE block (columns 72..143) through the sphere direction q(p, u)
+  auto block = [&](long long orow, long long irow, const float* u, float k, bool k_is_rough, float* du) {
     const float* src = p.d_x_outer + orow * p.ld_dxo;
     for (int j = 0; j < 72; ++j) dout[j] = src[j];
     if (irow >= 0) {
       const float* src2 = p.d_x_inner + irow * p.ld_dxi + PD;
       for (int j = 0; j < 72; ++j) dout[j] += src2[j];
     }
+    pw::ide_bwd(c_ide, u[0], u[1], u[2], k, dout, &gx, &gy, &gz, &gk);
+    du[0] += gx; du[1] += gy; du[2] += gz;
+    if (k_is_rough) drough += gk;
+    if (SPH) {
+      for (int j = 0; j < 72; ++j) dout[j] = src[72 + j];
+      float q[3], dq[3];
+      pw::sphere_dir_fwd(pt, u, q);
+      const bool rough_k = irow >= 0;               // blocks 1 and 2 encode q at the predicted roughness, block 0 at 1
+      pw::ide_bwd(c_ide, q[0], q[1], q[2], rough_k ? rough : 1.0f, dout, &dq[0], &dq[1], &dq[2], &gk);
+      if (rough_k) drough += gk;
+      pw::sphere_dir_bwd(pt, u, dq, du, p.d_pts ? dpt : nullptr);
+    }
   };
-  load(m, -1);
-  pw::ide_bwd(c_ide, s.n[0], s.n[1], s.n[2], 1.0f, dout, &gx, &gy, &gz, &gk);
-  dn[0] += gx; dn[1] += gy; dn[2] += gz;
-  load(M + m, m);
-  pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], rough, dout, &gx, &gy, &gz, &gk);
-  dr[0] += gx; dr[1] += gy; dr[2] += gz; drough += gk;
-  load(2 * M + m, M + m);
-  pw::ide_bwd(c_ide, s.r[0], s.r[1], s.r[2], 0.0f, dout, &gx, &gy, &gz, &gk);
-  dr[0] += gx; dr[1] += gy; dr[2] += gz;
+  block(m, -1, s.n, 1.0f, false, dn);
+  block(M + m, m, s.r, rough, true, dr);
+  block(2 * M + m, M + m, s.r, 0.0f, false, dr);
   float dg[3];
   if (p.d_pts) {
     const float* gi0 = p.d_x_inner + m * p.ld_dxi;
@@ -536,9 +551,9 @@ __global__ void shade_encode_bwd_var_kernel(nunerf_shade_encode_t p) {
     for (int j = 0; j < PD; ++j) gpe[j] = gi0[j] + gi1[j];
     float dvd[3] = {0.f, 0.f, 0.f};
     for (int c = 0; c < 3; ++c) {
-      float acc = pw::pe_bwd_coord(gpe, 3, PF, c, p.pts[3 * m + c]);
+      float acc = dpt[c] + pw::pe_bwd_coord(gpe, 3, PF, c, pt[c]);
       if (gr) {
-        acc += pw::pe_bwd_coord(gr, 3, RF, c, p.pts[3 * m + c]);
+        acc += pw::pe_bwd_coord(gr, 3, RF, c, pt[c]);
         dvd[c] = pw::pe_bwd_coord(gr + RD, 3, RF, c, s.v[c]);
       }
       p.d_pts[3 * m + c] += acc;
@@ -964,9 +979,13 @@ extern "C" int nunerf_shade_encode_fwd(const nunerf_shade_encode_t* p, void* str
                    p->lo_refrac) & 7) == 0 && p->ld_outer >= 128 && p->ld_inner >= 128 && p->ld_weight >= 128 &&
                      p->ld_refrac >= 128,
                  "shade_encode_fwd: operand rows must be >= 128 columns with 8-column aligned pitches");
-  const int pf = p->pos_freq ? p->pos_freq : 6, rf = p->refrac_freq ? p->refrac_freq : 6;
-  if (pf == 6 && rf == 6) shade_encode_fwd_kernel<<<cdiv(4LL * p->M, 128), 128, 0, ST(stream)>>>(*p);
-  else if (pf == 8 && rf == 2) shade_encode_fwd_var_kernel<8, 2><<<cdiv(4LL * p->M, 128), 128, 0, ST(stream)>>>(*p);
+  const int pf = p->pos_freq ? p->pos_freq : 6, rf = p->refrac_freq ? p->refrac_freq : 6, sph = p->sphere_direction;
+  NUNERF_REQUIRE(p->ld_outer >= (sph ? 192 : 128), "shade_encode_fwd: sphere_direction needs 192-column x_outer rows");
+  const int nb = (int)cdiv(4LL * p->M, 128);
+  if (pf == 6 && rf == 6 && !sph) shade_encode_fwd_kernel<<<nb, 128, 0, ST(stream)>>>(*p);
+  else if (pf == 6 && rf == 6) shade_encode_fwd_var_kernel<6, 6, true><<<nb, 128, 0, ST(stream)>>>(*p);
+  else if (pf == 8 && rf == 2 && !sph) shade_encode_fwd_var_kernel<8, 2, false><<<nb, 128, 0, ST(stream)>>>(*p);
+  else if (pf == 8 && rf == 2) shade_encode_fwd_var_kernel<8, 2, true><<<nb, 128, 0, ST(stream)>>>(*p);
   else return fail("%s", "shade_encode_fwd: supported (pos_freq, refrac_freq) are (6, 6) and (8, 2)");
   NUNERF_CHECK_LAUNCH("shade_encode_fwd_kernel");
   return 0;
@@ -977,9 +996,13 @@ extern "C" int nunerf_shade_encode_bwd(const nunerf_shade_encode_t* p, void* str
                  "shade_encode_bwd: bad arguments");
   NUNERF_REQUIRE(!p->d_pts || (p->pts && p->d_dirs), "shade_encode_bwd: d_pts needs pts and d_dirs");
   if (int r = ensure_ide()) return r;
-  const int pf = p->pos_freq ? p->pos_freq : 6, rf = p->refrac_freq ? p->refrac_freq : 6;
-  if (pf == 6 && rf == 6) shade_encode_bwd_kernel<<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
-  else if (pf == 8 && rf == 2) shade_encode_bwd_var_kernel<8, 2><<<cdiv(p->M, 128), 128, 0, ST(stream)>>>(*p);
+  const int pf = p->pos_freq ? p->pos_freq : 6, rf = p->refrac_freq ? p->refrac_freq : 6, sph = p->sphere_direction;
+  NUNERF_REQUIRE(!sph || (p->ld_dxo >= 144 && p->pts), "shade_encode_bwd: sphere_direction needs 144 gradient columns and pts");
+  const int nb = (int)cdiv(p->M, 128);
+  if (pf == 6 && rf == 6 && !sph) shade_encode_bwd_kernel<<<nb, 128, 0, ST(stream)>>>(*p);
+  else if (pf == 6 && rf == 6) shade_encode_bwd_var_kernel<6, 6, true><<<nb, 128, 0, ST(stream)>>>(*p);
+  else if (pf == 8 && rf == 2 && !sph) shade_encode_bwd_var_kernel<8, 2, false><<<nb, 128, 0, ST(stream)>>>(*p);
+  else if (pf == 8 && rf == 2) shade_encode_bwd_var_kernel<8, 2, true><<<nb, 128, 0, ST(stream)>>>(*p);
   else return fail("%s", "shade_encode_bwd: supported (pos_freq, refrac_freq) are (6, 6) and (8, 2)");
   NUNERF_CHECK_LAUNCH("shade_encode_bwd_kernel");
   return 0;

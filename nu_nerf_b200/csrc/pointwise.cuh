@@ -237,6 +237,57 @@ PW_HD void shade_dirs_bwd(const ShadeDirs& s, const float* d_r, const float* d_n
   for (int c = 0; c < 3; ++c) d_g[c] = (dn[c] - s.n[c] * ndn) / s.gn;
 }
 
+// ----------------------------------------------------------------------------- sphere direction (field.py:447-465, :641-644)
+// The `sphere_direction` shading variant looks the direct light up at the point where the ray (p, u) leaves the unit sphere:
+// q = normalize(ps + u t), ps = p pulled inside radius 0.999 (offset_points_to_sphere), t = -ps.u + sqrt((ps.u)^2 - ps.ps + 1
+// + 1e-6) (get_sphere_intersection).
+PW_HD void sphere_dir_fwd(const float* p, const float* u, float* q) {
+  float pn = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  float ps[3] = {p[0], p[1], p[2]};
+  if (pn > 0.999f)
+    for (int c = 0; c < 3; ++c) ps[c] = p[c] / pn * 0.999f;
+  float dtx = ps[0] * u[0] + ps[1] * u[1] + ps[2] * u[2];
+  float xtx = ps[0] * ps[0] + ps[1] * ps[1] + ps[2] * ps[2];
+  float t = -dtx + sqrtf(dtx * dtx - xtx + 1.0f + 1e-6f);
+  float y[3] = {ps[0] + u[0] * t, ps[1] + u[1] * t, ps[2] + u[2] * t};
+  float yn = fmaxf(sqrtf(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]), 1e-12f);
+  for (int c = 0; c < 3; ++c) q[c] = y[c] / yn;
+}
+// d_q -> d_u (added) and d_p (added when given)
+PW_HD void sphere_dir_bwd(const float* p, const float* u, const float* d_q, float* d_u, float* d_p) {
+  float pn = sqrtf(p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+  bool scaled = pn > 0.999f;
+  float ps[3] = {p[0], p[1], p[2]};
+  if (scaled)
+    for (int c = 0; c < 3; ++c) ps[c] = p[c] / pn * 0.999f;
+  float dtx = ps[0] * u[0] + ps[1] * u[1] + ps[2] * u[2];
+  float xtx = ps[0] * ps[0] + ps[1] * ps[1] + ps[2] * ps[2];
+  float sq = sqrtf(dtx * dtx - xtx + 1.0f + 1e-6f);
+  float t = -dtx + sq;
+  float y[3] = {ps[0] + u[0] * t, ps[1] + u[1] * t, ps[2] + u[2] * t};
+  float yn = fmaxf(sqrtf(y[0] * y[0] + y[1] * y[1] + y[2] * y[2]), 1e-12f);
+  float q[3] = {y[0] / yn, y[1] / yn, y[2] / yn};
+  float qdq = q[0] * d_q[0] + q[1] * d_q[1] + q[2] * d_q[2];
+  float dy[3];
+  for (int c = 0; c < 3; ++c) dy[c] = (d_q[c] - q[c] * qdq) / yn;
+  float dt = dy[0] * u[0] + dy[1] * u[1] + dy[2] * u[2];
+  float ddtx = dt * (-1.0f + dtx / sq), dxtx = -dt * 0.5f / sq;
+  float dps[3];
+  for (int c = 0; c < 3; ++c) {
+    d_u[c] += dy[c] * t + ddtx * ps[c];
+    dps[c] = dy[c] + ddtx * u[c] + 2.0f * dxtx * ps[c];
+  }
+  if (d_p) {
+    if (scaled) {
+      float ph[3] = {p[0] / pn, p[1] / pn, p[2] / pn};
+      float pd = ph[0] * dps[0] + ph[1] * dps[1] + ph[2] * dps[2];
+      for (int c = 0; c < 3; ++c) d_p[c] += 0.999f * (dps[c] - ph[c] * pd) / pn;
+    } else {
+      for (int c = 0; c < 3; ++c) d_p[c] += dps[c];
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- FG LUT (dr.texture linear/clamp)
 PW_HD void fg_lookup(const float* lut, float u, float v, float* fg, float* dfg_du, float* dfg_dv) {
   const int W = 256, H = 256;

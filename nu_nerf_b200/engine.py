@@ -594,6 +594,7 @@ class Stage1Weights:
         self.pos_freq, self.refrac_freq = int(ccfg.get("light_pos_freq", 6)), int(ccfg.get("refrac_freq", 6))
         if (self.pos_freq, self.refrac_freq) not in ((6, 6), (8, 2)):
             raise NotImplementedError("shading encode kernels: (light_pos_freq, refrac_freq) must be (6, 6) or (8, 2)")
+        self.sphere_dir = bool(ccfg.get("sphere_direction", False))           # 144-wide outer-light input (field.py:594-597)
         self.exp_max_refrac = float(getattr(net.color_network.refrac_light, "exp_max", ccfg.get("light_exp_max", 3.0)))
         self.lut = net.color_network.FG_LUT.detach().float().contiguous()
         self.inv_s = torch.zeros(1, device=device)
@@ -685,7 +686,8 @@ def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
     # material predictors on [feature | p]
     t.mat = {k: pred_forward(w.pred[k], t.xm, M, 320, planes) for k in _MAT}
     # directions + encodings (the encode kernel writes whole 128-column rows, zero padded: no prior fill needed)
-    t.xo, t.xi = P(3 * M, 128, planes, dev), P(2 * M, 128, planes, dev)
+    ow = 192 if w.sphere_dir else 128            # sphere_direction: [IDE(u) | IDE(q(p, u)) | 0] (144 real columns)
+    t.xo, t.xi = P(3 * M, ow, planes, dev), P(2 * M, 128, planes, dev)
     t.xw, t.xr = P(M, 128, planes, dev), P(M, 128, planes, dev)
     t.nov = _f(M, dev=dev)
     t.normals = normals
@@ -697,11 +699,11 @@ def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
     se.x_weight, se.ld_weight, se.lo_weight = t.xw.ptr, t.xw.ld, t.xw.lo
     se.x_refrac, se.ld_refrac, se.lo_refrac = t.xr.ptr, t.xr.ld, t.xr.lo
     se.nov = t.nov.data_ptr()
-    se.pos_freq, se.refrac_freq = w.pos_freq, w.refrac_freq
+    se.pos_freq, se.refrac_freq, se.sphere_direction = w.pos_freq, w.refrac_freq, int(w.sphere_dir)
     t.refl = _f(M, 3, dev=dev)
     se.refl = t.refl.data_ptr()
     call("nunerf_shade_encode_fwd", C.byref(se))
-    t.lo_ = pred_forward(w.pred["outer_light"], t.xo, 3 * M, 128, planes)
+    t.lo_ = pred_forward(w.pred["outer_light"], t.xo, 3 * M, ow, planes)
     t.li_ = pred_forward(w.pred["inner_light"], t.xi, 2 * M, 128, planes)
     t.lw_ = pred_forward(w.pred["inner_weight"], t.xw, M, 128, planes)
     if no_refraction:
@@ -718,6 +720,10 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
     """ZT:725-793 forward.  Returns the tape and the output tensors.  The dense per-sample compositing weights [R,S]
     are only needed by the validation outputs (depth / normal, ZT:657-693): a training step passes want_weights=False and
     the compositing kernel does not write them."""
+    if w.sphere_dir:
+        raise NotImplementedError("stage-1 render_core with shader_config.sphere_direction: the per-ray specular probe over "
+                                  "the rays whose 65th sample lies in the unit sphere (network/renderer.py:483-496) is not "
+                                  "built; renderer_zerothick.py:780 itself feeds 72 columns to the 144-wide outer light")
     planes = w.planes
     R, S = z_vals.shape
     dev = z_vals.device
@@ -840,8 +846,9 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     call("nunerf_shade_mix_bwd", C.byref(_mix_params(w, t, dc_in, d_trans, d_met, dz, d_rough, d_nov, d_occ)))
     if d_nov_ext is not None:
         d_nov += d_nov_ext
-    dxo, dxi = _f(3 * M, 128, dev=dev), _f(2 * M, 128, dev=dev)
-    pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=128)
+    ow = 192 if w.sphere_dir else 128
+    dxo, dxi = _f(3 * M, ow, dev=dev), _f(2 * M, 128, dev=dev)
+    pred_backward(w.pred["outer_light"], t.lo_, dz["outer"], planes, dx_f32=dxo, dx_n=ow)
     pred_backward(w.pred["inner_light"], t.li_, dz["inner"], planes, dx_f32=dxi, dx_n=128)
     pred_backward(w.pred["inner_weight"], t.lw_, dz["weight"], planes)
     dxr = None
@@ -873,9 +880,9 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
     se = _lib.ShadeEncodeT()
     se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.normals.data_ptr(), t.dirs_in.data_ptr()
     se.rough_raw, se.ld_rough = t.mat["roughness_predictor"].head.data_ptr(), 16
-    se.d_x_outer, se.ld_dxo, se.d_x_inner, se.ld_dxi = dxo.data_ptr(), 128, dxi.data_ptr(), 128
+    se.d_x_outer, se.ld_dxo, se.d_x_inner, se.ld_dxi = dxo.data_ptr(), dxo.stride(0), dxi.data_ptr(), 128
     se.d_nov, se.d_grad, se.d_rough_raw, se.ld_drough = d_nov.data_ptr(), d_grad.data_ptr(), d_rough.data_ptr(), 1
-    se.pos_freq, se.refrac_freq = w.pos_freq, w.refrac_freq
+    se.pos_freq, se.refrac_freq, se.sphere_direction = w.pos_freq, w.refrac_freq, int(w.sphere_dir)
     if want_geo:
         se.d_x_refrac, se.ld_dxr = ptr(dxr), (dxr.stride(0) if dxr is not None else 0)
         se.d_pts, se.d_dirs = d_pts.data_ptr(), d_dirs.data_ptr()

@@ -150,8 +150,8 @@ class AppShadingNetwork(nn.Module):
     def __init__(self, cfg):
         super().__init__()
         self.cfg = {**self.default_cfg, **cfg}
-        if self.cfg["human_light"] or self.cfg["sphere_direction"]:
-            raise NotImplementedError("human_light / sphere_direction shading variants are not on the B200 path")
+        if self.cfg["human_light"]:
+            raise NotImplementedError("the human_light shading variant is not on the B200 path")
         feats_dim = 256
         self.metallic_predictor = make_predictor(feats_dim + 3, 1)
         if self.cfg["metallic_init"] != 0:
@@ -165,7 +165,9 @@ class AppShadingNetwork(nn.Module):
         dir_dim = pe_dim(6)
         rf = pe_dim(self.cfg["refrac_freq"])
         exp_max = self.cfg["light_exp_max"]
-        self.outer_light = make_predictor(72, 3, activation="exp", exp_max=exp_max)
+        # sphere_direction (field.py:594-597): the direct light also sees IDE(exit point of the ray on the unit sphere)
+        self.outer_light = make_predictor(72 * 2 if self.cfg["sphere_direction"] else 72, 3, activation="exp",
+                                          exp_max=exp_max)
         nn.init.constant_(self.outer_light[-2].bias, np.log(0.5))
         self.inner_light = make_predictor(pos_dim + 72, 3, activation="exp", exp_max=exp_max)
         nn.init.constant_(self.inner_light[-2].bias, np.log(0.5))
@@ -233,6 +235,9 @@ class AppShadingNetwork_S2(nn.Module):
     def __init__(self, cfg, stage1):
         super().__init__()
         self.cfg = {**self.default_cfg, **cfg}
-        if self.cfg["human_light"] or self.cfg["sphere_direction"]:
-            raise NotImplementedError("stage-2 shader: human_light / sphere_direction variants are not built")
+        if self.cfg["human_light"]:
+            raise NotImplementedError("stage-2 shader: the human_light variant is not built")
+        if bool(self.cfg["sphere_direction"]) != bool(stage1.color_network.cfg["sphere_direction"]):
+            raise ValueError("shader_config.sphere_direction of stage 2 and of the stage-1 network must agree: the stage-2 "
+                             "shader evaluates the stage-1 outer_light (72 or 144 inputs, field.py:594-597, :829-833)")
         self.stage1_network = stage1

@@ -69,7 +69,7 @@ def torus(R=0.55, r=0.22, nu=40, nv=20):
     return np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int64)
 
 
-def make_stage2(precision="split", mesh=None, thick=False):
+def make_stage2(precision="split", mesh=None, thick=False, sphere_direction=False):
     """Stage2Renderer on the synthetic nested-sphere scene, built the way tests/golden/make_golden_stage2.py builds the
     reference's: stage-1 checkpoint
     from a seed-0 random-init NeROShapeRenderer, stage-2 modules from seed 5, in-memory UV-sphere outer mesh."""
@@ -77,9 +77,11 @@ def make_stage2(precision="split", mesh=None, thick=False):
     torch.manual_seed(0)
     cfg1 = load_default_cfg()
     cfg1["precision"] = precision
+    if sphere_direction:            # the shader variant of the reference's real-data configs (configs/shape/real/*.yaml)
+        cfg1["shader_config"] = {"sphere_direction": True, "human_light": False}
     net1 = NeROShapeRenderer(cfg1, training=False)
     cfg = {"name": "spherepot_s2", "network": "stage2", "database_name": "nerf/spherepot",
-           "shader_config": {"sphere_direction": False, "human_light": False}, "apply_occ_loss": True,
+           "shader_config": {"sphere_direction": bool(sphere_direction), "human_light": False}, "apply_occ_loss": True,
            "occ_loss_step": 20000, "is_nerf": True, "zero_thickness": True, "eikonal_weight": 0.02,
            "freeze_inv_s_step": 5000, "precision": precision,
            "stage1_ckpt_dir": {"network_state_dict": net1.state_dict()}, "stage1_cfg_dir": cfg1,

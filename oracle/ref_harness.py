@@ -259,7 +259,7 @@ def torus(R=0.55, r=0.22, nu=40, nv=20):
     return np.asarray(verts, dtype=np.float64), np.asarray(faces, dtype=np.int64)
 
 
-def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tmp", thick=False):
+def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tmp", thick=False, sphere_direction=False):
     """Stage2Renderer(cfg, training=False) of renderer_zerothick (thick=False) or of the non-zero-thickness
     network/renderer.py (thick=True) with configs/stage2/nerf/spherepot.yaml, a stage-1
     checkpoint made from a seeded random-init NeROShapeRenderer of the same module, and the in-memory mesh (shim 5: Scene
@@ -274,11 +274,18 @@ def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tm
         else:
             import network.renderer_zerothick as ZT
         cfg1 = load_cfg("configs/shape/nerf/spherepot.yaml")
+        if sphere_direction:        # the shader variant of the real-data configs (configs/shape/real/*.yaml)
+            cfg1 = {**cfg1, "shader_config": {**cfg1.get("shader_config", {}), "sphere_direction": True}}
+            cfg1_path = os.path.join(tmp_dir, "nunerf_stage1_cfg_sph.yaml")
+            import yaml
+            with open(cfg1_path, "w") as f:
+                yaml.safe_dump(cfg1, f)
         torch.manual_seed(stage1_seed)
         net1 = ZT.NeROShapeRenderer(cfg1, training=False)
     if fg_lut is not None:
         net1.color_network.FG_LUT.copy_(torch.as_tensor(fg_lut).reshape(1, 256, 256, 2))
-    ckpt = os.path.join(tmp_dir, "nunerf_stage1_ckpt_nz.pth" if thick else "nunerf_stage1_ckpt.pth")
+    ckpt = os.path.join(tmp_dir, ("nunerf_stage1_ckpt_nz%s.pth" % ("_sph" if sphere_direction else "")) if thick
+                        else "nunerf_stage1_ckpt.pth")
     torch.save({"network_state_dict": net1.state_dict(), "step": 0}, ckpt)
     curv = angle_defect_curvature(mesh_V, mesh_F) if thick else np.zeros((len(mesh_V), 1), np.float32)
     with in_ref_dir():
@@ -314,7 +321,9 @@ def load_stage2(mesh_V, mesh_F, stage1_seed=0, seed=5, fg_lut=None, tmp_dir="/tm
         ZT.Scene = ShimScene
         cfg = load_cfg("configs/stage2/nerf/spherepot.yaml")
         cfg["stage1_ckpt_dir"] = ckpt
-        cfg["stage1_cfg_dir"] = "configs/shape/nerf/spherepot.yaml"
+        cfg["stage1_cfg_dir"] = cfg1_path if sphere_direction else "configs/shape/nerf/spherepot.yaml"
+        if sphere_direction:
+            cfg["shader_config"] = {**cfg.get("shader_config", {}), "sphere_direction": True}
         cfg["stage1_mesh_dir"] = "<in-memory>"
         torch.manual_seed(seed)
         net = ZT.Stage2Renderer(cfg, training=False)

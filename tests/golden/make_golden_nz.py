@@ -10,6 +10,8 @@ Run in the build container only:  python tests/golden/make_golden_nz.py
                            path point) -- plus the render_core outputs dict (NZ:2155-2353) in train and eval mode.
   stage2nz_grads_R64.npz   sphere case with autograd on: trainer loss (mean charbonnier with the TIR mask + 0.02 * eikonal) and
                            strided samples + norms of every parameter gradient, incl. IORs_pred and thickness_pred.
+  stage2nz_sph_*.npz       the three sphere fixtures again with shader_config.sphere_direction: true in both stages (144-wide
+                           outer light, field.py:594-597, :641-651, :675-680) -- the shader variant of configs/*/real/*.yaml.
   stage2nz_torus_R96.npz   the same ray_trace record on a torus (both curvature signs, re-entering rays).
 
 Vertex Gaussian curvature: oracle/ref_harness.angle_defect_curvature (the stated replacement for the PyMesh attribute;
@@ -79,11 +81,11 @@ def trace_record(net, o, d):
     return res, out
 
 
-def main():
+def sphere_case(tag, sphere_direction):
     V, Fc = rh.uv_sphere(radius=0.6, nu=48, nv=24)
-    net, cfg = rh.load_stage2(V, Fc, thick=True)
+    net, cfg = rh.load_stage2(V, Fc, thick=True, sphere_direction=sphere_direction)
     sd = net.state_dict()
-    np.savez_compressed(os.path.join(OUT, "stage2nz_init.npz"),
+    np.savez_compressed(os.path.join(OUT, f"stage2nz{tag}_init.npz"),
                         **{k: fingerprint(v) for k, v in sd.items() if not k.endswith("FG_LUT")})
     o, d = rh.synthetic_rays(64)
     res, out = trace_record(net, o, d)
@@ -96,7 +98,7 @@ def main():
                                 cos_anneal_ratio=0.2, step=10000, is_train=is_train, is_nerf=True)
             for kk, v in r.items():
                 res[f"{mode}_{kk}"] = v.detach().float().numpy()
-    np.savez_compressed(os.path.join(OUT, "stage2nz_sphere_R64.npz"), **res)
+    np.savez_compressed(os.path.join(OUT, f"stage2nz{tag}_sphere_R64.npz"), **res)
     # ---- gradients of the stage-2 trainer loss through ray_trace + render_core (autograd of the reference): the IoR AND
     # the thickness network receive theirs through the shell geometry
     gt = rh.synthetic_targets(64)
@@ -114,12 +116,17 @@ def main():
         vals, idx = strided(p_.grad)
         gres["grad/" + name] = vals
         gres["gradnorm/" + name] = np.array(p_.grad.double().norm().item())
-    np.savez_compressed(os.path.join(OUT, "stage2nz_grads_R64.npz"), **gres)
+    np.savez_compressed(os.path.join(OUT, f"stage2nz{tag}_grads_R64.npz"), **gres)
     print("grad norms:", {k: float(v) for k, v in gres.items() if k.startswith("gradnorm/") and
                           ("IORs_pred" in k or "thickness" in k) and k.endswith("bias")})
     print("sphere:", [p.shape for p in pathes], [int(c.sum()) for c in converges], int(tir_mask.sum()),
           "rgb", res["train_ray_rgb"].mean(0))
 
+
+
+def main():
+    sphere_case("", False)
+    sphere_case("_sph", True)          # shader_config.sphere_direction: true (the real-data configs of this renderer)
     Vt, Ft = rh.torus()
     net2, _ = rh.load_stage2(Vt, Ft, thick=True)
     o, d = rh.synthetic_rays(96, seed=7)

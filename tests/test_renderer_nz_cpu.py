@@ -18,11 +18,13 @@ def _fp(t):
     return f(t)
 
 
-def test_nz_initialisation_is_bit_identical_to_the_reference():
-    net = make_stage2(thick=True)
+@pytest.mark.parametrize("sph", [False, True])
+def test_nz_initialisation_is_bit_identical_to_the_reference(sph):
+    net = make_stage2(thick=True, sphere_direction=sph)
     sd = net.state_dict()
-    G = np.load(os.path.join(GOLDEN, "stage2nz_init.npz"))
+    G = np.load(os.path.join(GOLDEN, "stage2nz_sph_init.npz" if sph else "stage2nz_init.npz"))
     assert len(G.files) == 562
+    assert net.stage1_network.color_network.outer_light[0].weight_v.shape[1] == (144 if sph else 72)
     for k in G.files:
         assert k in sd, f"missing parameter {k}"
         assert np.array_equal(_fp(sd[k]), G[k]), k

@@ -92,8 +92,11 @@ def test_ray_trace_matches_reference_torus():
     _check_trace(net_, G)
 
 
-def test_render_core_matches_reference(net, golden):
-    G = golden
+@pytest.mark.parametrize("sph", [False, True])
+def test_render_core_matches_reference(net, golden, sph):
+    """sph: shader_config.sphere_direction true in both stages (shade_encode_*_var_kernel<., ., true>, 144-wide outer light)."""
+    G = np.load(os.path.join(GOLDEN, "stage2nz_sph_sphere_R64.npz")) if sph else golden
+    net = make_stage2("split", thick=True, sphere_direction=True).cuda() if sph else net
     o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
     pathes, converges, directions, iors, bkgr, nmesh = _lists(G)
     for mode, is_train in (("train", True), ("eval", False)):
@@ -101,7 +104,7 @@ def test_render_core_matches_reference(net, golden):
             out = net.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2,
                                   step=10000, is_train=is_train, is_nerf=True)
         err = (out["ray_rgb"].cpu() - torch.from_numpy(G[f"{mode}_ray_rgb"])).abs().max().item()
-        print(f"[NZ render_core, {mode}] max |d rgb| = {err:.2e}")
+        print(f"[NZ render_core, {mode}, sphere_direction={sph}] max |d rgb| = {err:.2e}")
         assert err < 1e-4, (mode, err)
         assert abs(out["std"].item() - float(G[f"{mode}_std"])) < 1e-6
         ge = torch.from_numpy(G[f"{mode}_gradient_error"])
@@ -131,15 +134,16 @@ def test_render_end_to_end_and_bf16(net, golden):
     assert e16 < 2e-2, e16
 
 
-def test_parameter_gradients_match_reference(golden):
+@pytest.mark.parametrize("sph", [False, True])
+def test_parameter_gradients_match_reference(golden, sph):
     """Trainer loss backward through the product's own trace (hit kernels, IoR / thickness MLPs, shell geometry) and
     render_core on the sample parameters of the reference's trace, against the reference's autograd: every parameter
     tensor, strided samples relative to the tensor's largest entry and the norm.  Gates: 1e-2 on every tensor, 2e-3 on at
     least 90 % of them (the stage-1 material layers see ~55 surface hits behind ReLU / clamp kinks, cf. the zero-thickness
     test), and the IoR / thickness networks -- whose gradient exists only through the path geometry -- within 5e-3."""
-    G = golden
-    GG = np.load(os.path.join(GOLDEN, "stage2nz_grads_R64.npz"))
-    net_ = make_stage2("split", thick=True).cuda()
+    G = np.load(os.path.join(GOLDEN, "stage2nz_sph_sphere_R64.npz")) if sph else golden
+    GG = np.load(os.path.join(GOLDEN, "stage2nz_sph_grads_R64.npz" if sph else "stage2nz_grads_R64.npz"))
+    net_ = make_stage2("split", thick=True, sphere_direction=sph).cuda()
     o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
     # sample parameters of segment 1 as the reference drew them: z = |p - start| / |end - start|
     p1 = torch.from_numpy(G["path_1"]).to(DEV)
@@ -173,7 +177,7 @@ def test_parameter_gradients_match_reference(golden):
         rep.append((name, (g[idx] - ref).abs().max().item() / scale, abs(p.grad.double().norm().item() - ref_norm) / ref_norm))
     rep.sort(key=lambda r: -r[1])
     geo = [r for r in rep if r[0].startswith(("IORs_pred", "thickness_pred"))]
-    print(f"[NZ gradients, split] {len(rep)} tensors; worst (name, sampled rel. error, norm rel. error):")
+    print(f"[NZ gradients, split, sphere_direction={sph}] {len(rep)} tensors; worst (name, sampled rel. error, norm rel. error):")
     for r in rep[:6]:
         print("   %-60s %.2e %.2e" % r)
     print("   IoR / thickness networks:", [(n_, round(a, 6), round(b, 6)) for n_, a, b in geo])
