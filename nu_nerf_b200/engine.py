@@ -14,6 +14,7 @@ import math
 import os
 
 import torch
+import torch.nn.functional as F
 
 from . import _lib
 from ._lib import call, ptr
@@ -716,11 +717,27 @@ def shade_forward(w: Stage1Weights, t, normals, no_refraction=False):
     call("nunerf_shade_mix_fwd", C.byref(_mix_params(w, t)))
 
 
-def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_weights=True):
+def sphere_exit_dir(p, u):
+    """F.normalize(ps + u * get_sphere_intersection(ps, u)) with ps = offset_points_to_sphere(p) (field.py:447-465): where
+    the ray (p, u) leaves the unit sphere.  [R,3] torch glue for the per-ray specular probe (NZ:806-808); the per-sample
+    version lives in the encode kernels (pw::sphere_dir_fwd)."""
+    pn = p.norm(dim=-1, keepdim=True)
+    ps = torch.where(pn > 0.999, p / pn * 0.999, p)
+    dtx = (ps * u).sum(-1, keepdim=True)
+    xtx = (ps * ps).sum(-1, keepdim=True)
+    t_ = -dtx + torch.sqrt(dtx * dtx - xtx + 1 + 1e-6)
+    return F.normalize(ps + u * t_, dim=-1)
+
+
+def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_weights=True, nz=False):
     """ZT:725-793 forward.  Returns the tape and the output tensors.  The dense per-sample compositing weights [R,S]
     are only needed by the validation outputs (depth / normal, ZT:657-693): a training step passes want_weights=False and
-    the compositing kernel does not write them."""
-    if w.sphere_dir:
+    the compositing kernel does not write them.
+    nz: the stage-1 render_core of network/renderer.py (NZ:738-859) -- additionally t.loss_normal [R,1] = sum_j w_j
+    max(grad_j . dir_j, 0) (NZ:766-780: a second pass of the compositing kernel with that scalar in the first colour
+    channel), t.cand [R] = rays whose 65th mid-point lies in the unit sphere (NZ:798-802), and, with sphere_direction, the
+    specular probe on [IDE(d, 0) | IDE(exit direction of (p_65, d), 0)] (NZ:805-809)."""
+    if w.sphere_dir and not nz:
         raise NotImplementedError("stage-1 render_core with shader_config.sphere_direction: the per-ray specular probe over "
                                   "the rays whose 65th sample lies in the unit sphere (network/renderer.py:483-496) is not "
                                   "built; renderer_zerothick.py:780 itself feeds 72 columns to the 144-wide outer light")
@@ -763,11 +780,36 @@ def core_forward(w: Stage1Weights, rays_o, rays_d, z_vals, cos_anneal, is_nerf, 
     call("nunerf_composite_fwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
          None, R, S, t.is_nerf, rgb.data_ptr(), t.rgb_raw.data_ptr(), acc.data_ptr(), bkgr.data_ptr(),
          weights.data_ptr() if want_weights else None, t.ray_map.data_ptr())
+    t.nz = nz
+    if nz:
+        if S < 66:
+            raise ValueError("the non-zero-thickness stage-1 render_core reads sample 64 of every ray (NZ:798)")
+        t.loss_normal = torch.zeros(R, 1, device=dev)
+        if t.n_in > 0:
+            t.nd_pos = (t.sdf.grad * t.dirs_in).sum(-1) > 0
+            t.c_nd = torch.zeros(t.n_in, 3, device=dev)
+            t.c_nd[:, 0] = torch.clamp((t.sdf.grad * t.dirs_in).sum(-1), min=0.0)
+            t.c_zero = torch.zeros(max(t.n_out, 1), 3, device=dev)
+            raw, scr3, scr1 = _f(R, 3, dev=dev), _f(R, 3, dev=dev), _f(R, dev=dev)
+            call("nunerf_composite_fwd", t.a_in.data_ptr(), t.c_nd.data_ptr(), t.a_out.data_ptr(), t.c_zero.data_ptr(),
+                 None, R, S, 0, scr3.data_ptr(), raw.data_ptr(), scr1.data_ptr(), _f(R, 3, dev=dev).data_ptr(), None,
+                 t.ray_map.data_ptr())
+            t.loss_normal = raw[:, :1].clone()
+        zc = z[:, 64] + (z[:, 65] - z[:, 64]) * 0.5
+        p_c = o + d * zc[:, None]
+        t.cand = torch.norm(p_c, dim=-1) <= 1.0
     # ---- per-ray specular probe: outer_light(IDE(d, 0)) (ZT:780-781), activation applied by the caller
-    t.xs = P(R, 128, planes, dev)
     t.dn = _norm_dirs(d)
-    call("nunerf_ide_encode", t.dn.data_ptr(), R, 0.0, t.xs.ptr, t.xs.ld, t.xs.lo, 0)
-    t.ls_ = pred_forward(w.pred["outer_light"], t.xs, R, 128, planes)
+    if w.sphere_dir:
+        t.xs = P(R, 256, planes, dev, zero=True)      # [IDE(d, 0) (72) | IDE(q, 0) (72) | 0]: K = 192 of a 256-pitch row
+        q = sphere_exit_dir(p_c, t.dn).contiguous()
+        call("nunerf_ide_encode", t.dn.data_ptr(), R, 0.0, t.xs.ptr, t.xs.ld, t.xs.lo, 0)
+        call("nunerf_ide_encode", q.data_ptr(), R, 0.0, t.xs.ptr, t.xs.ld, t.xs.lo, 72)
+        t.ls_ = pred_forward(w.pred["outer_light"], t.xs, R, 192, planes)
+    else:
+        t.xs = P(R, 128, planes, dev)
+        call("nunerf_ide_encode", t.dn.data_ptr(), R, 0.0, t.xs.ptr, t.xs.ld, t.xs.lo, 0)
+        t.ls_ = pred_forward(w.pred["outer_light"], t.xs, R, 128, planes)
     return t, rgb, acc, bkgr, weights
 
 
@@ -803,9 +845,10 @@ def _mix_params(w, t, d_color=None, d_trans=None, d_met=None, dz=None, d_rough=N
 
 
 def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, want_inv_s,
-                  d_occ=None):
+                  d_occ=None, d_normal=None):
     """Reverse launch sequence of core_forward.  Returns {reference parameter name -> gradient of the EFFECTIVE
-    weight / bias} (+ 'inv_s')."""
+    weight / bias} (+ 'inv_s').  d_normal [R,1]: gradient of t.loss_normal (nz mode): the second compositing pass reversed
+    -- its d alpha joins the main one, its d colour is d loss / d max(grad . dir, 0) and reaches the SDF gradient."""
     planes, dev = w.planes, t.ray_map.device
     R, S, M = t.R, t.S, t.n_in
     g = {}
@@ -814,6 +857,20 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
     call("nunerf_composite_bwd", t.a_in.data_ptr(), t.c_in.data_ptr(), t.a_out.data_ptr(), t.c_out.data_ptr(),
          None, R, S, t.is_nerf, t.rgb_raw.data_ptr(), ptr(d_rgb), ptr(d_acc), ptr(d_bkgr),
          da_in.data_ptr(), dc_in.data_ptr(), da_out.data_ptr(), dc_out.data_ptr(), t.ray_map.data_ptr())
+    d_grad_extra = None
+    if d_normal is not None and M > 0:
+        g3 = torch.zeros(R, 3, device=dev)
+        g3[:, 0] = d_normal.reshape(-1)
+        half = torch.full((R, 3), 0.5, device=dev)               # inside (0, 1): the clamp of the colour pass lets it through
+        da2, dc2 = _f(max(M, 1), dev=dev), _f(max(M, 1), 3, dev=dev)
+        da3, dc3 = _f(max(t.n_out, 1), dev=dev), _f(max(t.n_out, 1), 3, dev=dev)
+        call("nunerf_composite_bwd", t.a_in.data_ptr(), t.c_nd.data_ptr(), t.a_out.data_ptr(), t.c_zero.data_ptr(),
+             None, R, S, 0, half.data_ptr(), g3.data_ptr(), None, None,
+             da2.data_ptr(), dc2.data_ptr(), da3.data_ptr(), dc3.data_ptr(), t.ray_map.data_ptr())
+        da_in += da2
+        if t.n_out > 0:
+            da_out += da3
+        d_grad_extra = (dc2[:M, 0] * t.nd_pos)[:, None] * t.dirs_in
     if t.n_out > 0:
         nerf_backward(w.nerf, t.nerf, da_out, dc_out, planes)
 
@@ -824,12 +881,12 @@ def core_backward(w: Stage1Weights, t: CoreTape, d_rgb, d_acc, d_bkgr, d_gerr, d
         pred_backward(w.pred["outer_light"], t.ls_, dzs, planes)
     if M == 0:
         return g
-    inner_backward(w, t, da_in, dc_in, d_gerr, d_trans, d_met, want_inv_s, d_occ, g)
+    inner_backward(w, t, da_in, dc_in, d_gerr, d_trans, d_met, want_inv_s, d_occ, g, d_grad_extra=d_grad_extra)
     return g
 
 
 def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, want_inv_s, d_occ=None, g=None,
-                   surface=False, want_geo=False, d_nov_ext=None):
+                   surface=False, want_geo=False, d_nov_ext=None, d_grad_extra=None):
     """Reverse of inner_forward on the M = t.n_in compact samples: shading mix, the light / material predictors,
     sdf -> alpha, the direction encodings and the SDF network (value pass + reverse-over-reverse of its gradient).
     surface=True is the reverse of the stage-2 surface shading (shade_forward with the MESH normal, no refraction
@@ -876,6 +933,8 @@ def inner_backward(w: Stage1Weights, t, da_in, dc_in, d_gerr, d_trans, d_met, wa
         call("nunerf_sdf_alpha_bwd", C.byref(sa))
         if want_inv_s:
             g["inv_s"] = d_inv
+    if d_grad_extra is not None:            # gradient that reaches the SDF gradient directly (loss_normal, NZ:766-780);
+        d_grad += d_grad_extra              # after sdf_alpha_bwd, which WRITES d_grad
     # ---- directions / encodings (adds into d_grad and d_rough; with want_geo also into d_pts / d_dirs)
     se = _lib.ShadeEncodeT()
     se.M, se.pts, se.grad, se.dirs = M, t.pts_in.data_ptr(), t.normals.data_ptr(), t.dirs_in.data_ptr()

@@ -33,8 +33,116 @@ import torch.nn.functional as F
 from .field import (SDFNetwork, SingleVarianceNetwork, NeRFNetwork, AppShadingNetwork_SpecInner, AppShadingNetwork_S2,
                     IoRNetwork, ThicknessNetwork)
 from .renderer_stage2 import Stage2Renderer as _ZTStage2Renderer, _HitFn, _engine
-from .renderer_zerothick import NeROShapeRenderer, load_cfg
+from .renderer_zerothick import NeROShapeRenderer as _ZTShapeRenderer, load_cfg, linear_to_srgb, _SdfValueFn
 from .shell import shell_bounce, signed_normal, outside_depths
+
+
+class _RenderCoreNZFn(torch.autograd.Function):
+    """NZ:738-859 as one autograd node: engine.core_forward(nz=True) / core_backward(d_normal=...).  Outputs of the
+    zero-thickness node plus loss_normal [R,1] (differentiable) and the candidate-ray mask of the specular probe."""
+
+    @staticmethod
+    def forward(ctx, pack, inv_s, *params):
+        eng = _engine()
+        w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max, want_inv_s, want_weights = pack
+        t, rgb, acc, bkgr, wts = eng.core_forward(w, rays_o, rays_d, z_vals, cos_anneal, is_nerf, exp_max,
+                                                  want_weights=want_weights, nz=True)
+        ctx.tape, ctx.w, ctx.n_params, ctx.want_inv_s = t, w, len(params), want_inv_s
+        dev = rgb.device
+        if t.n_in > 0:
+            gerr, trans, met, occ = t.gerr, t.trans[:, None], t.metallic[:, None], t.occ[:, None]
+            aux = (t.pts_in, t.sdf.sdf[:, 0], t.sdf.grad, t.dirs_in, t.refl)
+        else:
+            gerr, trans, met, occ = (torch.zeros(1, device=dev), torch.zeros(0, 1, device=dev),
+                                     torch.zeros(0, 1, device=dev), torch.zeros(0, 1, device=dev))
+            aux = tuple(torch.zeros(0, 3, device=dev) if i != 1 else torch.zeros(0, device=dev) for i in range(5))
+        spec = t.ls_.head[:, :3].clone()
+        ctx.mark_non_differentiable(wts, t.cand, *aux)
+        return (rgb, acc, bkgr, gerr, trans, met, spec, occ, t.loss_normal, wts, t.cand) + aux
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_acc, d_bkgr, d_gerr, d_trans, d_met, d_spec, d_occ, d_ln, *_unused):
+        eng = _engine()
+        t = ctx.tape
+        c = lambda x: None if x is None else x.contiguous().float()
+        has = t.n_in > 0
+        ctx.w.bank.zero_grads()
+        g = eng.core_backward(ctx.w, t, c(d_rgb), c(d_acc), c(d_bkgr), c(d_gerr) if has else None,
+                              c(d_trans).reshape(-1) if (has and d_trans is not None) else None,
+                              c(d_met).reshape(-1) if (has and d_met is not None) else None, c(d_spec), ctx.want_inv_s,
+                              d_occ=c(d_occ).reshape(-1) if (has and d_occ is not None) else None, d_normal=c(d_ln))
+        ctx.w.bank.backward()
+        ctx.tape = None
+        return (None, g.get("inv_s").reshape(()) if ctx.want_inv_s and "inv_s" in g else None,
+                *([None] * ctx.n_params))
+
+
+class NeROShapeRenderer(_ZTShapeRenderer):
+    """network/renderer.py:102-905: the stage-1 renderer of the non-zero-thickness pipeline.  Same modules, sampling and
+    field evaluation as the zero-thickness class; render_core additionally returns `loss_normal` (NZ:766-780: the
+    composited back-facing part of the SDF gradient, for NormalOrientationLoss, network/loss.py:105-112), evaluates the
+    specular probe -- with `sphere_direction` on [IDE(d) | IDE(exit direction)] -- and reports `color_spec` / `color_bkgr`
+    only for the rays whose 65th sample lies in the unit sphere (NZ:798-821); train_step adds `loss_mask` for synthetic
+    data (NZ:478)."""
+    default_cfg = {**_ZTShapeRenderer.default_cfg, "train_ray_num": 1024, "downsample_ratio": 1.0, "get_mask": False}
+
+    def __init__(self, cfg, training=True):
+        super().__init__(cfg, training=training)
+        self.get_mask = self.cfg["get_mask"]
+
+    def render_core(self, rays_o, rays_d, z_vals, human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True,
+                    is_nerf=False, prepared=None, occ_perm=None):
+        w = prepared if prepared is not None else self._prepare()
+        params = [p for d in w.bank.denses if d.has_grad for p in (d.v, d.g, d.bias) if p is not None]
+        params = list({id(p): p for p in params}.values())
+        freeze = self.cfg["freeze_inv_s_step"]
+        frozen = freeze is not None and step is not None and step < freeze
+        inv_s = torch.exp(self.deviation_network.variance * 10.0)
+        exp_max = self.color_network.cfg["light_exp_max"]
+        pack = (w, rays_o, rays_d, z_vals, float(cos_anneal_ratio), bool(is_nerf), exp_max, not frozen, not is_train)
+        (rgb, acc, bkgr, gerr, trans, met, spec, occ, loss_normal, weights, cand, pts_in, sdf_in, grad_in, dirs_in,
+         refl_in) = _RenderCoreNZFn.apply(pack, inv_s, *params)
+        inv_s_c = inv_s.clip(1e-6, 1e6)
+        if frozen:
+            inv_s_c = inv_s_c.detach()
+        has_inner = trans.shape[0] > 0
+        outputs = {
+            "ray_rgb": rgb, "gradient_error": gerr, "loss_normal": loss_normal, "acc": acc,
+            "color_bkgr": bkgr[cand],                                           # NZ:812 (boolean mask: one host sync)
+            "color_spec": linear_to_srgb(torch.exp(torch.clamp(spec, max=exp_max)))[cand],
+            "std": torch.mean(1.0 / inv_s_c) if has_inner else torch.zeros(1, device=rgb.device),
+        }
+        if step is not None and step < 1000:
+            zf = z_vals.float()
+            dist = torch.cat([zf[:, 1:] - zf[:, :-1], zf[:, -1:] - zf[:, -2:-1]], -1)
+            pts_all = rays_o.float()[:, None, :] + rays_d.float()[:, None, :] * (zf + dist * 0.5)[..., None]
+            mask = torch.norm(pts_all, dim=-1) < 1.2
+            sdf_pts = pts_all[mask].contiguous()
+            outputs["sdf_pts"] = sdf_pts
+            outputs["sdf_vals"] = _SdfValueFn.apply((w, sdf_pts), *params) if sdf_pts.shape[0] > 0 else \
+                torch.zeros(0, device=rgb.device)
+        if self.cfg["apply_occ_loss"]:
+            if has_inner and step is not None:
+                outputs["loss_occ"] = self.compute_occ_loss({"occ_prob": occ, "reflective": refl_in}, pts_in, sdf_in,
+                                                            grad_in, dirs_in, step, prepared=w, perm=occ_perm)
+            else:
+                outputs["loss_occ"] = torch.zeros(1, device=rgb.device)
+        if has_inner:
+            outputs["transmission"] = trans
+            outputs["metallic"] = met
+        if not is_train:
+            outputs.update(self.compute_validation_info(z_vals, rays_o, rays_d, weights, human_poses, step, prepared=w))
+        return outputs
+
+    def train_step(self, step):
+        outputs = super().train_step(step)
+        if self.is_nerf:                                                        # NZ:476-478
+            batch = self._last_batch
+            if "masks" not in batch:
+                raise KeyError("the non-zero-thickness stage-1 train_step needs batch['masks'] for synthetic data (NZ:478)")
+            outputs["loss_mask"] = F.l1_loss(batch["masks"].reshape(outputs["acc"].shape).float(), outputs["acc"],
+                                             reduction="mean")
+        return outputs
 
 
 class Stage2Renderer(_ZTStage2Renderer):
@@ -317,6 +425,6 @@ class Stage2Renderer(_ZTStage2Renderer):
 
 
 name2renderer = {
-    "shape": NeROShapeRenderer,         # modules / checkpoints identical to NZ:102-905; its loss_normal / loss_mask not built
+    "shape": NeROShapeRenderer,
     "stage2": Stage2Renderer,
 }

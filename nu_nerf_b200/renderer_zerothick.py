@@ -569,6 +569,7 @@ class NeROShapeRenderer(nn.Module):
             raise RuntimeError("no ray source attached: call set_ray_source(fn) (dataset ingest is outside the hot path)")
         rn = self.cfg["train_ray_num"]
         batch = self.ray_source(step, rn)
+        self._last_batch = batch
         rays_o = batch["rays_o"]
         rays_d = F.normalize(batch["rays_d"], dim=-1)
         if self.is_nerf:

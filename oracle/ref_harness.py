@@ -132,12 +132,16 @@ def injected_rand(draws):
         torch.rand = orig
 
 
-def load_stage1(seed=0, cfg_overrides=None, fg_lut=None):
-    """NeROShapeRenderer(cfg, training=False) of renderer_zerothick with spherepot.yaml."""
+def load_stage1(seed=0, cfg_overrides=None, fg_lut=None, thick=False):
+    """NeROShapeRenderer(cfg, training=False) of renderer_zerothick (or, thick=True, of the non-zero-thickness
+    network/renderer.py) with spherepot.yaml."""
     install()
     with in_ref_dir():
         from utils.base_utils import load_cfg
-        from network.renderer_zerothick import NeROShapeRenderer
+        if thick:
+            from network.renderer import NeROShapeRenderer
+        else:
+            from network.renderer_zerothick import NeROShapeRenderer
         cfg = load_cfg("configs/shape/nerf/spherepot.yaml")
         cfg.update(cfg_overrides or {})
         torch.manual_seed(seed)
