@@ -1,29 +1,35 @@
-"""Drop-in boundary for the reference's network/renderer.py ("NZ"): the NON-zero-thickness stage-2 renderer (SURVEY 8f
-row 1), i.e. the refraction path through a thin glass shell of learned thickness around the outer mesh.
+"""Drop-in boundary for the reference's network/renderer.py ("NZ"): the renderers of the NON-zero-thickness pipeline
+(SURVEY 8f row 1), i.e. the refraction path through a thin glass shell of learned thickness around the outer mesh.
 
     - from network.renderer import name2renderer
     + from nu_nerf_b200.renderer import name2renderer          # run_training.py:17-20 picks this module when
                                                                # cfg['zero_thickness'] is False
 
-What differs from the zero-thickness renderer (nu_nerf_b200/renderer_stage2.py) and is built here:
+What differs from the zero-thickness classes (renderer_zerothick.py / renderer_stage2.py) and is built here:
+  stage 1 (NeROShapeRenderer, NZ:102-905)
+  * render_core (NZ:738-859): `loss_normal` = sum_j w_j max(grad_j . dir_j, 0) -- a second pass of the compositing kernels
+    with that scalar as a colour channel, forward and backward (its d alpha joins the main one, its d colour reaches the SDF
+    gradient and from there the reverse-over-reverse passes); `color_spec` / `color_bkgr` for the rays whose 65th sample
+    lies in the unit sphere only (NZ:798-821), with `sphere_direction` the probe rows are [IDE(d) | IDE(exit direction)].
+  * train_step adds `loss_mask` = l1(masks, acc) for synthetic data (NZ:478).
+  stage 2 (Stage2Renderer, NZ:907-2378)
   * ray_trace (NZ:1610-2148): per bounce the curvature-radius shell offset with two refractions (nu_nerf_b200/shell.py,
     pinned bounce by bounce to the reference), the interpolated Gaussian curvature of the hit (Scene.Dintersect()['g_k'],
     tracer.discrete_gaussian_curvature -- the stated replacement of the PyMesh attribute, parity against PyMesh unpinned),
     IoR = 1 / (IORs_pred + 0.6), ThicknessNetwork * 0.01, retro-active un-convergence of rays that miss the mesh from the
     inside (NZ:1662-1672), 64 / 128 (64 + 2 x 32 SDF-guided) / 64 samples per segment, 64 inverse-depth samples for rays
     that leave the scene (NZ:2140-2143).  Kernels: BVH closest hit + re-intersection, IoR / thickness MLPs, inner-SDF
-    queries + up-sampling rounds, path points.  The closed-form bounce itself runs as fused-by-autograd torch expressions on
-    the [M, .] tensors of the hit rays (M <= rays per bounce; ~1 % of a step) so that the loss reaches IORs_pred AND
-    thickness_pred through it.
+    queries + up-sampling rounds, path points.  The closed-form bounce itself runs as torch expressions on the [M, .]
+    tensors of the hit rays (M <= rays per bounce; ~1 % of a step) so that the loss reaches IORs_pred AND thickness_pred
+    through it.
   * the inner field's shader is AppShadingNetwork_SpecInner (field.py:1320: PE-8 positions, PE-2 refraction inputs,
-    refraction light clamped at exp(-0.2)) -- shade_encode_*_var_kernel<8, 2>, exp_max_refrac of the mixing kernels.
+    refraction light clamped at exp(-0.2)) -- shade_encode_*_var_kernel<8, 2, .>, exp_max_refrac of the mixing kernels.
   * render_core (NZ:2155-2353): surface shading flagged `inner` for every segment but the first (NZ:2244), `loss_occ` key.
   * render(rays_o, rays_d, mask, near, far, ...) (NZ:1482) and the masked losses of train_step / test_step (NZ:1297-1299,
     :1364).
-Not built (raises NotImplementedError): the stage-1 twin of this module (NeROShapeRenderer with loss_normal / loss_mask,
-NZ:478, :784-793 -- 'shape' maps to the zero-thickness class, whose modules and checkpoints are identical), the
-sphere_direction / human_light shader variants, and the inner-field occlusion loss (NZ:2222-2230; the reference's real-data
-configs of this renderer all set apply_occ_loss: false).
+  both: shader_config.sphere_direction (field.py:594-597, :641-651, :675-680; every zero_thickness: False config sets it).
+Not built (raises NotImplementedError): the human_light shader variant and the inner-field occlusion loss of stage 2
+(NZ:2222-2230; the reference's configs of this renderer all set apply_occ_loss: false).
 """
 import numpy as np
 import torch
