@@ -373,6 +373,11 @@ def sub_records(args, torch, dev, hbm, tf_sus):
         c4["trace_only"]["hbm_frac_algorithmic"] = c4["trace_only"]["algorithmic_GBs"] / hbm
         out["config4_stage2"] = c4
         torch.cuda.empty_cache()
+        # the same scene through the non-zero-thickness renderer (network/renderer.py)
+        nz = bench_stage2.run(4096, train_iters=8, thick=True)
+        out["f1_stage2_nonzero_thickness"] = {k: nz[k] for k in ("workload", "ray_trace_with_sampling", "full_forward",
+                                                                 "train_step", "train_step_frozen_ior")}
+        torch.cuda.empty_cache()
         import bench_sweep
         out["config5_sweep_eval"] = bench_sweep.run(512)
         torch.cuda.empty_cache()

@@ -36,9 +36,13 @@ def timeit(fn, iters=10, warm=3, per_iter=False):
     return e0.elapsed_time(e1) / iters
 
 
-def run(R=4096, train_iters=20):
+def run(R=4096, train_iters=20, thick=False):
+    """thick: the non-zero-thickness renderer of network/renderer.py (nu_nerf_b200/renderer.py) on the same scene."""
     V, Fc = uv_sphere(0.6, 224, 224)
-    net = make_stage2("bf16", mesh=(V, Fc)).cuda()
+    net = make_stage2("bf16", mesh=(V, Fc), thick=thick).cuda()
+    # render(rays_o, rays_d, [mask,] near, far, human_poses, ...): the NZ signature carries the extra mask argument
+    rend = (lambda **kw: net.render(o, d, None, None, None, None, -1, 0.2, **kw)) if thick else \
+        (lambda **kw: net.render(o, d, None, None, None, -1, 0.2, **kw))
     g = torch.Generator().manual_seed(1)
     o = 3.0 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
     d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(R, 3, generator=g), dim=-1)
@@ -53,7 +57,7 @@ def run(R=4096, train_iters=20):
     ms_di = timeit(lambda: net.scene.Dintersect(ot, dt))
     hit, _ = bvh.trace(ot, dt)
     with torch.no_grad():
-        ms_full = timeit(lambda: net.render(o, d, None, None, None, -1, 0.2, is_train=False, step=10000, is_nerf=True),
+        ms_full = timeit(lambda: rend(is_train=False, step=10000, is_nerf=True),
                          iters=5, warm=2)
         ms_rt = timeit(lambda: net.ray_trace(o, d), iters=5, warm=2)
     # training step: trainer loss of configs/stage2/nerf/spherepot.yaml (TIR-masked charbonnier + 0.02 eikonal), Adam
@@ -62,7 +66,7 @@ def run(R=4096, train_iters=20):
 
     def train_step():
         opt.zero_grad(set_to_none=True)
-        out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+        out = rend(is_train=True, step=10000, is_nerf=True)
         tm = out["tir_mask"].detach()
         loss = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
         loss.backward()
@@ -75,7 +79,7 @@ def run(R=4096, train_iters=20):
     net.cfg["frozen_ior"] = False
     ms_frozen = t_frozen[len(t_frozen) // 2]
     return {
-        "workload": f"stage-2 zero-thickness forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
+        "workload": f"stage-2 {'non-zero-thickness (network/renderer.py)' if thick else 'zero-thickness'} forward, outer mesh {Fc.shape[0]} triangles ({bvh.n_nodes} BVH4 nodes), "
                     f"{R} rays, bf16 mode",
         "trace_only": {"rays": Rt, "ms": ms_trace, "Mrays_per_s": Rt / ms_trace / 1e3,
                        "algorithmic_GBs": 32.0 * Rt / ms_trace / 1e6, "hit_fraction": float(hit.mean())},
@@ -91,4 +95,5 @@ def run(R=4096, train_iters=20):
 
 
 if __name__ == "__main__":
-    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 4096)))
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    print(json.dumps(run(int(args[0]) if args else 4096, thick="--thick" in sys.argv)))
