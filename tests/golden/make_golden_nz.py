@@ -124,7 +124,41 @@ def sphere_case(tag, sphere_direction):
 
 
 
+def zero_thickness_sphere_direction():
+    """stage2_sph_R64.npz: the ZERO-thickness stage 2 (renderer_zerothick.py) with shader_config.sphere_direction: true in both
+    stages (configs/stage2/real/eikonal_wineglass.yaml): ray_trace lists, render_core outputs, trainer-loss gradients."""
+    V, Fc = rh.uv_sphere(radius=0.6, nu=48, nv=24)
+    net, cfg = rh.load_stage2(V, Fc, thick=False, sphere_direction=True)
+    o, d = rh.synthetic_rays(64)
+    gt = rh.synthetic_targets(64)
+    net.zero_grad()
+    pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = net.ray_trace(o, d)
+    r = net.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
+                        cos_anneal_ratio=0.2, step=10000, is_train=True, is_nerf=True)
+    tm = tir_mask.detach()
+    loss = net.compute_rgb_loss(r["ray_rgb"] * tm, gt * tm).mean() + (0.02 * r["gradient_error"]).mean()
+    loss.backward()
+    res = {"o": o.numpy(), "d": d.numpy(), "gt": gt.numpy(), "n_segments": np.array(len(pathes)),
+           "tir_mask": tir_mask.numpy(), "loss": loss.detach().numpy(), "train_ray_rgb": r["ray_rgb"].detach().numpy()}
+    for k in range(len(pathes)):
+        res[f"path_{k}"], res[f"converge_{k}"] = pathes[k].detach().numpy(), converges[k].numpy()
+        res[f"bkgr_{k}"] = infinity_bkgr[k].numpy()
+    for k in range(len(directions)):
+        res[f"dir_{k}"] = directions[k].detach().numpy()
+    for k in range(len(ior_ratios)):
+        res[f"ior_{k}"], res[f"nmesh_{k}"] = ior_ratios[k].detach().numpy(), gradient_mesh[k].detach().numpy()
+    for name, p_ in net.named_parameters():
+        if p_.grad is None or name.startswith("IORs_pred"):
+            continue
+        vals, idx = strided(p_.grad)
+        res["grad/" + name] = vals
+        res["gradnorm/" + name] = np.array(p_.grad.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, "stage2_sph_R64.npz"), **res)
+    print("zero-thickness + sphere_direction: loss", float(loss), "rgb", res["train_ray_rgb"].mean(0))
+
+
 def main():
+    zero_thickness_sphere_direction()
     sphere_case("", False)
     sphere_case("_sph", True)          # shader_config.sphere_direction: true (the real-data configs of this renderer)
     Vt, Ft = rh.torus()

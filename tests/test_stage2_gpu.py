@@ -402,3 +402,45 @@ def test_forward_eval_is_test_step(net):
     assert torch.equal(out["tir_mask"], ref["tir_mask"])
     assert (out["ray_rgb"].reshape(rn, 3) - ref["ray_rgb"] * ref["tir_mask"]).abs().max().item() < 1e-5
     assert torch.equal(out["gt_rgb"].reshape(rn, 3), imgs[0].permute(1, 2, 0).reshape(rn, 3) * ref["tir_mask"])
+
+
+def test_sphere_direction_variant_matches_reference():
+    """shader_config.sphere_direction: true in both stages (configs/stage2/real/eikonal_wineglass.yaml; field.py:594-597,
+    :641-651, :829-833): 144-wide outer light, the exit direction of the reflected / normal ray on the unit sphere encoded next
+    to the direction itself (shade_encode_*_var_kernel<6, 6, true>).  render_core on the reference's own lists against the
+    unmodified reference (tests/golden/stage2_sph_R64.npz): colour 1e-4, every field-parameter gradient within 1e-2 of the
+    tensor's largest entry (>= 90 % within 2e-3), norms within 2e-2."""
+    G = np.load(os.path.join(GOLDEN, "stage2_sph_R64.npz"))
+    net_ = make_stage2("split", sphere_direction=True).cuda()
+    assert net_.stage1_network.color_network.outer_light[0].weight_v.shape[1] == 144
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    pathes, converges, directions, iors, bkgr, nmesh = _lists(G)
+    gt, tm = torch.from_numpy(G["gt"]).to(DEV), torch.from_numpy(G["tir_mask"]).to(DEV)
+    net_.zero_grad()
+    out = net_.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2, step=10000,
+                           is_train=True, is_nerf=True)
+    err = (out["ray_rgb"].detach().cpu() - torch.from_numpy(G["train_ray_rgb"])).abs().max().item()
+    print(f"[stage 2 zero-thickness, sphere_direction] max |d rgb| = {err:.2e}")
+    assert err < 1e-4, err
+    loss = net_.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
+    loss.backward()
+    assert abs(loss.item() - float(G["loss"])) < 1e-4
+    named, rep = dict(net_.named_parameters()), []
+    for key in G.files:
+        if not key.startswith("grad/"):
+            continue
+        name = key[5:]
+        ref, ref_norm = torch.from_numpy(G[key]), float(G["gradnorm/" + name])
+        if ref_norm == 0.0:
+            continue
+        p = named[name]
+        assert p.grad is not None, name
+        g = p.grad.detach().reshape(-1).cpu()
+        idx = torch.linspace(0, g.numel() - 1, min(g.numel(), 64)).long()
+        scale = max(ref.abs().max().item(), ref_norm / max(g.numel(), 1) ** 0.5)
+        rep.append((name, (g[idx] - ref).abs().max().item() / scale, abs(p.grad.double().norm().item() - ref_norm) / ref_norm))
+    rep.sort(key=lambda r: -r[1])
+    print("   worst:", [(n_, round(a, 5), round(b, 5)) for n_, a, b in rep[:4]])
+    assert len(rep) >= 240
+    assert all(a < 1e-2 and b < 2e-2 for _, a, b in rep), rep[:4]
+    assert sum(a < 2e-3 for _, a, _ in rep) >= 0.9 * len(rep)
