@@ -210,6 +210,25 @@ class Stage2Renderer(_ZTStage2Renderer):
         return torch.is_grad_enabled() and not self.cfg.get("frozen_ior", False) and \
             any(p.requires_grad for m in (self.IORs_pred, self.thickness_pred) for p in m.parameters())
 
+    def _curvature_with_graph(self, x, tri, g_k):
+        """The interpolated Gaussian curvature of the hit as a function of the hit point (DiffRender.py:113-116: the
+        barycentric weights are differentiable w.r.t. the ray, so in the reference the curvature radius of the shell moves
+        with the refracted path).  x [M,3] lies on the plane of triangle tri [M]: its barycentric coordinates are affine in x.
+        Value = the trace's own g_k (straight-through), gradient = that of the interpolation."""
+        if not x.requires_grad:
+            return g_k
+        sc = self.scene
+        f = sc.faces[tri]
+        tv = sc.vertices.float()[f]                                            # [M,3,3]
+        kf = sc.gaussian_curvatures.float()[f].squeeze(-1)                      # [M,3]
+        e1, e2, w = tv[:, 1] - tv[:, 0], tv[:, 2] - tv[:, 0], x - tv[:, 0]
+        d00, d01, d11 = (e1 * e1).sum(-1), (e1 * e2).sum(-1), (e2 * e2).sum(-1)
+        d20, d21 = (w * e1).sum(-1), (w * e2).sum(-1)
+        den = d00 * d11 - d01 * d01
+        u, v = (d11 * d20 - d01 * d21) / den, (d00 * d21 - d01 * d20) / den
+        gk = ((1.0 - u - v) * kf[:, 0] + u * kf[:, 1] + v * kf[:, 2]).reshape(-1, 1)
+        return g_k.detach() + (gk - gk.detach())
+
     @staticmethod
     def _sigmoid_mlp(net, x):
         """IoRNetwork / ThicknessNetwork.forward (field.py:1046-1081) as a differentiable fp32 torch expression on the
@@ -275,6 +294,7 @@ class Stage2Renderer(_ZTStage2Renderer):
             if M > 0 and grad:
                 tri = info["faces_ind"].index_select(0, hit_idx).to(torch.int32).contiguous()
                 x_c, n_c = _HitFn.apply(next_start.index_select(0, hit_idx), d_c, (self.scene, tri, inside, x_c, n_c))
+                g_k = self._curvature_with_graph(x_c, tri.long(), g_k)
                 ior_sig = self._sigmoid_mlp(self.IORs_pred, x_c)
                 th_sig = self._sigmoid_mlp(self.thickness_pred, x_c)
             elif M > 0:

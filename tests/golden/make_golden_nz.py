@@ -167,6 +167,24 @@ def main():
     res2, out2 = trace_record(net2, o, d)
     res2.update(torus_R=np.array(0.55), torus_r=np.array(0.22), torus_nu=np.array(40), torus_nv=np.array(20))
     np.savez_compressed(os.path.join(OUT, "stage2nz_torus_R96.npz"), **res2)
+    # gradients on the torus: the vertex curvatures differ across a triangle there, so the curvature radius of the shell is
+    # itself a function of the refracted path (DiffRender.py:113-116) -- the IoR / thickness gradients contain that term
+    gt = rh.synthetic_targets(96)
+    net2.zero_grad()
+    pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tir_mask = net2.ray_trace(o, d, None)
+    r = net2.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
+                         cos_anneal_ratio=0.2, step=10000, is_train=True, is_nerf=True)
+    tm = tir_mask.detach()
+    loss = net2.compute_rgb_loss(r["ray_rgb"] * tm, gt * tm).mean() + (0.02 * r["gradient_error"]).mean()
+    loss.backward()
+    gres = {"gt": gt.numpy(), "loss": loss.detach().numpy(), "ray_rgb": r["ray_rgb"].detach().numpy()}
+    for name, p_ in net2.named_parameters():
+        if p_.grad is None:
+            continue
+        vals, idx = strided(p_.grad)
+        gres["grad/" + name] = vals
+        gres["gradnorm/" + name] = np.array(p_.grad.double().norm().item())
+    np.savez_compressed(os.path.join(OUT, "stage2nz_torus_grads_R96.npz"), **gres)
     print("torus:", [p.shape for p in out2[0]], [int(c.sum()) for c in out2[1]], int(out2[6].sum()),
           "curvature signs", [(float((res2[f"in_gk_{k}"] >= 0).mean()) if res2[f"in_gk_{k}"].size else None)
                               for k in range(int(res2["n_bounces"]))])

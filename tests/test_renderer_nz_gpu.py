@@ -134,16 +134,24 @@ def test_render_end_to_end_and_bf16(net, golden):
     assert e16 < 2e-2, e16
 
 
-@pytest.mark.parametrize("sph", [False, True])
-def test_parameter_gradients_match_reference(golden, sph):
+@pytest.mark.parametrize("case", ["sphere", "sphere_sph", "torus"])
+def test_parameter_gradients_match_reference(golden, case):
     """Trainer loss backward through the product's own trace (hit kernels, IoR / thickness MLPs, shell geometry) and
     render_core on the sample parameters of the reference's trace, against the reference's autograd: every parameter
     tensor, strided samples relative to the tensor's largest entry and the norm.  Gates: 1e-2 on every tensor, 2e-3 on at
     least 90 % of them (the stage-1 material layers see ~55 surface hits behind ReLU / clamp kinks, cf. the zero-thickness
     test), and the IoR / thickness networks -- whose gradient exists only through the path geometry -- within 5e-3."""
-    G = np.load(os.path.join(GOLDEN, "stage2nz_sph_sphere_R64.npz")) if sph else golden
-    GG = np.load(os.path.join(GOLDEN, "stage2nz_sph_grads_R64.npz" if sph else "stage2nz_grads_R64.npz"))
-    net_ = make_stage2("split", thick=True, sphere_direction=sph).cuda()
+    sph = case == "sphere_sph"
+    if case == "torus":
+        # vertex curvatures differ across a triangle: the shell's curvature radius moves with the refracted path
+        # (Stage2Renderer._curvature_with_graph; DiffRender.py:113-116), third-bounce hits, both curvature signs
+        G = np.load(os.path.join(GOLDEN, "stage2nz_torus_R96.npz"))
+        GG = np.load(os.path.join(GOLDEN, "stage2nz_torus_grads_R96.npz"))
+        net_ = make_stage2("split", mesh=torus(), thick=True).cuda()
+    else:
+        G = np.load(os.path.join(GOLDEN, "stage2nz_sph_sphere_R64.npz")) if sph else golden
+        GG = np.load(os.path.join(GOLDEN, "stage2nz_sph_grads_R64.npz" if sph else "stage2nz_grads_R64.npz"))
+        net_ = make_stage2("split", thick=True, sphere_direction=sph).cuda()
     o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
     # sample parameters of segment 1 as the reference drew them: z = |p - start| / |end - start|
     p1 = torch.from_numpy(G["path_1"]).to(DEV)
@@ -177,7 +185,7 @@ def test_parameter_gradients_match_reference(golden, sph):
         rep.append((name, (g[idx] - ref).abs().max().item() / scale, abs(p.grad.double().norm().item() - ref_norm) / ref_norm))
     rep.sort(key=lambda r: -r[1])
     geo = [r for r in rep if r[0].startswith(("IORs_pred", "thickness_pred"))]
-    print(f"[NZ gradients, split, sphere_direction={sph}] {len(rep)} tensors; worst (name, sampled rel. error, norm rel. error):")
+    print(f"[NZ gradients, split, {case}] {len(rep)} tensors; worst (name, sampled rel. error, norm rel. error):")
     for r in rep[:6]:
         print("   %-60s %.2e %.2e" % r)
     print("   IoR / thickness networks:", [(n_, round(a, 6), round(b, 6)) for n_, a, b in geo])
