@@ -5,7 +5,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function -Xcompiler -Wno-unknown-pragmas $(EXTRA)
 CSRC := nu_nerf_b200/csrc
 OBJDIR := build/obj
-SRCS := gemm.cu linear.cu chain.cu chain_ts.cu probe.cu weights.cu sampling.cu composite.cu field.cu bvh.cu mcubes.cu
+SRCS := gemm.cu linear.cu chain.cu chain_ts.cu probe.cu weights.cu sampling.cu composite.cu field.cu bvh.cu mcubes.cu shell.cu
 OBJS := $(SRCS:%.cu=$(OBJDIR)/%.o)
 LIB := nu_nerf_b200/libnunerf_b200.so
 ORACLE := oracle/_build/liboracle.so

@@ -388,6 +388,28 @@ int nunerf_refract_bounce(const float* x_hit, const float* n_hit, const float* r
                           const int32_t* tri, int N, int inside, float* d_out, float* o_out, uint8_t* pass,
                           void* stream);
 
+/* ------------------------------------------------------------------ non-zero-thickness bounce (network/renderer.py:1690-2009)
+ * One launch per bounce on the M rays that hit the mesh.  The mesh is one face of a glass shell of thickness
+ * 0.01 * thick_sig; at a hit the shell is modelled as two concentric spheres of radius r = 1 / sqrt(max(|g_k|, 1e-6)) and
+ * r -+ thickness (g_k = interpolated vertex Gaussian curvature, DiffRender.py:113-116): refraction into the glass with
+ * ior = 1 / (ior_sig + 0.6) (NZ:1733-1734), chord through the shell, second refraction with (1 / 1.0001) / ior (NZ:1739-1744);
+ * `inside` (the ray leaves the object): the ratios are inverted and swapped (NZ:1753-1756) and the hit is first pulled back
+ * onto the inner face (NZ:1884-1933).  n_signed = unit vertex normal, negated when inside.
+ *   pass[M]   the first refraction is no total internal reflection (ior^2 sin^2 <= 0.999; `converged_out`, NZ:1768)
+ *   tir[M]    pass and neither later refraction was clamped (`tir`, NZ:1773, :1860, :1939, :1993)
+ *   x_mod     the hit point (pulled back when inside); o_next / d_next / ratio: next segment's origin, direction and the
+ *             effective ratio of the first refraction (`ior_ratios`) -- defined on rows with pass = 1
+ * nunerf_shell_bounce_bwd: the reverse (the reference keeps the bounce inside autograd so that IORs_pred AND thickness_pred
+ *   are trained through the path geometry): g_* = d loss / d (o_next, d_next, ratio, x_mod) over all M rows (ignored where
+ *   pass = 0, except g_xmod) -> d loss / d (x_hit, n_signed, rays_d, g_k, ior_sig, thick_sig). */
+int nunerf_shell_bounce(const float* x_hit, const float* n_signed, const float* rays_d, const float* g_k,
+                        const float* ior_sig, const float* thick_sig, int M, int inside, uint8_t* pass, uint8_t* tir,
+                        float* x_mod, float* o_next, float* d_next, float* ratio, void* stream);
+int nunerf_shell_bounce_bwd(const float* x_hit, const float* n_signed, const float* rays_d, const float* g_k,
+                            const float* ior_sig, const float* thick_sig, const uint8_t* pass, int M, int inside,
+                            const float* g_onext, const float* g_dnext, const float* g_ratio, const float* g_xmod,
+                            float* d_x, float* d_n, float* d_d, float* d_gk, float* d_ior, float* d_thick, void* stream);
+
 /* ------------------------------------------------------------------ grid sweep (field.py:1286-1307)
  * grid_points: points start..start+count of the res^3 grid in x-major order (the order of torch.meshgrid 'ij' +
  *   reshape, field.py:1297-1300); lin = the three per-axis torch.linspace tables, [3, res].

@@ -145,6 +145,8 @@ _SIGS = {
     "nunerf_refract_bounce": [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp],
     "nunerf_hit_interp_bwd": [vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp],
     "nunerf_refract_bounce_bwd": [vp, vp, vp, ci, vp, vp, vp, vp, vp, vp, vp],
+    "nunerf_shell_bounce": [vp, vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp],
+    "nunerf_shell_bounce_bwd": [vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp],
     "nunerf_grid_points": [ci, cll, ci, vp, vp, vp],
     "nunerf_grid_mask": [vp, vp, ci, ci, cf, vp, vp],
     "nunerf_mc_count": [vp, ci, cf, vp, vp, vp],

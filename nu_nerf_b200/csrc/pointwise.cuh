@@ -288,6 +288,258 @@ PW_HD void sphere_dir_bwd(const float* p, const float* u, const float* d_q, floa
   }
 }
 
+// ----------------------------------------------------------------------------- non-zero-thickness bounce
+// network/renderer.py:1690-2009 per hit ray (see nu_nerf_b200/shell.py for the derivation and the reference line map): the
+// outer mesh is one face of a glass shell of thickness tau = 0.01 thick_sig, locally two concentric spheres of radius
+// r = 1 / sqrt(|K|) and r -+ tau.  Entering: refract (ratio ior), cross the shell along the chord, refract again (ratio ioo).
+// Leaving: first pull the hit back onto the inner face.  s = -1 / +1 folds the two curvature-sign cases (exact sign factor).
+struct ShellIn { float x[3], n[3], d[3], gk, ior_sig, th_sig; };
+struct ShellOut { int ok, tir; float x_mod[3], start[3], dir[3], ratio; };
+#define PW_SHELL_IOR_INNER (1.0f / 1.0001f)
+
+PW_HD float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+// u = v / (|v| + 1e-4)
+PW_HD float unit4(const float* v, float* u) {
+  float nv = sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  float den = nv + 0.0001f;
+  for (int c = 0; c < 3; ++c) u[c] = v[c] / den;
+  return nv;
+}
+// adjoint of unit4: d_v += (d_u - u (u.d_u) |v| / (|v| + 1e-4)) / (|v| + 1e-4)   [d|v|/dv = v/|v|]
+PW_HD void unit4_bwd(const float* v, float nv, const float* u, const float* d_u, float* d_v) {
+  float den = nv + 0.0001f;
+  float udu = dot3(u, d_u);
+  for (int c = 0; c < 3; ++c) d_v[c] += (d_u[c] - (nv > 0.f ? v[c] / nv : 0.f) * udu) / den;
+}
+
+PW_HD void shell_bounce_fwd(const ShellIn& in, int inside, ShellOut* o) {
+  const float* x = in.x; const float* n = in.n; const float* d = in.d;
+  float cos_i = -dot3(n, d);
+  float sin2_i = 1.0f - cos_i * cos_i;
+  float a = 1.0f / (in.ior_sig * 1.0f + 0.6f);
+  float b = PW_SHELL_IOR_INNER / a;
+  float th = in.th_sig * 0.01f;
+  float ior = inside ? 1.0f / b : a, ioo = inside ? 1.0f / a : b;
+  o->ok = !(ior * ior * sin2_i > 0.999f);
+  o->tir = o->ok;
+  o->ratio = ior;
+  for (int c = 0; c < 3; ++c) { o->x_mod[c] = x[c]; o->start[c] = 0.f; o->dir[c] = 0.f; }
+  if (!o->ok) return;
+  float sin2_t = sin2_i * ior * ior;
+  float r = 1.0f / sqrtf(fmaxf(fabsf(in.gk), 0.000001f));
+  if (r != r) r = 0.1f;
+  float cos_t = sqrtf(fmaxf(1.0f - sin2_t, 0.0001f));
+  float s, x_in[3], n_in[3], d_in[3], v1[3];
+  if (!inside) {
+    s = in.gk >= 0.f ? -1.0f : 1.0f;
+    float k1 = ior * cos_i - sqrtf(fmaxf(1.0f - sin2_t, 0.0001f));
+    for (int c = 0; c < 3; ++c) { v1[c] = ior * d[c] + k1 * n[c]; x_in[c] = x[c]; n_in[c] = n[c]; }
+    unit4(v1, d_in);
+  } else {
+    s = in.gk <= 0.f ? -1.0f : 1.0f;
+    float c_r = r * cos_i;
+    float delta = sqrtf(fmaxf(c_r * c_r + s * (2.0f * r * th) + th * th, 0.0001f));
+    float L1 = fabsf(c_r - delta);
+    float nm[3];
+    for (int c = 0; c < 3; ++c) {
+      float center = x[c] + s * (n[c] * r);
+      x_in[c] = x[c] - L1 * d[c];
+      nm[c] = -s * (x_in[c] - center);
+      o->x_mod[c] = x_in[c];
+    }
+    unit4(nm, n_in);
+    float cos_m = -dot3(n_in, d);
+    float e2 = (1.0f - cos_m * cos_m) * ior * ior;
+    if (e2 > 0.999f) o->tir = 0;
+    float k1 = ior * cos_m - sqrtf(fmaxf(1.0f - fminf(e2, 0.999f), 0.0001f));
+    for (int c = 0; c < 3; ++c) v1[c] = ior * d[c] + k1 * n_in[c];
+    unit4(v1, d_in);
+  }
+  float ctr = r * cos_t;
+  float delta2 = sqrtf(fmaxf(ctr * ctr + s * (2.0f * r * th) + th * th, 0.0001f));
+  float L2 = fabsf(ctr - delta2);
+  float na[3], n_af[3], v3[3];
+  for (int c = 0; c < 3; ++c) {
+    float center = x_in[c] + s * (n_in[c] * r);
+    o->start[c] = x_in[c] + d_in[c] * (L2 + 0.001f);
+    na[c] = -s * (o->start[c] - center);
+  }
+  unit4(na, n_af);
+  float cos_2 = -dot3(n_af, d_in);
+  float e3 = (1.0f - cos_2 * cos_2) * ioo * ioo;
+  if (e3 > 0.999f) o->tir = 0;
+  float k3 = ioo * cos_2 - sqrtf(fmaxf(1.0f - fminf(e3, 0.999f), 0.0001f));
+  for (int c = 0; c < 3; ++c) v3[c] = ioo * d_in[c] + k3 * n_af[c];
+  unit4(v3, o->dir);
+}
+
+// Adjoint of shell_bounce_fwd for a ray with ok = 1: gradients of (start, dir, ratio, x_mod) -> d_in (x, n, d, gk, ior_sig,
+// th_sig); every clamp / abs / min passes the gradient on its active side only, like autograd.
+PW_HD void shell_bounce_bwd(const ShellIn& in, int inside, const float* g_start, const float* g_dir, float g_ratio,
+                            const float* g_xmod, ShellIn* di) {
+  const float* x = in.x; const float* n = in.n; const float* d = in.d;
+  for (int c = 0; c < 3; ++c) { di->x[c] = 0.f; di->n[c] = 0.f; di->d[c] = 0.f; }
+  di->gk = 0.f; di->ior_sig = 0.f; di->th_sig = 0.f;
+  // ---- forward again, keeping the intermediates
+  float cos_i = -dot3(n, d);
+  float sin2_i = 1.0f - cos_i * cos_i;
+  float a = 1.0f / (in.ior_sig * 1.0f + 0.6f);
+  float b = PW_SHELL_IOR_INNER / a;
+  float th = in.th_sig * 0.01f;
+  float ior = inside ? 1.0f / b : a, ioo = inside ? 1.0f / a : b;
+  float sin2_t = sin2_i * ior * ior;
+  float ak = fabsf(in.gk);
+  float r = 1.0f / sqrtf(fmaxf(ak, 0.000001f));
+  float ct_arg = 1.0f - sin2_t;
+  float cos_t = sqrtf(fmaxf(ct_arg, 0.0001f));
+  float s, x_in[3], n_in[3], d_in[3], v1[3], nv1, nm[3] = {0.f, 0.f, 0.f}, nnm = 0.f;
+  float c_r = 0.f, q1 = 0.f, delta1 = 0.f, L1 = 0.f, cos_m = 0.f, e2 = 0.f, k1;
+  if (!inside) {
+    s = in.gk >= 0.f ? -1.0f : 1.0f;
+    k1 = ior * cos_i - cos_t;
+    for (int c = 0; c < 3; ++c) { v1[c] = ior * d[c] + k1 * n[c]; x_in[c] = x[c]; n_in[c] = n[c]; }
+  } else {
+    s = in.gk <= 0.f ? -1.0f : 1.0f;
+    c_r = r * cos_i;
+    q1 = c_r * c_r + s * (2.0f * r * th) + th * th;
+    delta1 = sqrtf(fmaxf(q1, 0.0001f));
+    L1 = fabsf(c_r - delta1);
+    for (int c = 0; c < 3; ++c) {
+      float center = x[c] + s * (n[c] * r);
+      x_in[c] = x[c] - L1 * d[c];
+      nm[c] = -s * (x_in[c] - center);
+    }
+    nnm = unit4(nm, n_in);
+    cos_m = -dot3(n_in, d);
+    e2 = (1.0f - cos_m * cos_m) * ior * ior;
+    k1 = ior * cos_m - sqrtf(fmaxf(1.0f - fminf(e2, 0.999f), 0.0001f));
+    for (int c = 0; c < 3; ++c) v1[c] = ior * d[c] + k1 * n_in[c];
+  }
+  nv1 = unit4(v1, d_in);
+  float ctr = r * cos_t;
+  float q2 = ctr * ctr + s * (2.0f * r * th) + th * th;
+  float delta2 = sqrtf(fmaxf(q2, 0.0001f));
+  float L2 = fabsf(ctr - delta2);
+  float start[3], na[3], n_af[3], v3[3], dirn[3];
+  for (int c = 0; c < 3; ++c) {
+    float center = x_in[c] + s * (n_in[c] * r);
+    start[c] = x_in[c] + d_in[c] * (L2 + 0.001f);
+    na[c] = -s * (start[c] - center);
+  }
+  float nna = unit4(na, n_af);
+  float cos_2 = -dot3(n_af, d_in);
+  float e3 = (1.0f - cos_2 * cos_2) * ioo * ioo;
+  float a3 = 1.0f - fminf(e3, 0.999f);
+  float sq3 = sqrtf(fmaxf(a3, 0.0001f));
+  float k3 = ioo * cos_2 - sq3;
+  for (int c = 0; c < 3; ++c) v3[c] = ioo * d_in[c] + k3 * n_af[c];
+  float nv3 = unit4(v3, dirn);
+  // ---- reverse
+  float d_ior = g_ratio, d_ioo = 0.f, d_r = 0.f, d_th = 0.f, d_cos_t = 0.f, d_cos_i = 0.f;
+  float d_xin[3] = {0.f, 0.f, 0.f}, d_nin[3] = {0.f, 0.f, 0.f}, d_din[3] = {0.f, 0.f, 0.f};
+  float d_v3[3] = {0.f, 0.f, 0.f}, d_naf[3] = {0.f, 0.f, 0.f}, d_start[3];
+  unit4_bwd(v3, nv3, dirn, g_dir, d_v3);
+  // v3 = ioo d_in + k3 n_af
+  float d_k3 = dot3(d_v3, n_af);
+  d_ioo += dot3(d_v3, d_in);
+  for (int c = 0; c < 3; ++c) { d_din[c] += ioo * d_v3[c]; d_naf[c] += k3 * d_v3[c]; }
+  // k3 = ioo cos_2 - sqrt(max(1 - min(e3, .999), 1e-4))
+  d_ioo += d_k3 * cos_2;
+  float d_cos_2 = d_k3 * ioo;
+  float d_e3 = (a3 > 0.0001f && e3 < 0.999f) ? d_k3 * 0.5f / sq3 : 0.f;       // d(-sqrt(1 - e3)) / d e3 = +1 / (2 sqrt)
+  // e3 = (1 - cos_2^2) ioo^2
+  d_cos_2 += d_e3 * (-2.0f * cos_2) * ioo * ioo;
+  d_ioo += d_e3 * (1.0f - cos_2 * cos_2) * 2.0f * ioo;
+  // cos_2 = -(n_af . d_in)
+  for (int c = 0; c < 3; ++c) { d_naf[c] -= d_cos_2 * d_in[c]; d_din[c] -= d_cos_2 * n_af[c]; }
+  // n_af = unit4(na); na = -s (start - center2); center2 = x_in + s n_in r
+  float d_na[3] = {0.f, 0.f, 0.f};
+  unit4_bwd(na, nna, n_af, d_naf, d_na);
+  for (int c = 0; c < 3; ++c) {
+    d_start[c] = g_start[c] - s * d_na[c];
+    float d_center = s * d_na[c];
+    d_xin[c] += d_center;
+    d_nin[c] += d_center * s * r;
+    d_r += d_center * s * n_in[c];
+  }
+  // start = x_in + d_in (L2 + 0.001)
+  float d_L2 = 0.f;
+  for (int c = 0; c < 3; ++c) { d_xin[c] += d_start[c]; d_din[c] += d_start[c] * (L2 + 0.001f); d_L2 += d_start[c] * d_in[c]; }
+  // L2 = |ctr - delta2|; delta2 = sqrt(max(q2, 1e-4)); q2 = ctr^2 + s 2 r th + th^2; ctr = r cos_t
+  float sg2 = (ctr - delta2) > 0.f ? 1.0f : ((ctr - delta2) < 0.f ? -1.0f : 0.f);
+  float d_ctr = d_L2 * sg2, d_delta2 = -d_L2 * sg2;
+  float d_q2 = q2 > 0.0001f ? d_delta2 * 0.5f / delta2 : 0.f;
+  d_ctr += d_q2 * 2.0f * ctr;
+  d_r += d_q2 * s * 2.0f * th;
+  d_th += d_q2 * (s * 2.0f * r + 2.0f * th);
+  d_r += d_ctr * cos_t;
+  d_cos_t += d_ctr * r;
+  // d_in = unit4(v1)
+  float d_v1[3] = {0.f, 0.f, 0.f};
+  unit4_bwd(v1, nv1, d_in, d_din, d_v1);
+  float d_d[3] = {0.f, 0.f, 0.f}, d_n[3] = {0.f, 0.f, 0.f}, d_x[3] = {0.f, 0.f, 0.f};
+  if (!inside) {
+    // v1 = ior d + k1 n, k1 = ior cos_i - cos_t; x_in = x, n_in = n
+    float d_k1 = dot3(d_v1, n);
+    d_ior += dot3(d_v1, d);
+    for (int c = 0; c < 3; ++c) { d_d[c] += ior * d_v1[c]; d_n[c] += k1 * d_v1[c] + d_nin[c]; d_x[c] += d_xin[c] + g_xmod[c]; }
+    d_ior += d_k1 * cos_i;
+    d_cos_i += d_k1 * ior;
+    d_cos_t -= d_k1;
+  } else {
+    // v1 = ior d + k1 n_in, k1 = ior cos_m - sqrt(max(1 - min(e2, .999), 1e-4))
+    float d_k1 = dot3(d_v1, n_in);
+    d_ior += dot3(d_v1, d);
+    for (int c = 0; c < 3; ++c) { d_d[c] += ior * d_v1[c]; d_nin[c] += k1 * d_v1[c]; }
+    d_ior += d_k1 * cos_m;
+    float d_cos_m = d_k1 * ior;
+    float a2 = 1.0f - fminf(e2, 0.999f);
+    float d_e2 = (a2 > 0.0001f && e2 < 0.999f) ? d_k1 * 0.5f / sqrtf(a2) : 0.f;
+    d_cos_m += d_e2 * (-2.0f * cos_m) * ior * ior;
+    d_ior += d_e2 * (1.0f - cos_m * cos_m) * 2.0f * ior;
+    // cos_m = -(n_in . d)
+    for (int c = 0; c < 3; ++c) { d_nin[c] -= d_cos_m * d[c]; d_d[c] -= d_cos_m * n_in[c]; }
+    // n_in = unit4(nm); nm = -s (x_in - center1); center1 = x + s n r; x_in = x - L1 d  (x_mod = x_in)
+    float d_nm[3] = {0.f, 0.f, 0.f};
+    unit4_bwd(nm, nnm, n_in, d_nin, d_nm);
+    float d_L1 = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      float d_xi = d_xin[c] + g_xmod[c] - s * d_nm[c];
+      float d_center = s * d_nm[c];
+      d_x[c] += d_xi + d_center;
+      d_d[c] -= d_xi * L1;
+      d_L1 -= d_xi * d[c];
+      d_n[c] += d_center * s * r;
+      d_r += d_center * s * n[c];
+    }
+    // L1 = |c_r - delta1|; delta1 = sqrt(max(q1, 1e-4)); q1 = c_r^2 + s 2 r th + th^2; c_r = r cos_i
+    float sg1 = (c_r - delta1) > 0.f ? 1.0f : ((c_r - delta1) < 0.f ? -1.0f : 0.f);
+    float d_cr = d_L1 * sg1, d_delta1 = -d_L1 * sg1;
+    float d_q1 = q1 > 0.0001f ? d_delta1 * 0.5f / delta1 : 0.f;
+    d_cr += d_q1 * 2.0f * c_r;
+    d_r += d_q1 * s * 2.0f * th;
+    d_th += d_q1 * (s * 2.0f * r + 2.0f * th);
+    d_r += d_cr * cos_i;
+    d_cos_i += d_cr * r;
+  }
+  // cos_t = sqrt(max(1 - sin2_t, 1e-4)); sin2_t = sin2_i ior^2; sin2_i = 1 - cos_i^2; cos_i = -(n . d)
+  float d_sin2_t = ct_arg > 0.0001f ? -d_cos_t * 0.5f / cos_t : 0.f;
+  float d_sin2_i = d_sin2_t * ior * ior;
+  d_ior += d_sin2_t * sin2_i * 2.0f * ior;
+  d_cos_i += d_sin2_i * (-2.0f * cos_i);
+  for (int c = 0; c < 3; ++c) { d_n[c] -= d_cos_i * d[c]; d_d[c] -= d_cos_i * n[c]; }
+  // r = 1 / sqrt(max(|gk|, 1e-6))
+  if (ak > 0.000001f) di->gk = d_r * (-0.5f) * r / ak * (in.gk > 0.f ? 1.0f : -1.0f);
+  // ior / ioo -> a, b -> ior_sig;  a = 1 / (sig + 0.6), b = IOR_INNER / a
+  float d_a, d_b;
+  if (inside) { d_b = -d_ior / (b * b); d_a = -d_ioo / (a * a); }
+  else { d_a = d_ior; d_b = d_ioo; }
+  d_a += d_b * (-PW_SHELL_IOR_INNER / (a * a));
+  di->ior_sig = d_a * (-a * a);
+  di->th_sig = d_th * 0.01f;
+  for (int c = 0; c < 3; ++c) { di->x[c] = d_x[c]; di->n[c] = d_n[c]; di->d[c] = d_d[c]; }
+}
+
 // ----------------------------------------------------------------------------- FG LUT (dr.texture linear/clamp)
 PW_HD void fg_lookup(const float* lut, float u, float v, float* fg, float* dfg_du, float* dfg_dv) {
   const int W = 256, H = 256;

@@ -19,9 +19,9 @@ What differs from the zero-thickness classes (renderer_zerothick.py / renderer_s
     IoR = 1 / (IORs_pred + 0.6), ThicknessNetwork * 0.01, retro-active un-convergence of rays that miss the mesh from the
     inside (NZ:1662-1672), 64 / 128 (64 + 2 x 32 SDF-guided) / 64 samples per segment, 64 inverse-depth samples for rays
     that leave the scene (NZ:2140-2143).  Kernels: BVH closest hit + re-intersection, IoR / thickness MLPs, inner-SDF
-    queries + up-sampling rounds, path points.  The closed-form bounce itself runs as torch expressions on the [M, .]
-    tensors of the hit rays (M <= rays per bounce; ~1 % of a step) so that the loss reaches IORs_pred AND thickness_pred
-    through it.
+    queries + up-sampling rounds, path points, and the closed-form bounce itself (csrc/shell.cu: one launch per bounce
+    forward, one backward -- the hand-derived adjoint, so that the loss reaches IORs_pred AND thickness_pred through it;
+    shell.shell_bounce, the torch restatement, is the cross-check: cfg['shell_impl'] = 'torch').
   * the inner field's shader is AppShadingNetwork_SpecInner (field.py:1320: PE-8 positions, PE-2 refraction inputs,
     refraction light clamped at exp(-0.2)) -- shade_encode_*_var_kernel<8, 2, .>, exp_max_refrac of the mixing kernels.
   * render_core (NZ:2155-2353): surface shading flagged `inner` for every segment but the first (NZ:2244), `loss_occ` key.
@@ -41,6 +41,55 @@ from .field import (SDFNetwork, SingleVarianceNetwork, NeRFNetwork, AppShadingNe
 from .renderer_stage2 import Stage2Renderer as _ZTStage2Renderer, _HitFn, _engine
 from .renderer_zerothick import NeROShapeRenderer as _ZTShapeRenderer, load_cfg, linear_to_srgb, _SdfValueFn
 from .shell import shell_bounce, signed_normal, outside_depths
+
+
+class _ShellFn(torch.autograd.Function):
+    """The non-zero-thickness bounce (NZ:1690-2009) on the M hit rays as ONE launch forward (`shell_bounce_fwd_kernel`) and
+    one backward (`shell_bounce_bwd_kernel`, the hand-derived adjoint; csrc/shell.cu, pointwise.cuh).  The torch
+    restatement nu_nerf_b200/shell.shell_bounce is its cross-check (cfg['shell_impl'] = 'torch')."""
+
+    @staticmethod
+    def forward(ctx, x, n, d, gk, ior_sig, th_sig, inside):
+        eng = _engine()
+        c = lambda t: t.detach().contiguous().float()
+        x, n, d, gk, ior_sig, th_sig = c(x), c(n), c(d), c(gk), c(ior_sig), c(th_sig)
+        M, dev = x.shape[0], x.device
+        ok, tir = (torch.empty(M, dtype=torch.uint8, device=dev) for _ in range(2))
+        x_mod, start, dirn = (torch.empty(M, 3, device=dev) for _ in range(3))
+        ratio = torch.empty(M, device=dev)
+        eng.call("nunerf_shell_bounce", x.data_ptr(), n.data_ptr(), d.data_ptr(), gk.data_ptr(), ior_sig.data_ptr(),
+                 th_sig.data_ptr(), M, int(inside), ok.data_ptr(), tir.data_ptr(), x_mod.data_ptr(), start.data_ptr(),
+                 dirn.data_ptr(), ratio.data_ptr())
+        ctx.save_for_backward(x, n, d, gk, ior_sig, th_sig, ok)
+        ctx.inside = bool(inside)
+        ctx.mark_non_differentiable(ok, tir)
+        return ok, tir, x_mod, start, dirn, ratio
+
+    @staticmethod
+    def backward(ctx, _g_ok, _g_tir, g_xmod, g_start, g_dir, g_ratio):
+        eng = _engine()
+        x, n, d, gk, ior_sig, th_sig, ok = ctx.saved_tensors
+        M, dev = x.shape[0], x.device
+        z = lambda g, *shape: torch.zeros(*shape, device=dev) if g is None else g.contiguous().float()
+        g_xmod, g_start, g_dir, g_ratio = z(g_xmod, M, 3), z(g_start, M, 3), z(g_dir, M, 3), z(g_ratio, M)
+        d_x, d_n, d_d = (torch.empty(M, 3, device=dev) for _ in range(3))
+        d_gk, d_ior, d_th = (torch.empty(M, device=dev) for _ in range(3))
+        eng.call("nunerf_shell_bounce_bwd", x.data_ptr(), n.data_ptr(), d.data_ptr(), gk.data_ptr(), ior_sig.data_ptr(),
+                 th_sig.data_ptr(), ok.data_ptr(), M, int(ctx.inside), g_start.data_ptr(), g_dir.data_ptr(),
+                 g_ratio.data_ptr(), g_xmod.data_ptr(), d_x.data_ptr(), d_n.data_ptr(), d_d.data_ptr(), d_gk.data_ptr(),
+                 d_ior.data_ptr(), d_th.data_ptr())
+        return d_x, d_n, d_d, d_gk.reshape(gk.shape), d_ior.reshape(ior_sig.shape), d_th.reshape(th_sig.shape), None
+
+
+def shell_bounce_kernels(x, normal, d, g_k, ior_sig, thick_sig, inside):
+    """shell.shell_bounce with the bounce on the device kernels: same arguments, same result dict."""
+    ok, tir, x_mod, start, dirn, ratio = _ShellFn.apply(x, normal, d, g_k.reshape(-1), ior_sig.reshape(-1),
+                                                        thick_sig.reshape(-1), inside)
+    ok = ok.bool()
+    ok_idx = ok.nonzero().squeeze(1)
+    return {"ok": ok, "ok_idx": ok_idx, "tir": tir.bool(), "x_mod": x_mod, "normal": normal.index_select(0, ok_idx),
+            "ratio": ratio.index_select(0, ok_idx).reshape(-1, 1), "start": start.index_select(0, ok_idx),
+            "dir": dirn.index_select(0, ok_idx)}
 
 
 class _RenderCoreNZFn(torch.autograd.Function):
@@ -303,7 +352,10 @@ class Stage2Renderer(_ZTStage2Renderer):
                     th_sig = eng.ior_forward(wth, x_c).reshape(-1, 1)
             else:
                 ior_sig = th_sig = torch.zeros(0, 1, device=dev)
-            b = shell_bounce(x_c, n_c, d_c, g_k, ior_sig, th_sig, inside)
+            if M > 0 and x_c.is_cuda and self.cfg.get("shell_impl", "kernels") == "kernels":
+                b = shell_bounce_kernels(x_c, n_c, d_c, g_k, ior_sig, th_sig, inside)        # one launch (csrc/shell.cu)
+            else:
+                b = shell_bounce(x_c, n_c, d_c, g_k, ior_sig, th_sig, inside)                # torch restatement (cross-check)
             ok_idx = b["ok_idx"]
             converged_out = torch.zeros(N, 1, dtype=torch.bool, device=dev)
             converged_out[hit_idx[ok_idx]] = True

@@ -1,0 +1,33 @@
+// TEST INFRASTRUCTURE ONLY -- host build of pw::shell_bounce_fwd / _bwd (nu_nerf_b200/csrc/pointwise.cuh, the source the CUDA
+// kernels of csrc/shell.cu compile) behind a C ABI for ctypes: tests/test_shell_cpu.py checks it against the torch
+// restatement nu_nerf_b200/shell.py (pinned to the unmodified reference) and against its autograd.
+#include <cmath>
+#include <cstdint>
+#include "pointwise.cuh"
+using namespace nunerf;
+extern "C" void shell_fwd(const float* in, int M, int inside, float* out) {      // in [M,12], out [M,12]
+  for (int m = 0; m < M; ++m) {
+    pw::ShellIn a; pw::ShellOut o;
+    const float* p = in + 12 * m;
+    for (int c = 0; c < 3; ++c) { a.x[c] = p[c]; a.n[c] = p[3 + c]; a.d[c] = p[6 + c]; }
+    a.gk = p[9]; a.ior_sig = p[10]; a.th_sig = p[11];
+    pw::shell_bounce_fwd(a, inside, &o);
+    float* q = out + 12 * m;
+    q[0] = (float)o.ok; q[1] = (float)o.tir;
+    for (int c = 0; c < 3; ++c) { q[2 + c] = o.x_mod[c]; q[5 + c] = o.start[c]; q[8 + c] = o.dir[c]; }
+    q[11] = o.ratio;
+  }
+}
+extern "C" void shell_bwd(const float* in, int M, int inside, const float* g, float* din) {   // g [M,10]: start, dir, ratio, xmod
+  for (int m = 0; m < M; ++m) {
+    pw::ShellIn a, d;
+    const float* p = in + 12 * m;
+    for (int c = 0; c < 3; ++c) { a.x[c] = p[c]; a.n[c] = p[3 + c]; a.d[c] = p[6 + c]; }
+    a.gk = p[9]; a.ior_sig = p[10]; a.th_sig = p[11];
+    const float* gg = g + 10 * m;
+    pw::shell_bounce_bwd(a, inside, gg, gg + 3, gg[6], gg + 7, &d);
+    float* q = din + 12 * m;
+    for (int c = 0; c < 3; ++c) { q[c] = d.x[c]; q[3 + c] = d.n[c]; q[6 + c] = d.d[c]; }
+    q[9] = d.gk; q[10] = d.ior_sig; q[11] = d.th_sig;
+  }
+}

@@ -273,3 +273,33 @@ def test_stage1_train_step_adds_loss_mask():
     assert out["loss_normal"].shape == (64, 1) and "loss_rgb" in out
     (out["loss_mask"] + out["loss_normal"].mean()).backward()
     assert net.sdf_network.lin0.weight_v.grad is not None and net.sdf_network.lin0.weight_v.grad.abs().sum().item() > 0
+
+
+def test_shell_kernels_match_the_torch_restatement():
+    """csrc/shell.cu (one launch per bounce, hand-derived adjoint) against nu_nerf_b200/shell.shell_bounce and its autograd
+    on the reference's recorded bounce inputs (torus: entering, leaving, re-entering; both curvature signs)."""
+    from nu_nerf_b200.renderer import shell_bounce_kernels
+    from nu_nerf_b200.shell import shell_bounce, signed_normal
+    G = np.load(os.path.join(GOLDEN, "stage2nz_torus_R96.npz"))
+    T = lambda k: torch.from_numpy(G[k]).to(DEV)
+    for k in range(int(G["n_bounces"])):
+        idx = T(f"in_hit_{k}").bool().flatten().nonzero().squeeze(1)
+        if idx.numel() == 0:
+            continue
+        inside = k % 2 == 1
+        base = [T(f"in_x_{k}"), signed_normal(T(f"in_n_{k}"), inside), T(f"in_d_{k}")[idx], T(f"in_gk_{k}").reshape(-1, 1),
+                T(f"in_ior_{k}").reshape(-1, 1), T(f"in_thick_{k}").reshape(-1, 1)]
+        res = []
+        for fn in (shell_bounce_kernels, shell_bounce):
+            leaves = [t.clone().float().requires_grad_(True) for t in base]
+            b = fn(*leaves, inside)
+            gen = torch.Generator().manual_seed(k)
+            cot = {key: torch.randn(b[key].shape, generator=gen).to(DEV) for key in ("start", "dir", "ratio", "x_mod", "normal")}
+            sum((b[key] * cot[key]).sum() for key in cot).backward()
+            res.append((b, [t.grad for t in leaves]))
+        (bk, gk_), (bt, gt_) = res
+        assert torch.equal(bk["ok"], bt["ok"]) and torch.equal(bk["tir"], bt["tir"]) and torch.equal(bk["ok_idx"], bt["ok_idx"])
+        for key in ("start", "dir", "ratio", "x_mod", "normal"):
+            assert (bk[key] - bt[key]).abs().max().item() <= 2e-6, (k, key)
+        for a, b_ in zip(gk_, gt_):
+            assert (a - b_).abs().max().item() <= 2e-5 * max(b_.abs().max().item(), 1e-12), k
