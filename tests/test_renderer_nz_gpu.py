@@ -301,5 +301,7 @@ def test_shell_kernels_match_the_torch_restatement():
         assert torch.equal(bk["ok"], bt["ok"]) and torch.equal(bk["tir"], bt["tir"]) and torch.equal(bk["ok_idx"], bt["ok_idx"])
         for key in ("start", "dir", "ratio", "x_mod", "normal"):
             assert (bk[key] - bt[key]).abs().max().item() <= 2e-6, (k, key)
-        for a, b_ in zip(gk_, gt_):
-            assert (a - b_).abs().max().item() <= 2e-5 * max(b_.abs().max().item(), 1e-12), k
+        # (the curvature gradient is a sum of chord terms that cancel to ~1e-2 of their size: 5e-4 there, fp32 on both sides)
+        for j, (a, b_) in enumerate(zip(gk_, gt_)):
+            tol = 5e-4 if j == 3 else 2e-5
+            assert (a - b_).abs().max().item() <= tol * max(b_.abs().max().item(), 1e-12), (k, j)

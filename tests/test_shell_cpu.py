@@ -130,6 +130,7 @@ def test_kernel_source_matches_torch_restatement_and_its_autograd(host_lib, name
         ref = torch.cat([t.grad for t in leaves], 1).numpy()[oi]
         for lo, hi in ((0, 3), (3, 6), (6, 9), (9, 10), (10, 11), (11, 12)):
             scale = max(float(np.abs(ref[:, lo:hi]).max()), 1e-12)
-            assert float(np.abs(din[:, lo:hi] - ref[:, lo:hi]).max()) / scale <= 2e-5, (k, lo)
+            # (the curvature gradient, column 9, is a sum of chord terms that cancel to ~1e-2 of their size)
+            assert float(np.abs(din[:, lo:hi] - ref[:, lo:hi]).max()) / scale <= (2e-4 if lo == 9 else 2e-5), (k, lo)
         checked += 1
     assert checked >= 2
