@@ -11,6 +11,7 @@ python bench.py --step 20000 --no-cpu-baseline --no-subrecords > $out/${tag}_ben
 python bench.py --rays-per-gpu 32768 --chunk 8192 --no-cpu-baseline --no-subrecords > $out/${tag}_bench_config3_32768rays_1gpu.json 2>> $out/${tag}_bench.err
 python tools/bench_hbm_kernels.py > $out/${tag}_hbm_kernels_32768rays.json 2> $out/${tag}_hbm.err
 python tools/bench_stage2.py > $out/${tag}_stage2_config4.json 2> $out/${tag}_stage2.err
+python tools/bench_stage2.py 4096 --thick > $out/${tag}_stage2_nonzero_thickness.json 2>> $out/${tag}_stage2.err
 python tools/bench_sweep.py 512 > $out/${tag}_config5_sweep512_evalrender.json 2> $out/${tag}_sweep.err
 # ncu: launch list of the bench step, then one --set full capture of the HBM-side kernels and the marching-cubes kernels
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/${tag}_launches.csv \
