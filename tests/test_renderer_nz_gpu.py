@@ -305,3 +305,50 @@ def test_shell_kernels_match_the_torch_restatement():
         for j, (a, b_) in enumerate(zip(gk_, gt_)):
             tol = 5e-4 if j == 3 else 2e-5
             assert (a - b_).abs().max().item() <= tol * max(b_.abs().max().item(), 1e-12), (k, j)
+
+
+def test_edge_cases_all_rays_miss_single_ray_and_forward(net):
+    """Ragged path lists of the non-zero-thickness trace: a batch whose rays all miss the outer mesh (one background segment
+    of 64 inverse-depth samples, no bounce), a batch of one ray through the centre (three segments: 64 / 128 / 64 samples),
+    and forward({'step'}) / forward({'eval'}) through attached sources with the reference's masks (NZ:1297-1299, :1364)."""
+    from nu_nerf_b200 import feeder
+    o_miss = torch.tensor([[3.0, 0.0, 0.0], [3.0, 0.1, 0.0], [0.0, 3.0, 0.2]], device=DEV)
+    d_miss = torch.nn.functional.normalize(torch.tensor([[0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 0.0, 0.0]], device=DEV), dim=-1)
+    o_one = torch.tensor([[0.0, 0.0, 3.0]], device=DEV)
+    d_one = torch.tensor([[0.0, 0.0, -1.0]], device=DEV)
+    for name, o, d, shapes in (("all miss", o_miss, d_miss, [64]), ("single ray", o_one, d_one, [64, 128, 64])):
+        with torch.no_grad():
+            lists = net.ray_trace(o, d, None)
+        assert [p.shape[1] for p in lists[0]] == shapes, (name, [p.shape for p in lists[0]])
+        net.zero_grad()
+        out = net.render(o, d, None, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+        assert out["ray_rgb"].shape == (o.shape[0], 3) and torch.isfinite(out["ray_rgb"]).all(), name
+        assert out["tir_mask"].shape == (o.shape[0], 1) and out["loss_occ"].shape == (1,)
+        (out["ray_rgb"].sum() + (0.02 * out["gradient_error"]).mean()).backward()
+        g = net.stage1_network.outer_nerf.pts_linears[0].weight.grad
+        assert g is not None and torch.isfinite(g).all(), name
+        if name == "single ray":
+            gi = net.thickness_pred.module0[0].weight_v.grad
+            assert gi is not None and torch.isfinite(gi).all() and gi.abs().sum().item() > 0
+    # train forward with a foreground mask: masked rays drop out of loss_rgb
+    G = np.load(os.path.join(GOLDEN, "stage2nz_sphere_R64.npz"))
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    gt = torch.rand(64, 3, device=DEV)
+    masks = (torch.arange(64, device=DEV) % 2).float()
+    net.set_ray_source(lambda step, n: {"rays_o": o, "rays_d": d, "rgbs": gt, "masks": masks})
+    net.cfg["train_ray_num"] = 64
+    out = net({"step": 10000})
+    tm = out["tir_mask"].float() * masks[:, None]
+    ref = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm)
+    assert out["loss_rgb"].shape == (64,) and (out["loss_rgb"] - ref).abs().max().item() < 1e-7
+    assert abs(out["loss_rgb"][0].item() - 0.001 ** 0.5) < 1e-6                 # a masked ray: sqrt(0 + 0.001)
+    # eval forward
+    h, w = 4, 6
+    imgs = torch.rand(1, 3, h, w, generator=torch.Generator().manual_seed(2)).to(DEV)
+    K = torch.tensor([[12.0, 0, 3.0], [0, 12.0, 2.0], [0, 0, 1]])[None].to(DEV)
+    c2w = torch.eye(3, 4)[None].clone()
+    c2w[0, 2, 3] = 3.0
+    net.set_eval_source(feeder.image_eval_source(imgs, K, c2w.to(DEV), is_nerf=True))
+    out = net({"eval": True, "index": 0, "step": 10000})
+    assert out["ray_rgb"].shape == (h, w, 3) and out["gt_rgb"].shape == (h, w, 3) and out["loss_rgb"].shape == (h * w,)
+    assert torch.isfinite(out["ray_rgb"]).all()
