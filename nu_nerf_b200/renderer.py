@@ -28,8 +28,8 @@ What differs from the zero-thickness classes (renderer_zerothick.py / renderer_s
   * render(rays_o, rays_d, mask, near, far, ...) (NZ:1482) and the masked losses of train_step / test_step (NZ:1297-1299,
     :1364).
   both: shader_config.sphere_direction (field.py:594-597, :641-651, :675-680; every zero_thickness: False config sets it).
-Not built (raises NotImplementedError): the human_light shader variant and the inner-field occlusion loss of stage 2
-(NZ:2222-2230; the reference's configs of this renderer all set apply_occ_loss: false).
+  * the occlusion-probe loss of the inner field (NZ:2222-2230, :1580-1608) on the stage-1 probe machinery.
+Not built (raises NotImplementedError): the human_light shader variant (no config of the reference sets it).
 """
 import numpy as np
 import torch
@@ -38,7 +38,7 @@ import torch.nn.functional as F
 
 from .field import (SDFNetwork, SingleVarianceNetwork, NeRFNetwork, AppShadingNetwork_SpecInner, AppShadingNetwork_S2,
                     IoRNetwork, ThicknessNetwork)
-from .renderer_stage2 import Stage2Renderer as _ZTStage2Renderer, _HitFn, _engine
+from .renderer_stage2 import Stage2Renderer as _ZTStage2Renderer, _HitFn, _engine, _zf
 from .renderer_zerothick import NeROShapeRenderer as _ZTShapeRenderer, load_cfg, linear_to_srgb, _SdfValueFn
 from .shell import shell_bounce, signed_normal, outside_depths
 
@@ -90,6 +90,51 @@ def shell_bounce_kernels(x, normal, d, g_k, ior_sig, thick_sig, inside):
     return {"ok": ok, "ok_idx": ok_idx, "tir": tir.bool(), "x_mod": x_mod, "normal": normal.index_select(0, ok_idx),
             "ratio": ratio.index_select(0, ok_idx).reshape(-1, 1), "start": start.index_select(0, ok_idx),
             "dir": dirn.index_select(0, ok_idx)}
+
+
+class _InnerOccFn(torch.autograd.Function):
+    """renderer_stage2._InnerFn with the outputs the inner-field occlusion loss reads (NZ:2222-2230): the predicted
+    occlusion probability (differentiable) and, without a graph, the samples' points, SDF values, SDF gradients, ray
+    directions and reflected directions."""
+
+    @staticmethod
+    def forward(ctx, pack, inv_s, pts, dirs, dists, *params):
+        eng = _engine()
+        w, cos_anneal, exp_max, want_inv_s = pack
+        t = eng.inner_tape(pts, dirs, dists, cos_anneal, exp_max)
+        eng.inner_forward(w, t)
+        ctx.w, ctx.tape, ctx.n, ctx.want_inv_s = w, t, len(params), want_inv_s
+        aux = (t.pts_in, t.sdf.sdf[:, 0], t.sdf.grad, t.dirs_in, t.refl)
+        ctx.mark_non_differentiable(*aux)
+        return (t.a_in, t.c_in, t.gerr, t.occ[:, None]) + aux
+
+    @staticmethod
+    def backward(ctx, d_alpha, d_color, d_gerr, d_occ, *_unused):
+        eng = _engine()
+        w, t = ctx.w, ctx.tape
+        dev, M = t.pts_in.device, t.n_in
+        geo = any(ctx.needs_input_grad[2:5])
+        w.bank.zero_grads()
+        g = eng.inner_backward(w, t, _zf(d_alpha, dev, M), _zf(d_color, dev, M, 3), _zf(d_gerr, dev, M), None, None,
+                               ctx.want_inv_s, d_occ=None if d_occ is None else d_occ.contiguous().float().reshape(-1),
+                               want_geo=geo)
+        w.bank.backward()
+        ctx.tape = None
+        d_inv = g["inv_s"].reshape(()) if ctx.want_inv_s and "inv_s" in g else None
+        return (None, d_inv, g.get("d_pts"), g.get("d_dirs"), g.get("d_dists")) + (None,) * ctx.n
+
+
+class _InnerOccAdapter:
+    """compute_occ_loss / occ_probability of the stage-1 class (ZT:695-723 == NZ:1580-1608, field.py:501-554) bound to the
+    INNER field of stage 2: `sdf_inter_fun` = sdf_network_inner.sdf, `deviation_network_inner` (NZ:1025, :1596)."""
+    compute_occ_loss = _ZTShapeRenderer.compute_occ_loss
+    occ_probability = _ZTShapeRenderer.occ_probability
+
+    def __init__(self, r):
+        self.cfg, self.deviation_network = r.cfg, r.deviation_network_inner
+
+    def _prepare(self):
+        raise RuntimeError("the inner-field occlusion loss is always called with prepared operands")
 
 
 class _RenderCoreNZFn(torch.autograd.Function):
@@ -419,15 +464,27 @@ class Stage2Renderer(_ZTStage2Renderer):
         return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
 
     # ------------------------------------------------------------------ NZ:2155-2353
+    def _eval_inner(self, pack, inv_s, pts, dirs, dists, params, step, is_train):
+        """With apply_occ_loss from occ_loss_step on: the occlusion-probe loss of the inner field (NZ:2222-2230,
+        :1580-1608), on the stage-1 machinery (fused SDF query + probe kernel) with the inner operands."""
+        if not (self.cfg["apply_occ_loss"] and step is not None and step >= self.cfg["occ_loss_step"]):
+            return super()._eval_inner(pack, inv_s, pts, dirs, dists, params, step, is_train)
+        a_i, c_i, gerr, occ, pts_in, sdf_in, grad_in, dirs_in, refl_in = _InnerOccFn.apply(pack, inv_s, pts, dirs, dists,
+                                                                                          *params)
+        self._loss_occ = _InnerOccAdapter(self).compute_occ_loss({"occ_prob": occ, "reflective": refl_in}, pts_in, sdf_in,
+                                                                 grad_in, dirs_in, step, prepared=pack[0],
+                                                                 perm=getattr(self, "_occ_perm", None))
+        return a_i, c_i, gerr
+
     def render_core(self, rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
                     human_poses=None, cos_anneal_ratio=0.0, step=None, is_train=True, is_nerf=False, prepared=None):
-        if self.cfg["apply_occ_loss"] and is_train and step is not None and step >= self.cfg["occ_loss_step"]:
-            raise NotImplementedError("non-zero-thickness stage 2: the inner-field occlusion loss (NZ:2222-2230) is not "
-                                      "built; set apply_occ_loss: false (as the reference's configs of this renderer do)")
+        self._loss_occ = None
         out = super().render_core(rays_o, rays_d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios,
                                   human_poses, cos_anneal_ratio=cos_anneal_ratio, step=step, is_train=is_train,
                                   is_nerf=is_nerf, prepared=prepared)
-        out["loss_occ"] = torch.zeros(1, device=rays_o.device)            # NZ:1584-1585 before occ_loss_step / disabled
+        # zeros(1) before occ_loss_step / when disabled / without inner samples (NZ:1584-1585, :2227-2230)
+        out["loss_occ"] = self._loss_occ if self._loss_occ is not None else torch.zeros(1, device=rays_o.device)
+        self._loss_occ = None
         return out
 
     # ------------------------------------------------------------------ NZ:1482-1506

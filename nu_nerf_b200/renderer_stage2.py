@@ -576,6 +576,10 @@ class Stage2Renderer(nn.Module):
             self._geo_debug = dict(pathes=new_pathes, directions=new_dirs, gradient_mesh=new_gm)
         return new_pathes, new_dirs, new_gm
 
+    def _eval_inner(self, pack, inv_s, pts, dirs, dists, params, step, is_train):
+        """Inner SDF field + inner shading on the compact inner samples of segment 1 -> (alpha, colour, eikonal term)."""
+        return _InnerFn.apply(pack, inv_s, pts, dirs, dists, *params)
+
     @staticmethod
     def _hit_from_inside(i):
         """The `inner` flag of the surface shader at the hits of segment i (ZT:1915: i % 2 != 0)."""
@@ -638,9 +642,10 @@ class Stage2Renderer(nn.Module):
             if i == 1 and inner_idx.numel() > 0:
                 # inner SDF field + inner shading on segment 1 (ZT:1883-1906)
                 inv_s = torch.exp(self.deviation_network_inner.variance * 10.0)
-                a_i, c_i, gerr = _InnerFn.apply((wi, float(cos_anneal_ratio), exp_maxi, not frozen), inv_s,
-                                                pts_f.index_select(0, inner_idx), dirs_i.index_select(0, ray_of(inner_idx)),
-                                                dists_f.index_select(0, inner_idx), *p_in)
+                a_i, c_i, gerr = self._eval_inner((wi, float(cos_anneal_ratio), exp_maxi, not frozen), inv_s,
+                                                  pts_f.index_select(0, inner_idx),
+                                                  dirs_i.index_select(0, ray_of(inner_idx)),
+                                                  dists_f.index_select(0, inner_idx), p_in, step, is_train)
                 alpha = alpha.index_put((inner_idx,), a_i)
                 color = color.index_put((inner_idx,), c_i)
                 inv_s_c = inv_s.clip(1e-6, 1e6)

@@ -98,6 +98,24 @@ def sphere_case(tag, sphere_direction):
                                 cos_anneal_ratio=0.2, step=10000, is_train=is_train, is_nerf=True)
             for kk, v in r.items():
                 res[f"{mode}_{kk}"] = v.detach().float().numpy()
+    if not sphere_direction:
+        # step 20000: the occlusion-probe loss of the INNER field (NZ:2222-2230, :1580-1608); occ_sdf_thresh widened so that
+        # a random-init field has candidates (|sdf| < 0.01 selects almost nothing there), no randperm sub-sampling
+        net.cfg["occ_sdf_thresh"], net.cfg["occ_loss_max_pn"] = 0.05, 1 << 20
+        net.zero_grad()
+        r20 = net.render_core(o, d, pathes, converges, directions, infinity_bkgr, gradient_mesh, ior_ratios, None,
+                              cos_anneal_ratio=0.2, step=20000, is_train=True, is_nerf=True)
+        res["occ20_loss_occ"] = r20["loss_occ"].detach().reshape(-1).numpy()
+        res["occ20_ray_rgb"] = r20["ray_rgb"].detach().numpy()
+        r20["loss_occ"].mean().backward()
+        n_g = 0
+        for name, p_ in net.named_parameters():
+            if p_.grad is not None and float(p_.grad.abs().sum()) > 0:
+                vals, idx = strided(p_.grad)
+                res["occ20_grad/" + name], res["occ20_gradnorm/" + name] = vals, np.array(p_.grad.double().norm().item())
+                n_g += 1
+        print("inner occlusion loss at step 20000:", res["occ20_loss_occ"], "tensors with a gradient:", n_g)
+        net.cfg["occ_sdf_thresh"], net.cfg["occ_loss_max_pn"] = 0.01, 2048
     np.savez_compressed(os.path.join(OUT, f"stage2nz{tag}_sphere_R64.npz"), **res)
     # ---- gradients of the stage-2 trainer loss through ray_trace + render_core (autograd of the reference): the IoR AND
     # the thickness network receive theirs through the shell geometry

@@ -352,3 +352,41 @@ def test_edge_cases_all_rays_miss_single_ray_and_forward(net):
     out = net({"eval": True, "index": 0, "step": 10000})
     assert out["ray_rgb"].shape == (h, w, 3) and out["gt_rgb"].shape == (h, w, 3) and out["loss_rgb"].shape == (h * w,)
     assert torch.isfinite(out["ray_rgb"]).all()
+
+
+def test_inner_field_occlusion_loss_matches_reference(golden):
+    """NZ:2222-2230, :1580-1608 at step 20000: the occlusion-probe loss of the INNER field (predicted occlusion probability
+    of color_network_inner against the hit probability of a 64 + 16 sample probe of sdf_network_inner along the reflected
+    ray).  The probe goes through two CDF inversions: loss within 2e-3 relative (the stage-1 gate); its gradient reaches the
+    inner_weight predictor only (12 tensors): norms within 1e-2, strided samples within 1e-2 of the largest entry."""
+    G = golden
+    net_ = make_stage2("split", thick=True).cuda()
+    net_.cfg["occ_sdf_thresh"], net_.cfg["occ_loss_max_pn"] = 0.05, 1 << 20          # as in make_golden_nz.py
+    net_._occ_perm = torch.arange(1)              # the reference's exact (non sync-free) selection path; no sub-sampling here
+    o, d = torch.from_numpy(G["o"]).to(DEV), torch.from_numpy(G["d"]).to(DEV)
+    pathes, converges, directions, iors, bkgr, nmesh = _lists(G)
+    net_.zero_grad()
+    out = net_.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2, step=20000,
+                           is_train=True, is_nerf=True)
+    ref = float(G["occ20_loss_occ"][0])
+    got = out["loss_occ"].mean().item()
+    print(f"[NZ inner occlusion loss] {got:.6f} vs reference {ref:.6f}")
+    assert ref > 1e-3 and abs(got - ref) < 2e-3 * ref + 1e-5, (got, ref)
+    assert (out["ray_rgb"].detach().cpu() - torch.from_numpy(G["occ20_ray_rgb"])).abs().max().item() < 1e-4
+    out["loss_occ"].mean().backward()
+    named = dict(net_.named_parameters())
+    keys = [k for k in G.files if k.startswith("occ20_grad/")]
+    assert len(keys) == 12 and all("color_network_inner.inner_weight" in k for k in keys)
+    for key in keys:
+        name = key[len("occ20_grad/"):]
+        ref_g, ref_norm = torch.from_numpy(G[key]), float(G["occ20_gradnorm/" + name])
+        g = named[name].grad.detach().reshape(-1).cpu()
+        idx = torch.linspace(0, g.numel() - 1, min(g.numel(), 64)).long()
+        scale = max(ref_g.abs().max().item(), ref_norm / max(g.numel(), 1) ** 0.5)
+        assert (g[idx] - ref_g).abs().max().item() / scale < 1e-2, name
+        assert abs(named[name].grad.double().norm().item() - ref_norm) / ref_norm < 1e-2, name
+    # before occ_loss_step / disabled: zeros(1)
+    with torch.no_grad():
+        out0 = net_.render_core(o, d, pathes, converges, directions, bkgr, nmesh, iors, None, cos_anneal_ratio=0.2,
+                                step=10000, is_train=True, is_nerf=True)
+    assert out0["loss_occ"].shape == (1,) and out0["loss_occ"].item() == 0.0
