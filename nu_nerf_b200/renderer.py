@@ -551,7 +551,9 @@ class Stage2Renderer(_ZTStage2Renderer):
             raise NotImplementedError("dataset ingest is outside the hot path: attach a ray source and call render()")
         batch = self.ray_source(step, self.cfg["train_ray_num"])
         rays_d = F.normalize(batch["rays_d"], dim=-1)
-        mask = batch["masks"].reshape(-1, 1).float() if "masks" in batch else torch.ones_like(rays_d[:, :1])
+        # the reference's ray tables call it 'mask' (real data, NZ:1073-1081) or 'masks' (synthetic data, NZ:56)
+        m = batch.get("mask", batch.get("masks"))
+        mask = m.reshape(-1, 1).float() if m is not None else torch.ones_like(rays_d[:, :1])
         out = self.render(batch["rays_o"], rays_d, mask, None, None, None, -1, self.get_anneal_val(step), is_train=True,
                           step=step, is_nerf=self.is_nerf)
         tm = out["tir_mask"].detach() * mask
