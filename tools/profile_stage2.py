@@ -1,4 +1,5 @@
-"""torch.profiler kernel table of one stage-2 training step (config 4 mesh, 4096 rays)."""
+"""torch.profiler kernel table of one stage-2 training step (config 4 mesh, 4096 rays).  `--thick`: the non-zero-thickness
+renderer of network/renderer.py (nu_nerf_b200/renderer.py)."""
 import os
 import sys
 
@@ -10,7 +11,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import make_stage2, uv_sphere
 R = 4096
 V, Fc = uv_sphere(0.6, 224, 224)
-net = make_stage2("bf16", mesh=(V, Fc)).cuda()
+THICK = "--thick" in sys.argv
+net = make_stage2("bf16", mesh=(V, Fc), thick=THICK).cuda()
 g = torch.Generator().manual_seed(1)
 o = 3.0 * torch.nn.functional.normalize(torch.randn(R, 3, generator=g), dim=-1)
 d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(R, 3, generator=g), dim=-1)
@@ -18,7 +20,8 @@ o, d = o.cuda(), d.cuda()
 gt = torch.rand(R, 3, generator=g).cuda()
 def step():
     net.zero_grad(set_to_none=True)
-    out = net.render(o, d, None, None, None, -1, 0.2, is_train=True, step=10000, is_nerf=True)
+    args = (o, d, None, None, None, None) if THICK else (o, d, None, None, None)      # NZ:1482 carries a mask argument
+    out = net.render(*args, -1, 0.2, is_train=True, step=10000, is_nerf=True)
     tm = out["tir_mask"].detach()
     loss = net.compute_rgb_loss(out["ray_rgb"] * tm, gt * tm).mean() + (0.02 * out["gradient_error"]).mean()
     loss.backward()
