@@ -31,3 +31,14 @@ extern "C" void shell_bwd(const float* in, int M, int inside, const float* g, fl
     q[9] = d.gk; q[10] = d.ior_sig; q[11] = d.th_sig;
   }
 }
+
+// pw::sphere_dir_fwd / _bwd (the `sphere_direction` shader variant, field.py:447-465, :641-644) on arrays
+extern "C" void sphere_dir(const float* p, const float* u, int M, float* q) {
+  for (int m = 0; m < M; ++m) pw::sphere_dir_fwd(p + 3 * m, u + 3 * m, q + 3 * m);
+}
+extern "C" void sphere_dir_bwd(const float* p, const float* u, const float* dq, int M, float* du, float* dp) {
+  for (int m = 0; m < M; ++m) {
+    for (int c = 0; c < 3; ++c) { du[3 * m + c] = 0.f; dp[3 * m + c] = 0.f; }
+    pw::sphere_dir_bwd(p + 3 * m, u + 3 * m, dq + 3 * m, du + 3 * m, dp + 3 * m);
+  }
+}

@@ -134,3 +134,43 @@ def test_kernel_source_matches_torch_restatement_and_its_autograd(host_lib, name
             assert float(np.abs(din[:, lo:hi] - ref[:, lo:hi]).max()) / scale <= (2e-4 if lo == 9 else 2e-5), (k, lo)
         checked += 1
     assert checked >= 2
+
+
+def test_sphere_direction_kernel_source_matches_reference_functions(host_lib):
+    """pw::sphere_dir_fwd / _bwd (the exit point of the ray (p, u) on the unit sphere, encoded a second time by the
+    `sphere_direction` shaders) against the reference's own offset_points_to_sphere + get_sphere_intersection + F.normalize
+    (field.py:447-465, :641-644), restated in torch, and against their autograd -- points inside AND outside radius 0.999."""
+    import ctypes
+    import torch.nn.functional as F
+    fp = ctypes.POINTER(ctypes.c_float)
+    ptr = lambda a: a.ctypes.data_as(fp)
+    gen = torch.Generator().manual_seed(4)
+    M = 400
+    p = torch.randn(M, 3, generator=gen) * torch.where(torch.arange(M) % 2 == 0, 0.5, 1.2)[:, None]
+    u = F.normalize(torch.randn(M, 3, generator=gen), dim=-1)
+    p.requires_grad_(True)
+    u.requires_grad_(True)
+
+    def reference(points, dirs):                       # field.py:447-465 as written
+        norm = torch.norm(points, dim=-1)
+        mask = norm > 0.999
+        pts = torch.clone(points)
+        pts[mask] = pts[mask] / norm[mask].unsqueeze(-1) * 0.999
+        dtx = torch.sum(pts * dirs, dim=-1, keepdim=True)
+        xtx = torch.sum(pts ** 2, dim=-1, keepdim=True)
+        dist = -dtx + torch.sqrt(dtx ** 2 - xtx + 1 + 1e-6)
+        return F.normalize(pts + dirs * dist, dim=-1)
+    q_ref = reference(p, u)
+    assert (p.detach().norm(dim=-1) > 0.999).any() and (p.detach().norm(dim=-1) < 0.999).any()
+    pn, un = (np.ascontiguousarray(t.detach().numpy(), dtype=np.float32) for t in (p, u))
+    q = np.zeros((M, 3), np.float32)
+    host_lib.sphere_dir(ptr(pn), ptr(un), M, ptr(q))
+    assert np.abs(q - q_ref.detach().numpy()).max() <= 5e-6      # points just outside the sphere: sqrt of a cancelling sum
+    from nu_nerf_b200.engine import sphere_exit_dir   # the [R,3] torch glue of the per-ray specular probe
+    assert (sphere_exit_dir(p.detach(), u.detach()) - q_ref.detach()).abs().max().item() <= 5e-6
+    cot = torch.randn(M, 3, generator=gen)
+    (q_ref * cot).sum().backward()
+    du, dp = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32)
+    host_lib.sphere_dir_bwd(ptr(pn), ptr(un), ptr(np.ascontiguousarray(cot.numpy())), M, ptr(du), ptr(dp))
+    for got, ref in ((du, u.grad.numpy()), (dp, p.grad.numpy())):
+        assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)
