@@ -116,9 +116,11 @@ def init_sdf_reg(out, step, reg_step=1000, small_threshold=0.1, large_threshold=
 
 
 def stage1_loss(out, loss_rgb, r_global, group=None, eikonal_weight=0.1, step=0, occ_loss_step=None,
-                outer_reg_weight=0.5, share=1.0, n_in_global=None, outer_reg_step=15000, sdf_reg=True):
+                outer_reg_weight=0.5, share=1.0, n_in_global=None, outer_reg_step=15000, sdf_reg=True,
+                normal_ori=False, mask_weight=0.01):
     """Trainer loss (trainer_zero.py:157-161 over the loss.py adapters of spherepot.yaml: nerf_render, eikonal, std,
-    init_sdf_reg, occ, mask, outer_reg) with global denominators.
+    init_sdf_reg, occ, mask, outer_reg; normal_ori=True adds the normal-orientation term of the non-zero-thickness stage-1
+    configs) with global denominators.
     `out` is the renderer's outputs dict of THIS rank (or of one chunk of its rays: `share` = the chunk's fraction of
     the rank's rays), `loss_rgb` [R_chunk]; returns the local share whose SUM over ranks (and chunks) is the global
     loss, so gradients are summed, not averaged, across ranks."""
@@ -141,7 +143,20 @@ def stage1_loss(out, loss_rgb, r_global, group=None, eikonal_weight=0.1, step=0,
         loss = loss + share * out["loss_occ"].mean() / world
     if step >= outer_reg_step and "color_bkgr" in out:
         # OuterRegLoss has its own hard-coded gate (loss.py:206: step >= 15000), independent of occ_loss_step
-        loss = loss + outer_reg_weight * ((out["color_bkgr"] - out["color_spec"]) ** 2).sum() / (3.0 * r_global)
+        sq = ((out["color_bkgr"] - out["color_spec"]) ** 2).sum()
+        if "loss_normal" in out:
+            # the stage-1 renderer of network/renderer.py reports both colours for the candidate rays only (NZ:798-821):
+            # the mean runs over the candidates of all ranks (of this chunk: chunks are share-weighted)
+            n_c = global_count(out["color_bkgr"].shape[0], dev, group)
+            loss = loss + outer_reg_weight * share * sq / (3.0 * torch.clamp(n_c, min=1.0))
+        else:
+            loss = loss + outer_reg_weight * sq / (3.0 * r_global)
+    if normal_ori and "loss_normal" in out:
+        # NormalOrientationLoss (loss.py:101-112, configs/shape/real/ballstatue.yaml:17): mean over the rays
+        loss = loss + out["loss_normal"].sum() / r_global
+    if mask_weight and "loss_mask" in out:
+        # MaskLoss (loss.py:152-164): the renderer's l1(masks, acc) is a mean over one rank's (chunk's) rays
+        loss = loss + mask_weight * share * out["loss_mask"].reshape(()) / world
     if sdf_reg:
         # InitSDFRegLoss (first 1000 steps): its count-based denominators are per batch; ranks / chunks are averaged
         reg = init_sdf_reg(out, step)

@@ -69,3 +69,24 @@ def test_init_sdf_reg_edge_cases(ref_loss):
             got = init_sdf_reg({"sdf_pts": pts, "sdf_vals": sdf}, step)
             assert abs(float(got) - float(want)) < 1e-6 * max(1.0, abs(float(want))), (case, step)
     assert init_sdf_reg({"sdf_pts": pts, "sdf_vals": sdf}, 1000) is None and init_sdf_reg({}, 0) is None
+
+
+@pytest.mark.parametrize("step", [400, 14999, 15000])
+def test_trainer_loss_with_the_nonzero_thickness_outputs(ref_loss, step):
+    """Outputs dict of the stage-1 renderer of network/renderer.py (loss_normal [R,1], loss_mask (), colours on the
+    candidate rays only) through the loss list of configs/shape/real/ballstatue.yaml:17 + 'mask'."""
+    from nu_nerf_b200 import dist as nd
+    out = _outputs(step)
+    g = torch.Generator().manual_seed(77)
+    out["loss_normal"], out["loss_mask"] = torch.rand(64, 1, generator=g), torch.rand((), generator=g)
+    out["color_bkgr"], out["color_spec"] = out["color_bkgr"][:41], out["color_spec"][:41]          # 41 of 64 candidates
+    if step < 15000:
+        out["loss_occ"] = torch.zeros(1)
+    names = ["nerf_render", "eikonal", "std", "init_sdf_reg", "occ", "outer_reg", "normal_ori", "mask"]
+    log = {}
+    for n in names:
+        log.update(ref_loss.name2loss[n]({})(out, None, step))
+    want = sum(torch.mean(v) for k, v in log.items() if k.startswith("loss"))
+    got = nd.stage1_loss(out, out["loss_rgb"], 64, eikonal_weight=0.1, step=step, occ_loss_step=15000, normal_ori=True)
+    assert "loss_normal" in log and "loss_mask" in log
+    assert abs(float(got) - float(want)) < 1e-6 * max(1.0, abs(float(want))), (step, float(got), float(want))
