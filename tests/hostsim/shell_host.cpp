@@ -42,3 +42,44 @@ extern "C" void sphere_dir_bwd(const float* p, const float* u, const float* dq, 
     pw::sphere_dir_bwd(p + 3 * m, u + 3 * m, dq + 3 * m, du + 3 * m, dp + 3 * m);
   }
 }
+
+// pw::shade_mix_fwd / _bwd (AppShadingNetwork.forward mixing, field.py:684-741; exp_max_r = the refraction-light clamp of
+// AppShadingNetwork_SpecInner, field.py:1373) on one point: in / d_in are the 26 floats of ShadeMixIn in declaration order
+static void mix_in(const float* v, pw::ShadeMixIn* a) {
+  int i = 0;
+  a->metallic = v[i++]; a->rough = v[i++];
+  for (int c = 0; c < 3; ++c) a->albedo[c] = v[i++];
+  a->trans = v[i++];
+  for (int c = 0; c < 3; ++c) a->diffuse_l[c] = v[i++];
+  for (int c = 0; c < 3; ++c) a->direct[c] = v[i++];
+  for (int c = 0; c < 3; ++c) a->direct0[c] = v[i++];
+  for (int c = 0; c < 3; ++c) a->indirect[c] = v[i++];
+  for (int c = 0; c < 3; ++c) a->indirect0[c] = v[i++];
+  a->occ = v[i++];
+  for (int c = 0; c < 3; ++c) a->refrac[c] = v[i++];
+  a->nov = v[i++];
+}
+extern "C" void mix_fwd(const float* in, const float* lut, float exp_max, float exp_max_r, float* out) {   // out: rgb, T, met, occ
+  pw::ShadeMixIn a;
+  mix_in(in, &a);
+  pw::ShadeMixOut o = pw::shade_mix_fwd(a, lut, exp_max, exp_max_r);
+  out[0] = o.color[0]; out[1] = o.color[1]; out[2] = o.color[2]; out[3] = o.trans; out[4] = o.metallic; out[5] = o.occ_prob;
+}
+extern "C" void mix_bwd(const float* in, const float* lut, float exp_max, float exp_max_r, const float* d_color,
+                        float d_trans, float d_met, float* d_in) {
+  pw::ShadeMixIn a, d;
+  mix_in(in, &a);
+  pw::shade_mix_bwd(a, lut, exp_max, exp_max_r, d_color, d_trans, d_met, &d);
+  int i = 0;
+  d_in[i++] = d.metallic; d_in[i++] = d.rough;
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.albedo[c];
+  d_in[i++] = d.trans;
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.diffuse_l[c];
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.direct[c];
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.direct0[c];
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.indirect[c];
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.indirect0[c];
+  d_in[i++] = d.occ;
+  for (int c = 0; c < 3; ++c) d_in[i++] = d.refrac[c];
+  d_in[i++] = d.nov;
+}

@@ -174,3 +174,47 @@ def test_sphere_direction_kernel_source_matches_reference_functions(host_lib):
     host_lib.sphere_dir_bwd(ptr(pn), ptr(un), ptr(np.ascontiguousarray(cot.numpy())), M, ptr(du), ptr(dp))
     for got, ref in ((du, u.grad.numpy()), (dp, p.grad.numpy())):
         assert np.abs(got - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0)
+
+
+def test_shading_mix_kernel_source_with_the_specinner_refraction_clamp(host_lib):
+    """pw::shade_mix_fwd / _bwd with a refraction-light clamp different from light_exp_max (AppShadingNetwork_SpecInner:
+    exp(min(x, -0.2)), field.py:1373): the refraction term saturates at exp(-0.2) while the other lights keep exp_max = 5,
+    and the hand-derived backward agrees with central differences of the forward (smooth region: no clamp / LUT-cell edges)."""
+    import ctypes
+    fp = ctypes.POINTER(ctypes.c_float)
+    ptr = lambda a: a.ctypes.data_as(fp)
+    lut = np.load(os.path.join(G, "fg_lut_reference.npz"))["FG_LUT"].astype(np.float32).reshape(-1)
+    rng = np.random.default_rng(5)
+    f = ctypes.c_float
+
+    def fwd(v, er):
+        out = np.zeros(6, np.float32)
+        host_lib.mix_fwd(ptr(np.ascontiguousarray(v, dtype=np.float32)), ptr(lut), f(5.0), f(er), ptr(out))
+        return out
+    checked = 0
+    for trial in range(40):
+        v = rng.normal(0.0, 0.6, 26).astype(np.float32)
+        v[25] = rng.uniform(0.15, 0.85)                         # NoV inside (0, 1)
+        v[22:25] = rng.uniform(-1.5, -0.4, 3) if trial % 2 == 0 else rng.uniform(0.2, 1.5, 3)    # below / above the clamp
+        # saturation: raising a clamped refraction head does not change the colour, with the shared clamp (5.0) it does
+        hi = v.copy()
+        hi[22:25] += 0.5
+        if trial % 2 == 1:
+            assert np.array_equal(fwd(v, -0.2), fwd(hi, -0.2)) and not np.array_equal(fwd(v, 5.0), fwd(hi, 5.0))
+        cot = rng.normal(size=3).astype(np.float32)
+        d_in = np.zeros(26, np.float32)
+        host_lib.mix_bwd(ptr(v), ptr(lut), f(5.0), f(-0.2), ptr(cot), f(0.3), f(-0.2), ptr(d_in))
+        if trial % 2 == 1:
+            assert np.all(d_in[22:25] == 0.0)                    # clamped heads receive no gradient
+        h = 2e-3
+        for j in range(26):
+            if j == 1 or j == 25:
+                continue                                         # roughness / NoV move the bilinear LUT taps: piecewise
+            a, b = v.copy(), v.copy()
+            a[j] += h
+            b[j] -= h
+            oa, ob = fwd(a, -0.2).astype(np.float64), fwd(b, -0.2).astype(np.float64)
+            fd = (np.dot(cot, oa[:3] - ob[:3]) + 0.3 * (oa[3] - ob[3]) - 0.2 * (oa[4] - ob[4])) / (2 * h)
+            assert abs(fd - d_in[j]) <= 2e-3 * (1.0 + abs(fd)), (trial, j, fd, d_in[j])
+            checked += 1
+    assert checked > 850
