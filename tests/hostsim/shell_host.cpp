@@ -83,3 +83,20 @@ extern "C" void mix_bwd(const float* in, const float* lut, float exp_max, float 
   for (int c = 0; c < 3; ++c) d_in[i++] = d.refrac[c];
   d_in[i++] = d.nov;
 }
+
+// pw::ide_fwd / ide_bwd (integrated directional encoding, utils/ref_utils.py:85-114) with the table build_ide_table() makes
+// for the device's constant memory
+extern "C" void ide_host(const float* xyz, const float* kinv, int M, float* out) {
+  static pw::IdeTable tb;
+  static bool init = false;
+  if (!init) { pw::build_ide_table(&tb); init = true; }
+  for (int m = 0; m < M; ++m) pw::ide_fwd(tb, xyz[3 * m], xyz[3 * m + 1], xyz[3 * m + 2], kinv[m], out + 72 * m);
+}
+extern "C" void ide_bwd_host(const float* xyz, const float* kinv, const float* dout, int M, float* dxyz, float* dk) {
+  static pw::IdeTable tb;
+  static bool init = false;
+  if (!init) { pw::build_ide_table(&tb); init = true; }
+  for (int m = 0; m < M; ++m)
+    pw::ide_bwd(tb, xyz[3 * m], xyz[3 * m + 1], xyz[3 * m + 2], kinv[m], dout + 72 * m, dxyz + 3 * m, dxyz + 3 * m + 1,
+                dxyz + 3 * m + 2, dk + m);
+}
