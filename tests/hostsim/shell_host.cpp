@@ -100,3 +100,20 @@ extern "C" void ide_bwd_host(const float* xyz, const float* kinv, const float* d
     pw::ide_bwd(tb, xyz[3 * m], xyz[3 * m + 1], xyz[3 * m + 2], kinv[m], dout + 72 * m, dxyz + 3 * m, dxyz + 3 * m + 1,
                 dxyz + 3 * m + 2, dk + m);
 }
+
+// pw::sdf_alpha_fwd / _bwd (compute_sdf_alpha ZT:657-685 + the eikonal term ZT:769) on arrays: in [M,9] = sdf, g[3], dist,
+// dir[3], (unused); out [M,2] = alpha, gerr; bwd: cot [M,2] -> d [M,9] = d_sdf, d_g[3], d_dist, d_dir[3], d_inv_s
+extern "C" void sdf_alpha_host(const float* in, int M, float inv_s, float anneal, float* out) {
+  for (int m = 0; m < M; ++m) {
+    const float* p = in + 9 * m;
+    pw::SdfAlphaOut o = pw::sdf_alpha_fwd(p[0], p + 1, p[4], p + 5, inv_s, anneal);
+    out[2 * m] = o.alpha; out[2 * m + 1] = o.gerr;
+  }
+}
+extern "C" void sdf_alpha_bwd_host(const float* in, int M, float inv_s, float anneal, const float* cot, float* d) {
+  for (int m = 0; m < M; ++m) {
+    const float* p = in + 9 * m;
+    float* q = d + 9 * m;
+    pw::sdf_alpha_bwd(p[0], p + 1, p[4], p + 5, inv_s, anneal, cot[2 * m], cot[2 * m + 1], q, q + 1, q + 8, q + 4, q + 5);
+  }
+}

@@ -261,3 +261,46 @@ def test_ide_kernel_source_matches_the_oracle_and_its_autograd(host_lib):
     host_lib.ide_bwd_host(ptr(xn), ptr(kn), ptr(np.ascontiguousarray(cot.numpy())), M, ptr(dx), ptr(dk))
     for got, want in ((dx, x64.grad.numpy()), (dk, k64.grad.numpy().reshape(-1))):
         assert np.abs(got - want).max() <= 2e-4 * max(1.0, float(np.abs(want).max())), np.abs(got - want).max()
+
+
+@pytest.mark.parametrize("inv_s,anneal", [(20.0, 0.2), (300.0, 1.0), (64.0, 0.0)])
+def test_sdf_alpha_kernel_source_matches_the_reference_expression(host_lib, inv_s, anneal):
+    """pw::sdf_alpha_fwd / _bwd (sdf_alpha_fwd/bwd_kernel) against compute_sdf_alpha as the reference writes it
+    (renderer_zerothick.py:669-684) + the eikonal term (:769) and their torch autograd, at the init-like and a trained-like
+    sharpness: alpha / eikonal within 2e-6, every gradient (sdf, SDF gradient, interval length, ray direction, inv_s) within
+    1e-4 of the largest entry, fp64 on the torch side."""
+    import ctypes
+    import torch.nn.functional as F
+    fp = ctypes.POINTER(ctypes.c_float)
+    ptr = lambda a: a.ctypes.data_as(fp)
+    f = ctypes.c_float
+    gen = torch.Generator().manual_seed(int(inv_s))
+    M = 2000
+    sdf = (torch.randn(M, generator=gen) * (3.0 / inv_s)).double().requires_grad_(True)
+    g = (F.normalize(torch.randn(M, 3, generator=gen), dim=-1) * (0.7 + 0.6 * torch.rand(M, 1, generator=gen))).double().requires_grad_(True)
+    dist = (0.002 + 0.03 * torch.rand(M, generator=gen)).double().requires_grad_(True)
+    dirs = F.normalize(torch.randn(M, 3, generator=gen), dim=-1).double().requires_grad_(True)
+    s = torch.tensor(float(inv_s), dtype=torch.float64, requires_grad=True)
+    true_cos = (dirs * g).sum(-1)
+    iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - anneal) + F.relu(-true_cos) * anneal)
+    en, ep = sdf + iter_cos * dist * 0.5, sdf - iter_cos * dist * 0.5
+    pc, nc = torch.sigmoid(ep * s), torch.sigmoid(en * s)
+    alpha = ((pc - nc + 1e-5) / (pc + 1e-5)).clip(0.0, 1.0)
+    gerr = (torch.linalg.norm(g, ord=2, dim=-1) - 1.0) ** 2
+    inp = torch.cat([sdf[:, None], g, dist[:, None], dirs, torch.zeros(M, 1)], 1).detach().float().contiguous().numpy()
+    out = np.zeros((M, 2), np.float32)
+    host_lib.sdf_alpha_host(ptr(inp), M, f(inv_s), f(anneal), ptr(out))
+    assert np.abs(out[:, 0] - alpha.detach().numpy()).max() <= 2e-6 * max(1.0, inv_s / 50.0)
+    assert np.abs(out[:, 1] - gerr.detach().numpy()).max() <= 2e-6
+    cot = torch.randn(M, 2, generator=gen)
+    ((alpha * cot[:, 0].double()).sum() + (gerr * cot[:, 1].double()).sum()).backward()
+    d = np.zeros((M, 9), np.float32)
+    host_lib.sdf_alpha_bwd_host(ptr(inp), M, f(inv_s), f(anneal), ptr(np.ascontiguousarray(cot.numpy())), ptr(d))
+    interior = ((alpha.detach() > 1e-6) & (alpha.detach() < 1 - 1e-6)).numpy()          # away from the clip edges
+    for got, want in ((d[:, 0], sdf.grad.numpy()), (d[:, 1:4], g.grad.numpy()), (d[:, 4], dist.grad.numpy()),
+                      (d[:, 5:8], dirs.grad.numpy())):
+        scale = max(1.0, float(np.abs(want).max()))
+        assert np.abs(got[interior] - want[interior]).max() <= 1e-4 * scale, (np.abs(got[interior] - want[interior]).max(), scale)
+    want_s = s.grad.item()
+    got_s = float(d[interior, 8].astype(np.float64).sum()) + float(d[~interior, 8].astype(np.float64).sum())
+    assert abs(got_s - want_s) <= 2e-4 * max(1.0, abs(want_s)), (got_s, want_s)
