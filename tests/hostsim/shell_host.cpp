@@ -1,5 +1,5 @@
 // TEST INFRASTRUCTURE ONLY -- host build of pw::shell_bounce_fwd / _bwd (nu_nerf_b200/csrc/pointwise.cuh, the source the CUDA
-// kernels of csrc/shell.cu compile) behind a C ABI for ctypes: tests/test_shell_cpu.py checks it against the torch
+// kernels of csrc/shell.cu compile) behind a C ABI for ctypes: tests/test_kernel_source_cpu.py checks it against the torch
 // restatement nu_nerf_b200/shell.py (pinned to the unmodified reference) and against its autograd.
 #include <cmath>
 #include <cstdint>
@@ -115,5 +115,34 @@ extern "C" void sdf_alpha_bwd_host(const float* in, int M, float inv_s, float an
     const float* p = in + 9 * m;
     float* q = d + 9 * m;
     pw::sdf_alpha_bwd(p[0], p + 1, p[4], p + 5, inv_s, anneal, cot[2 * m], cot[2 * m + 1], q, q + 1, q + 8, q + 4, q + 5);
+  }
+}
+
+// pw::nerf_out_fwd / _bwd (compute_density_alpha ZT:687-693, density_activation ZT:515-516, linear_to_srgb) and
+// pw::shade_dirs / shade_dirs_bwd (normal, view, reflected direction, NoV: field.py:686-689) on arrays
+extern "C" void nerf_out_host(const float* in, int M, float* out) {          // in [M,5] = sigma, rgb[3], dist; out [M,4]
+  for (int m = 0; m < M; ++m) pw::nerf_out_fwd(in[5 * m], in + 5 * m + 1, in[5 * m + 4], out + 4 * m, out + 4 * m + 1);
+}
+extern "C" void nerf_out_bwd_host(const float* in, int M, const float* cot, float* d) {     // cot [M,4] -> d [M,5]
+  for (int m = 0; m < M; ++m)
+    pw::nerf_out_bwd(in[5 * m], in + 5 * m + 1, in[5 * m + 4], cot[4 * m], cot + 4 * m + 1, d + 5 * m, d + 5 * m + 1,
+                     d + 5 * m + 4);
+}
+extern "C" void shade_dirs_host(const float* g, const float* raydir, int M, float* out) {   // out [M,10] = n, v, r, nov
+  for (int m = 0; m < M; ++m) {
+    pw::ShadeDirs s = pw::shade_dirs(g + 3 * m, raydir + 3 * m);
+    float* q = out + 10 * m;
+    for (int c = 0; c < 3; ++c) { q[c] = s.n[c]; q[3 + c] = s.v[c]; q[6 + c] = s.r[c]; }
+    q[9] = s.nov;
+  }
+}
+// cot [M,10] = d_n (direct), d_v (direct), d_r, d_nov -> d_g [M,3], d_raydir [M,3]
+extern "C" void shade_dirs_bwd_host(const float* g, const float* raydir, const float* cot, int M, float* d_g, float* d_rd) {
+  for (int m = 0; m < M; ++m) {
+    pw::ShadeDirs s = pw::shade_dirs(g + 3 * m, raydir + 3 * m);
+    const float* c = cot + 10 * m;
+    const float* rd = raydir + 3 * m;
+    float vn = fmaxf(sqrtf(rd[0] * rd[0] + rd[1] * rd[1] + rd[2] * rd[2]), 1e-12f);
+    pw::shade_dirs_bwd(s, c + 6, c, c[9], d_g + 3 * m, c + 3, vn, d_rd + 3 * m);
   }
 }

@@ -1,7 +1,12 @@
-"""Non-zero-thickness bounce geometry (nu_nerf_b200/shell.shell_bounce) against the UNMODIFIED reference's
-ray_trace (network/renderer.py:1610-2148), bounce by bounce, on the inputs the reference itself saw (hit point, interpolated
-normal and Gaussian curvature, IoR / thickness network outputs): tests/golden/stage2nz_*.npz, made by make_golden_nz.py.
-fp32 on both sides with the reference's operation order: the gate is 2e-6 (a few ulp of O(1) quantities)."""
+"""Kernel SOURCE on the CPU (`-m "not gpu"`): the per-point / per-ray math of the CUDA kernels lives in
+nu_nerf_b200/csrc/pointwise.cuh as __host__ __device__ functions; tests/hostsim/shell_host.cpp builds it for the host (g++)
+and this file checks it -- values and the hand-derived adjoints -- against (1) the torch restatement of the
+non-zero-thickness bounce nu_nerf_b200/shell.py, which is itself pinned bounce by bounce to the UNMODIFIED reference's
+ray_trace (network/renderer.py:1610-2148) on the inputs the reference saw (tests/golden/stage2nz_*.npz, made by
+make_golden_nz.py), (2) the reference's own expressions restated in torch (sphere direction field.py:447-465, sdf -> alpha
+renderer_zerothick.py:669-684, NeRF++ activations :515-516 / :691-692, shading directions field.py:686-689) and their autograd
+in fp64, and (3) the oracle's integrated directional encoding.  The GPU suite then only has to show that the launched
+kernels compute what this source says."""
 import os
 
 import numpy as np
@@ -304,3 +309,51 @@ def test_sdf_alpha_kernel_source_matches_the_reference_expression(host_lib, inv_
     want_s = s.grad.item()
     got_s = float(d[interior, 8].astype(np.float64).sum()) + float(d[~interior, 8].astype(np.float64).sum())
     assert abs(got_s - want_s) <= 2e-4 * max(1.0, abs(want_s)), (got_s, want_s)
+
+
+def test_nerf_output_and_shading_direction_kernel_sources(host_lib):
+    """pw::nerf_out_fwd / _bwd against compute_density_alpha as the reference writes it (renderer_zerothick.py:515-516,
+    :691-692, utils/raw_utils.py:5-12) and pw::shade_dirs / shade_dirs_bwd against the direction block of
+    AppShadingNetwork.forward (field.py:686-689), values and autograd (fp64 on the torch side)."""
+    import ctypes
+    import torch.nn.functional as F
+    fp = ctypes.POINTER(ctypes.c_float)
+    ptr = lambda a: a.ctypes.data_as(fp)
+    gen = torch.Generator().manual_seed(8)
+    M = 1500
+    # ---- NeRF++ output activation
+    sigma = (torch.randn(M, generator=gen) * 4.0).double().requires_grad_(True)
+    rgb = (torch.randn(M, 3, generator=gen) * 2.0 - 1.0).double().requires_grad_(True)
+    dist = (0.01 + torch.rand(M, generator=gen)).double().requires_grad_(True)
+    alpha = 1.0 - torch.exp(-F.softplus(sigma) * dist)
+    lin = torch.exp(torch.clamp(rgb, max=5.0))
+    eps = torch.finfo(torch.float32).eps
+    col = torch.where(lin <= 0.0031308, 323 / 25 * lin, (211 * torch.clamp(lin, min=eps) ** (5 / 12) - 11) / 200)
+    inp = torch.cat([sigma[:, None], rgb, dist[:, None]], 1).detach().float().contiguous().numpy()
+    out = np.zeros((M, 4), np.float32)
+    host_lib.nerf_out_host(ptr(inp), M, ptr(out))
+    assert np.abs(out[:, 0] - alpha.detach().numpy()).max() <= 2e-6
+    assert np.abs(out[:, 1:] - col.detach().numpy()).max() <= 2e-5 * float(col.max())
+    cot = torch.randn(M, 4, generator=gen)
+    ((alpha * cot[:, 0].double()).sum() + (col * cot[:, 1:].double()).sum()).backward()
+    d = np.zeros((M, 5), np.float32)
+    host_lib.nerf_out_bwd_host(ptr(inp), M, ptr(np.ascontiguousarray(cot.numpy())), ptr(d))
+    for got, want in ((d[:, 0], sigma.grad.numpy()), (d[:, 1:4], rgb.grad.numpy()), (d[:, 4], dist.grad.numpy())):
+        assert np.abs(got - want).max() <= 1e-4 * max(1.0, float(np.abs(want).max()))
+    # ---- shading directions
+    g = (torch.randn(M, 3, generator=gen) * 1.3).double().requires_grad_(True)          # un-normalised SDF gradient
+    rd = (F.normalize(torch.randn(M, 3, generator=gen), dim=-1) * 1.0).double().requires_grad_(True)
+    n, v = F.normalize(g, dim=-1), F.normalize(-rd, dim=-1)
+    r = torch.sum(v * n, -1, keepdim=True) * n * 2 - v
+    nov = torch.sum(n * v, -1, keepdim=True)
+    out = np.zeros((M, 10), np.float32)
+    gn, rn = (np.ascontiguousarray(t.detach().float().numpy()) for t in (g, rd))
+    host_lib.shade_dirs_host(ptr(gn), ptr(rn), M, ptr(out))
+    ref = torch.cat([n, v, r, nov], 1).detach().numpy()
+    assert np.abs(out - ref).max() <= 2e-6
+    cot = torch.randn(M, 10, generator=gen)
+    (torch.cat([n, v, r, nov], 1) * cot.double()).sum().backward()
+    dg, drd = np.zeros((M, 3), np.float32), np.zeros((M, 3), np.float32)
+    host_lib.shade_dirs_bwd_host(ptr(gn), ptr(rn), ptr(np.ascontiguousarray(cot.numpy())), M, ptr(dg), ptr(drd))
+    for got, want in ((dg, g.grad.numpy()), (drd, rd.grad.numpy())):
+        assert np.abs(got - want).max() <= 1e-4 * max(1.0, float(np.abs(want).max())), np.abs(got - want).max()
