@@ -333,7 +333,7 @@ def test_nerf_output_and_shading_direction_kernel_sources(host_lib):
     out = np.zeros((M, 4), np.float32)
     host_lib.nerf_out_host(ptr(inp), M, ptr(out))
     assert np.abs(out[:, 0] - alpha.detach().numpy()).max() <= 2e-6
-    assert np.abs(out[:, 1:] - col.detach().numpy()).max() <= 2e-5 * float(col.max())
+    assert np.abs(out[:, 1:] - col.detach().numpy()).max() <= 2e-5 * float(col.detach().max())
     cot = torch.randn(M, 4, generator=gen)
     ((alpha * cot[:, 0].double()).sum() + (col * cot[:, 1:].double()).sum()).backward()
     d = np.zeros((M, 5), np.float32)
