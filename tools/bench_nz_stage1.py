@@ -55,7 +55,7 @@ def run(R=4096, sph=False):
         res[name] = {"ms_per_step": ms, "rays_per_s": R / ms * 1e3}
         if normal:
             res[name]["candidate_rays"] = int(out["color_spec"].shape[0])
-            res[name]["loss_normal_mean"] = float(out["loss_normal"].mean())
+            res[name]["loss_normal_mean"] = float(out["loss_normal"].detach().mean())
         del net
         torch.cuda.empty_cache()
     return res
