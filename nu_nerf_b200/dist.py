@@ -181,7 +181,8 @@ class DataParallelTrainer:
     """
 
     def __init__(self, module, render_fn, rgb_loss_fn, adam_fn=cuda_adam, lr_fn=warm_up_cos_lr, group=None,
-                 eikonal_weight=0.1, occ_loss_step=None, sample_fn=None, core_fn=None, count_fn=None, outer_reg_step=15000):
+                 eikonal_weight=0.1, occ_loss_step=None, sample_fn=None, core_fn=None, count_fn=None, outer_reg_step=15000,
+                 normal_ori=False, mask_weight=0.01):
         """sample_fn(rays_o, rays_d, near, far, step) -> z_vals; count_fn(rays_o, rays_d, z_vals) -> number of inner samples
         (a 0-d device tensor); core_fn(rays_o, rays_d, z_vals, step) -> outputs dict.  When the three are given and a step
         is split into several chunks, the step runs in two phases -- sample every chunk and count its inner samples
@@ -193,6 +194,9 @@ class DataParallelTrainer:
         self.sample_fn, self.core_fn, self.count_fn = sample_fn, core_fn, count_fn
         self.group = group
         self.eikonal_weight, self.occ_loss_step, self.outer_reg_step = eikonal_weight, occ_loss_step, outer_reg_step
+        # loss terms of the non-zero-thickness stage-1 configs (loss list of configs/shape/real/ballstatue.yaml:17): the
+        # normal-orientation term and, for renderers that emit `loss_mask`, the mask term (see stage1_loss)
+        self.normal_ori, self.mask_weight = normal_ori, mask_weight
         self.last = {}
 
     def step(self, rays_o, rays_d, rgbs, near, far, step, chunk=None):
@@ -222,7 +226,8 @@ class DataParallelTrainer:
             loss_rgb = self.rgb_loss_fn(out["ray_rgb"], rgbs[sl])
             share = (sl.stop - sl.start) / r_local
             loss = stage1_loss(out, loss_rgb, r_global, self.group, self.eikonal_weight, step, self.occ_loss_step,
-                               share=share, n_in_global=n_in_global, outer_reg_step=self.outer_reg_step)
+                               share=share, n_in_global=n_in_global, outer_reg_step=self.outer_reg_step,
+                               normal_ori=self.normal_ori, mask_weight=self.mask_weight)
             loss.backward()
             total = total + loss.detach()
             n_in_seen += int(out["gradient_error"].shape[0]) if "transmission" in out else 0
