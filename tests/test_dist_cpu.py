@@ -20,8 +20,9 @@ if ROOT not in sys.path:
 
 
 class TinyField(torch.nn.Module):
-    def __init__(self):
+    def __init__(self, nz=False):
         super().__init__()
+        self.nz = nz            # outputs of the stage-1 class of network/renderer.py: loss_normal, colours on candidate rays
         torch.manual_seed(7)
         self.a = torch.nn.Linear(6, 16)
         self.b = torch.nn.Linear(16, 4)
@@ -40,6 +41,10 @@ class TinyField(torch.nn.Module):
             out["transmission"] = g[:, None].detach()
         else:
             out["gradient_error"] = torch.zeros(1)
+        if self.nz:
+            out["loss_normal"] = torch.relu(y[:, 3:4])
+            cand = o[:, 1] > 0                                           # a property of the ray: a data-dependent subset
+            out["color_bkgr"], out["color_spec"] = rgb[cand], torch.sigmoid(0.5 * y[cand, :3])
         return out
 
 
@@ -62,26 +67,26 @@ def charb(pr, gt):
     return torch.sqrt(((gt - pr) ** 2).sum(-1) + 0.001)
 
 
-def run_steps(world, rank, R, steps=3):
+def run_steps(world, rank, R, steps=3, nz=False):
     from nu_nerf_b200 import dist as nd
-    net = TinyField()
-    tr = nd.DataParallelTrainer(net, net.render, charb, adam_fn=torch_adam, lr_fn=lambda s: 1e-2)
+    net = TinyField(nz)
+    tr = nd.DataParallelTrainer(net, net.render, charb, adam_fn=torch_adam, lr_fn=lambda s: 1e-2, normal_ori=nz)
     o, d, rgb, near, far = make_batch(R)
     idx = nd.shard_batch(torch.arange(R), rank, world)
     losses = []
     for s in range(steps):
-        loss = tr.step(o[idx], d[idx], rgb[idx], near[idx], far[idx], 10000 + s)
+        loss = tr.step(o[idx], d[idx], rgb[idx], near[idx], far[idx], (15000 if nz else 10000) + s)
         if world > 1:
             dist.all_reduce(loss)
         losses.append(loss.item())
     return tr.fp.flat.clone(), tr.fp.grad.clone(), losses
 
 
-def _worker(rank, world, port, R, q):
+def _worker(rank, world, port, R, q, nz=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        flat, grad, losses = run_steps(world, rank, R)
+        flat, grad, losses = run_steps(world, rank, R, nz=nz)
         q.put((rank, flat.numpy(), grad.numpy(), losses))
     finally:
         dist.destroy_process_group()
@@ -96,13 +101,17 @@ def _free_port():
 
 
 @pytest.mark.timeout(300)
-def test_two_gloo_ranks_equal_the_single_process_large_batch_step():
+@pytest.mark.parametrize("nz", [False, True])
+def test_two_gloo_ranks_equal_the_single_process_large_batch_step(nz):
+    """nz: with the outputs / loss list of the non-zero-thickness stage-1 configs at step >= 15000 -- the normal-orientation
+    mean over the global ray count and the outer-regularisation mean over the candidate rays of ALL ranks (a data-dependent
+    subset per rank: one scalar all-reduce of the counts)."""
     R, world = 64, 2
-    ref_flat, ref_grad, ref_losses = run_steps(1, 0, R)
+    ref_flat, ref_grad, ref_losses = run_steps(1, 0, R, nz=nz)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, R, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, R, q, nz)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=240) for _ in range(world)]
