@@ -453,14 +453,15 @@ class Stage2Renderer(_ZTStage2Renderer):
                 if k == 1:
                     raise RuntimeError("non-zero-thickness trace: a ray of segment 1 has no exit hit after the filter")
                 # rays that leave the scene: 64 inverse-depth samples along the direction (NZ:2140-2143)
-                m_idx = infinity_bkgr[k].flatten().nonzero().squeeze(1)
-                Z[m_idx] = outside_depths(dev)
-                delta = delta.index_copy(0, m_idx, dk.index_select(0, m_idx))
+                miss = infinity_bkgr[k]                                     # [n_seg, 1]: selected in place, no index list
+                Z = torch.where(miss, outside_depths(dev).unsqueeze(0), Z)
+                delta = torch.where(miss, dk, delta)
             if start.requires_grad or delta.requires_grad:
                 pts = start[:, None, :] + delta[:, None, :] * Z[:, :, None]
             else:
                 pts = eng.segment_points(start.contiguous(), delta.contiguous(), Z.contiguous())
             pathes.append(pts)
+        self._trace_cache = (list(converges), list(conv_idxs))          # see the zero-thickness ray_trace
         return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
 
     # ------------------------------------------------------------------ NZ:2155-2353

@@ -467,6 +467,9 @@ class Stage2Renderer(nn.Module):
             if rec is not None:
                 rec.setdefault("segments", []).append(dict(Z=Z, h_idx=h_idx, m_idx=m_idx, start=start, dir=dk))
             pathes.append(pts)
+        # render_core reuses the index lists of the rays that continue (no second nonzero / host sync per segment) when it
+        # is handed these very mask tensors (the cache holds them, so identity is a safe test)
+        self._trace_cache = (list(converges), list(conv_idxs))
         return pathes, converges, directions, ior_ratios, infinity_bkgr, gradient_mesh, tirs[0]
 
     # ------------------------------------------------------------------ gradient of IORs_pred
@@ -611,7 +614,11 @@ class Stage2Renderer(nn.Module):
         for i in range(len(pathes)):
             cand = keep(pathes[i])
             N, S = cand.shape[0], cand.shape[1] - 1
-            conv_idx = converges[i].flatten().nonzero().squeeze(1)        # one host sync per segment for this mask
+            cache = getattr(self, "_trace_cache", None)
+            if cache is not None and i < len(cache[0]) and converges[i] is cache[0][i]:
+                conv_idx = cache[1][i]                                    # from ray_trace: no host sync
+            else:
+                conv_idx = converges[i].flatten().nonzero().squeeze(1)    # foreign lists: one host sync per segment
             conv_idxs.append(conv_idx)
             dirs_i = keep(directions[i])
             if cand.requires_grad:
