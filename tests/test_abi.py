@@ -52,3 +52,24 @@ def test_chain_argument_validation_without_gpu():
     assert rc < 0 and b"mlp_chain" in _lib.lib.nunerf_last_error()
     a.ldx, a.K0, a.n_layers = 64, 64, 11                                              # too many layers
     assert _lib.lib.nunerf_mlp_chain(ctypes.byref(a), None) < 0
+
+
+def test_nonzero_thickness_entry_points_validate_without_gpu():
+    """The entry points added for network/renderer.py: same error convention, checked before any CUDA call -- null pointers /
+    empty launches of the shell bounce, null operands of the shading encode with the new frequency / sphere_direction
+    fields set."""
+    from nu_nerf_b200 import _lib
+    lib = _lib.lib
+    n = None
+    assert lib.nunerf_shell_bounce(n, n, n, n, n, n, 4, 0, n, n, n, n, n, n, n) < 0
+    assert b"shell_bounce" in lib.nunerf_last_error()
+    buf = (ctypes.c_char * 4096)()
+    a = ctypes.addressof(buf)
+    assert lib.nunerf_shell_bounce(a, a, a, a, a, a, 0, 0, a, a, a, a, a, a, n) < 0                     # M = 0
+    assert lib.nunerf_shell_bounce_bwd(a, a, a, a, a, a, n, 4, 1, a, a, a, a, a, a, a, a, a, a, n) < 0    # no pass mask
+    assert b"shell_bounce_bwd" in lib.nunerf_last_error()
+    se = _lib.ShadeEncodeT()                     # (the frequency / row-width checks sit behind the constant-table upload)
+    se.M, se.pos_freq, se.refrac_freq, se.sphere_direction = 8, 8, 2, 1
+    rc = lib.nunerf_shade_encode_fwd(ctypes.byref(se), None)
+    assert rc < 0 and b"shade_encode_fwd" in lib.nunerf_last_error()
+    assert ctypes.sizeof(_lib.ShadeEncodeT) % 8 == 0 and ctypes.sizeof(_lib.ShadeMixT) % 8 == 0
