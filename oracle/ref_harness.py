@@ -17,6 +17,9 @@ imports it.  The shims below are the deviations listed in SURVEY.md section 8(c)
      Parity unpinned: nvdiffrast is not vendored in the reference (field.py:721).
   5. optix_mesh.intersect -> brute force closest hit (oracle definition, see tracing section).
   6. torch.rand / torch.randperm injection so both sides consume identical uniform draws.
+  7. (non-zero-thickness module, network/renderer.py: load_stage1 / load_stage2 with thick=True) the vertex Gaussian
+     curvature DiffRender.Scene reads from PyMesh (DiffRender.py:331, :360) is angle_defect_curvature() below -- a stated
+     definition (angle defect / barycentric vertex area, clipped to [-10, 10]); parity against PyMesh itself unpinned.
 """
 import contextlib
 import math
